@@ -1,0 +1,1230 @@
+/* rrrmc_oracle.c — CPU restatement of RRRMC.jl's single-spin-flip hot path (plain C11).
+ *
+ * TEST INFRASTRUCTURE ONLY (see rrrmc_oracle.h).  PARITY UNPINNED by reference golden
+ * vectors (none exist; Julia is not runnable here) — pinned by reference invariants instead.
+ *
+ * Each block cites the reference file:line it restates.  Site indices are 1-based at this
+ * API (like the reference); spin s_i is bit (i-1)&63 of chunk (i-1)>>6 (src/Common.jl:15-22,
+ * src/Interface.jl:21-29), σ = 2s-1.
+ */
+#include "rrrmc_oracle.h"
+#include <math.h>
+#include <float.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+/* ------------------------------------------------------------------------------------------
+ * Config bits  (src/Interface.jl:21-43, src/Common.jl:15-22)
+ * ---------------------------------------------------------------------------------------- */
+static inline int cfg_get(const uint64_t *c, int64_t i) { return (int)((c[(i - 1) >> 6] >> ((i - 1) & 63)) & 1u); }
+static inline void cfg_flip(uint64_t *c, int64_t i) { c[(i - 1) >> 6] ^= (uint64_t)1 << ((i - 1) & 63); }
+
+/* ------------------------------------------------------------------------------------------
+ * Philox4x32-10 (Salmon et al., SC'11; Random123 constants).  Shared *definition* with the
+ * CUDA engine (which carries its own implementation); pinned by Random123's published KATs
+ * in tests/test_oracle_philox.py.
+ * ---------------------------------------------------------------------------------------- */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+static void philox_src_next(orc_philox_src *s, uint32_t out[4])
+{
+    uint32_t ctr[4] = { (uint32_t)s->n, (uint32_t)(s->n >> 32), (uint32_t)s->chain, s->tag ^ (uint32_t)(s->chain >> 32) };
+    uint32_t key[2] = { (uint32_t)s->seed, (uint32_t)(s->seed >> 32) };
+    orc_philox4x32_10(ctr, key, out);
+    s->n++;
+}
+uint64_t orc_philox_u64(orc_philox_src *s)
+{
+    uint32_t o[4]; philox_src_next(s, o);
+    return ((uint64_t)o[1] << 32) | o[0];
+}
+/* uniform in [0,1) with 53 bits: same construction on the GPU side */
+double orc_philox_f64(void *src)
+{
+    uint64_t x = orc_philox_u64((orc_philox_src *)src);
+    return (double)(x >> 11) * 0x1.0p-53;
+}
+/* unbiased 1..n by multiply-shift with rejection (Lemire 2019); one Philox call per trial */
+int64_t orc_philox_range(void *src, int64_t n)
+{
+    orc_philox_src *s = (orc_philox_src *)src;
+    uint64_t un = (uint64_t)n;
+    for (;;) {
+        uint64_t x = orc_philox_u64(s);
+        __uint128_t m = (__uint128_t)x * un;
+        uint64_t lo = (uint64_t)m;
+        if (lo < un) {
+            uint64_t t = (0 - un) % un;
+            if (lo < t) continue;
+        }
+        return (int64_t)(m >> 64) + 1;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Draw traces
+ * ---------------------------------------------------------------------------------------- */
+orc_trace *orc_trace_new(void) { return (orc_trace *)calloc(1, sizeof(orc_trace)); }
+void orc_trace_free(orc_trace *t) { if (!t) return; free(t->kind); free(t->ival); free(t->fval); free(t); }
+static void trace_push(orc_trace *t, uint8_t kind, int64_t iv, double fv)
+{
+    if (t->len == t->cap) {
+        t->cap = t->cap ? 2 * t->cap : 1024;
+        t->kind = (uint8_t *)realloc(t->kind, (size_t)t->cap);
+        t->ival = (int64_t *)realloc(t->ival, (size_t)t->cap * 8);
+        t->fval = (double *)realloc(t->fval, (size_t)t->cap * 8);
+    }
+    t->kind[t->len] = kind; t->ival[t->len] = iv; t->fval[t->len] = fv; t->len++;
+}
+void orc_trace_load(orc_trace *t, int64_t len, const uint8_t *kind, const int64_t *ival, const double *fval)
+{
+    t->len = 0; t->pos = 0; t->error = 0;
+    for (int64_t k = 0; k < len; k++) trace_push(t, kind[k], ival[k], fval[k]);
+}
+double orc_trace_rec_f64(void *p) { orc_trace *t = (orc_trace *)p; double v = t->inner.f64(t->inner.user); trace_push(t, 1, 0, v); return v; }
+int64_t orc_trace_rec_range(void *p, int64_t n) { orc_trace *t = (orc_trace *)p; int64_t v = t->inner.range(t->inner.user, n); trace_push(t, 0, v, 0.0); return v; }
+double orc_trace_play_f64(void *p)
+{
+    orc_trace *t = (orc_trace *)p;
+    if (t->pos >= t->len || t->kind[t->pos] != 1) { t->error = 1; return 0.5; }
+    return t->fval[t->pos++];
+}
+int64_t orc_trace_play_range(void *p, int64_t n)
+{
+    orc_trace *t = (orc_trace *)p;
+    if (t->pos >= t->len || t->kind[t->pos] != 0 || t->ival[t->pos] < 1 || t->ival[t->pos] > n) { t->error = 1; return 1; }
+    return t->ival[t->pos++];
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Graph object
+ * ---------------------------------------------------------------------------------------- */
+struct orc_graph {
+    int kind;
+    int64_t N;
+    /* EA (EA.jl:138-169, 534-553) */
+    int twoD;
+    int64_t *A;      /* [N*twoD] 1-based, rows sorted ascending */
+    int64_t *Ji;     /* [N*twoD] (EA_INT) */
+    double *Jd;      /* [N*twoD] (EA_F64) ; [N*N] (SK_F64) */
+    int64_t *uA;     /* unique neighbours per row (EA.jl:158 / :548) */
+    int *nuA;
+    /* LocalFields{ET} (Common.jl:27-36) */
+    int64_t *lfi, *lfi_last;
+    double *lfd, *lfd_last;
+    int64_t move_last;
+    /* allΔE */
+    int nDE;
+    double DE[64];
+    /* SK */
+    uint8_t *Jb; /* [N*N] 0/1 (SK_BIN) */
+    double sN;
+    int owns_J;
+    /* QT / Quant */
+    int64_t M, Nk;
+    double fourK, beta, Gamma;
+    orc_graph *X0;
+    orc_graph **X1;
+    uint64_t **C1;
+};
+
+int orc_kind(const orc_graph *g) { return g->kind; }
+int64_t orc_getN(const orc_graph *g) { return g->N; }
+double orc_quant_fourK(const orc_graph *g) { return g->kind == ORC_QUANT ? g->X0->fourK : g->fourK; }
+orc_graph *orc_inner_graph(orc_graph *g) { return g->kind == ORC_QUANT ? g->X0 : g; } /* Interface.jl:239-240 */
+
+static int is_discr(const orc_graph *g) { return g->kind == ORC_EA_INT || g->kind == ORC_QT; }
+static int is_double(const orc_graph *g) { return g->kind == ORC_QUANT; }
+
+/* gen_EA — src/graphs/EA.jl:24-43.  Column-major linear index, first coordinate fastest;
+ * for every site and dimension one forward bond, recorded at both ends; rows sorted. */
+static int cmp_i64(const void *a, const void *b) { int64_t x = *(const int64_t *)a, y = *(const int64_t *)b; return (x > y) - (x < y); }
+int64_t orc_gen_EA(int64_t L, int D, int64_t *A)
+{
+    if (L < 2 || D < 1) return -1;
+    int64_t N = 1; for (int d = 0; d < D; d++) N *= L;
+    int twoD = 2 * D;
+    int *cnt = (int *)calloc((size_t)N, sizeof(int));
+    for (int64_t x0 = 0; x0 < N; x0++) {            /* CartesianIndices order == linear order */
+        int64_t stride = 1, rem = x0;
+        for (int d = 0; d < D; d++) {
+            int64_t id = rem % L; rem /= L;
+            int64_t id1 = (id + 1) % L;               /* mod1(i+1, L) in 0-based form */
+            int64_t y0 = x0 + (id1 - id) * stride;
+            A[x0 * twoD + cnt[x0]++] = y0 + 1;        /* push!(A[x], y) */
+            A[y0 * twoD + cnt[y0]++] = x0 + 1;        /* push!(A[y], x) */
+            stride *= L;
+        }
+    }
+    for (int64_t x = 0; x < N; x++) qsort(A + x * twoD, (size_t)twoD, sizeof(int64_t), cmp_i64);
+    free(cnt);
+    return N;
+}
+
+/* gen_J — src/graphs/EA.jl:45-71.  One draw per bond with x<y in (x,k) order; mirrored into the
+ * first still-empty slot of J[y]. `draws` supplies f() values in consumption order. */
+int orc_gen_J_f64(int64_t N, int twoD, const int64_t *A, const double *draws, int64_t ndraws, double *J)
+{
+    const double m = -INFINITY; /* sentinel(Float64)=typemin */
+    for (int64_t k = 0; k < N * twoD; k++) J[k] = m;
+    int64_t nd = 0;
+    for (int64_t x = 1; x <= N; x++)
+        for (int k = 0; k < twoD; k++) {
+            int64_t y = A[(x - 1) * twoD + k];
+            if (x < y) {
+                if (nd >= ndraws) return -1;
+                double Jxy = draws[nd++];
+                J[(x - 1) * twoD + k] = Jxy;
+                int l = 0; while (l < twoD && J[(y - 1) * twoD + l] != m) l++;
+                if (l == twoD) return -2;
+                J[(y - 1) * twoD + l] = Jxy;
+            }
+        }
+    for (int64_t k = 0; k < N * twoD; k++) if (J[k] == m) return -3;
+    return (int)nd;
+}
+
+static void ea_common_init(orc_graph *g, int64_t N, int twoD, const int64_t *A)
+{
+    g->N = N; g->twoD = twoD;
+    g->A = (int64_t *)malloc((size_t)(N * twoD) * 8); memcpy(g->A, A, (size_t)(N * twoD) * 8);
+    g->uA = (int64_t *)malloc((size_t)(N * twoD) * 8);
+    g->nuA = (int *)malloc((size_t)N * sizeof(int));
+    for (int64_t x = 0; x < N; x++) {               /* unique of a sorted row */
+        int n = 0;
+        for (int k = 0; k < twoD; k++) {
+            int64_t y = A[x * twoD + k];
+            if (n == 0 || g->uA[x * twoD + n - 1] != y) g->uA[x * twoD + n++] = y;
+        }
+        g->nuA[x] = n;
+    }
+}
+
+/* generic allΔE for GraphEA — src/graphs/EA.jl:295-309 (the (-1,1) special case :293 gives the same tuple) */
+static int cmp_f64(const void *a, const void *b) { double x = *(const double *)a, y = *(const double *)b; return (x > y) - (x < y); }
+static void ea_int_allDE(orc_graph *g, const int64_t *lev, int nlev)
+{
+    int64_t cap = 1 << 16, ne = 1, *es = (int64_t *)malloc((size_t)cap * 8), *nw = (int64_t *)malloc((size_t)cap * 8);
+    es[0] = 0;
+    for (int n = 0; n < g->twoD; n++) {
+        int64_t nn = 0;
+        for (int64_t a = 0; a < ne; a++)
+            for (int l = 0; l < nlev; l++) { nw[nn++] = es[a] + lev[l]; nw[nn++] = es[a] - lev[l]; }
+        qsort(nw, (size_t)nn, 8, cmp_i64);
+        int64_t u = 0; for (int64_t a = 0; a < nn; a++) if (u == 0 || nw[u - 1] != nw[a]) nw[u++] = nw[a];
+        memcpy(es, nw, (size_t)u * 8); ne = u;
+    }
+    int nd = 0; double tmp[4096];
+    for (int64_t a = 0; a < ne; a++) tmp[nd++] = 2.0 * (double)llabs(es[a]);
+    qsort(tmp, (size_t)nd, 8, cmp_f64);
+    g->nDE = 0;
+    for (int a = 0; a < nd; a++) if (g->nDE == 0 || g->DE[g->nDE - 1] != tmp[a]) g->DE[g->nDE++] = tmp[a];
+    free(es); free(nw);
+}
+
+orc_graph *orc_ea_int_create(int64_t N, int twoD, const int64_t *A, const int64_t *J, const int64_t *lev, int nlev)
+{
+    orc_graph *g = (orc_graph *)calloc(1, sizeof(orc_graph));
+    g->kind = ORC_EA_INT; ea_common_init(g, N, twoD, A);
+    g->Ji = (int64_t *)malloc((size_t)(N * twoD) * 8); memcpy(g->Ji, J, (size_t)(N * twoD) * 8);
+    g->lfi = (int64_t *)calloc((size_t)N, 8); g->lfi_last = (int64_t *)calloc((size_t)N, 8);
+    g->owns_J = 1;
+    ea_int_allDE(g, lev, nlev);
+    return g;
+}
+static orc_graph *ea_f64_create_shared(int64_t N, int twoD, const int64_t *A, double *J, int own)
+{
+    orc_graph *g = (orc_graph *)calloc(1, sizeof(orc_graph));
+    g->kind = ORC_EA_F64; ea_common_init(g, N, twoD, A);
+    if (own) { g->Jd = (double *)malloc((size_t)(N * twoD) * 8); memcpy(g->Jd, J, (size_t)(N * twoD) * 8); }
+    else g->Jd = J;
+    g->owns_J = own;
+    g->lfd = (double *)calloc((size_t)N, 8); g->lfd_last = (double *)calloc((size_t)N, 8);
+    return g;
+}
+orc_graph *orc_ea_f64_create(int64_t N, int twoD, const int64_t *A, const double *J) { return ea_f64_create_shared(N, twoD, A, (double *)J, 1); }
+
+static orc_graph *sk_f64_create_shared(int64_t N, double *J, int own)
+{
+    orc_graph *g = (orc_graph *)calloc(1, sizeof(orc_graph));
+    g->kind = ORC_SK_F64; g->N = N;
+    if (own) { g->Jd = (double *)malloc((size_t)(N * N) * 8); memcpy(g->Jd, J, (size_t)(N * N) * 8); } else g->Jd = J;
+    g->owns_J = own;
+    g->lfd = (double *)calloc((size_t)N, 8); g->lfd_last = (double *)calloc((size_t)N, 8);
+    return g;
+}
+orc_graph *orc_sk_f64_create(int64_t N, const double *J) { return sk_f64_create_shared(N, (double *)J, 1); }
+static orc_graph *sk_bin_create_shared(int64_t N, uint8_t *J, int own)
+{
+    orc_graph *g = (orc_graph *)calloc(1, sizeof(orc_graph));
+    g->kind = ORC_SK_BIN; g->N = N; g->sN = sqrt((double)N); /* SK.jl:47 √N */
+    if (own) { g->Jb = (uint8_t *)malloc((size_t)(N * N)); memcpy(g->Jb, J, (size_t)(N * N)); } else g->Jb = J;
+    g->owns_J = own;
+    g->lfi = (int64_t *)calloc((size_t)N, 8); g->lfi_last = (int64_t *)calloc((size_t)N, 8);
+    return g;
+}
+orc_graph *orc_sk_bin_create(int64_t N, const uint8_t *J) { return sk_bin_create_shared(N, (uint8_t *)J, 1); }
+
+orc_graph *orc_qt_create(int64_t N, int64_t M, double fourK) /* QT.jl:42-54, allΔE :111 */
+{
+    if (M <= 2 || N % M != 0) return NULL;
+    orc_graph *g = (orc_graph *)calloc(1, sizeof(orc_graph));
+    g->kind = ORC_QT; g->N = N; g->M = M; g->Nk = N / M; g->fourK = fourK;
+    g->nDE = 2; g->DE[0] = 0.0; g->DE[1] = fourK;
+    return g;
+}
+orc_graph *orc_empty_create(int64_t N)
+{
+    orc_graph *g = (orc_graph *)calloc(1, sizeof(orc_graph));
+    g->kind = ORC_EMPTY; g->N = N;
+    return g;
+}
+
+/* round(x, digits=8) as Julia does it for Float64 (RoundNearest on x*10^8, then /10^8) — QT.jl:165 */
+static double round8(double x) { return nearbyint(x * 1e8) / 1e8; }
+
+orc_graph *orc_quant_create(int64_t Nk, int64_t M, double Gamma, double beta, int inner_kind,
+                            const void *J_inner, int twoD, const int64_t *A_inner)
+{
+    if (!(Gamma >= 0) || M <= 2) return NULL;
+    double fourK = round8(2.0 / beta * log(1.0 / tanh(beta * Gamma / (double)M))); /* QT.jl:165 */
+    orc_graph *g = (orc_graph *)calloc(1, sizeof(orc_graph));
+    g->kind = ORC_QUANT; g->N = Nk * M; g->M = M; g->Nk = Nk; g->beta = beta; g->Gamma = Gamma;
+    g->X0 = orc_qt_create(g->N, M, fourK);
+    g->X1 = (orc_graph **)calloc((size_t)M, sizeof(orc_graph *));
+    g->C1 = (uint64_t **)calloc((size_t)M, sizeof(uint64_t *));
+    void *Jshared = NULL;
+    for (int64_t k = 0; k < M; k++) {
+        switch (inner_kind) { /* QT.jl:139-145: M inner graphs sharing the constructor args, separate caches */
+        case ORC_SK_BIN:
+            if (k == 0) { g->X1[0] = orc_sk_bin_create(Nk, (const uint8_t *)J_inner); Jshared = g->X1[0]->Jb; }
+            else g->X1[k] = sk_bin_create_shared(Nk, (uint8_t *)Jshared, 0);
+            break;
+        case ORC_SK_F64:
+            if (k == 0) { g->X1[0] = orc_sk_f64_create(Nk, (const double *)J_inner); Jshared = g->X1[0]->Jd; }
+            else g->X1[k] = sk_f64_create_shared(Nk, (double *)Jshared, 0);
+            break;
+        case ORC_EA_F64:
+            if (k == 0) { g->X1[0] = orc_ea_f64_create(Nk, twoD, A_inner, (const double *)J_inner); Jshared = g->X1[0]->Jd; }
+            else g->X1[k] = ea_f64_create_shared(Nk, twoD, A_inner, (double *)Jshared, 0);
+            break;
+        case ORC_EMPTY: g->X1[k] = orc_empty_create(Nk); break;
+        default: return NULL;
+        }
+        g->C1[k] = (uint64_t *)calloc((size_t)((Nk + 63) / 64), 8); /* Config(Nk, init=false) QT.jl:144 */
+    }
+    return g;
+}
+
+void orc_graph_free(orc_graph *g)
+{
+    if (!g) return;
+    if (g->kind == ORC_QUANT) {
+        for (int64_t k = g->M - 1; k >= 0; k--) { orc_graph_free(g->X1[k]); free(g->C1[k]); }
+        free(g->X1); free(g->C1); orc_graph_free(g->X0);
+    }
+    free(g->A); free(g->uA); free(g->nuA);
+    if (g->owns_J) { free(g->Ji); free(g->Jd); free(g->Jb); }
+    free(g->lfi); free(g->lfi_last); free(g->lfd); free(g->lfd_last);
+    free(g);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * energy  (also (re)initialises the cache — Interface.jl:103)
+ * ---------------------------------------------------------------------------------------- */
+static int64_t qt_energy0(const orc_graph *g, const uint64_t *s) /* QT.jl:68-82 */
+{
+    int64_t n = 0, M = g->M, Nk = g->Nk;
+    for (int64_t i = 1; i <= Nk; i++) {
+        int sj = cfg_get(s, i + (M - 1) * Nk);
+        for (int64_t k = 1; k <= M; k++) {
+            int sk = cfg_get(s, i + (k - 1) * Nk);
+            n -= 1 - 2 * (sk ^ sj);
+            sj = sk;
+        }
+    }
+    return n;
+}
+
+double orc_energy(orc_graph *g, const uint64_t *s)
+{
+    int64_t N = g->N;
+    switch (g->kind) {
+    case ORC_EA_INT: { /* EA.jl:195-222 */
+        int64_t n = 0;
+        for (int64_t x = 1; x <= N; x++) {
+            int64_t sx = 2 * cfg_get(s, x) - 1, lf = 0;
+            for (int k = 0; k < g->twoD; k++) {
+                int64_t y = g->A[(x - 1) * g->twoD + k];
+                int64_t sy = 2 * cfg_get(s, y) - 1;
+                lf -= g->Ji[(x - 1) * g->twoD + k] * sx * sy;
+            }
+            n += lf;
+            g->lfi[x - 1] = 2 * lf;
+        }
+        g->move_last = 0;
+        memset(g->lfi_last, 0, (size_t)N * 8);
+        return (double)n / 2.0; /* n /= 2 ; discr(Int, n) */
+    }
+    case ORC_EA_F64: { /* EA.jl:584-611 */
+        double E1 = 0.0;
+        for (int64_t x = 1; x <= N; x++) {
+            double sx = (double)(2 * cfg_get(s, x) - 1), lf = 0.0;
+            for (int k = 0; k < g->twoD; k++) {
+                int64_t y = g->A[(x - 1) * g->twoD + k];
+                double sy = (double)(2 * cfg_get(s, y) - 1);
+                lf -= g->Jd[(x - 1) * g->twoD + k] * sx * sy; /* (Jxy*σx)*σy */
+            }
+            E1 += lf;
+            g->lfd[x - 1] = 2 * lf;
+        }
+        E1 /= 2;
+        g->move_last = 0;
+        memset(g->lfd_last, 0, (size_t)N * 8);
+        return E1;
+    }
+    case ORC_SK_F64: { /* SK.jl:212-237 */
+        double n = 0.0;
+        for (int64_t i = 1; i <= N; i++) {
+            const double *Ji = g->Jd + (i - 1) * N;
+            int si = cfg_get(s, i);
+            double lf = 0.0;
+            for (int64_t j = 1; j <= N; j++) lf += (double)(1 - 2 * (si ^ cfg_get(s, j))) * Ji[j - 1];
+            g->lfd[i - 1] = 2 * lf;
+            n -= lf;
+        }
+        n /= 2;
+        g->move_last = 0;
+        memset(g->lfd_last, 0, (size_t)N * 8);
+        return n;
+    }
+    case ORC_SK_BIN: { /* SK.jl:62-94 */
+        int64_t sums = 0;
+        for (int64_t i = 1; i <= N; i++) sums += cfg_get(s, i);
+        int64_t n = -2 * sums;
+        for (int64_t i = 1; i <= N; i++) {
+            const uint8_t *Ji = g->Jb + (i - 1) * N;
+            int64_t sc = 0;
+            for (int64_t j = 1; j <= N; j++) sc += Ji[j - 1] ^ cfg_get(s, j);
+            int64_t si = cfg_get(s, i);
+            int64_t lf = -(2 * si - 1) * (N - 1 - 2 * sc);
+            g->lfi[i - 1] = 2 * (-lf + 2 * si);
+            n += lf;
+        }
+        n /= 2; /* @assert n % 2 == 0 ; n ÷= 2 */
+        g->move_last = 0;
+        memset(g->lfi_last, 0, (size_t)N * 8);
+        return (double)n / g->sN;
+    }
+    case ORC_QT: /* QT.jl:84 */
+        return (double)qt_energy0(g, s) * g->fourK / 4;
+    case ORC_EMPTY:
+        return 0.0;
+    case ORC_QUANT: { /* QT.jl:185-199 */
+        double E = orc_energy(g->X0, s);
+        for (int64_t k = 1; k <= g->M; k++) {
+            uint64_t *s1 = g->C1[k - 1];
+            memset(s1, 0, (size_t)((g->Nk + 63) / 64) * 8);
+            for (int64_t i = 1; i <= g->Nk; i++) if (cfg_get(s, (k - 1) * g->Nk + i)) cfg_flip(s1, i); /* copyto! */
+            E += orc_energy(g->X1[k - 1], s1) / (double)g->M;
+        }
+        return E;
+    }
+    }
+    return NAN;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * delta_energy  (called BEFORE the flip — Interface.jl:127-128)
+ * ---------------------------------------------------------------------------------------- */
+static void qt_neighbors(const orc_graph *g, int64_t i, int64_t *k1, int64_t *k2) /* QT.jl:105-108 */
+{
+    *k1 = i - g->Nk + g->N * (i <= g->Nk);
+    *k2 = i + g->Nk - g->N * (i + g->Nk > g->N);
+}
+
+double orc_delta_energy_residual(orc_graph *g, const uint64_t *s, int64_t move) /* QT.jl:270-281 */
+{
+    (void)s;
+    if (g->kind != ORC_QUANT) return 0.0;
+    int64_t k = (move - 1) / g->Nk + 1, i = (move - 1) % g->Nk + 1;
+    return orc_delta_energy(g->X1[k - 1], g->C1[k - 1], i) / (double)g->M;
+}
+
+double orc_delta_energy(orc_graph *g, const uint64_t *s, int64_t move)
+{
+    switch (g->kind) {
+    case ORC_EA_INT: return (double)(-g->lfi[move - 1]);     /* EA.jl:266-275 */
+    case ORC_EA_F64: return -g->lfd[move - 1];               /* EA.jl:655-663 */
+    case ORC_SK_F64: return g->lfd[move - 1];                /* SK.jl:278-284 */
+    case ORC_SK_BIN: return (double)g->lfi[move - 1] / g->sN; /* SK.jl:135-140 */
+    case ORC_QT: {                                           /* QT.jl:86-103 */
+        int64_t k1, k2; qt_neighbors(g, move, &k1, &k2);
+        int sk = cfg_get(s, move), s1 = cfg_get(s, k1), s2 = cfg_get(s, k2);
+        int d = (sk == s1) - (sk != s2);                     /* (sk ⊻ ~s1) - (sk ⊻ s2) on Bools */
+        return (double)d * g->fourK;
+    }
+    case ORC_EMPTY: return 0.0;
+    case ORC_QUANT: /* QT.jl:283-286 */
+        return orc_delta_energy(g->X0, s, move) + orc_delta_energy_residual(g, s, move);
+    }
+    return NAN;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * update_cache!  (called AFTER the flip — Interface.jl:84-85) and spinflip! (Interface.jl:89-92)
+ * ---------------------------------------------------------------------------------------- */
+static void update_cache(orc_graph *g, uint64_t *s, int64_t move);
+
+void orc_spinflip(orc_graph *g, uint64_t *s, int64_t move)
+{
+    cfg_flip(s, move);
+    update_cache(g, s, move);
+}
+
+static void update_cache(orc_graph *g, uint64_t *s, int64_t move)
+{
+    int64_t N = g->N;
+    switch (g->kind) {
+    case ORC_EA_INT: { /* EA.jl:224-264 */
+        const int64_t *U = g->uA + (move - 1) * g->twoD; int nU = g->nuA[move - 1];
+        if (g->move_last == move) {
+            for (int k = 0; k < nU; k++) { int64_t y = U[k] - 1, t = g->lfi[y]; g->lfi[y] = g->lfi_last[y]; g->lfi_last[y] = t; }
+            g->lfi[move - 1] = -g->lfi[move - 1];
+            g->lfi_last[move - 1] = -g->lfi_last[move - 1];
+            return;
+        }
+        for (int k = 0; k < nU; k++) g->lfi_last[U[k] - 1] = g->lfi[U[k] - 1];
+        int sx = cfg_get(s, move);
+        for (int k = 0; k < g->twoD; k++) {
+            int64_t y = g->A[(move - 1) * g->twoD + k];
+            int64_t sxy = 1 - 2 * (sx ^ cfg_get(s, y));
+            g->lfi[y - 1] = g->lfi[y - 1] - 4 * sxy * g->Ji[(move - 1) * g->twoD + k];
+        }
+        int64_t lfm = g->lfi[move - 1];
+        g->lfi_last[move - 1] = lfm;
+        g->lfi[move - 1] = -lfm;
+        g->move_last = move;
+        return;
+    }
+    case ORC_EA_F64: { /* EA.jl:613-653 */
+        const int64_t *U = g->uA + (move - 1) * g->twoD; int nU = g->nuA[move - 1];
+        if (g->move_last == move) {
+            for (int k = 0; k < nU; k++) { int64_t y = U[k] - 1; double t = g->lfd[y]; g->lfd[y] = g->lfd_last[y]; g->lfd_last[y] = t; }
+            g->lfd[move - 1] = -g->lfd[move - 1];
+            g->lfd_last[move - 1] = -g->lfd_last[move - 1];
+            return;
+        }
+        for (int k = 0; k < nU; k++) g->lfd_last[U[k] - 1] = g->lfd[U[k] - 1];
+        int sx = cfg_get(s, move);
+        for (int k = 0; k < g->twoD; k++) {
+            int64_t y = g->A[(move - 1) * g->twoD + k];
+            double f = (double)(4 * (1 - 2 * (sx ^ cfg_get(s, y)))); /* 4 * σxy */
+            g->lfd[y - 1] -= f * g->Jd[(move - 1) * g->twoD + k];
+        }
+        double lfm = g->lfd[move - 1];
+        g->lfd_last[move - 1] = lfm;
+        g->lfd[move - 1] = -lfm;
+        g->move_last = move;
+        return;
+    }
+    case ORC_SK_F64: { /* SK.jl:239-276 */
+        if (g->move_last == move) { double *t = g->lfd; g->lfd = g->lfd_last; g->lfd_last = t; return; }
+        const double *Ji = g->Jd + (move - 1) * N;
+        int si = cfg_get(s, move);
+        double lfm = g->lfd[move - 1];
+        for (int64_t j = 1; j <= N; j++) {
+            double Js = (double)(1 - 2 * (si ^ cfg_get(s, j))) * Ji[j - 1];
+            double lfj = g->lfd[j - 1];
+            g->lfd_last[j - 1] = lfj;
+            g->lfd[j - 1] = lfj + 4 * Js;
+        }
+        g->lfd_last[move - 1] = lfm;
+        g->lfd[move - 1] = -lfm;
+        g->move_last = move;
+        return;
+    }
+    case ORC_SK_BIN: { /* SK.jl:96-133 */
+        if (g->move_last == move) { int64_t *t = g->lfi; g->lfi = g->lfi_last; g->lfi_last = t; return; }
+        const uint8_t *Ji = g->Jb + (move - 1) * N;
+        int si = cfg_get(s, move);
+        int64_t lfm = g->lfi[move - 1];
+        for (int64_t j = 1; j <= N; j++) {
+            int64_t Js = si ^ cfg_get(s, j) ^ Ji[j - 1];
+            int64_t lfj = g->lfi[j - 1];
+            g->lfi_last[j - 1] = lfj;
+            g->lfi[j - 1] = lfj + 8 * Js - 4;
+        }
+        g->lfi_last[move - 1] = lfm;
+        g->lfi[move - 1] = -lfm;
+        g->move_last = move;
+        return;
+    }
+    case ORC_QT: case ORC_EMPTY: return; /* Interface.jl:87 default: nothing */
+    case ORC_QUANT: { /* QT.jl:172-183 */
+        int64_t k = (move - 1) / g->Nk + 1, i = (move - 1) % g->Nk + 1;
+        orc_spinflip(g->X1[k - 1], g->C1[k - 1], i);
+        return;
+    }
+    }
+}
+
+/* neighbors — EA.jl:292,680 (uA); SK.jl:165,297 + Common.jl:78-92 (AllButOne); QT.jl:105-108; QT.jl:288-321 */
+int orc_neighbors(const orc_graph *g, int64_t i, int64_t *out)
+{
+    switch (g->kind) {
+    case ORC_EA_INT: case ORC_EA_F64: {
+        int n = g->nuA[i - 1];
+        for (int k = 0; k < n; k++) out[k] = g->uA[(i - 1) * g->twoD + k];
+        return n;
+    }
+    case ORC_SK_F64: case ORC_SK_BIN: {
+        int n = 0;
+        for (int64_t j = 1; j <= g->N; j++) if (j != i) out[n++] = j;
+        return n;
+    }
+    case ORC_QT: qt_neighbors(g, i, &out[0], &out[1]); return 2;
+    case ORC_EMPTY: return 0;
+    case ORC_QUANT: {
+        qt_neighbors(g->X0, i, &out[0], &out[1]);
+        int64_t k = (i - 1) / g->Nk + 1, j = (i - 1) % g->Nk + 1;
+        int n = orc_neighbors(g->X1[k - 1], j, out + 2);
+        for (int a = 0; a < n; a++) out[2 + a] += (k - 1) * g->Nk;
+        return n + 2;
+    }
+    }
+    return 0;
+}
+
+int orc_allDE(const orc_graph *g, double *out) /* Interface.jl:200-201,270 */
+{
+    const orc_graph *h = g->kind == ORC_QUANT ? g->X0 : g;
+    if (!is_discr(h)) return -1;
+    for (int k = 0; k < h->nDE; k++) out[k] = h->DE[k];
+    return h->nDE;
+}
+
+int64_t orc_get_lfields(const orc_graph *g, double *out)
+{
+    if (g->lfi) { for (int64_t i = 0; i < g->N; i++) out[i] = (double)g->lfi[i]; return g->N; }
+    if (g->lfd) { for (int64_t i = 0; i < g->N; i++) out[i] = g->lfd[i]; return g->N; }
+    return 0;
+}
+
+/* observables — QT.jl:113-121, 201-268 */
+double orc_transverse_mag(orc_graph *g, const uint64_t *s, double beta)
+{
+    orc_graph *q = orc_inner_graph(g);
+    double p = -(double)qt_energy0(q, s) / (double)q->N;
+    double x = beta * q->fourK / 2;
+    return cosh(x) - p * sinh(x);
+}
+double orc_Qenergy(orc_graph *g, const uint64_t *s)
+{
+    double E = -g->Gamma * orc_transverse_mag(g, s, g->beta);
+    for (int64_t k = 0; k < g->M; k++) E += orc_energy(g->X1[k], g->C1[k]) / (double)g->N;
+    return E;
+}
+void orc_Renergies(orc_graph *g, double *out) { for (int64_t k = 0; k < g->M; k++) out[k] = orc_energy(g->X1[k], g->C1[k]); }
+void orc_overlaps(orc_graph *g, double *ovs)
+{
+    int64_t M = g->M, Nk = g->Nk;
+    for (int64_t d = 0; d < M / 2; d++) ovs[d] = 0.0;
+    for (int64_t k1 = 1; k1 <= M - 1; k1++)
+        for (int64_t k2 = k1 + 1; k2 <= M; k2++) {
+            int64_t sum = 0;
+            for (int64_t i = 1; i <= Nk; i++) sum += cfg_get(g->C1[k1 - 1], i) ^ cfg_get(g->C1[k2 - 1], i);
+            int64_t dl = k2 - k1 < M + k1 - k2 ? k2 - k1 : M + k1 - k2;
+            ovs[dl - 1] += (double)(Nk - 2 * sum);
+        }
+    for (int64_t d = 1; d <= (M - 1) / 2; d++) ovs[d - 1] /= (double)(M * Nk);
+    if (M % 2 == 0) ovs[M / 2 - 1] /= (double)(M * Nk) / 2;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * ArraySet — src/ArraySets.jl:19-85
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { int64_t N, t; int64_t *v, *pos; } arrayset;
+static void as_init(arrayset *a, int64_t N) { a->N = N; a->t = 0; a->v = (int64_t *)calloc((size_t)N + 1, 8); a->pos = (int64_t *)calloc((size_t)N + 1, 8); }
+static void as_free(arrayset *a) { free(a->v); free(a->pos); }
+static inline void as_push(arrayset *a, int64_t i) { a->t++; a->v[a->t] = i; a->pos[i] = a->t; }
+static inline void as_delete(arrayset *a, int64_t i)
+{
+    int64_t p = a->pos[i];
+    a->v[p] = a->v[a->t];
+    a->pos[a->v[p]] = p;
+    a->pos[i] = 0;
+    a->t--;
+}
+static int as_check(const arrayset *a) /* ArraySets.jl:27-42 */
+{
+    if (a->t < 0 || a->t > a->N) return 1;
+    int64_t c = 0;
+    for (int64_t i = 1; i <= a->N; i++) {
+        if (a->pos[i] == 0) continue;
+        c++;
+        if (a->pos[i] < 1 || a->pos[i] > a->t) return 2;
+        if (a->v[a->pos[i]] != i) return 3;
+    }
+    if (c != a->t) return 4;
+    for (int64_t i = 1; i <= a->t; i++) { if (a->v[i] == 0) return 5; if (a->pos[a->v[i]] != i) return 6; }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * DeltaECache (discrete) — src/DeltaE.jl:28-295
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t N; int L;
+    double DE[64], ft[64];
+    double *T, *Tp; double z, zp;
+    arrayset *as; int64_t *pos;
+    int64_t (*staged)[3]; int64_t nstaged;
+    int rrr;
+} decache;
+
+static int findk(const decache *c, double dE) /* DeltaE.jl:28-60: index of |ΔE| in ΔElist, 0 if absent */
+{
+    dE = fabs(dE);
+    for (int k = 1; k <= c->L; k++) if (c->DE[k - 1] == dE) return k;
+    return 0;
+}
+static inline double class_f(const decache *c, int k) { return k > c->L ? c->ft[k - c->L - 1] : 1.0; } /* DeltaE.jl:138-139 */
+
+static decache *decache_new(orc_graph *X, const uint64_t *s, double beta, int rrr) /* DeltaE.jl:74-104 */
+{
+    decache *c = (decache *)calloc(1, sizeof(decache));
+    c->N = X->N; c->L = orc_allDE(X, c->DE); c->rrr = rrr;
+    int L = c->L;
+    c->as = (arrayset *)calloc((size_t)(2 * L + 1), sizeof(arrayset));
+    for (int k = 1; k <= 2 * L; k++) as_init(&c->as[k], c->N);
+    c->pos = (int64_t *)calloc((size_t)c->N + 1, 8);
+    for (int64_t i = 1; i <= c->N; i++) {
+        double dE = orc_delta_energy(X, s, i);
+        int aki = findk(c, dE);
+        int upi = dE > 0 || (dE == 0 && cfg_get(s, i) == 1);
+        int ki = aki + L * upi;
+        c->pos[i] = ki;
+        as_push(&c->as[ki], i);
+    }
+    c->staged = (int64_t(*)[3])malloc((size_t)(c->N + 1) * 3 * 8);
+    for (int k = 0; k < L; k++) c->ft[k] = exp(-beta * c->DE[k]);
+    c->T = (double *)calloc((size_t)(2 * L + 1), 8);
+    c->z = 0.0;
+    for (int k = 1; k <= 2 * L; k++) {
+        double x = (double)c->as[k].t * class_f(c, k);
+        c->z += x;
+        c->T[k] = x;
+    }
+    c->Tp = rrr ? (double *)calloc((size_t)(2 * L + 1), 8) : c->T;
+    c->zp = c->z;
+    return c;
+}
+static void decache_free(decache *c)
+{
+    for (int k = 1; k <= 2 * c->L; k++) as_free(&c->as[k]);
+    free(c->as); free(c->pos); free(c->staged);
+    if (c->Tp != c->T) free(c->Tp);
+    free(c->T); free(c);
+}
+static int decache_check(const decache *c) /* DeltaE.jl:120-136 */
+{
+    for (int k = 1; k <= 2 * c->L; k++) { int e = as_check(&c->as[k]); if (e) return 10 * k + e; }
+    for (int64_t i = 1; i <= c->N; i++) {
+        int64_t k = c->pos[i];
+        if (k < 1 || k > 2 * c->L) return 1000;
+        int64_t p = c->as[k].pos[i];
+        if (p < 1 || p > c->as[k].t) return 1001;
+        for (int k1 = 1; k1 <= 2 * c->L; k1++) if (k1 != k && c->as[k1].pos[i] != 0) return 1002;
+    }
+    return 0;
+}
+
+static int64_t d_rand_skip(const decache *c, orc_draws d) /* DeltaE.jl:141-144 */
+{
+    return (int64_t)floor(log1p(-d.f64(d.user)) / log1p(-c->z / (double)c->N));
+}
+static int64_t d_rand_move(const decache *c, orc_draws d, double *dE) /* DeltaE.jl:146-167 */
+{
+    int L = c->L;
+    double r = d.f64(d.user) * c->z, cT = 0.0;
+    int k = 0, broke = 0;
+    for (k = 1; k <= 2 * L; k++) { cT += c->T[k]; if (r < cT) { broke = 1; break; } }
+    if (!broke) k = 2 * L;                  /* `for outer k` leaves k at the last value */
+    if (!(r < cT)) while (c->T[k] == 0) k--;
+    *dE = k <= L ? -c->DE[k - 1] : c->DE[k - L - 1];
+    const arrayset *a = &c->as[k];
+    return a->v[d.range(d.user, a->t)];     /* ArraySets.jl:81-85 */
+}
+static void d_compute_staged(orc_graph *X, uint64_t *s, int64_t i, decache *c) /* DeltaE.jl:202-230 */
+{
+    int L = c->L; int64_t nb[64]; /* discrete graphs on this path have ≤ 2D (or 2) neighbours */
+    orc_spinflip(X, s, i);
+    c->nstaged = 0;
+    int n = orc_neighbors(X, i, nb);
+    for (int a = 0; a < n; a++) {
+        int64_t j = nb[a], k0 = c->pos[j];
+        double dE1 = orc_delta_energy(X, s, j);
+        int ak1 = findk(c, dE1);
+        int upj1 = dE1 > 0 || (dE1 == 0 && cfg_get(s, j) == 1);
+        int64_t k1 = ak1 + L * upj1;
+        if (k0 == k1) continue;
+        c->staged[c->nstaged][0] = j; c->staged[c->nstaged][1] = k0; c->staged[c->nstaged][2] = k1; c->nstaged++;
+    }
+    int64_t k0 = c->pos[i], k1 = k0 - L * (2 * (k0 > L) - 1);
+    c->staged[c->nstaged][0] = i; c->staged[c->nstaged][1] = k0; c->staged[c->nstaged][2] = k1; c->nstaged++;
+    orc_spinflip(X, s, i);
+}
+static double d_reverse_probs(decache *c) /* DeltaE.jl:184-200 */
+{
+    double zp = c->z;
+    if (c->Tp != c->T) memcpy(c->Tp, c->T, (size_t)(2 * c->L + 1) * 8);
+    for (int64_t a = 0; a < c->nstaged; a++) {
+        int k0 = (int)c->staged[a][1], k1 = (int)c->staged[a][2];
+        double f0 = class_f(c, k0), f1 = class_f(c, k1);
+        c->Tp[k0] -= f0;
+        c->Tp[k1] += f1;
+        zp += f1 - f0;
+    }
+    c->zp = zp;
+    return zp;
+}
+static void d_apply_staged(decache *c) /* DeltaE.jl:169-182 */
+{
+    for (int64_t a = 0; a < c->nstaged; a++) {
+        int64_t j = c->staged[a][0]; int k0 = (int)c->staged[a][1], k1 = (int)c->staged[a][2];
+        as_delete(&c->as[k0], j);
+        as_push(&c->as[k1], j);
+        c->pos[j] = k1;
+    }
+    double *t = c->T; c->T = c->Tp; c->Tp = t; c->z = c->zp;
+}
+/* apply_move! for DiscrGraph / DoubleGraph{DiscrGraph} — DeltaE.jl:232-295 */
+static double d_apply_move(orc_graph *X, uint64_t *s, int64_t move, decache *c)
+{
+    int L = c->L; int64_t nb[64];
+    orc_spinflip(X, s, move);
+    orc_graph *X0 = orc_inner_graph(X);
+    double zp = c->z;
+    int n = orc_neighbors(X0, move, nb);
+    for (int a = 0; a <= n; a++) {
+        int64_t j, k0, k1;
+        if (a < n) {
+            j = nb[a]; k0 = c->pos[j];
+            double dE1 = orc_delta_energy(X0, s, j);
+            int ak1 = findk(c, dE1);
+            int upj1 = dE1 > 0 || (dE1 == 0 && cfg_get(s, j) == 1);
+            k1 = ak1 + L * upj1;
+            if (k0 == k1) continue;
+        } else {
+            j = move; k0 = c->pos[move]; k1 = k0 - L * (2 * (k0 > L) - 1);
+        }
+        double f0 = class_f(c, (int)k0), f1 = class_f(c, (int)k1);
+        c->T[k0] -= f0;
+        c->T[k1] += f1;
+        zp += f1 - f0;
+        as_delete(&c->as[k0], j);
+        as_push(&c->as[k1], j);
+        c->pos[j] = k1;
+    }
+    double cc = c->z / zp;
+    c->z = zp;
+    return cc;
+}
+
+int orc_check_discrete_cache(orc_graph *g, uint64_t *s, double beta, const int64_t *sites, int64_t nmoves)
+{
+    orc_graph *X0 = orc_inner_graph(g);
+    orc_energy(g, s);
+    decache *c = decache_new(X0, s, beta, 1);
+    int e = decache_check(c);
+    for (int64_t m = 0; m < nmoves && !e; m++) {
+        d_apply_move(g, s, sites[m], c);
+        e = decache_check(c);
+        if (!e) { /* classes must equal a fresh classification */
+            for (int64_t i = 1; i <= c->N && !e; i++) {
+                double dE = orc_delta_energy(X0, s, i);
+                int ki = findk(c, dE) + c->L * (dE > 0 || (dE == 0 && cfg_get(s, i) == 1));
+                if (ki != c->pos[i]) e = 2000;
+            }
+            double z = 0; for (int k = 1; k <= 2 * c->L; k++) z += (double)c->as[k].t * class_f(c, k);
+            if (fabs(z - c->z) > 1e-9 * (1 + fabs(z))) e = 2001;
+        }
+    }
+    decache_free(c);
+    return e;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * DynamicSampler — src/DynamicSamplers.jl:18-176 (tree walk instead of the tinds/tpos tables;
+ * the reference keeps that equivalent form in comments, :182-196)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { double *v, *ps; double z; int64_t N, N2; int levs; int64_t trefresh; } dynsmp;
+
+static void ds_add_path(dynsmp *d, int64_t i, double x) /* ps[k] += x along the path of element i (1-based) */
+{
+    int64_t k = 0, off = 1, u = d->levs > 0 ? (int64_t)1 << (d->levs - 1) : 0, i0 = i - 1;
+    for (int lev = 1; lev <= d->levs; lev++) {
+        if ((i0 & u) == 0) { d->ps[off + k] += x; k *= 2; }
+        else k = 2 * k + 1;
+        u >>= 1; off *= 2;
+    }
+}
+static void ds_refresh(dynsmp *d) /* DynamicSamplers.jl:84-98 */
+{
+    double z = 0.0;
+    for (int64_t i = 1; i <= d->N2; i++) z += d->v[i]; /* sum(v): Julia sums pairwise; differs by O(ε) only */
+    d->z = z;
+    memset(d->ps, 0, (size_t)(d->N2 + 1) * 8);
+    for (int64_t i = 1; i <= d->N; i++) ds_add_path(d, i, d->v[i]);
+    d->trefresh = 0;
+}
+static dynsmp *ds_new(int64_t N, const double *v) /* DynamicSamplers.jl:35-51 */
+{
+    dynsmp *d = (dynsmp *)calloc(1, sizeof(dynsmp));
+    d->N = N; d->levs = 0; while (((int64_t)1 << d->levs) < N) d->levs++;
+    d->N2 = (int64_t)1 << d->levs;
+    d->v = (double *)calloc((size_t)d->N2 + 2, 8);
+    d->ps = (double *)calloc((size_t)d->N2 + 2, 8);
+    for (int64_t i = 1; i <= N; i++) d->v[i] = v[i - 1];
+    ds_refresh(d);
+    return d;
+}
+static void ds_free(dynsmp *d) { free(d->v); free(d->ps); free(d); }
+static int64_t ds_getel(dynsmp *d, double x, int *err) /* DynamicSamplers.jl:130-152 */
+{
+    x *= d->z;
+    int64_t k = 0, off = 1;
+    for (int lev = 1; lev <= d->levs; lev++) {
+        double p = d->ps[off + k];
+        k *= 2;
+        if (x > p) { x -= p; k += 1; }
+        off *= 2;
+    }
+    if (k >= d->N || d->v[k + 1] == 0) {
+        if (!(d->trefresh > 0)) { *err = 1; return 1; }
+        ds_refresh(d);
+        return ds_getel(d, x, err); /* sic: the reference recurses with the already-scaled residual x */
+    }
+    return k + 1;
+}
+static void ds_set(dynsmp *d, int64_t i, double x) /* DynamicSamplers.jl:159-176 */
+{
+    if (d->trefresh >= (d->N > 100 ? d->N : 100)) ds_refresh(d);
+    d->trefresh++;
+    double dd = x - d->v[i];
+    d->v[i] = x;
+    d->z += dd;
+    ds_add_path(d, i, dd);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * DeltaECacheCont — src/DeltaE.jl:297-410
+ * ---------------------------------------------------------------------------------------- */
+static inline double prior(double x) { return x > 0 ? exp(-x) : 1.0; } /* DeltaE.jl:297 */
+typedef struct { dynsmp *ds; double *dEs; double beta; int64_t *sj; double *sdE, *sp; int64_t nstaged; int64_t *nb; } cocache;
+
+static cocache *cocache_new(orc_graph *X, const uint64_t *s, double beta) /* DeltaE.jl:304-311 */
+{
+    cocache *c = (cocache *)calloc(1, sizeof(cocache));
+    int64_t N = X->N;
+    c->dEs = (double *)malloc((size_t)(N + 1) * 8);
+    double *p = (double *)malloc((size_t)N * 8);
+    for (int64_t i = 1; i <= N; i++) { c->dEs[i] = orc_delta_energy(X, s, i); p[i - 1] = prior(beta * c->dEs[i]); }
+    c->ds = ds_new(N, p);
+    free(p);
+    c->beta = beta;
+    c->sj = (int64_t *)malloc((size_t)(N + 1) * 8); c->sdE = (double *)malloc((size_t)(N + 1) * 8); c->sp = (double *)malloc((size_t)(N + 1) * 8);
+    c->nb = (int64_t *)malloc((size_t)(N + 2) * 8);
+    return c;
+}
+static void cocache_free(cocache *c) { ds_free(c->ds); free(c->dEs); free(c->sj); free(c->sdE); free(c->sp); free(c->nb); free(c); }
+static int64_t c_rand_skip(const cocache *c, orc_draws d) /* DeltaE.jl:319-324 */
+{
+    double b = c->ds->z / (double)c->ds->N;
+    if (b < DBL_MIN) b = DBL_MIN;
+    if (b > 1.0) b = 1.0;
+    return (int64_t)floor(log1p(-d.f64(d.user)) / log1p(-b));
+}
+static int64_t c_rand_move(cocache *c, orc_draws d, double *dE, int *err) /* DeltaE.jl:326-332 */
+{
+    int64_t move = ds_getel(c->ds, d.f64(d.user), err);
+    *dE = c->dEs[move];
+    return move;
+}
+static void c_compute_staged(orc_graph *X, uint64_t *s, int64_t i, cocache *c) /* DeltaE.jl:356-373 */
+{
+    orc_spinflip(X, s, i);
+    c->nstaged = 0;
+    double dE = orc_delta_energy(X, s, i);
+    c->sj[0] = i; c->sdE[0] = dE; c->sp[0] = prior(c->beta * dE); c->nstaged = 1;
+    int n = orc_neighbors(X, i, c->nb);
+    for (int a = 0; a < n; a++) {
+        int64_t j = c->nb[a];
+        dE = orc_delta_energy(X, s, j);
+        c->sj[c->nstaged] = j; c->sdE[c->nstaged] = dE; c->sp[c->nstaged] = prior(c->beta * dE); c->nstaged++;
+    }
+    orc_spinflip(X, s, i);
+}
+static double c_reverse_probs(cocache *c) /* DeltaE.jl:344-354 */
+{
+    double z = c->ds->z;
+    for (int64_t a = 0; a < c->nstaged; a++) z += c->sp[a] - c->ds->v[c->sj[a]];
+    if (z < DBL_MIN) z = DBL_MIN;
+    if (z > (double)c->ds->N) z = (double)c->ds->N;
+    return z;
+}
+static void c_apply_staged(cocache *c) /* DeltaE.jl:334-342 */
+{
+    for (int64_t a = 0; a < c->nstaged; a++) { c->dEs[c->sj[a]] = c->sdE[a]; ds_set(c->ds, c->sj[a], c->sp[a]); }
+}
+static double c_apply_move(orc_graph *X, uint64_t *s, int64_t move, cocache *c, int inner) /* DeltaE.jl:378-410 */
+{
+    orc_spinflip(X, s, move);
+    orc_graph *X0 = inner ? orc_inner_graph(X) : X;
+    double z = c->ds->z;
+    double dE = orc_delta_energy(X0, s, move);
+    c->dEs[move] = dE;
+    ds_set(c->ds, move, prior(c->beta * dE));
+    int n = orc_neighbors(X0, move, c->nb);
+    for (int a = 0; a < n; a++) {
+        int64_t j = c->nb[a];
+        dE = orc_delta_energy(X0, s, j);
+        c->dEs[j] = dE;
+        ds_set(c->ds, j, prior(c->beta * dE));
+    }
+    return z / c->ds->z;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Samplers — src/RRRMC.jl
+ * ---------------------------------------------------------------------------------------- */
+static inline int accept1(double x, orc_draws d) { return x >= 0 || d.f64(d.user) < exp(x); } /* RRRMC.jl:39 */
+static inline int accept2(double c, double x, orc_draws d)                                    /* RRRMC.jl:40-44 */
+{
+    if (c >= 1 && x >= 0) return 1;
+    double a = c * exp(x);
+    return a >= 1 || d.f64(d.user) < a;
+}
+#define PUSH_SAMPLE()                                                              \
+    do {                                                                           \
+        if (res.nsamples < Es_cap && Es) Es[res.nsamples] = E;                     \
+        res.nsamples++;                                                            \
+    } while (0)
+
+/* standardMC — RRRMC.jl:81-127 */
+orc_result orc_standardMC(orc_graph *X, double beta, int64_t iters, int64_t step, uint64_t *s,
+                          orc_draws d, orc_hook hook, void *user, double *Es, int64_t Es_cap)
+{
+    orc_result res = { 0, 0, 0, 0, 0 };
+    int64_t N = X->N;
+    double E = orc_energy(X, s);
+    int64_t accepted = 0, it = 0;
+    while (it < iters) {
+        it++;
+        if (it % step == 0) {
+            PUSH_SAMPLE();
+            if (hook && !hook(user, it, E, accepted)) break;
+        }
+        int64_t i = d.range(d.user, N);
+        double dE = orc_delta_energy(X, s, i);
+        if (!accept1(-beta * dE, d)) continue;
+        orc_spinflip(X, s, i);
+        E += dE;
+        accepted++;
+    }
+    res.iters_done = it; res.accepted = accepted;
+    return res;
+}
+
+/* rrrMC(::SingleGraph) RRRMC.jl:149-219 and rrrMC(::DoubleGraph) RRRMC.jl:221-290 */
+orc_result orc_rrrMC(orc_graph *X, double beta, int64_t iters, int64_t step, uint64_t *s,
+                     orc_draws d, double staged_thr, double staged_thr_fact,
+                     orc_hook hook, void *user, double *Es, int64_t Es_cap)
+{
+    orc_result res = { 0, 0, 0, 0, 0 };
+    if (!isfinite(beta)) { res.status = -1; return res; }         /* ArgumentError :159/:230 */
+    int dbl = is_double(X);
+    orc_graph *X0 = orc_inner_graph(X);
+    int discr = is_discr(X0);
+    if (dbl && !discr) { res.status = -2; return res; }           /* not on this path */
+    if (isnan(staged_thr)) staged_thr = dbl ? 0.5 : (discr ? 0.5 : 0.8); /* :163-165, :226 */
+    int64_t N = X->N;
+    double E = orc_energy(X, s);
+    if (dbl && !isfinite(E)) { res.status = -3; return res; }     /* @assert isfinite(E) :238 */
+    decache *dc = discr ? decache_new(X0, s, beta, 1) : NULL;     /* gen_ΔEcache :171/:240 */
+    cocache *cc = discr ? NULL : cocache_new(X0, s, beta);
+    double lambda = staged_thr_fact / (double)N;
+    int64_t staged_its = 0, it = 0, accepted = 0;
+    double acc_rate = 0.5;
+    int err = 0;
+    while (it < iters && !err) {
+        it++;
+        if (it % step == 0) {
+            PUSH_SAMPLE();
+            if (hook && !hook(user, it, E, accepted)) break;
+        }
+        int acc = 0;
+        if (acc_rate < staged_thr) {
+            staged_its++;
+            /* step_rrr — RRRMC.jl:131-138 */
+            double z, zp, dE0; int64_t move;
+            if (discr) { z = dc->z; move = d_rand_move(dc, d, &dE0); d_compute_staged(X0, s, move, dc); zp = d_reverse_probs(dc); }
+            else       { z = cc->ds->z; move = c_rand_move(cc, d, &dE0, &err); c_compute_staged(X0, s, move, cc); zp = c_reverse_probs(cc); }
+            double c = z / zp;
+            int ok; double dE1 = 0.0;
+            if (dbl) { dE1 = orc_delta_energy_residual(X, s, move); ok = accept2(c, -beta * dE1, d); }
+            else ok = d.f64(d.user) < c;
+            if (ok) {
+                orc_spinflip(X, s, move);
+                if (discr) d_apply_staged(dc); else c_apply_staged(cc);
+                E += dE0 + dE1;
+                accepted++; acc = 1;
+            }
+        } else {
+            double dE0, dE1 = 0.0; int64_t move;
+            if (discr) move = d_rand_move(dc, d, &dE0); else move = c_rand_move(cc, d, &dE0, &err);
+            if (dbl) dE1 = orc_delta_energy_residual(X, s, move);
+            double c = discr ? d_apply_move(X, s, move, dc) : c_apply_move(X, s, move, cc, 1);
+            int ok = dbl ? accept2(c, -beta * dE1, d) : (d.f64(d.user) < c);
+            if (ok) { E += dE0 + dE1; accepted++; acc = 1; }
+            else { if (discr) d_apply_move(X, s, move, dc); else c_apply_move(X, s, move, cc, 1); }
+        }
+        acc_rate = acc_rate * (1 - lambda) + acc * lambda;
+    }
+    if (dc) decache_free(dc);
+    if (cc) cocache_free(cc);
+    res.iters_done = it; res.accepted = accepted; res.staged_its = staged_its; res.status = err ? -4 : 0;
+    return res;
+}
+
+/* bklMC — RRRMC.jl:311-359 (apply_step_bkl! :294-298) */
+orc_result orc_bklMC(orc_graph *X, double beta, int64_t iters, int64_t step, uint64_t *s,
+                     orc_draws d, orc_hook hook, void *user, double *Es, int64_t Es_cap)
+{
+    orc_result res = { 0, 0, 0, 0, 0 };
+    int discr = is_discr(X);
+    double E = orc_energy(X, s);
+    decache *dc = discr ? decache_new(X, s, beta, 0) : NULL;
+    cocache *cc = discr ? NULL : cocache_new(X, s, beta);
+    int64_t it = 0, accepted = 0, nextstep = step;
+    int err = 0;
+    while (it < iters && !err) {
+        int64_t skip = discr ? d_rand_skip(dc, d) : c_rand_skip(cc, d);
+        double dE; int64_t move = discr ? d_rand_move(dc, d, &dE) : c_rand_move(cc, d, &dE, &err);
+        int out = 0;
+        while (it + skip + 1 >= nextstep) {
+            PUSH_SAMPLE();
+            if (hook && !hook(user, nextstep, E, accepted)) { out = 1; break; }
+            nextstep += step;
+            if (nextstep > iters) { out = 1; break; }
+        }
+        if (out) break;
+        if (discr) d_apply_move(X, s, move, dc); else c_apply_move(X, s, move, cc, 0);
+        it += skip + 1;
+        E += dE;
+        accepted++;
+    }
+    if (dc) decache_free(dc);
+    if (cc) cocache_free(cc);
+    res.iters_done = it; res.accepted = accepted; res.status = err ? -4 : 0;
+    return res;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * CPU model of the engine's checkerboard Metropolis (new-engine feature).
+ * Deliberately scalar: per (site, replica) ΔE from the ±J definition (EA.jl:277-289 naive form),
+ * acceptance = Metropolis (RRRMC.jl:39) with U drawn by the engine's per-task bit procedure:
+ *   task=(site i, group g of 128 replicas, sweep t); call q of the task is
+ *   Philox4x32-10(ctr=(q | (t>>32)<<16, i, g, t&0xffffffff), key=seed).
+ *   Plane phase (q=0..K-1): bit b of word w of call q is the q-th most significant bit of U for
+ *   replica 128g+32w+b; lanes are decided at the first bit where U differs from the 64-bit
+ *   fixed-point threshold T_c.  Tail: the lanes still undecided after K planes are visited in
+ *   ascending (w,b) order; the n-th one takes word n%4 of call K+n/4 as the next 32 bits of U
+ *   and accepts iff it is < bits [63-K .. 32-K] of T_c.
+ * ---------------------------------------------------------------------------------------- */
+void orc_checkerboard_sweeps(int L, int D, int64_t R, uint32_t *spins, const int8_t *Jfwd,
+                             const uint64_t *thr, int K, uint64_t seed, uint64_t sweep0, int64_t nsweeps,
+                             int64_t *accepted)
+{
+    int64_t N = 1; for (int d = 0; d < D; d++) N *= L;
+    int64_t W = R / 32, G = (R + 127) / 128;
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    for (int64_t sw = 0; sw < nsweeps; sw++) {
+        uint64_t t = sweep0 + (uint64_t)sw;
+        for (int colour = 0; colour < 2; colour++)
+            for (int64_t i = 0; i < N; i++) {
+                int64_t co[3] = { 0, 0, 0 }, rem = i, par = 0;
+                for (int d = 0; d < D; d++) { co[d] = rem % L; rem /= L; par += co[d]; }
+                if ((par & 1) != colour) continue;
+                /* neighbour sites and couplings */
+                int64_t nbr[6]; int Jn[6]; int64_t stride = 1;
+                for (int d = 0; d < D; d++) {
+                    int64_t up = i + (((co[d] + 1) % L) - co[d]) * stride;
+                    int64_t dn = i + (((co[d] + L - 1) % L) - co[d]) * stride;
+                    nbr[2 * d] = up; Jn[2 * d] = Jfwd[i * D + d];
+                    nbr[2 * d + 1] = dn; Jn[2 * d + 1] = Jfwd[dn * D + d];
+                    stride *= L;
+                }
+                for (int64_t g = 0; g < G; g++) {
+                    int cls[128]; /* 0: ΔE≤0 (always flip); c≥1: ΔE = 4c */
+                    int und[128];
+                    for (int l = 0; l < 128; l++) {
+                        int64_t r = 128 * g + l; cls[l] = -1; und[l] = 0;
+                        if (r >= R) continue;
+                        int64_t w = r >> 5; int b = (int)(r & 31);
+                        int sc = (spins[i * W + w] >> b) & 1, acc = 0;
+                        for (int k = 0; k < 2 * D; k++) {
+                            int sk = (spins[nbr[k] * W + w] >> b) & 1;
+                            acc += Jn[k] * (2 * sc - 1) * (2 * sk - 1);
+                        }
+                        int dE = 2 * acc;
+                        cls[l] = dE <= 0 ? 0 : dE / 4;
+                        und[l] = cls[l] > 0;
+                    }
+                    int flip[128]; for (int l = 0; l < 128; l++) flip[l] = (cls[l] == 0);
+                    uint32_t ctr[4], out[4];
+                    ctr[1] = (uint32_t)i; ctr[2] = (uint32_t)g; ctr[3] = (uint32_t)t;
+                    for (int q = 0; q < K; q++) {
+                        int any = 0; for (int l = 0; l < 128; l++) any |= und[l];
+                        if (!any) break;
+                        ctr[0] = (uint32_t)q | ((uint32_t)(t >> 32) << 16);
+                        orc_philox4x32_10(ctr, key, out);
+                        for (int l = 0; l < 128; l++) {
+                            if (!und[l]) continue;
+                            int ub = (out[l >> 5] >> (l & 31)) & 1;
+                            int tb = (int)((thr[cls[l] - 1] >> (63 - q)) & 1);
+                            if (ub != tb) { und[l] = 0; flip[l] = (ub < tb); }
+                        }
+                    }
+                    int n = 0;
+                    for (int l = 0; l < 128; l++) {
+                        if (!und[l]) continue;
+                        if ((n & 3) == 0) { ctr[0] = (uint32_t)(K + n / 4) | ((uint32_t)(t >> 32) << 16); orc_philox4x32_10(ctr, key, out); }
+                        uint32_t V = out[n & 3];
+                        uint32_t rem32 = (uint32_t)((K ? (thr[cls[l] - 1] << K) : thr[cls[l] - 1]) >> 32);
+                        flip[l] = V < rem32;
+                        n++;
+                    }
+                    for (int l = 0; l < 128; l++) {
+                        int64_t r = 128 * g + l;
+                        if (r >= R || !flip[l]) continue;
+                        spins[i * W + (r >> 5)] ^= (uint32_t)1 << (r & 31);
+                        if (accepted) accepted[r]++;
+                    }
+                }
+            }
+    }
+}

@@ -1,0 +1,137 @@
+/* rrrmc_oracle.h — CPU restatement of RRRMC.jl's single-spin-flip hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library, and only as the checker / the CPU baseline.
+ *
+ * PARITY UNPINNED: the reference (pure Julia) cannot run in this image and ships
+ * no golden vectors (test/runtests.jl asserts only the energy-consistency
+ * invariant).  This restatement is pinned by (i) that invariant, (ii) closed
+ * forms / hand-checked adjacency from the reference sources, (iii) exact
+ * Boltzmann stationarity on tiny instances — see tests/test_oracle_*.py.
+ *
+ * Every function cites the reference file:line it follows (paths relative to
+ * the reference checkout, e.g. src/graphs/EA.jl:195-222).
+ */
+#ifndef RRRMC_ORACLE_H
+#define RRRMC_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    ORC_EA_INT = 1, /* GraphEA{Int,LEV,twoD}   <: DiscrGraph{Int}      src/graphs/EA.jl:138-169 */
+    ORC_EA_F64 = 2, /* GraphEANormal{twoD}     <: SimpleGraph{Float64} src/graphs/EA.jl:534-553 */
+    ORC_SK_BIN = 3, /* GraphSK                 <: SimpleGraph{Float64} src/graphs/SK.jl:28-49   */
+    ORC_SK_F64 = 4, /* GraphSKNormal           <: SimpleGraph{Float64} src/graphs/SK.jl:181-199 */
+    ORC_QT     = 5, /* GraphQT{fourK}          <: DiscrGraph{Float64}  src/graphs/QT.jl:42-54   */
+    ORC_QUANT  = 6, /* GraphQuant{fourK,G}     <: DoubleGraph          src/graphs/QT.jl:126-147 */
+    ORC_EMPTY  = 7  /* GraphEmpty              <: SimpleGraph{Int}     src/graphs/Empty.jl:14-31*/
+};
+
+typedef struct orc_graph orc_graph;
+
+/* ---- draw source (injectable; Appendix A.8 of SURVEY.md lists the draw order) ---- */
+typedef struct {
+    double  (*f64)(void *user);              /* Julia rand()      in [0,1) */
+    int64_t (*range)(void *user, int64_t n); /* Julia rand(1:n)   in 1..n  */
+    void *user;
+} orc_draws;
+
+/* Counter-based source shared with the CUDA chain kernels: Philox4x32-10,
+ * key=(seed_lo,seed_hi), counter=(n_lo,n_hi,chain,tag), one call per draw. */
+typedef struct { uint64_t seed, chain, n; uint32_t tag; } orc_philox_src;
+void     orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+double   orc_philox_f64(void *src);
+int64_t  orc_philox_range(void *src, int64_t n);
+uint64_t orc_philox_u64(orc_philox_src *src);
+
+/* Trace of typed draws: kind 0 = RANGE (ival), 1 = FLOAT (fval). */
+typedef struct {
+    int64_t len, cap, pos;
+    uint8_t *kind; int64_t *ival; double *fval;
+    orc_draws inner; /* recorder: source being recorded; replayer: unused */
+    int error;       /* replayer: set when kind mismatches / trace exhausted */
+} orc_trace;
+orc_trace *orc_trace_new(void);
+void       orc_trace_free(orc_trace *t);
+void       orc_trace_load(orc_trace *t, int64_t len, const uint8_t *kind, const int64_t *ival, const double *fval);
+double     orc_trace_rec_f64(void *t);
+int64_t    orc_trace_rec_range(void *t, int64_t n);
+double     orc_trace_play_f64(void *t);
+int64_t    orc_trace_play_range(void *t, int64_t n);
+
+/* ---- lattice / coupling generators ---- */
+int64_t orc_gen_EA(int64_t L, int D, int64_t *A_out /* [L^D * 2D], 1-based, rows sorted */);
+int     orc_gen_J_f64(int64_t N, int twoD, const int64_t *A, const double *draws, int64_t ndraws, double *J_out);
+
+/* ---- graph constructors (A, site indices are 1-based like the reference) ---- */
+orc_graph *orc_ea_int_create(int64_t N, int twoD, const int64_t *A, const int64_t *J, const int64_t *lev, int nlev);
+orc_graph *orc_ea_f64_create(int64_t N, int twoD, const int64_t *A, const double *J);
+orc_graph *orc_sk_f64_create(int64_t N, const double *J /* [N*N] row-major, symmetric, zero diag */);
+orc_graph *orc_sk_bin_create(int64_t N, const uint8_t *J /* [N*N] 0/1, symmetric, zero diag */);
+orc_graph *orc_qt_create(int64_t N, int64_t M, double fourK);
+orc_graph *orc_empty_create(int64_t N);
+/* GraphQuant(Nk,M,Γ,β,Gconstr,args...) QT.jl:163-170: inner_kind ∈ {ORC_SK_BIN, ORC_SK_F64, ORC_EMPTY, ORC_EA_F64};
+ * all M slices share the inner couplings (QAliases.jl:43), each slice owns its cache. For ORC_EA_F64 pass twoD and A. */
+orc_graph *orc_quant_create(int64_t Nk, int64_t M, double Gamma, double beta, int inner_kind,
+                            const void *J_inner, int twoD, const int64_t *A_inner);
+void       orc_graph_free(orc_graph *g);
+
+/* ---- Interface (src/Interface.jl:87-270) ---- */
+int     orc_kind(const orc_graph *g);
+int64_t orc_getN(const orc_graph *g);
+double  orc_energy(orc_graph *g, const uint64_t *chunks);            /* (re)initialises caches */
+double  orc_delta_energy(orc_graph *g, const uint64_t *chunks, int64_t i);
+double  orc_delta_energy_residual(orc_graph *g, const uint64_t *chunks, int64_t i);
+void    orc_spinflip(orc_graph *g, uint64_t *chunks, int64_t i);    /* flip + update_cache! */
+int     orc_neighbors(const orc_graph *g, int64_t i, int64_t *out); /* returns count */
+int     orc_allDE(const orc_graph *g, double *out);                  /* DiscrGraph / DoubleGraph{DiscrGraph} only */
+int64_t orc_get_lfields(const orc_graph *g, double *out);            /* cached local fields (as double) */
+double  orc_quant_fourK(const orc_graph *g);
+orc_graph *orc_inner_graph(orc_graph *g);
+/* observables QT.jl:113-121, 201-268 */
+double  orc_transverse_mag(orc_graph *g, const uint64_t *chunks, double beta);
+double  orc_Qenergy(orc_graph *g, const uint64_t *chunks);
+void    orc_Renergies(orc_graph *g, double *out /* [M] */);
+void    orc_overlaps(orc_graph *g, double *out /* [M/2] */);
+
+/* ---- samplers (src/RRRMC.jl:81-359). hook returns 0 to stop. ---- */
+typedef int (*orc_hook)(void *user, int64_t it, double E, int64_t accepted);
+typedef struct {
+    int64_t nsamples;   /* entries written to Es */
+    int64_t iters_done; /* final `it` */
+    int64_t accepted;
+    int64_t staged_its; /* rrr only */
+    int     status;     /* 0 ok, <0 error */
+} orc_result;
+
+orc_result orc_standardMC(orc_graph *g, double beta, int64_t iters, int64_t step, uint64_t *chunks,
+                          orc_draws d, orc_hook hook, void *user, double *Es, int64_t Es_cap);
+/* staged_thr = NaN selects the reference default (0.8 Simple / 0.5 Discr / 0.5 Double) */
+orc_result orc_rrrMC(orc_graph *g, double beta, int64_t iters, int64_t step, uint64_t *chunks,
+                     orc_draws d, double staged_thr, double staged_thr_fact,
+                     orc_hook hook, void *user, double *Es, int64_t Es_cap);
+orc_result orc_bklMC(orc_graph *g, double beta, int64_t iters, int64_t step, uint64_t *chunks,
+                     orc_draws d, orc_hook hook, void *user, double *Es, int64_t Es_cap);
+
+/* ΔE-class cache consistency (DeltaE.jl:120-136, ArraySets.jl:27-42); exposed for tests:
+ * builds a cache for (g,chunks,beta), applies `nmoves` eager apply_move! calls on sites[], checks
+ * consistency after each, and returns 0 when consistent. */
+int orc_check_discrete_cache(orc_graph *g, uint64_t *chunks, double beta, const int64_t *sites, int64_t nmoves);
+
+/* ---- CPU model of the engine's checkerboard Metropolis (NOT in the reference).
+ * Restates, with scalar per-(site,replica) loops on top of orc-level ΔE, the exact per-task
+ * random-bit procedure the CUDA kernel uses, so the two can be compared bit for bit.
+ * spins: multispin words [N][R/32] (site-major, 0-based site = x + L*y + L*L*z), updated in place.
+ * J: forward-bond couplings [N][D] (±1) for bonds to x+1,y+1,(z+1).
+ * thr: per-class 64-bit fixed-point acceptance thresholds floor(exp(-β·ΔE_c)·2^64), c=1..D (ΔE=4c). */
+void orc_checkerboard_sweeps(int L, int D, int64_t R, uint32_t *spins, const int8_t *Jfwd,
+                             const uint64_t *thr, int K, uint64_t seed, uint64_t sweep0, int64_t nsweeps,
+                             int64_t *accepted /* [R] += */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
