@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — spin-flip attempts/s, 3D EA L=64 ±J × 1024 replicas (BASELINE.json configs[1]) on N B200s.
+
+A "step" = SWEEPS_PER_STEP checkerboard Metropolis sweeps over the whole replica batch of one GPU
+(L^3 * R * SWEEPS_PER_STEP spin-flip attempts). Replicas shard across ranks (weak scaling: every rank owns its own
+1024 replicas of the same instance); NCCL is used only for the barrier, the max-over-ranks time and the gather of
+the per-replica energies behind `hook`.
+
+  python bench.py [--gpus N --steps K --warmup W]          # our arm
+  python bench.py --impl reference [...]                    # CPU arm: the oracle restatement of RRRMC.jl's
+                                                            # standardMC on all host cores (Julia cannot run here)
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L, D, R_PER_GPU = 64, 3, 1024
+N_SITES = L ** D
+SWEEPS_PER_STEP = 100
+BETA = 1.0
+PLANES_K = 6
+SEED = 0x5EEDEA64
+METRIC = "spin-flip attempts/s, 3D EA L=64 ±J ×1024 replicas"
+UNIT = "attempts/s"
+# 2 bits spin RMW per attempt + 3 coupling bits per site per sweep shared by R replicas
+ALG_BYTES_PER_SWEEP = 2 * N_SITES * R_PER_GPU // 8 + 3 * N_SITES // 8
+
+
+def synthetic_instance():
+    """3 forward bonds/site iid uniform{-1,+1}; one instance shared by all replicas and ranks."""
+    import rrrmc_b200 as rb
+    rng = np.random.default_rng(SEED)
+    A = rb.gen_EA(L, D)
+    J = rb.gen_J(lambda n: rng.choice(np.array([-1.0, 1.0]), n), A)
+    return A, J.astype(np.int64)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement of the reference's standardMC (random-site Metropolis with cached local
+# fields, RRRMC.jl:81-127 + EA.jl:195-275), one replica per host thread, each with its own graph copy.
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_rate(A, J, iters_per_thread, nthreads):
+    from oracle import ffi
+    graphs = [ffi.Graph.ea_int(A, J) for _ in range(nthreads)]
+    srcs = [ffi.XoshiroDraws(SEED + t) for t in range(nthreads)]
+    cfgs = [s.config(N_SITES) for s in srcs]
+    for g, c in zip(graphs, cfgs):
+        g.energy(c)
+    done = [0] * nthreads
+
+    def work(t):
+        _, res = ffi.standardMC(graphs[t], BETA, iters_per_thread, cfgs[t], srcs[t], step=iters_per_thread)
+        done[t] = res.iters_done
+    th = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+    t0 = time.perf_counter()
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    dt = time.perf_counter() - t0
+    return sum(done) / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import rrrmc_b200 as rb  # host-side lattice helpers only (no device needed)
+    A, J = synthetic_instance()
+    cores = os.cpu_count() or 1
+    iters = 6_000_000  # per thread per step: a bounded sample of the workload (full step = 2.7e10 attempts/replica batch)
+    for _ in range(max(0, args.warmup)):
+        cpu_reference_rate(A, J, 200_000, cores)
+    rates, t_tot = [], 0.0
+    for _ in range(max(1, args.steps)):
+        r, dt = cpu_reference_rate(A, J, iters, cores)
+        rates.append(r); t_tot += dt
+    v = float(np.mean(rates))
+    sample = f"{cores} independent replicas (1 per thread), {iters} random-site attempts each per step, L=64 3D ±J, β={BETA}"
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u32 bit-sliced / int64 local fields", "data": "synthetic",
+           "config": {"workload": "EA3D L=64 ±J standardMC (reference algorithm, CPU)", "L": L, "D": D, "beta": BETA},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0,
+           "note": "reference is pure Julia (no julia binary in the image): timed the C restatement oracle/rrrmc_oracle.c"}
+    print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import rrrmc_b200 as rb
+    from rrrmc_b200 import _ffi
+    from rrrmc_b200._ffi import check, lib, ptr
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = rb.Context(local_rank)
+    A, J = synthetic_instance()
+    X = rb.GraphEA(L, D, replicas=R_PER_GPU, A=A, J=J, ctx=ctx)
+    st = X._ensure_state()
+    check(lib().rrrmc_state_randomize(st, SEED + rank))
+    beta = BETA
+    thr = np.array([min(int(np.exp(-beta * 4 * c) * 2.0 ** 64), 2 ** 64 - 1) for c in range(1, D + 1)], dtype=np.uint64)
+
+    def step(k):
+        check(lib().rrrmc_checkerboard_sweeps(st, ptr(thr), D, PLANES_K, SEED + 1000 * rank, k * SWEEPS_PER_STEP, SWEEPS_PER_STEP))
+
+    # ---- device-resident arm ("value"): inputs already in HBM, CUDA events on the launching stream ----------
+    for k in range(args.warmup):
+        step(k)
+    ctx.flush_l2()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = ctx.launch_count()
+    ms_steps = []
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        ctx.timer_start()
+        step(args.warmup + k)
+        ms_steps.append(ctx.timer_stop())
+        ctx.flush_l2()  # evict L2 between timed steps (outside the event pair); the 32 MiB state would otherwise stay resident
+        ctx.sync()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = ctx.launch_count() - l0 - args.steps  # minus the flush kernels
+    clk = clocks.stop() if rank == 0 else None
+    ms_total = float(sum(ms_steps))
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    attempts_per_step = N_SITES * R_PER_GPU * SWEEPS_PER_STEP
+    value = world * attempts_per_step * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end arm: the public sampler call with HOST buffers (pinned), H2D + D2H inside the timed region --
+    nch = (N_SITES + 63) // 64
+    h_in = torch.empty((R_PER_GPU, nch), dtype=torch.int64).pin_memory()
+    h_out = torch.empty((R_PER_GPU, nch), dtype=torch.int64).pin_memory()
+    h_E = torch.empty((1, R_PER_GPU), dtype=torch.float64).pin_memory()
+    rng = np.random.default_rng(SEED + 7 + rank)
+    h_in.numpy().view(np.uint64)[...] = rng.integers(0, 2 ** 64, (R_PER_GPU, nch), dtype=np.uint64)
+    betas = np.full(R_PER_GPU, beta)
+    opts = _ffi.Opts(); check(lib().rrrmc_opts_default(C.byref(opts)))
+    opts.planes_K = PLANES_K
+    opts.count_accepted = 0
+    info = _ffi.RunInfo()
+    iters = SWEEPS_PER_STEP * N_SITES
+    gathered = [torch.empty(R_PER_GPU, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
+
+    def e2e_step(k):
+        check(lib().rrrmc_state_upload(st, 0, R_PER_GPU, h_in.data_ptr()))
+        check(lib().rrrmc_standard_mc(st, ptr(betas), iters, iters, SEED + 17 * k + 1000 * rank, C.cast(None, _ffi.HOOK), None,
+                                      C.byref(opts), h_E.data_ptr(), 1, C.byref(info)))
+        check(lib().rrrmc_state_download(st, 0, R_PER_GPU, h_out.data_ptr()))
+        if world > 1:  # the observable reduction behind `hook`: per-replica energies of every rank
+            dist.all_gather(gathered, h_E[0].cuda(non_blocking=True))
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        e2e_step(1 + k)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e_value = world * attempts_per_step * args.steps / t_e2e
+    assert float(h_E.mean()) < -1.0 * N_SITES, "e2e energies look wrong"
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        launch_ms = ms_total / (args.steps * 2 * SWEEPS_PER_STEP)  # two colour launches per sweep
+        achieved = (ALG_BYTES_PER_SWEEP / 2) / (launch_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "checkerboard_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        cores = os.cpu_count() or 1
+        cpu_iters = 4_000_000
+        cpu_v, cpu_dt = cpu_reference_rate(A, J, cpu_iters, cores)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 bit-sliced (multispin, 32 replicas/word)", "data": "synthetic",
+            "config": {"workload": "GraphEA 3D L=64 ±J, checkerboard Metropolis, 1024 replicas per GPU (BASELINE configs[1])",
+                       "L": L, "D": D, "replicas_per_gpu": R_PER_GPU, "beta": beta, "sweeps_per_step": SWEEPS_PER_STEP,
+                       "rng": "Philox4x32-10, exact per-(site,replica) Bernoulli via %d bit planes + 32-bit tail" % PLANES_K,
+                       "parallelism": f"replica-sharded x{world}", "l2": "flushed between timed steps (256 MiB write)",
+                       "accepted_counters": "off in the timed loop"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_checkerboard<3,true>",
+                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_SWEEP // 2, "launch_ms": launch_ms,
+                         "note": "integer-issue bound by the per-(site,replica) RNG, not by HBM (see DESIGN.md)"},
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{cores} replicas (1/thread) x {cpu_iters} random-site attempts, same instance, beta={beta}; {cpu_dt:.1f}s"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(R_PER_GPU * nch * 8),
+                    "d2h_bytes_per_step": int(R_PER_GPU * nch * 8 + R_PER_GPU * 8),
+                    "api": "rrrmc_state_upload + rrrmc_standard_mc + rrrmc_state_download (host pinned buffers)"},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,156 @@
+/* rrrmc_b200.h — C ABI of the B200-native engine for RRRMC.jl's single-spin-flip Monte Carlo hot path.
+ *
+ * The reference (pure Julia) has no FFI; its "operator API" is multiple dispatch on
+ * AbstractGraph (src/Interface.jl:87-270) plus the sampler functions (src/RRRMC.jl:81-359).
+ * Each entry point below names the reference interface it replaces.  A Julia host binds these
+ * with `ccall` (see INTEGRATION.md and rrrmc.jl_b200/julia/RRRMCB200.jl); this repository's
+ * tests and bench drive the same symbols from Python through ctypes.
+ *
+ * Conventions kept from the reference: site indices are 1-based; a configuration is the
+ * `BitVector` chunk array of src/Interface.jl:21-29 (site i = bit (i-1)&63 of UInt64 chunk
+ * (i-1)>>6, σ = 2s-1); `energy` (re)initialises caches (Interface.jl:103); `delta_energy` is
+ * evaluated before the flip, `update_cache`/`spinflip` after it (Interface.jl:84-85,127-128).
+ * New: every call acts on a *replica batch* of R independent chains of the same graph.
+ *
+ * All functions return rrrmc_status_t (0 = ok). Negative codes map to Julia exceptions in the
+ * shim (RRRMC_ERR_ARG -> ArgumentError). rrrmc_last_error() gives the thread-local message.
+ * A context and everything created from it must be used from one host thread at a time.
+ * There is no CPU fallback: every compute entry point fails with RRRMC_ERR_CUDA without a device.
+ */
+#ifndef RRRMC_B200_H
+#define RRRMC_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int rrrmc_status_t;
+#define RRRMC_OK               0
+#define RRRMC_ERR_ARG         -1 /* invalid argument (Julia: ArgumentError)            */
+#define RRRMC_ERR_CUDA        -2 /* CUDA runtime failure / no device                    */
+#define RRRMC_ERR_UNSUPPORTED -3 /* valid request the engine does not implement         */
+#define RRRMC_ERR_STATE       -4 /* object in the wrong state (e.g. energy not called)  */
+
+typedef struct rrrmc_ctx   rrrmc_ctx_t;
+typedef struct rrrmc_graph rrrmc_graph_t;
+typedef struct rrrmc_state rrrmc_state_t;
+
+const char *rrrmc_last_error(void);
+const char *rrrmc_version(void);
+
+/* ---- context: one device, one stream ------------------------------------------------------ */
+/* cuda_stream: a cudaStream_t to launch on (e.g. torch's current stream) or NULL to create one. */
+rrrmc_status_t rrrmc_ctx_create(int device, void *cuda_stream, rrrmc_ctx_t **out);
+rrrmc_status_t rrrmc_ctx_destroy(rrrmc_ctx_t *ctx);
+rrrmc_status_t rrrmc_ctx_sync(rrrmc_ctx_t *ctx);
+/* CUDA-event stopwatch on the context's stream (bench.py times kernels with this). */
+rrrmc_status_t rrrmc_ctx_timer_start(rrrmc_ctx_t *ctx);
+rrrmc_status_t rrrmc_ctx_timer_stop(rrrmc_ctx_t *ctx, float *elapsed_ms);
+/* number of kernels this context has launched so far (bench.py's gpu_launches). */
+rrrmc_status_t rrrmc_ctx_launch_count(rrrmc_ctx_t *ctx, uint64_t *count);
+/* writes >= `bytes` of device memory to evict L2 between timed steps. */
+rrrmc_status_t rrrmc_ctx_flush_l2(rrrmc_ctx_t *ctx);
+
+/* ---- graphs ------------------------------------------------------------------------------- */
+#define RRRMC_EA_PM1 1 /* GraphEA{Int,(-1,1),2D}: J is int64, every entry ±1   (EA.jl:138-191) */
+#define RRRMC_EA_INT 2 /* GraphEA{Int,LEV,2D}: J is int64, small integers      (EA.jl:181-190) */
+#define RRRMC_EA_F64 3 /* GraphEANormal{2D}: J is double                       (EA.jl:534-574) */
+
+/* Replaces GraphEA{ET,LEV,twoD}(A, J) (EA.jl:145-168) / GraphEANormal{twoD}(L, A, J) (EA.jl:540-552).
+ * A: [N*2D] int64, 1-based, rows sorted ascending — must be the gen_EA(L,D) lattice (EA.jl:24-43);
+ * J: [N*2D] aligned slot-for-slot with A (gen_J, EA.jl:45-71); int64 for PM1/INT, double for F64. */
+rrrmc_status_t rrrmc_graph_ea_create(rrrmc_ctx_t *ctx, int L, int D, int coupling_kind,
+                                     const int64_t *A, const void *J, rrrmc_graph_t **out);
+/* Convenience: the gen_EA adjacency itself (EA.jl:24-43) so hosts without the reference can build A. */
+rrrmc_status_t rrrmc_gen_ea_adjacency(int L, int D, int64_t *A_out /* [L^D * 2D] */);
+rrrmc_status_t rrrmc_graph_destroy(rrrmc_graph_t *g);
+
+/* getN (Interface.jl:145) */
+rrrmc_status_t rrrmc_getN(const rrrmc_graph_t *g, int64_t *N);
+/* neighbors(X, i) (Interface.jl:158; EA.jl:292): distinct neighbours of 1-based site i, ascending. */
+rrrmc_status_t rrrmc_neighbors(const rrrmc_graph_t *g, int64_t site, int64_t *out, int *n);
+/* allΔE(X) (Interface.jl:200-201; EA.jl:293-309): sorted non-negative |ΔE| values. out has room for 64. */
+rrrmc_status_t rrrmc_allDE(const rrrmc_graph_t *g, double *out, int *n);
+
+/* ---- replica-batch state (R chains; replaces `Config`, Interface.jl:21-54) ------------------ */
+rrrmc_status_t rrrmc_state_create(rrrmc_graph_t *g, int64_t n_replicas, rrrmc_state_t **out);
+rrrmc_status_t rrrmc_state_destroy(rrrmc_state_t *s);
+/* Config(N) random init for every replica (Interface.jl:24-28), from Philox keyed by `seed`. */
+rrrmc_status_t rrrmc_state_randomize(rrrmc_state_t *s, uint64_t seed);
+/* chunks: [count][ceil(N/64)] uint64 in the reference BitVector layout; the library transposes
+ * to/from its device layout. Unused high bits of the last chunk are written as zero on download. */
+rrrmc_status_t rrrmc_state_upload(rrrmc_state_t *s, int64_t first_replica, int64_t count, const uint64_t *chunks);
+rrrmc_status_t rrrmc_state_download(rrrmc_state_t *s, int64_t first_replica, int64_t count, uint64_t *chunks);
+
+/* ---- Interface queries on the batch ------------------------------------------------------- */
+/* energy(X, C) for every replica (Interface.jl:105; EA.jl:195-222): E_out[R]. Integer-valued
+ * (exact) for PM1/INT graphs. Also (re)initialises the device-side local-field caches. */
+rrrmc_status_t rrrmc_energy(rrrmc_state_t *s, double *E_out);
+/* delta_energy(X, C, i) for every replica (Interface.jl:130; EA.jl:266-275): dE_out[R]. */
+rrrmc_status_t rrrmc_delta_energy(rrrmc_state_t *s, int64_t site, double *dE_out);
+/* delta_energy(X, C, i) for i = 1..N of one replica: dE_out[N]. */
+rrrmc_status_t rrrmc_all_delta_energy(rrrmc_state_t *s, int64_t replica, double *dE_out);
+/* spinflip!(X, C, i) = flip + update_cache! (Interface.jl:89-92; EA.jl:224-264) on the replicas
+ * selected by replica_mask (bit r&31 of word r>>5; NULL = all replicas). */
+rrrmc_status_t rrrmc_spinflip(rrrmc_state_t *s, int64_t site, const uint32_t *replica_mask);
+/* magnetisation Σσ per replica (hook-side observable). */
+rrrmc_status_t rrrmc_magnetization(rrrmc_state_t *s, double *m_out);
+
+/* ---- samplers ------------------------------------------------------------------------------ */
+/* hook(it, X, C, accepted, E)::Bool of RRRMC.jl:61-64,104-109, batched: E[R], accepted[R]
+ * (accepted[r] = -1 when counting is disabled). Return 0 to stop the run. Called on the host
+ * thread that invoked the sampler; the state may be queried/downloaded from inside the hook. */
+typedef int (*rrrmc_hook_fn)(void *user, int64_t it, const double *E, const int64_t *accepted, int64_t R);
+
+#define RRRMC_SCHED_CHECKERBOARD 0 /* two-colour lattice sweeps, all replicas in lock step (new engine) */
+#define RRRMC_SCHED_RANDOM_SITE  1 /* the reference's order: i = rand(1:N) per attempt (RRRMC.jl:113)   */
+
+typedef struct {
+    int    schedule;        /* RRRMC_SCHED_*; default checkerboard                                   */
+    int    planes_K;        /* checkerboard: random bit-planes before the per-lane tail (default 6)    */
+    int    count_accepted;  /* 1: exact per-replica accepted counters; 0: hook gets accepted = -1      */
+    double staged_thr;      /* rrrMC: NaN = reference default (RRRMC.jl:163-165)                       */
+    double staged_thr_fact; /* rrrMC: default 5.0 (RRRMC.jl:155)                                       */
+    int    reserved[8];
+} rrrmc_opts_t;
+rrrmc_status_t rrrmc_opts_default(rrrmc_opts_t *o);
+
+typedef struct {
+    int64_t nsamples;   /* rows written to Es                                                  */
+    int64_t iters_done; /* attempts per replica actually executed                              */
+    int64_t launches;   /* kernels launched by this call                                       */
+    float   device_ms;  /* CUDA-event time of the sampling kernels of this call (0 if unknown) */
+} rrrmc_run_info_t;
+
+/* standardMC(X, β, iters; seed, step, hook, C0) (RRRMC.jl:81-127) on the batch. C0 is the state's
+ * current contents (upload or randomize first). beta[R]: per-replica inverse temperature (must be
+ * constant inside each 32-replica word). Es: [Es_cap][R] row-major or NULL. With the checkerboard
+ * schedule `iters` and `step` are rounded up to whole sweeps (N attempts per replica). */
+rrrmc_status_t rrrmc_standard_mc(rrrmc_state_t *s, const double *beta, int64_t iters, int64_t step, uint64_t seed,
+                                 rrrmc_hook_fn hook, void *user, const rrrmc_opts_t *opts,
+                                 double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
+/* rrrMC(X, β, iters; ...) (RRRMC.jl:149-290) and bklMC(X, β, iters; ...) (RRRMC.jl:311-359). */
+rrrmc_status_t rrrmc_rrr_mc(rrrmc_state_t *s, const double *beta, int64_t iters, int64_t step, uint64_t seed,
+                            rrrmc_hook_fn hook, void *user, const rrrmc_opts_t *opts,
+                            double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
+rrrmc_status_t rrrmc_bkl_mc(rrrmc_state_t *s, const double *beta, int64_t iters, int64_t step, uint64_t seed,
+                            rrrmc_hook_fn hook, void *user, const rrrmc_opts_t *opts,
+                            double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
+
+/* Replay: feed one chain the typed draw stream the reference consumed
+ * (kind 0 = rand(1:n) value, 1 = rand() value) and reproduce its trajectory.
+ * sampler: 0 standardMC, 1 rrrMC, 2 bklMC. Es: [Es_cap] energies at every `step`. */
+rrrmc_status_t rrrmc_replay(rrrmc_state_t *s, int64_t replica, int sampler, double beta, int64_t iters, int64_t step,
+                            const uint8_t *draw_kind, const int64_t *draw_ival, const double *draw_fval, int64_t ndraws,
+                            const rrrmc_opts_t *opts, double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
+
+/* Device-resident sweep loop without host round trips (what bench.py times as `value`):
+ * runs `nsweeps` checkerboard sweeps starting at sweep counter `sweep0`. thr64: per-class
+ * fixed-point acceptance table floor(exp(-β·ΔE_c)·2^64), ΔE_c = allΔE[c], c = 1..nclasses-1. */
+rrrmc_status_t rrrmc_checkerboard_sweeps(rrrmc_state_t *s, const uint64_t *thr64, int nthr, int planes_K,
+                                         uint64_t seed, uint64_t sweep0, int64_t nsweeps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

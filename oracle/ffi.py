@@ -31,6 +31,10 @@ class PhiloxSrc(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("chain", C.c_uint64), ("n", C.c_uint64), ("tag", C.c_uint32)]
 
 
+class XoshiroSrc(C.Structure):
+    _fields_ = [("s", C.c_uint64 * 4)]
+
+
 class Trace(C.Structure):
     pass
 
@@ -61,6 +65,8 @@ def lib():
         "orc_philox4x32_10": (None, [p(np.uint32), p(np.uint32), p(np.uint32)]),
         "orc_philox_f64": (f64, [vp]), "orc_philox_range": (i64, [vp, i64]),
         "orc_philox_u64": (C.c_uint64, [C.POINTER(PhiloxSrc)]),
+        "orc_xoshiro_seed": (None, [C.POINTER(XoshiroSrc), C.c_uint64]),
+        "orc_xoshiro_f64": (f64, [vp]), "orc_xoshiro_range": (i64, [vp, i64]),
         "orc_trace_new": (C.POINTER(Trace), []), "orc_trace_free": (None, [C.POINTER(Trace)]),
         "orc_trace_load": (None, [C.POINTER(Trace), i64, p(np.uint8), p(np.int64), p(np.float64)]),
         "orc_gen_EA": (i64, [i64, i32, p(np.int64)]),
@@ -118,6 +124,23 @@ class PhiloxDraws:
         """Config(N): ⌈N/64⌉ raw 64-bit words, unused high bits zero (Interface.jl:24-28)."""
         nch = (N + 63) // 64
         ch = np.array([self.u64() for _ in range(nch)], dtype=np.uint64)
+        if N % 64:
+            ch[-1] &= np.uint64((1 << (N % 64)) - 1)
+        return ch
+
+
+class XoshiroDraws:
+    """xoshiro256++ source (CPU-baseline timing only)."""
+
+    def __init__(self, seed):
+        self.src = XoshiroSrc()
+        lib().orc_xoshiro_seed(C.byref(self.src), seed)
+        self.draws = Draws(_fnptr("orc_xoshiro_f64"), _fnptr("orc_xoshiro_range"), C.addressof(self.src))
+
+    def config(self, N):
+        rng = np.random.default_rng(int(self.src.s[0]) & 0xffffffff)
+        nch = (N + 63) // 64
+        ch = rng.integers(0, 2 ** 64, nch, dtype=np.uint64)
         if N % 64:
             ch[-1] &= np.uint64((1 << (N % 64)) - 1)
         return ch

@@ -73,6 +73,36 @@ int64_t orc_philox_range(void *src, int64_t n)
     }
 }
 
+/* xoshiro256++ (Blackman & Vigna) — the generator family Julia >= 1.7 uses by default; used only for the
+ * CPU-baseline timing in bench.py so that the baseline is not handicapped by a counter-based RNG. */
+static inline uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+static inline uint64_t xoshiro_next(orc_xoshiro_src *g)
+{
+    uint64_t *s = g->s;
+    const uint64_t result = rotl64(s[0] + s[3], 23) + s[0], t = s[1] << 17;
+    s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl64(s[3], 45);
+    return result;
+}
+void orc_xoshiro_seed(orc_xoshiro_src *g, uint64_t seed)
+{
+    for (int k = 0; k < 4; k++) { /* splitmix64 */
+        uint64_t z = (seed += 0x9e3779b97f4a7c15ull);
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull; z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        g->s[k] = z ^ (z >> 31);
+    }
+}
+double orc_xoshiro_f64(void *src) { return (double)(xoshiro_next((orc_xoshiro_src *)src) >> 11) * 0x1.0p-53; }
+int64_t orc_xoshiro_range(void *src, int64_t n)
+{
+    const uint64_t un = (uint64_t)n;
+    for (;;) {
+        __uint128_t m = (__uint128_t)xoshiro_next((orc_xoshiro_src *)src) * un;
+        uint64_t lo = (uint64_t)m;
+        if (lo < un) { uint64_t t = (0 - un) % un; if (lo < t) continue; }
+        return (int64_t)(m >> 64) + 1;
+    }
+}
+
 /* ------------------------------------------------------------------------------------------
  * Draw traces
  * ---------------------------------------------------------------------------------------- */

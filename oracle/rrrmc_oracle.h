@@ -47,6 +47,12 @@ double   orc_philox_f64(void *src);
 int64_t  orc_philox_range(void *src, int64_t n);
 uint64_t orc_philox_u64(orc_philox_src *src);
 
+/* xoshiro256++ source (Julia >= 1.7's default generator family) for CPU-baseline timing. */
+typedef struct { uint64_t s[4]; } orc_xoshiro_src;
+void     orc_xoshiro_seed(orc_xoshiro_src *g, uint64_t seed);
+double   orc_xoshiro_f64(void *src);
+int64_t  orc_xoshiro_range(void *src, int64_t n);
+
 /* Trace of typed draws: kind 0 = RANGE (ival), 1 = FLOAT (fval). */
 typedef struct {
     int64_t len, cap, pos;

@@ -1,0 +1,630 @@
+// C-ABI entry points (include/rrrmc_b200.h): handle management, host-side graph logic, drivers.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <set>
+#include "common.cuh"
+#include "kernels.cuh"
+#include "chain.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void rrrmc_set_error(const char *fmt, ...)
+{
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *rrrmc_last_error(void) { return g_err; }
+extern "C" const char *rrrmc_version(void) { return "rrrmc_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" rrrmc_status_t rrrmc_ctx_create(int device, void *cuda_stream, rrrmc_ctx_t **out)
+{
+    RR_ARG(out != nullptr, "rrrmc_ctx_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        rrrmc_set_error("rrrmc_ctx_create: no CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(e));
+        return RRRMC_ERR_CUDA;
+    }
+    RR_ARG(device >= 0 && device < ndev, "rrrmc_ctx_create: device %d out of range (0..%d)", device, ndev - 1);
+    RR_CUDA(cudaSetDevice(device));
+    rrrmc_ctx *c = new rrrmc_ctx();
+    c->device = device;
+    if (cuda_stream) c->stream = (cudaStream_t)cuda_stream;
+    else { RR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    RR_CUDA(cudaEventCreate(&c->ev0));
+    RR_CUDA(cudaEventCreate(&c->ev1));
+    RR_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    *out = c;
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_ctx_destroy(rrrmc_ctx_t *c)
+{
+    if (!c) return RRRMC_OK;
+    cudaSetDevice(c->device);
+    if (c->flush_buf) cudaFree(c->flush_buf);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_ctx_sync(rrrmc_ctx_t *c)
+{
+    RR_ARG(c, "ctx is NULL");
+    RR_CUDA(cudaStreamSynchronize(c->stream));
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_ctx_timer_start(rrrmc_ctx_t *c)
+{
+    RR_ARG(c, "ctx is NULL");
+    RR_CUDA(cudaEventRecord(c->ev0, c->stream));
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_ctx_timer_stop(rrrmc_ctx_t *c, float *ms)
+{
+    RR_ARG(c && ms, "ctx/ms is NULL");
+    RR_CUDA(cudaEventRecord(c->ev1, c->stream));
+    RR_CUDA(cudaEventSynchronize(c->ev1));
+    RR_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_ctx_launch_count(rrrmc_ctx_t *c, uint64_t *count)
+{
+    RR_ARG(c && count, "ctx/count is NULL");
+    *count = c->launches;
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_ctx_flush_l2(rrrmc_ctx_t *c)
+{
+    RR_ARG(c, "ctx is NULL");
+    RR_CUDA(cudaSetDevice(c->device));
+    if (!c->flush_buf) {
+        c->flush_bytes = (size_t)256 << 20; // 2x the 126 MB L2
+        RR_CUDA(cudaMalloc(&c->flush_buf, c->flush_bytes));
+    }
+    return launch_flush(c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// EA lattice host logic
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct nb_slot { int64_t site; int code; }; // code = 2d (own forward bond) or 2d+1 (bond owned by the i-e_d neighbour)
+
+// neighbours of 0-based site i in the reference's slot order: ascending index (EA.jl:40); for L=2 the
+// two bonds to the same neighbour are ordered "lower site's forward bond first" (gen_J fill order, EA.jl:50-59)
+void lattice_slots(int L, int D, int64_t i, nb_slot *out)
+{
+    int64_t stride = 1, rem = i;
+    for (int d = 0; d < D; d++) {
+        const int64_t c = rem % L; rem /= L;
+        const int64_t up = i + ((c + 1 == L ? 0 : c + 1) - c) * stride;
+        const int64_t dn = i + ((c == 0 ? L - 1 : c - 1) - c) * stride;
+        out[2 * d] = { up, 2 * d };
+        out[2 * d + 1] = { dn, 2 * d + 1 };
+        stride *= L;
+    }
+    std::stable_sort(out, out + 2 * D, [i](const nb_slot &a, const nb_slot &b) {
+        if (a.site != b.site) return a.site < b.site;
+        const bool a_first = (a.code & 1) == (i < a.site ? 0 : 1); // i<nbr: own forward first; else the other's
+        const bool b_first = (b.code & 1) == (i < b.site ? 0 : 1);
+        return a_first && !b_first;
+    });
+}
+int64_t ipow(int64_t b, int e) { int64_t r = 1; while (e-- > 0) r *= b; return r; }
+} // namespace
+
+extern "C" rrrmc_status_t rrrmc_gen_ea_adjacency(int L, int D, int64_t *A_out)
+{
+    RR_ARG(L >= 2, "L must be >= 2, given: %d", L);   // EA.jl:25
+    RR_ARG(D >= 1 && D <= 8, "D must be in 1..8, given: %d", D);
+    RR_ARG(A_out, "A_out is NULL");
+    const int64_t N = ipow(L, D);
+    nb_slot sl[16];
+    for (int64_t i = 0; i < N; i++) {
+        lattice_slots(L, D, i, sl);
+        for (int k = 0; k < 2 * D; k++) A_out[i * 2 * D + k] = sl[k].site + 1;
+    }
+    return RRRMC_OK;
+}
+
+extern "C" rrrmc_status_t rrrmc_graph_ea_create(rrrmc_ctx_t *ctx, int L, int D, int kind,
+                                                const int64_t *A, const void *J, rrrmc_graph_t **out)
+{
+    RR_ARG(ctx && A && J && out, "rrrmc_graph_ea_create: NULL argument");
+    RR_ARG(L >= 2, "L must be >= 2, given: %d", L);
+    RR_ARG(D >= 1 && D <= 4, "D must be in 1..4, given: %d", D);
+    RR_ARG(kind == RRRMC_EA_PM1 || kind == RRRMC_EA_INT || kind == RRRMC_EA_F64, "unknown coupling kind %d", kind);
+    const int twoD = 2 * D;
+    const int64_t N = ipow(L, D);
+    RR_ARG(N >= 2 && N < ((int64_t)1 << 31), "N = L^D = %lld out of range", (long long)N);
+    rrrmc_graph *g = new rrrmc_graph();
+    g->ctx = ctx; g->kind = kind; g->L = L; g->D = D; g->twoD = twoD; g->N = N;
+    g->bipartite = (L % 2 == 0);
+    g->A0.resize(N * twoD);
+    std::vector<int8_t> code(N * twoD);
+    nb_slot sl[16];
+    for (int64_t i = 0; i < N; i++) {
+        lattice_slots(L, D, i, sl);
+        for (int k = 0; k < twoD; k++) {
+            if (A[i * twoD + k] != sl[k].site + 1) {
+                rrrmc_set_error("invalid A, does not look like an EA graph: A[%lld][%d] = %lld, expected %lld",
+                                (long long)i + 1, k + 1, (long long)A[i * twoD + k], (long long)sl[k].site + 1);
+                delete g; return RRRMC_ERR_ARG;
+            }
+            g->A0[i * twoD + k] = (int32_t)sl[k].site;
+            code[i * twoD + k] = (int8_t)sl[k].code;
+        }
+    }
+    // unique neighbours (EA.jl:158, :548)
+    g->uA0.resize(N * twoD); g->nuA.resize(N);
+    for (int64_t i = 0; i < N; i++) {
+        int n = 0;
+        for (int k = 0; k < twoD; k++) {
+            const int32_t y = g->A0[i * twoD + k];
+            if (n == 0 || g->uA0[i * twoD + n - 1] != y) g->uA0[i * twoD + n++] = y;
+        }
+        g->nuA[i] = n;
+    }
+    // couplings, slot-aligned with A; symmetry check through the (site, bond) codes
+    if (kind == RRRMC_EA_F64) g->Jd.assign((const double *)J, (const double *)J + N * twoD);
+    else g->Ji.assign((const int64_t *)J, (const int64_t *)J + N * twoD);
+    auto Jat = [&](int64_t idx) { return kind == RRRMC_EA_F64 ? g->Jd[idx] : (double)g->Ji[idx]; };
+    for (int64_t i = 0; i < N; i++)
+        for (int k = 0; k < twoD; k++) {
+            const int c = code[i * twoD + k];
+            if (c & 1) continue;                       // own forward bond (i -> up); find it at the other end
+            const int64_t up = g->A0[i * twoD + k];
+            int l = -1;
+            for (int m = 0; m < twoD; m++) if (g->A0[up * twoD + m] == i && code[up * twoD + m] == (c | 1)) l = m;
+            if (l < 0 || Jat(i * twoD + k) != Jat(up * twoD + l)) {
+                rrrmc_set_error("J is not symmetric at bond (%lld,%lld)", (long long)i + 1, (long long)up + 1);
+                delete g; return RRRMC_ERR_ARG;
+            }
+        }
+    std::set<int64_t> levels;
+    if (kind != RRRMC_EA_F64) {
+        for (int64_t v : g->Ji) {
+            if (kind == RRRMC_EA_PM1 && v != 1 && v != -1) {
+                rrrmc_set_error("the given J is incompatible with levels (-1, 1): found %lld", (long long)v);
+                delete g; return RRRMC_ERR_ARG;
+            }
+            if (v < -127 || v > 127) { rrrmc_set_error("integer couplings must fit int8, found %lld", (long long)v); delete g; return RRRMC_ERR_ARG; }
+            levels.insert(v);
+        }
+        // allΔE (EA.jl:293-309): all sums of 2D signed levels
+        std::set<int64_t> es = { 0 };
+        if (kind == RRRMC_EA_PM1) levels = { -1, 1 };
+        for (int n = 0; n < twoD; n++) {
+            std::set<int64_t> nw;
+            for (int64_t e : es) for (int64_t l : levels) { nw.insert(e + l); nw.insert(e - l); }
+            es.swap(nw);
+        }
+        std::set<int64_t> de;
+        for (int64_t e : es) de.insert(2 * (e < 0 ? -e : e));
+        for (int64_t d : de) g->allDE.push_back((double)d);
+        if (g->allDE.size() > 64) { rrrmc_set_error("too many ΔE classes (%zu > 64)", g->allDE.size()); delete g; return RRRMC_ERR_UNSUPPORTED; }
+    }
+    // device copies
+    RR_CUDA(cudaSetDevice(ctx->device));
+    RR_CUDA(cudaMalloc(&g->d_A, sizeof(int32_t) * N * twoD));
+    RR_CUDA(cudaMemcpy(g->d_A, g->A0.data(), sizeof(int32_t) * N * twoD, cudaMemcpyHostToDevice));
+    if (kind == RRRMC_EA_F64) {
+        RR_CUDA(cudaMalloc(&g->d_Jd, sizeof(double) * N * twoD));
+        RR_CUDA(cudaMemcpy(g->d_Jd, g->Jd.data(), sizeof(double) * N * twoD, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<int8_t> j8(N * twoD);
+        for (int64_t k = 0; k < N * twoD; k++) j8[k] = (int8_t)g->Ji[k];
+        RR_CUDA(cudaMalloc(&g->d_J8, N * twoD));
+        RR_CUDA(cudaMemcpy(g->d_J8, j8.data(), N * twoD, cudaMemcpyHostToDevice));
+    }
+    if (kind == RRRMC_EA_PM1 && D <= 3) {
+        std::vector<uint8_t> jc(N, 0);
+        for (int64_t i = 0; i < N; i++)
+            for (int k = 0; k < twoD; k++)
+                if (g->Ji[i * twoD + k] < 0) jc[i] |= (uint8_t)(1u << code[i * twoD + k]);
+        RR_CUDA(cudaMalloc(&g->d_jcode, N));
+        RR_CUDA(cudaMemcpy(g->d_jcode, jc.data(), N, cudaMemcpyHostToDevice));
+    }
+    *out = g;
+    return RRRMC_OK;
+}
+
+extern "C" rrrmc_status_t rrrmc_graph_destroy(rrrmc_graph_t *g)
+{
+    if (!g) return RRRMC_OK;
+    cudaSetDevice(g->ctx->device);
+    cudaFree(g->d_jcode); cudaFree(g->d_A); cudaFree(g->d_J8); cudaFree(g->d_Jd);
+    delete g;
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_getN(const rrrmc_graph_t *g, int64_t *N)
+{
+    RR_ARG(g && N, "NULL argument");
+    *N = g->N;
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_neighbors(const rrrmc_graph_t *g, int64_t site, int64_t *out, int *n)
+{
+    RR_ARG(g && out && n, "NULL argument");
+    RR_ARG(site >= 1 && site <= g->N, "site %lld out of range 1..%lld", (long long)site, (long long)g->N);
+    *n = g->nuA[site - 1];
+    for (int k = 0; k < *n; k++) out[k] = g->uA0[(site - 1) * g->twoD + k] + 1;
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_allDE(const rrrmc_graph_t *g, double *out, int *n)
+{
+    RR_ARG(g && out && n, "NULL argument");
+    if (g->allDE.empty()) { rrrmc_set_error("allΔE is only defined for DiscrGraph types"); return RRRMC_ERR_UNSUPPORTED; }
+    *n = (int)g->allDE.size();
+    for (int k = 0; k < *n; k++) out[k] = g->allDE[k];
+    return RRRMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// state
+// ------------------------------------------------------------------------------------------------
+extern "C" rrrmc_status_t rrrmc_state_create(rrrmc_graph_t *g, int64_t R, rrrmc_state_t **out)
+{
+    RR_ARG(g && out, "NULL argument");
+    RR_ARG(R >= 1 && R <= ((int64_t)1 << 24), "n_replicas %lld out of range", (long long)R);
+    rrrmc_state *s = new rrrmc_state();
+    s->g = g; s->R = R; s->W = (R + 31) / 32; s->nchunks = (g->N + 63) / 64;
+    RR_CUDA(cudaSetDevice(g->ctx->device));
+    RR_CUDA(cudaMalloc(&s->d_spins, sizeof(uint32_t) * g->N * s->W));
+    RR_CUDA(cudaMemsetAsync(s->d_spins, 0, sizeof(uint32_t) * g->N * s->W, g->ctx->stream));
+    s->ibuf_len = std::max<int64_t>(g->N, s->W * 32);
+    RR_CUDA(cudaMalloc(&s->d_ibuf, sizeof(int32_t) * s->ibuf_len));
+    RR_CUDA(cudaMalloc(&s->d_acc, sizeof(long long) * s->W * 32));
+    *out = s;
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_state_destroy(rrrmc_state_t *s)
+{
+    if (!s) return RRRMC_OK;
+    cudaSetDevice(s->g->ctx->device);
+    cudaStreamSynchronize(s->g->ctx->stream);
+    cudaFree(s->d_spins); cudaFree(s->d_chunks); cudaFree(s->d_ibuf); cudaFree(s->d_acc);
+    cudaFree(s->d_flips); cudaFree(s->d_mask);
+    chain_free(s);
+    delete s;
+    return RRRMC_OK;
+}
+static rrrmc_status_t ensure_chunks(rrrmc_state *s)
+{
+    if (!s->d_chunks) RR_CUDA(cudaMalloc(&s->d_chunks, sizeof(uint64_t) * s->R * s->nchunks));
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_state_randomize(rrrmc_state_t *s, uint64_t seed)
+{
+    RR_ARG(s, "state is NULL");
+    RR_CUDA(cudaSetDevice(s->g->ctx->device));
+    s->energy_valid = false; s->chain_valid = false;
+    return launch_randomize(s, seed);
+}
+extern "C" rrrmc_status_t rrrmc_state_upload(rrrmc_state_t *s, int64_t first, int64_t count, const uint64_t *chunks)
+{
+    RR_ARG(s && chunks, "NULL argument");
+    RR_ARG(first >= 0 && count >= 1 && first + count <= s->R, "replica range [%lld,%lld) outside 0..%lld",
+           (long long)first, (long long)(first + count), (long long)s->R);
+    rrrmc_ctx *ctx = s->g->ctx;
+    RR_CUDA(cudaSetDevice(ctx->device));
+    RR_TRY(ensure_chunks(s));
+    RR_TRY(chain_sync_to_multispin(s));
+    RR_CUDA(cudaMemcpyAsync(s->d_chunks, chunks, sizeof(uint64_t) * count * s->nchunks, cudaMemcpyHostToDevice, ctx->stream));
+    RR_TRY(launch_upload_transpose(s, first, count));
+    RR_CUDA(cudaStreamSynchronize(ctx->stream)); // the caller may free `chunks` on return
+    s->energy_valid = false; s->chain_valid = false;
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_state_download(rrrmc_state_t *s, int64_t first, int64_t count, uint64_t *chunks)
+{
+    RR_ARG(s && chunks, "NULL argument");
+    RR_ARG(first >= 0 && count >= 1 && first + count <= s->R, "replica range [%lld,%lld) outside 0..%lld",
+           (long long)first, (long long)(first + count), (long long)s->R);
+    rrrmc_ctx *ctx = s->g->ctx;
+    RR_CUDA(cudaSetDevice(ctx->device));
+    RR_TRY(ensure_chunks(s));
+    RR_TRY(chain_sync_to_multispin(s));
+    RR_TRY(launch_download_transpose(s, first, count));
+    RR_CUDA(cudaMemcpyAsync(chunks, s->d_chunks, sizeof(uint64_t) * count * s->nchunks, cudaMemcpyDeviceToHost, ctx->stream));
+    RR_CUDA(cudaStreamSynchronize(ctx->stream));
+    s->chain_valid = (first == 0 && count == s->R); // d_chunks doubles as the chain layout
+    return RRRMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Interface queries
+// ------------------------------------------------------------------------------------------------
+static rrrmc_status_t energy_to_host(rrrmc_state *s, double *E_out)
+{
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    if (g->kind == RRRMC_EA_PM1 && g->d_jcode) {
+        RR_TRY(launch_energy_pm1(s, s->d_ibuf));
+        std::vector<int> h(s->W * 32);
+        RR_CUDA(cudaMemcpyAsync(h.data(), s->d_ibuf, sizeof(int) * s->W * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        RR_CUDA(cudaStreamSynchronize(ctx->stream));
+        const double base = -(double)g->D * (double)g->N;
+        for (int64_t r = 0; r < s->R; r++) E_out[r] = base + 2.0 * (double)h[r];
+        return RRRMC_OK;
+    }
+    return chain_energy(s, E_out);
+}
+extern "C" rrrmc_status_t rrrmc_energy(rrrmc_state_t *s, double *E_out)
+{
+    RR_ARG(s && E_out, "NULL argument");
+    RR_CUDA(cudaSetDevice(s->g->ctx->device));
+    RR_TRY(chain_sync_to_multispin(s));
+    RR_TRY(energy_to_host(s, E_out));
+    s->energy_valid = true;
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_delta_energy(rrrmc_state_t *s, int64_t site, double *dE_out)
+{
+    RR_ARG(s && dE_out, "NULL argument");
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    RR_ARG(site >= 1 && site <= g->N, "site %lld out of range 1..%lld", (long long)site, (long long)g->N);
+    RR_CUDA(cudaSetDevice(ctx->device));
+    RR_TRY(chain_sync_to_multispin(s));
+    if (g->kind == RRRMC_EA_PM1 && g->d_jcode) {
+        RR_TRY(launch_delta_energy_site(s, site - 1, s->d_ibuf));
+        std::vector<int> h(s->W * 32);
+        RR_CUDA(cudaMemcpyAsync(h.data(), s->d_ibuf, sizeof(int) * s->W * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        RR_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int64_t r = 0; r < s->R; r++) dE_out[r] = (double)h[r];
+        return RRRMC_OK;
+    }
+    return chain_delta_energy_site(s, site - 1, dE_out);
+}
+extern "C" rrrmc_status_t rrrmc_all_delta_energy(rrrmc_state_t *s, int64_t replica, double *dE_out)
+{
+    RR_ARG(s && dE_out, "NULL argument");
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    RR_ARG(replica >= 0 && replica < s->R, "replica %lld out of range 0..%lld", (long long)replica, (long long)s->R - 1);
+    RR_CUDA(cudaSetDevice(ctx->device));
+    RR_TRY(chain_sync_to_multispin(s));
+    if (g->kind == RRRMC_EA_PM1 && g->d_jcode) {
+        RR_TRY(launch_delta_energy_replica(s, replica, s->d_ibuf));
+        std::vector<int> h(g->N);
+        RR_CUDA(cudaMemcpyAsync(h.data(), s->d_ibuf, sizeof(int) * g->N, cudaMemcpyDeviceToHost, ctx->stream));
+        RR_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int64_t i = 0; i < g->N; i++) dE_out[i] = (double)h[i];
+        return RRRMC_OK;
+    }
+    return chain_delta_energy_replica(s, replica, dE_out);
+}
+extern "C" rrrmc_status_t rrrmc_spinflip(rrrmc_state_t *s, int64_t site, const uint32_t *replica_mask)
+{
+    RR_ARG(s, "state is NULL");
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    RR_ARG(site >= 1 && site <= g->N, "site %lld out of range 1..%lld", (long long)site, (long long)g->N);
+    RR_CUDA(cudaSetDevice(ctx->device));
+    RR_TRY(chain_sync_to_multispin(s));
+    const uint32_t *d_mask = nullptr;
+    if (replica_mask) {
+        if (!s->d_mask) RR_CUDA(cudaMalloc(&s->d_mask, sizeof(uint32_t) * s->W));
+        RR_CUDA(cudaMemcpyAsync(s->d_mask, replica_mask, sizeof(uint32_t) * s->W, cudaMemcpyHostToDevice, ctx->stream));
+        d_mask = s->d_mask;
+    }
+    RR_TRY(launch_flip_site(s, site - 1, d_mask));
+    RR_CUDA(cudaStreamSynchronize(ctx->stream));
+    s->chain_valid = false;
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_magnetization(rrrmc_state_t *s, double *m_out)
+{
+    RR_ARG(s && m_out, "NULL argument");
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    RR_CUDA(cudaSetDevice(ctx->device));
+    RR_TRY(chain_sync_to_multispin(s));
+    RR_CUDA(cudaMemsetAsync(s->d_acc, 0, sizeof(long long) * s->W * 32, ctx->stream));
+    RR_TRY(launch_count_lanes(ctx, s->d_spins, g->N, (int)s->W, s->d_acc));
+    std::vector<long long> h(s->W * 32);
+    RR_CUDA(cudaMemcpyAsync(h.data(), s->d_acc, sizeof(long long) * s->W * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    RR_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int64_t r = 0; r < s->R; r++) m_out[r] = 2.0 * (double)h[r] - (double)g->N;
+    return RRRMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// samplers
+// ------------------------------------------------------------------------------------------------
+extern "C" rrrmc_status_t rrrmc_opts_default(rrrmc_opts_t *o)
+{
+    RR_ARG(o, "opts is NULL");
+    memset(o, 0, sizeof *o);
+    o->schedule = RRRMC_SCHED_CHECKERBOARD;
+    o->planes_K = 6;
+    o->count_accepted = 1;
+    o->staged_thr = NAN;
+    o->staged_thr_fact = 5.0;
+    return RRRMC_OK;
+}
+
+static uint64_t fixed64(double p) // floor(p * 2^64) clamped to 2^64-1, p in [0,1]
+{
+    if (!(p > 0)) return 0;
+    const double v = ldexp(p, 64);
+    if (v >= 18446744073709551616.0) return ~0ull;
+    return (uint64_t)v;
+}
+
+static rrrmc_status_t fill_cb_params(rrrmc_state *s, const uint64_t *thr64, int nthr, int K, uint64_t seed, cb_params &p)
+{
+    rrrmc_graph *g = s->g;
+    if (!(g->kind == RRRMC_EA_PM1 && g->d_jcode)) {
+        rrrmc_set_error("checkerboard sweeps need a ±J GraphEA with D<=3");
+        return RRRMC_ERR_UNSUPPORTED;
+    }
+    if (!g->bipartite) {
+        rrrmc_set_error("checkerboard sweeps need even L (a two-colourable lattice), given L=%d; use schedule=RANDOM_SITE", g->L);
+        return RRRMC_ERR_UNSUPPORTED;
+    }
+    RR_ARG(nthr == g->D, "expected %d acceptance thresholds (ΔE=4..%d), given %d", g->D, 4 * g->D, nthr);
+    RR_ARG(K >= 0 && K <= CB_MAXK, "planes_K must be in 0..%d, given %d", CB_MAXK, K);
+    memset(&p, 0, sizeof p);
+    p.spins = s->d_spins; p.flips = nullptr; p.jcode = g->d_jcode;
+    p.L = g->L; p.Lh = g->L / 2; p.W = (int)s->W; p.G = (int)((s->W + 3) / 4);
+    p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32);
+    p.K = K;
+    for (int c = 0; c < nthr; c++) {
+        for (int q = 0; q < K; q++) p.plane[q][c] = ((thr64[c] >> (63 - q)) & 1ull) ? 0xffffffffu : 0u;
+        p.rem[c] = (uint32_t)((K ? (thr64[c] << K) : thr64[c]) >> 32);
+    }
+    return RRRMC_OK;
+}
+
+static rrrmc_status_t run_sweep(rrrmc_state *s, cb_params &p, uint64_t t)
+{
+    rrrmc_graph *g = s->g;
+    p.t_lo = (uint32_t)t; p.t_hi16 = (uint32_t)(t >> 32) << 16;
+    RR_TRY(launch_checkerboard(g->ctx, p, g->D, 0));
+    RR_TRY(launch_checkerboard(g->ctx, p, g->D, 1));
+    return RRRMC_OK;
+}
+
+extern "C" rrrmc_status_t rrrmc_checkerboard_sweeps(rrrmc_state_t *s, const uint64_t *thr64, int nthr, int K,
+                                                    uint64_t seed, uint64_t sweep0, int64_t nsweeps)
+{
+    RR_ARG(s && thr64, "NULL argument");
+    RR_ARG(nsweeps >= 0, "nsweeps must be >= 0");
+    RR_CUDA(cudaSetDevice(s->g->ctx->device));
+    RR_TRY(chain_sync_to_multispin(s));
+    cb_params p;
+    RR_TRY(fill_cb_params(s, thr64, nthr, K, seed, p));
+    for (int64_t k = 0; k < nsweeps; k++) RR_TRY(run_sweep(s, p, sweep0 + (uint64_t)k));
+    s->energy_valid = false; s->chain_valid = false;
+    return RRRMC_OK;
+}
+
+static rrrmc_status_t uniform_beta(const rrrmc_state *s, const double *beta, double *b)
+{
+    RR_ARG(beta, "beta is NULL");
+    for (int64_t r = 0; r < s->R; r++) {
+        RR_ARG(std::isfinite(beta[r]) && beta[r] >= 0, "β must be finite and >= 0, given: %g (replica %lld)", beta[r], (long long)r);
+        if (beta[r] != beta[0]) {
+            rrrmc_set_error("per-replica β ladders are not implemented for this sampler yet (replica %lld differs)", (long long)r);
+            return RRRMC_ERR_UNSUPPORTED;
+        }
+    }
+    *b = beta[0];
+    return RRRMC_OK;
+}
+
+static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int64_t iters, int64_t step, uint64_t seed,
+                                               rrrmc_hook_fn hook, void *user, const rrrmc_opts_t *o,
+                                               double *Es, int64_t Es_cap, rrrmc_run_info_t *info)
+{
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    RR_TRY(chain_sync_to_multispin(s));
+    uint64_t thr[3];
+    for (int c = 1; c <= g->D; c++) thr[c - 1] = fixed64(exp(-beta * 4.0 * c));
+    cb_params p;
+    RR_TRY(fill_cb_params(s, thr, g->D, o->planes_K, seed, p));
+    const int64_t N = g->N;
+    const int64_t nsweeps = (iters + N - 1) / N, step_sw = std::max<int64_t>(1, (step + N - 1) / N);
+    const bool count = o->count_accepted != 0;
+    if (count) {
+        if (!s->d_flips) RR_CUDA(cudaMalloc(&s->d_flips, sizeof(uint32_t) * N * s->W));
+        p.flips = s->d_flips;
+        RR_CUDA(cudaMemsetAsync(s->d_acc, 0, sizeof(long long) * s->W * 32, ctx->stream));
+    }
+    const uint64_t l0 = ctx->launches;
+    std::vector<double> E(s->R);
+    std::vector<long long> acc_h(s->W * 32);
+    std::vector<int64_t> acc(s->R, -1);
+    int64_t nsamples = 0, done = 0;
+    cudaEvent_t e0, e1;
+    RR_CUDA(cudaEventCreate(&e0)); RR_CUDA(cudaEventCreate(&e1));
+    RR_CUDA(cudaEventRecord(e0, ctx->stream));
+    for (int64_t sw = 1; sw <= nsweeps; sw++) {
+        RR_TRY(run_sweep(s, p, (uint64_t)(sw - 1)));
+        if (count) RR_TRY(launch_count_lanes(ctx, s->d_flips, N, (int)s->W, s->d_acc));
+        done = sw;
+        if (sw % step_sw == 0 && (hook || (Es && nsamples < Es_cap))) {
+            RR_TRY(energy_to_host(s, E.data()));
+            if (count) {
+                RR_CUDA(cudaMemcpyAsync(acc_h.data(), s->d_acc, sizeof(long long) * s->W * 32, cudaMemcpyDeviceToHost, ctx->stream));
+                RR_CUDA(cudaStreamSynchronize(ctx->stream));
+                for (int64_t r = 0; r < s->R; r++) acc[r] = acc_h[r];
+            }
+            if (Es && nsamples < Es_cap) memcpy(Es + nsamples * s->R, E.data(), sizeof(double) * s->R);
+            nsamples++;
+            if (hook && !hook(user, sw * N, E.data(), acc.data(), s->R)) break;
+        }
+    }
+    RR_CUDA(cudaEventRecord(e1, ctx->stream));
+    RR_CUDA(cudaEventSynchronize(e1));
+    float ms = 0; RR_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    s->energy_valid = false; s->chain_valid = false;
+    if (info) { info->nsamples = std::min(nsamples, Es ? Es_cap : nsamples); info->iters_done = done * N; info->launches = (int64_t)(ctx->launches - l0); info->device_ms = ms; }
+    return RRRMC_OK;
+}
+
+extern "C" rrrmc_status_t rrrmc_standard_mc(rrrmc_state_t *s, const double *beta, int64_t iters, int64_t step, uint64_t seed,
+                                            rrrmc_hook_fn hook, void *user, const rrrmc_opts_t *opts,
+                                            double *Es, int64_t Es_cap, rrrmc_run_info_t *info)
+{
+    RR_ARG(s, "state is NULL");
+    RR_ARG(iters >= 0, "iters must be >= 0, given %lld", (long long)iters);
+    RR_ARG(step >= 1, "step must be >= 1, given %lld", (long long)step);
+    rrrmc_opts_t o;
+    if (opts) o = *opts; else rrrmc_opts_default(&o);
+    RR_CUDA(cudaSetDevice(s->g->ctx->device));
+    if (info) memset(info, 0, sizeof *info);
+    if (o.schedule == RRRMC_SCHED_CHECKERBOARD) {
+        double b; RR_TRY(uniform_beta(s, beta, &b));
+        return standard_mc_checkerboard(s, b, iters, step, seed, hook, user, &o, Es, Es_cap, info);
+    }
+    if (o.schedule == RRRMC_SCHED_RANDOM_SITE)
+        return chain_run(s, CHAIN_STANDARD, beta, iters, step, seed, hook, user, &o, Es, Es_cap, info);
+    rrrmc_set_error("unknown schedule %d", o.schedule);
+    return RRRMC_ERR_ARG;
+}
+
+extern "C" rrrmc_status_t rrrmc_rrr_mc(rrrmc_state_t *s, const double *beta, int64_t iters, int64_t step, uint64_t seed,
+                                       rrrmc_hook_fn hook, void *user, const rrrmc_opts_t *opts,
+                                       double *Es, int64_t Es_cap, rrrmc_run_info_t *info)
+{
+    RR_ARG(s, "state is NULL");
+    RR_ARG(iters >= 0 && step >= 1, "iters must be >= 0 and step >= 1");
+    rrrmc_opts_t o;
+    if (opts) o = *opts; else rrrmc_opts_default(&o);
+    RR_CUDA(cudaSetDevice(s->g->ctx->device));
+    if (info) memset(info, 0, sizeof *info);
+    return chain_run(s, CHAIN_RRR, beta, iters, step, seed, hook, user, &o, Es, Es_cap, info);
+}
+extern "C" rrrmc_status_t rrrmc_bkl_mc(rrrmc_state_t *s, const double *beta, int64_t iters, int64_t step, uint64_t seed,
+                                       rrrmc_hook_fn hook, void *user, const rrrmc_opts_t *opts,
+                                       double *Es, int64_t Es_cap, rrrmc_run_info_t *info)
+{
+    RR_ARG(s, "state is NULL");
+    RR_ARG(iters >= 0 && step >= 1, "iters must be >= 0 and step >= 1");
+    rrrmc_opts_t o;
+    if (opts) o = *opts; else rrrmc_opts_default(&o);
+    RR_CUDA(cudaSetDevice(s->g->ctx->device));
+    if (info) memset(info, 0, sizeof *info);
+    return chain_run(s, CHAIN_BKL, beta, iters, step, seed, hook, user, &o, Es, Es_cap, info);
+}
+extern "C" rrrmc_status_t rrrmc_replay(rrrmc_state_t *s, int64_t replica, int sampler, double beta, int64_t iters, int64_t step,
+                                       const uint8_t *kind, const int64_t *ival, const double *fval, int64_t ndraws,
+                                       const rrrmc_opts_t *opts, double *Es, int64_t Es_cap, rrrmc_run_info_t *info)
+{
+    RR_ARG(s && kind && ival && fval, "NULL argument");
+    RR_ARG(replica >= 0 && replica < s->R, "replica out of range");
+    RR_ARG(sampler >= 0 && sampler <= 2, "sampler must be 0 (standardMC), 1 (rrrMC) or 2 (bklMC)");
+    rrrmc_opts_t o;
+    if (opts) o = *opts; else rrrmc_opts_default(&o);
+    RR_CUDA(cudaSetDevice(s->g->ctx->device));
+    if (info) memset(info, 0, sizeof *info);
+    return chain_replay(s, replica, sampler, beta, iters, step, kind, ival, fval, ndraws, &o, Es, Es_cap, info);
+}

@@ -1,0 +1,18 @@
+// Sequential ("one Markov chain = one lane") samplers: the reference's standardMC / rrrMC / bklMC loops
+// (src/RRRMC.jl:81-359) executed per replica with the reference's data structures in HBM.
+#pragma once
+#include "common.cuh"
+
+enum { CHAIN_STANDARD = 0, CHAIN_RRR = 1, CHAIN_BKL = 2 };
+
+void chain_free(rrrmc_state *s);
+rrrmc_status_t chain_sync_to_multispin(rrrmc_state *s);   // make the multispin copy current
+rrrmc_status_t chain_sync_from_multispin(rrrmc_state *s); // make the chain copy (d_chunks) current
+rrrmc_status_t chain_energy(rrrmc_state *s, double *E_out);
+rrrmc_status_t chain_delta_energy_site(rrrmc_state *s, int64_t site0, double *out);
+rrrmc_status_t chain_delta_energy_replica(rrrmc_state *s, int64_t replica, double *out);
+rrrmc_status_t chain_run(rrrmc_state *s, int sampler, const double *beta, int64_t iters, int64_t step, uint64_t seed,
+                         rrrmc_hook_fn hook, void *user, const rrrmc_opts_t *o, double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
+rrrmc_status_t chain_replay(rrrmc_state *s, int64_t replica, int sampler, double beta, int64_t iters, int64_t step,
+                            const uint8_t *kind, const int64_t *ival, const double *fval, int64_t ndraws,
+                            const rrrmc_opts_t *o, double *Es, int64_t Es_cap, rrrmc_run_info_t *info);

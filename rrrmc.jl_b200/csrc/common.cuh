@@ -1,0 +1,73 @@
+// Shared declarations of the engine: handles, error plumbing, launch bookkeeping.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/rrrmc_b200.h"
+
+void rrrmc_set_error(const char *fmt, ...);
+
+#define RR_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            rrrmc_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return RRRMC_ERR_CUDA;                                                            \
+        }                                                                                     \
+    } while (0)
+#define RR_ARG(cond, ...)                                                                     \
+    do { if (!(cond)) { rrrmc_set_error(__VA_ARGS__); return RRRMC_ERR_ARG; } } while (0)
+#define RR_TRY(call) do { rrrmc_status_t s__ = (call); if (s__ != RRRMC_OK) return s__; } while (0)
+
+struct rrrmc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0;
+    uint64_t launches = 0;
+    void *flush_buf = nullptr;
+    size_t flush_bytes = 0;
+};
+
+struct rrrmc_graph {
+    rrrmc_ctx *ctx = nullptr;
+    int kind = 0;
+    int L = 0, D = 0, twoD = 0;
+    int64_t N = 0;
+    bool bipartite = false;          // even L >= 4: two-colour sweeps are valid
+    std::vector<int32_t> A0;         // [N*twoD] 0-based neighbours, reference slot order
+    std::vector<int32_t> uA0;        // unique neighbours per site (EA.jl:158)
+    std::vector<int> nuA;
+    std::vector<int64_t> Ji;         // [N*twoD] (PM1/INT)
+    std::vector<double> Jd;          // [N*twoD] (F64)
+    std::vector<double> allDE;
+    // device
+    uint8_t *d_jcode = nullptr;      // PM1 lattice: bit 2d = J(i -> i+e_d) < 0, bit 2d+1 = J(i-e_d -> i) < 0
+    int32_t *d_A = nullptr;          // [N*twoD]
+    int8_t *d_J8 = nullptr;          // [N*twoD] (PM1/INT)
+    double *d_Jd = nullptr;          // [N*twoD] (F64)
+};
+
+struct rrrmc_state {
+    rrrmc_graph *g = nullptr;
+    int64_t R = 0;                   // replicas
+    int64_t W = 0;                   // 32-replica words per site (R padded up)
+    uint32_t *d_spins = nullptr;     // multispin layout: [N][W], site-major, replica-minor
+    // scratch
+    uint64_t *d_chunks = nullptr;    // [R][nchunks] staging in the reference BitVector layout
+    int64_t nchunks = 0;
+    int32_t *d_ibuf = nullptr;       // [max(N, W*32)] integer scratch (energies, ΔE)
+    int64_t ibuf_len = 0;
+    long long *d_acc = nullptr;      // [W*32] accepted counters
+    uint32_t *d_flips = nullptr;     // [N][W] accept masks of the last sweep (count_accepted)
+    uint32_t *d_mask = nullptr;      // [W] replica mask staging
+    bool energy_valid = false;
+    // chain layout (sequential samplers): d_chunks is the spin state, one BitVector per chain
+    bool ms_valid = true;            // multispin copy is current
+    bool chain_valid = false;        // d_chunks copy is current
+    struct chain_store *chain = nullptr;
+};
+
+static inline unsigned div_up(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }

@@ -1,0 +1,481 @@
+// Multispin (bit-packed over replicas) kernels for GraphEA ±J on the periodic hyper-cubic lattice.
+//
+// Layout in HBM: spins[N][W] uint32, site-major / replica-minor; bit b of word w of site i is the
+// spin s∈{0,1} of replica 32w+b (σ=2s-1, Interface.jl:34-37); site i = x + L*y + L*L*z is the
+// reference's 1-based index minus one (EA.jl:31-35). One 128-bit load serves 128 replicas.
+// Couplings are shared by all replicas: jcode[i] holds the sign bits of the 2D bonds of site i.
+//
+// ΔE (EA.jl:266-275, naive form :277-289) is evaluated bit-sliced: per bond k the plane
+// b_k = s_i ^ s_k ^ neg_k is 1 where the bond is unsatisfied; with u = Σ_k b_k (carry-save adders),
+// ΔE = 4(D-u) ∈ {-4D..4D}, i.e. exactly -lfields[i] of the reference cache.
+#include "common.cuh"
+#include "philox.cuh"
+#include "kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// bit-sliced helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void full_add(uint32_t a, uint32_t b, uint32_t c, uint32_t &s, uint32_t &cy)
+{
+    s = a ^ b ^ c;
+    cy = (a & b) | (c & (a ^ b));
+}
+
+template <int D> struct site_geom {
+    int64_t i;            // site
+    int64_t nb[2 * D];    // neighbour sites in (d+, d-) order
+};
+
+template <int D>
+__device__ __forceinline__ site_geom<D> make_geom(int L, int x, int y, int z)
+{
+    site_geom<D> s;
+    const int64_t row = (int64_t)L * (y + (int64_t)L * z);
+    s.i = row + x;
+    s.nb[0] = row + (x + 1 == L ? 0 : x + 1);
+    s.nb[1] = row + (x == 0 ? L - 1 : x - 1);
+    if (D >= 2) {
+        s.nb[2] = s.i + (y + 1 == L ? -(int64_t)(L - 1) * L : (int64_t)L);
+        s.nb[3] = s.i + (y == 0 ? (int64_t)(L - 1) * L : -(int64_t)L);
+    }
+    if (D >= 3) {
+        const int64_t LL = (int64_t)L * L;
+        s.nb[4] = s.i + (z + 1 == L ? -(int64_t)(L - 1) * LL : LL);
+        s.nb[5] = s.i + (z == 0 ? (int64_t)(L - 1) * LL : -LL);
+    }
+    return s;
+}
+
+// number of unsatisfied bonds among the 2D bonds of a site, as bit planes (u2,u1,u0)
+template <int D>
+__device__ __forceinline__ void unsat_planes(uint32_t sc, const uint32_t (&sn)[2 * D], uint32_t jc,
+                                             uint32_t &u0, uint32_t &u1, uint32_t &u2)
+{
+    uint32_t b[2 * D];
+#pragma unroll
+    for (int k = 0; k < 2 * D; k++) {
+        const uint32_t neg = 0u - ((jc >> k) & 1u);
+        b[k] = sc ^ sn[k] ^ neg;
+    }
+    if (D == 1) { u0 = b[0] ^ b[1]; u1 = b[0] & b[1]; u2 = 0; }
+    if (D == 2) {
+        uint32_t s1, c1; full_add(b[0], b[1], b[2], s1, c1);
+        u0 = s1 ^ b[3];
+        const uint32_t c2 = s1 & b[3];
+        u1 = c1 ^ c2; u2 = c1 & c2;
+    }
+    if (D == 3) {
+        uint32_t s1, c1, s2, c2; full_add(b[0], b[1], b[2], s1, c1); full_add(b[3], b[4], b[5], s2, c2);
+        u0 = s1 ^ s2;
+        const uint32_t c3 = s1 & s2;
+        full_add(c1, c2, c3, u1, u2);
+    }
+}
+
+// class masks: mc[c-1] = lanes with ΔE = 4c > 0, i.e. u = D-c
+template <int D>
+__device__ __forceinline__ void class_masks(uint32_t u0, uint32_t u1, uint32_t u2, uint32_t (&mc)[3])
+{
+    if (D == 1) { mc[0] = ~u1 & ~u0; mc[1] = 0; mc[2] = 0; }                        // u=0
+    if (D == 2) { mc[0] = ~u2 & ~u1 & u0; mc[1] = ~u2 & ~u1 & ~u0; mc[2] = 0; }     // u=1, u=0
+    if (D == 3) { mc[0] = ~u2 & u1 & ~u0; mc[1] = ~u2 & ~u1 & u0; mc[2] = ~(u2 | u1 | u0); } // u=2,1,0
+}
+
+// ------------------------------------------------------------------------------------------------
+// Checkerboard Metropolis half-sweep. One thread = one task (site of the active colour, group of
+// 128 replicas). Acceptance is Metropolis (RRRMC.jl:39: ΔE<=0 always, else U<exp(-βΔE)) with U built
+// from Philox bit planes — procedure documented in DESIGN.md §"Random bits" and restated on the CPU
+// in oracle/rrrmc_oracle.c:orc_checkerboard_sweeps (the two must agree bit for bit).
+// ------------------------------------------------------------------------------------------------
+template <int D, bool FULL>
+__global__ void __launch_bounds__(256) k_checkerboard(cb_params p, int colour)
+{
+    const int row_tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row_tid >= p.Lh * p.G) return;
+    const int g = row_tid % p.G, xh = row_tid / p.G;
+    const int y = (D >= 2) ? blockIdx.y : 0, z = (D >= 3) ? blockIdx.z : 0;
+    const int x = 2 * xh + ((y + z + colour) & 1);
+    const site_geom<D> sg = make_geom<D>(p.L, x, y, z);
+    const int W = p.W;
+
+    uint32_t sc[4], sn[4][2 * D];
+    if (FULL) {
+        const uint4 *sp = reinterpret_cast<const uint4 *>(p.spins);
+        const int64_t W4 = W >> 2;
+        const uint4 c = sp[sg.i * W4 + g];
+        sc[0] = c.x; sc[1] = c.y; sc[2] = c.z; sc[3] = c.w;
+#pragma unroll
+        for (int k = 0; k < 2 * D; k++) {
+            const uint4 v = sp[sg.nb[k] * W4 + g];
+            sn[0][k] = v.x; sn[1][k] = v.y; sn[2][k] = v.z; sn[3][k] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            const bool ok = 4 * g + w < W;
+            sc[w] = ok ? p.spins[sg.i * W + 4 * g + w] : 0u;
+#pragma unroll
+            for (int k = 0; k < 2 * D; k++) sn[w][k] = ok ? p.spins[sg.nb[k] * W + 4 * g + w] : 0u;
+        }
+    }
+    const uint32_t jc = p.jcode[sg.i];
+
+    uint32_t mc[4][3], eq[4], lt[4], up[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        uint32_t u0, u1, u2;
+        unsat_planes<D>(sc[w], sn[w], jc, u0, u1, u2);
+        class_masks<D>(u0, u1, u2, mc[w]);
+        up[w] = mc[w][0] | mc[w][1] | mc[w][2];
+        if (!FULL && !(4 * g + w < W)) { up[w] = 0; mc[w][0] = mc[w][1] = mc[w][2] = 0; }
+        eq[w] = up[w]; lt[w] = 0;
+    }
+
+    const uint32_t c1 = (uint32_t)sg.i, c2 = (uint32_t)g;
+    // plane phase: bit q (from the MSB) of U for every lane of the task comes from Philox call q
+    for (int q = 0; q < p.K; q++) {
+        if (!(eq[0] | eq[1] | eq[2] | eq[3])) break;
+        const philox_out r = philox4x32_10((uint32_t)q | p.t_hi16, c1, c2, p.t_lo, p.k0, p.k1);
+        const uint32_t rr[4] = { r.x, r.y, r.z, r.w };
+        const uint32_t B0 = p.plane[q][0], B1 = p.plane[q][1], B2 = p.plane[q][2];
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            const uint32_t thr = (mc[w][0] & B0) | (mc[w][1] & B1) | (mc[w][2] & B2);
+            lt[w] |= eq[w] & ~rr[w] & thr;
+            eq[w] &= ~(rr[w] ^ thr);
+        }
+    }
+    // tail: undecided lanes in ascending (w,b) order take 32 fresh bits each
+    {
+        int n = 0;
+        philox_out r = { 0, 0, 0, 0 };
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            uint32_t e = eq[w];
+            while (e) {
+                const uint32_t bit = e & (0u - e);
+                e ^= bit;
+                const uint32_t rem = (mc[w][0] & bit) ? p.rem[0] : ((mc[w][1] & bit) ? p.rem[1] : p.rem[2]);
+                if ((n & 3) == 0) r = philox4x32_10((uint32_t)(p.K + (n >> 2)) | p.t_hi16, c1, c2, p.t_lo, p.k0, p.k1);
+                const int m = n & 3;
+                const uint32_t V = m == 0 ? r.x : (m == 1 ? r.y : (m == 2 ? r.z : r.w));
+                if (V < rem) lt[w] |= bit;
+                n++;
+            }
+        }
+    }
+    uint32_t fl[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        fl[w] = ~up[w] | lt[w];
+        if (!FULL && !(4 * g + w < W)) fl[w] = 0;
+        sc[w] ^= fl[w];
+    }
+    if (FULL) {
+        const int64_t W4 = W >> 2;
+        reinterpret_cast<uint4 *>(p.spins)[sg.i * W4 + g] = make_uint4(sc[0], sc[1], sc[2], sc[3]);
+        if (p.flips) reinterpret_cast<uint4 *>(p.flips)[sg.i * W4 + g] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+    } else {
+#pragma unroll
+        for (int w = 0; w < 4; w++)
+            if (4 * g + w < W) {
+                p.spins[sg.i * W + 4 * g + w] = sc[w];
+                if (p.flips) p.flips[sg.i * W + 4 * g + w] = fl[w];
+            }
+    }
+}
+
+rrrmc_status_t launch_checkerboard(rrrmc_ctx *ctx, const cb_params &p, int D, int colour)
+{
+    const bool full = (p.W % 4) == 0;
+    dim3 block(256), grid(div_up((int64_t)p.Lh * p.G, 256), D >= 2 ? p.L : 1, D >= 3 ? p.L : 1);
+#define LAUNCH(DD, FF) k_checkerboard<DD, FF><<<grid, block, 0, ctx->stream>>>(p, colour)
+    if (D == 1) { if (full) LAUNCH(1, true); else LAUNCH(1, false); }
+    else if (D == 2) { if (full) LAUNCH(2, true); else LAUNCH(2, false); }
+    else if (D == 3) { if (full) LAUNCH(3, true); else LAUNCH(3, false); }
+    else { rrrmc_set_error("checkerboard: D=%d unsupported (1..3)", D); return RRRMC_ERR_UNSUPPORTED; }
+#undef LAUNCH
+    ctx->launches++;
+    RR_CUDA(cudaGetLastError());
+    return RRRMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// vertical (bit-sliced) counters: cnt[b] holds bit b of a per-lane counter
+// ------------------------------------------------------------------------------------------------
+template <int B>
+__device__ __forceinline__ void vc_add(uint32_t (&cnt)[B], uint32_t plane, int from)
+{
+#pragma unroll
+    for (int b = 0; b < B; b++) {
+        if (b < from) continue;
+        const uint32_t t = cnt[b] & plane;
+        cnt[b] ^= plane;
+        plane = t;
+    }
+}
+template <int B>
+__device__ __forceinline__ int vc_lane(const uint32_t (&cnt)[B], int lane)
+{
+    int v = 0;
+#pragma unroll
+    for (int b = 0; b < B; b++) v |= (int)((cnt[b] >> lane) & 1u) << b;
+    return v;
+}
+
+// energy(X, C) (EA.jl:195-222) for every replica: E = -Σ_<xy> J σσ = 2·#unsat − D·N (±J).
+// Thread = (chunk of ENERGY_S sites, word); counts unsatisfied *forward* bonds per lane.
+constexpr int ENERGY_S = 64;
+template <int D>
+__global__ void __launch_bounds__(128) k_energy_pm1(const uint32_t *__restrict__ spins, const uint8_t *__restrict__ jcode,
+                                                    int L, int64_t N, int W, int *__restrict__ unsat_out)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = (int)(tid % W);
+    const int64_t chunk = tid / W;
+    if (chunk * ENERGY_S >= N) return;
+    uint32_t cnt[9];
+#pragma unroll
+    for (int b = 0; b < 9; b++) cnt[b] = 0;
+    const int64_t i1 = min(N, (chunk + 1) * ENERGY_S);
+    for (int64_t i = chunk * ENERGY_S; i < i1; i++) {
+        const int x = (int)(i % L), y = D >= 2 ? (int)((i / L) % L) : 0, z = D >= 3 ? (int)(i / ((int64_t)L * L)) : 0;
+        const site_geom<D> sg = make_geom<D>(L, x, y, z);
+        const uint32_t sc = spins[i * W + w], jc = jcode[i];
+        uint32_t b[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) b[d] = sc ^ spins[sg.nb[2 * d] * W + w] ^ (0u - ((jc >> (2 * d)) & 1u));
+        if (D == 1) vc_add<9>(cnt, b[0], 0);
+        if (D == 2) { vc_add<9>(cnt, b[0] ^ b[1], 0); vc_add<9>(cnt, b[0] & b[1], 1); }
+        if (D == 3) { uint32_t s, c; full_add(b[0], b[1], b[2], s, c); vc_add<9>(cnt, s, 0); vc_add<9>(cnt, c, 1); }
+    }
+#pragma unroll 1
+    for (int lane = 0; lane < 32; lane++) {
+        const int v = vc_lane<9>(cnt, lane);
+        if (v) atomicAdd(&unsat_out[32 * w + lane], v);
+    }
+}
+
+rrrmc_status_t launch_energy_pm1(rrrmc_state *s, int *d_unsat)
+{
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    RR_CUDA(cudaMemsetAsync(d_unsat, 0, sizeof(int) * s->W * 32, ctx->stream));
+    const int64_t nthreads = (int64_t)div_up(g->N, ENERGY_S) * s->W;
+    dim3 block(128), grid(div_up(nthreads, 128));
+    if (g->D == 1) k_energy_pm1<1><<<grid, block, 0, ctx->stream>>>(s->d_spins, g->d_jcode, g->L, g->N, (int)s->W, d_unsat);
+    else if (g->D == 2) k_energy_pm1<2><<<grid, block, 0, ctx->stream>>>(s->d_spins, g->d_jcode, g->L, g->N, (int)s->W, d_unsat);
+    else k_energy_pm1<3><<<grid, block, 0, ctx->stream>>>(s->d_spins, g->d_jcode, g->L, g->N, (int)s->W, d_unsat);
+    ctx->launches++;
+    RR_CUDA(cudaGetLastError());
+    return RRRMC_OK;
+}
+
+// per-lane popcount over sites of a mask array [N][W] (accepted-move counters, magnetisation)
+constexpr int COUNT_S = 128;
+__global__ void __launch_bounds__(128) k_count_lanes(const uint32_t *__restrict__ masks, int64_t N, int W,
+                                                     long long *__restrict__ out)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = (int)(tid % W);
+    const int64_t chunk = tid / W;
+    if (chunk * COUNT_S >= N) return;
+    uint32_t cnt[8];
+#pragma unroll
+    for (int b = 0; b < 8; b++) cnt[b] = 0;
+    const int64_t i1 = min(N, (chunk + 1) * COUNT_S);
+    for (int64_t i = chunk * COUNT_S; i < i1; i++) vc_add<8>(cnt, masks[i * W + w], 0);
+#pragma unroll 1
+    for (int lane = 0; lane < 32; lane++) {
+        const int v = vc_lane<8>(cnt, lane);
+        if (v) atomicAdd((unsigned long long *)&out[32 * w + lane], (unsigned long long)v);
+    }
+}
+
+rrrmc_status_t launch_count_lanes(rrrmc_ctx *ctx, const uint32_t *masks, int64_t N, int W, long long *d_out)
+{
+    const int64_t nthreads = (int64_t)div_up(N, COUNT_S) * W;
+    k_count_lanes<<<div_up(nthreads, 128), 128, 0, ctx->stream>>>(masks, N, W, d_out);
+    ctx->launches++;
+    RR_CUDA(cudaGetLastError());
+    return RRRMC_OK;
+}
+
+// delta_energy(X, C, i) for all replicas of one site (EA.jl:266-275): out[32w+b] = 4(D-u)
+template <int D>
+__global__ void k_delta_energy_site(const uint32_t *__restrict__ spins, const uint8_t *__restrict__ jcode,
+                                    int L, int W, int64_t site, int *__restrict__ out)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    const int x = (int)(site % L), y = D >= 2 ? (int)((site / L) % L) : 0, z = D >= 3 ? (int)(site / ((int64_t)L * L)) : 0;
+    const site_geom<D> sg = make_geom<D>(L, x, y, z);
+    uint32_t sn[2 * D];
+#pragma unroll
+    for (int k = 0; k < 2 * D; k++) sn[k] = spins[sg.nb[k] * W + w];
+    uint32_t u0, u1, u2;
+    unsat_planes<D>(spins[site * W + w], sn, jcode[site], u0, u1, u2);
+    for (int b = 0; b < 32; b++) {
+        const int u = (int)((u0 >> b) & 1) | (int)((u1 >> b) & 1) << 1 | (int)((u2 >> b) & 1) << 2;
+        out[32 * w + b] = 4 * (D - u);
+    }
+}
+
+// delta_energy(X, C, i), i=1..N, for one replica
+template <int D>
+__global__ void k_delta_energy_replica(const uint32_t *__restrict__ spins, const uint8_t *__restrict__ jcode,
+                                       int L, int64_t N, int W, int64_t replica, int *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int w = (int)(replica >> 5), b = (int)(replica & 31);
+    const int x = (int)(i % L), y = D >= 2 ? (int)((i / L) % L) : 0, z = D >= 3 ? (int)(i / ((int64_t)L * L)) : 0;
+    const site_geom<D> sg = make_geom<D>(L, x, y, z);
+    const uint32_t jc = jcode[i];
+    const int sc = (spins[i * W + w] >> b) & 1;
+    int u = 0;
+#pragma unroll
+    for (int k = 0; k < 2 * D; k++) u += sc ^ (int)((spins[sg.nb[k] * W + w] >> b) & 1) ^ (int)((jc >> k) & 1);
+    out[i] = 4 * (D - u);
+}
+
+rrrmc_status_t launch_delta_energy_site(rrrmc_state *s, int64_t site0, int *d_out)
+{
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    dim3 block(128), grid(div_up(s->W, 128));
+    if (g->D == 1) k_delta_energy_site<1><<<grid, block, 0, ctx->stream>>>(s->d_spins, g->d_jcode, g->L, (int)s->W, site0, d_out);
+    else if (g->D == 2) k_delta_energy_site<2><<<grid, block, 0, ctx->stream>>>(s->d_spins, g->d_jcode, g->L, (int)s->W, site0, d_out);
+    else k_delta_energy_site<3><<<grid, block, 0, ctx->stream>>>(s->d_spins, g->d_jcode, g->L, (int)s->W, site0, d_out);
+    ctx->launches++;
+    RR_CUDA(cudaGetLastError());
+    return RRRMC_OK;
+}
+rrrmc_status_t launch_delta_energy_replica(rrrmc_state *s, int64_t replica, int *d_out)
+{
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    dim3 block(256), grid(div_up(g->N, 256));
+    if (g->D == 1) k_delta_energy_replica<1><<<grid, block, 0, ctx->stream>>>(s->d_spins, g->d_jcode, g->L, g->N, (int)s->W, replica, d_out);
+    else if (g->D == 2) k_delta_energy_replica<2><<<grid, block, 0, ctx->stream>>>(s->d_spins, g->d_jcode, g->L, g->N, (int)s->W, replica, d_out);
+    else k_delta_energy_replica<3><<<grid, block, 0, ctx->stream>>>(s->d_spins, g->d_jcode, g->L, g->N, (int)s->W, replica, d_out);
+    ctx->launches++;
+    RR_CUDA(cudaGetLastError());
+    return RRRMC_OK;
+}
+
+// spinflip!(C, i) on selected replicas (multispin layout has no local-field cache to update)
+__global__ void k_flip_site(uint32_t *spins, int W, int64_t site, const uint32_t *mask)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < W) spins[site * W + w] ^= mask ? mask[w] : 0xffffffffu;
+}
+rrrmc_status_t launch_flip_site(rrrmc_state *s, int64_t site0, const uint32_t *d_mask)
+{
+    rrrmc_ctx *ctx = s->g->ctx;
+    k_flip_site<<<div_up(s->W, 128), 128, 0, ctx->stream>>>(s->d_spins, (int)s->W, site0, d_mask);
+    ctx->launches++;
+    RR_CUDA(cudaGetLastError());
+    return RRRMC_OK;
+}
+
+// Config(N) random init (Interface.jl:24-28): word (i,w) = Philox(ctr=(i_lo,i_hi,w,'CNFG'), key=seed).x
+__global__ void k_randomize(uint32_t *spins, int64_t N, int W, uint32_t k0, uint32_t k1)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= N * W) return;
+    const int64_t i = tid / W; const int w = (int)(tid % W);
+    spins[tid] = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)w, 0x434e4647u, k0, k1).x;
+}
+rrrmc_status_t launch_randomize(rrrmc_state *s, uint64_t seed)
+{
+    rrrmc_ctx *ctx = s->g->ctx;
+    const int64_t n = s->g->N * s->W;
+    k_randomize<<<div_up(n, 256), 256, 0, ctx->stream>>>(s->d_spins, s->g->N, (int)s->W, (uint32_t)seed, (uint32_t)(seed >> 32));
+    ctx->launches++;
+    RR_CUDA(cudaGetLastError());
+    return RRRMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layout transposes: reference BitVector chunks [count][nchunks] (site-major bits per chain,
+// Interface.jl:21-29) <-> multispin words. Thread = (chunk c, word w): a 32x64 bit-matrix transpose.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_chunks_to_multispin(const uint64_t *__restrict__ chunks, int64_t nchunks, int64_t first,
+                                                             int64_t count, uint32_t *__restrict__ spins, int64_t N, int W, int w0, int nw)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= nchunks * nw) return;
+    const int w = w0 + (int)(tid % nw);
+    const int64_t c = tid / nw;
+    uint64_t ch[32];
+    uint32_t lanes = 0;
+#pragma unroll
+    for (int b = 0; b < 32; b++) {
+        const int64_t r = 32 * (int64_t)w + b - first;
+        const bool ok = r >= 0 && r < count;
+        ch[b] = ok ? chunks[r * nchunks + c] : 0ull;
+        lanes |= ok ? (1u << b) : 0u;
+    }
+    for (int k = 0; k < 64; k++) {
+        const int64_t i = 64 * c + k;
+        if (i >= N) break;
+        uint32_t word = 0;
+#pragma unroll
+        for (int b = 0; b < 32; b++) word |= (uint32_t)((ch[b] >> k) & 1ull) << b;
+        uint32_t *dst = &spins[i * W + w];
+        *dst = lanes == 0xffffffffu ? word : ((*dst & ~lanes) | word);
+    }
+}
+__global__ void __launch_bounds__(128) k_multispin_to_chunks(const uint32_t *__restrict__ spins, int64_t N, int W, int64_t first,
+                                                             int64_t count, uint64_t *__restrict__ chunks, int64_t nchunks, int w0, int nw)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= nchunks * nw) return;
+    const int w = w0 + (int)(tid % nw);
+    const int64_t c = tid / nw;
+    uint64_t ch[32];
+#pragma unroll
+    for (int b = 0; b < 32; b++) ch[b] = 0;
+    for (int k = 0; k < 64; k++) {
+        const int64_t i = 64 * c + k;
+        if (i >= N) break;
+        const uint32_t word = spins[i * W + w];
+#pragma unroll
+        for (int b = 0; b < 32; b++) ch[b] |= (uint64_t)((word >> b) & 1u) << k;
+    }
+#pragma unroll
+    for (int b = 0; b < 32; b++) {
+        const int64_t r = 32 * (int64_t)w + b - first;
+        if (r >= 0 && r < count) chunks[r * nchunks + c] = ch[b];
+    }
+}
+
+rrrmc_status_t launch_upload_transpose(rrrmc_state *s, int64_t first, int64_t count)
+{
+    rrrmc_ctx *ctx = s->g->ctx;
+    const int w0 = (int)(first / 32), w1 = (int)((first + count + 31) / 32), nw = w1 - w0;
+    const int64_t n = s->nchunks * nw;
+    k_chunks_to_multispin<<<div_up(n, 128), 128, 0, ctx->stream>>>(s->d_chunks, s->nchunks, first, count, s->d_spins, s->g->N, (int)s->W, w0, nw);
+    ctx->launches++;
+    RR_CUDA(cudaGetLastError());
+    return RRRMC_OK;
+}
+rrrmc_status_t launch_download_transpose(rrrmc_state *s, int64_t first, int64_t count)
+{
+    rrrmc_ctx *ctx = s->g->ctx;
+    const int w0 = (int)(first / 32), w1 = (int)((first + count + 31) / 32), nw = w1 - w0;
+    const int64_t n = s->nchunks * nw;
+    k_multispin_to_chunks<<<div_up(n, 128), 128, 0, ctx->stream>>>(s->d_spins, s->g->N, (int)s->W, first, count, s->d_chunks, s->nchunks, w0, nw);
+    ctx->launches++;
+    RR_CUDA(cudaGetLastError());
+    return RRRMC_OK;
+}
+
+__global__ void k_flush(uint32_t *buf, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = (uint32_t)i;
+}
+rrrmc_status_t launch_flush(rrrmc_ctx *ctx)
+{
+    k_flush<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((uint32_t *)ctx->flush_buf, ctx->flush_bytes / 4);
+    RR_CUDA(cudaGetLastError());
+    return RRRMC_OK;
+}

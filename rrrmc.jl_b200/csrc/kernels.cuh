@@ -1,0 +1,28 @@
+// Kernel launchers shared between translation units.
+#pragma once
+#include "common.cuh"
+
+constexpr int CB_MAXK = 32;
+
+struct cb_params {
+    uint32_t *spins;        // [N][W]
+    uint32_t *flips;        // [N][W] or nullptr: per-attempt accept masks (for accepted counters)
+    const uint8_t *jcode;   // [N]
+    int L, Lh, W, G;        // lattice side, L/2, words per site, 128-replica groups per site
+    uint32_t k0, k1;        // Philox key = seed
+    uint32_t t_lo, t_hi16;  // sweep counter: low 32 bits, (high bits) << 16
+    int K;                  // bit planes before the per-lane tail
+    uint32_t plane[CB_MAXK][3]; // plane[q][c-1] = all-ones iff bit (63-q) of thr64[c] is set
+    uint32_t rem[3];        // bits [63-K .. 32-K] of thr64[c]
+};
+
+rrrmc_status_t launch_checkerboard(rrrmc_ctx *ctx, const cb_params &p, int D, int colour);
+rrrmc_status_t launch_energy_pm1(rrrmc_state *s, int *d_unsat);
+rrrmc_status_t launch_count_lanes(rrrmc_ctx *ctx, const uint32_t *masks, int64_t N, int W, long long *d_out);
+rrrmc_status_t launch_delta_energy_site(rrrmc_state *s, int64_t site0, int *d_out);
+rrrmc_status_t launch_delta_energy_replica(rrrmc_state *s, int64_t replica, int *d_out);
+rrrmc_status_t launch_flip_site(rrrmc_state *s, int64_t site0, const uint32_t *d_mask);
+rrrmc_status_t launch_randomize(rrrmc_state *s, uint64_t seed);
+rrrmc_status_t launch_upload_transpose(rrrmc_state *s, int64_t first, int64_t count);
+rrrmc_status_t launch_download_transpose(rrrmc_state *s, int64_t first, int64_t count);
+rrrmc_status_t launch_flush(rrrmc_ctx *ctx);

@@ -1,0 +1,401 @@
+"""Host-side mirror of RRRMC.jl's graph Interface and samplers for the B200 engine.
+
+Same names, argument meaning and error behaviour as the reference (src/Interface.jl, src/RRRMC.jl), with one
+extension: a graph carries a *replica batch* of R independent chains, so energies are arrays of length R and a
+`Config` holds R bit-vectors.  With replicas=1 the calls read exactly like the reference's:
+
+    X = GraphEA(32, 2)                                   # src/graphs/EA.jl:181-191
+    Es, C = standardMC(X, 1.0, 10**6, step=10**3)        # src/RRRMC.jl:81-127
+
+All compute goes through the C ABI (include/rrrmc_b200.h) into CUDA kernels; there is no CPU path here.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import check, lib, ptr
+
+DEFAULT_SEED = 167432777111  # src/RRRMC.jl:82
+
+
+# ----------------------------------------------------------------------------------------------------
+class Context:
+    """One device + one stream (rrrmc_ctx_t)."""
+    _default = {}
+
+    def __init__(self, device=0, stream=None):
+        h = C.c_void_p()
+        check(lib().rrrmc_ctx_create(device, stream, C.byref(h)))
+        self.h, self.device = h, device
+
+    @classmethod
+    def default(cls, device=0):
+        if device not in cls._default:
+            cls._default[device] = cls(device)
+        return cls._default[device]
+
+    def sync(self):
+        check(lib().rrrmc_ctx_sync(self.h))
+
+    def timer_start(self):
+        check(lib().rrrmc_ctx_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(lib().rrrmc_ctx_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_uint64()
+        check(lib().rrrmc_ctx_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def flush_l2(self):
+        check(lib().rrrmc_ctx_flush_l2(self.h))
+
+
+# ----------------------------------------------------------------------------------------------------
+class Config:
+    """Config (src/Interface.jl:21-54) for a batch: `chunks[r]` is replica r's BitVector chunk array
+    (site i = bit (i-1)&63 of chunk (i-1)>>6). `s` gives the bits as a (R, N) bool array."""
+
+    def __init__(self, N, replicas=1, chunks=None, init=True, rng=None):
+        self.N, self.R = int(N), int(replicas)
+        nch = (self.N + 63) // 64
+        if chunks is not None:
+            self.chunks = np.ascontiguousarray(chunks, dtype=np.uint64).reshape(self.R, nch)
+        elif init:
+            rng = rng or np.random.default_rng()
+            self.chunks = rng.integers(0, 2 ** 64, (self.R, nch), dtype=np.uint64)
+            if self.N % 64:
+                self.chunks[:, -1] &= np.uint64((1 << (self.N % 64)) - 1)
+        else:
+            self.chunks = np.zeros((self.R, nch), np.uint64)
+
+    def __len__(self):
+        return self.N
+
+    @property
+    def s(self):
+        b = np.unpackbits(self.chunks.view(np.uint8), axis=1, bitorder="little")[:, :self.N]
+        return b.astype(bool)
+
+    @classmethod
+    def from_bits(cls, bits):
+        bits = np.atleast_2d(np.asarray(bits, dtype=np.uint8))
+        R, N = bits.shape
+        pad = (-N) % 64
+        packed = np.packbits(np.pad(bits, ((0, 0), (0, pad))), axis=1, bitorder="little")
+        return cls(N, R, chunks=packed.view(np.uint64))
+
+    def copy(self):
+        return Config(self.N, self.R, chunks=self.chunks.copy())
+
+    def __eq__(self, other):
+        return isinstance(other, Config) and self.N == other.N and np.array_equal(self.chunks, other.chunks)
+
+
+# ----------------------------------------------------------------------------------------------------
+def gen_EA(L, D):
+    """gen_EA (src/graphs/EA.jl:24-43): (N, 2D) int64, 1-based, rows sorted ascending."""
+    if L < 2:
+        raise ValueError(f"L must be ≥ 2, given: {L}")
+    if D < 1:
+        raise ValueError(f"D must be ≥ 0, given: {D}")
+    A = np.zeros((L ** D, 2 * D), np.int64)
+    check(lib().rrrmc_gen_ea_adjacency(L, D, ptr(A)))
+    return A
+
+
+def gen_J(f, A):
+    """gen_J (src/graphs/EA.jl:45-71): one draw f() per bond x<y in (x, slot) order, mirrored into the first
+    still-empty slot of J[y]. `f(n)` must return n draws in consumption order."""
+    N, twoD = A.shape
+    x = np.arange(1, N + 1)[:, None]
+    fwd = A > x
+    J = np.zeros((N, twoD), np.float64)
+    draws = np.asarray(f(int(fwd.sum())), dtype=np.float64)
+    J[fwd] = draws
+    if (A[:, 1:] == A[:, :-1]).any():  # L=2: duplicated neighbours, follow the fill order literally
+        filled = fwd.copy()
+        for xi in range(N):
+            for k in range(twoD):
+                y = A[xi, k] - 1
+                if xi < y:
+                    l = int(np.flatnonzero(~filled[y])[0])
+                    J[y, l] = J[xi, k]; filled[y, l] = True
+        return J
+    xs, ks = np.nonzero(fwd)
+    ys = A[xs, ks] - 1
+    ls = np.array([np.searchsorted(A[y], xx + 1) for y, xx in zip(ys, xs)]) if len(xs) < 4096 else \
+        (A[ys] == (xs + 1)[:, None]).argmax(axis=1)
+    J[ys, ls] = J[xs, ks]
+    return J
+
+
+class AbstractGraph:
+    """AbstractGraph{ET} (src/Interface.jl:66): a model plus the device-resident replica batch it samples."""
+    _state = None
+    ET = float
+
+    def getN(self):
+        return self.N
+
+    # -- state plumbing
+    def _ensure_state(self):
+        if self._state is None:
+            h = C.c_void_p()
+            check(lib().rrrmc_state_create(self._h, self.replicas, C.byref(h)))
+            self._state = h
+        return self._state
+
+    def _upload(self, Cfg):
+        if Cfg.N != self.N:
+            raise ValueError(f"Invalid C0, wrong N, expected {self.N}, given: {Cfg.N}")  # RRRMC.jl:94
+        if Cfg.R != self.replicas:
+            raise ValueError(f"Config holds {Cfg.R} replicas, graph batch has {self.replicas}")
+        check(lib().rrrmc_state_upload(self._ensure_state(), 0, self.replicas, ptr(Cfg.chunks)))
+
+    def _download(self):
+        out = Config(self.N, self.replicas, init=False)
+        check(lib().rrrmc_state_download(self._ensure_state(), 0, self.replicas, ptr(out.chunks)))
+        return out
+
+    def __del__(self):
+        try:
+            if self._state is not None:
+                lib().rrrmc_state_destroy(self._state)
+            if getattr(self, "_h", None) is not None:
+                lib().rrrmc_graph_destroy(self._h)
+        except Exception:
+            pass
+
+
+def _scalarize(X, a):
+    a = np.asarray(a)
+    if X.ET is int:
+        a = np.rint(a).astype(np.int64)
+    return a[0] if X.replicas == 1 else a
+
+
+def energy(X, Cfg):
+    """energy(X, C) (Interface.jl:105): array of R energies (a scalar when replicas == 1). Resets caches."""
+    X._upload(Cfg)
+    E = np.zeros(X.replicas, np.float64)
+    check(lib().rrrmc_energy(X._state, ptr(E)))
+    return _scalarize(X, E)
+
+
+def delta_energy(X, Cfg, move):
+    """delta_energy(X, C, move) (Interface.jl:130): ΔE of flipping 1-based spin `move`, per replica."""
+    if not 1 <= move <= X.N:
+        raise ValueError(f"move out of range 1..{X.N}: {move}")
+    X._upload(Cfg)
+    dE = np.zeros(X.replicas, np.float64)
+    check(lib().rrrmc_delta_energy(X._state, move, ptr(dE)))
+    return _scalarize(X, dE)
+
+
+def all_delta_energy(X, Cfg, replica=0):
+    """[delta_energy(X, C, i) for i in 1:N] for one replica (what gen_ΔEcache evaluates, DeltaE.jl:79-80)."""
+    X._upload(Cfg)
+    dE = np.zeros(X.N, np.float64)
+    check(lib().rrrmc_all_delta_energy(X._state, replica, ptr(dE)))
+    return np.rint(dE).astype(np.int64) if X.ET is int else dE
+
+
+def neighbors(X, i):
+    """neighbors(X, i) (Interface.jl:158)."""
+    out = np.zeros(64, np.int64); n = C.c_int()
+    check(lib().rrrmc_neighbors(X._h, i, ptr(out), C.byref(n)))
+    return tuple(int(v) for v in out[:n.value])
+
+
+def allDeltaE(X):
+    """allΔE(X) (Interface.jl:200-201)."""
+    out = np.zeros(64, np.float64); n = C.c_int()
+    check(lib().rrrmc_allDE(X._h, ptr(out), C.byref(n)))
+    vals = out[:n.value]
+    return tuple(int(v) for v in vals) if X.ET is int else tuple(float(v) for v in vals)
+
+
+allΔE = allDeltaE
+
+
+def spinflip(X, Cfg, move, replica_mask=None):
+    """spinflip!(X, C, move) (Interface.jl:89-92): flips the spin on the device batch and in `Cfg`."""
+    X._upload(Cfg)
+    m = None
+    if replica_mask is not None:
+        bits = np.zeros(((X.replicas + 31) // 32) * 32, np.uint8); bits[:X.replicas] = replica_mask
+        m = np.packbits(bits, bitorder="little").view(np.uint32).copy()
+    check(lib().rrrmc_spinflip(X._state, move, ptr(m)))
+    Cfg.chunks[...] = X._download().chunks
+
+
+update_cache = spinflip  # the device batch has no separately visible cache; update_cache! ≡ post-flip refresh
+
+
+class GraphEA(AbstractGraph):
+    """GraphEA(L, D, LEV=(-1,1)) <: DiscrGraph (src/graphs/EA.jl:138-191) on a replica batch.
+    Pass `A`, `J` (reference layout) to wrap an existing instance: GraphEA{ET,LEV,twoD}(A, J), EA.jl:145."""
+    ET = int
+
+    def __init__(self, L, D, LEV=(-1, 1), replicas=1, A=None, J=None, rng=None, ctx=None):
+        if not all(float(l).is_integer() for l in LEV):
+            raise NotImplementedError("non-integer levels (DFloat64 path, EA.jl:193) are not on this engine's path yet")
+        if len(set(LEV)) != len(LEV):
+            raise ValueError(f"repeated levels in LEV: {LEV}")  # EA.jl:122
+        self.L, self.D, self.LEV, self.replicas = L, D, tuple(int(l) for l in LEV), int(replicas)
+        self.ctx = ctx or Context.default()
+        self.A = gen_EA(L, D) if A is None else np.ascontiguousarray(A, np.int64)
+        self.N = self.A.shape[0]
+        if J is None:
+            rng = rng or np.random.default_rng()
+            lev = np.asarray(self.LEV, np.float64)
+            J = gen_J(lambda n: rng.choice(lev, n), self.A)  # rand(vLEV), EA.jl:185-187
+        self.J = np.ascontiguousarray(np.rint(J), np.int64)
+        if not np.isin(self.J, self.LEV).all():
+            raise ValueError(f"the given J is incompatible with levels {LEV}")  # EA.jl:161
+        kind = _ffi.EA_PM1 if set(self.LEV) == {-1, 1} else _ffi.EA_INT
+        h = C.c_void_p()
+        check(lib().rrrmc_graph_ea_create(self.ctx.h, L, D, kind, ptr(self.A), ptr(self.J), C.byref(h)))
+        self._h = h
+
+
+class GraphEANormal(AbstractGraph):
+    """GraphEANormal(L, D) <: SimpleGraph{Float64} (src/graphs/EA.jl:534-574)."""
+    ET = float
+
+    def __init__(self, L, D, replicas=1, A=None, J=None, rng=None, ctx=None):
+        self.L, self.D, self.replicas = L, D, int(replicas)
+        self.ctx = ctx or Context.default()
+        self.A = gen_EA(L, D) if A is None else np.ascontiguousarray(A, np.int64)
+        self.N = self.A.shape[0]
+        if J is None:
+            rng = rng or np.random.default_rng()
+            J = gen_J(lambda n: rng.standard_normal(n), self.A)
+        self.J = np.ascontiguousarray(J, np.float64)
+        h = C.c_void_p()
+        check(lib().rrrmc_graph_ea_create(self.ctx.h, L, D, _ffi.EA_F64, ptr(self.A), ptr(self.J), C.byref(h)))
+        self._h = h
+
+
+# ----------------------------------------------------------------------------------------------------
+class _LazyConfig:
+    """The `C` a hook sees: downloads the batch from the device on first access."""
+
+    def __init__(self, X):
+        self._X, self._c = X, None
+
+    def _get(self):
+        if self._c is None:
+            self._c = self._X._download()
+        return self._c
+
+    def __getattr__(self, k):
+        return getattr(self._get(), k)
+
+
+def _run(fn, X, beta, iters, seed, step, hook, C0, quiet, opts, name):
+    if step < 1:
+        raise ValueError("step must be ≥ 1")
+    st = X._ensure_state()
+    if C0 is None:
+        check(lib().rrrmc_state_randomize(st, seed if seed > 0 else np.random.SeedSequence().entropy & (2 ** 63 - 1)))
+    else:
+        X._upload(C0)
+    R = X.replicas
+    betas = np.ascontiguousarray(np.broadcast_to(np.asarray(beta, np.float64), (R,)))
+    cap = min(10 ** 8, iters // step)  # RRRMC.jl:90
+    Es = np.zeros((max(cap, 1), R), np.float64)
+    info = _ffi.RunInfo()
+    last = {}
+
+    def _hook(user, it, E, acc, n):
+        Ev = np.ctypeslib.as_array(E, (n,)).copy()
+        av = np.ctypeslib.as_array(acc, (n,)).copy()
+        last["acc"], last["it"] = av, it
+        try:
+            ok = hook(it, X, _LazyConfig(X), av if R > 1 else int(av[0]), _scalarize(X, Ev))
+        except Exception as e:  # propagate after the C call returns
+            last["exc"] = e
+            return 0
+        return 1 if ok else 0
+    cb = _ffi.HOOK(_hook) if hook is not None else C.cast(None, _ffi.HOOK)
+    check(fn(st, ptr(betas), int(iters), int(step), int(seed) if seed > 0 else 0, cb, None, C.byref(opts),
+             ptr(Es), cap, C.byref(info)))
+    if "exc" in last:
+        raise last["exc"]
+    Cout = X._download()
+    Es = Es[:info.nsamples]
+    if X.ET is int:
+        Es = np.rint(Es).astype(np.int64)
+    if not quiet:
+        print("samples =", info.nsamples)
+        print("iters =", info.iters_done)
+        if "acc" in last and (last["acc"] >= 0).all():
+            print("accept rate =", float(np.mean(last["acc"])) / max(1, last["it"]))
+    X.last_run = info
+    return (Es[:, 0] if R == 1 else Es), Cout
+
+
+def _opts(schedule=None, planes_K=None, count_accepted=None, staged_thr=None, staged_thr_fact=None):
+    o = _ffi.Opts()
+    check(lib().rrrmc_opts_default(C.byref(o)))
+    if schedule is not None:
+        o.schedule = {"checkerboard": _ffi.SCHED_CHECKERBOARD, "random": _ffi.SCHED_RANDOM_SITE}[schedule]
+    if planes_K is not None:
+        o.planes_K = planes_K
+    if count_accepted is not None:
+        o.count_accepted = int(count_accepted)
+    if staged_thr is not None:
+        o.staged_thr = staged_thr
+    if staged_thr_fact is not None:
+        o.staged_thr_fact = staged_thr_fact
+    return o
+
+
+def standardMC(X, β, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, quiet=False,
+               schedule=None, planes_K=None, count_accepted=None):
+    """standardMC(X, β, iters; seed, step, hook, C0, quiet) (src/RRRMC.jl:81-127) -> (Es, C).
+
+    schedule="random" is the reference's order (i = rand(1:N) per attempt, one chain per lane);
+    schedule="checkerboard" (default where the lattice is two-colourable) updates all replicas in lock step,
+    a whole sweep (N attempts) at a time — `iters`/`step` are rounded up to whole sweeps."""
+    if schedule is None:
+        schedule = "checkerboard" if (isinstance(X, GraphEA) and set(X.LEV) == {-1, 1} and X.L % 2 == 0 and X.D <= 3) else "random"
+    return _run(lib().rrrmc_standard_mc, X, β, iters, seed, step, hook, C0, quiet,
+                _opts(schedule, planes_K, count_accepted), "standardMC")
+
+
+def rrrMC(X, β, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, staged_thr=float("nan"),
+          staged_thr_fact=5.0, quiet=False):
+    """rrrMC(X, β, iters; ...) (src/RRRMC.jl:149-219)."""
+    if not math.isfinite(β):
+        raise ValueError(f"β must be finite, given: {β}")  # RRRMC.jl:159
+    return _run(lib().rrrmc_rrr_mc, X, β, iters, seed, step, hook, C0, quiet,
+                _opts(staged_thr=staged_thr, staged_thr_fact=staged_thr_fact), "rrrMC")
+
+
+def bklMC(X, β, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, quiet=False):
+    """bklMC(X, β, iters; ...) (src/RRRMC.jl:311-359)."""
+    return _run(lib().rrrmc_bkl_mc, X, β, iters, seed, step, hook, C0, quiet, _opts(), "bklMC")
+
+
+def replay(X, C0, sampler, β, iters, kind, ival, fval, *, step=1, replica=0, staged_thr=float("nan"), staged_thr_fact=5.0):
+    """Feed chain `replica` the typed draw stream the reference consumed -> (Es, C)."""
+    X._upload(C0)
+    kind = np.ascontiguousarray(kind, np.uint8); ival = np.ascontiguousarray(ival, np.int64); fval = np.ascontiguousarray(fval, np.float64)
+    cap = iters // step
+    Es = np.zeros(max(cap, 1), np.float64)
+    info = _ffi.RunInfo()
+    o = _opts(staged_thr=staged_thr, staged_thr_fact=staged_thr_fact)
+    code = {"standardMC": 0, "rrrMC": 1, "bklMC": 2}[sampler]
+    check(lib().rrrmc_replay(X._state, replica, code, float(β), int(iters), int(step), ptr(kind), ptr(ival), ptr(fval),
+                             len(kind), C.byref(o), ptr(Es), cap, C.byref(info)))
+    Es = Es[:info.nsamples]
+    X.last_run = info
+    return (np.rint(Es).astype(np.int64) if X.ET is int else Es), X._download()

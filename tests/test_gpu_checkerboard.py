@@ -1,0 +1,140 @@
+"""GPU parity of the headline kernel: the checkerboard Metropolis kernel must reproduce the CPU model of the
+same per-task random-bit procedure (oracle/rrrmc_oracle.c:orc_checkerboard_sweeps) bit for bit, and its
+observables must agree with the reference's random-site Metropolis within 3σ."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import rrrmc_b200 as rb
+from oracle import ffi
+from rrrmc_b200._ffi import check, lib, ptr
+from tests.helpers import ea_instance
+
+pytestmark = pytest.mark.gpu
+
+
+def _fwd(A, J, L, D):
+    """forward-bond couplings [N][D] from the reference (A,J) layout."""
+    N = A.shape[0]
+    out = np.zeros((N, D), np.int8)
+    for i in range(N):
+        stride = 1
+        for d in range(D):
+            c = (i // stride) % L
+            up = i + (((c + 1) % L) - c) * stride
+            ks = np.flatnonzero(A[i] == up + 1)
+            # L=2: two bonds to the same neighbour; the lower site's forward bond sits first
+            k = ks[0] if (len(ks) == 1 or i < up) else ks[1]
+            out[i, d] = J[i, k]
+            stride *= L
+    return out
+
+
+def _multispin(Cfg):
+    """(R,N) bits -> multispin words [N][W]"""
+    b = Cfg.s.astype(np.uint8)
+    R, N = b.shape
+    W = (R + 31) // 32
+    pad = np.zeros((W * 32, N), np.uint8); pad[:R] = b
+    return np.ascontiguousarray(np.packbits(pad.T.reshape(N, W, 32), axis=2, bitorder="little").view(np.uint32).reshape(N, W))
+
+
+def _from_multispin(sp, R):
+    N, W = sp.shape
+    bits = np.unpackbits(sp.view(np.uint8).reshape(N, W * 4), axis=1, bitorder="little")[:, :R]
+    return rb.Config.from_bits(bits.T)
+
+
+@pytest.mark.parametrize("L,D,R,K,beta", [(4, 2, 32, 6, 0.5), (6, 2, 96, 3, 1.0), (4, 3, 128, 6, 0.7), (6, 3, 160, 0, 1.2),
+                                          (8, 3, 256, 8, 0.3), (2, 3, 64, 6, 0.9), (4, 1, 32, 4, 0.6), (8, 3, 100, 6, 2.0)])
+def test_checkerboard_bit_exact_vs_cpu_model(L, D, R, K, beta):
+    A, J = ea_instance(L, D, seed=L * 10 + D)
+    X = rb.GraphEA(L, D, replicas=R, A=A, J=J)
+    C0 = rb.Config(X.N, R, rng=np.random.default_rng(7))
+    thr = ffi.thresholds_fixed64(beta, D)
+    seed, nsw = 0xC0FFEE1234, 5
+    X._upload(C0)
+    check(lib().rrrmc_checkerboard_sweeps(X._state, ptr(thr), D, K, seed, 3, nsw))
+    got = X._download()
+    Rp = ((R + 31) // 32) * 32
+    sp = _multispin(C0)
+    acc = np.zeros(Rp, np.int64)
+    ffi.checkerboard_sweeps(L, D, Rp, sp, _fwd(A, J, L, D), thr, K, seed, 3, nsw, acc)
+    want = _from_multispin(sp, R)
+    assert got == want
+    assert not (got == C0)
+
+
+def test_standardMC_checkerboard_energies_and_accepted():
+    L, D, R, beta = 6, 3, 64, 0.8
+    A, J = ea_instance(L, D, seed=3)
+    X = rb.GraphEA(L, D, replicas=R, A=A, J=J)
+    g = ffi.Graph.ea_int(A, J)
+    C0 = rb.Config(X.N, R, rng=np.random.default_rng(8))
+    seen = []
+
+    def hook(it, X_, C, acc, E):
+        seen.append((it, np.array(acc), np.array(E), C.chunks.copy()))
+        return True
+    N = X.N
+    Es, Cf = rb.standardMC(X, beta, 6 * N, step=2 * N, seed=77, C0=C0, hook=hook, quiet=True, planes_K=6)
+    assert Es.shape == (3, R) and [s[0] for s in seen] == [2 * N, 4 * N, 6 * N]
+    # CPU model with the same seed / thresholds
+    sp = _multispin(C0); acc = np.zeros(R, np.int64)
+    thr = ffi.thresholds_fixed64(beta, D)
+    for k in range(3):
+        ffi.checkerboard_sweeps(L, D, R, sp, _fwd(A, J, L, D), thr, 6, 77, 2 * k, 2, acc)
+        cfg = _from_multispin(sp, R)
+        assert np.array_equal(seen[k][3], cfg.chunks)
+        assert np.array_equal(seen[k][1], acc)                       # exact accepted counters
+        e = np.array([g.energy(cfg.chunks[r]) for r in range(R)])
+        assert np.array_equal(seen[k][2], e.astype(np.int64)) and np.array_equal(Es[k], e.astype(np.int64))
+    assert Cf == _from_multispin(sp, R)
+
+
+def test_checkerboard_statistics_vs_reference_sampler():
+    """⟨E⟩ from checkerboard sweeps vs the oracle's random-site standardMC (RRRMC.jl:81-127) within 3σ (L=6, 3D)."""
+    L, D, beta = 6, 3, 0.6
+    A, J = ea_instance(L, D, seed=21)
+    R = 256
+    X = rb.GraphEA(L, D, replicas=R, A=A, J=J)
+    N = X.N
+    Es, _ = rb.standardMC(X, beta, 400 * N, step=400 * N, seed=5, quiet=True)
+    e_gpu = Es[-1] / N
+    g = ffi.Graph.ea_int(A, J)
+    e_cpu = []
+    for r in range(64):
+        src = ffi.PhiloxDraws(1234, chain=r)
+        s = src.config(N)
+        E, _ = ffi.standardMC(g, beta, 400 * N, s, src, step=400 * N)
+        e_cpu.append(E[-1] / N)
+    e_cpu = np.array(e_cpu)
+    sigma = np.sqrt(e_gpu.var(ddof=1) / R + e_cpu.var(ddof=1) / len(e_cpu))
+    assert abs(e_gpu.mean() - e_cpu.mean()) < 3 * sigma, (e_gpu.mean(), e_cpu.mean(), sigma)
+    m = np.zeros(R); check(lib().rrrmc_magnetization(X._state, ptr(m)))
+    assert abs(m.mean() / N) < 0.1
+
+
+def test_full_size_properties_L64_R1024():
+    """BASELINE config (3D L=64 ±J × 1024): energy kernel vs oracle on sampled replicas after device sweeps;
+    flipping every site twice is the identity; sweeps at β=0 flip every spin every sweep (ΔE<=0 or U<1)."""
+    L, D, R = 64, 3, 1024
+    X = rb.GraphEA(L, D, replicas=R, rng=np.random.default_rng(0))
+    st = X._ensure_state()
+    check(lib().rrrmc_state_randomize(st, 99))
+    thr = ffi.thresholds_fixed64(1.0, D)
+    check(lib().rrrmc_checkerboard_sweeps(st, ptr(thr), D, 6, 1, 0, 4))
+    E = np.zeros(R); check(lib().rrrmc_energy(st, ptr(E)))
+    Cf = X._download()
+    g = ffi.Graph.ea_int(X.A, X.J)
+    for r in (0, 511, 1023):
+        assert g.energy(Cf.chunks[r]) == E[r]
+    assert (E < -0.5 * X.N).all()  # four sweeps at β=1 are already far below the random-state energy 0
+    # β=0: thresholds saturate (p=1-2^-64): every attempt is accepted, two sweeps restore the state
+    thr0 = np.full(D, 2 ** 64 - 1, np.uint64)
+    check(lib().rrrmc_checkerboard_sweeps(st, ptr(thr0), D, 6, 2, 0, 1))
+    mid = X._download()
+    assert np.array_equal(mid.chunks, ~Cf.chunks)
+    check(lib().rrrmc_checkerboard_sweeps(st, ptr(thr0), D, 6, 2, 1, 1))
+    assert X._download() == Cf
