@@ -743,6 +743,7 @@ static rrrmc_status_t chain_drive(rrrmc_state *s, chain_params &P, rrrmc_hook_fn
     for (int guard = 0; !stop; guard++) {
         k_chain_run<SRC><<<grid, 32, 0, ctx->stream>>>(P);
         ctx->launches++;
+        s->ms_valid = false; s->chain_valid = true; // the chains own the configuration (a hook may have re-synced)
         RR_CUDA(cudaGetLastError());
         RR_CUDA(cudaMemcpyAsync(hh.data(), c->hdr + P.chain0, sizeof(chain_hdr) * P.R, cudaMemcpyDeviceToHost, ctx->stream));
         RR_CUDA(cudaMemcpyAsync(row.data(), c->d_Es, 8 * P.R * rows_per_launch, cudaMemcpyDeviceToHost, ctx->stream));

@@ -87,7 +87,7 @@ class Config:
         bits = np.atleast_2d(np.asarray(bits, dtype=np.uint8))
         R, N = bits.shape
         pad = (-N) % 64
-        packed = np.packbits(np.pad(bits, ((0, 0), (0, pad))), axis=1, bitorder="little")
+        packed = np.ascontiguousarray(np.packbits(np.pad(np.ascontiguousarray(bits), ((0, 0), (0, pad))), axis=1, bitorder="little"))
         return cls(N, R, chunks=packed.view(np.uint64))
 
     def copy(self):
