@@ -28,7 +28,7 @@ L, D, R_PER_GPU = 64, 3, 1024
 N_SITES = L ** D
 SWEEPS_PER_STEP = int(os.environ.get("BENCH_SWEEPS", "400"))
 BETA = 1.0
-PLANES_K = 6
+PLANES_K = int(os.environ.get("BENCH_K", "8"))
 SEED = 0x5EEDEA64
 METRIC = "spin-flip attempts/s, 3D EA L=64 ±J ×1024 replicas"
 UNIT = "attempts/s"

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 #include "common.cuh"
@@ -475,9 +476,17 @@ static rrrmc_status_t fill_cb_params(rrrmc_state *s, const uint64_t *thr64, int 
     p.L = g->L; p.Lh = g->L / 2; p.W = (int)s->W; p.G = (int)((s->W + 3) / 4);
     p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32);
     p.K = K;
+    RR_ARG((int64_t)g->N * s->W < ((int64_t)1 << 31), "N*W = %lld words exceeds the kernel's 32-bit indexing", (long long)(g->N * s->W));
+    p.invG = 1.0f / (float)p.G;
+    { const char *v = getenv("RRRMC_CB_VARIANT"); p.variant = v ? atoi(v) : 0; }
     for (int c = 0; c < nthr; c++) {
         for (int q = 0; q < K; q++) p.plane[q][c] = ((thr64[c] >> (63 - q)) & 1ull) ? 0xffffffffu : 0u;
         p.rem[c] = (uint32_t)((K ? (thr64[c] << K) : thr64[c]) >> 32);
+    }
+    for (int q = 0; q < K; q++) {
+        int ones = 0;
+        for (int c = 0; c < nthr; c++) ones += p.plane[q][c] != 0;
+        p.planeop[q] = ones == 0 ? 0 : (ones == nthr ? 1 : 2);
     }
     return RRRMC_OK;
 }

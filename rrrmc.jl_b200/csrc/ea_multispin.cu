@@ -86,39 +86,62 @@ __device__ __forceinline__ void class_masks(uint32_t u0, uint32_t u1, uint32_t u
 // 128 replicas). Acceptance is Metropolis (RRRMC.jl:39: ΔE<=0 always, else U<exp(-βΔE)) with U built
 // from Philox bit planes — procedure documented in DESIGN.md §"Random bits" and restated on the CPU
 // in oracle/rrrmc_oracle.c:orc_checkerboard_sweeps (the two must agree bit for bit).
+//
+// Cost model (ncu, profiles/): the kernel is integer-issue bound (LOP3 on the ALU pipe for the bit-sliced
+// logic + Philox xors, IMAD.WIDE on the FMA pipe for the Philox multiplies), not HBM bound. Hence:
+//  * plane bits of the thresholds are kernel-uniform, so each plane runs a specialised 1-, 2- or 6-LOP3 body;
+//  * the tail's first two Philox calls are issued by the converged warp (one call serves 4 lanes of a task);
+//  * index arithmetic is 32-bit with a float-reciprocal split of (site, group).
 // ------------------------------------------------------------------------------------------------
-template <int D, bool FULL>
-__global__ void __launch_bounds__(256) k_checkerboard(cb_params p, int colour)
+template <int D, bool FULL, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_checkerboard(cb_params p, int colour)
 {
     const int row_tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row_tid >= p.Lh * p.G) return;
-    const int g = row_tid % p.G, xh = row_tid / p.G;
+    const bool valid = row_tid < p.Lh * p.G;
+    const int rt = valid ? row_tid : 0;
+    const int xh = __float2int_rz(((float)rt + 0.5f) * p.invG);   // rt / G, exact for rt < 2^22
+    const int g = rt - xh * p.G;
     const int y = (D >= 2) ? blockIdx.y : 0, z = (D >= 3) ? blockIdx.z : 0;
+    const int L = p.L;
     const int x = 2 * xh + ((y + z + colour) & 1);
-    const site_geom<D> sg = make_geom<D>(p.L, x, y, z);
-    const int W = p.W;
+    // site index and neighbour sites (32-bit; N*W < 2^31 words is checked on the host)
+    const uint32_t row = (uint32_t)L * (uint32_t)(y + L * z);
+    const uint32_t i = row + x;
+    uint32_t nb[2 * D];
+    nb[0] = row + (x + 1 == L ? 0 : x + 1);
+    nb[1] = row + (x == 0 ? L - 1 : x - 1);
+    if (D >= 2) {
+        nb[2] = y + 1 == L ? i - (uint32_t)(L - 1) * L : i + L;
+        nb[3] = y == 0 ? i + (uint32_t)(L - 1) * L : i - L;
+    }
+    if (D >= 3) {
+        const uint32_t LL = (uint32_t)L * L;
+        nb[4] = z + 1 == L ? i - (uint32_t)(L - 1) * LL : i + LL;
+        nb[5] = z == 0 ? i + (uint32_t)(L - 1) * LL : i - LL;
+    }
+    const uint32_t W = p.W;
 
     uint32_t sc[4], sn[4][2 * D];
     if (FULL) {
         const uint4 *sp = reinterpret_cast<const uint4 *>(p.spins);
-        const int64_t W4 = W >> 2;
-        const uint4 c = sp[sg.i * W4 + g];
+        const uint32_t W4 = W >> 2;
+        const uint4 c = sp[i * W4 + g];
         sc[0] = c.x; sc[1] = c.y; sc[2] = c.z; sc[3] = c.w;
 #pragma unroll
         for (int k = 0; k < 2 * D; k++) {
-            const uint4 v = sp[sg.nb[k] * W4 + g];
+            const uint4 v = sp[nb[k] * W4 + g];
             sn[0][k] = v.x; sn[1][k] = v.y; sn[2][k] = v.z; sn[3][k] = v.w;
         }
     } else {
 #pragma unroll
         for (int w = 0; w < 4; w++) {
             const bool ok = 4 * g + w < W;
-            sc[w] = ok ? p.spins[sg.i * W + 4 * g + w] : 0u;
+            sc[w] = ok ? p.spins[i * W + 4 * g + w] : 0u;
 #pragma unroll
-            for (int k = 0; k < 2 * D; k++) sn[w][k] = ok ? p.spins[sg.nb[k] * W + 4 * g + w] : 0u;
+            for (int k = 0; k < 2 * D; k++) sn[w][k] = ok ? p.spins[nb[k] * W + 4 * g + w] : 0u;
         }
     }
-    const uint32_t jc = p.jcode[sg.i];
+    const uint32_t jc = p.jcode[i];
 
     uint32_t mc[4][3], eq[4], lt[4], up[4];
 #pragma unroll
@@ -127,28 +150,42 @@ __global__ void __launch_bounds__(256) k_checkerboard(cb_params p, int colour)
         unsat_planes<D>(sc[w], sn[w], jc, u0, u1, u2);
         class_masks<D>(u0, u1, u2, mc[w]);
         up[w] = mc[w][0] | mc[w][1] | mc[w][2];
-        if (!FULL && !(4 * g + w < W)) { up[w] = 0; mc[w][0] = mc[w][1] = mc[w][2] = 0; }
+        if (!valid || (!FULL && !(4 * g + w < W))) { up[w] = 0; mc[w][0] = mc[w][1] = mc[w][2] = 0; }
         eq[w] = up[w]; lt[w] = 0;
     }
 
-    const uint32_t c1 = (uint32_t)sg.i, c2 = (uint32_t)g;
+    const uint32_t c1 = i, c2 = (uint32_t)g;
     // plane phase: bit q (from the MSB) of U for every lane of the task comes from Philox call q
     for (int q = 0; q < p.K; q++) {
-        if (!(eq[0] | eq[1] | eq[2] | eq[3])) break;
         const philox_out r = philox4x32_10((uint32_t)q | p.t_hi16, c1, c2, p.t_lo, p.k0, p.k1);
         const uint32_t rr[4] = { r.x, r.y, r.z, r.w };
-        const uint32_t B0 = p.plane[q][0], B1 = p.plane[q][1], B2 = p.plane[q][2];
+        const int op = p.planeop[q];
+        if (op == 0) {                 // threshold bit 0 for every class: lanes with U bit 1 are rejected
 #pragma unroll
-        for (int w = 0; w < 4; w++) {
-            const uint32_t thr = (mc[w][0] & B0) | (mc[w][1] & B1) | (mc[w][2] & B2);
-            lt[w] |= eq[w] & ~rr[w] & thr;
-            eq[w] &= ~(rr[w] ^ thr);
+            for (int w = 0; w < 4; w++) eq[w] &= ~rr[w];
+        } else if (op == 1) {          // threshold bit 1 for every class: lanes with U bit 0 are accepted
+#pragma unroll
+            for (int w = 0; w < 4; w++) { lt[w] |= eq[w] & ~rr[w]; eq[w] &= rr[w]; }
+        } else {
+            const uint32_t B0 = p.plane[q][0], B1 = p.plane[q][1], B2 = p.plane[q][2];
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const uint32_t thr = (mc[w][0] & B0) | (mc[w][1] & B1) | (mc[w][2] & B2);
+                lt[w] |= eq[w] & ~rr[w] & thr;
+                eq[w] &= ~(rr[w] ^ thr);
+            }
         }
     }
-    // tail: undecided lanes in ascending (w,b) order take 32 fresh bits each
+    // tail: undecided lanes in ascending (w,b) order take 32 fresh bits each: the n-th one uses word n%4 of
+    // Philox call K+n/4. Calls K and K+1 are issued by the whole (converged) warp when any lane needs them.
     {
+        const int nun = __popc(eq[0]) + __popc(eq[1]) + __popc(eq[2]) + __popc(eq[3]);
+        const unsigned am = __activemask();
+        philox_out r0 = { 0, 0, 0, 0 }, r1 = { 0, 0, 0, 0 };
+        if (__any_sync(am, nun > 0)) r0 = philox4x32_10((uint32_t)p.K | p.t_hi16, c1, c2, p.t_lo, p.k0, p.k1);
+        if (__any_sync(am, nun > 4)) r1 = philox4x32_10((uint32_t)(p.K + 1) | p.t_hi16, c1, c2, p.t_lo, p.k0, p.k1);
         int n = 0;
-        philox_out r = { 0, 0, 0, 0 };
+        philox_out r = r0;
 #pragma unroll
         for (int w = 0; w < 4; w++) {
             uint32_t e = eq[w];
@@ -156,7 +193,8 @@ __global__ void __launch_bounds__(256) k_checkerboard(cb_params p, int colour)
                 const uint32_t bit = e & (0u - e);
                 e ^= bit;
                 const uint32_t rem = (mc[w][0] & bit) ? p.rem[0] : ((mc[w][1] & bit) ? p.rem[1] : p.rem[2]);
-                if ((n & 3) == 0) r = philox4x32_10((uint32_t)(p.K + (n >> 2)) | p.t_hi16, c1, c2, p.t_lo, p.k0, p.k1);
+                if (n == 4) r = r1;
+                else if (n >= 8 && (n & 3) == 0) r = philox4x32_10((uint32_t)(p.K + (n >> 2)) | p.t_hi16, c1, c2, p.t_lo, p.k0, p.k1);
                 const int m = n & 3;
                 const uint32_t V = m == 0 ? r.x : (m == 1 ? r.y : (m == 2 ? r.z : r.w));
                 if (V < rem) lt[w] |= bit;
@@ -171,16 +209,17 @@ __global__ void __launch_bounds__(256) k_checkerboard(cb_params p, int colour)
         if (!FULL && !(4 * g + w < W)) fl[w] = 0;
         sc[w] ^= fl[w];
     }
+    if (!valid) return;
     if (FULL) {
-        const int64_t W4 = W >> 2;
-        reinterpret_cast<uint4 *>(p.spins)[sg.i * W4 + g] = make_uint4(sc[0], sc[1], sc[2], sc[3]);
-        if (p.flips) reinterpret_cast<uint4 *>(p.flips)[sg.i * W4 + g] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+        const uint32_t W4 = W >> 2;
+        reinterpret_cast<uint4 *>(p.spins)[i * W4 + g] = make_uint4(sc[0], sc[1], sc[2], sc[3]);
+        if (p.flips) reinterpret_cast<uint4 *>(p.flips)[i * W4 + g] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
     } else {
 #pragma unroll
         for (int w = 0; w < 4; w++)
             if (4 * g + w < W) {
-                p.spins[sg.i * W + 4 * g + w] = sc[w];
-                if (p.flips) p.flips[sg.i * W + 4 * g + w] = fl[w];
+                p.spins[i * W + 4 * g + w] = sc[w];
+                if (p.flips) p.flips[i * W + 4 * g + w] = fl[w];
             }
     }
 }
@@ -189,10 +228,15 @@ rrrmc_status_t launch_checkerboard(rrrmc_ctx *ctx, const cb_params &p, int D, in
 {
     const bool full = (p.W % 4) == 0;
     dim3 block(256), grid(div_up((int64_t)p.Lh * p.G, 256), D >= 2 ? p.L : 1, D >= 3 ? p.L : 1);
-#define LAUNCH(DD, FF) k_checkerboard<DD, FF><<<grid, block, 0, ctx->stream>>>(p, colour)
-    if (D == 1) { if (full) LAUNCH(1, true); else LAUNCH(1, false); }
-    else if (D == 2) { if (full) LAUNCH(2, true); else LAUNCH(2, false); }
-    else if (D == 3) { if (full) LAUNCH(3, true); else LAUNCH(3, false); }
+#define LAUNCH(DD, FF, MB) k_checkerboard<DD, FF, MB><<<grid, block, 0, ctx->stream>>>(p, colour)
+    if (D == 1) { if (full) LAUNCH(1, true, 1); else LAUNCH(1, false, 1); }
+    else if (D == 2) { if (full) LAUNCH(2, true, 1); else LAUNCH(2, false, 1); }
+    else if (D == 3) {
+        if (!full) LAUNCH(3, false, 1);
+        else if (p.variant == 1) LAUNCH(3, true, 5);
+        else if (p.variant == 2) LAUNCH(3, true, 6);
+        else LAUNCH(3, true, 4);
+    }
     else { rrrmc_set_error("checkerboard: D=%d unsupported (1..3)", D); return RRRMC_ERR_UNSUPPORTED; }
 #undef LAUNCH
     ctx->launches++;

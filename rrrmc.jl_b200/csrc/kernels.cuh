@@ -12,6 +12,9 @@ struct cb_params {
     uint32_t k0, k1;        // Philox key = seed
     uint32_t t_lo, t_hi16;  // sweep counter: low 32 bits, (high bits) << 16
     int K;                  // bit planes before the per-lane tail
+    float invG;             // 1/G
+    int variant;            // occupancy variant (tuning)
+    uint8_t planeop[CB_MAXK]; // 0: threshold bit 0 for all classes, 1: bit 1 for all classes, 2: mixed
     uint32_t plane[CB_MAXK][3]; // plane[q][c-1] = all-ones iff bit (63-q) of thr64[c] is set
     uint32_t rem[3];        // bits [63-K .. 32-K] of thr64[c]
 };

@@ -37,7 +37,8 @@ def _multispin(Cfg):
     R, N = b.shape
     W = (R + 31) // 32
     pad = np.zeros((W * 32, N), np.uint8); pad[:R] = b
-    return np.ascontiguousarray(np.packbits(pad.T.reshape(N, W, 32), axis=2, bitorder="little").view(np.uint32).reshape(N, W))
+    packed = np.ascontiguousarray(np.packbits(np.ascontiguousarray(pad.T).reshape(N, W, 32), axis=2, bitorder="little"))
+    return np.ascontiguousarray(packed.reshape(N, W * 4).view(np.uint32).reshape(N, W))
 
 
 def _from_multispin(sp, R):
