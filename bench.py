@@ -28,7 +28,8 @@ L, D, R_PER_GPU = 64, 3, 1024
 N_SITES = L ** D
 SWEEPS_PER_STEP = int(os.environ.get("BENCH_SWEEPS", "400"))
 BETA = 1.0
-PLANES_K = int(os.environ.get("BENCH_K", "8"))
+PLANES_K = int(os.environ.get("BENCH_K", "5"))
+PLANES_M = int(os.environ.get("BENCH_M", "4"))
 SEED = 0x5EEDEA64
 METRIC = "spin-flip attempts/s, 3D EA L=64 ±J ×1024 replicas"
 UNIT = "attempts/s"
@@ -181,7 +182,7 @@ def run_ours(args, rank, world, local_rank):
     thr = np.array([min(int(np.exp(-beta * 4 * c) * 2.0 ** 64), 2 ** 64 - 1) for c in range(1, D + 1)], dtype=np.uint64)
 
     def step(k):
-        check(lib().rrrmc_checkerboard_sweeps(st, ptr(thr), D, PLANES_K, SEED + 1000 * rank, k * SWEEPS_PER_STEP, SWEEPS_PER_STEP))
+        check(lib().rrrmc_checkerboard_sweeps(st, ptr(thr), D, PLANES_K, PLANES_M, SEED + 1000 * rank, k * SWEEPS_PER_STEP, SWEEPS_PER_STEP))
 
     # ---- device-resident arm ("value"): inputs already in HBM, CUDA events on the launching stream ----------
     for k in range(args.warmup):
@@ -222,6 +223,7 @@ def run_ours(args, rank, world, local_rank):
     betas = np.full(R_PER_GPU, beta)
     opts = _ffi.Opts(); check(lib().rrrmc_opts_default(C.byref(opts)))
     opts.planes_K = PLANES_K
+    opts.planes_M = PLANES_M
     opts.count_accepted = 0
     info = _ffi.RunInfo()
     iters = SWEEPS_PER_STEP * N_SITES
@@ -268,7 +270,7 @@ def run_ours(args, rank, world, local_rank):
             "dtype": "u32 bit-sliced (multispin, 32 replicas/word)", "data": "synthetic",
             "config": {"workload": "GraphEA 3D L=64 ±J, checkerboard Metropolis, 1024 replicas per GPU (BASELINE configs[1])",
                        "L": L, "D": D, "replicas_per_gpu": R_PER_GPU, "beta": beta, "sweeps_per_step": SWEEPS_PER_STEP,
-                       "rng": "Philox4x32-10, exact per-(site,replica) Bernoulli via %d bit planes + 32-bit tail" % PLANES_K,
+                       "rng": "Philox4x32-10, exact per-(site,replica) Bernoulli via %d full + %d merged bit planes + 32-bit tail" % (PLANES_K, PLANES_M),
                        "parallelism": f"replica-sharded x{world}", "l2": "flushed between timed steps (256 MiB write)",
                        "accepted_counters": "off in the timed loop"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

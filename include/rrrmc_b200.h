@@ -107,11 +107,13 @@ typedef int (*rrrmc_hook_fn)(void *user, int64_t it, const double *E, const int6
 
 typedef struct {
     int    schedule;        /* RRRMC_SCHED_*; default checkerboard                                   */
-    int    planes_K;        /* checkerboard: random bit-planes before the per-lane tail (default 6)    */
+    int    planes_K;        /* checkerboard: full random bit planes, one Philox call each (default 5)  */
     int    count_accepted;  /* 1: exact per-replica accepted counters; 0: hook gets accepted = -1      */
     double staged_thr;      /* rrrMC: NaN = reference default (RRRMC.jl:163-165)                       */
     double staged_thr_fact; /* rrrMC: default 5.0 (RRRMC.jl:155)                                       */
-    int    reserved[8];
+    int    planes_M;        /* checkerboard: merged bit planes after the full ones, four per Philox
+                               call (default 4, a multiple of 4); planes_K + planes_M <= 32. See DESIGN.md §5.          */
+    int    reserved[7];
 } rrrmc_opts_t;
 rrrmc_status_t rrrmc_opts_default(rrrmc_opts_t *o);
 
@@ -147,7 +149,7 @@ rrrmc_status_t rrrmc_replay(rrrmc_state_t *s, int64_t replica, int sampler, doub
 /* Device-resident sweep loop without host round trips (what bench.py times as `value`):
  * runs `nsweeps` checkerboard sweeps starting at sweep counter `sweep0`. thr64: per-class
  * fixed-point acceptance table floor(exp(-β·ΔE_c)·2^64), ΔE_c = allΔE[c], c = 1..nclasses-1. */
-rrrmc_status_t rrrmc_checkerboard_sweeps(rrrmc_state_t *s, const uint64_t *thr64, int nthr, int planes_K,
+rrrmc_status_t rrrmc_checkerboard_sweeps(rrrmc_state_t *s, const uint64_t *thr64, int nthr, int planes_K, int planes_M,
                                          uint64_t seed, uint64_t sweep0, int64_t nsweeps);
 
 #ifdef __cplusplus

@@ -95,7 +95,7 @@ def lib():
         "orc_rrrMC": (Result, [vp, f64, i64, i64, p(np.uint64), Draws, f64, f64, HOOK, vp, vp, i64]),
         "orc_bklMC": (Result, [vp, f64, i64, i64, p(np.uint64), Draws, HOOK, vp, vp, i64]),
         "orc_check_discrete_cache": (i32, [vp, p(np.uint64), f64, p(np.int64), i64]),
-        "orc_checkerboard_sweeps": (None, [i32, i32, i64, p(np.uint32), p(np.int8), p(np.uint64), i32,
+        "orc_checkerboard_sweeps": (None, [i32, i32, i64, p(np.uint32), p(np.int8), p(np.uint64), i32, i32,
                                            C.c_uint64, C.c_uint64, i64, vp]),
     }
     for name, (res, args) in sig.items():
@@ -339,7 +339,8 @@ def thresholds_fixed64(beta, D):
     return np.array(out, dtype=np.uint64)
 
 
-def checkerboard_sweeps(L, D, R, spins, Jfwd, thr, K, seed, sweep0, nsweeps, accepted=None):
+def checkerboard_sweeps(L, D, R, spins, Jfwd, thr, K, seed, sweep0, nsweeps, accepted=None, M=0):
+    """CPU model of the engine's checkerboard sweeps: K full bit planes, M merged planes, 32-bit tail."""
     acc_p = accepted.ctypes.data if accepted is not None else None
     lib().orc_checkerboard_sweeps(L, D, R, spins, np.ascontiguousarray(Jfwd, np.int8),
-                                  np.ascontiguousarray(thr, np.uint64), K, seed, sweep0, nsweeps, acc_p)
+                                  np.ascontiguousarray(thr, np.uint64), K, M, seed, sweep0, nsweeps, acc_p)

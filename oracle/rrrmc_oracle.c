@@ -1186,7 +1186,7 @@ orc_result orc_bklMC(orc_graph *X, double beta, int64_t iters, int64_t step, uin
  *   and accepts iff it is < bits [63-K .. 32-K] of T_c.
  * ---------------------------------------------------------------------------------------- */
 void orc_checkerboard_sweeps(int L, int D, int64_t R, uint32_t *spins, const int8_t *Jfwd,
-                             const uint64_t *thr, int K, uint64_t seed, uint64_t sweep0, int64_t nsweeps,
+                             const uint64_t *thr, int K, int M, uint64_t seed, uint64_t sweep0, int64_t nsweeps,
                              int64_t *accepted)
 {
     int64_t N = 1; for (int d = 0; d < D; d++) N *= L;
@@ -1239,12 +1239,33 @@ void orc_checkerboard_sweeps(int L, int D, int64_t R, uint32_t *spins, const int
                             if (ub != tb) { und[l] = 0; flip[l] = (ub < tb); }
                         }
                     }
-                    int n = 0;
+                    /* merged planes: still-undecided lanes are sparse, so the four words are overlaid on one:
+                     * at bit position b the lowest word with an undecided lane is "merged" and reads bit b of
+                     * word j%4 of call K+j/4 as bit K+j of its U; lanes shadowed at their position keep K bits. */
+                    int merged[128];
+                    for (int l = 0; l < 128; l++) merged[l] = 0;
+                    if (M > 0) {
+                        for (int b = 0; b < 32; b++)
+                            for (int w = 0; w < 4; w++)
+                                if (und[32 * w + b]) { merged[32 * w + b] = 1; break; }
+                        for (int j = 0; j < M; j++) {
+                            if ((j & 3) == 0) { ctr[0] = (uint32_t)(K + j / 4) | ((uint32_t)(t >> 32) << 16); orc_philox4x32_10(ctr, key, out); }
+                            for (int l = 0; l < 128; l++) {
+                                if (!und[l] || !merged[l]) continue;
+                                int ub = (out[j & 3] >> (l & 31)) & 1;
+                                int tb = (int)((thr[cls[l] - 1] >> (63 - K - j)) & 1);
+                                if (ub != tb) { und[l] = 0; flip[l] = (ub < tb); }
+                            }
+                        }
+                    }
+                    /* tail: the n-th lane still undecided takes 32 fresh bits against its next 32 threshold bits */
+                    int n = 0, call0 = K + (M + 3) / 4;
                     for (int l = 0; l < 128; l++) {
                         if (!und[l]) continue;
-                        if ((n & 3) == 0) { ctr[0] = (uint32_t)(K + n / 4) | ((uint32_t)(t >> 32) << 16); orc_philox4x32_10(ctr, key, out); }
+                        if ((n & 3) == 0) { ctr[0] = (uint32_t)(call0 + n / 4) | ((uint32_t)(t >> 32) << 16); orc_philox4x32_10(ctr, key, out); }
                         uint32_t V = out[n & 3];
-                        uint32_t rem32 = (uint32_t)((K ? (thr[cls[l] - 1] << K) : thr[cls[l] - 1]) >> 32);
+                        int used = merged[l] ? K + M : K;
+                        uint32_t rem32 = (uint32_t)((used ? (thr[cls[l] - 1] << used) : thr[cls[l] - 1]) >> 32);
                         flip[l] = V < rem32;
                         n++;
                     }

@@ -134,7 +134,7 @@ int orc_check_discrete_cache(orc_graph *g, uint64_t *chunks, double beta, const 
  * J: forward-bond couplings [N][D] (±1) for bonds to x+1,y+1,(z+1).
  * thr: per-class 64-bit fixed-point acceptance thresholds floor(exp(-β·ΔE_c)·2^64), c=1..D (ΔE=4c). */
 void orc_checkerboard_sweeps(int L, int D, int64_t R, uint32_t *spins, const int8_t *Jfwd,
-                             const uint64_t *thr, int K, uint64_t seed, uint64_t sweep0, int64_t nsweeps,
+                             const uint64_t *thr, int K, int M, uint64_t seed, uint64_t sweep0, int64_t nsweeps,
                              int64_t *accepted /* [R] += */);
 
 #ifdef __cplusplus

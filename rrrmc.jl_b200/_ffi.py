@@ -17,7 +17,7 @@ HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POIN
 
 class Opts(C.Structure):
     _fields_ = [("schedule", C.c_int), ("planes_K", C.c_int), ("count_accepted", C.c_int),
-                ("staged_thr", C.c_double), ("staged_thr_fact", C.c_double), ("reserved", C.c_int * 8)]
+                ("staged_thr", C.c_double), ("staged_thr_fact", C.c_double), ("planes_M", C.c_int), ("reserved", C.c_int * 7)]
 
 
 class RunInfo(C.Structure):
@@ -59,7 +59,7 @@ SIGNATURES = {
     "rrrmc_rrr_mc": (_i32, _SAMPLER),
     "rrrmc_bkl_mc": (_i32, _SAMPLER),
     "rrrmc_replay": (_i32, [_vp, _i64, _i32, _f64, _i64, _i64, _vp, _vp, _vp, _i64, C.POINTER(Opts), _vp, _i64, C.POINTER(RunInfo)]),
-    "rrrmc_checkerboard_sweeps": (_i32, [_vp, _vp, _i32, _i32, _u64, _u64, _i64]),
+    "rrrmc_checkerboard_sweeps": (_i32, [_vp, _vp, _i32, _i32, _i32, _u64, _u64, _i64]),
 }
 
 _lib = None

@@ -443,7 +443,8 @@ extern "C" rrrmc_status_t rrrmc_opts_default(rrrmc_opts_t *o)
     RR_ARG(o, "opts is NULL");
     memset(o, 0, sizeof *o);
     o->schedule = RRRMC_SCHED_CHECKERBOARD;
-    o->planes_K = 6;
+    o->planes_K = 5;
+    o->planes_M = 4;
     o->count_accepted = 1;
     o->staged_thr = NAN;
     o->staged_thr_fact = 5.0;
@@ -458,7 +459,7 @@ static uint64_t fixed64(double p) // floor(p * 2^64) clamped to 2^64-1, p in [0,
     return (uint64_t)v;
 }
 
-static rrrmc_status_t fill_cb_params(rrrmc_state *s, const uint64_t *thr64, int nthr, int K, uint64_t seed, cb_params &p)
+static rrrmc_status_t fill_cb_params(rrrmc_state *s, const uint64_t *thr64, int nthr, int K, int M, uint64_t seed, cb_params &p)
 {
     rrrmc_graph *g = s->g;
     if (!(g->kind == RRRMC_EA_PM1 && g->d_jcode)) {
@@ -470,24 +471,32 @@ static rrrmc_status_t fill_cb_params(rrrmc_state *s, const uint64_t *thr64, int 
         return RRRMC_ERR_UNSUPPORTED;
     }
     RR_ARG(nthr == g->D, "expected %d acceptance thresholds (ΔE=4..%d), given %d", g->D, 4 * g->D, nthr);
-    RR_ARG(K >= 0 && K <= CB_MAXK, "planes_K must be in 0..%d, given %d", CB_MAXK, K);
+    RR_ARG(K >= 0 && M >= 0 && K + M <= CB_MAXK, "planes_K and planes_M must be >= 0 with planes_K + planes_M <= %d, given %d + %d", CB_MAXK, K, M);
+    RR_ARG(M % 4 == 0, "planes_M must be a multiple of 4 (one Philox call serves four merged planes), given %d", M);
     memset(&p, 0, sizeof p);
     p.spins = s->d_spins; p.flips = nullptr; p.jcode = g->d_jcode;
     p.L = g->L; p.Lh = g->L / 2; p.W = (int)s->W; p.G = (int)((s->W + 3) / 4);
     p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32);
-    p.K = K;
+    p.K = K; p.M = M;
     RR_ARG((int64_t)g->N * s->W < ((int64_t)1 << 31), "N*W = %lld words exceeds the kernel's 32-bit indexing", (long long)(g->N * s->W));
     p.invG = 1.0f / (float)p.G;
     { const char *v = getenv("RRRMC_CB_VARIANT"); p.variant = v ? atoi(v) : 0; }
+    auto after = [](uint64_t t, int used) { return (uint32_t)((used ? (t << used) : t) >> 32); }; // next 32 bits
     for (int c = 0; c < nthr; c++) {
-        for (int q = 0; q < K; q++) p.plane[q][c] = ((thr64[c] >> (63 - q)) & 1ull) ? 0xffffffffu : 0u;
-        p.rem[c] = (uint32_t)((K ? (thr64[c] << K) : thr64[c]) >> 32);
+        for (int q = 0; q < K + M; q++) p.plane[q][c] = ((thr64[c] >> (63 - q)) & 1ull) ? 0xffffffffu : 0u;
+        p.rem[c] = after(thr64[c], K);
+        p.remM[c] = after(thr64[c], K + M);
     }
-    for (int q = 0; q < K; q++) {
+    for (int q = 0; q < K + M; q++) {
         int ones = 0;
         for (int c = 0; c < nthr; c++) ones += p.plane[q][c] != 0;
         p.planeop[q] = ones == 0 ? 0 : (ones == nthr ? 1 : 2);
     }
+    p.Ku = 0;
+    while (p.Ku < K && p.planeop[p.Ku] != 2) p.Ku++;
+    p.Kz = 0;
+    while (p.Kz < p.Ku && p.planeop[p.Kz] == 0) p.Kz++;
+    for (int r = 0; r < 10; r++) { p.rk[r][0] = p.k0 + (uint32_t)r * 0x9E3779B9u; p.rk[r][1] = p.k1 + (uint32_t)r * 0xBB67AE85u; }
     return RRRMC_OK;
 }
 
@@ -500,7 +509,7 @@ static rrrmc_status_t run_sweep(rrrmc_state *s, cb_params &p, uint64_t t)
     return RRRMC_OK;
 }
 
-extern "C" rrrmc_status_t rrrmc_checkerboard_sweeps(rrrmc_state_t *s, const uint64_t *thr64, int nthr, int K,
+extern "C" rrrmc_status_t rrrmc_checkerboard_sweeps(rrrmc_state_t *s, const uint64_t *thr64, int nthr, int K, int M,
                                                     uint64_t seed, uint64_t sweep0, int64_t nsweeps)
 {
     RR_ARG(s && thr64, "NULL argument");
@@ -508,7 +517,7 @@ extern "C" rrrmc_status_t rrrmc_checkerboard_sweeps(rrrmc_state_t *s, const uint
     RR_CUDA(cudaSetDevice(s->g->ctx->device));
     RR_TRY(chain_sync_to_multispin(s));
     cb_params p;
-    RR_TRY(fill_cb_params(s, thr64, nthr, K, seed, p));
+    RR_TRY(fill_cb_params(s, thr64, nthr, K, M, seed, p));
     for (int64_t k = 0; k < nsweeps; k++) RR_TRY(run_sweep(s, p, sweep0 + (uint64_t)k));
     s->energy_valid = false; s->chain_valid = false;
     return RRRMC_OK;
@@ -537,7 +546,7 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
     uint64_t thr[3];
     for (int c = 1; c <= g->D; c++) thr[c - 1] = fixed64(exp(-beta * 4.0 * c));
     cb_params p;
-    RR_TRY(fill_cb_params(s, thr, g->D, o->planes_K, seed, p));
+    RR_TRY(fill_cb_params(s, thr, g->D, o->planes_K, o->planes_M, seed, p));
     const int64_t N = g->N;
     const int64_t nsweeps = (iters + N - 1) / N, step_sw = std::max<int64_t>(1, (step + N - 1) / N);
     const bool count = o->count_accepted != 0;

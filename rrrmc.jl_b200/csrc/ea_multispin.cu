@@ -84,23 +84,42 @@ __device__ __forceinline__ void class_masks(uint32_t u0, uint32_t u1, uint32_t u
 // ------------------------------------------------------------------------------------------------
 // Checkerboard Metropolis half-sweep. One thread = one task (site of the active colour, group of
 // 128 replicas). Acceptance is Metropolis (RRRMC.jl:39: ΔE<=0 always, else U<exp(-βΔE)) with U built
-// from Philox bit planes — procedure documented in DESIGN.md §"Random bits" and restated on the CPU
-// in oracle/rrrmc_oracle.c:orc_checkerboard_sweeps (the two must agree bit for bit).
+// from Philox bits — procedure documented in DESIGN.md §5 and restated on the CPU in
+// oracle/rrrmc_oracle.c:orc_checkerboard_sweeps (the two must agree bit for bit).
 //
 // Cost model (ncu, profiles/): the kernel is integer-issue bound (LOP3 on the ALU pipe for the bit-sliced
 // logic + Philox xors, IMAD.WIDE on the FMA pipe for the Philox multiplies), not HBM bound. Hence:
-//  * plane bits of the thresholds are kernel-uniform, so each plane runs a specialised 1-, 2- or 6-LOP3 body;
-//  * the tail's first two Philox calls are issued by the converged warp (one call serves 4 lanes of a task);
+//  * the leading planes whose threshold bit is the same for every class do not depend on the spins: they
+//    run first, while the seven 128-bit loads of the task are still in flight;
+//  * once undecided lanes are sparse the four words of the task are overlaid on one ("merged planes"), so
+//    one Philox call serves four planes instead of one;
+//  * the per-lane 32-bit tail is a rare slow path;
 //  * index arithmetic is 32-bit with a float-reciprocal split of (site, group).
 // ------------------------------------------------------------------------------------------------
+// Philox4x32-10 with the ten round keys precomputed on the host (they are kernel-uniform): the xors read them
+// straight from the constant bank instead of re-deriving them on the uniform datapath in every call.
+__device__ __forceinline__ philox_out philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const cb_params &p)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ p.rk[r][0];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ p.rk[r][1];
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+    }
+    philox_out o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+#define CB_PHILOX(ctr0) philox4x32_10_rk((uint32_t)(ctr0) | p.t_hi16, c1, c2, p.t_lo, p)
+
 template <int D, bool FULL, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_checkerboard(cb_params p, int colour)
+__global__ void __launch_bounds__(256, MINB) k_checkerboard(const __grid_constant__ cb_params p, int colour)
 {
     const int row_tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = row_tid < p.Lh * p.G;
-    const int rt = valid ? row_tid : 0;
-    const int xh = __float2int_rz(((float)rt + 0.5f) * p.invG);   // rt / G, exact for rt < 2^22
-    const int g = rt - xh * p.G;
+    if (row_tid >= p.Lh * p.G) return;
+    const int xh = __float2int_rz(((float)row_tid + 0.5f) * p.invG);   // row_tid / G, exact for row_tid < 2^22
+    const int g = row_tid - xh * p.G;
     const int y = (D >= 2) ? blockIdx.y : 0, z = (D >= 3) ? blockIdx.z : 0;
     const int L = p.L;
     const int x = 2 * xh + ((y + z + colour) & 1);
@@ -142,28 +161,58 @@ __global__ void __launch_bounds__(256, MINB) k_checkerboard(cb_params p, int col
         }
     }
     const uint32_t jc = p.jcode[i];
-
-    uint32_t mc[4][3], eq[4], lt[4], up[4];
-#pragma unroll
-    for (int w = 0; w < 4; w++) {
-        uint32_t u0, u1, u2;
-        unsat_planes<D>(sc[w], sn[w], jc, u0, u1, u2);
-        class_masks<D>(u0, u1, u2, mc[w]);
-        up[w] = mc[w][0] | mc[w][1] | mc[w][2];
-        if (!valid || (!FULL && !(4 * g + w < W))) { up[w] = 0; mc[w][0] = mc[w][1] = mc[w][2] = 0; }
-        eq[w] = up[w]; lt[w] = 0;
-    }
-
     const uint32_t c1 = i, c2 = (uint32_t)g;
-    // plane phase: bit q (from the MSB) of U for every lane of the task comes from Philox call q
-    for (int q = 0; q < p.K; q++) {
-        const philox_out r = philox4x32_10((uint32_t)q | p.t_hi16, c1, c2, p.t_lo, p.k0, p.k1);
+
+    // ΔE classes of the four words (spin dependent)
+    uint32_t mc[4][3], up[4], eq[4], lt[4];
+    // acc = "U < thr decided", und = "U == thr so far", before the spins are known
+    uint32_t acc[4] = { 0u, 0u, 0u, 0u }, und[4] = { ~0u, ~0u, ~0u, ~0u };
+    auto classes = [&]() {
+        // keep the spin-dependent work behind the spin-independent planes: the loads issued above stay in flight
+        // while the first Philox calls run (ptxas would otherwise consume them first to free registers).
+        // p.zero is always 0; the data dependency on `und` is what pins the order.
+#pragma unroll
+        for (int w = 0; w < 4; w++) sc[w] ^= und[w] & p.zero;
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            uint32_t u0, u1, u2;
+            unsat_planes<D>(sc[w], sn[w], jc, u0, u1, u2);
+            class_masks<D>(u0, u1, u2, mc[w]);
+            up[w] = mc[w][0] | mc[w][1] | mc[w][2];
+            if (!FULL && !(4 * g + w < W)) { up[w] = 0; mc[w][0] = mc[w][1] = mc[w][2] = 0; }
+            eq[w] = up[w] & und[w]; lt[w] = up[w] & acc[w];
+        }
+    };
+    // merged planes (see below): mg = lanes of each word that own their bit position, em/lm = eq/lt of the overlay
+    uint32_t mg[4] = { 0u, 0u, 0u, 0u }, mm[3] = { 0u, 0u, 0u }, em = 0u, lm = 0u;
+
+    // plane phase, part 1: bit q (from the MSB) of U for every lane of the task comes from Philox call q. While the
+    // threshold bit is class-independent (q < Ku) the comparison needs no spins.
+    for (int q = 0; q < p.Kz; q++) {   // leading zeros of every threshold: lanes with U bit 1 are rejected
+        const philox_out r = CB_PHILOX(q);
+        und[0] &= ~r.x; und[1] &= ~r.y; und[2] &= ~r.z; und[3] &= ~r.w;
+    }
+    for (int q = p.Kz; q < p.Ku; q++) {
+        const philox_out r = CB_PHILOX(q);
+        const uint32_t rr[4] = { r.x, r.y, r.z, r.w };
+        if (p.planeop[q] == 0) {
+#pragma unroll
+            for (int w = 0; w < 4; w++) und[w] &= ~rr[w];
+        } else {                       // threshold bit 1: lanes with U bit 0 are accepted
+#pragma unroll
+            for (int w = 0; w < 4; w++) { acc[w] |= und[w] & ~rr[w]; und[w] &= rr[w]; }
+        }
+    }
+    classes();
+    // plane phase, part 2: the remaining full planes
+    for (int q = p.Ku; q < p.K; q++) {
+        const philox_out r = CB_PHILOX(q);
         const uint32_t rr[4] = { r.x, r.y, r.z, r.w };
         const int op = p.planeop[q];
-        if (op == 0) {                 // threshold bit 0 for every class: lanes with U bit 1 are rejected
+        if (op == 0) {
 #pragma unroll
             for (int w = 0; w < 4; w++) eq[w] &= ~rr[w];
-        } else if (op == 1) {          // threshold bit 1 for every class: lanes with U bit 0 are accepted
+        } else if (op == 1) {
 #pragma unroll
             for (int w = 0; w < 4; w++) { lt[w] |= eq[w] & ~rr[w]; eq[w] &= rr[w]; }
         } else {
@@ -176,25 +225,44 @@ __global__ void __launch_bounds__(256, MINB) k_checkerboard(cb_params p, int col
             }
         }
     }
-    // tail: undecided lanes in ascending (w,b) order take 32 fresh bits each: the n-th one uses word n%4 of
-    // Philox call K+n/4. Calls K and K+1 are issued by the whole (converged) warp when any lane needs them.
-    {
-        const int nun = __popc(eq[0]) + __popc(eq[1]) + __popc(eq[2]) + __popc(eq[3]);
-        const unsigned am = __activemask();
-        philox_out r0 = { 0, 0, 0, 0 }, r1 = { 0, 0, 0, 0 };
-        if (__any_sync(am, nun > 0)) r0 = philox4x32_10((uint32_t)p.K | p.t_hi16, c1, c2, p.t_lo, p.k0, p.k1);
-        if (__any_sync(am, nun > 4)) r1 = philox4x32_10((uint32_t)(p.K + 1) | p.t_hi16, c1, c2, p.t_lo, p.k0, p.k1);
+    // merged planes: undecided lanes are sparse now, so overlay the four words on one. At every bit position the
+    // lowest word with an undecided lane owns the merged lane; bit K+j of its U is that bit of word j%4 of call
+    // K+j/4. Lanes shadowed at their position stay undecided with K bits consumed (slow path).
+    const int ncalls = p.K + (p.M >> 2);
+    if (p.M > 0) {
+        mg[0] = eq[0]; mg[1] = eq[1] & ~eq[0]; mg[2] = eq[2] & ~(eq[0] | eq[1]); mg[3] = eq[3] & ~(eq[0] | eq[1] | eq[2]);
+        em = eq[0] | eq[1] | eq[2] | eq[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) mm[c] = (mc[0][c] & mg[0]) | (mc[1][c] & mg[1]) | (mc[2][c] & mg[2]) | (mc[3][c] & mg[3]);
+        for (int call = p.K; call < ncalls; call++) {
+            const philox_out r = CB_PHILOX(call);
+            const uint32_t rr[4] = { r.x, r.y, r.z, r.w };
+            const int q0 = p.K + ((call - p.K) << 2);
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const uint32_t thr = (mm[0] & p.plane[q0 + jj][0]) | (mm[1] & p.plane[q0 + jj][1]) | (mm[2] & p.plane[q0 + jj][2]);
+                lm |= em & ~rr[jj] & thr;
+                em &= ~(rr[jj] ^ thr);
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < 4; w++) { lt[w] |= lm & mg[w]; eq[w] &= em | ~mg[w]; }
+    }
+
+    // slow path (rare): the n-th lane still undecided, in ascending (word, bit) order, takes word n%4 of call
+    // K+M/4+n/4 against the next 32 bits of its threshold.
+    if (eq[0] | eq[1] | eq[2] | eq[3]) {
         int n = 0;
-        philox_out r = r0;
+        philox_out r = CB_PHILOX(ncalls);
 #pragma unroll
         for (int w = 0; w < 4; w++) {
             uint32_t e = eq[w];
             while (e) {
                 const uint32_t bit = e & (0u - e);
                 e ^= bit;
-                const uint32_t rem = (mc[w][0] & bit) ? p.rem[0] : ((mc[w][1] & bit) ? p.rem[1] : p.rem[2]);
-                if (n == 4) r = r1;
-                else if (n >= 8 && (n & 3) == 0) r = philox4x32_10((uint32_t)(p.K + (n >> 2)) | p.t_hi16, c1, c2, p.t_lo, p.k0, p.k1);
+                const int c = (mc[w][0] & bit) ? 0 : ((mc[w][1] & bit) ? 1 : 2);
+                const uint32_t rem = (mg[w] & bit) ? p.remM[c] : p.rem[c];
+                if (n >= 4 && (n & 3) == 0) r = CB_PHILOX(ncalls + (n >> 2));
                 const int m = n & 3;
                 const uint32_t V = m == 0 ? r.x : (m == 1 ? r.y : (m == 2 ? r.z : r.w));
                 if (V < rem) lt[w] |= bit;
@@ -209,7 +277,6 @@ __global__ void __launch_bounds__(256, MINB) k_checkerboard(cb_params p, int col
         if (!FULL && !(4 * g + w < W)) fl[w] = 0;
         sc[w] ^= fl[w];
     }
-    if (!valid) return;
     if (FULL) {
         const uint32_t W4 = W >> 2;
         reinterpret_cast<uint4 *>(p.spins)[i * W4 + g] = make_uint4(sc[0], sc[1], sc[2], sc[3]);
@@ -223,18 +290,21 @@ __global__ void __launch_bounds__(256, MINB) k_checkerboard(cb_params p, int col
             }
     }
 }
+#undef CB_PHILOX
 
 rrrmc_status_t launch_checkerboard(rrrmc_ctx *ctx, const cb_params &p, int D, int colour)
 {
     const bool full = (p.W % 4) == 0;
-    dim3 block(256), grid(div_up((int64_t)p.Lh * p.G, 256), D >= 2 ? p.L : 1, D >= 3 ? p.L : 1);
+    const int bs = (p.variant & 8) ? 128 : 256;
+    dim3 block(bs), grid(div_up((int64_t)p.Lh * p.G, bs), D >= 2 ? p.L : 1, D >= 3 ? p.L : 1);
 #define LAUNCH(DD, FF, MB) k_checkerboard<DD, FF, MB><<<grid, block, 0, ctx->stream>>>(p, colour)
     if (D == 1) { if (full) LAUNCH(1, true, 1); else LAUNCH(1, false, 1); }
     else if (D == 2) { if (full) LAUNCH(2, true, 1); else LAUNCH(2, false, 1); }
     else if (D == 3) {
         if (!full) LAUNCH(3, false, 1);
-        else if (p.variant == 1) LAUNCH(3, true, 5);
-        else if (p.variant == 2) LAUNCH(3, true, 6);
+        else if ((p.variant & 7) == 1) LAUNCH(3, true, 5);
+        else if ((p.variant & 7) == 2) LAUNCH(3, true, 6);
+        else if ((p.variant & 7) == 3) LAUNCH(3, true, 3);
         else LAUNCH(3, true, 4);
     }
     else { rrrmc_set_error("checkerboard: D=%d unsupported (1..3)", D); return RRRMC_ERR_UNSUPPORTED; }

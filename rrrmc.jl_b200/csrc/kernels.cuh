@@ -11,12 +11,18 @@ struct cb_params {
     int L, Lh, W, G;        // lattice side, L/2, words per site, 128-replica groups per site
     uint32_t k0, k1;        // Philox key = seed
     uint32_t t_lo, t_hi16;  // sweep counter: low 32 bits, (high bits) << 16
-    int K;                  // bit planes before the per-lane tail
+    int K;                  // full bit planes (one Philox call per plane)
+    int Ku;                 // leading planes whose threshold bit is class-independent (spin-independent part), <= K
+    int Kz;                 // leading planes whose threshold bit is 0 for every class, <= Ku
+    uint32_t rk[10][2];     // Philox round keys: key + r*(0x9E3779B9, 0xBB67AE85)
+    int M;                  // merged planes after the full ones (one Philox call per four planes)
     float invG;             // 1/G
     int variant;            // occupancy variant (tuning)
-    uint8_t planeop[CB_MAXK]; // 0: threshold bit 0 for all classes, 1: bit 1 for all classes, 2: mixed
+    uint32_t zero;          // always 0 (opaque to ptxas: orders spin-dependent work after the first planes)
+    uint8_t planeop[CB_MAXK]; // q < K+M. 0: threshold bit 0 for all classes, 1: bit 1 for all classes, 2: mixed
     uint32_t plane[CB_MAXK][3]; // plane[q][c-1] = all-ones iff bit (63-q) of thr64[c] is set
     uint32_t rem[3];        // bits [63-K .. 32-K] of thr64[c]
+    uint32_t remM[3];       // bits [63-K-M .. 32-K-M] of thr64[c]
 };
 
 rrrmc_status_t launch_checkerboard(rrrmc_ctx *ctx, const cb_params &p, int D, int colour);

@@ -342,13 +342,15 @@ def _run(fn, X, beta, iters, seed, step, hook, C0, quiet, opts, name):
     return (Es[:, 0] if R == 1 else Es), Cout
 
 
-def _opts(schedule=None, planes_K=None, count_accepted=None, staged_thr=None, staged_thr_fact=None):
+def _opts(schedule=None, planes_K=None, count_accepted=None, staged_thr=None, staged_thr_fact=None, planes_M=None):
     o = _ffi.Opts()
     check(lib().rrrmc_opts_default(C.byref(o)))
     if schedule is not None:
         o.schedule = {"checkerboard": _ffi.SCHED_CHECKERBOARD, "random": _ffi.SCHED_RANDOM_SITE}[schedule]
     if planes_K is not None:
         o.planes_K = planes_K
+    if planes_M is not None:
+        o.planes_M = planes_M
     if count_accepted is not None:
         o.count_accepted = int(count_accepted)
     if staged_thr is not None:
@@ -359,7 +361,7 @@ def _opts(schedule=None, planes_K=None, count_accepted=None, staged_thr=None, st
 
 
 def standardMC(X, β, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, quiet=False,
-               schedule=None, planes_K=None, count_accepted=None):
+               schedule=None, planes_K=None, planes_M=None, count_accepted=None):
     """standardMC(X, β, iters; seed, step, hook, C0, quiet) (src/RRRMC.jl:81-127) -> (Es, C).
 
     schedule="random" is the reference's order (i = rand(1:N) per attempt, one chain per lane);
@@ -368,7 +370,7 @@ def standardMC(X, β, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, q
     if schedule is None:
         schedule = "checkerboard" if (isinstance(X, GraphEA) and set(X.LEV) == {-1, 1} and X.L % 2 == 0 and X.D <= 3) else "random"
     return _run(lib().rrrmc_standard_mc, X, β, iters, seed, step, hook, C0, quiet,
-                _opts(schedule, planes_K, count_accepted), "standardMC")
+                _opts(schedule, planes_K, count_accepted, planes_M=planes_M), "standardMC")
 
 
 def rrrMC(X, β, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, staged_thr=float("nan"),

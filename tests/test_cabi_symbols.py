@@ -33,7 +33,7 @@ def test_version_and_opts_default():
     import ctypes as C
     o = _ffi.Opts()
     assert _ffi.lib().rrrmc_opts_default(C.byref(o)) == 0
-    assert o.planes_K == 6 and o.staged_thr_fact == 5.0 and np.isnan(o.staged_thr) and o.schedule == 0
+    assert o.planes_K == 5 and o.planes_M == 4 and o.staged_thr_fact == 5.0 and np.isnan(o.staged_thr) and o.schedule == 0
 
 
 def test_no_device_fails_loudly():

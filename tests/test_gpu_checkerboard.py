@@ -47,21 +47,22 @@ def _from_multispin(sp, R):
     return rb.Config.from_bits(bits.T)
 
 
-@pytest.mark.parametrize("L,D,R,K,beta", [(4, 2, 32, 6, 0.5), (6, 2, 96, 3, 1.0), (4, 3, 128, 6, 0.7), (6, 3, 160, 0, 1.2),
-                                          (8, 3, 256, 8, 0.3), (2, 3, 64, 6, 0.9), (4, 1, 32, 4, 0.6), (8, 3, 100, 6, 2.0)])
-def test_checkerboard_bit_exact_vs_cpu_model(L, D, R, K, beta):
+@pytest.mark.parametrize("L,D,R,K,M,beta", [(4, 2, 32, 6, 0, 0.5), (6, 2, 96, 3, 8, 1.0), (4, 3, 128, 6, 8, 0.7), (6, 3, 160, 0, 0, 1.2),
+                                            (8, 3, 256, 8, 4, 0.3), (2, 3, 64, 6, 8, 0.9), (4, 1, 32, 4, 4, 0.6), (8, 3, 100, 6, 8, 2.0),
+                                            (8, 3, 512, 0, 4, 0.2), (8, 3, 384, 1, 12, 0.4), (6, 3, 128, 4, 28, 1.0), (8, 2, 1024, 7, 8, 1.0)])
+def test_checkerboard_bit_exact_vs_cpu_model(L, D, R, K, M, beta):
     A, J = ea_instance(L, D, seed=L * 10 + D)
     X = rb.GraphEA(L, D, replicas=R, A=A, J=J)
     C0 = rb.Config(X.N, R, rng=np.random.default_rng(7))
     thr = ffi.thresholds_fixed64(beta, D)
     seed, nsw = 0xC0FFEE1234, 5
     X._upload(C0)
-    check(lib().rrrmc_checkerboard_sweeps(X._state, ptr(thr), D, K, seed, 3, nsw))
+    check(lib().rrrmc_checkerboard_sweeps(X._state, ptr(thr), D, K, M, seed, 3, nsw))
     got = X._download()
     Rp = ((R + 31) // 32) * 32
     sp = _multispin(C0)
     acc = np.zeros(Rp, np.int64)
-    ffi.checkerboard_sweeps(L, D, Rp, sp, _fwd(A, J, L, D), thr, K, seed, 3, nsw, acc)
+    ffi.checkerboard_sweeps(L, D, Rp, sp, _fwd(A, J, L, D), thr, K, seed, 3, nsw, acc, M=M)
     want = _from_multispin(sp, R)
     assert got == want
     assert not (got == C0)
@@ -79,13 +80,13 @@ def test_standardMC_checkerboard_energies_and_accepted():
         seen.append((it, np.array(acc), np.array(E), C.chunks.copy()))
         return True
     N = X.N
-    Es, Cf = rb.standardMC(X, beta, 6 * N, step=2 * N, seed=77, C0=C0, hook=hook, quiet=True, planes_K=6)
+    Es, Cf = rb.standardMC(X, beta, 6 * N, step=2 * N, seed=77, C0=C0, hook=hook, quiet=True, planes_K=6, planes_M=4)
     assert Es.shape == (3, R) and [s[0] for s in seen] == [2 * N, 4 * N, 6 * N]
     # CPU model with the same seed / thresholds
     sp = _multispin(C0); acc = np.zeros(R, np.int64)
     thr = ffi.thresholds_fixed64(beta, D)
     for k in range(3):
-        ffi.checkerboard_sweeps(L, D, R, sp, _fwd(A, J, L, D), thr, 6, 77, 2 * k, 2, acc)
+        ffi.checkerboard_sweeps(L, D, R, sp, _fwd(A, J, L, D), thr, 6, 77, 2 * k, 2, acc, M=4)
         cfg = _from_multispin(sp, R)
         assert np.array_equal(seen[k][3], cfg.chunks)
         assert np.array_equal(seen[k][1], acc)                       # exact accepted counters
@@ -125,7 +126,7 @@ def test_full_size_properties_L64_R1024():
     st = X._ensure_state()
     check(lib().rrrmc_state_randomize(st, 99))
     thr = ffi.thresholds_fixed64(1.0, D)
-    check(lib().rrrmc_checkerboard_sweeps(st, ptr(thr), D, 6, 1, 0, 4))
+    check(lib().rrrmc_checkerboard_sweeps(st, ptr(thr), D, 6, 8, 1, 0, 4))
     E = np.zeros(R); check(lib().rrrmc_energy(st, ptr(E)))
     Cf = X._download()
     g = ffi.Graph.ea_int(X.A, X.J)
@@ -134,8 +135,8 @@ def test_full_size_properties_L64_R1024():
     assert (E < -0.5 * X.N).all()  # four sweeps at β=1 are already far below the random-state energy 0
     # β=0: thresholds saturate (p=1-2^-64): every attempt is accepted, two sweeps restore the state
     thr0 = np.full(D, 2 ** 64 - 1, np.uint64)
-    check(lib().rrrmc_checkerboard_sweeps(st, ptr(thr0), D, 6, 2, 0, 1))
+    check(lib().rrrmc_checkerboard_sweeps(st, ptr(thr0), D, 6, 8, 2, 0, 1))
     mid = X._download()
     assert np.array_equal(mid.chunks, ~Cf.chunks)
-    check(lib().rrrmc_checkerboard_sweeps(st, ptr(thr0), D, 6, 2, 1, 1))
+    check(lib().rrrmc_checkerboard_sweeps(st, ptr(thr0), D, 6, 8, 2, 1, 1))
     assert X._download() == Cf
