@@ -61,14 +61,35 @@ rrrmc_status_t rrrmc_ctx_flush_l2(rrrmc_ctx_t *ctx);
  * J: [N*2D] aligned slot-for-slot with A (gen_J, EA.jl:45-71); int64 for PM1/INT, double for F64. */
 rrrmc_status_t rrrmc_graph_ea_create(rrrmc_ctx_t *ctx, int L, int D, int coupling_kind,
                                      const int64_t *A, const void *J, rrrmc_graph_t **out);
+#define RRRMC_SK_F64 4 /* GraphSKNormal: J is double [N*N], symmetric, zero diagonal (SK.jl:181-210) */
+#define RRRMC_SK_BIN 5 /* GraphSK: J is uint8 [N*N] of 0/1 bits, J_ij = (2b-1)/sqrt(N) (SK.jl:28-60)  */
+#define RRRMC_QT     6 /* GraphQT{fourK}: Trotter-direction ring couplings (QT.jl:42-121)              */
+#define RRRMC_QUANT  7 /* GraphQuant{fourK,G}: M Trotter slices of a classical graph (QT.jl:126-321)   */
+#define RRRMC_EMPTY  8 /* GraphEmpty as the inner graph of GraphQuant (GraphQ0T, QAliases.jl:19-31)    */
+
+/* Replaces GraphSKNormal(N) / GraphSK(N) with explicit couplings (SK.jl:181-199 / :28-49; the generators are
+ * gen_J_gauss SK.jl:170-179 and gen_J SK.jl:17-26). J: [N*N] row-major, symmetric, zero diagonal; double for
+ * RRRMC_SK_F64, uint8 0/1 for RRRMC_SK_BIN. */
+rrrmc_status_t rrrmc_graph_sk_create(rrrmc_ctx_t *ctx, int64_t N, int coupling_kind, const void *J, rrrmc_graph_t **out);
+/* Replaces GraphQuant(Nk, M, Γ, β, Gconstr, args...) (QT.jl:163-170) for the inner graphs on this path:
+ * inner_kind RRRMC_SK_BIN (GraphQSKT, QAliases.jl:34-43), RRRMC_SK_F64 (GraphQSKNormalT, :46-47) or RRRMC_EMPTY
+ * (GraphQ0T, :19-31; J_inner NULL). All M slices share J_inner [Nk*Nk]; fourK = round(2/β·log coth(βΓ/M), digits=8). */
+rrrmc_status_t rrrmc_graph_quant_create(rrrmc_ctx_t *ctx, int64_t Nk, int64_t M, double Gamma, double beta,
+                                        int inner_kind, const void *J_inner, rrrmc_graph_t **out);
+/* Replaces GraphQT{fourK}(N, M) (QT.jl:46-54) = inner_graph(X::GraphQuant) (Interface.jl:239-240). */
+rrrmc_status_t rrrmc_graph_qt_create(rrrmc_ctx_t *ctx, int64_t N, int64_t M, double fourK, rrrmc_graph_t **out);
+/* the fourK type parameter of a GraphQuant / GraphQT (QT.jl:42,165) */
+rrrmc_status_t rrrmc_graph_fourK(const rrrmc_graph_t *g, double *fourK);
 /* Convenience: the gen_EA adjacency itself (EA.jl:24-43) so hosts without the reference can build A. */
 rrrmc_status_t rrrmc_gen_ea_adjacency(int L, int D, int64_t *A_out /* [L^D * 2D] */);
 rrrmc_status_t rrrmc_graph_destroy(rrrmc_graph_t *g);
 
 /* getN (Interface.jl:145) */
 rrrmc_status_t rrrmc_getN(const rrrmc_graph_t *g, int64_t *N);
-/* neighbors(X, i) (Interface.jl:158; EA.jl:292): distinct neighbours of 1-based site i, ascending. */
+/* neighbors(X, i) (Interface.jl:158; EA.jl:292; Common.jl:78-92 AllButOne; QT.jl:105-108, :288-321), in the
+ * reference's iteration order. `out` must have room for rrrmc_max_neighbors entries. */
 rrrmc_status_t rrrmc_neighbors(const rrrmc_graph_t *g, int64_t site, int64_t *out, int *n);
+rrrmc_status_t rrrmc_max_neighbors(const rrrmc_graph_t *g, int64_t *n);
 /* allΔE(X) (Interface.jl:200-201; EA.jl:293-309): sorted non-negative |ΔE| values. out has room for 64. */
 rrrmc_status_t rrrmc_allDE(const rrrmc_graph_t *g, double *out, int *n);
 
@@ -95,6 +116,16 @@ rrrmc_status_t rrrmc_all_delta_energy(rrrmc_state_t *s, int64_t replica, double 
 rrrmc_status_t rrrmc_spinflip(rrrmc_state_t *s, int64_t site, const uint32_t *replica_mask);
 /* magnetisation Σσ per replica (hook-side observable). */
 rrrmc_status_t rrrmc_magnetization(rrrmc_state_t *s, double *m_out);
+/* delta_energy_residual(X, C, i) (Interface.jl:254-261; QT.jl:270-281): dE_out[R]. 0 for single graphs.
+ * Like the reference it reads the caches: call rrrmc_energy first. */
+rrrmc_status_t rrrmc_delta_energy_residual(rrrmc_state_t *s, int64_t site, double *dE_out);
+/* GraphQuant observables for hooks, per replica: transverse_mag(X, C, β) (QT.jl:113-121) -> out[R];
+ * Qenergy(X, C) (QT.jl:253-268) -> out[R]; Renergies(X) (QT.jl:201-211) -> out[R*M]; overlaps(X) (QT.jl:213-251)
+ * -> out[R*(M/2)]. They (re)compute the slice caches from the current configuration. */
+rrrmc_status_t rrrmc_transverse_mag(rrrmc_state_t *s, double beta, double *out);
+rrrmc_status_t rrrmc_Qenergy(rrrmc_state_t *s, double *out);
+rrrmc_status_t rrrmc_Renergies(rrrmc_state_t *s, double *out);
+rrrmc_status_t rrrmc_overlaps(rrrmc_state_t *s, double *out);
 
 /* ---- samplers ------------------------------------------------------------------------------ */
 /* hook(it, X, C, accepted, E)::Bool of RRRMC.jl:61-64,104-109, batched: E[R], accepted[R]
@@ -122,6 +153,7 @@ typedef struct {
     int64_t iters_done; /* attempts per replica actually executed                              */
     int64_t launches;   /* kernels launched by this call                                       */
     float   device_ms;  /* CUDA-event time of the sampling kernels of this call (0 if unknown) */
+    int64_t accepted_total; /* accepted moves summed over replicas (chain samplers; -1 if not counted) */
 } rrrmc_run_info_t;
 
 /* standardMC(X, β, iters; seed, step, hook, C0) (RRRMC.jl:81-127) on the batch. C0 is the state's

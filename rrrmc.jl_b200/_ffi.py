@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "lib", "librrrmc_b200.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4
-EA_PM1, EA_INT, EA_F64 = 1, 2, 3
+EA_PM1, EA_INT, EA_F64, SK_F64, SK_BIN, QT, QUANT, EMPTY = 1, 2, 3, 4, 5, 6, 7, 8
 SCHED_CHECKERBOARD, SCHED_RANDOM_SITE = 0, 1
 
 HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int64)
@@ -21,7 +21,8 @@ class Opts(C.Structure):
 
 
 class RunInfo(C.Structure):
-    _fields_ = [("nsamples", C.c_int64), ("iters_done", C.c_int64), ("launches", C.c_int64), ("device_ms", C.c_float)]
+    _fields_ = [("nsamples", C.c_int64), ("iters_done", C.c_int64), ("launches", C.c_int64), ("device_ms", C.c_float),
+                ("accepted_total", C.c_int64)]
 
 
 # every symbol include/rrrmc_b200.h declares: name -> (restype, argtypes)
@@ -39,10 +40,15 @@ SIGNATURES = {
     "rrrmc_ctx_launch_count": (_i32, [_vp, C.POINTER(C.c_uint64)]),
     "rrrmc_ctx_flush_l2": (_i32, [_vp]),
     "rrrmc_graph_ea_create": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _pp]),
+    "rrrmc_graph_sk_create": (_i32, [_vp, _i64, _i32, _vp, _pp]),
+    "rrrmc_graph_quant_create": (_i32, [_vp, _i64, _i64, _f64, _f64, _i32, _vp, _pp]),
+    "rrrmc_graph_qt_create": (_i32, [_vp, _i64, _i64, _f64, _pp]),
+    "rrrmc_graph_fourK": (_i32, [_vp, C.POINTER(C.c_double)]),
     "rrrmc_gen_ea_adjacency": (_i32, [_i32, _i32, _vp]),
     "rrrmc_graph_destroy": (_i32, [_vp]),
     "rrrmc_getN": (_i32, [_vp, C.POINTER(C.c_int64)]),
     "rrrmc_neighbors": (_i32, [_vp, _i64, _vp, C.POINTER(C.c_int)]),
+    "rrrmc_max_neighbors": (_i32, [_vp, C.POINTER(C.c_int64)]),
     "rrrmc_allDE": (_i32, [_vp, _vp, C.POINTER(C.c_int)]),
     "rrrmc_state_create": (_i32, [_vp, _i64, _pp]),
     "rrrmc_state_destroy": (_i32, [_vp]),
@@ -54,6 +60,11 @@ SIGNATURES = {
     "rrrmc_all_delta_energy": (_i32, [_vp, _i64, _vp]),
     "rrrmc_spinflip": (_i32, [_vp, _i64, _vp]),
     "rrrmc_magnetization": (_i32, [_vp, _vp]),
+    "rrrmc_delta_energy_residual": (_i32, [_vp, _i64, _vp]),
+    "rrrmc_transverse_mag": (_i32, [_vp, _f64, _vp]),
+    "rrrmc_Qenergy": (_i32, [_vp, _vp]),
+    "rrrmc_Renergies": (_i32, [_vp, _vp]),
+    "rrrmc_overlaps": (_i32, [_vp, _vp]),
     "rrrmc_opts_default": (_i32, [C.POINTER(Opts)]),
     "rrrmc_standard_mc": (_i32, _SAMPLER),
     "rrrmc_rrr_mc": (_i32, _SAMPLER),

@@ -149,6 +149,7 @@ extern "C" rrrmc_status_t rrrmc_graph_ea_create(rrrmc_ctx_t *ctx, int L, int D, 
     RR_ARG(N >= 2 && N < ((int64_t)1 << 31), "N = L^D = %lld out of range", (long long)N);
     rrrmc_graph *g = new rrrmc_graph();
     g->ctx = ctx; g->kind = kind; g->L = L; g->D = D; g->twoD = twoD; g->N = N;
+    g->Nk = N; g->M = 1; g->max_deg = twoD;
     g->bipartite = (L % 2 == 0);
     g->A0.resize(N * twoD);
     std::vector<int8_t> code(N * twoD);
@@ -239,11 +240,101 @@ extern "C" rrrmc_status_t rrrmc_graph_ea_create(rrrmc_ctx_t *ctx, int L, int D, 
     return RRRMC_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// SK / QT / GraphQuant host logic
+// ------------------------------------------------------------------------------------------------
+static rrrmc_status_t upload_sk_couplings(rrrmc_graph *g, int64_t n, int kind, const void *J)
+{
+    // validation as in the constructors (SK.jl:32-46, :185-196): square, symmetric, zero diagonal
+    if (kind == RRRMC_SK_F64) {
+        const double *Jd = (const double *)J;
+        for (int64_t i = 0; i < n; i++) {
+            RR_ARG(Jd[i * n + i] == 0, "invalid J: diagonal entry J[%lld][%lld] = %g, expected 0", (long long)i + 1, (long long)i + 1, Jd[i * n + i]);
+            for (int64_t j = i + 1; j < n; j++)
+                RR_ARG(Jd[i * n + j] == Jd[j * n + i], "invalid J: not symmetric at (%lld,%lld)", (long long)i + 1, (long long)j + 1);
+        }
+        RR_CUDA(cudaMalloc(&g->d_Jd, sizeof(double) * n * n));
+        RR_CUDA(cudaMemcpy(g->d_Jd, Jd, sizeof(double) * n * n, cudaMemcpyHostToDevice));
+    } else {
+        const uint8_t *Jb = (const uint8_t *)J;
+        for (int64_t i = 0; i < n; i++) {
+            RR_ARG(Jb[i * n + i] == 0, "invalid J: diagonal bit J[%lld][%lld] set, expected 0", (long long)i + 1, (long long)i + 1);
+            for (int64_t j = 0; j < n; j++) {
+                RR_ARG(Jb[i * n + j] <= 1, "invalid J: entries must be 0/1 bits");
+                RR_ARG(Jb[i * n + j] == Jb[j * n + i], "invalid J: not symmetric at (%lld,%lld)", (long long)i + 1, (long long)j + 1);
+            }
+        }
+        RR_CUDA(cudaMalloc(&g->d_Jb, n * n));
+        RR_CUDA(cudaMemcpy(g->d_Jb, Jb, n * n, cudaMemcpyHostToDevice));
+    }
+    return RRRMC_OK;
+}
+
+extern "C" rrrmc_status_t rrrmc_graph_sk_create(rrrmc_ctx_t *ctx, int64_t N, int kind, const void *J, rrrmc_graph_t **out)
+{
+    RR_ARG(ctx && J && out, "rrrmc_graph_sk_create: NULL argument");
+    RR_ARG(kind == RRRMC_SK_F64 || kind == RRRMC_SK_BIN, "coupling kind must be RRRMC_SK_F64 or RRRMC_SK_BIN, given %d", kind);
+    RR_ARG(N >= 1 && N <= 46340, "N = %lld out of range 1..46340", (long long)N);
+    rrrmc_graph *g = new rrrmc_graph();
+    g->ctx = ctx; g->kind = kind; g->N = N; g->Nk = N; g->M = 1; g->max_deg = (int)N - 1;
+    g->sN = sqrt((double)N); // SK.jl:47
+    RR_CUDA(cudaSetDevice(ctx->device));
+    rrrmc_status_t st = upload_sk_couplings(g, N, kind, J);
+    if (st != RRRMC_OK) { delete g; return st; }
+    *out = g;
+    return RRRMC_OK;
+}
+
+extern "C" rrrmc_status_t rrrmc_graph_qt_create(rrrmc_ctx_t *ctx, int64_t N, int64_t M, double fourK, rrrmc_graph_t **out)
+{
+    RR_ARG(ctx && out, "rrrmc_graph_qt_create: NULL argument");
+    RR_ARG(M > 2, "M must be greater than 2, given: %lld", (long long)M);                     // QT.jl:47
+    RR_ARG(N >= M && N % M == 0, "N must be divisible by M, given: N=%lld M=%lld", (long long)N, (long long)M); // QT.jl:48
+    RR_ARG(N < ((int64_t)1 << 31), "N = %lld out of range", (long long)N);
+    rrrmc_graph *g = new rrrmc_graph();
+    g->ctx = ctx; g->kind = RRRMC_QT; g->N = N; g->M = M; g->Nk = N / M; g->fourK = fourK; g->max_deg = 2;
+    g->allDE = { 0.0, fourK };                                                                 // QT.jl:111
+    *out = g;
+    return RRRMC_OK;
+}
+
+extern "C" rrrmc_status_t rrrmc_graph_quant_create(rrrmc_ctx_t *ctx, int64_t Nk, int64_t M, double Gamma, double beta,
+                                                   int inner, const void *J_inner, rrrmc_graph_t **out)
+{
+    RR_ARG(ctx && out, "rrrmc_graph_quant_create: NULL argument");
+    RR_ARG(Gamma >= 0, "Γ must be non-negative, given: %g", Gamma);                           // QT.jl:164
+    RR_ARG(M > 2, "M must be greater than 2, given: %lld", (long long)M);
+    RR_ARG(inner == RRRMC_SK_F64 || inner == RRRMC_SK_BIN || inner == RRRMC_EMPTY, "unsupported inner graph kind %d", inner);
+    RR_ARG(inner == RRRMC_EMPTY || J_inner, "J_inner is NULL");
+    RR_ARG(Nk >= 1 && Nk <= 46340 && Nk * M < ((int64_t)1 << 31), "Nk = %lld, M = %lld out of range", (long long)Nk, (long long)M);
+    RR_ARG(std::isfinite(beta) && beta > 0, "β must be finite and positive, given: %g", beta);
+    rrrmc_graph *g = new rrrmc_graph();
+    g->ctx = ctx; g->kind = RRRMC_QUANT; g->N = Nk * M; g->Nk = Nk; g->M = M; g->inner = inner;
+    g->Gamma = Gamma; g->beta = beta; g->sN = sqrt((double)Nk);
+    g->fourK = nearbyint(2.0 / beta * log(1.0 / tanh(beta * Gamma / (double)M)) * 1e8) / 1e8; // round(·, digits=8), QT.jl:165
+    g->allDE = { 0.0, g->fourK };                                                              // allΔE of inner_graph(X), QT.jl:111
+    g->max_deg = 2 + (inner == RRRMC_EMPTY ? 0 : (int)Nk - 1);
+    RR_CUDA(cudaSetDevice(ctx->device));
+    if (inner != RRRMC_EMPTY) {
+        rrrmc_status_t st = upload_sk_couplings(g, Nk, inner, J_inner);
+        if (st != RRRMC_OK) { delete g; return st; }
+    }
+    *out = g;
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_graph_fourK(const rrrmc_graph_t *g, double *fourK)
+{
+    RR_ARG(g && fourK, "NULL argument");
+    RR_ARG(g->kind == RRRMC_QT || g->kind == RRRMC_QUANT, "fourK is a parameter of GraphQT / GraphQuant only");
+    *fourK = g->fourK;
+    return RRRMC_OK;
+}
+
 extern "C" rrrmc_status_t rrrmc_graph_destroy(rrrmc_graph_t *g)
 {
     if (!g) return RRRMC_OK;
     cudaSetDevice(g->ctx->device);
-    cudaFree(g->d_jcode); cudaFree(g->d_A); cudaFree(g->d_J8); cudaFree(g->d_Jd);
+    cudaFree(g->d_jcode); cudaFree(g->d_A); cudaFree(g->d_J8); cudaFree(g->d_Jd); cudaFree(g->d_Jb);
     delete g;
     return RRRMC_OK;
 }
@@ -257,8 +348,27 @@ extern "C" rrrmc_status_t rrrmc_neighbors(const rrrmc_graph_t *g, int64_t site, 
 {
     RR_ARG(g && out && n, "NULL argument");
     RR_ARG(site >= 1 && site <= g->N, "site %lld out of range 1..%lld", (long long)site, (long long)g->N);
-    *n = g->nuA[site - 1];
-    for (int k = 0; k < *n; k++) out[k] = g->uA0[(site - 1) * g->twoD + k] + 1;
+    int m = 0;
+    if (g->kind == RRRMC_SK_F64 || g->kind == RRRMC_SK_BIN) {        // AllButOne, Common.jl:78-92
+        for (int64_t j = 1; j <= g->N; j++) if (j != site) out[m++] = j;
+    } else if (g->kind == RRRMC_QT || g->kind == RRRMC_QUANT) {      // QT.jl:105-108; QNeighbIter QT.jl:288-321
+        out[m++] = site - g->Nk + (site <= g->Nk ? g->N : 0);
+        out[m++] = site + g->Nk - (site + g->Nk > g->N ? g->N : 0);
+        if (g->kind == RRRMC_QUANT && g->inner != RRRMC_EMPTY) {
+            const int64_t k = (site - 1) / g->Nk, i = (site - 1) % g->Nk + 1;
+            for (int64_t j = 1; j <= g->Nk; j++) if (j != i) out[m++] = k * g->Nk + j;
+        }
+    } else {
+        m = g->nuA[site - 1];
+        for (int k = 0; k < m; k++) out[k] = g->uA0[(site - 1) * g->twoD + k] + 1;
+    }
+    *n = m;
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_max_neighbors(const rrrmc_graph_t *g, int64_t *n)
+{
+    RR_ARG(g && n, "NULL argument");
+    *n = g->max_deg;
     return RRRMC_OK;
 }
 extern "C" rrrmc_status_t rrrmc_allDE(const rrrmc_graph_t *g, double *out, int *n)
@@ -308,7 +418,7 @@ extern "C" rrrmc_status_t rrrmc_state_randomize(rrrmc_state_t *s, uint64_t seed)
 {
     RR_ARG(s, "state is NULL");
     RR_CUDA(cudaSetDevice(s->g->ctx->device));
-    s->energy_valid = false; s->chain_valid = false;
+    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false;
     return launch_randomize(s, seed);
 }
 extern "C" rrrmc_status_t rrrmc_state_upload(rrrmc_state_t *s, int64_t first, int64_t count, const uint64_t *chunks)
@@ -323,7 +433,7 @@ extern "C" rrrmc_status_t rrrmc_state_upload(rrrmc_state_t *s, int64_t first, in
     RR_CUDA(cudaMemcpyAsync(s->d_chunks, chunks, sizeof(uint64_t) * count * s->nchunks, cudaMemcpyHostToDevice, ctx->stream));
     RR_TRY(launch_upload_transpose(s, first, count));
     RR_CUDA(cudaStreamSynchronize(ctx->stream)); // the caller may free `chunks` on return
-    s->energy_valid = false; s->chain_valid = false;
+    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false;
     return RRRMC_OK;
 }
 extern "C" rrrmc_status_t rrrmc_state_download(rrrmc_state_t *s, int64_t first, int64_t count, uint64_t *chunks)
@@ -383,7 +493,7 @@ extern "C" rrrmc_status_t rrrmc_delta_energy(rrrmc_state_t *s, int64_t site, dou
         for (int64_t r = 0; r < s->R; r++) dE_out[r] = (double)h[r];
         return RRRMC_OK;
     }
-    return chain_delta_energy_site(s, site - 1, dE_out);
+    return chain_delta_energy_site(s, site - 1, 0, dE_out);
 }
 extern "C" rrrmc_status_t rrrmc_all_delta_energy(rrrmc_state_t *s, int64_t replica, double *dE_out)
 {
@@ -417,7 +527,7 @@ extern "C" rrrmc_status_t rrrmc_spinflip(rrrmc_state_t *s, int64_t site, const u
     }
     RR_TRY(launch_flip_site(s, site - 1, d_mask));
     RR_CUDA(cudaStreamSynchronize(ctx->stream));
-    s->chain_valid = false;
+    s->chain_valid = false; s->chain_fields_valid = false;
     return RRRMC_OK;
 }
 extern "C" rrrmc_status_t rrrmc_magnetization(rrrmc_state_t *s, double *m_out)
@@ -434,6 +544,30 @@ extern "C" rrrmc_status_t rrrmc_magnetization(rrrmc_state_t *s, double *m_out)
     for (int64_t r = 0; r < s->R; r++) m_out[r] = 2.0 * (double)h[r] - (double)g->N;
     return RRRMC_OK;
 }
+
+extern "C" rrrmc_status_t rrrmc_delta_energy_residual(rrrmc_state_t *s, int64_t site, double *dE_out)
+{
+    RR_ARG(s && dE_out, "NULL argument");
+    rrrmc_graph *g = s->g;
+    RR_ARG(site >= 1 && site <= g->N, "site %lld out of range 1..%lld", (long long)site, (long long)g->N);
+    RR_CUDA(cudaSetDevice(g->ctx->device));
+    if (g->kind != RRRMC_QUANT) { for (int64_t r = 0; r < s->R; r++) dE_out[r] = 0.0; return RRRMC_OK; } // Interface.jl:261
+    RR_TRY(chain_sync_to_multispin(s));
+    return chain_delta_energy_site(s, site - 1, 1, dE_out);
+}
+static rrrmc_status_t quant_observable(rrrmc_state_t *s, int what, double arg, double *out)
+{
+    RR_ARG(s && out, "NULL argument");
+    rrrmc_graph *g = s->g;
+    RR_ARG(g->kind == RRRMC_QUANT || (what == 0 && g->kind == RRRMC_QT), "this observable is defined for GraphQuant only");
+    RR_CUDA(cudaSetDevice(g->ctx->device));
+    RR_TRY(chain_sync_to_multispin(s));
+    return chain_quant_observable(s, what, arg, out);
+}
+extern "C" rrrmc_status_t rrrmc_transverse_mag(rrrmc_state_t *s, double beta, double *out) { return quant_observable(s, 0, beta, out); }
+extern "C" rrrmc_status_t rrrmc_Qenergy(rrrmc_state_t *s, double *out) { return quant_observable(s, 1, 0, out); }
+extern "C" rrrmc_status_t rrrmc_Renergies(rrrmc_state_t *s, double *out) { return quant_observable(s, 2, 0, out); }
+extern "C" rrrmc_status_t rrrmc_overlaps(rrrmc_state_t *s, double *out) { return quant_observable(s, 3, 0, out); }
 
 // ------------------------------------------------------------------------------------------------
 // samplers
@@ -519,7 +653,7 @@ extern "C" rrrmc_status_t rrrmc_checkerboard_sweeps(rrrmc_state_t *s, const uint
     cb_params p;
     RR_TRY(fill_cb_params(s, thr64, nthr, K, M, seed, p));
     for (int64_t k = 0; k < nsweeps; k++) RR_TRY(run_sweep(s, p, sweep0 + (uint64_t)k));
-    s->energy_valid = false; s->chain_valid = false;
+    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false;
     return RRRMC_OK;
 }
 
@@ -583,8 +717,8 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
     RR_CUDA(cudaEventSynchronize(e1));
     float ms = 0; RR_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    s->energy_valid = false; s->chain_valid = false;
-    if (info) { info->nsamples = std::min(nsamples, Es ? Es_cap : nsamples); info->iters_done = done * N; info->launches = (int64_t)(ctx->launches - l0); info->device_ms = ms; }
+    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false;
+    if (info) { info->nsamples = std::min(nsamples, Es ? Es_cap : nsamples); info->iters_done = done * N; info->launches = (int64_t)(ctx->launches - l0); info->device_ms = ms; info->accepted_total = -1; }
     return RRRMC_OK;
 }
 

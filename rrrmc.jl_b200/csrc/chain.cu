@@ -1,11 +1,14 @@
 // Sequential samplers on the chain layout: every replica is an independent Markov chain that runs the
 // reference's loop with the reference's data structures (local-field cache, ΔE classes as ArraySets,
-// Wong-Easton dynamic sampler), one chain per active lane.  Chains are latency-bound; they are spread one
-// per warp across the SMs while R is small so that divergent chains never serialise each other.
+// Wong-Easton dynamic sampler).  Chains are latency-bound; they are spread one per warp across the SMs while
+// R is small so that divergent chains never serialise each other.  For the fully connected families (SK and
+// GraphQuant over SK) a chain owns a whole warp: lane 0 runs the sampler, the other lanes wait in a helper loop
+// and join it for the O(N) local-field update of an accepted flip.
 //
-// Reference map: standardMC RRRMC.jl:81-127; rrrMC RRRMC.jl:131-219; bklMC RRRMC.jl:294-359;
+// Reference map: standardMC RRRMC.jl:81-127; rrrMC RRRMC.jl:131-290; bklMC RRRMC.jl:294-359;
 // DeltaECache DeltaE.jl:63-295; ArraySet ArraySets.jl:58-85; DeltaECacheCont DeltaE.jl:297-410;
-// DynamicSampler DynamicSamplers.jl:84-176; GraphEA cache EA.jl:195-275, 584-663.
+// DynamicSampler DynamicSamplers.jl:84-176; GraphEA cache EA.jl:195-275, 584-663; GraphSKNormal SK.jl:212-284;
+// GraphSK SK.jl:62-140; GraphQT QT.jl:68-111; GraphQuant QT.jl:172-199, 270-321.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -14,40 +17,48 @@
 #include "philox.cuh"
 
 constexpr int MAXL = 16;  // |allΔE| supported by the discrete cache
-constexpr int MAXDEG = 8; // 2D <= 8
+constexpr int MAXDEG = 8; // neighbours of a discrete graph on this path: 2D <= 8 (EA), 2 (QT)
+constexpr unsigned FULLMASK = 0xffffffffu;
 
 struct chain_hdr {
     double E, acc_rate, z, pdE;
     double T[2 * MAXL + 1];
     long long it, accepted, staged_its, nextstep, skip, rng_n;
     int t[2 * MAXL + 1];
-    int move_last, pending, pmove, status, built, trefresh, done, pad;
+    int pending, pmove, status, built, trefresh, done;
 };
 
 struct chain_store {
     int64_t R = 0, N = 0, N2 = 0;
     int levs = 0, nDE = 0;
-    bool f64 = false;
-    int32_t *lfi = nullptr, *lfi_last = nullptr;
-    double *lfd = nullptr, *lfd_last = nullptr;
+    bool f64 = false;             // fp64 local fields (EA F64, SK F64, QUANT over SK F64)
+    bool cont_ready = false, disc_ready = false;
+    int32_t *lfi = nullptr;       // [R][2][N] (EA: cur,last; SK family: per slice [2][Nk])
+    double *lfd = nullptr;
+    int32_t *ml = nullptr;        // [R][M] move_last per slice (0-based, -1 = none)
+    uint8_t *sw = nullptr;        // [R][M] SK family: which half of the slice's field pair is current
     chain_hdr *hdr = nullptr;
     int32_t *av = nullptr, *apos = nullptr;
     uint8_t *cls = nullptr;
     double *dEs = nullptr, *dv = nullptr, *dps = nullptr;
+    int32_t *csj = nullptr; double *csdE = nullptr, *csp = nullptr; // staged list of the continuous cache [R][N+1]
     double *d_Es = nullptr; int64_t Es_rows = 0;
-    double *d_DE = nullptr, *d_beta = nullptr, *d_E = nullptr;
+    double *d_DE = nullptr, *d_beta = nullptr, *d_E = nullptr, *d_aux = nullptr; int64_t aux_len = 0;
     uint8_t *d_tkind = nullptr; int64_t *d_tival = nullptr; double *d_tfval = nullptr; int64_t tcap = 0;
 };
 
 struct chain_params {
-    int kind, N, twoD, sampler, nDE, levs, cpw;
+    int kind, N, twoD, sampler, nDE, levs, cpw, coop;
+    int Nk, M, inner;
+    double fourK, sN;
     int64_t R, N2, nchunks, chain0;
-    const int32_t *A; const int8_t *J8; const double *Jd;
+    const int32_t *A; const int8_t *J8; const double *Jd; const uint8_t *Jb;
     uint64_t *chunks;
-    int32_t *lfi, *lfi_last; double *lfd, *lfd_last;
+    int32_t *lfi; double *lfd; int32_t *ml; uint8_t *sw;
     chain_hdr *hdr;
     int32_t *av, *apos; uint8_t *cls;
     double *dEs, *dv, *dps;
+    int32_t *csj; double *csdE, *csp;
     const double *DE, *beta;
     double *Es; int64_t Es_rows, quota;
     long long iters, step;
@@ -75,69 +86,194 @@ struct src_trace { // typed draw stream dumped from the reference (SURVEY Append
 };
 
 // ------------------------------------------------------------------------------------------------
-// chain view of a GraphEA (int or Float64 couplings)
+// chain view of a graph: the Interface of src/Interface.jl:87-270 on one replica
 // ------------------------------------------------------------------------------------------------
-struct cview {
-    int f64, N, twoD;
-    const int32_t *A; const int8_t *J8; const double *Jd;
+struct gview {
+    int kind, N, twoD;
+    const int32_t *A; const int8_t *J8; const double *Jd; const uint8_t *Jb;
     uint64_t *s;
-    int32_t *lfi, *lfi_last; double *lfd, *lfd_last;
-    int move_last; // 0-based site, -1 = none
+    int32_t *lfi; double *lfd;   // EA: [2][N] = (lfields, lfields_last). SK family: [M][2][Nk], halves swapped by sw[k]
+    int32_t *ml; uint8_t *sw;
+    int Nk, M, inner;
+    double fourK, sN;
+    int coop;                    // 1: a warp serves this chain (lane 0 leads)
 };
 __device__ __forceinline__ int sget(const uint64_t *s, int i) { return (int)((s[i >> 6] >> (i & 63)) & 1ull); }
+__device__ __forceinline__ bool is_ea(int kind) { return kind == RRRMC_EA_PM1 || kind == RRRMC_EA_INT || kind == RRRMC_EA_F64; }
+__device__ __forceinline__ bool is_sk(int kind) { return kind == RRRMC_SK_F64 || kind == RRRMC_SK_BIN; }
 
-__device__ __forceinline__ double cv_delta_energy(const cview &c, int i) // EA.jl:266-275 / :655-663
+// -- SK slice k of the view (SK proper: k = 0): current / last halves of the field pair
+__device__ __forceinline__ int64_t sk_cur_off(const gview &c, int k) { return ((int64_t)k * 2 + c.sw[k]) * c.Nk; }
+__device__ __forceinline__ int64_t sk_last_off(const gview &c, int k) { return ((int64_t)k * 2 + (c.sw[k] ^ 1)) * c.Nk; }
+__device__ __forceinline__ double sk_delta(const gview &c, int skind, int k, int i) // SK.jl:278-284 / :135-140
 {
-    return c.f64 ? -c.lfd[i] : -(double)c.lfi[i];
+    if (skind == RRRMC_SK_F64) return c.lfd[sk_cur_off(c, k) + i];
+    if (skind == RRRMC_SK_BIN) return (double)c.lfi[sk_cur_off(c, k) + i] / c.sN;
+    return 0.0; // GraphEmpty (Empty.jl:28-31)
 }
-__device__ int cv_neighbors(const cview &c, int i, int *out) // uA[i], EA.jl:292
+// part of update_cache! that every lane of the serving warp runs: sites j = lane, lane+nl, ... of slice k
+// (SK.jl:252-265 / :109-122). `si` is the new spin of site i; spins of the slice sit at bit offset k*Nk.
+__device__ __forceinline__ void sk_update_part(const gview &c, int skind, int k, int i, int si, int lane, int nl)
 {
-    int n = 0;
-    for (int k = 0; k < c.twoD; k++) {
-        const int y = c.A[(int64_t)i * c.twoD + k];
-        if (n == 0 || out[n - 1] != y) out[n++] = y;
+    const int64_t cur = sk_cur_off(c, k), last = sk_last_off(c, k);
+    const int64_t off = (int64_t)k * c.Nk;
+    if (skind == RRRMC_SK_F64) {
+        const double *Ji = c.Jd + (int64_t)i * c.Nk;
+        for (int j = lane; j < c.Nk; j += nl) {
+            const double Js = __dmul_rn((double)(1 - 2 * (si ^ sget(c.s, (int)(off + j)))), Ji[j]);
+            const double lfj = c.lfd[cur + j];
+            c.lfd[last + j] = lfj;
+            c.lfd[cur + j] = __dadd_rn(lfj, 4 * Js);
+        }
+    } else {
+        const uint8_t *Ji = c.Jb + (int64_t)i * c.Nk;
+        for (int j = lane; j < c.Nk; j += nl) {
+            const int Js = si ^ sget(c.s, (int)(off + j)) ^ (int)Ji[j];
+            const int lfj = c.lfi[cur + j];
+            c.lfi[last + j] = lfj;
+            c.lfi[cur + j] = lfj + 8 * Js - 4;
+        }
     }
-    return n;
 }
-__device__ void cv_spinflip(cview &c, int i) // Interface.jl:89-92 + update_cache! EA.jl:224-264 / :613-653
+enum { COOP_EXIT = 0, COOP_SK_UPDATE = 1 };
+// update_cache! of one SK slice after s_i flipped (SK.jl:239-276 / :96-133); called by the chain's leader
+__device__ void sk_update_cache(gview &c, int skind, int k, int i)
+{
+    if (skind == RRRMC_EMPTY) return;
+    if (c.ml[k] == i) { c.sw[k] ^= 1; return; } // swap lfields <-> lfields_last (SK.jl:247-250)
+    const int si = sget(c.s, (int)((int64_t)k * c.Nk + i));
+    double lfm_d = 0; int lfm_i = 0;
+    if (skind == RRRMC_SK_F64) lfm_d = c.lfd[sk_cur_off(c, k) + i]; else lfm_i = c.lfi[sk_cur_off(c, k) + i];
+    if (c.coop) {
+        __threadfence_block();
+        __shfl_sync(FULLMASK, (int)COOP_SK_UPDATE, 0); __shfl_sync(FULLMASK, k, 0); __shfl_sync(FULLMASK, i, 0); __shfl_sync(FULLMASK, si, 0);
+        sk_update_part(c, skind, k, i, si, 0, 32);
+        __syncwarp(FULLMASK);
+    } else sk_update_part(c, skind, k, i, si, 0, 1);
+    if (skind == RRRMC_SK_F64) { c.lfd[sk_last_off(c, k) + i] = lfm_d; c.lfd[sk_cur_off(c, k) + i] = -lfm_d; }
+    else { c.lfi[sk_last_off(c, k) + i] = lfm_i; c.lfi[sk_cur_off(c, k) + i] = -lfm_i; }
+    c.ml[k] = i;
+}
+// helper lanes of a cooperative chain: serve the leader until it says exit
+__device__ void coop_helper_loop(const gview &c, int lane)
+{
+    const int skind = c.kind == RRRMC_QUANT ? c.inner : c.kind;
+    for (;;) {
+        const int cmd = __shfl_sync(FULLMASK, 0, 0);
+        if (cmd == COOP_EXIT) return;
+        const int k = __shfl_sync(FULLMASK, 0, 0), i = __shfl_sync(FULLMASK, 0, 0), si = __shfl_sync(FULLMASK, 0, 0);
+        sk_update_part(c, skind, k, i, si, lane, 32);
+        __threadfence_block();
+        __syncwarp(FULLMASK);
+    }
+}
+
+// -- GraphQT (QT.jl:86-108)
+__device__ __forceinline__ void qt_neighbors(const gview &c, int i, int &k1, int &k2)
+{
+    k1 = i - c.Nk + (i < c.Nk ? c.N : 0);
+    k2 = i + c.Nk - (i + c.Nk >= c.N ? c.N : 0);
+}
+__device__ __forceinline__ double qt_delta(const gview &c, int i)
+{
+    int k1, k2; qt_neighbors(c, i, k1, k2);
+    const int sk = sget(c.s, i), s1 = sget(c.s, k1), s2 = sget(c.s, k2);
+    return (double)((sk == s1) - (sk != s2)) * c.fourK;
+}
+
+// delta_energy(X, C, i): `inner` selects inner_graph(X) for a DoubleGraph (Interface.jl:239-240)
+__device__ __forceinline__ double gv_delta_energy(const gview &c, int i, bool inner = false)
+{
+    switch (c.kind) {
+    case RRRMC_EA_F64: return -c.lfd[i];                       // EA.jl:655-663
+    case RRRMC_EA_PM1: case RRRMC_EA_INT: return -(double)c.lfi[i]; // EA.jl:266-275
+    case RRRMC_SK_F64: case RRRMC_SK_BIN: return sk_delta(c, c.kind, 0, i);
+    case RRRMC_QT: return qt_delta(c, i);
+    case RRRMC_QUANT: {                                        // QT.jl:283-286, residual :270-281
+        const double d0 = qt_delta(c, i);
+        if (inner) return d0;
+        return d0 + sk_delta(c, c.inner, i / c.Nk, i % c.Nk) / (double)c.M;
+    }
+    }
+    return 0.0;
+}
+__device__ __forceinline__ double gv_delta_residual(const gview &c, int i) // Interface.jl:254-261; QT.jl:270-281
+{
+    if (c.kind != RRRMC_QUANT) return 0.0;
+    return sk_delta(c, c.inner, i / c.Nk, i % c.Nk) / (double)c.M;
+}
+// neighbors(X, i) in the reference's iteration order (EA.jl:292 uA; Common.jl:78-92 AllButOne; QT.jl:105-108, :288-321)
+template <class F> __device__ __forceinline__ void gv_for_neighbors(const gview &c, int i, bool inner, F f)
+{
+    if (is_ea(c.kind)) {
+        int prev = -1;
+        for (int k = 0; k < c.twoD; k++) {
+            const int y = c.A[(int64_t)i * c.twoD + k];
+            if (y != prev) f(y);
+            prev = y;
+        }
+    } else if (is_sk(c.kind)) {
+        for (int j = 0; j < c.N; j++) if (j != i) f(j);
+    } else {
+        int k1, k2; qt_neighbors(c, i, k1, k2);
+        f(k1); f(k2);
+        if (c.kind == RRRMC_QUANT && !inner && c.inner != RRRMC_EMPTY) {
+            const int base = (i / c.Nk) * c.Nk, ii = i - base;
+            for (int j = 0; j < c.Nk; j++) if (j != ii) f(base + j);
+        }
+    }
+}
+// spinflip!(X, C, i) = flip + update_cache! (Interface.jl:89-92)
+__device__ void gv_spinflip(gview &c, int i, bool inner = false)
 {
     c.s[i >> 6] ^= 1ull << (i & 63);
-    int U[MAXDEG]; const int nU = cv_neighbors(c, i, U);
-    if (c.f64) {
-        if (c.move_last == i) {
-            for (int k = 0; k < nU; k++) { const double t = c.lfd[U[k]]; c.lfd[U[k]] = c.lfd_last[U[k]]; c.lfd_last[U[k]] = t; }
-            c.lfd[i] = -c.lfd[i]; c.lfd_last[i] = -c.lfd_last[i];
+    if (c.kind == RRRMC_QT || (c.kind == RRRMC_QUANT && inner)) return;   // Interface.jl:87: no cache
+    if (c.kind == RRRMC_QUANT) { sk_update_cache(c, c.inner, i / c.Nk, i % c.Nk); return; } // QT.jl:172-183
+    if (is_sk(c.kind)) { sk_update_cache(c, c.kind, 0, i); return; }
+    // GraphEA update_cache! EA.jl:224-264 / :613-653
+    int U[MAXDEG], nU = 0;
+    for (int k = 0; k < c.twoD; k++) {
+        const int y = c.A[(int64_t)i * c.twoD + k];
+        if (nU == 0 || U[nU - 1] != y) U[nU++] = y;
+    }
+    const int N = c.N;
+    if (c.kind == RRRMC_EA_F64) {
+        double *lf = c.lfd, *lfl = c.lfd + N;
+        if (c.ml[0] == i) {
+            for (int k = 0; k < nU; k++) { const double t = lf[U[k]]; lf[U[k]] = lfl[U[k]]; lfl[U[k]] = t; }
+            lf[i] = -lf[i]; lfl[i] = -lfl[i];
             return;
         }
-        for (int k = 0; k < nU; k++) c.lfd_last[U[k]] = c.lfd[U[k]];
+        for (int k = 0; k < nU; k++) lfl[U[k]] = lf[U[k]];
         const int sx = sget(c.s, i);
         for (int k = 0; k < c.twoD; k++) {
             const int y = c.A[(int64_t)i * c.twoD + k];
             const double f = (double)(4 * (1 - 2 * (sx ^ sget(c.s, y))));
-            c.lfd[y] = __dsub_rn(c.lfd[y], __dmul_rn(f, c.Jd[(int64_t)i * c.twoD + k]));
+            lf[y] = __dsub_rn(lf[y], __dmul_rn(f, c.Jd[(int64_t)i * c.twoD + k]));
         }
-        const double lfm = c.lfd[i];
-        c.lfd_last[i] = lfm; c.lfd[i] = -lfm;
+        const double lfm = lf[i];
+        lfl[i] = lfm; lf[i] = -lfm;
     } else {
-        if (c.move_last == i) {
-            for (int k = 0; k < nU; k++) { const int t = c.lfi[U[k]]; c.lfi[U[k]] = c.lfi_last[U[k]]; c.lfi_last[U[k]] = t; }
-            c.lfi[i] = -c.lfi[i]; c.lfi_last[i] = -c.lfi_last[i];
+        int32_t *lf = c.lfi, *lfl = c.lfi + N;
+        if (c.ml[0] == i) {
+            for (int k = 0; k < nU; k++) { const int t = lf[U[k]]; lf[U[k]] = lfl[U[k]]; lfl[U[k]] = t; }
+            lf[i] = -lf[i]; lfl[i] = -lfl[i];
             return;
         }
-        for (int k = 0; k < nU; k++) c.lfi_last[U[k]] = c.lfi[U[k]];
+        for (int k = 0; k < nU; k++) lfl[U[k]] = lf[U[k]];
         const int sx = sget(c.s, i);
         for (int k = 0; k < c.twoD; k++) {
             const int y = c.A[(int64_t)i * c.twoD + k];
-            c.lfi[y] -= 4 * (1 - 2 * (sx ^ sget(c.s, y))) * (int)c.J8[(int64_t)i * c.twoD + k];
+            lf[y] -= 4 * (1 - 2 * (sx ^ sget(c.s, y))) * (int)c.J8[(int64_t)i * c.twoD + k];
         }
-        const int lfm = c.lfi[i];
-        c.lfi_last[i] = lfm; c.lfi[i] = -lfm;
+        const int lfm = lf[i];
+        lfl[i] = lfm; lf[i] = -lfm;
     }
-    c.move_last = i;
+    c.ml[0] = i;
 }
 
 // ------------------------------------------------------------------------------------------------
-// discrete ΔE-class cache (DeltaE.jl:63-295) with ArraySets (ArraySets.jl:58-85)
+// discrete ΔE-class cache (DeltaE.jl:63-295) with ArraySets (ArraySets.jl:58-85); built on inner_graph(X)
 // ------------------------------------------------------------------------------------------------
 struct dcache {
     int N, L;
@@ -167,13 +303,13 @@ __device__ __forceinline__ void as_delete(dcache &c, int k, int i)
     c.apos[i] = 0;
     c.t[k]--;
 }
-__device__ __forceinline__ int dc_class_of(const dcache &c, const cview &X, int j)
+__device__ __forceinline__ int dc_class_of(const dcache &c, const gview &X, int j)
 {
-    const double dE = cv_delta_energy(X, j);
+    const double dE = gv_delta_energy(X, j, true);
     const int up = dE > 0 || (dE == 0 && sget(X.s, j) == 1);
     return dc_findk(c, dE) + c.L * up;
 }
-__device__ void dc_build(dcache &c, const cview &X, double beta) // DeltaE.jl:74-104
+__device__ void dc_build(dcache &c, const gview &X, double beta) // DeltaE.jl:74-104
 {
     for (int k = 0; k <= 2 * c.L; k++) c.t[k] = 0;
     for (int i = 0; i < c.N; i++) {
@@ -202,19 +338,18 @@ template <class SRC> __device__ int dc_rand_move(const dcache &c, SRC &d, double
     const long long p = d.range(c.t[k]);
     return c.av[(int64_t)(k - 1) * c.N + p - 1];
 }
-__device__ void dc_compute_staged(dcache &c, cview &X, int i) // DeltaE.jl:202-230
+__device__ void dc_compute_staged(dcache &c, gview &X, int i) // DeltaE.jl:202-230 (on the inner graph)
 {
-    cv_spinflip(X, i);
+    gv_spinflip(X, i, true);
     c.nst = 0;
-    int nb[MAXDEG]; const int n = cv_neighbors(X, i, nb);
-    for (int a = 0; a < n; a++) {
-        const int j = nb[a], k0 = c.cls[j], k1 = dc_class_of(c, X, j);
-        if (k0 == k1) continue;
+    gv_for_neighbors(X, i, true, [&](int j) {
+        const int k0 = c.cls[j], k1 = dc_class_of(c, X, j);
+        if (k0 == k1) return;
         c.st[c.nst][0] = j; c.st[c.nst][1] = k0; c.st[c.nst][2] = k1; c.nst++;
-    }
+    });
     const int k0 = c.cls[i], k1 = k0 - c.L * (2 * (k0 > c.L) - 1);
     c.st[c.nst][0] = i; c.st[c.nst][1] = k0; c.st[c.nst][2] = k1; c.nst++;
-    cv_spinflip(X, i);
+    gv_spinflip(X, i, true);
 }
 __device__ double dc_reverse(dcache &c) // DeltaE.jl:184-200
 {
@@ -237,20 +372,21 @@ __device__ void dc_apply_staged(dcache &c) // DeltaE.jl:169-182
     }
     double *tmp = c.T; c.T = c.Tp; c.Tp = tmp; c.z = c.zp;
 }
-__device__ double dc_apply_move(dcache &c, cview &X, int move) // DeltaE.jl:232-295
+__device__ double dc_apply_move(dcache &c, gview &X, int move) // DeltaE.jl:232-295 (flip on X, classes on inner_graph(X))
 {
-    cv_spinflip(X, move);
+    gv_spinflip(X, move, false);
     double zp = c.z;
-    int nb[MAXDEG]; const int n = cv_neighbors(X, move, nb);
-    for (int a = 0; a <= n; a++) {
-        int j, k0, k1;
-        if (a < n) { j = nb[a]; k0 = c.cls[j]; k1 = dc_class_of(c, X, j); if (k0 == k1) continue; }
-        else { j = move; k0 = c.cls[move]; k1 = k0 - c.L * (2 * (k0 > c.L) - 1); }
+    auto reclass = [&](int j, int k0, int k1) {
         const double f0 = dc_f(c, k0), f1 = dc_f(c, k1);
         c.T[k0] -= f0; c.T[k1] += f1;
         zp += f1 - f0;
         as_delete(c, k0, j); as_push(c, k1, j); c.cls[j] = (uint8_t)k1;
-    }
+    };
+    gv_for_neighbors(X, move, true, [&](int j) {
+        const int k0 = c.cls[j], k1 = dc_class_of(c, X, j);
+        if (k0 != k1) reclass(j, k0, k1);
+    });
+    { const int k0 = c.cls[move]; reclass(move, k0, k0 - c.L * (2 * (k0 > c.L) - 1)); }
     const double cc = c.z / zp;
     c.z = zp;
     return cc;
@@ -264,7 +400,7 @@ struct ccache {
     double *v, *ps, *dEs;  // v,ps 1-based
     double z, beta;
     int trefresh;
-    int sj[MAXDEG + 1]; double sdE[MAXDEG + 1], sp[MAXDEG + 1]; int nst;
+    int32_t *sj; double *sdE, *sp; int nst; // staged list, up to N entries
 };
 __device__ __forceinline__ double prior(double x) { return x > 0 ? exp(-x) : 1.0; } // DeltaE.jl:297
 __device__ void ds_add_path(ccache &c, int i1, double x)
@@ -314,10 +450,10 @@ __device__ void ds_set(ccache &c, int i1, double x) // DynamicSamplers.jl:159-17
     c.z += d;
     ds_add_path(c, i1, d);
 }
-__device__ void cc_build(ccache &c, const cview &X) // DeltaE.jl:304-311 + DynamicSamplers.jl:35-51
+__device__ void cc_build(ccache &c, const gview &X, bool inner) // DeltaE.jl:304-311 + DynamicSamplers.jl:35-51
 {
     for (long long i = 0; i <= c.N2; i++) c.v[i] = 0.0;
-    for (int i = 0; i < c.N; i++) { c.dEs[i] = cv_delta_energy(X, i); c.v[i + 1] = prior(c.beta * c.dEs[i]); }
+    for (int i = 0; i < c.N; i++) { c.dEs[i] = gv_delta_energy(X, i, inner); c.v[i + 1] = prior(c.beta * c.dEs[i]); }
     ds_refresh(c);
 }
 template <class SRC> __device__ long long cc_rand_skip(const ccache &c, SRC &d) // DeltaE.jl:319-324
@@ -326,17 +462,16 @@ template <class SRC> __device__ long long cc_rand_skip(const ccache &c, SRC &d) 
     b = fmin(fmax(b, 2.2250738585072014e-308), 1.0);
     return (long long)floor(log1p(-d.f64()) / log1p(-b));
 }
-__device__ void cc_compute_staged(ccache &c, cview &X, int i) // DeltaE.jl:356-373
+__device__ void cc_compute_staged(ccache &c, gview &X, int i) // DeltaE.jl:356-373 (SingleGraph only)
 {
-    cv_spinflip(X, i);
-    double dE = cv_delta_energy(X, i);
+    gv_spinflip(X, i);
+    double dE = gv_delta_energy(X, i);
     c.sj[0] = i; c.sdE[0] = dE; c.sp[0] = prior(c.beta * dE); c.nst = 1;
-    int nb[MAXDEG]; const int n = cv_neighbors(X, i, nb);
-    for (int a = 0; a < n; a++) {
-        dE = cv_delta_energy(X, nb[a]);
-        c.sj[c.nst] = nb[a]; c.sdE[c.nst] = dE; c.sp[c.nst] = prior(c.beta * dE); c.nst++;
-    }
-    cv_spinflip(X, i);
+    gv_for_neighbors(X, i, false, [&](int j) {
+        const double d = gv_delta_energy(X, j);
+        c.sj[c.nst] = j; c.sdE[c.nst] = d; c.sp[c.nst] = prior(c.beta * d); c.nst++;
+    });
+    gv_spinflip(X, i);
 }
 __device__ double cc_reverse(const ccache &c) // DeltaE.jl:344-354
 {
@@ -348,18 +483,30 @@ __device__ void cc_apply_staged(ccache &c) // DeltaE.jl:334-342
 {
     for (int a = 0; a < c.nst; a++) { c.dEs[c.sj[a]] = c.sdE[a]; ds_set(c, c.sj[a] + 1, c.sp[a]); }
 }
-__device__ double cc_apply_move(ccache &c, cview &X, int move) // DeltaE.jl:378-410
+__device__ double cc_apply_move(ccache &c, gview &X, int move, bool inner) // DeltaE.jl:378-410
 {
-    cv_spinflip(X, move);
+    gv_spinflip(X, move);
     const double z = c.z;
-    double dE = cv_delta_energy(X, move);
+    double dE = gv_delta_energy(X, move, inner);
     c.dEs[move] = dE; ds_set(c, move + 1, prior(c.beta * dE));
-    int nb[MAXDEG]; const int n = cv_neighbors(X, move, nb);
-    for (int a = 0; a < n; a++) {
-        dE = cv_delta_energy(X, nb[a]);
-        c.dEs[nb[a]] = dE; ds_set(c, nb[a] + 1, prior(c.beta * dE));
-    }
+    gv_for_neighbors(X, move, inner, [&](int j) {
+        const double d = gv_delta_energy(X, j, inner);
+        c.dEs[j] = d; ds_set(c, j + 1, prior(c.beta * d));
+    });
     return z / c.z;
+}
+
+__device__ __forceinline__ gview make_view(const chain_params &P, int64_t r)
+{
+    gview X;
+    X.kind = P.kind; X.N = P.N; X.twoD = P.twoD; X.A = P.A; X.J8 = P.J8; X.Jd = P.Jd; X.Jb = P.Jb;
+    X.s = P.chunks + r * P.nchunks;
+    X.lfi = P.lfi ? P.lfi + r * 2 * (int64_t)P.N : nullptr;
+    X.lfd = P.lfd ? P.lfd + r * 2 * (int64_t)P.N : nullptr;
+    X.ml = P.ml + r * P.M; X.sw = P.sw + r * P.M;
+    X.Nk = P.Nk; X.M = P.M; X.inner = P.inner; X.fourK = P.fourK; X.sN = P.sN;
+    X.coop = P.coop;
+    return X;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -369,21 +516,25 @@ template <class SRC>
 __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
 {
     const int lane = threadIdx.x;
-    if (lane >= P.cpw) return;
-    const int64_t r = P.chain0 + (int64_t)blockIdx.x * P.cpw + lane;
-    if (r >= P.chain0 + P.R) return;
+    int64_t r;
+    if (P.coop) r = P.chain0 + blockIdx.x;
+    else {
+        if (lane >= P.cpw) return;
+        r = P.chain0 + (int64_t)blockIdx.x * P.cpw + lane;
+        if (r >= P.chain0 + P.R) return;
+    }
+    gview X = make_view(P, r);
+    if (P.coop && lane != 0) { coop_helper_loop(X, lane); return; }
     chain_hdr h = P.hdr[r];
-    if (h.done) return;
+    if (h.done) { if (P.coop) __shfl_sync(FULLMASK, (int)COOP_EXIT, 0); return; }
     const int N = P.N;
-    cview X;
-    X.f64 = P.kind == RRRMC_EA_F64; X.N = N; X.twoD = P.twoD; X.A = P.A; X.J8 = P.J8; X.Jd = P.Jd;
-    X.s = P.chunks + r * P.nchunks;
-    X.lfi = P.lfi ? P.lfi + r * N : nullptr; X.lfi_last = P.lfi_last ? P.lfi_last + r * N : nullptr;
-    X.lfd = P.lfd ? P.lfd + r * N : nullptr; X.lfd_last = P.lfd_last ? P.lfd_last + r * N : nullptr;
-    X.move_last = h.move_last;
     SRC src(P, r, h.rng_n);
     const double beta = P.beta[r];
-    const bool discr = !X.f64;
+    const bool dbl = P.kind == RRRMC_QUANT;                                        // DoubleGraph
+    const bool discr_full = P.kind == RRRMC_EA_PM1 || P.kind == RRRMC_EA_INT || P.kind == RRRMC_QT; // X <: DiscrGraph
+    // rrrMC builds its cache on inner_graph(X) (RRRMC.jl:170-171, :239-240); bklMC on X itself (:325)
+    const bool discr = P.sampler == CHAIN_RRR ? (discr_full || dbl) : discr_full;
+    const bool cc_inner = P.sampler == CHAIN_RRR;
     long long emitted = 0;
     const long long iters = P.iters, step = P.step;
     double *Es = P.Es;
@@ -400,8 +551,9 @@ __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
         } else {
             cc.N = N; cc.levs = P.levs; cc.N2 = P.N2; cc.beta = beta;
             cc.v = P.dv + r * (P.N2 + 1); cc.ps = P.dps + r * (P.N2 + 1); cc.dEs = P.dEs + r * N;
+            cc.sj = P.csj + r * ((int64_t)N + 1); cc.sdE = P.csdE + r * ((int64_t)N + 1); cc.sp = P.csp + r * ((int64_t)N + 1);
             cc.z = h.z; cc.trefresh = h.trefresh; cc.nst = 0;
-            if (!h.built) { cc_build(cc, X); h.built = 1; }
+            if (!h.built) { cc_build(cc, X, cc_inner); h.built = 1; }
         }
     }
 #define EMIT_SAMPLE()                                                         \
@@ -409,6 +561,12 @@ __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
         if (Es && emitted < P.Es_rows) Es[emitted * P.R + (r - P.chain0)] = h.E; \
         emitted++;                                                            \
     } while (0)
+    // accept(c, x) of RRRMC.jl:40-44 (DoubleGraph residual filter)
+    auto accept2 = [&](double c, double x) -> bool {
+        if (c >= 1 && x >= 0) return true;
+        const double a = c * exp(x);
+        return a >= 1 || src.f64() < a;
+    };
 
     if (P.sampler == CHAIN_STANDARD) { // RRRMC.jl:100-119
         for (;;) {
@@ -419,14 +577,15 @@ __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
             }
             h.pending = 0;
             const int i = (int)src.range(N) - 1;
-            const double dE = cv_delta_energy(X, i);
+            const double dE = gv_delta_energy(X, i);
             const double x = -beta * dE;
+            if (src.err) { h.done = 1; break; }
             if (!(x >= 0 || src.f64() < exp(x))) continue; // accept(), RRRMC.jl:39
-            cv_spinflip(X, i);
+            gv_spinflip(X, i);
             h.E += dE;
             h.accepted++;
         }
-    } else if (P.sampler == CHAIN_RRR) { // RRRMC.jl:180-211
+    } else if (P.sampler == CHAIN_RRR) { // RRRMC.jl:180-211 (SingleGraph), :249-282 (DoubleGraph)
         const double lambda = P.staged_thr_fact / (double)N;
         for (;;) {
             if (!h.pending) {
@@ -438,21 +597,26 @@ __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
             int acc = 0;
             if (h.acc_rate < P.staged_thr) {
                 h.staged_its++;
-                double z, zp, dE; int move;
-                if (discr) { z = dc.z; move = dc_rand_move(dc, src, dE); dc_compute_staged(dc, X, move); zp = dc_reverse(dc); }
-                else { z = cc.z; move = ds_getel(cc, src.f64(), src.err) - 1; dE = cc.dEs[move]; cc_compute_staged(cc, X, move); zp = cc_reverse(cc); }
+                double z, zp, dE0, dE1 = 0.0; int move;
+                if (discr) { z = dc.z; move = dc_rand_move(dc, src, dE0); dc_compute_staged(dc, X, move); zp = dc_reverse(dc); }
+                else { z = cc.z; move = ds_getel(cc, src.f64(), src.err) - 1; dE0 = cc.dEs[move]; cc_compute_staged(cc, X, move); zp = cc_reverse(cc); }
                 const double c = z / zp;
-                if (src.f64() < c) {
-                    cv_spinflip(X, move);
+                bool ok;
+                if (dbl) { dE1 = gv_delta_residual(X, move); ok = accept2(c, -beta * dE1); }
+                else ok = src.f64() < c;
+                if (ok) {
+                    gv_spinflip(X, move);
                     if (discr) dc_apply_staged(dc); else cc_apply_staged(cc);
-                    h.E += dE; h.accepted++; acc = 1;
+                    h.E += dE0 + dE1; h.accepted++; acc = 1;
                 }
             } else {
-                double dE; int move;
-                if (discr) move = dc_rand_move(dc, src, dE); else { move = ds_getel(cc, src.f64(), src.err) - 1; dE = cc.dEs[move]; }
-                const double c = discr ? dc_apply_move(dc, X, move) : cc_apply_move(cc, X, move);
-                if (src.f64() < c) { h.E += dE; h.accepted++; acc = 1; }
-                else { if (discr) dc_apply_move(dc, X, move); else cc_apply_move(cc, X, move); }
+                double dE0, dE1 = 0.0; int move;
+                if (discr) move = dc_rand_move(dc, src, dE0); else { move = ds_getel(cc, src.f64(), src.err) - 1; dE0 = cc.dEs[move]; }
+                if (dbl) dE1 = gv_delta_residual(X, move);
+                const double c = discr ? dc_apply_move(dc, X, move) : cc_apply_move(cc, X, move, true);
+                const bool ok = dbl ? accept2(c, -beta * dE1) : (src.f64() < c);
+                if (ok) { h.E += dE0 + dE1; h.accepted++; acc = 1; }
+                else { if (discr) dc_apply_move(dc, X, move); else cc_apply_move(cc, X, move, true); }
             }
             h.acc_rate = h.acc_rate * (1 - lambda) + acc * lambda;
             if (src.err) { h.done = 1; break; }
@@ -474,7 +638,7 @@ __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
             }
             if (paused) break;
             if (out || src.err) { h.done = 1; break; }
-            if (discr) dc_apply_move(dc, X, h.pmove); else cc_apply_move(cc, X, h.pmove);
+            if (discr) dc_apply_move(dc, X, h.pmove); else cc_apply_move(cc, X, h.pmove, false);
             h.it += h.skip + 1;
             h.E += h.pdE;
             h.accepted++;
@@ -482,19 +646,19 @@ __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
         }
     }
 #undef EMIT_SAMPLE
+    if (P.coop) __shfl_sync(FULLMASK, (int)COOP_EXIT, 0);
     if (P.sampler != CHAIN_STANDARD) {
         if (discr) { for (int k = 0; k <= 2 * dc.L; k++) h.T[k] = dc.T[k]; h.z = dc.z; }
         else { h.z = cc.z; h.trefresh = cc.trefresh; }
     }
-    h.move_last = X.move_last;
     h.rng_n = src.pos();
     if (src.err) h.status = src.err;
     P.hdr[r] = h;
 }
 
 // ------------------------------------------------------------------------------------------------
-// energy(X, C) on the chain layout: local fields (EA.jl:201-215 / :591-605), then the per-chain sum in
-// site order (sequential, so Float64 energies round exactly like the reference's loop)
+// energy(X, C) on the chain layout: (re)initialises the local fields (Interface.jl:103), then the per-chain sum
+// in site order (sequential, so Float64 energies round exactly like the reference's loop)
 // ------------------------------------------------------------------------------------------------
 __global__ void k_chain_lfields(chain_params P)
 {
@@ -502,41 +666,99 @@ __global__ void k_chain_lfields(chain_params P)
     if (tid >= P.R * P.N) return;
     const int64_t r = tid / P.N; const int x = (int)(tid % P.N);
     const uint64_t *s = P.chunks + r * P.nchunks;
-    const int sx = 2 * sget(s, x) - 1;
-    if (P.kind == RRRMC_EA_F64) {
+    if (x < P.M) { P.ml[r * P.M + x] = -1; P.sw[r * P.M + x] = 0; }
+    if (P.kind == RRRMC_QT) return;
+    if (is_ea(P.kind)) { // EA.jl:201-215 / :591-605
+        const int sx = 2 * sget(s, x) - 1;
+        if (P.kind == RRRMC_EA_F64) {
+            double lf = 0.0;
+            for (int k = 0; k < P.twoD; k++) {
+                const int y = P.A[(int64_t)x * P.twoD + k];
+                const double sy = (double)(2 * sget(s, y) - 1);
+                lf = __dsub_rn(lf, __dmul_rn(__dmul_rn(P.Jd[(int64_t)x * P.twoD + k], (double)sx), sy));
+            }
+            P.lfd[r * 2 * P.N + x] = 2 * lf; P.lfd[r * 2 * P.N + P.N + x] = 0.0;
+        } else {
+            int lf = 0;
+            for (int k = 0; k < P.twoD; k++) {
+                const int y = P.A[(int64_t)x * P.twoD + k];
+                lf -= (int)P.J8[(int64_t)x * P.twoD + k] * sx * (2 * sget(s, y) - 1);
+            }
+            P.lfi[r * 2 * P.N + x] = 2 * lf; P.lfi[r * 2 * P.N + P.N + x] = 0;
+        }
+        return;
+    }
+    // SK family: slice k, site i of the slice (J symmetric: read column i so that consecutive threads coalesce)
+    const int skind = P.kind == RRRMC_QUANT ? P.inner : P.kind;
+    if (skind == RRRMC_EMPTY) return;
+    const int k = x / P.Nk, i = x % P.Nk;
+    const int64_t off = (int64_t)k * P.Nk, cur = r * 2 * P.N + (int64_t)k * 2 * P.Nk;
+    const int si = sget(s, (int)(off + i));
+    if (skind == RRRMC_SK_F64) { // SK.jl:218-231
         double lf = 0.0;
-        for (int k = 0; k < P.twoD; k++) {
-            const int y = P.A[(int64_t)x * P.twoD + k];
-            const double sy = (double)(2 * sget(s, y) - 1);
-            lf = __dsub_rn(lf, __dmul_rn(__dmul_rn(P.Jd[(int64_t)x * P.twoD + k], (double)sx), sy));
-        }
-        P.lfd[tid] = 2 * lf; P.lfd_last[tid] = 0.0;
-    } else {
-        int lf = 0;
-        for (int k = 0; k < P.twoD; k++) {
-            const int y = P.A[(int64_t)x * P.twoD + k];
-            lf -= (int)P.J8[(int64_t)x * P.twoD + k] * sx * (2 * sget(s, y) - 1);
-        }
-        P.lfi[tid] = 2 * lf; P.lfi_last[tid] = 0;
+        for (int j = 0; j < P.Nk; j++) lf = __dadd_rn(lf, __dmul_rn((double)(1 - 2 * (si ^ sget(s, (int)(off + j)))), P.Jd[(int64_t)j * P.Nk + i]));
+        P.lfd[cur + i] = 2 * lf; P.lfd[cur + P.Nk + i] = 0.0;
+    } else {                     // SK.jl:68-76
+        int sc = 0;
+        for (int j = 0; j < P.Nk; j++) sc += (int)P.Jb[(int64_t)j * P.Nk + i] ^ sget(s, (int)(off + j));
+        const int lf = -(2 * si - 1) * (P.Nk - 1 - 2 * sc);
+        P.lfi[cur + i] = 2 * (-lf + 2 * si); P.lfi[cur + P.Nk + i] = 0;
     }
 }
-__global__ void k_chain_energy_sum(chain_params P, double *E_out)
+// energy of one SK slice from its fresh fields, summed in site order (SK.jl:212-237 / :62-94)
+__device__ double sk_slice_energy(const chain_params &P, int skind, int64_t r, int k, const uint64_t *s)
+{
+    const int64_t cur = r * 2 * P.N + (int64_t)k * 2 * P.Nk;
+    if (skind == RRRMC_SK_F64) {
+        double n = 0.0;
+        for (int i = 0; i < P.Nk; i++) n = __dsub_rn(n, P.lfd[cur + i] / 2);
+        return n / 2;
+    }
+    if (skind == RRRMC_SK_BIN) {
+        long long sums = 0, n;
+        for (int i = 0; i < P.Nk; i++) sums += sget(s, (int)((int64_t)k * P.Nk + i));
+        n = -2 * sums;
+        for (int i = 0; i < P.Nk; i++) { const int si = sget(s, (int)((int64_t)k * P.Nk + i)); n += -(P.lfi[cur + i] / 2 - 2 * si); }
+        n /= 2;
+        return (double)n / P.sN;
+    }
+    return 0.0;
+}
+__device__ long long qt_energy0(const chain_params &P, const uint64_t *s) // QT.jl:68-82
+{
+    long long n = 0;
+    for (int i = 0; i < P.Nk; i++) {
+        int sj = sget(s, i + (P.M - 1) * P.Nk);
+        for (int k = 0; k < P.M; k++) { const int sk = sget(s, i + k * P.Nk); n -= 1 - 2 * (sk ^ sj); sj = sk; }
+    }
+    return n;
+}
+// mode 0: energy(X, C) -> E_out[r];  3: same and start the chain's tracked energy from it;
+// 1: Renergies -> E_out[r*M + k];  2: energy0 -> E_out[r]
+__global__ void k_chain_energy_sum(chain_params P, double *E_out, int mode)
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= P.R) return;
+    const uint64_t *s = P.chunks + r * P.nchunks;
+    if (mode == 1) { for (int k = 0; k < P.M; k++) E_out[r * P.M + k] = sk_slice_energy(P, P.inner, r, k, s); return; }
+    if (mode == 2) { E_out[r] = (double)qt_energy0(P, s); return; }
     double E;
-    if (P.kind == RRRMC_EA_F64) {
+    if (P.kind == RRRMC_EA_F64) { // EA.jl:606-611
         double e = 0.0;
-        for (int x = 0; x < P.N; x++) e = __dadd_rn(e, P.lfd[r * P.N + x] / 2);
+        for (int x = 0; x < P.N; x++) e = __dadd_rn(e, P.lfd[r * 2 * P.N + x] / 2);
         E = e / 2;
-    } else {
+    } else if (is_ea(P.kind)) {   // EA.jl:216-221
         long long n = 0;
-        for (int x = 0; x < P.N; x++) n += P.lfi[r * P.N + x] / 2;
+        for (int x = 0; x < P.N; x++) n += P.lfi[r * 2 * P.N + x] / 2;
         E = (double)n / 2.0;
+    } else if (is_sk(P.kind)) E = sk_slice_energy(P, P.kind, r, 0, s);
+    else if (P.kind == RRRMC_QT) E = (double)qt_energy0(P, s) * P.fourK / 4; // QT.jl:84
+    else {                        // GraphQuant, QT.jl:185-199
+        E = (double)qt_energy0(P, s) * P.fourK / 4;
+        for (int k = 0; k < P.M; k++) E = __dadd_rn(E, sk_slice_energy(P, P.inner, r, k, s) / (double)P.M);
     }
     E_out[r] = E;
-    chain_hdr &h = P.hdr[r];
-    h.E = E; h.move_last = -1;
+    if (mode == 3) P.hdr[r].E = E;
 }
 __global__ void k_chain_hdr_reset(chain_params P, int keep_rng)
 {
@@ -548,34 +770,38 @@ __global__ void k_chain_hdr_reset(chain_params P, int keep_rng)
     if (!keep_rng) h.rng_n = 0;
     h.pending = 0; h.pmove = 0; h.status = 0; h.built = 0; h.trefresh = 0; h.done = 0;
 }
-// naive ΔE straight from the spins (EA.jl:277-289 commented form == -lfields of a fresh cache)
-__global__ void k_chain_delta_site(chain_params P, int site, double *out)
+// delta_energy straight from the caches: what = 0 delta_energy(X,C,i), 1 residual; all replicas of one site
+__global__ void k_chain_delta_site(chain_params P, int site, int what, double *out)
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= P.R) return;
-    const uint64_t *s = P.chunks + r * P.nchunks;
-    const int sx = 2 * sget(s, site) - 1;
-    double lf = 0.0;
-    for (int k = 0; k < P.twoD; k++) {
-        const int y = P.A[(int64_t)site * P.twoD + k];
-        const double J = P.kind == RRRMC_EA_F64 ? P.Jd[(int64_t)site * P.twoD + k] : (double)P.J8[(int64_t)site * P.twoD + k];
-        lf = __dsub_rn(lf, __dmul_rn(__dmul_rn(J, (double)sx), (double)(2 * sget(s, y) - 1)));
-    }
-    out[r] = -(2 * lf);
+    const gview X = make_view(P, r);
+    out[r] = what ? gv_delta_residual(X, site) : gv_delta_energy(X, site);
 }
 __global__ void k_chain_delta_replica(chain_params P, int64_t r, double *out)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= P.N) return;
+    const gview X = make_view(P, r);
+    out[x] = gv_delta_energy(X, x);
+}
+// overlaps(X) (QT.jl:213-251): out[r*(M/2) + d-1] = normalised Σ over slice pairs at Trotter distance d of Σ_i σσ'
+__global__ void k_chain_overlaps(chain_params P, double *out)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.R) return;
     const uint64_t *s = P.chunks + r * P.nchunks;
-    const int sx = 2 * sget(s, x) - 1;
-    double lf = 0.0;
-    for (int k = 0; k < P.twoD; k++) {
-        const int y = P.A[(int64_t)x * P.twoD + k];
-        const double J = P.kind == RRRMC_EA_F64 ? P.Jd[(int64_t)x * P.twoD + k] : (double)P.J8[(int64_t)x * P.twoD + k];
-        lf = __dsub_rn(lf, __dmul_rn(__dmul_rn(J, (double)sx), (double)(2 * sget(s, y) - 1)));
-    }
-    out[x] = -(2 * lf);
+    const int M = P.M, Nk = P.Nk, H = M / 2;
+    for (int d = 0; d < H; d++) out[r * H + d] = 0.0;
+    for (int k1 = 0; k1 < M - 1; k1++)
+        for (int k2 = k1 + 1; k2 < M; k2++) {
+            long long sum = 0;
+            for (int i = 0; i < Nk; i++) sum += sget(s, k1 * Nk + i) ^ sget(s, k2 * Nk + i);
+            const int dl = k2 - k1 < M + k1 - k2 ? k2 - k1 : M + k1 - k2;
+            out[r * H + dl - 1] += (double)(Nk - 2 * sum);
+        }
+    for (int d = 1; d <= (M - 1) / 2; d++) out[r * H + d - 1] /= (double)((long long)M * Nk);
+    if (M % 2 == 0) out[r * H + H - 1] /= (double)((long long)M * Nk) / 2; // multiplicity M/2 at the antipodal distance (QT.jl:240-249)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -585,9 +811,10 @@ void chain_free(rrrmc_state *s)
 {
     chain_store *c = s->chain;
     if (!c) return;
-    cudaFree(c->lfi); cudaFree(c->lfi_last); cudaFree(c->lfd); cudaFree(c->lfd_last); cudaFree(c->hdr);
+    cudaFree(c->lfi); cudaFree(c->lfd); cudaFree(c->ml); cudaFree(c->sw); cudaFree(c->hdr);
     cudaFree(c->av); cudaFree(c->apos); cudaFree(c->cls); cudaFree(c->dEs); cudaFree(c->dv); cudaFree(c->dps);
-    cudaFree(c->d_Es); cudaFree(c->d_DE); cudaFree(c->d_beta); cudaFree(c->d_E);
+    cudaFree(c->csj); cudaFree(c->csdE); cudaFree(c->csp);
+    cudaFree(c->d_Es); cudaFree(c->d_DE); cudaFree(c->d_beta); cudaFree(c->d_E); cudaFree(c->d_aux);
     cudaFree(c->d_tkind); cudaFree(c->d_tival); cudaFree(c->d_tfval);
     delete c;
     s->chain = nullptr;
@@ -609,17 +836,31 @@ rrrmc_status_t chain_sync_from_multispin(rrrmc_state *s)
     return RRRMC_OK;
 }
 
-static rrrmc_status_t chain_ensure(rrrmc_state *s, bool need_cache)
+static bool graph_f64_fields(const rrrmc_graph *g)
+{
+    return g->kind == RRRMC_EA_F64 || g->kind == RRRMC_SK_F64 || (g->kind == RRRMC_QUANT && g->inner == RRRMC_SK_F64);
+}
+static bool graph_has_fields(const rrrmc_graph *g)
+{
+    return !(g->kind == RRRMC_QT || (g->kind == RRRMC_QUANT && g->inner == RRRMC_EMPTY));
+}
+
+// cache: 0 none, 1 discrete (ΔE classes), 2 continuous (Wong-Easton tree)
+static rrrmc_status_t chain_ensure(rrrmc_state *s, int cache)
 {
     rrrmc_graph *g = s->g;
-    RR_ARG(g->twoD <= MAXDEG, "2D = %d exceeds the chain kernels' limit %d", g->twoD, MAXDEG);
+    RR_ARG(g->kind == RRRMC_QT || g->kind == RRRMC_QUANT || is_sk_kind(g->kind) || g->twoD <= MAXDEG,
+           "2D = %d exceeds the chain kernels' limit %d", g->twoD, MAXDEG);
     if (!s->chain) {
         chain_store *c = new chain_store();
-        c->R = s->R; c->N = g->N; c->f64 = g->kind == RRRMC_EA_F64; c->nDE = (int)g->allDE.size();
+        c->R = s->R; c->N = g->N; c->f64 = graph_f64_fields(g); c->nDE = (int)g->allDE.size();
         s->chain = c;
         const size_t RN = (size_t)s->R * g->N;
-        if (c->f64) { RR_CUDA(cudaMalloc(&c->lfd, RN * 8)); RR_CUDA(cudaMalloc(&c->lfd_last, RN * 8)); }
-        else { RR_CUDA(cudaMalloc(&c->lfi, RN * 4)); RR_CUDA(cudaMalloc(&c->lfi_last, RN * 4)); }
+        if (graph_has_fields(g)) {
+            if (c->f64) RR_CUDA(cudaMalloc(&c->lfd, RN * 2 * 8)); else RR_CUDA(cudaMalloc(&c->lfi, RN * 2 * 4));
+        }
+        RR_CUDA(cudaMalloc(&c->ml, sizeof(int32_t) * s->R * g->M));
+        RR_CUDA(cudaMalloc(&c->sw, (size_t)s->R * g->M));
         RR_CUDA(cudaMalloc(&c->hdr, sizeof(chain_hdr) * s->R));
         RR_CUDA(cudaMemsetAsync(c->hdr, 0, sizeof(chain_hdr) * s->R, g->ctx->stream));
         RR_CUDA(cudaMalloc(&c->d_beta, 8 * s->R));
@@ -630,22 +871,32 @@ static rrrmc_status_t chain_ensure(rrrmc_state *s, bool need_cache)
         }
     }
     chain_store *c = s->chain;
-    if (need_cache) {
-        const size_t RN = (size_t)s->R * g->N;
-        if (!c->f64 && !c->av) {
-            RR_ARG(c->nDE >= 1 && c->nDE <= MAXL, "|allΔE| = %d exceeds the discrete cache limit %d", c->nDE, MAXL);
-            RR_CUDA(cudaMalloc(&c->av, RN * 4 * 2 * c->nDE));
-            RR_CUDA(cudaMalloc(&c->apos, RN * 4));
-            RR_CUDA(cudaMalloc(&c->cls, RN));
-        }
-        if (c->f64 && !c->dv) {
-            c->levs = 0; while (((int64_t)1 << c->levs) < g->N) c->levs++;
-            c->N2 = (int64_t)1 << c->levs;
-            RR_CUDA(cudaMalloc(&c->dEs, RN * 8));
-            RR_CUDA(cudaMalloc(&c->dv, (size_t)s->R * (c->N2 + 1) * 8));
-            RR_CUDA(cudaMalloc(&c->dps, (size_t)s->R * (c->N2 + 1) * 8));
-        }
+    const size_t RN = (size_t)s->R * g->N;
+    if (cache == 1 && !c->disc_ready) {
+        RR_ARG(c->nDE >= 1 && c->nDE <= MAXL, "|allΔE| = %d exceeds the discrete cache limit %d", c->nDE, MAXL);
+        RR_CUDA(cudaMalloc(&c->av, RN * 4 * 2 * c->nDE));
+        RR_CUDA(cudaMalloc(&c->apos, RN * 4));
+        RR_CUDA(cudaMalloc(&c->cls, RN));
+        c->disc_ready = true;
     }
+    if (cache == 2 && !c->cont_ready) {
+        c->levs = 0; while (((int64_t)1 << c->levs) < g->N) c->levs++;
+        c->N2 = (int64_t)1 << c->levs;
+        RR_CUDA(cudaMalloc(&c->dEs, RN * 8));
+        RR_CUDA(cudaMalloc(&c->dv, (size_t)s->R * (c->N2 + 1) * 8));
+        RR_CUDA(cudaMalloc(&c->dps, (size_t)s->R * (c->N2 + 1) * 8));
+        RR_CUDA(cudaMalloc(&c->csj, (size_t)s->R * (g->N + 1) * 4));
+        RR_CUDA(cudaMalloc(&c->csdE, (size_t)s->R * (g->N + 1) * 8));
+        RR_CUDA(cudaMalloc(&c->csp, (size_t)s->R * (g->N + 1) * 8));
+        c->cont_ready = true;
+    }
+    return RRRMC_OK;
+}
+static rrrmc_status_t chain_aux(rrrmc_state *s, int64_t n, double **out)
+{
+    chain_store *c = s->chain;
+    if (c->aux_len < n) { cudaFree(c->d_aux); c->d_aux = nullptr; RR_CUDA(cudaMalloc(&c->d_aux, 8 * n)); c->aux_len = n; }
+    *out = c->d_aux;
     return RRRMC_OK;
 }
 
@@ -654,28 +905,33 @@ static void chain_fill_params(rrrmc_state *s, chain_params &P)
     rrrmc_graph *g = s->g; chain_store *c = s->chain;
     memset(&P, 0, sizeof P);
     P.kind = g->kind; P.N = (int)g->N; P.twoD = g->twoD; P.nDE = c->nDE; P.levs = c->levs; P.N2 = c->N2;
+    P.Nk = (int)g->Nk; P.M = (int)g->M; P.inner = g->inner; P.fourK = g->fourK; P.sN = g->sN;
     P.R = s->R; P.nchunks = s->nchunks; P.chain0 = 0;
-    P.A = g->d_A; P.J8 = g->d_J8; P.Jd = g->d_Jd;
+    P.A = g->d_A; P.J8 = g->d_J8; P.Jd = g->d_Jd; P.Jb = g->d_Jb;
     P.chunks = s->d_chunks;
-    P.lfi = c->lfi; P.lfi_last = c->lfi_last; P.lfd = c->lfd; P.lfd_last = c->lfd_last;
+    P.lfi = c->lfi; P.lfd = c->lfd; P.ml = c->ml; P.sw = c->sw;
     P.hdr = c->hdr; P.av = c->av; P.apos = c->apos; P.cls = c->cls;
-    P.dEs = c->dEs; P.dv = c->dv; P.dps = c->dps; P.DE = c->d_DE; P.beta = c->d_beta;
+    P.dEs = c->dEs; P.dv = c->dv; P.dps = c->dps; P.csj = c->csj; P.csdE = c->csdE; P.csp = c->csp;
+    P.DE = c->d_DE; P.beta = c->d_beta;
     P.step = 1;
+    // a warp per chain where an accepted flip costs O(N) (SK and GraphQuant over SK)
+    P.coop = (is_sk_kind(g->kind) || (g->kind == RRRMC_QUANT && g->inner != RRRMC_EMPTY)) ? 1 : 0;
 }
 
-static rrrmc_status_t chain_energy_init(rrrmc_state *s, chain_params &P)
+static rrrmc_status_t chain_energy_init(rrrmc_state *s, chain_params &P, bool start_run = false)
 {
     rrrmc_ctx *ctx = s->g->ctx;
     k_chain_lfields<<<div_up(P.R * P.N, 256), 256, 0, ctx->stream>>>(P);
-    k_chain_energy_sum<<<div_up(P.R, 64), 64, 0, ctx->stream>>>(P, s->chain->d_E);
+    k_chain_energy_sum<<<div_up(P.R, 64), 64, 0, ctx->stream>>>(P, s->chain->d_E, start_run ? 3 : 0);
     ctx->launches += 2;
     RR_CUDA(cudaGetLastError());
+    s->chain_fields_valid = true;
     return RRRMC_OK;
 }
 
 rrrmc_status_t chain_energy(rrrmc_state *s, double *E_out)
 {
-    RR_TRY(chain_ensure(s, false));
+    RR_TRY(chain_ensure(s, 0));
     RR_TRY(chain_sync_from_multispin(s));
     chain_params P; chain_fill_params(s, P);
     RR_TRY(chain_energy_init(s, P));
@@ -683,13 +939,20 @@ rrrmc_status_t chain_energy(rrrmc_state *s, double *E_out)
     RR_CUDA(cudaStreamSynchronize(s->g->ctx->stream));
     return RRRMC_OK;
 }
-rrrmc_status_t chain_delta_energy_site(rrrmc_state *s, int64_t site0, double *out)
+// delta_energy / residual read the caches, like the reference: (re)build them when the configuration changed
+static rrrmc_status_t chain_fields_current(rrrmc_state *s, chain_params &P)
 {
-    RR_TRY(chain_ensure(s, false));
+    RR_TRY(chain_ensure(s, 0));
     RR_TRY(chain_sync_from_multispin(s));
-    chain_params P; chain_fill_params(s, P);
+    chain_fill_params(s, P);
+    if (!s->chain_fields_valid) RR_TRY(chain_energy_init(s, P));
+    return RRRMC_OK;
+}
+rrrmc_status_t chain_delta_energy_site(rrrmc_state *s, int64_t site0, int what, double *out)
+{
+    chain_params P; RR_TRY(chain_fields_current(s, P));
     rrrmc_ctx *ctx = s->g->ctx;
-    k_chain_delta_site<<<div_up(P.R, 128), 128, 0, ctx->stream>>>(P, (int)site0, s->chain->d_E);
+    k_chain_delta_site<<<div_up(P.R, 128), 128, 0, ctx->stream>>>(P, (int)site0, what, s->chain->d_E);
     ctx->launches++;
     RR_CUDA(cudaGetLastError());
     RR_CUDA(cudaMemcpyAsync(out, s->chain->d_E, 8 * s->R, cudaMemcpyDeviceToHost, ctx->stream));
@@ -698,18 +961,57 @@ rrrmc_status_t chain_delta_energy_site(rrrmc_state *s, int64_t site0, double *ou
 }
 rrrmc_status_t chain_delta_energy_replica(rrrmc_state *s, int64_t replica, double *out)
 {
-    RR_TRY(chain_ensure(s, false));
-    RR_TRY(chain_sync_from_multispin(s));
-    chain_params P; chain_fill_params(s, P);
+    chain_params P; RR_TRY(chain_fields_current(s, P));
     rrrmc_ctx *ctx = s->g->ctx;
-    double *d_tmp = nullptr;
-    RR_CUDA(cudaMalloc(&d_tmp, 8 * P.N));
+    double *d_tmp; RR_TRY(chain_aux(s, P.N, &d_tmp));
     k_chain_delta_replica<<<div_up(P.N, 128), 128, 0, ctx->stream>>>(P, replica, d_tmp);
     ctx->launches++;
     RR_CUDA(cudaGetLastError());
     RR_CUDA(cudaMemcpyAsync(out, d_tmp, 8 * P.N, cudaMemcpyDeviceToHost, ctx->stream));
     RR_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_tmp);
+    return RRRMC_OK;
+}
+// GraphQuant observables (QT.jl:113-121, 201-268). what: 0 transverse_mag(β=arg), 1 Qenergy, 2 Renergies, 3 overlaps
+rrrmc_status_t chain_quant_observable(rrrmc_state *s, int what, double arg, double *out)
+{
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    RR_TRY(chain_ensure(s, 0));
+    RR_TRY(chain_sync_from_multispin(s));
+    chain_params P; chain_fill_params(s, P);
+    const int64_t R = s->R, M = g->M, H = M / 2;
+    if (what == 3) {
+        double *d; RR_TRY(chain_aux(s, R * std::max<int64_t>(H, 1), &d));
+        k_chain_overlaps<<<div_up(R, 64), 64, 0, ctx->stream>>>(P, d);
+        ctx->launches++;
+        RR_CUDA(cudaGetLastError());
+        RR_CUDA(cudaMemcpyAsync(out, d, 8 * R * H, cudaMemcpyDeviceToHost, ctx->stream));
+        RR_CUDA(cudaStreamSynchronize(ctx->stream));
+        return RRRMC_OK;
+    }
+    double *d; RR_TRY(chain_aux(s, R * (M + 1), &d));
+    std::vector<double> e0(R), re;
+    k_chain_energy_sum<<<div_up(R, 64), 64, 0, ctx->stream>>>(P, d, 2);
+    ctx->launches++;
+    RR_CUDA(cudaMemcpyAsync(e0.data(), d, 8 * R, cudaMemcpyDeviceToHost, ctx->stream));
+    if (what != 0) { // slice energies need fresh fields (energy(X1[k], C1[k]) resets them, QT.jl:204-209, :262-265)
+        RR_TRY(chain_energy_init(s, P));
+        k_chain_energy_sum<<<div_up(R, 64), 64, 0, ctx->stream>>>(P, d + R, 1);
+        ctx->launches++;
+        re.resize(R * M);
+        RR_CUDA(cudaMemcpyAsync(re.data(), d + R, 8 * R * M, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    RR_CUDA(cudaGetLastError());
+    RR_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (what == 2) { memcpy(out, re.data(), 8 * R * M); return RRRMC_OK; }
+    const double beta = what == 0 ? arg : g->beta;
+    for (int64_t r = 0; r < R; r++) {
+        const double p = -e0[r] / (double)g->N, x = beta * g->fourK / 2;
+        const double tm = cosh(x) - p * sinh(x);                 // QT.jl:113-121
+        if (what == 0) { out[r] = tm; continue; }
+        double E = -g->Gamma * tm;                               // QT.jl:253-268
+        for (int64_t k = 0; k < M; k++) E += re[r * M + k] / (double)g->N;
+        out[r] = E;
+    }
     return RRRMC_OK;
 }
 
@@ -730,7 +1032,7 @@ static rrrmc_status_t chain_drive(rrrmc_state *s, chain_params &P, rrrmc_hook_fn
     P.Es = c->d_Es; P.Es_rows = rows_per_launch; P.quota = rows_per_launch;
     // spread chains: one per warp while they fit on the chip's schedulers
     const int64_t warps = (int64_t)ctx->sm_count * 16;
-    P.cpw = (int)std::min<int64_t>(32, std::max<int64_t>(1, (P.R + warps - 1) / warps));
+    P.cpw = P.coop ? 1 : (int)std::min<int64_t>(32, std::max<int64_t>(1, (P.R + warps - 1) / warps));
     const unsigned grid = div_up(P.R, P.cpw);
     std::vector<double> row((size_t)P.R * rows_per_launch);
     std::vector<chain_hdr> hh(P.R);
@@ -771,11 +1073,27 @@ static rrrmc_status_t chain_drive(rrrmc_state *s, chain_params &P, rrrmc_hook_fn
     float ms = 0; RR_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (info) {
-        int64_t itmax = 0; for (int64_t r = 0; r < P.R; r++) itmax = std::max<int64_t>(itmax, hh[r].it);
+        int64_t itmax = 0, accs = 0;
+        for (int64_t r = 0; r < P.R; r++) { itmax = std::max<int64_t>(itmax, hh[r].it); accs += hh[r].accepted; }
         info->nsamples = std::min(nsamples, want_rows); info->iters_done = itmax;
-        info->launches = (int64_t)(ctx->launches - l0); info->device_ms = ms;
+        info->launches = (int64_t)(ctx->launches - l0); info->device_ms = ms; info->accepted_total = accs;
     }
     return RRRMC_OK;
+}
+
+// which cache a sampler builds for this graph: rrrMC on inner_graph(X), bklMC on X (DeltaE.jl:116, RRRMC.jl:171,240,325)
+static rrrmc_status_t sampler_cache(const rrrmc_graph *g, int sampler, int *cache)
+{
+    const bool discr_full = g->kind == RRRMC_EA_PM1 || g->kind == RRRMC_EA_INT || g->kind == RRRMC_QT;
+    if (sampler == CHAIN_STANDARD) *cache = 0;
+    else if (sampler == CHAIN_RRR) *cache = (discr_full || g->kind == RRRMC_QUANT) ? 1 : 2;
+    else *cache = discr_full ? 1 : 2;
+    return RRRMC_OK;
+}
+static double default_staged_thr(const rrrmc_graph *g)
+{
+    const bool simple = g->kind == RRRMC_EA_F64 || is_sk_kind(g->kind);
+    return simple ? 0.8 : 0.5; // RRRMC.jl:163-165 (SimpleGraph 0.8, else 0.5), :226 (DoubleGraph 0.5)
 }
 
 rrrmc_status_t chain_run(rrrmc_state *s, int sampler, const double *beta, int64_t iters, int64_t step, uint64_t seed,
@@ -784,18 +1102,18 @@ rrrmc_status_t chain_run(rrrmc_state *s, int sampler, const double *beta, int64_
     rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
     RR_ARG(beta, "beta is NULL");
     for (int64_t r = 0; r < s->R; r++) RR_ARG(std::isfinite(beta[r]), "β must be finite, given: %g", beta[r]); // RRRMC.jl:159
-    RR_TRY(chain_ensure(s, sampler != CHAIN_STANDARD));
+    int cache; RR_TRY(sampler_cache(g, sampler, &cache));
+    RR_TRY(chain_ensure(s, cache));
     RR_TRY(chain_sync_from_multispin(s));
     chain_store *c = s->chain;
     chain_params P; chain_fill_params(s, P);
     P.sampler = sampler; P.iters = iters; P.step = step; P.seed = seed;
-    const bool discr = g->kind != RRRMC_EA_F64;
-    P.staged_thr = std::isnan(o->staged_thr) ? (discr ? 0.5 : 0.8) : o->staged_thr; // RRRMC.jl:163-165
+    P.staged_thr = std::isnan(o->staged_thr) ? default_staged_thr(g) : o->staged_thr;
     P.staged_thr_fact = o->staged_thr_fact;
     RR_CUDA(cudaMemcpyAsync(c->d_beta, beta, 8 * s->R, cudaMemcpyHostToDevice, ctx->stream));
     k_chain_hdr_reset<<<div_up(P.R, 64), 64, 0, ctx->stream>>>(P, seed == 0);
     ctx->launches++;
-    RR_TRY(chain_energy_init(s, P));
+    RR_TRY(chain_energy_init(s, P, true));
     s->ms_valid = false; // chains now own the configuration
     RR_TRY(chain_drive<src_philox>(s, P, hook, user, Es, Es_cap, info));
     return RRRMC_OK;
@@ -807,7 +1125,8 @@ rrrmc_status_t chain_replay(rrrmc_state *s, int64_t replica, int sampler, double
 {
     rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
     RR_ARG(std::isfinite(beta), "β must be finite, given: %g", beta);
-    RR_TRY(chain_ensure(s, sampler != CHAIN_STANDARD));
+    int cache; RR_TRY(sampler_cache(g, sampler, &cache));
+    RR_TRY(chain_ensure(s, cache));
     RR_TRY(chain_sync_from_multispin(s));
     chain_store *c = s->chain;
     if (c->tcap < ndraws) {
@@ -820,15 +1139,14 @@ rrrmc_status_t chain_replay(rrrmc_state *s, int64_t replica, int sampler, double
     RR_CUDA(cudaMemcpyAsync(c->d_tfval, fval, 8 * ndraws, cudaMemcpyHostToDevice, ctx->stream));
     chain_params P; chain_fill_params(s, P);
     P.sampler = sampler; P.iters = iters; P.step = step; P.seed = 0;
-    const bool discr = g->kind != RRRMC_EA_F64;
-    P.staged_thr = std::isnan(o->staged_thr) ? (discr ? 0.5 : 0.8) : o->staged_thr;
+    P.staged_thr = std::isnan(o->staged_thr) ? default_staged_thr(g) : o->staged_thr;
     P.staged_thr_fact = o->staged_thr_fact;
     P.tkind = c->d_tkind; P.tival = c->d_tival; P.tfval = c->d_tfval; P.tlen = ndraws;
     std::vector<double> b(s->R, beta);
     RR_CUDA(cudaMemcpyAsync(c->d_beta, b.data(), 8 * s->R, cudaMemcpyHostToDevice, ctx->stream));
     k_chain_hdr_reset<<<div_up(P.R, 64), 64, 0, ctx->stream>>>(P, 0);
     ctx->launches++;
-    RR_TRY(chain_energy_init(s, P));
+    RR_TRY(chain_energy_init(s, P, true));
     s->ms_valid = false;
     // run only the requested chain
     P.chain0 = replica; P.R = 1;

@@ -4,12 +4,14 @@
 #include "common.cuh"
 
 enum { CHAIN_STANDARD = 0, CHAIN_RRR = 1, CHAIN_BKL = 2 };
+static inline bool is_sk_kind(int k) { return k == RRRMC_SK_F64 || k == RRRMC_SK_BIN; }
 
 void chain_free(rrrmc_state *s);
 rrrmc_status_t chain_sync_to_multispin(rrrmc_state *s);   // make the multispin copy current
 rrrmc_status_t chain_sync_from_multispin(rrrmc_state *s); // make the chain copy (d_chunks) current
 rrrmc_status_t chain_energy(rrrmc_state *s, double *E_out);
-rrrmc_status_t chain_delta_energy_site(rrrmc_state *s, int64_t site0, double *out);
+rrrmc_status_t chain_delta_energy_site(rrrmc_state *s, int64_t site0, int what, double *out); // what: 0 ΔE, 1 residual
+rrrmc_status_t chain_quant_observable(rrrmc_state *s, int what, double arg, double *out);
 rrrmc_status_t chain_delta_energy_replica(rrrmc_state *s, int64_t replica, double *out);
 rrrmc_status_t chain_run(rrrmc_state *s, int sampler, const double *beta, int64_t iters, int64_t step, uint64_t seed,
                          rrrmc_hook_fn hook, void *user, const rrrmc_opts_t *o, double *Es, int64_t Es_cap, rrrmc_run_info_t *info);

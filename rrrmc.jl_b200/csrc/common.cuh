@@ -47,7 +47,13 @@ struct rrrmc_graph {
     uint8_t *d_jcode = nullptr;      // PM1 lattice: bit 2d = J(i -> i+e_d) < 0, bit 2d+1 = J(i-e_d -> i) < 0
     int32_t *d_A = nullptr;          // [N*twoD]
     int8_t *d_J8 = nullptr;          // [N*twoD] (PM1/INT)
-    double *d_Jd = nullptr;          // [N*twoD] (F64)
+    double *d_Jd = nullptr;          // [N*twoD] (EA F64); [N*N] (SK F64); [Nk*Nk] (QUANT inner SK F64)
+    uint8_t *d_Jb = nullptr;         // [N*N] 0/1 (SK BIN); [Nk*Nk] (QUANT inner SK BIN)
+    // SK / QT / QUANT (SK.jl, QT.jl)
+    int64_t Nk = 0, M = 1;           // slice size and number of Trotter slices (SK: Nk = N, M = 1)
+    int inner = 0;                   // QUANT: kind of the inner graph (RRRMC_SK_F64 / RRRMC_SK_BIN / RRRMC_EMPTY)
+    double fourK = 0, Gamma = 0, beta = 0, sN = 1;
+    int max_deg = 0;                 // upper bound of |neighbors(X, i)|
 };
 
 struct rrrmc_state {
@@ -67,6 +73,7 @@ struct rrrmc_state {
     // chain layout (sequential samplers): d_chunks is the spin state, one BitVector per chain
     bool ms_valid = true;            // multispin copy is current
     bool chain_valid = false;        // d_chunks copy is current
+    bool chain_fields_valid = false; // the chains' local-field caches match d_chunks
     struct chain_store *chain = nullptr;
 };
 

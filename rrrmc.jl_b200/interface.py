@@ -207,8 +207,10 @@ def all_delta_energy(X, Cfg, replica=0):
 
 
 def neighbors(X, i):
-    """neighbors(X, i) (Interface.jl:158)."""
-    out = np.zeros(64, np.int64); n = C.c_int()
+    """neighbors(X, i) (Interface.jl:158), in the reference's iteration order."""
+    m = C.c_int64()
+    check(lib().rrrmc_max_neighbors(X._h, C.byref(m)))
+    out = np.zeros(max(64, m.value), np.int64); n = C.c_int()
     check(lib().rrrmc_neighbors(X._h, i, ptr(out), C.byref(n)))
     return tuple(int(v) for v in out[:n.value])
 
@@ -281,6 +283,142 @@ class GraphEANormal(AbstractGraph):
         h = C.c_void_p()
         check(lib().rrrmc_graph_ea_create(self.ctx.h, L, D, _ffi.EA_F64, ptr(self.A), ptr(self.J), C.byref(h)))
         self._h = h
+
+
+def gen_J_gauss(N, rng=None):
+    """gen_J_gauss (src/graphs/SK.jl:170-179): symmetric N(0, 1/N) couplings, zero diagonal, as an (N, N) array."""
+    rng = rng or np.random.default_rng()
+    J = np.triu(rng.standard_normal((N, N)) / np.sqrt(N), 1)
+    return J + J.T
+
+
+def gen_J_bits(N, rng=None):
+    """gen_J (src/graphs/SK.jl:17-26): symmetric random bit matrix, zero diagonal, as an (N, N) uint8 array."""
+    rng = rng or np.random.default_rng()
+    J = np.triu(rng.integers(0, 2, (N, N)), 1)
+    return (J + J.T).astype(np.uint8)
+
+
+class GraphSKNormal(AbstractGraph):
+    """GraphSKNormal(N) <: SimpleGraph{Float64} (src/graphs/SK.jl:181-210): J_ij ~ N(0, 1/N)."""
+    ET = float
+
+    def __init__(self, N, replicas=1, J=None, rng=None, ctx=None):
+        self.N, self.replicas = int(N), int(replicas)
+        self.ctx = ctx or Context.default()
+        self.J = np.ascontiguousarray(gen_J_gauss(N, rng) if J is None else J, np.float64)
+        if self.J.shape != (self.N, self.N):
+            raise ValueError(f"invalid J inner length, expected {self.N}")  # SK.jl:188
+        h = C.c_void_p()
+        check(lib().rrrmc_graph_sk_create(self.ctx.h, self.N, _ffi.SK_F64, ptr(self.J), C.byref(h)))
+        self._h = h
+
+
+class GraphSK(AbstractGraph):
+    """GraphSK(N) <: SimpleGraph{Float64} (src/graphs/SK.jl:28-60): J_ij = ±1/√N stored as bits."""
+    ET = float
+
+    def __init__(self, N, replicas=1, J=None, rng=None, ctx=None):
+        self.N, self.replicas = int(N), int(replicas)
+        self.ctx = ctx or Context.default()
+        self.J = np.ascontiguousarray(gen_J_bits(N, rng) if J is None else J, np.uint8)
+        if self.J.shape != (self.N, self.N):
+            raise ValueError(f"invalid J inner length, expected {self.N}")  # SK.jl:35
+        h = C.c_void_p()
+        check(lib().rrrmc_graph_sk_create(self.ctx.h, self.N, _ffi.SK_BIN, ptr(self.J), C.byref(h)))
+        self._h = h
+
+
+class GraphQT(AbstractGraph):
+    """GraphQT{fourK}(N, M) <: DiscrGraph{Float64} (src/graphs/QT.jl:42-54): the Trotter-direction couplings."""
+    ET = float
+
+    def __init__(self, N, M, fourK, replicas=1, ctx=None):
+        self.N, self.M, self.Nk, self.fourK, self.replicas = int(N), int(M), int(N) // int(M), float(fourK), int(replicas)
+        self.ctx = ctx or Context.default()
+        h = C.c_void_p()
+        check(lib().rrrmc_graph_qt_create(self.ctx.h, self.N, self.M, self.fourK, C.byref(h)))
+        self._h = h
+
+
+class GraphQuant(AbstractGraph):
+    """GraphQuant(Nk, M, Γ, β, inner, J) <: DoubleGraph{Float64} (src/graphs/QT.jl:126-170): M Suzuki-Trotter
+    slices of a classical graph. inner: "SK" (GraphQSKT, QAliases.jl:34-43), "SKNormal" (GraphQSKNormalT, :46-47)
+    or "Empty" (GraphQ0T, :19-31)."""
+    ET = float
+
+    def __init__(self, Nk, M, Γ, β, inner="SK", replicas=1, J=None, rng=None, ctx=None):
+        self.Nk, self.M, self.N, self.Γ, self.β, self.replicas = int(Nk), int(M), int(Nk) * int(M), float(Γ), float(β), int(replicas)
+        self.ctx = ctx or Context.default()
+        self.inner = inner
+        kind = {"SK": _ffi.SK_BIN, "SKNormal": _ffi.SK_F64, "Empty": _ffi.EMPTY}[inner]
+        if inner == "SK":
+            self.J = np.ascontiguousarray(gen_J_bits(Nk, rng) if J is None else J, np.uint8)
+        elif inner == "SKNormal":
+            self.J = np.ascontiguousarray(gen_J_gauss(Nk, rng) if J is None else J, np.float64)
+        else:
+            self.J = None
+        h = C.c_void_p()
+        check(lib().rrrmc_graph_quant_create(self.ctx.h, self.Nk, self.M, self.Γ, self.β, kind, ptr(self.J), C.byref(h)))
+        self._h = h
+        fk = C.c_double()
+        check(lib().rrrmc_graph_fourK(self._h, C.byref(fk)))
+        self.fourK = fk.value
+
+    def inner_graph(self):
+        """inner_graph(X) (Interface.jl:239-240; QT.jl:148): the GraphQT part, on its own replica batch."""
+        return GraphQT(self.N, self.M, self.fourK, replicas=self.replicas, ctx=self.ctx)
+
+
+def GraphQSKT(N, M, Γ, β, **kw):
+    """GraphQSKT(N, M, Γ, β) (src/QAliases.jl:34-43)."""
+    return GraphQuant(N, M, Γ, β, "SK", **kw)
+
+
+def GraphQSKNormalT(N, M, Γ, β, **kw):
+    """GraphQSKNormalT(N, M, Γ, β) (src/QAliases.jl:46-47)."""
+    return GraphQuant(N, M, Γ, β, "SKNormal", **kw)
+
+
+def GraphQ0T(N, M, Γ, β, **kw):
+    """GraphQ0T(N, M, Γ, β) (src/QAliases.jl:19-31)."""
+    return GraphQuant(N, M, Γ, β, "Empty", **kw)
+
+
+def delta_energy_residual(X, Cfg, move):
+    """delta_energy_residual(X, C, move) (Interface.jl:254-261; QT.jl:270-281)."""
+    X._upload(Cfg)
+    dE = np.zeros(X.replicas, np.float64)
+    check(lib().rrrmc_delta_energy_residual(X._state, move, ptr(dE)))
+    return _scalarize(X, dE)
+
+
+def _observable(fn, X, Cfg, n, *args):
+    if Cfg is not None:
+        X._upload(Cfg)
+    out = np.zeros((X.replicas, n) if n > 1 else X.replicas, np.float64)
+    check(fn(X._ensure_state(), *args, ptr(out)))
+    return out[0] if X.replicas == 1 else out
+
+
+def transverse_mag(X, Cfg, β):
+    """transverse_mag(X, C, β) (QT.jl:113-121)."""
+    return _observable(lib().rrrmc_transverse_mag, X, Cfg, 1, float(β))
+
+
+def Qenergy(X, Cfg):
+    """Qenergy(X, C) (QT.jl:253-268)."""
+    return _observable(lib().rrrmc_Qenergy, X, Cfg, 1)
+
+
+def Renergies(X, Cfg=None):
+    """Renergies(X) (QT.jl:201-211): classical energy of every Trotter slice."""
+    return _observable(lib().rrrmc_Renergies, X, Cfg, X.M)
+
+
+def overlaps(X, Cfg=None):
+    """overlaps(X) (QT.jl:213-251): mean overlap between slices at Trotter distance 1..M÷2."""
+    return _observable(lib().rrrmc_overlaps, X, Cfg, X.M // 2)
 
 
 # ----------------------------------------------------------------------------------------------------
