@@ -184,6 +184,20 @@ rrrmc_status_t rrrmc_replay(rrrmc_state_t *s, int64_t replica, int sampler, doub
 rrrmc_status_t rrrmc_checkerboard_sweeps(rrrmc_state_t *s, const uint64_t *thr64, int nthr, int planes_K, int planes_M,
                                          uint64_t seed, uint64_t sweep0, int64_t nsweeps);
 
+/* ---- dense GraphSKNormal path (BASELINE config 4) ----------------------------------------------
+ * Local-field initialisation for the whole batch = the energy(X, C) contraction of SK.jl:212-237,
+ * lfields[r][i] = 2 σ_ri Σ_j J_ij σ_rj. use_tensor_cores=1: exact fixed-point INT8 digit-plane GEMMs on tcgen05
+ * (|error| <= N·2^-(P+1) from quantising J to 40 bits); 0: CUDA cores in the reference's summation order (bit-exact).
+ * E_out[R] (may be NULL): energies; device_ms (may be NULL): CUDA-event time of the field kernels. */
+rrrmc_status_t rrrmc_sk_fields_init(rrrmc_state_t *s, int use_tensor_cores, double *E_out, float *device_ms);
+rrrmc_status_t rrrmc_sk_get_fields(rrrmc_state_t *s, double *lf_out /* [R*N] */);
+/* Lock-step Metropolis sweeps (new engine): every replica attempts sites 1..N in order, accept() of RRRMC.jl:39 with
+ * ΔE_i = lfields[i] (SK.jl:278-284) and the update_cache! axpy of SK.jl:252-265 on acceptance. U for (sweep t, site i,
+ * replica r) is Philox4x32-10(ctr=(i, r, t_lo, t_hi^'SKLS'), key=seed). E_out[R], accepted_out[R] may be NULL;
+ * the accepted counters accumulate over calls. */
+rrrmc_status_t rrrmc_sk_metropolis_sweeps(rrrmc_state_t *s, const double *beta, uint64_t seed, uint64_t sweep0,
+                                          int64_t nsweeps, double *E_out, int64_t *accepted_out);
+
 #ifdef __cplusplus
 }
 #endif

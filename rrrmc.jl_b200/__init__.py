@@ -7,11 +7,11 @@ from ._ffi import RRRMCError
 from .interface import (DEFAULT_SEED, Config, Context, GraphEA, GraphEANormal, GraphQ0T, GraphQSKNormalT, GraphQSKT, GraphQT,
                         GraphQuant, GraphSK, GraphSKNormal, Qenergy, Renergies, allDeltaE, all_delta_energy, bklMC, delta_energy,
                         delta_energy_residual, energy, gen_EA, gen_J, gen_J_bits, gen_J_gauss, neighbors, overlaps, replay, rrrMC,
-                        spinflip, standardMC, transverse_mag, update_cache)
+                        sk_fields_init, sk_metropolis_sweeps, spinflip, standardMC, transverse_mag, update_cache)
 from .interface import allΔE  # noqa: F401
 
 __all__ = ["Config", "Context", "GraphEA", "GraphEANormal", "GraphSK", "GraphSKNormal", "GraphQT", "GraphQuant", "GraphQSKT",
            "GraphQSKNormalT", "GraphQ0T", "allDeltaE", "allΔE", "all_delta_energy", "bklMC", "delta_energy",
            "delta_energy_residual", "energy", "gen_EA", "gen_J", "gen_J_gauss", "gen_J_bits", "neighbors", "replay", "rrrMC",
-           "spinflip", "standardMC", "update_cache", "transverse_mag", "Qenergy", "Renergies", "overlaps", "RRRMCError",
+           "spinflip", "standardMC", "update_cache", "sk_fields_init", "sk_metropolis_sweeps", "transverse_mag", "Qenergy", "Renergies", "overlaps", "RRRMCError",
            "DEFAULT_SEED"]

@@ -65,6 +65,9 @@ SIGNATURES = {
     "rrrmc_Qenergy": (_i32, [_vp, _vp]),
     "rrrmc_Renergies": (_i32, [_vp, _vp]),
     "rrrmc_overlaps": (_i32, [_vp, _vp]),
+    "rrrmc_sk_fields_init": (_i32, [_vp, _i32, _vp, C.POINTER(C.c_float)]),
+    "rrrmc_sk_get_fields": (_i32, [_vp, _vp]),
+    "rrrmc_sk_metropolis_sweeps": (_i32, [_vp, _vp, _u64, _u64, _i64, _vp, _vp]),
     "rrrmc_opts_default": (_i32, [C.POINTER(Opts)]),
     "rrrmc_standard_mc": (_i32, _SAMPLER),
     "rrrmc_rrr_mc": (_i32, _SAMPLER),

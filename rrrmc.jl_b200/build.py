@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "librrrmc_b200.so")
-SOURCES = ["api.cu", "ea_multispin.cu", "chain.cu"]
+SOURCES = ["api.cu", "ea_multispin.cu", "chain.cu", "sk_dense.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--fmad=false", "-Xptxas", "-v"]
 

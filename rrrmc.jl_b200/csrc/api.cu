@@ -278,6 +278,7 @@ extern "C" rrrmc_status_t rrrmc_graph_sk_create(rrrmc_ctx_t *ctx, int64_t N, int
     rrrmc_graph *g = new rrrmc_graph();
     g->ctx = ctx; g->kind = kind; g->N = N; g->Nk = N; g->M = 1; g->max_deg = (int)N - 1;
     g->sN = sqrt((double)N); // SK.jl:47
+    if (kind == RRRMC_SK_F64) g->Jd.assign((const double *)J, (const double *)J + N * N);
     RR_CUDA(cudaSetDevice(ctx->device));
     rrrmc_status_t st = upload_sk_couplings(g, N, kind, J);
     if (st != RRRMC_OK) { delete g; return st; }
@@ -406,6 +407,7 @@ extern "C" rrrmc_status_t rrrmc_state_destroy(rrrmc_state_t *s)
     cudaFree(s->d_spins); cudaFree(s->d_chunks); cudaFree(s->d_ibuf); cudaFree(s->d_acc);
     cudaFree(s->d_flips); cudaFree(s->d_mask);
     chain_free(s);
+    sk_dense_free(s);
     delete s;
     return RRRMC_OK;
 }
@@ -418,7 +420,7 @@ extern "C" rrrmc_status_t rrrmc_state_randomize(rrrmc_state_t *s, uint64_t seed)
 {
     RR_ARG(s, "state is NULL");
     RR_CUDA(cudaSetDevice(s->g->ctx->device));
-    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false;
+    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
     return launch_randomize(s, seed);
 }
 extern "C" rrrmc_status_t rrrmc_state_upload(rrrmc_state_t *s, int64_t first, int64_t count, const uint64_t *chunks)
@@ -433,7 +435,7 @@ extern "C" rrrmc_status_t rrrmc_state_upload(rrrmc_state_t *s, int64_t first, in
     RR_CUDA(cudaMemcpyAsync(s->d_chunks, chunks, sizeof(uint64_t) * count * s->nchunks, cudaMemcpyHostToDevice, ctx->stream));
     RR_TRY(launch_upload_transpose(s, first, count));
     RR_CUDA(cudaStreamSynchronize(ctx->stream)); // the caller may free `chunks` on return
-    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false;
+    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
     return RRRMC_OK;
 }
 extern "C" rrrmc_status_t rrrmc_state_download(rrrmc_state_t *s, int64_t first, int64_t count, uint64_t *chunks)
@@ -527,7 +529,7 @@ extern "C" rrrmc_status_t rrrmc_spinflip(rrrmc_state_t *s, int64_t site, const u
     }
     RR_TRY(launch_flip_site(s, site - 1, d_mask));
     RR_CUDA(cudaStreamSynchronize(ctx->stream));
-    s->chain_valid = false; s->chain_fields_valid = false;
+    s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
     return RRRMC_OK;
 }
 extern "C" rrrmc_status_t rrrmc_magnetization(rrrmc_state_t *s, double *m_out)
@@ -568,6 +570,29 @@ extern "C" rrrmc_status_t rrrmc_transverse_mag(rrrmc_state_t *s, double beta, do
 extern "C" rrrmc_status_t rrrmc_Qenergy(rrrmc_state_t *s, double *out) { return quant_observable(s, 1, 0, out); }
 extern "C" rrrmc_status_t rrrmc_Renergies(rrrmc_state_t *s, double *out) { return quant_observable(s, 2, 0, out); }
 extern "C" rrrmc_status_t rrrmc_overlaps(rrrmc_state_t *s, double *out) { return quant_observable(s, 3, 0, out); }
+
+extern "C" rrrmc_status_t rrrmc_sk_fields_init(rrrmc_state_t *s, int use_tensor_cores, double *E_out, float *device_ms)
+{
+    RR_ARG(s, "state is NULL");
+    RR_CUDA(cudaSetDevice(s->g->ctx->device));
+    RR_TRY(chain_sync_to_multispin(s));
+    return sk_dense_fields_init(s, use_tensor_cores, E_out, device_ms);
+}
+extern "C" rrrmc_status_t rrrmc_sk_get_fields(rrrmc_state_t *s, double *lf_out)
+{
+    RR_ARG(s && lf_out, "NULL argument");
+    RR_CUDA(cudaSetDevice(s->g->ctx->device));
+    return sk_dense_get_fields(s, lf_out);
+}
+extern "C" rrrmc_status_t rrrmc_sk_metropolis_sweeps(rrrmc_state_t *s, const double *beta, uint64_t seed, uint64_t sweep0,
+                                                     int64_t nsweeps, double *E_out, int64_t *accepted_out)
+{
+    RR_ARG(s && beta, "NULL argument");
+    RR_ARG(nsweeps >= 0 && nsweeps < ((int64_t)1 << 31), "nsweeps out of range");
+    RR_CUDA(cudaSetDevice(s->g->ctx->device));
+    RR_TRY(chain_sync_to_multispin(s));
+    return sk_dense_sweeps(s, beta, seed, sweep0, nsweeps, E_out, accepted_out);
+}
 
 // ------------------------------------------------------------------------------------------------
 // samplers
@@ -653,7 +678,7 @@ extern "C" rrrmc_status_t rrrmc_checkerboard_sweeps(rrrmc_state_t *s, const uint
     cb_params p;
     RR_TRY(fill_cb_params(s, thr64, nthr, K, M, seed, p));
     for (int64_t k = 0; k < nsweeps; k++) RR_TRY(run_sweep(s, p, sweep0 + (uint64_t)k));
-    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false;
+    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
     return RRRMC_OK;
 }
 
@@ -717,7 +742,7 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
     RR_CUDA(cudaEventSynchronize(e1));
     float ms = 0; RR_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false;
+    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
     if (info) { info->nsamples = std::min(nsamples, Es ? Es_cap : nsamples); info->iters_done = done * N; info->launches = (int64_t)(ctx->launches - l0); info->device_ms = ms; info->accepted_total = -1; }
     return RRRMC_OK;
 }

@@ -1115,6 +1115,7 @@ rrrmc_status_t chain_run(rrrmc_state *s, int sampler, const double *beta, int64_
     ctx->launches++;
     RR_TRY(chain_energy_init(s, P, true));
     s->ms_valid = false; // chains now own the configuration
+    sk_dense_invalidate(s);
     RR_TRY(chain_drive<src_philox>(s, P, hook, user, Es, Es_cap, info));
     return RRRMC_OK;
 }
@@ -1148,6 +1149,7 @@ rrrmc_status_t chain_replay(rrrmc_state *s, int64_t replica, int sampler, double
     ctx->launches++;
     RR_TRY(chain_energy_init(s, P, true));
     s->ms_valid = false;
+    sk_dense_invalidate(s);
     // run only the requested chain
     P.chain0 = replica; P.R = 1;
     P.beta = c->d_beta; // all equal

@@ -18,3 +18,11 @@ rrrmc_status_t chain_run(rrrmc_state *s, int sampler, const double *beta, int64_
 rrrmc_status_t chain_replay(rrrmc_state *s, int64_t replica, int sampler, double beta, int64_t iters, int64_t step,
                             const uint8_t *kind, const int64_t *ival, const double *fval, int64_t ndraws,
                             const rrrmc_opts_t *o, double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
+
+// dense GraphSKNormal kernels (sk_dense.cu): tensor-core local-field initialisation, lock-step Metropolis sweeps
+void sk_dense_free(rrrmc_state *s);
+void sk_dense_invalidate(rrrmc_state *s);
+rrrmc_status_t sk_dense_fields_init(rrrmc_state *s, int use_tensor_cores, double *E_out, float *ms_out);
+rrrmc_status_t sk_dense_get_fields(rrrmc_state *s, double *lf_out);
+rrrmc_status_t sk_dense_sweeps(rrrmc_state *s, const double *beta, uint64_t seed, uint64_t sweep0, int64_t nsweeps,
+                               double *E_out, int64_t *acc_out);

@@ -75,6 +75,7 @@ struct rrrmc_state {
     bool chain_valid = false;        // d_chunks copy is current
     bool chain_fields_valid = false; // the chains' local-field caches match d_chunks
     struct chain_store *chain = nullptr;
+    struct sk_dense_store *skd = nullptr; // dense GraphSKNormal kernels (sk_dense.cu)
 };
 
 static inline unsigned div_up(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }

@@ -1,0 +1,414 @@
+// Dense kernels for GraphSKNormal on a replica batch (BASELINE config 4: N=4096 Gaussian couplings × 512 replicas).
+//
+//  * Local-field initialisation — the one dense contraction of the path, energy(X, C) of SK.jl:212-237:
+//        lfields[r][i] = 2 σ_ri Σ_j J_ij σ_rj
+//    as H = J·Sᵀ on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM). The spins are
+//    exactly ±1, so the product is made *exact* instead of approximated in reduced-precision floating point: J is
+//    quantised once to 40-bit fixed point and split into five signed 8-bit digit planes, each plane is an INT8 GEMM
+//    with INT32 accumulation (no rounding, no order dependence), and the epilogue recombines the five accumulators
+//    in int64. The only error is the 2^-P quantisation of J itself (|ΔH| <= N·2^-(P+1), ~1e-9 at N=4096), far inside
+//    the 1e-6 relative tolerance of the contract.
+//  * Lock-step Metropolis sweeps (new engine; the reference's per-flip update_cache! SK.jl:239-276 is the axpy):
+//    all replicas attempt site i = 1..N in order; an accepted flip streams row i of J once per CTA and updates the
+//    local fields of the CTA's replicas held in shared memory.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include "common.cuh"
+#include "kernels.cuh"
+#include "chain.cuh"
+#include "philox.cuh"
+
+constexpr int SKQ_SLICES = 5;          // 8-bit digit planes of the fixed-point couplings
+constexpr int TC_M = 128, TC_N = 64, TC_KB = 128; // CTA tile: 128 sites x 64 replicas, 128 bytes of K per stage
+
+// ------------------------------------------------------------------------------------------------
+// spins as int8 ±1, [R][Npad] (B operand of the GEMM; K-major)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_spins_to_s8(const uint64_t *__restrict__ chunks, int64_t nchunks, int64_t R, int N, int Npad, int8_t *__restrict__ out)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= R * Npad) return;
+    const int64_t r = tid / Npad; const int j = (int)(tid % Npad);
+    out[tid] = j < N ? (int8_t)(2 * (int)((chunks[r * nchunks + (j >> 6)] >> (j & 63)) & 1ull) - 1) : (int8_t)0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 helpers (PTX ISA: tcgen05.alloc / mma / commit / ld; descriptors as in CUTLASS cute/arch/mma_sm100_desc.hpp)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// K-major operand tile with 128-byte swizzle: rows of 128 bytes, 8-row atoms of 1024 bytes (SBO), descriptor version 1
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);          // start address
+    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset between 8-row atoms
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+// kind::i8, S8 x S8 -> S32, both operands K-major, M x N tile
+__host__ __device__ constexpr uint32_t umma_idesc_s8(int M, int N)
+{
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" :: "r"(mbar), "r"(parity) : "memory");
+}
+// 16 bytes of row `row` at 16-byte chunk `c16` of a swizzled 128-byte-row tile
+__device__ __forceinline__ uint32_t sw128_off(int row, int c16) { return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c16 ^ (row & 7)) << 4)); }
+
+struct sk_tc_params {
+    const int8_t *Jq;       // [SLICES][Npad][Npad] digit planes
+    const int8_t *S8;       // [Rpad][Npad]
+    double *lf;             // [R][N] out: local fields
+    int N, Npad; int64_t R, Rpad;
+    double scale;           // 2^-P
+};
+
+__global__ void __launch_bounds__(128, 1) k_sk_fields_tc(sk_tc_params P)
+{
+    __shared__ __align__(1024) uint8_t sA[TC_M * TC_KB];
+    __shared__ __align__(1024) uint8_t sB[TC_N * TC_KB];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int i0 = blockIdx.x * TC_M;
+    const int64_t r0 = (int64_t)blockIdx.y * TC_N;
+    constexpr uint32_t TMEM_COLS = 512;              // 5 accumulators x 64 columns, rounded up to a power of two
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t idesc = umma_idesc_s8(TC_M, TC_N);
+    const uint64_t descA = umma_desc_k_sw128(smem_u32(sA)), descB = umma_desc_k_sw128(smem_u32(sB));
+    uint32_t phase = 0;
+    const int nkc = P.Npad / TC_KB;
+    for (int s = 0; s < SKQ_SLICES; s++) {
+        const int8_t *A = P.Jq + (size_t)s * P.Npad * P.Npad + (size_t)(i0 + tid) * P.Npad;   // thread = one row of the A tile
+        const int8_t *B = P.S8 + (size_t)(r0 + (tid & 63)) * P.Npad + (tid >> 6) * 64;        // thread = half a row of the B tile
+        for (int kc = 0; kc < nkc; kc++) {
+            const uint4 *ga = reinterpret_cast<const uint4 *>(A + (size_t)kc * TC_KB);
+            const uint4 *gb = reinterpret_cast<const uint4 *>(B + (size_t)kc * TC_KB);
+            uint4 va[8], vb[4];
+#pragma unroll
+            for (int c = 0; c < 8; c++) va[c] = ga[c];
+#pragma unroll
+            for (int c = 0; c < 4; c++) vb[c] = gb[c];
+#pragma unroll
+            for (int c = 0; c < 8; c++) *reinterpret_cast<uint4 *>(sA + sw128_off(tid, c)) = va[c];
+#pragma unroll
+            for (int c = 0; c < 4; c++) *reinterpret_cast<uint4 *>(sB + sw128_off(tid & 63, (tid >> 6) * 4 + c)) = vb[c];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < TC_KB / 32; k++) {                    // K = 32 bytes per instruction for 8-bit operands
+                    const uint32_t accumulate = (kc | k) ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                        :: "r"(tmem_base + (uint32_t)(s * TC_N)), "l"(descA + (uint64_t)(k * 32 >> 4)), "l"(descB + (uint64_t)(k * 32 >> 4)),
+                           "r"(idesc), "r"(accumulate) : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
+            }
+            mbar_wait(smem_u32(&mbar), phase);                            // the MMAs have consumed sA/sB
+            phase ^= 1;
+        }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: thread = TMEM lane = site i0+tid; columns = replicas. Recombine the five digit accumulators exactly.
+    const int i = i0 + tid;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < TC_N; c0 += 16) {
+        long long acc[16];
+#pragma unroll
+        for (int n = 0; n < 16; n++) acc[n] = 0;
+#pragma unroll
+        for (int s = SKQ_SLICES - 1; s >= 0; s--) {
+            uint32_t v[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                         : "r"(lane_base + (uint32_t)(s * TC_N + c0)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int n = 0; n < 16; n++) acc[n] = acc[n] * 256 + (long long)(int32_t)v[n];
+        }
+        if (i < P.N) {
+#pragma unroll
+            for (int n = 0; n < 16; n++) {
+                const int64_t r = r0 + c0 + n;
+                if (r < P.R) {
+                    const double H = (double)acc[n] * P.scale;           // Σ_j J_ij σ_rj
+                    const double si = (double)P.S8[(size_t)r * P.Npad + i];
+                    P.lf[(size_t)r * P.N + i] = 2.0 * si * H;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(TMEM_COLS) : "memory");
+}
+
+// CUDA-core path in the reference's summation order (bit-identical to energy() of SK.jl:218-231)
+__global__ void k_sk_fields_ordered(const double *__restrict__ J, const uint64_t *__restrict__ chunks, int64_t nchunks, int64_t R, int N, double *__restrict__ lf)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= R * N) return;
+    const int64_t r = tid / N; const int i = (int)(tid % N);
+    const uint64_t *s = chunks + r * nchunks;
+    const int si = (int)((s[i >> 6] >> (i & 63)) & 1ull);
+    double a = 0.0;
+    for (int j = 0; j < N; j++) {
+        const int sj = (int)((s[j >> 6] >> (j & 63)) & 1ull);
+        a = __dadd_rn(a, __dmul_rn((double)(1 - 2 * (si ^ sj)), J[(size_t)j * N + i]));
+    }
+    lf[tid] = 2 * a;
+}
+// E_r = -½ Σ_i lf_i / 2 summed in site order (SK.jl:232-236)
+__global__ void k_sk_energy_from_fields(const double *__restrict__ lf, int64_t R, int N, double *__restrict__ E)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    double n = 0.0;
+    for (int i = 0; i < N; i++) n = __dsub_rn(n, lf[r * N + i] / 2);
+    E[r] = n / 2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lock-step Metropolis sweeps: CTA = RPC replicas, their local fields in shared memory
+// ------------------------------------------------------------------------------------------------
+struct sk_ls_params {
+    const double *J; uint64_t *chunks; int64_t nchunks; double *lf; double *E; long long *acc; const double *beta;
+    int N; int64_t R; uint64_t seed, sweep0; int nsweeps;
+};
+template <int RPC>
+__global__ void __launch_bounds__(512, 1) k_sk_lockstep(sk_ls_params P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = P.N, tid = threadIdx.x, nt = blockDim.x;
+    double *lf = reinterpret_cast<double *>(smem_raw);                    // [RPC][N]
+    uint32_t *sp = reinterpret_cast<uint32_t *>(lf + (size_t)RPC * N);     // [RPC][nw]
+    const int nw = (N + 31) / 32;
+    __shared__ int flag[RPC];
+    __shared__ int snew[RPC];
+    const int64_t rbase = (int64_t)blockIdx.x * RPC;
+    for (int rp = 0; rp < RPC; rp++) {
+        const int64_t r = rbase + rp;
+        for (int j = tid; j < N; j += nt) lf[(size_t)rp * N + j] = r < P.R ? P.lf[r * N + j] : 0.0;
+        for (int w = tid; w < nw; w += nt) {
+            const uint64_t c = r < P.R ? P.chunks[r * P.nchunks + (w >> 1)] : 0ull;
+            sp[rp * nw + w] = (uint32_t)(c >> ((w & 1) * 32));
+        }
+    }
+    double E = 0.0, beta = 0.0; long long nacc = 0;
+    if (tid < RPC && rbase + tid < P.R) { E = P.E[rbase + tid]; beta = P.beta[rbase + tid]; nacc = P.acc[rbase + tid]; }
+    __syncthreads();
+    for (int sw = 0; sw < P.nsweeps; sw++) {
+        const uint64_t t = P.sweep0 + (uint64_t)sw;
+        for (int i = 0; i < N; i++) {
+            if (tid < RPC) {                                   // Metropolis decision, accept() of RRRMC.jl:39
+                const int64_t r = rbase + tid;
+                int ok = 0;
+                if (r < P.R) {
+                    const double dE = lf[(size_t)tid * N + i];                      // ΔE_i = +lfields[i], SK.jl:278-284
+                    const double x = -beta * dE;
+                    if (x >= 0) ok = 1;
+                    else {
+                        const philox_out u = philox4x32_10((uint32_t)i, (uint32_t)r, (uint32_t)t, (uint32_t)(t >> 32) ^ 0x534b4c53u,
+                                                           (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+                        const double U = (double)((((uint64_t)u.y << 32) | u.x) >> 11) * 0x1.0p-53;
+                        ok = U < exp(x);
+                    }
+                    if (ok) { E += dE; nacc++; }
+                }
+                flag[tid] = ok;
+                snew[tid] = 1 ^ (int)((sp[tid * nw + (i >> 5)] >> (i & 31)) & 1u);
+            }
+            __syncthreads();
+            bool any = false;
+#pragma unroll
+            for (int rp = 0; rp < RPC; rp++) any |= flag[rp] != 0;
+            if (any) {                                         // update_cache!, SK.jl:252-265, for the accepted replicas
+                const double *Ji = P.J + (size_t)i * N;
+                for (int j = tid; j < N; j += nt) {
+                    const double Jij = Ji[j];
+#pragma unroll
+                    for (int rp = 0; rp < RPC; rp++) {
+                        if (!flag[rp]) continue;
+                        const int sj = (int)((sp[rp * nw + (j >> 5)] >> (j & 31)) & 1u);
+                        double *p = &lf[(size_t)rp * N + j];
+                        if (j == i) *p = -*p;
+                        else *p = __dadd_rn(*p, 4 * __dmul_rn((double)(1 - 2 * (snew[rp] ^ sj)), Jij));
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid < RPC && flag[tid]) sp[tid * nw + (i >> 5)] ^= 1u << (i & 31);
+        }
+    }
+    __syncthreads();
+    for (int rp = 0; rp < RPC; rp++) {
+        const int64_t r = rbase + rp;
+        if (r >= P.R) continue;
+        for (int j = tid; j < N; j += nt) P.lf[r * N + j] = lf[(size_t)rp * N + j];
+        for (int c = tid; c < (int)P.nchunks; c += nt) {
+            const uint64_t lo = sp[rp * nw + 2 * c], hi = 2 * c + 1 < nw ? sp[rp * nw + 2 * c + 1] : 0u;
+            P.chunks[r * P.nchunks + c] = lo | (hi << 32);
+        }
+    }
+    if (tid < RPC && rbase + tid < P.R) { P.E[rbase + tid] = E; P.acc[rbase + tid] = nacc; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct sk_dense_store {
+    double *lf = nullptr, *E = nullptr, *beta = nullptr; long long *acc = nullptr;
+    int8_t *Jq = nullptr, *S8 = nullptr; int Npad = 0; int64_t Rpad = 0; double scale = 0; int P = 0;
+    bool fields_valid = false;
+};
+
+void sk_dense_free(rrrmc_state *s)
+{
+    sk_dense_store *d = s->skd;
+    if (!d) return;
+    cudaFree(d->lf); cudaFree(d->E); cudaFree(d->beta); cudaFree(d->acc); cudaFree(d->Jq); cudaFree(d->S8);
+    delete d;
+    s->skd = nullptr;
+}
+void sk_dense_invalidate(rrrmc_state *s) { if (s->skd) s->skd->fields_valid = false; }
+
+static rrrmc_status_t sk_dense_ensure(rrrmc_state *s)
+{
+    rrrmc_graph *g = s->g;
+    if (g->kind != RRRMC_SK_F64) { rrrmc_set_error("the dense SK kernels need a GraphSKNormal (RRRMC_SK_F64) graph"); return RRRMC_ERR_UNSUPPORTED; }
+    if (!s->skd) {
+        sk_dense_store *d = new sk_dense_store();
+        s->skd = d;
+        RR_CUDA(cudaMalloc(&d->lf, sizeof(double) * s->R * g->N));
+        RR_CUDA(cudaMalloc(&d->E, sizeof(double) * s->R));
+        RR_CUDA(cudaMalloc(&d->beta, sizeof(double) * s->R));
+        RR_CUDA(cudaMalloc(&d->acc, sizeof(long long) * s->R));
+        RR_CUDA(cudaMemsetAsync(d->acc, 0, sizeof(long long) * s->R, g->ctx->stream));
+    }
+    return RRRMC_OK;
+}
+// quantise J once: J ≈ 2^-P Σ_s d_s 256^s with signed 8-bit digits d_s (balanced, so that Σ is exact in 40 bits)
+static rrrmc_status_t sk_dense_quantise(rrrmc_state *s, const std::vector<double> &J)
+{
+    rrrmc_graph *g = s->g; sk_dense_store *d = s->skd;
+    if (d->Jq) return RRRMC_OK;
+    const int64_t N = g->N;
+    d->Npad = (int)(((N + TC_M - 1) / TC_M) * TC_M);
+    d->Rpad = ((s->R + TC_N - 1) / TC_N) * TC_N;
+    double mx = 0;
+    for (double v : J) mx = std::max(mx, std::fabs(v));
+    int e = 0; if (mx > 0) frexp(mx, &e);                 // mx < 2^e
+    d->P = 38 - e; d->scale = ldexp(1.0, -d->P);           // |J·2^P| < 2^38: digits fit five signed bytes
+    std::vector<int8_t> q((size_t)SKQ_SLICES * d->Npad * d->Npad, 0);
+    for (int64_t i = 0; i < N; i++)
+        for (int64_t j = 0; j < N; j++) {
+            long long v = llrint(ldexp(J[i * N + j], d->P));
+            for (int sl = 0; sl < SKQ_SLICES; sl++) {
+                const long long dg = ((v + 128) & 255) - 128;  // balanced digit in [-128, 127]
+                q[((size_t)sl * d->Npad + i) * d->Npad + j] = (int8_t)dg;
+                v = (v - dg) / 256;
+            }
+        }
+    RR_CUDA(cudaMalloc(&d->Jq, q.size()));
+    RR_CUDA(cudaMemcpy(d->Jq, q.data(), q.size(), cudaMemcpyHostToDevice));
+    RR_CUDA(cudaMalloc(&d->S8, (size_t)d->Rpad * d->Npad));
+    RR_CUDA(cudaMemset(d->S8, 0, (size_t)d->Rpad * d->Npad));
+    return RRRMC_OK;
+}
+
+rrrmc_status_t sk_dense_fields_init(rrrmc_state *s, int use_tensor_cores, double *E_out, float *ms_out)
+{
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    RR_TRY(sk_dense_ensure(s));
+    RR_TRY(chain_sync_from_multispin(s));
+    sk_dense_store *d = s->skd;
+    const int N = (int)g->N;
+    cudaEvent_t e0, e1;
+    RR_CUDA(cudaEventCreate(&e0)); RR_CUDA(cudaEventCreate(&e1));
+    if (use_tensor_cores) {
+        RR_TRY(sk_dense_quantise(s, g->Jd));
+        RR_CUDA(cudaEventRecord(e0, ctx->stream));
+        k_spins_to_s8<<<div_up(s->R * d->Npad, 256), 256, 0, ctx->stream>>>(s->d_chunks, s->nchunks, s->R, N, d->Npad, d->S8);
+        sk_tc_params P{ d->Jq, d->S8, d->lf, N, d->Npad, s->R, d->Rpad, d->scale };
+        dim3 grid(d->Npad / TC_M, (unsigned)(d->Rpad / TC_N));
+        k_sk_fields_tc<<<grid, 128, 0, ctx->stream>>>(P);
+        ctx->launches += 2;
+    } else {
+        RR_CUDA(cudaEventRecord(e0, ctx->stream));
+        k_sk_fields_ordered<<<div_up(s->R * N, 128), 128, 0, ctx->stream>>>(g->d_Jd, s->d_chunks, s->nchunks, s->R, N, d->lf);
+        ctx->launches++;
+    }
+    RR_CUDA(cudaEventRecord(e1, ctx->stream));
+    k_sk_energy_from_fields<<<div_up(s->R, 64), 64, 0, ctx->stream>>>(d->lf, s->R, N, d->E);
+    ctx->launches++;
+    RR_CUDA(cudaGetLastError());
+    if (E_out) RR_CUDA(cudaMemcpyAsync(E_out, d->E, sizeof(double) * s->R, cudaMemcpyDeviceToHost, ctx->stream));
+    RR_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ms_out) RR_CUDA(cudaEventElapsedTime(ms_out, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    d->fields_valid = true;
+    return RRRMC_OK;
+}
+rrrmc_status_t sk_dense_get_fields(rrrmc_state *s, double *lf_out)
+{
+    RR_ARG(s->skd && s->skd->fields_valid, "local fields are not initialised: call rrrmc_sk_fields_init first");
+    RR_CUDA(cudaMemcpy(lf_out, s->skd->lf, sizeof(double) * s->R * s->g->N, cudaMemcpyDeviceToHost));
+    return RRRMC_OK;
+}
+
+rrrmc_status_t sk_dense_sweeps(rrrmc_state *s, const double *beta, uint64_t seed, uint64_t sweep0, int64_t nsweeps,
+                               double *E_out, int64_t *acc_out)
+{
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    RR_TRY(sk_dense_ensure(s));
+    sk_dense_store *d = s->skd;
+    if (!d->fields_valid) RR_TRY(sk_dense_fields_init(s, 1, nullptr, nullptr));
+    RR_TRY(chain_sync_from_multispin(s));
+    for (int64_t r = 0; r < s->R; r++) RR_ARG(std::isfinite(beta[r]), "β must be finite, given: %g", beta[r]);
+    RR_CUDA(cudaMemcpyAsync(d->beta, beta, sizeof(double) * s->R, cudaMemcpyHostToDevice, ctx->stream));
+    const int N = (int)g->N, nw = (N + 31) / 32;
+    sk_ls_params P{ g->d_Jd, s->d_chunks, s->nchunks, d->lf, d->E, d->acc, d->beta, N, s->R, seed, sweep0, (int)nsweeps };
+    int rpc = 4;
+    while (rpc > 1 && (size_t)rpc * N * 8 + (size_t)rpc * nw * 4 > (size_t)200 * 1024) rpc >>= 1;
+    const size_t smem = (size_t)rpc * N * 8 + (size_t)rpc * nw * 4;
+    RR_ARG(smem <= (size_t)220 * 1024, "N = %d is too large for the lock-step SK kernel (local fields must fit shared memory)", N);
+    const unsigned grid = div_up(s->R, rpc);
+#define LS(RP) do { RR_CUDA(cudaFuncSetAttribute(k_sk_lockstep<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                    k_sk_lockstep<RP><<<grid, 512, smem, ctx->stream>>>(P); } while (0)
+    if (rpc == 4) LS(4); else if (rpc == 2) LS(2); else LS(1);
+#undef LS
+    ctx->launches++;
+    RR_CUDA(cudaGetLastError());
+    s->ms_valid = false; s->chain_valid = true; s->chain_fields_valid = false; s->energy_valid = false;
+    if (E_out) RR_CUDA(cudaMemcpyAsync(E_out, d->E, sizeof(double) * s->R, cudaMemcpyDeviceToHost, ctx->stream));
+    if (acc_out) RR_CUDA(cudaMemcpyAsync(acc_out, d->acc, sizeof(long long) * s->R, cudaMemcpyDeviceToHost, ctx->stream));
+    RR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RRRMC_OK;
+}

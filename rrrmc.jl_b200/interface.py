@@ -421,6 +421,31 @@ def overlaps(X, Cfg=None):
     return _observable(lib().rrrmc_overlaps, X, Cfg, X.M // 2)
 
 
+def sk_fields_init(X, Cfg=None, tensor_cores=True):
+    """Local fields of the whole batch, lfields[r][i] = 2σ_ri Σ_j J_ij σ_rj — the contraction inside energy(X, C) of
+    SK.jl:212-237 — on the tensor cores (exact INT8 digit-plane GEMMs) or on CUDA cores in the reference's
+    summation order. -> (lfields (R, N), E (R,), device_ms)"""
+    if Cfg is not None:
+        X._upload(Cfg)
+    E = np.zeros(X.replicas, np.float64); ms = C.c_float()
+    check(lib().rrrmc_sk_fields_init(X._ensure_state(), int(bool(tensor_cores)), ptr(E), C.byref(ms)))
+    lf = np.zeros((X.replicas, X.N), np.float64)
+    check(lib().rrrmc_sk_get_fields(X._state, ptr(lf)))
+    return lf, E, ms.value
+
+
+def sk_metropolis_sweeps(X, β, nsweeps, *, seed=DEFAULT_SEED, sweep0=0, C0=None):
+    """Lock-step Metropolis sweeps on a GraphSKNormal batch (sites 1..N in order, all replicas together).
+    -> (E (R,), accepted (R,), C)"""
+    st = X._ensure_state()
+    if C0 is not None:
+        X._upload(C0)
+    betas = np.ascontiguousarray(np.broadcast_to(np.asarray(β, np.float64), (X.replicas,)))
+    E = np.zeros(X.replicas, np.float64); acc = np.zeros(X.replicas, np.int64)
+    check(lib().rrrmc_sk_metropolis_sweeps(st, ptr(betas), int(seed), int(sweep0), int(nsweeps), ptr(E), ptr(acc)))
+    return E, acc, X._download()
+
+
 # ----------------------------------------------------------------------------------------------------
 class _LazyConfig:
     """The `C` a hook sees: downloads the batch from the device on first access."""
