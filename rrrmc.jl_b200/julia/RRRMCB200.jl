@@ -1,0 +1,180 @@
+# RRRMCB200.jl — the Julia host side of the B200 engine: RRRMC.jl's calling convention on top of the C ABI of
+# include/rrrmc_b200.h (librrrmc_b200.so), bound with `ccall`. No CUDA.jl, no CPU fallback.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image and the GPU box have no `julia` binary; the same symbols are
+# driven from Python (rrrmc.jl_b200/interface.py) by the tests. This file is kept declarative and thin so that a
+# maintainer can check it against the header line by line (INTEGRATION.md walks through it).
+#
+# Usage (mirrors src/RRRMC.jl:81-88, 149-157, 311-317 and src/Interface.jl:87-270):
+#     using RRRMCB200
+#     X = RRRMCB200.GraphEA(64, 3; replicas=1024)          # GraphEA{Int,(-1,1),6} on a replica batch
+#     Es, C = standardMC(X, 1.0, 10^3 * X.N; step = 10 * X.N)
+module RRRMCB200
+
+export standardMC, rrrMC, bklMC
+
+const lib = get(ENV, "RRRMC_B200_LIB", joinpath(@__DIR__, "..", "lib", "librrrmc_b200.so"))
+
+const RRRMC_OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = Cint(0), Cint(-1), Cint(-2), Cint(-3), Cint(-4)
+const EA_PM1, EA_INT, EA_F64, SK_F64, SK_BIN, QT, QUANT, EMPTY = Cint.(1:8)
+
+last_error() = unsafe_string(ccall((:rrrmc_last_error, lib), Cstring, ()))
+function check(st::Cint)
+    st == RRRMC_OK && return
+    msg = last_error()
+    st == ERR_ARG && throw(ArgumentError(msg))          # the reference throws ArgumentError (e.g. RRRMC.jl:94,159)
+    throw(ErrorException("rrrmc_b200 [$st]: $msg"))
+end
+
+# ---- context ------------------------------------------------------------------------------------
+mutable struct Context
+    h::Ptr{Cvoid}
+    function Context(device::Integer = 0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:rrrmc_ctx_create, lib), Cint, (Cint, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), device, C_NULL, r))
+        c = new(r[]); finalizer(c -> ccall((:rrrmc_ctx_destroy, lib), Cint, (Ptr{Cvoid},), c.h), c); c
+    end
+end
+const default_ctx = Ref{Union{Nothing,Context}}(nothing)
+ctx() = (default_ctx[] === nothing && (default_ctx[] = Context()); default_ctx[])
+
+# ---- Config (src/Interface.jl:21-54) for a batch: chunks[:, r] is replica r's BitVector chunk array ----------
+struct Config
+    N::Int
+    chunks::Matrix{UInt64}      # (cld(N,64), R), column r = BitVector(s).chunks of replica r
+end
+Config(N::Integer, R::Integer = 1) = Config(N, zeros(UInt64, cld(N, 64), R))
+Base.BitVector(C::Config, r::Integer = 1) = (b = BitVector(undef, C.N); b.chunks .= view(C.chunks, :, r); b)
+
+# ---- graphs ---------------------------------------------------------------------------------------
+abstract type AbstractGraph{ET<:Real} end          # src/Interface.jl:66
+mutable struct Graph{ET} <: AbstractGraph{ET}
+    h::Ptr{Cvoid}; state::Ptr{Cvoid}; N::Int; replicas::Int; kind::Cint
+end
+function _finish(h::Ptr{Cvoid}, ET, replicas, kind)
+    n = Ref{Int64}(0); check(ccall((:rrrmc_getN, lib), Cint, (Ptr{Cvoid}, Ref{Int64}), h, n))
+    s = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:rrrmc_state_create, lib), Cint, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), h, replicas, s))
+    X = Graph{ET}(h, s[], n[], replicas, kind)
+    finalizer(X) do x
+        ccall((:rrrmc_state_destroy, lib), Cint, (Ptr{Cvoid},), x.state)
+        ccall((:rrrmc_graph_destroy, lib), Cint, (Ptr{Cvoid},), x.h)
+    end
+    X
+end
+getN(X::Graph) = X.N                                  # Interface.jl:145
+
+"GraphEA{ET,LEV,twoD}(A, J) (src/graphs/EA.jl:145-168) / GraphEANormal (EA.jl:540-552): A, J as N×2D matrices (row-major copy)."
+function GraphEA(L::Integer, D::Integer, A::Matrix{Int64}, J::Matrix; replicas::Integer = 1)
+    kind = eltype(J) <: AbstractFloat ? EA_F64 : (all(abs.(J) .== 1) ? EA_PM1 : EA_INT)
+    Jc = eltype(J) <: AbstractFloat ? Matrix{Float64}(permutedims(J)) : Matrix{Int64}(permutedims(J))
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:rrrmc_graph_ea_create, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+                ctx().h, L, D, kind, permutedims(A), Jc, r))
+    _finish(r[], kind == EA_F64 ? Float64 : Int, replicas, kind)
+end
+"GraphEA(L, D) with ±1 couplings drawn here (src/graphs/EA.jl:181-191)."
+function GraphEA(L::Integer, D::Integer; replicas::Integer = 1)
+    N = L^D
+    A = Matrix{Int64}(undef, 2D, N)
+    check(ccall((:rrrmc_gen_ea_adjacency, lib), Cint, (Cint, Cint, Ptr{Int64}), L, D, A))
+    A = permutedims(A); J = zeros(Int64, N, 2D)
+    for x = 1:N, k = 1:2D                                  # gen_J, EA.jl:45-71
+        y = A[x, k]; x < y || continue
+        J[x, k] = rand((-1, 1)); l = findfirst(==(0), view(J, y, :)); J[y, l] = J[x, k]
+    end
+    GraphEA(L, D, A, J; replicas = replicas)
+end
+"GraphSKNormal(N) / GraphSK(N) with explicit couplings (src/graphs/SK.jl:181-199 / :28-49)."
+function GraphSK(J::Matrix; replicas::Integer = 1)
+    N = size(J, 1); kind = eltype(J) <: AbstractFloat ? SK_F64 : SK_BIN
+    Jc = kind == SK_F64 ? Matrix{Float64}(J) : Matrix{UInt8}(J)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:rrrmc_graph_sk_create, lib), Cint, (Ptr{Cvoid}, Int64, Cint, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), ctx().h, N, kind, Jc, r))
+    _finish(r[], Float64, replicas, kind)
+end
+"GraphQuant(Nk, M, Γ, β, inner, J) (src/graphs/QT.jl:163-170): inner = SK_BIN (GraphQSKT), SK_F64 (GraphQSKNormalT), EMPTY (GraphQ0T)."
+function GraphQuant(Nk::Integer, M::Integer, Γ::Real, β::Real, inner::Cint, J = nothing; replicas::Integer = 1)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    Jp = J === nothing ? C_NULL : pointer(J)
+    GC.@preserve J check(ccall((:rrrmc_graph_quant_create, lib), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Cdouble, Cdouble, Cint, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), ctx().h, Nk, M, Γ, β, inner, Jp, r))
+    _finish(r[], Float64, replicas, QUANT)
+end
+
+# ---- Interface (src/Interface.jl:87-270) on the batch ------------------------------------------------
+upload!(X::Graph, C::Config) = (C.N == X.N || throw(ArgumentError("Invalid C0, wrong N, expected $(X.N), given: $(C.N)"));
+    check(ccall((:rrrmc_state_upload, lib), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{UInt64}), X.state, 0, X.replicas, C.chunks)))
+function download(X::Graph)
+    C = Config(X.N, X.replicas)
+    check(ccall((:rrrmc_state_download, lib), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{UInt64}), X.state, 0, X.replicas, C.chunks)); C
+end
+function energy(X::Graph, C::Config)                    # Interface.jl:105 — also resets the caches
+    upload!(X, C); E = zeros(X.replicas)
+    check(ccall((:rrrmc_energy, lib), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), X.state, E)); E
+end
+function delta_energy(X::Graph, C::Config, move::Integer) # Interface.jl:130
+    upload!(X, C); dE = zeros(X.replicas)
+    check(ccall((:rrrmc_delta_energy, lib), Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}), X.state, move, dE)); dE
+end
+function delta_energy_residual(X::Graph, C::Config, move::Integer) # Interface.jl:254-261
+    upload!(X, C); dE = zeros(X.replicas)
+    check(ccall((:rrrmc_delta_energy_residual, lib), Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}), X.state, move, dE)); dE
+end
+function neighbors(X::Graph, i::Integer)                # Interface.jl:158
+    m = Ref{Int64}(0); check(ccall((:rrrmc_max_neighbors, lib), Cint, (Ptr{Cvoid}, Ref{Int64}), X.h, m))
+    out = zeros(Int64, max(m[], 1)); n = Ref{Cint}(0)
+    check(ccall((:rrrmc_neighbors, lib), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ref{Cint}), X.h, i, out, n)); out[1:n[]]
+end
+function allΔE(X::Graph)                                # Interface.jl:200-201
+    out = zeros(64); n = Ref{Cint}(0)
+    check(ccall((:rrrmc_allDE, lib), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ref{Cint}), X.h, out, n)); Tuple(out[1:n[]])
+end
+"spinflip!(X, C, move) = flip + update_cache! (Interface.jl:89-92) on every replica of the batch."
+function spinflip!(X::Graph, C::Config, move::Integer)
+    upload!(X, C)
+    check(ccall((:rrrmc_spinflip, lib), Cint, (Ptr{Cvoid}, Int64, Ptr{UInt32}), X.state, move, C_NULL))
+    C.chunks .= download(X).chunks; C
+end
+update_cache!(X::Graph, C::Config, move::Integer) = nothing  # the device caches are rebuilt lazily from the configuration
+
+# ---- samplers (src/RRRMC.jl:81-127, 149-290, 311-359) ---------------------------------------------------
+struct Opts
+    schedule::Cint; planes_K::Cint; count_accepted::Cint; staged_thr::Cdouble; staged_thr_fact::Cdouble
+    planes_M::Cint; reserved::NTuple{7,Cint}
+end
+struct RunInfo
+    nsamples::Int64; iters_done::Int64; launches::Int64; device_ms::Cfloat; accepted_total::Int64
+end
+# hook(it, X, C, accepted, E)::Bool of RRRMC.jl:61-64 arrives through a C callback; `user` carries the closure
+function _hook_tramp(user::Ptr{Cvoid}, it::Int64, E::Ptr{Cdouble}, acc::Ptr{Int64}, R::Int64)::Cint
+    f, X = unsafe_pointer_to_objref(user)::Tuple{Function,Graph}
+    Cint(f(it, X, download(X), unsafe_wrap(Array, acc, R), unsafe_wrap(Array, E, R)) ? 1 : 0)
+end
+function _run(sym::Symbol, X::Graph, β, iters::Integer; seed = 167432777111, step::Integer = 1, hook = (x...) -> true,
+              C0::Union{Config,Nothing} = nothing, quiet::Bool = false, staged_thr::Real = NaN, staged_thr_fact::Real = 5.0,
+              schedule::Integer = 0)
+    isfinite(β) || throw(ArgumentError("β must be finite, given: $β"))                    # RRRMC.jl:159
+    C0 === nothing ? check(ccall((:rrrmc_state_randomize, lib), Cint, (Ptr{Cvoid}, UInt64), X.state, seed > 0 ? seed : rand(UInt64))) :
+                     upload!(X, C0)
+    o = Ref{Opts}(); check(ccall((:rrrmc_opts_default, lib), Cint, (Ref{Opts},), o))
+    o[] = Opts(schedule, o[].planes_K, o[].count_accepted, staged_thr, staged_thr_fact, o[].planes_M, o[].reserved)
+    cap = min(10^8, iters ÷ step)                                                          # RRRMC.jl:90
+    Es = zeros(X.replicas, max(cap, 1)); info = Ref{RunInfo}()
+    betas = fill(Float64(β), X.replicas)
+    ud = Ref((hook, X)); cb = @cfunction(_hook_tramp, Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Int64}, Int64))
+    GC.@preserve ud check(ccall((sym, lib), Cint,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Int64, UInt64, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Opts}, Ptr{Cdouble}, Int64, Ref{RunInfo}),
+        X.state, betas, iters, step, seed > 0 ? seed : 0, cb, pointer_from_objref(ud), o, Es, cap, info))
+    quiet || (println("samples = ", info[].nsamples); println("iters = ", info[].iters_done))
+    Es[:, 1:info[].nsamples], download(X)
+end
+"standardMC(X, β, iters; seed, step, hook, C0, quiet) (src/RRRMC.jl:81-127); schedule=0 checkerboard sweeps, 1 the reference's rand(1:N) order."
+standardMC(X::Graph, β::Real, iters::Integer; schedule::Integer = (X.kind == EA_PM1 ? 0 : 1), kw...) =
+    _run(:rrrmc_standard_mc, X, β, iters; schedule = schedule, kw...)
+"rrrMC(X, β, iters; seed, step, hook, C0, staged_thr, staged_thr_fact, quiet) (src/RRRMC.jl:149-290)"
+rrrMC(X::Graph, β::Real, iters::Integer; kw...) = _run(:rrrmc_rrr_mc, X, β, iters; kw...)
+"bklMC(X, β, iters; seed, step, hook, C0, quiet) (src/RRRMC.jl:311-359)"
+bklMC(X::Graph, β::Real, iters::Integer; kw...) = _run(:rrrmc_bkl_mc, X, β, iters; kw...)
+
+end # module

@@ -1,0 +1,148 @@
+"""Multi-GPU host logic: replicas are independent chains on a shared read-only instance, so the replica axis is
+sharded across ranks (one process per GPU) with no data-path collective. torch.distributed (NCCL on GPUs, gloo in the
+CPU tests) is used only for what the path really exchanges: the per-replica observables behind `hook`, and the
+energies that drive parallel-tempering swaps. Swaps exchange β *labels* — every rank evaluates identical decisions
+from the all-gathered energies and a shared counter-based RNG — so no spin data ever crosses NVLink.
+
+The reference has no multi-replica or multi-process path; this module is new-engine plumbing."""
+import numpy as np
+
+ALIGN = 128  # one 128-bit multispin load serves 128 replicas: shards are multiples of it
+
+
+def replica_range(rank, world, total, align=ALIGN):
+    """Contiguous [lo, hi) of the `total` replicas owned by `rank`; every boundary is a multiple of `align`
+    (the remainder goes to the last ranks one block at a time)."""
+    if total % align:
+        raise ValueError(f"total replicas {total} must be a multiple of {align}")
+    blocks = total // align
+    base, rem = divmod(blocks, world)
+    counts = [base + (1 if r >= world - rem else 0) for r in range(world)]
+    lo = sum(counts[:rank]) * align
+    return lo, lo + counts[rank] * align
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        return dist if dist.is_available() and dist.is_initialized() else None
+    except Exception:
+        return None
+
+
+def all_gather(x_local, device=None):
+    """All-gather of a per-replica observable (E, m, accepted ...): (R_local, ...) -> (R_total, ...), rank order.
+    Shards may differ in size (padded to the largest for the collective). Without an initialised process group it is
+    the identity."""
+    x_local = np.ascontiguousarray(x_local)
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return x_local
+    import torch
+    world = dist.get_world_size()
+    dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    n = torch.tensor([x_local.shape[0]], dtype=torch.int64, device=dev)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n)
+    ns = [int(v.item()) for v in ns]
+    nmax = max(ns)
+    pad = np.zeros((nmax,) + x_local.shape[1:], x_local.dtype)
+    pad[:x_local.shape[0]] = x_local
+    t = torch.from_numpy(pad).to(dev)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return np.concatenate([o.cpu().numpy()[:k] for o, k in zip(out, ns)], axis=0)
+
+
+def classical_action(beta, E):
+    """β·E: the weight exponent of a classical graph (GraphEA, GraphSK...)."""
+    return beta * E
+
+
+def quantum_action(M, Gamma):
+    """β-dependent action of GraphQuant (QT.jl:163-199): E_β(s) = K(β)·e0(s) + E_cl(s)/M with
+    K(β) = fourK(β)/4, fourK = round(2/β·log coth(βΓ/M), digits=8) (QT.jl:165). `terms` = (e0, E_cl_sum)."""
+    def fourK(beta):
+        return np.round(2.0 / beta * np.log(1.0 / np.tanh(beta * Gamma / M)), 8)
+
+    def action(beta, terms):
+        e0, ecl = terms
+        return beta * (fourK(beta) / 4.0 * e0 + ecl / M)
+    return action
+
+
+class TemperingLadder:
+    """Parallel tempering by label exchange. `order[k]` is the replica currently holding the k-th inverse
+    temperature of `betas` (ascending ladder). Every rank owns an identical copy and updates it identically."""
+
+    def __init__(self, betas, seed=0, action=classical_action):
+        self.betas = np.asarray(betas, np.float64)
+        self.order = np.arange(len(self.betas))
+        self.seed, self.action = int(seed), action
+        self.attempts = np.zeros(len(self.betas) - 1, np.int64)
+        self.accepts = np.zeros(len(self.betas) - 1, np.int64)
+
+    def beta_of_replica(self):
+        b = np.empty_like(self.betas)
+        b[self.order] = self.betas
+        return b
+
+    def swap(self, terms, sweep):
+        """One round of neighbour swaps (pairs (k, k+1) with k ≡ sweep mod 2). `terms`: per-replica energy terms in
+        replica order — an array E, or a tuple of arrays for a β-dependent action — already all-gathered.
+        Acceptance min(1, exp(-ΔS)), ΔS = [S(β_k, x_b) + S(β_{k+1}, x_a)] − [S(β_k, x_a) + S(β_{k+1}, x_b)]."""
+        tup = terms if isinstance(terms, tuple) else (np.asarray(terms, np.float64),)
+        rng = np.random.Generator(np.random.Philox(key=self.seed, counter=[int(sweep), 0, 0, 0]))
+        u = rng.random(len(self.betas))
+        for k in range(int(sweep) % 2, len(self.betas) - 1, 2):
+            a, b = self.order[k], self.order[k + 1]
+            xa = tuple(t[a] for t in tup); xb = tuple(t[b] for t in tup)
+            if not isinstance(terms, tuple):
+                xa, xb = xa[0], xb[0]
+            dS = (self.action(self.betas[k], xb) + self.action(self.betas[k + 1], xa)) - \
+                 (self.action(self.betas[k], xa) + self.action(self.betas[k + 1], xb))
+            self.attempts[k] += 1
+            if dS <= 0 or u[k] < np.exp(-dS):
+                self.order[k], self.order[k + 1] = b, a
+                self.accepts[k] += 1
+        return self.beta_of_replica()
+
+
+class ReplicaShard:
+    """This rank's slice of a replica batch of `total` chains."""
+
+    def __init__(self, total, rank=None, world=None, align=ALIGN):
+        dist = _dist()
+        self.rank = rank if rank is not None else (dist.get_rank() if dist else 0)
+        self.world = world if world is not None else (dist.get_world_size() if dist else 1)
+        self.total = total
+        self.lo, self.hi = replica_range(self.rank, self.world, total, align)
+
+    @property
+    def count(self):
+        return self.hi - self.lo
+
+    def local(self, x_global):
+        return np.asarray(x_global)[self.lo:self.hi]
+
+
+def tempered_run(X, ladder, shard, rounds, iters_per_round, sampler, *, seed=1, C0=None, terms_fn=None, **kw):
+    """Runs `sampler(X, β_local, iters_per_round, ...)` on this rank's batch for `rounds` rounds with a label swap
+    after each: energies are all-gathered, every rank applies the same swaps, the local β vector is refreshed.
+    -> (E_history (rounds, R_total), final Config of the local batch)."""
+    C = C0
+    hist = []
+    for rd in range(rounds):
+        beta_local = shard.local(ladder.beta_of_replica())
+        Es, C = sampler(X, beta_local, iters_per_round, step=iters_per_round, seed=seed + 7919 * rd, C0=C, quiet=True, **kw)
+        E_local = np.asarray(Es[-1], np.float64).reshape(-1)
+        if terms_fn is None:
+            E_all = all_gather(E_local)
+            ladder.swap(E_all, rd)
+            hist.append(E_all)
+        else:
+            t_local = terms_fn(X, C)
+            t_all = tuple(all_gather(t) for t in t_local)
+            ladder.swap(t_all, rd)
+            hist.append(all_gather(E_local))
+    return np.array(hist), C
