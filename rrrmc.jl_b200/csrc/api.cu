@@ -236,6 +236,7 @@ extern "C" rrrmc_status_t rrrmc_graph_ea_create(rrrmc_ctx_t *ctx, int L, int D, 
         RR_CUDA(cudaMalloc(&g->d_jcode, N));
         RR_CUDA(cudaMemcpy(g->d_jcode, jc.data(), N, cudaMemcpyHostToDevice));
     }
+    RR_CUDA(cudaDeviceSynchronize()); // default-stream uploads are complete before any non-blocking stream uses them
     *out = g;
     return RRRMC_OK;
 }
@@ -282,6 +283,7 @@ extern "C" rrrmc_status_t rrrmc_graph_sk_create(rrrmc_ctx_t *ctx, int64_t N, int
     RR_CUDA(cudaSetDevice(ctx->device));
     rrrmc_status_t st = upload_sk_couplings(g, N, kind, J);
     if (st != RRRMC_OK) { delete g; return st; }
+    RR_CUDA(cudaDeviceSynchronize()); // default-stream uploads are complete before any non-blocking stream uses them
     *out = g;
     return RRRMC_OK;
 }
@@ -295,6 +297,7 @@ extern "C" rrrmc_status_t rrrmc_graph_qt_create(rrrmc_ctx_t *ctx, int64_t N, int
     rrrmc_graph *g = new rrrmc_graph();
     g->ctx = ctx; g->kind = RRRMC_QT; g->N = N; g->M = M; g->Nk = N / M; g->fourK = fourK; g->max_deg = 2;
     g->allDE = { 0.0, fourK };                                                                 // QT.jl:111
+    RR_CUDA(cudaDeviceSynchronize()); // default-stream uploads are complete before any non-blocking stream uses them
     *out = g;
     return RRRMC_OK;
 }
@@ -320,6 +323,7 @@ extern "C" rrrmc_status_t rrrmc_graph_quant_create(rrrmc_ctx_t *ctx, int64_t Nk,
         rrrmc_status_t st = upload_sk_couplings(g, Nk, inner, J_inner);
         if (st != RRRMC_OK) { delete g; return st; }
     }
+    RR_CUDA(cudaDeviceSynchronize()); // default-stream uploads are complete before any non-blocking stream uses them
     *out = g;
     return RRRMC_OK;
 }

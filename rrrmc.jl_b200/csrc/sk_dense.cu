@@ -338,8 +338,9 @@ static rrrmc_status_t sk_dense_quantise(rrrmc_state *s, const std::vector<double
         }
     RR_CUDA(cudaMalloc(&d->Jq, q.size()));
     RR_CUDA(cudaMemcpy(d->Jq, q.data(), q.size(), cudaMemcpyHostToDevice));
+    RR_CUDA(cudaDeviceSynchronize());
     RR_CUDA(cudaMalloc(&d->S8, (size_t)d->Rpad * d->Npad));
-    RR_CUDA(cudaMemset(d->S8, 0, (size_t)d->Rpad * d->Npad));
+    RR_CUDA(cudaMemsetAsync(d->S8, 0, (size_t)d->Rpad * d->Npad, s->g->ctx->stream)); // on the context stream: ordered before k_spins_to_s8
     return RRRMC_OK;
 }
 

@@ -539,7 +539,7 @@ def standardMC(X, β, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, q
 def rrrMC(X, β, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, staged_thr=float("nan"),
           staged_thr_fact=5.0, quiet=False):
     """rrrMC(X, β, iters; ...) (src/RRRMC.jl:149-219)."""
-    if not math.isfinite(β):
+    if not np.all(np.isfinite(β)):
         raise ValueError(f"β must be finite, given: {β}")  # RRRMC.jl:159
     return _run(lib().rrrmc_rrr_mc, X, β, iters, seed, step, hook, C0, quiet,
                 _opts(staged_thr=staged_thr, staged_thr_fact=staged_thr_fact), "rrrMC")
