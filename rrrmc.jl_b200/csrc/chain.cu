@@ -117,21 +117,46 @@ __device__ __forceinline__ void sk_update_part(const gview &c, int skind, int k,
 {
     const int64_t cur = sk_cur_off(c, k), last = sk_last_off(c, k);
     const int64_t off = (int64_t)k * c.Nk;
+    constexpr int UB = 8; // loads of UB sites are issued together: the loop is bound by memory latency, not arithmetic
     if (skind == RRRMC_SK_F64) {
         const double *Ji = c.Jd + (int64_t)i * c.Nk;
-        for (int j = lane; j < c.Nk; j += nl) {
-            const double Js = __dmul_rn((double)(1 - 2 * (si ^ sget(c.s, (int)(off + j)))), Ji[j]);
-            const double lfj = c.lfd[cur + j];
-            c.lfd[last + j] = lfj;
-            c.lfd[cur + j] = __dadd_rn(lfj, 4 * Js);
+        double *lf = c.lfd + cur, *lfl = c.lfd + last;
+        for (int j0 = lane; j0 < c.Nk; j0 += nl * UB) {
+            double Jv[UB], lv[UB]; int sv[UB];
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+                const int j = j0 + u * nl;
+                if (j < c.Nk) { Jv[u] = Ji[j]; lv[u] = lf[j]; sv[u] = sget(c.s, (int)(off + j)); }
+            }
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+                const int j = j0 + u * nl;
+                if (j < c.Nk) {
+                    const double Js = __dmul_rn((double)(1 - 2 * (si ^ sv[u])), Jv[u]);
+                    lfl[j] = lv[u];
+                    lf[j] = __dadd_rn(lv[u], 4 * Js);
+                }
+            }
         }
     } else {
         const uint8_t *Ji = c.Jb + (int64_t)i * c.Nk;
-        for (int j = lane; j < c.Nk; j += nl) {
-            const int Js = si ^ sget(c.s, (int)(off + j)) ^ (int)Ji[j];
-            const int lfj = c.lfi[cur + j];
-            c.lfi[last + j] = lfj;
-            c.lfi[cur + j] = lfj + 8 * Js - 4;
+        int32_t *lf = c.lfi + cur, *lfl = c.lfi + last;
+        for (int j0 = lane; j0 < c.Nk; j0 += nl * UB) {
+            int Jv[UB], lv[UB], sv[UB];
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+                const int j = j0 + u * nl;
+                if (j < c.Nk) { Jv[u] = (int)Ji[j]; lv[u] = lf[j]; sv[u] = sget(c.s, (int)(off + j)); }
+            }
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+                const int j = j0 + u * nl;
+                if (j < c.Nk) {
+                    const int Js = si ^ sv[u] ^ Jv[u];
+                    lfl[j] = lv[u];
+                    lf[j] = lv[u] + 8 * Js - 4;
+                }
+            }
         }
     }
 }

@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Secondary BASELINE configs (3, 4, 5): one JSON line each. The headline (config 2) is bench.py.
+  C3: GraphEA 3D L=32 ±J, rrrMC and bklMC at β=3, 256 replicas              -> iterations/s and executed moves/s
+  C4: GraphSKNormal N=4096, 512 replicas: tensor-core field init + lock-step Metropolis sweeps
+  C5: GraphQSKT Nk=1024, M=64, Γ=0.3, rrrMC, 64 replicas
+usage: python scripts/bench_configs.py [c3] [c4] [c5] [--quick]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rrrmc_b200 as rb
+
+quick = "--quick" in sys.argv
+which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c3", "c4", "c5"]
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+if "c3" in which:
+    L, D, R, beta = 32, 3, 256, 3.0
+    X = rb.GraphEA(L, D, replicas=R, rng=np.random.default_rng(1))
+    # equilibrate with checkerboard sweeps so that the low-T rejection-free samplers start from a typical state
+    _, C = rb.standardMC(X, beta, 200 * X.N, step=200 * X.N, seed=1, quiet=True)
+    for name, fn, iters in (("rrrMC", rb.rrrMC, 200_000 if quick else 2_000_000), ("bklMC", rb.bklMC, 10_000_000 if quick else 200_000_000)):
+        fn(X, beta, iters // 20, step=iters // 20, seed=2, C0=C, quiet=True)
+        t0 = time.perf_counter()
+        Es, C2 = fn(X, beta, iters, step=iters, seed=3, C0=C, quiet=True)
+        dt = time.perf_counter() - t0
+        info = X.last_run
+        emit(config="C3", sampler=name, L=L, D=D, replicas=R, beta=beta, iters_per_replica=iters,
+             iterations_per_s=R * iters / (info.device_ms * 1e-3), executed_moves_per_s=info.accepted_total / (info.device_ms * 1e-3),
+             device_ms=info.device_ms, wall_s=dt, launches=info.launches)
+
+if "c4" in which:
+    N, R, beta = 4096, 512, 1.0
+    X = rb.GraphSKNormal(N, replicas=R, rng=np.random.default_rng(2))
+    C0 = rb.Config(N, R, rng=np.random.default_rng(3))
+    for tc in (True, False):
+        rb.sk_fields_init(X, C0, tensor_cores=tc)
+        ms = min(rb.sk_fields_init(X, None, tensor_cores=tc)[2] for _ in range(3))
+        flop = 2.0 * N * N * R
+        emit(config="C4", op="local-field init", path="tcgen05 int8 x5 digit planes" if tc else "cuda cores, reference order (fp64)",
+             N=N, replicas=R, device_ms=ms, useful_tflops=flop / (ms * 1e-3) / 1e12,
+             int8_tops=(5 * flop / (ms * 1e-3) / 1e12) if tc else None)
+    nsw = 1 if quick else 3
+    rb.sk_fields_init(X, C0, tensor_cores=True)
+    rb.sk_metropolis_sweeps(X, beta, 1, seed=1)
+    t0 = time.perf_counter()
+    E, acc, _ = rb.sk_metropolis_sweeps(X, beta, nsw, seed=2, sweep0=1)
+    dt = time.perf_counter() - t0
+    emit(config="C4", op="lock-step Metropolis", N=N, replicas=R, beta=beta, sweeps=nsw, attempts_per_s=nsw * N * R / dt,
+         accept_rate=float(acc.sum()) / ((nsw + 1) * N * R), wall_s=dt, mean_E_per_N=float(E.mean() / N))
+
+if "c5" in which:
+    Nk, M, G, beta, R = 1024, 64, 0.3, 2.0, 64
+    X = rb.GraphQSKT(Nk, M, G, beta, replicas=R, rng=np.random.default_rng(4))
+    iters = 20_000 if quick else 400_000
+    _, C = rb.rrrMC(X, beta, iters // 10, step=iters // 10, seed=1, quiet=True)
+    t0 = time.perf_counter()
+    Es, C2 = rb.rrrMC(X, beta, iters, step=iters, seed=2, C0=C, quiet=True)
+    dt = time.perf_counter() - t0
+    info = X.last_run
+    emit(config="C5", sampler="rrrMC(DoubleGraph)", Nk=Nk, M=M, Gamma=G, beta=beta, replicas=R, iters_per_replica=iters,
+         iterations_per_s=R * iters / (info.device_ms * 1e-3), accepted_per_s=info.accepted_total / (info.device_ms * 1e-3),
+         device_ms=info.device_ms, wall_s=dt, Qenergy_mean=float(np.mean(rb.Qenergy(X, C2))))
