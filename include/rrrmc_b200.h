@@ -136,6 +136,13 @@ typedef int (*rrrmc_hook_fn)(void *user, int64_t it, const double *E, const int6
 #define RRRMC_SCHED_CHECKERBOARD 0 /* two-colour lattice sweeps, all replicas in lock step (new engine) */
 #define RRRMC_SCHED_RANDOM_SITE  1 /* the reference's order: i = rand(1:N) per attempt (RRRMC.jl:113)   */
 
+/* How a checkerboard task turns Philox bits into the Metropolis filter accept() of RRRMC.jl:39.
+ * Both are exact per-(site,replica) Bernoulli(exp(-βΔE)) decisions, independent across lanes; they consume the
+ * counter stream differently, so trajectories differ between procedures (each has its own CPU restatement). */
+#define RRRMC_CB_AUTO   0 /* sparse while 32·exp(-4β) <= 1.5 (β >~ 0.77), else planes                        */
+#define RRRMC_CB_PLANES 1 /* bit-plane comparison of a (K+32)-bit uniform per lane against 64-bit thresholds */
+#define RRRMC_CB_SPARSE 2 /* binomial count of passing lanes per ΔE class + uniform distinct positions       */
+
 typedef struct {
     int    schedule;        /* RRRMC_SCHED_*; default checkerboard                                   */
     int    planes_K;        /* checkerboard: full random bit planes, one Philox call each (default 5)  */
@@ -144,7 +151,8 @@ typedef struct {
     double staged_thr_fact; /* rrrMC: default 5.0 (RRRMC.jl:155)                                       */
     int    planes_M;        /* checkerboard: merged bit planes after the full ones, four per Philox
                                call (default 4, a multiple of 4); planes_K + planes_M <= 32. See DESIGN.md §5.          */
-    int    reserved[7];
+    int    cb_method;       /* checkerboard acceptance procedure: RRRMC_CB_AUTO (default), _PLANES, _SPARSE  */
+    int    reserved[6];
 } rrrmc_opts_t;
 rrrmc_status_t rrrmc_opts_default(rrrmc_opts_t *o);
 
@@ -183,6 +191,14 @@ rrrmc_status_t rrrmc_replay(rrrmc_state_t *s, int64_t replica, int sampler, doub
  * fixed-point acceptance table floor(exp(-β·ΔE_c)·2^64), ΔE_c = allΔE[c], c = 1..nclasses-1. */
 rrrmc_status_t rrrmc_checkerboard_sweeps(rrrmc_state_t *s, const uint64_t *thr64, int nthr, int planes_K, int planes_M,
                                          uint64_t seed, uint64_t sweep0, int64_t nsweeps);
+
+/* The same loop with the sparse procedure. tbl: count tables, class 1 (ΔE=4) first: 33 entries for Bin(32,p1)
+ * (one count per 32-replica word), then 129 entries per class c=2..D for Bin(128,pc) (one count per 128-replica
+ * task); entry k = round(P(count <= k)·2^32) - 1, last entry 2^32-1: more than k lanes pass iff x > tbl[k] for a
+ * 32-bit uniform x. rrrmc_checkerboard_sparse_tables builds them from the 64-bit fixed-point probabilities. */
+rrrmc_status_t rrrmc_checkerboard_sparse_tables(const uint64_t *thr64, int nthr, uint32_t *tbl, int tbl_len);
+rrrmc_status_t rrrmc_checkerboard_sweeps_sparse(rrrmc_state_t *s, const uint32_t *tbl, int tbl_len,
+                                                uint64_t seed, uint64_t sweep0, int64_t nsweeps);
 
 /* ---- dense GraphSKNormal path (BASELINE config 4) ----------------------------------------------
  * Local-field initialisation for the whole batch = the energy(X, C) contraction of SK.jl:212-237,

@@ -97,6 +97,9 @@ def lib():
         "orc_check_discrete_cache": (i32, [vp, p(np.uint64), f64, p(np.int64), i64]),
         "orc_checkerboard_sweeps": (None, [i32, i32, i64, p(np.uint32), p(np.int8), p(np.uint64), i32, i32,
                                            C.c_uint64, C.c_uint64, i64, vp]),
+        "orc_checkerboard_sweeps_sparse": (None, [i32, i32, i64, p(np.uint32), p(np.int8), p(np.uint32),
+                                                  C.c_uint64, C.c_uint64, i64, vp]),
+        "orc_cb_sparse_tables": (None, [p(np.uint64), i32, p(np.uint32)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -344,3 +347,38 @@ def checkerboard_sweeps(L, D, R, spins, Jfwd, thr, K, seed, sweep0, nsweeps, acc
     acc_p = accepted.ctypes.data if accepted is not None else None
     lib().orc_checkerboard_sweeps(L, D, R, spins, np.ascontiguousarray(Jfwd, np.int8),
                                   np.ascontiguousarray(thr, np.uint64), K, M, seed, sweep0, nsweeps, acc_p)
+
+
+CB_T1, CB_TC = 33, 129
+
+
+def cb_sparse_tables(thr):
+    """Count tables of the sparse procedure from the 64-bit fixed-point probabilities (oracle's long-double build)."""
+    thr = np.ascontiguousarray(thr, np.uint64)
+    tbl = np.zeros(CB_T1 + (len(thr) - 1) * CB_TC, np.uint32)
+    lib().orc_cb_sparse_tables(thr, len(thr), tbl)
+    return tbl
+
+
+def cb_sparse_tables_exact(thr):
+    """The same tables in exact rational arithmetic (pins the long-double builds to within one unit of 2^-32)."""
+    from fractions import Fraction
+    from math import comb
+    out = []
+    for c, t in enumerate(thr, start=1):
+        n = 32 if c == 1 else 128
+        p = Fraction(int(t), 1 << 64); q = 1 - p
+        cdf = Fraction(0)
+        for k in range(n + 1):
+            cdf += comb(n, k) * p ** k * q ** (n - k)
+            v = int(cdf * (1 << 32) + Fraction(1, 2))   # round half up
+            out.append(0xffffffff if (k == n or v >= 1 << 32) else max(v, 1) - 1)
+    return np.array(out, dtype=np.uint32)
+
+
+def checkerboard_sweeps_sparse(L, D, R, spins, Jfwd, tbl, seed, sweep0, nsweeps, accepted=None):
+    """CPU model of the engine's checkerboard sweeps with the sparse acceptance procedure."""
+    acc_p = accepted.ctypes.data if accepted is not None else None
+    assert len(tbl) == CB_T1 + (D - 1) * CB_TC
+    lib().orc_checkerboard_sweeps_sparse(L, D, R, spins, np.ascontiguousarray(Jfwd, np.int8),
+                                         np.ascontiguousarray(tbl, np.uint32), seed, sweep0, nsweeps, acc_p)

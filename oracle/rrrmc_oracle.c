@@ -1279,3 +1279,110 @@ void orc_checkerboard_sweeps(int L, int D, int64_t R, uint32_t *spins, const int
             }
     }
 }
+
+/* ---- "sparse" acceptance procedure ---------------------------------------------------------------------------
+ * Slot stream of a task: 7-bit slots taken LSB-first from a 64-bit window = words (0,1) of a Philox call; a window
+ * holds 9 slots; window k=0 comes from call 1, window k>=1 from call 1+k. */
+typedef struct { uint32_t ctr[4], key[2]; uint64_t win; int left; uint32_t call; uint32_t hi16; } orc_slots;
+static uint32_t orc_slot_next(orc_slots *s)
+{
+    if (s->left == 0) {
+        uint32_t out[4];
+        s->ctr[0] = s->call | s->hi16;
+        orc_philox4x32_10(s->ctr, s->key, out);
+        s->win = (uint64_t)out[0] | ((uint64_t)out[1] << 32);
+        s->left = 9; s->call++;
+    }
+    uint32_t v = (uint32_t)(s->win & 127u);
+    s->win >>= 7; s->left--;
+    return v;
+}
+
+void orc_cb_sparse_tables(const uint64_t *thr, int D, uint32_t *tbl)
+{
+    for (int c = 1; c <= D; c++) {
+        int n = c == 1 ? 32 : 128;
+        uint32_t *T = c == 1 ? tbl : tbl + ORC_CB_T1 + (c - 2) * ORC_CB_TC;
+        long double p = (long double)thr[c - 1] / 18446744073709551616.0L, q = 1.0L - p;
+        long double pk = powl(q, (long double)n), cdf = 0.0L;
+        for (int k = 0; k <= n; k++) {
+            cdf += pk;
+            /* "more than k lanes pass" iff x > T[k], x uniform on 32 bits: P = 1 - round(CDF·2^32)/2^32 */
+            long double v = rintl(cdf * 4294967296.0L);
+            T[k] = (k == n || v >= 4294967296.0L) ? 0xffffffffu : (v < 1.0L ? 0u : (uint32_t)(v - 1.0L));
+            pk = q > 0.0L ? pk * (long double)(n - k) / (long double)(k + 1) * (p / q) : (k + 1 == n ? 1.0L : 0.0L);
+        }
+    }
+}
+
+void orc_checkerboard_sweeps_sparse(int L, int D, int64_t R, uint32_t *spins, const int8_t *Jfwd,
+                                    const uint32_t *tbl, uint64_t seed, uint64_t sweep0, int64_t nsweeps,
+                                    int64_t *accepted)
+{
+    int64_t N = 1; for (int d = 0; d < D; d++) N *= L;
+    int64_t W = R / 32, G = (R + 127) / 128;
+    for (int64_t sw = 0; sw < nsweeps; sw++) {
+        uint64_t t = sweep0 + (uint64_t)sw;
+        for (int colour = 0; colour < 2; colour++)
+            for (int64_t i = 0; i < N; i++) {
+                int64_t co[3] = { 0, 0, 0 }, rem = i, par = 0;
+                for (int d = 0; d < D; d++) { co[d] = rem % L; rem /= L; par += co[d]; }
+                if ((par & 1) != colour) continue;
+                int64_t nbr[6]; int Jn[6]; int64_t stride = 1;
+                for (int d = 0; d < D; d++) {
+                    int64_t up = i + (((co[d] + 1) % L) - co[d]) * stride;
+                    int64_t dn = i + (((co[d] + L - 1) % L) - co[d]) * stride;
+                    nbr[2 * d] = up; Jn[2 * d] = Jfwd[i * D + d];
+                    nbr[2 * d + 1] = dn; Jn[2 * d + 1] = Jfwd[dn * D + d];
+                    stride *= L;
+                }
+                for (int64_t g = 0; g < G; g++) {
+                    /* pass[c][l] = 1: lane l passes the filter of class c (ΔE = 4c) in this attempt */
+                    unsigned char pass[4][128];
+                    memset(pass, 0, sizeof pass);
+                    orc_slots st;
+                    uint32_t A[4], B[4];
+                    st.key[0] = (uint32_t)seed; st.key[1] = (uint32_t)(seed >> 32);
+                    st.ctr[1] = (uint32_t)i; st.ctr[2] = (uint32_t)g; st.ctr[3] = (uint32_t)t;
+                    st.hi16 = (uint32_t)(t >> 32) << 16;
+                    st.ctr[0] = 0u | st.hi16; orc_philox4x32_10(st.ctr, st.key, A);
+                    st.ctr[0] = 1u | st.hi16; orc_philox4x32_10(st.ctr, st.key, B);
+                    st.win = (uint64_t)B[0] | ((uint64_t)B[1] << 32); st.left = 9; st.call = 2;
+                    /* class 1: one binomial count per 32-lane word, uniform = word w of call 0 */
+                    for (int w = 0; w < 4; w++) {
+                        int s = 0;
+                        while (s < 32 && A[w] > tbl[s]) {
+                            uint32_t pos = orc_slot_next(&st) & 31u;
+                            if (pass[1][32 * w + pos]) continue; /* duplicate: redraw */
+                            pass[1][32 * w + pos] = 1; s++;
+                        }
+                    }
+                    /* classes 2..D: one count per task, uniform = word c of call 1 */
+                    for (int c = 2; c <= D; c++) {
+                        const uint32_t *T = tbl + ORC_CB_T1 + (c - 2) * ORC_CB_TC;
+                        int s = 0;
+                        while (s < 128 && B[c] > T[s]) {
+                            uint32_t pos = orc_slot_next(&st);
+                            if (pass[c][pos]) continue;
+                            pass[c][pos] = 1; s++;
+                        }
+                    }
+                    for (int l = 0; l < 128; l++) {
+                        int64_t r = 128 * g + l;
+                        if (r >= R) continue;
+                        int64_t w = r >> 5; int b = (int)(r & 31);
+                        int sc = (spins[i * W + w] >> b) & 1, acc = 0;
+                        for (int k = 0; k < 2 * D; k++) {
+                            int sk = (spins[nbr[k] * W + w] >> b) & 1;
+                            acc += Jn[k] * (2 * sc - 1) * (2 * sk - 1);
+                        }
+                        int dE = 2 * acc;
+                        int flip = dE <= 0 ? 1 : pass[dE / 4][l];
+                        if (!flip) continue;
+                        spins[i * W + w] ^= (uint32_t)1 << b;
+                        if (accepted) accepted[r]++;
+                    }
+                }
+            }
+    }
+}

@@ -137,6 +137,20 @@ void orc_checkerboard_sweeps(int L, int D, int64_t R, uint32_t *spins, const int
                              const uint64_t *thr, int K, int M, uint64_t seed, uint64_t sweep0, int64_t nsweeps,
                              int64_t *accepted /* [R] += */);
 
+/* Same sweeps with the engine's "sparse" acceptance procedure: instead of comparing a uniform per
+ * lane, each task draws, per ΔE class, HOW MANY of its lanes pass (a binomial count by inverse CDF on one 32-bit
+ * uniform) and then WHICH ones (uniform distinct positions, duplicates redrawn).
+ * tbl: class 1 (ΔE=4): 33 entries T1[k] = round(P(Bin(32,p1) <= k)·2^32) - 1, one count per 32-lane word
+ *      (more than k lanes pass iff the 32-bit uniform x > T1[k]; T1[32] = 2^32-1 ends the scan);
+ *      classes c=2..D: 129 entries each, Tc[k] likewise for Bin(128,pc), one count per 128-lane task. */
+#define ORC_CB_T1 33
+#define ORC_CB_TC 129
+void orc_checkerboard_sweeps_sparse(int L, int D, int64_t R, uint32_t *spins, const int8_t *Jfwd,
+                                    const uint32_t *tbl, uint64_t seed, uint64_t sweep0, int64_t nsweeps,
+                                    int64_t *accepted /* [R] += */);
+/* Reference construction of those tables from the 64-bit fixed-point acceptance probabilities (long double). */
+void orc_cb_sparse_tables(const uint64_t *thr, int D, uint32_t *tbl);
+
 #ifdef __cplusplus
 }
 #endif

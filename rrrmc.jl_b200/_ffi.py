@@ -11,13 +11,16 @@ SO = os.path.join(HERE, "lib", "librrrmc_b200.so")
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4
 EA_PM1, EA_INT, EA_F64, SK_F64, SK_BIN, QT, QUANT, EMPTY = 1, 2, 3, 4, 5, 6, 7, 8
 SCHED_CHECKERBOARD, SCHED_RANDOM_SITE = 0, 1
+CB_AUTO, CB_PLANES, CB_SPARSE = 0, 1, 2
+CBS_T1, CBS_TC = 33, 129
 
 HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int64)
 
 
 class Opts(C.Structure):
     _fields_ = [("schedule", C.c_int), ("planes_K", C.c_int), ("count_accepted", C.c_int),
-                ("staged_thr", C.c_double), ("staged_thr_fact", C.c_double), ("planes_M", C.c_int), ("reserved", C.c_int * 7)]
+                ("staged_thr", C.c_double), ("staged_thr_fact", C.c_double), ("planes_M", C.c_int), ("cb_method", C.c_int),
+                ("reserved", C.c_int * 6)]
 
 
 class RunInfo(C.Structure):
@@ -74,6 +77,8 @@ SIGNATURES = {
     "rrrmc_bkl_mc": (_i32, _SAMPLER),
     "rrrmc_replay": (_i32, [_vp, _i64, _i32, _f64, _i64, _i64, _vp, _vp, _vp, _i64, C.POINTER(Opts), _vp, _i64, C.POINTER(RunInfo)]),
     "rrrmc_checkerboard_sweeps": (_i32, [_vp, _vp, _i32, _i32, _i32, _u64, _u64, _i64]),
+    "rrrmc_checkerboard_sparse_tables": (_i32, [_vp, _i32, _vp, _i32]),
+    "rrrmc_checkerboard_sweeps_sparse": (_i32, [_vp, _vp, _i32, _u64, _u64, _i64]),
 }
 
 _lib = None

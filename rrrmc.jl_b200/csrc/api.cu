@@ -8,6 +8,7 @@
 #include <set>
 #include "common.cuh"
 #include "kernels.cuh"
+#include "cb_params.cuh"
 #include "chain.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -608,6 +609,7 @@ extern "C" rrrmc_status_t rrrmc_opts_default(rrrmc_opts_t *o)
     o->schedule = RRRMC_SCHED_CHECKERBOARD;
     o->planes_K = 5;
     o->planes_M = 4;
+    o->cb_method = RRRMC_CB_AUTO;
     o->count_accepted = 1;
     o->staged_thr = NAN;
     o->staged_thr_fact = 5.0;
@@ -686,6 +688,82 @@ extern "C" rrrmc_status_t rrrmc_checkerboard_sweeps(rrrmc_state_t *s, const uint
     return RRRMC_OK;
 }
 
+// ---- "sparse" acceptance procedure: binomial-count tables and sweeps (ea_multispin.cu:k_checkerboard_sparse)
+extern "C" rrrmc_status_t rrrmc_checkerboard_sparse_tables(const uint64_t *thr64, int nthr, uint32_t *tbl, int tbl_len)
+{
+    RR_ARG(thr64 && tbl, "NULL argument");
+    RR_ARG(nthr >= 1 && nthr <= 3, "expected 1..3 acceptance thresholds, given %d", nthr);
+    RR_ARG(tbl_len >= CBS_T1 + (nthr - 1) * CBS_TC, "table buffer too small: %d < %d", tbl_len, CBS_T1 + (nthr - 1) * CBS_TC);
+    for (int c = 1; c <= nthr; c++) {
+        const int n = c == 1 ? 32 : 128;
+        uint32_t *T = c == 1 ? tbl : tbl + CBS_T1 + (c - 2) * CBS_TC;
+        const long double p = (long double)thr64[c - 1] / 18446744073709551616.0L, q = 1.0L - p;
+        long double pk = powl(q, (long double)n), cdf = 0.0L;   // P(Bin(n,p) = k), running CDF
+        for (int k = 0; k <= n; k++) {
+            cdf += pk;
+            const long double v = rintl(cdf * 4294967296.0L);    // more than k lanes pass iff x > T[k]
+            T[k] = (k == n || v >= 4294967296.0L) ? 0xffffffffu : (v < 1.0L ? 0u : (uint32_t)(v - 1.0L));
+            pk = q > 0.0L ? pk * (long double)(n - k) / (long double)(k + 1) * (p / q) : (k + 1 == n ? 1.0L : 0.0L);
+        }
+    }
+    return RRRMC_OK;
+}
+
+static rrrmc_status_t fill_cbs_params(rrrmc_state *s, const uint32_t *tbl, int tbl_len, uint64_t seed, cbs_params &p)
+{
+    rrrmc_graph *g = s->g;
+    if (!(g->kind == RRRMC_EA_PM1 && g->d_jcode)) {
+        rrrmc_set_error("checkerboard sweeps need a ±J GraphEA with D<=3");
+        return RRRMC_ERR_UNSUPPORTED;
+    }
+    if (!g->bipartite) {
+        rrrmc_set_error("checkerboard sweeps need even L (a two-colourable lattice), given L=%d; use schedule=RANDOM_SITE", g->L);
+        return RRRMC_ERR_UNSUPPORTED;
+    }
+    const int need = CBS_T1 + (g->D - 1) * CBS_TC;
+    RR_ARG(tbl_len == need, "expected a %d-entry count table for D=%d, given %d", need, g->D, tbl_len);
+    RR_ARG((int64_t)g->N * s->W < ((int64_t)1 << 31), "N*W = %lld words exceeds the kernel's 32-bit indexing", (long long)(g->N * s->W));
+    RR_ARG(tbl[CBS_T1 - 1] == 0xffffffffu, "count table of class 1 must end with 2^32-1");
+    for (int c = 2; c <= g->D; c++) RR_ARG(tbl[CBS_T1 + (c - 1) * CBS_TC - 1] == 0xffffffffu, "count table of class %d must end with 2^32-1", c);
+    memset(&p, 0, sizeof p);
+    p.spins = s->d_spins; p.flips = nullptr; p.jcode = g->d_jcode;
+    p.L = g->L; p.Lh = g->L / 2; p.W = (int)s->W; p.G = (int)((s->W + 3) / 4);
+    p.invG = 1.0f / (float)p.G;
+    { const char *v = getenv("RRRMC_CB_VARIANT"); p.variant = v ? atoi(v) : 0; }
+    memcpy(p.tbl, tbl, sizeof(uint32_t) * need);
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; r++) { p.rk[r][0] = k0 + (uint32_t)r * 0x9E3779B9u; p.rk[r][1] = k1 + (uint32_t)r * 0xBB67AE85u; }
+    return RRRMC_OK;
+}
+static rrrmc_status_t run_sweep_sparse(rrrmc_state *s, cbs_params &p, uint64_t t)
+{
+    rrrmc_graph *g = s->g;
+    p.t_lo = (uint32_t)t; p.t_hi16 = (uint32_t)(t >> 32) << 16;
+    RR_TRY(launch_checkerboard_sparse(g->ctx, p, g->D, 0));
+    RR_TRY(launch_checkerboard_sparse(g->ctx, p, g->D, 1));
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_checkerboard_sweeps_sparse(rrrmc_state_t *s, const uint32_t *tbl, int tbl_len,
+                                                           uint64_t seed, uint64_t sweep0, int64_t nsweeps)
+{
+    RR_ARG(s && tbl, "NULL argument");
+    RR_ARG(nsweeps >= 0, "nsweeps must be >= 0");
+    RR_CUDA(cudaSetDevice(s->g->ctx->device));
+    RR_TRY(chain_sync_to_multispin(s));
+    cbs_params p;
+    RR_TRY(fill_cbs_params(s, tbl, tbl_len, seed, p));
+    for (int64_t k = 0; k < nsweeps; k++) RR_TRY(run_sweep_sparse(s, p, sweep0 + (uint64_t)k));
+    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
+    return RRRMC_OK;
+}
+// AUTO: the sparse procedure wins while few lanes pass (expected passing lanes per 32-lane word <= 1.5)
+static bool cb_use_sparse(const rrrmc_opts_t *o, double p1)
+{
+    if (o->cb_method == RRRMC_CB_SPARSE) return true;
+    if (o->cb_method == RRRMC_CB_PLANES) return false;
+    return 32.0 * p1 <= 1.5;
+}
+
 static rrrmc_status_t uniform_beta(const rrrmc_state *s, const double *beta, double *b)
 {
     RR_ARG(beta, "beta is NULL");
@@ -708,14 +786,20 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
     RR_TRY(chain_sync_to_multispin(s));
     uint64_t thr[3];
     for (int c = 1; c <= g->D; c++) thr[c - 1] = fixed64(exp(-beta * 4.0 * c));
-    cb_params p;
-    RR_TRY(fill_cb_params(s, thr, g->D, o->planes_K, o->planes_M, seed, p));
+    RR_ARG(o->cb_method >= RRRMC_CB_AUTO && o->cb_method <= RRRMC_CB_SPARSE, "unknown cb_method %d", o->cb_method);
+    const bool sparse = cb_use_sparse(o, exp(-beta * 4.0));
+    cb_params p; cbs_params ps;
+    if (sparse) {
+        uint32_t tbl[CBS_T1 + 2 * CBS_TC];
+        RR_TRY(rrrmc_checkerboard_sparse_tables(thr, g->D, tbl, CBS_T1 + 2 * CBS_TC));
+        RR_TRY(fill_cbs_params(s, tbl, CBS_T1 + (g->D - 1) * CBS_TC, seed, ps));
+    } else RR_TRY(fill_cb_params(s, thr, g->D, o->planes_K, o->planes_M, seed, p));
     const int64_t N = g->N;
     const int64_t nsweeps = (iters + N - 1) / N, step_sw = std::max<int64_t>(1, (step + N - 1) / N);
     const bool count = o->count_accepted != 0;
     if (count) {
         if (!s->d_flips) RR_CUDA(cudaMalloc(&s->d_flips, sizeof(uint32_t) * N * s->W));
-        p.flips = s->d_flips;
+        p.flips = ps.flips = s->d_flips;
         RR_CUDA(cudaMemsetAsync(s->d_acc, 0, sizeof(long long) * s->W * 32, ctx->stream));
     }
     const uint64_t l0 = ctx->launches;
@@ -727,7 +811,7 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
     RR_CUDA(cudaEventCreate(&e0)); RR_CUDA(cudaEventCreate(&e1));
     RR_CUDA(cudaEventRecord(e0, ctx->stream));
     for (int64_t sw = 1; sw <= nsweeps; sw++) {
-        RR_TRY(run_sweep(s, p, (uint64_t)(sw - 1)));
+        if (sparse) RR_TRY(run_sweep_sparse(s, ps, (uint64_t)(sw - 1))); else RR_TRY(run_sweep(s, p, (uint64_t)(sw - 1)));
         if (count) RR_TRY(launch_count_lanes(ctx, s->d_flips, N, (int)s->W, s->d_acc));
         done = sw;
         if (sw % step_sw == 0 && (hook || (Es && nsamples < Es_cap))) {

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "philox.cuh"
 #include "kernels.cuh"
+#include "cb_params.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // bit-sliced helpers
@@ -98,7 +99,8 @@ __device__ __forceinline__ void class_masks(uint32_t u0, uint32_t u1, uint32_t u
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 with the ten round keys precomputed on the host (they are kernel-uniform): the xors read them
 // straight from the constant bank instead of re-deriving them on the uniform datapath in every call.
-__device__ __forceinline__ philox_out philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const cb_params &p)
+template <class PARAMS>
+__device__ __forceinline__ philox_out philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PARAMS &p)
 {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
@@ -306,6 +308,169 @@ rrrmc_status_t launch_checkerboard(rrrmc_ctx *ctx, const cb_params &p, int D, in
         else if ((p.variant & 7) == 2) LAUNCH(3, true, 6);
         else if ((p.variant & 7) == 3) LAUNCH(3, true, 3);
         else LAUNCH(3, true, 4);
+    }
+    else { rrrmc_set_error("checkerboard: D=%d unsupported (1..3)", D); return RRRMC_ERR_UNSUPPORTED; }
+#undef LAUNCH
+    ctx->launches++;
+    RR_CUDA(cudaGetLastError());
+    return RRRMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Checkerboard Metropolis half-sweep, "sparse" acceptance procedure. Same task decomposition as k_checkerboard.
+// At low temperature almost every lane with ΔE>0 is rejected, so instead of comparing one uniform per lane the
+// task samples the SET of passing lanes of each ΔE class directly: the number of passing lanes is binomial
+// (inverse CDF on one 32-bit uniform against a host-built table), their positions are uniform and distinct
+// (7-bit slots from a 64-bit window, duplicates redrawn). Lane l of class c flips iff l is in the set of class c,
+// i.e. with probability p_c, independently across lanes, exactly as accept() of RRRMC.jl:39 prescribes.
+//   call 0: words 0..3 = count uniforms of class 1 (ΔE=4) for the four 32-lane words of the task
+//   call 1: words 0,1 = first slot window; word 2 / 3 = count uniform of class 2 / 3 (128-lane counts)
+//   call 2+k: words 0,1 = slot window k+1 (rare)
+// Restated on the CPU in oracle/rrrmc_oracle.c:orc_checkerboard_sweeps_sparse (bit-for-bit).
+// Everything up to the class-1 sets is spin independent and runs while the seven 128-bit loads are in flight.
+// ------------------------------------------------------------------------------------------------
+#define CB_PHILOX(ctr0) philox4x32_10_rk((uint32_t)(ctr0) | p.t_hi16, c1, c2, p.t_lo, p)
+template <int D, bool FULL, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_checkerboard_sparse(const __grid_constant__ cbs_params p, int colour)
+{
+    const int row_tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row_tid >= p.Lh * p.G) return;
+    const int xh = __float2int_rz(((float)row_tid + 0.5f) * p.invG);   // row_tid / G, exact for row_tid < 2^22
+    const int g = row_tid - xh * p.G;
+    const int y = (D >= 2) ? blockIdx.y : 0, z = (D >= 3) ? blockIdx.z : 0;
+    const int L = p.L;
+    const int x = 2 * xh + ((y + z + colour) & 1);
+    const uint32_t row = (uint32_t)L * (uint32_t)(y + L * z);
+    const uint32_t i = row + x;
+    uint32_t nb[2 * D];
+    nb[0] = row + (x + 1 == L ? 0 : x + 1);
+    nb[1] = row + (x == 0 ? L - 1 : x - 1);
+    if (D >= 2) {
+        nb[2] = y + 1 == L ? i - (uint32_t)(L - 1) * L : i + L;
+        nb[3] = y == 0 ? i + (uint32_t)(L - 1) * L : i - L;
+    }
+    if (D >= 3) {
+        const uint32_t LL = (uint32_t)L * L;
+        nb[4] = z + 1 == L ? i - (uint32_t)(L - 1) * LL : i + LL;
+        nb[5] = z == 0 ? i + (uint32_t)(L - 1) * LL : i - LL;
+    }
+    const uint32_t W = p.W;
+
+    uint32_t sc[4], sn[4][2 * D];
+    if (FULL) {
+        const uint4 *sp = reinterpret_cast<const uint4 *>(p.spins);
+        const uint32_t W4 = W >> 2;
+        const uint4 c = sp[i * W4 + g];
+        sc[0] = c.x; sc[1] = c.y; sc[2] = c.z; sc[3] = c.w;
+#pragma unroll
+        for (int k = 0; k < 2 * D; k++) {
+            const uint4 v = sp[nb[k] * W4 + g];
+            sn[0][k] = v.x; sn[1][k] = v.y; sn[2][k] = v.z; sn[3][k] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            const bool ok = 4 * g + w < W;
+            sc[w] = ok ? p.spins[i * W + 4 * g + w] : 0u;
+#pragma unroll
+            for (int k = 0; k < 2 * D; k++) sn[w][k] = ok ? p.spins[nb[k] * W + 4 * g + w] : 0u;
+        }
+    }
+    const uint32_t jc = p.jcode[i];
+    const uint32_t c1 = i, c2 = (uint32_t)g;
+
+    // ---- spin-independent part: the sets of passing lanes
+    const philox_out A = CB_PHILOX(0), B = CB_PHILOX(1);
+    uint32_t y0 = B.x, y1 = B.y, call = 2;
+    int left = 9;
+    auto slot = [&]() -> uint32_t {     // next 7-bit slot of the task's stream
+        if (left == 0) { const philox_out r = CB_PHILOX(call); call++; y0 = r.x; y1 = r.y; left = 9; }
+        const uint32_t v = y0 & 127u;
+        y0 = __funnelshift_r(y0, y1, 7); y1 >>= 7; left--;
+        return v;
+    };
+    uint32_t P1[4];
+    {
+        const uint32_t xa[4] = { A.x, A.y, A.z, A.w };
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            uint32_t m = 0; int s = 0;
+            while (xa[w] > p.tbl[s]) {  // tbl[32] = 2^32-1 ends the scan
+                const uint32_t nm = m | (1u << (slot() & 31u));
+                s += nm != m;           // a duplicate position is redrawn
+                m = nm;
+            }
+            P1[w] = m;
+        }
+    }
+
+    // ---- spin-dependent part. p.zero is always 0: the data dependency keeps the loads in flight behind the RNG phase.
+#pragma unroll
+    for (int w = 0; w < 4; w++) sc[w] ^= P1[w] & p.zero;
+    uint32_t mc[4][3], fl[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        uint32_t u0, u1, u2;
+        unsat_planes<D>(sc[w], sn[w], jc, u0, u1, u2);
+        class_masks<D>(u0, u1, u2, mc[w]);
+        fl[w] = ~(mc[w][0] | mc[w][1] | mc[w][2]) | (mc[w][0] & P1[w]);
+    }
+    // classes 2..D: rare at the temperatures where this procedure is selected
+    if (D >= 2) {
+        const uint32_t xc[2] = { B.z, B.w };
+#pragma unroll
+        for (int c = 2; c <= D; c++) {
+            const uint32_t *T = p.tbl + CBS_T1 + (c - 2) * CBS_TC;
+            if (xc[c - 2] > T[0]) {
+                uint32_t m[4] = { 0u, 0u, 0u, 0u };
+                int s = 0;
+                while (xc[c - 2] > T[s]) {  // T[128] = 2^32-1
+                    const uint32_t pos = slot();
+                    const uint32_t bit = 1u << (pos & 31u);
+                    const int ww = (int)(pos >> 5);
+                    bool dup = false;
+#pragma unroll
+                    for (int w = 0; w < 4; w++) if (w == ww) { dup = (m[w] & bit) != 0; m[w] |= bit; }
+                    s += !dup;
+                }
+#pragma unroll
+                for (int w = 0; w < 4; w++) fl[w] |= mc[w][c - 1] & m[w];
+            }
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        if (!FULL && !(4 * g + w < W)) fl[w] = 0;
+        sc[w] ^= fl[w];
+    }
+    if (FULL) {
+        const uint32_t W4 = W >> 2;
+        reinterpret_cast<uint4 *>(p.spins)[i * W4 + g] = make_uint4(sc[0], sc[1], sc[2], sc[3]);
+        if (p.flips) reinterpret_cast<uint4 *>(p.flips)[i * W4 + g] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+    } else {
+#pragma unroll
+        for (int w = 0; w < 4; w++)
+            if (4 * g + w < W) {
+                p.spins[i * W + 4 * g + w] = sc[w];
+                if (p.flips) p.flips[i * W + 4 * g + w] = fl[w];
+            }
+    }
+}
+#undef CB_PHILOX
+
+rrrmc_status_t launch_checkerboard_sparse(rrrmc_ctx *ctx, const cbs_params &p, int D, int colour)
+{
+    const bool full = (p.W % 4) == 0;
+    dim3 block(256), grid(div_up((int64_t)p.Lh * p.G, 256), D >= 2 ? p.L : 1, D >= 3 ? p.L : 1);
+#define LAUNCH(DD, FF, MB) k_checkerboard_sparse<DD, FF, MB><<<grid, block, 0, ctx->stream>>>(p, colour)
+    if (D == 1) { if (full) LAUNCH(1, true, 1); else LAUNCH(1, false, 1); }
+    else if (D == 2) { if (full) LAUNCH(2, true, 1); else LAUNCH(2, false, 1); }
+    else if (D == 3) {
+        if (!full) LAUNCH(3, false, 1);
+        else if ((p.variant & 7) == 1) LAUNCH(3, true, 4);
+        else if ((p.variant & 7) == 2) LAUNCH(3, true, 6);
+        else if ((p.variant & 7) == 3) LAUNCH(3, true, 8);
+        else LAUNCH(3, true, 5);
     }
     else { rrrmc_set_error("checkerboard: D=%d unsupported (1..3)", D); return RRRMC_ERR_UNSUPPORTED; }
 #undef LAUNCH

@@ -2,30 +2,10 @@
 #pragma once
 #include "common.cuh"
 
-constexpr int CB_MAXK = 32;
-
-struct cb_params {
-    uint32_t *spins;        // [N][W]
-    uint32_t *flips;        // [N][W] or nullptr: per-attempt accept masks (for accepted counters)
-    const uint8_t *jcode;   // [N]
-    int L, Lh, W, G;        // lattice side, L/2, words per site, 128-replica groups per site
-    uint32_t k0, k1;        // Philox key = seed
-    uint32_t t_lo, t_hi16;  // sweep counter: low 32 bits, (high bits) << 16
-    int K;                  // full bit planes (one Philox call per plane)
-    int Ku;                 // leading planes whose threshold bit is class-independent (spin-independent part), <= K
-    int Kz;                 // leading planes whose threshold bit is 0 for every class, <= Ku
-    uint32_t rk[10][2];     // Philox round keys: key + r*(0x9E3779B9, 0xBB67AE85)
-    int M;                  // merged planes after the full ones (one Philox call per four planes)
-    float invG;             // 1/G
-    int variant;            // occupancy variant (tuning)
-    uint32_t zero;          // always 0 (opaque to ptxas: orders spin-dependent work after the first planes)
-    uint8_t planeop[CB_MAXK]; // q < K+M. 0: threshold bit 0 for all classes, 1: bit 1 for all classes, 2: mixed
-    uint32_t plane[CB_MAXK][3]; // plane[q][c-1] = all-ones iff bit (63-q) of thr64[c] is set
-    uint32_t rem[3];        // bits [63-K .. 32-K] of thr64[c]
-    uint32_t remM[3];       // bits [63-K-M .. 32-K-M] of thr64[c]
-};
-
+struct cb_params;
+struct cbs_params;
 rrrmc_status_t launch_checkerboard(rrrmc_ctx *ctx, const cb_params &p, int D, int colour);
+rrrmc_status_t launch_checkerboard_sparse(rrrmc_ctx *ctx, const cbs_params &p, int D, int colour);
 rrrmc_status_t launch_energy_pm1(rrrmc_state *s, int *d_unsat);
 rrrmc_status_t launch_count_lanes(rrrmc_ctx *ctx, const uint32_t *masks, int64_t N, int W, long long *d_out);
 rrrmc_status_t launch_delta_energy_site(rrrmc_state *s, int64_t site0, int *d_out);

@@ -505,7 +505,8 @@ def _run(fn, X, beta, iters, seed, step, hook, C0, quiet, opts, name):
     return (Es[:, 0] if R == 1 else Es), Cout
 
 
-def _opts(schedule=None, planes_K=None, count_accepted=None, staged_thr=None, staged_thr_fact=None, planes_M=None):
+def _opts(schedule=None, planes_K=None, count_accepted=None, staged_thr=None, staged_thr_fact=None, planes_M=None,
+          cb_method=None):
     o = _ffi.Opts()
     check(lib().rrrmc_opts_default(C.byref(o)))
     if schedule is not None:
@@ -514,6 +515,8 @@ def _opts(schedule=None, planes_K=None, count_accepted=None, staged_thr=None, st
         o.planes_K = planes_K
     if planes_M is not None:
         o.planes_M = planes_M
+    if cb_method is not None:
+        o.cb_method = {"auto": _ffi.CB_AUTO, "planes": _ffi.CB_PLANES, "sparse": _ffi.CB_SPARSE}[cb_method]
     if count_accepted is not None:
         o.count_accepted = int(count_accepted)
     if staged_thr is not None:
@@ -524,16 +527,17 @@ def _opts(schedule=None, planes_K=None, count_accepted=None, staged_thr=None, st
 
 
 def standardMC(X, β, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, quiet=False,
-               schedule=None, planes_K=None, planes_M=None, count_accepted=None):
+               schedule=None, planes_K=None, planes_M=None, count_accepted=None, cb_method=None):
     """standardMC(X, β, iters; seed, step, hook, C0, quiet) (src/RRRMC.jl:81-127) -> (Es, C).
 
     schedule="random" is the reference's order (i = rand(1:N) per attempt, one chain per lane);
     schedule="checkerboard" (default where the lattice is two-colourable) updates all replicas in lock step,
-    a whole sweep (N attempts) at a time — `iters`/`step` are rounded up to whole sweeps."""
+    a whole sweep (N attempts) at a time — `iters`/`step` are rounded up to whole sweeps. cb_method selects how a
+    task turns Philox bits into accept() decisions: "planes", "sparse" or "auto" (include/rrrmc_b200.h)."""
     if schedule is None:
         schedule = "checkerboard" if (isinstance(X, GraphEA) and set(X.LEV) == {-1, 1} and X.L % 2 == 0 and X.D <= 3) else "random"
     return _run(lib().rrrmc_standard_mc, X, β, iters, seed, step, hook, C0, quiet,
-                _opts(schedule, planes_K, count_accepted, planes_M=planes_M), "standardMC")
+                _opts(schedule, planes_K, count_accepted, planes_M=planes_M, cb_method=cb_method), "standardMC")
 
 
 def rrrMC(X, β, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, staged_thr=float("nan"),

@@ -68,6 +68,86 @@ def test_checkerboard_bit_exact_vs_cpu_model(L, D, R, K, M, beta):
     assert not (got == C0)
 
 
+def _sparse_tbl(beta, D):
+    thr = ffi.thresholds_fixed64(beta, D)
+    n = ffi.CB_T1 + (D - 1) * ffi.CB_TC
+    tbl = np.zeros(n, np.uint32)
+    check(lib().rrrmc_checkerboard_sparse_tables(ptr(thr), D, ptr(tbl), n))
+    return tbl
+
+
+@pytest.mark.parametrize("L,D,R,beta", [(4, 2, 32, 0.5), (6, 2, 96, 1.0), (4, 3, 128, 0.7), (6, 3, 160, 1.2), (8, 3, 256, 0.3),
+                                        (2, 3, 64, 0.9), (4, 1, 32, 0.6), (8, 3, 100, 2.0), (8, 3, 512, 0.05), (8, 3, 384, 1.0),
+                                        (6, 3, 128, 0.0), (8, 2, 1024, 1.0), (16, 3, 1024, 1.0)])
+def test_checkerboard_sparse_bit_exact_vs_cpu_model(L, D, R, beta):
+    """Sparse acceptance procedure (binomial counts + positions) against orc_checkerboard_sweeps_sparse. Small β makes
+    almost every lane pass, which drives the duplicate-redraw and window-refill paths hard."""
+    A, J = ea_instance(L, D, seed=L * 10 + D)
+    X = rb.GraphEA(L, D, replicas=R, A=A, J=J)
+    C0 = rb.Config(X.N, R, rng=np.random.default_rng(7))
+    tbl = _sparse_tbl(beta, D)
+    seed, nsw = 0xC0FFEE1234, 5
+    X._upload(C0)
+    check(lib().rrrmc_checkerboard_sweeps_sparse(X._state, ptr(tbl), len(tbl), seed, (1 << 33) + 3, nsw))
+    got = X._download()
+    Rp = ((R + 31) // 32) * 32
+    sp = _multispin(C0)
+    ffi.checkerboard_sweeps_sparse(L, D, Rp, sp, _fwd(A, J, L, D), tbl, seed, (1 << 33) + 3, nsw)
+    want = _from_multispin(sp, R)
+    assert got == want
+    assert not (got == C0)
+
+
+def test_standardMC_sparse_energies_and_accepted():
+    L, D, R, beta = 6, 3, 64, 1.1
+    A, J = ea_instance(L, D, seed=3)
+    X = rb.GraphEA(L, D, replicas=R, A=A, J=J)
+    g = ffi.Graph.ea_int(A, J)
+    C0 = rb.Config(X.N, R, rng=np.random.default_rng(8))
+    seen = []
+
+    def hook(it, X_, C, acc, E):
+        seen.append((it, np.array(acc), np.array(E), C.chunks.copy()))
+        return True
+    N = X.N
+    Es, Cf = rb.standardMC(X, beta, 6 * N, step=2 * N, seed=77, C0=C0, hook=hook, quiet=True)  # auto -> sparse at β=1.1
+    sp = _multispin(C0); acc = np.zeros(R, np.int64)
+    tbl = ffi.cb_sparse_tables(ffi.thresholds_fixed64(beta, D))
+    for k in range(3):
+        ffi.checkerboard_sweeps_sparse(L, D, R, sp, _fwd(A, J, L, D), tbl, 77, 2 * k, 2, acc)
+        cfg = _from_multispin(sp, R)
+        assert np.array_equal(seen[k][3], cfg.chunks)
+        assert np.array_equal(seen[k][1], acc)
+        e = np.array([g.energy(cfg.chunks[r]) for r in range(R)])
+        assert np.array_equal(seen[k][2], e.astype(np.int64)) and np.array_equal(Es[k], e.astype(np.int64))
+    assert Cf == _from_multispin(sp, R)
+    # the two procedures are different consumers of the same counter stream: trajectories differ, both are valid
+    Es2, _ = rb.standardMC(X, beta, 6 * N, step=2 * N, seed=77, C0=C0, quiet=True, cb_method="planes")
+    assert not np.array_equal(Es, Es2)
+
+
+@pytest.mark.parametrize("method,beta", [("sparse", 1.0), ("sparse", 0.6), ("planes", 1.0)])
+def test_checkerboard_methods_statistics_vs_reference_sampler(method, beta):
+    """⟨E⟩ after equilibration: each acceptance procedure vs the oracle's random-site standardMC within 3σ."""
+    L, D = 6, 3
+    A, J = ea_instance(L, D, seed=22)
+    R = 512
+    X = rb.GraphEA(L, D, replicas=R, A=A, J=J)
+    N = X.N
+    Es, _ = rb.standardMC(X, beta, 600 * N, step=600 * N, seed=6, quiet=True, cb_method=method)
+    e_gpu = Es[-1] / N
+    g = ffi.Graph.ea_int(A, J)
+    e_cpu = []
+    for r in range(96):
+        src = ffi.PhiloxDraws(4321, chain=r)
+        s = src.config(N)
+        E, _ = ffi.standardMC(g, beta, 600 * N, s, src, step=600 * N)
+        e_cpu.append(E[-1] / N)
+    e_cpu = np.array(e_cpu)
+    sigma = np.sqrt(e_gpu.var(ddof=1) / R + e_cpu.var(ddof=1) / len(e_cpu))
+    assert abs(e_gpu.mean() - e_cpu.mean()) < 3 * sigma, (method, e_gpu.mean(), e_cpu.mean(), sigma)
+
+
 def test_standardMC_checkerboard_energies_and_accepted():
     L, D, R, beta = 6, 3, 64, 0.8
     A, J = ea_instance(L, D, seed=3)
@@ -80,7 +160,8 @@ def test_standardMC_checkerboard_energies_and_accepted():
         seen.append((it, np.array(acc), np.array(E), C.chunks.copy()))
         return True
     N = X.N
-    Es, Cf = rb.standardMC(X, beta, 6 * N, step=2 * N, seed=77, C0=C0, hook=hook, quiet=True, planes_K=6, planes_M=4)
+    Es, Cf = rb.standardMC(X, beta, 6 * N, step=2 * N, seed=77, C0=C0, hook=hook, quiet=True, planes_K=6, planes_M=4,
+                           cb_method="planes")
     assert Es.shape == (3, R) and [s[0] for s in seen] == [2 * N, 4 * N, 6 * N]
     # CPU model with the same seed / thresholds
     sp = _multispin(C0); acc = np.zeros(R, np.int64)
@@ -140,3 +221,11 @@ def test_full_size_properties_L64_R1024():
     assert np.array_equal(mid.chunks, ~Cf.chunks)
     check(lib().rrrmc_checkerboard_sweeps(st, ptr(thr0), D, 6, 8, 2, 1, 1))
     assert X._download() == Cf
+    # sparse procedure at full size: energies keep decreasing towards equilibrium and match the oracle's energy()
+    tbl = _sparse_tbl(1.0, D)
+    check(lib().rrrmc_checkerboard_sweeps_sparse(st, ptr(tbl), len(tbl), 3, 0, 6))
+    E2 = np.zeros(R); check(lib().rrrmc_energy(st, ptr(E2)))
+    C2 = X._download()
+    for r in (1, 700):
+        assert g.energy(C2.chunks[r]) == E2[r]
+    assert E2.mean() < E.mean()
