@@ -1281,8 +1281,12 @@ void orc_checkerboard_sweeps(int L, int D, int64_t R, uint32_t *spins, const int
 }
 
 /* ---- "sparse" acceptance procedure ---------------------------------------------------------------------------
- * Slot stream of a task: 7-bit slots taken LSB-first from a 64-bit window = words (0,1) of a Philox call; a window
- * holds 9 slots; window k=0 comes from call 1, window k>=1 from call 1+k. */
+ * Random words of a task: call 0 = (A0..A3), call 1 = (B0..B3). S = B0 | B1<<32.
+ *   S bits [0,40): eight 5-bit "static" slots; word w of class 1 takes slots 2w and 2w+1 for its first two draws
+ *   S bits [40,61): the first three 7-bit slots of the task's overflow stream
+ *   calls 2,3,...: words (0,1) of each form a 64-bit window holding nine more 7-bit overflow slots (LSB first)
+ * The overflow stream serves, in this order: the 3rd, 4th... draws (and redraws) of class-1 words 0..3, then the
+ * draws of class 2, then of class 3. */
 typedef struct { uint32_t ctr[4], key[2]; uint64_t win; int left; uint32_t call; uint32_t hi16; } orc_slots;
 static uint32_t orc_slot_next(orc_slots *s)
 {
@@ -1347,12 +1351,14 @@ void orc_checkerboard_sweeps_sparse(int L, int D, int64_t R, uint32_t *spins, co
                     st.hi16 = (uint32_t)(t >> 32) << 16;
                     st.ctr[0] = 0u | st.hi16; orc_philox4x32_10(st.ctr, st.key, A);
                     st.ctr[0] = 1u | st.hi16; orc_philox4x32_10(st.ctr, st.key, B);
-                    st.win = (uint64_t)B[0] | ((uint64_t)B[1] << 32); st.left = 9; st.call = 2;
+                    uint64_t S = (uint64_t)B[0] | ((uint64_t)B[1] << 32);
+                    st.win = S >> 40; st.left = 3; st.call = 2;
                     /* class 1: one binomial count per 32-lane word, uniform = word w of call 0 */
                     for (int w = 0; w < 4; w++) {
-                        int s = 0;
+                        int s = 0, j = 0;
                         while (s < 32 && A[w] > tbl[s]) {
-                            uint32_t pos = orc_slot_next(&st) & 31u;
+                            uint32_t pos = j < 2 ? (uint32_t)(S >> (5 * (2 * w + j))) & 31u : orc_slot_next(&st) & 31u;
+                            j++;
                             if (pass[1][32 * w + pos]) continue; /* duplicate: redraw */
                             pass[1][32 * w + pos] = 1; s++;
                         }

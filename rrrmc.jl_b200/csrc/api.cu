@@ -236,6 +236,13 @@ extern "C" rrrmc_status_t rrrmc_graph_ea_create(rrrmc_ctx_t *ctx, int L, int D, 
                 if (g->Ji[i * twoD + k] < 0) jc[i] |= (uint8_t)(1u << code[i * twoD + k]);
         RR_CUDA(cudaMalloc(&g->d_jcode, N));
         RR_CUDA(cudaMemcpy(g->d_jcode, jc.data(), N, cudaMemcpyHostToDevice));
+        // the same signs expanded to whole-word masks [N][8] (two unused): the sparse checkerboard kernel is bound
+        // by its ALU pipe, so it loads the six masks (32 B per site, shared by all replicas) instead of expanding bits
+        std::vector<uint32_t> jm(N * 8, 0u);
+        for (int64_t i = 0; i < N; i++)
+            for (int k = 0; k < 6; k++) jm[i * 8 + k] = ((jc[i] >> k) & 1u) ? 0xffffffffu : 0u;
+        RR_CUDA(cudaMalloc(&g->d_jmask, sizeof(uint32_t) * N * 8));
+        RR_CUDA(cudaMemcpy(g->d_jmask, jm.data(), sizeof(uint32_t) * N * 8, cudaMemcpyHostToDevice));
     }
     RR_CUDA(cudaDeviceSynchronize()); // default-stream uploads are complete before any non-blocking stream uses them
     *out = g;
@@ -340,7 +347,7 @@ extern "C" rrrmc_status_t rrrmc_graph_destroy(rrrmc_graph_t *g)
 {
     if (!g) return RRRMC_OK;
     cudaSetDevice(g->ctx->device);
-    cudaFree(g->d_jcode); cudaFree(g->d_A); cudaFree(g->d_J8); cudaFree(g->d_Jd); cudaFree(g->d_Jb);
+    cudaFree(g->d_jcode); cudaFree(g->d_jmask); cudaFree(g->d_A); cudaFree(g->d_J8); cudaFree(g->d_Jd); cudaFree(g->d_Jb);
     delete g;
     return RRRMC_OK;
 }
@@ -726,9 +733,12 @@ static rrrmc_status_t fill_cbs_params(rrrmc_state *s, const uint32_t *tbl, int t
     RR_ARG(tbl[CBS_T1 - 1] == 0xffffffffu, "count table of class 1 must end with 2^32-1");
     for (int c = 2; c <= g->D; c++) RR_ARG(tbl[CBS_T1 + (c - 1) * CBS_TC - 1] == 0xffffffffu, "count table of class %d must end with 2^32-1", c);
     memset(&p, 0, sizeof p);
-    p.spins = s->d_spins; p.flips = nullptr; p.jcode = g->d_jcode;
+    p.spins = s->d_spins; p.flips = nullptr; p.jcode = g->d_jcode; p.jmask = reinterpret_cast<const uint4 *>(g->d_jmask);
     p.L = g->L; p.Lh = g->L / 2; p.W = (int)s->W; p.G = (int)((s->W + 3) / 4);
     p.invG = 1.0f / (float)p.G;
+    p.one = 1u;
+    p.Gshift = -1;
+    for (int b = 0; b < 30; b++) if (p.G == (1 << b)) p.Gshift = b;
     { const char *v = getenv("RRRMC_CB_VARIANT"); p.variant = v ? atoi(v) : 0; }
     memcpy(p.tbl, tbl, sizeof(uint32_t) * need);
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);

@@ -32,11 +32,13 @@ struct cbs_params {
     uint32_t *spins;        // [N][W]
     uint32_t *flips;        // [N][W] or nullptr
     const uint8_t *jcode;   // [N]
+    const uint4 *jmask;     // [N][2]: whole-word sign masks of the six bonds of a site (api.cu)
     int L, Lh, W, G;
     uint32_t t_lo, t_hi16;
     uint32_t rk[10][2];     // Philox round keys
+    uint32_t one;           // always 1, opaque to ptxas: keeps compare-by-carry multiplies on the FMA pipe
     float invG;
+    int Gshift;             // log2(G) when G is a power of two, else -1
     int variant;
-    uint32_t zero;          // always 0 (see cb_params)
     uint32_t tbl[CBS_T1 + 2 * CBS_TC]; // more than k lanes pass iff x > tbl[k]
 };

@@ -44,6 +44,7 @@ struct rrrmc_graph {
     std::vector<double> Jd;          // [N*twoD] (F64)
     std::vector<double> allDE;
     // device
+    uint32_t *d_jmask = nullptr;     // PM1 lattice: the six sign bits of d_jcode as whole-word masks, [N][8]
     uint8_t *d_jcode = nullptr;      // PM1 lattice: bit 2d = J(i -> i+e_d) < 0, bit 2d+1 = J(i-e_d -> i) < 0
     int32_t *d_A = nullptr;          // [N*twoD]
     int8_t *d_J8 = nullptr;          // [N*twoD] (PM1/INT)

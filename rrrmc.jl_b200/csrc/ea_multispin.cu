@@ -82,6 +82,29 @@ __device__ __forceinline__ void class_masks(uint32_t u0, uint32_t u1, uint32_t u
     if (D == 3) { mc[0] = ~u2 & u1 & ~u0; mc[1] = ~u2 & ~u1 & u0; mc[2] = ~(u2 | u1 | u0); } // u=2,1,0
 }
 
+// unsat_planes with the bond sign masks already expanded
+template <int D>
+__device__ __forceinline__ void unsat_planes_neg(uint32_t sc, const uint32_t (&sn)[2 * D], const uint32_t (&neg)[2 * D],
+                                                 uint32_t &u0, uint32_t &u1, uint32_t &u2)
+{
+    uint32_t b[2 * D];
+#pragma unroll
+    for (int k = 0; k < 2 * D; k++) b[k] = sc ^ sn[k] ^ neg[k];
+    if (D == 1) { u0 = b[0] ^ b[1]; u1 = b[0] & b[1]; u2 = 0; }
+    if (D == 2) {
+        uint32_t s1, c1; full_add(b[0], b[1], b[2], s1, c1);
+        u0 = s1 ^ b[3];
+        const uint32_t c2 = s1 & b[3];
+        u1 = c1 ^ c2; u2 = c1 & c2;
+    }
+    if (D == 3) {
+        uint32_t s1, c1, s2, c2; full_add(b[0], b[1], b[2], s1, c1); full_add(b[3], b[4], b[5], s2, c2);
+        u0 = s1 ^ s2;
+        const uint32_t c3 = s1 & s2;
+        full_add(c1, c2, c3, u1, u2);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Checkerboard Metropolis half-sweep. One thread = one task (site of the active colour, group of
 // 128 replicas). Acceptance is Metropolis (RRRMC.jl:39: ΔE<=0 always, else U<exp(-βΔE)) with U built
@@ -321,22 +344,74 @@ rrrmc_status_t launch_checkerboard(rrrmc_ctx *ctx, const cb_params &p, int D, in
 // At low temperature almost every lane with ΔE>0 is rejected, so instead of comparing one uniform per lane the
 // task samples the SET of passing lanes of each ΔE class directly: the number of passing lanes is binomial
 // (inverse CDF on one 32-bit uniform against a host-built table), their positions are uniform and distinct
-// (7-bit slots from a 64-bit window, duplicates redrawn). Lane l of class c flips iff l is in the set of class c,
-// i.e. with probability p_c, independently across lanes, exactly as accept() of RRRMC.jl:39 prescribes.
+// (duplicates redrawn). Lane l of class c flips iff l is in the set of class c, i.e. with probability p_c,
+// independently across lanes, exactly as accept() of RRRMC.jl:39 prescribes. Random words of a task:
 //   call 0: words 0..3 = count uniforms of class 1 (ΔE=4) for the four 32-lane words of the task
-//   call 1: words 0,1 = first slot window; word 2 / 3 = count uniform of class 2 / 3 (128-lane counts)
-//   call 2+k: words 0,1 = slot window k+1 (rare)
+//   call 1: S = word0 | word1<<32: bits [0,40) eight 5-bit static slots (word w draws 2w, 2w+1), bits [40,61) the
+//           first three 7-bit slots of the overflow stream; word 2 / 3 = count uniform of class 2 / 3 (128 lanes)
+//   call 2+k: words 0,1 = nine more 7-bit overflow slots (rare)
+// The overflow stream serves the 3rd.. draws and redraws of class-1 words 0..3, then class 2, then class 3.
 // Restated on the CPU in oracle/rrrmc_oracle.c:orc_checkerboard_sweeps_sparse (bit-for-bit).
-// Everything up to the class-1 sets is spin independent and runs while the seven 128-bit loads are in flight.
+// The common case (<= 2 passing lanes per word, no duplicate, no class-2/3 lane) is branch free.
 // ------------------------------------------------------------------------------------------------
+struct cbs_stream { uint32_t y0, y1, call; int left; };
+// refill of the overflow window: rare, kept out of line so that the hot path stays small
+__device__ __noinline__ uint2 cbs_refill(uint32_t ctr0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+{
+    const philox_out r = philox4x32_10(ctr0, c1, c2, c3, k0, k1);
+    return make_uint2(r.x, r.y);
+}
+
+// one LOP3 with an explicit truth table (inputs a=0xF0, b=0xCC, c=0xAA): the bit-sliced ΔE logic is the ALU-pipe
+// bottleneck of this kernel, so its operation count is pinned by hand instead of left to the optimiser
+template <int LUT> __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return r;
+}
+constexpr int LUT_XOR3 = 0x96, LUT_MAJ = 0xE8;
+
+// flip mask of one 32-lane word: lanes with ΔE<=0 plus the class-1 lanes (ΔE=4) that are in the pass set m.
+// 3D: with (s1,k1), (s2,k2) the full-adder outputs of bonds 0-2 and 3-5, u = s1+s2+2(k1+k2) and
+//     [u>=3] | ([u==2] & m) = MAJ(k1, k2, s1|s2|m) | (s1&s2&m)  — 14 LOP3 per word including the six bond planes.
+template <int D>
+__device__ __forceinline__ uint32_t cbs_flip_word(uint32_t sc, const uint32_t (&sn)[2 * D], const uint32_t (&neg)[2 * D], uint32_t m)
+{
+    uint32_t b[2 * D];
+#pragma unroll
+    for (int k = 0; k < 2 * D; k++) b[k] = lop3<LUT_XOR3>(sc, sn[k], neg[k]);
+    if (D == 1) return lop3<0xFE>(b[0], b[1], m);                       // u>=1 free; u==0 needs m
+    if (D == 2) {                                                        // u>=2 free; u==1 needs m
+        const uint32_t s1 = lop3<LUT_XOR3>(b[0], b[1], b[2]), k1 = lop3<LUT_MAJ>(b[0], b[1], b[2]);
+        return k1 | lop3<LUT_MAJ>(s1, b[3], m);
+    }
+    const uint32_t s1 = lop3<LUT_XOR3>(b[0], b[1], b[2]), k1 = lop3<LUT_MAJ>(b[0], b[1], b[2]);
+    const uint32_t s2 = lop3<LUT_XOR3>(b[3], b[4], b[5]), k2 = lop3<LUT_MAJ>(b[3], b[4], b[5]);
+    const uint32_t f1 = lop3<0xFE>(s1, s2, m), f2 = lop3<0x80>(s1, s2, m);
+    return lop3<LUT_MAJ>(k1, k2, f1) | f2;
+}
+
+// acc + [x > T] as the carry of x·1 + ~T into the high word of a 64-bit multiply-add: a compare on the FMA pipe
+__device__ __forceinline__ uint32_t gt_carry(uint32_t x, uint32_t one, uint32_t notT, uint32_t acc)
+{
+    uint64_t t;
+    const uint64_t c = ((uint64_t)acc << 32) | notT;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(t) : "r"(x), "r"(one), "l"(c));
+    return (uint32_t)(t >> 32);
+}
+
 #define CB_PHILOX(ctr0) philox4x32_10_rk((uint32_t)(ctr0) | p.t_hi16, c1, c2, p.t_lo, p)
-template <int D, bool FULL, int MINB>
+// OPT bit 0: class-1 counts compared on the FMA pipe (gt_carry) instead of ISETP/SEL on the ALU pipe
+// OPT bit 1: bond sign masks loaded from jmask instead of expanded from jcode bits
+template <int D, bool FULL, int MINB, int OPT>
 __global__ void __launch_bounds__(256, MINB) k_checkerboard_sparse(const __grid_constant__ cbs_params p, int colour)
 {
     const int row_tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (row_tid >= p.Lh * p.G) return;
-    const int xh = __float2int_rz(((float)row_tid + 0.5f) * p.invG);   // row_tid / G, exact for row_tid < 2^22
-    const int g = row_tid - xh * p.G;
+    int xh, g;
+    if (p.Gshift >= 0) { xh = row_tid >> p.Gshift; g = row_tid & (p.G - 1); }
+    else { xh = __float2int_rz(((float)row_tid + 0.5f) * p.invG); g = row_tid - xh * p.G; } // exact for row_tid < 2^22
     const int y = (D >= 2) ? blockIdx.y : 0, z = (D >= 3) ? blockIdx.z : 0;
     const int L = p.L;
     const int x = 2 * xh + ((y + z + colour) & 1);
@@ -354,17 +429,16 @@ __global__ void __launch_bounds__(256, MINB) k_checkerboard_sparse(const __grid_
         nb[4] = z + 1 == L ? i - (uint32_t)(L - 1) * LL : i + LL;
         nb[5] = z == 0 ? i + (uint32_t)(L - 1) * LL : i - LL;
     }
-    const uint32_t W = p.W;
+    const uint32_t W = p.W, W4 = W >> 2;
 
     uint32_t sc[4], sn[4][2 * D];
     if (FULL) {
-        const uint4 *sp = reinterpret_cast<const uint4 *>(p.spins);
-        const uint32_t W4 = W >> 2;
-        const uint4 c = sp[i * W4 + g];
+        const uint4 *sp4 = reinterpret_cast<const uint4 *>(p.spins);
+        const uint4 c = sp4[i * W4 + g];
         sc[0] = c.x; sc[1] = c.y; sc[2] = c.z; sc[3] = c.w;
 #pragma unroll
         for (int k = 0; k < 2 * D; k++) {
-            const uint4 v = sp[nb[k] * W4 + g];
+            const uint4 v = sp4[nb[k] * W4 + g];
             sn[0][k] = v.x; sn[1][k] = v.y; sn[2][k] = v.z; sn[3][k] = v.w;
         }
     } else {
@@ -376,53 +450,110 @@ __global__ void __launch_bounds__(256, MINB) k_checkerboard_sparse(const __grid_
             for (int k = 0; k < 2 * D; k++) sn[w][k] = ok ? p.spins[nb[k] * W + 4 * g + w] : 0u;
         }
     }
-    const uint32_t jc = p.jcode[i];
-    const uint32_t c1 = i, c2 = (uint32_t)g;
-
-    // ---- spin-independent part: the sets of passing lanes
-    const philox_out A = CB_PHILOX(0), B = CB_PHILOX(1);
-    uint32_t y0 = B.x, y1 = B.y, call = 2;
-    int left = 9;
-    auto slot = [&]() -> uint32_t {     // next 7-bit slot of the task's stream
-        if (left == 0) { const philox_out r = CB_PHILOX(call); call++; y0 = r.x; y1 = r.y; left = 9; }
-        const uint32_t v = y0 & 127u;
-        y0 = __funnelshift_r(y0, y1, 7); y1 >>= 7; left--;
-        return v;
-    };
-    uint32_t P1[4];
-    {
-        const uint32_t xa[4] = { A.x, A.y, A.z, A.w };
+    uint32_t neg[2 * D];
+    if (OPT & 2) {
+        const uint4 a = p.jmask[2 * i];
+        neg[0] = a.x; neg[1] = a.y;
+        if (D >= 2) { neg[2] = a.z; neg[3] = a.w; }
+        if (D >= 3) { const uint2 c = reinterpret_cast<const uint2 *>(p.jmask)[4 * i + 2]; neg[4] = c.x; neg[5] = c.y; }
+    } else {
+        const uint32_t jc = p.jcode[i];
 #pragma unroll
-        for (int w = 0; w < 4; w++) {
-            uint32_t m = 0; int s = 0;
-            while (xa[w] > p.tbl[s]) {  // tbl[32] = 2^32-1 ends the scan
-                const uint32_t nm = m | (1u << (slot() & 31u));
-                s += nm != m;           // a duplicate position is redrawn
-                m = nm;
+        for (int k = 0; k < 2 * D; k++) neg[k] = 0u - ((jc >> k) & 1u);
+    }
+    const uint32_t c1 = i, c2 = (uint32_t)g;
+    const int skip = p.variant >> 4;   // timing experiments only (tune_cb.py): bit 0 Philox, bit 1 class-1, bit 2 ΔE logic
+
+    // ---- spin-independent part: the sets of passing lanes of class 1
+    philox_out A, B;
+    if (skip & 1) { A.x = i; A.y = g; A.z = i ^ g; A.w = i + g; B = A; }
+    else { A = CB_PHILOX(0); B = CB_PHILOX(1); }
+    const uint32_t xa[4] = { A.x, A.y, A.z, A.w };
+    const uint32_t T0 = p.tbl[0], T1 = p.tbl[1], T2 = p.tbl[2];
+    uint32_t m[4] = { 0u, 0u, 0u, 0u }, need = 0;
+    if (!(skip & 2)) {
+        if (OPT & 1) {
+            uint32_t n3 = 0; uint64_t dups = 0;
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                // static slots at bit offsets 10w and 10w+5 of S = B.x | B.y << 32; only the low 5 bits of a shift count
+                // are used, so a slot is extracted by one high-multiply (FMA pipe) wherever it does not straddle
+                uint32_t q[2];
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int off = 10 * w + 5 * j;
+                    if (off == 0) q[j] = B.x;
+                    else if (off + 5 <= 32) q[j] = __umulhi(B.x, p.one << (32 - off));
+                    else if (off >= 32) q[j] = off == 32 ? B.y : __umulhi(B.y, p.one << (64 - off));
+                    else q[j] = __funnelshift_r(B.x, B.y, off);
+                }
+                const uint32_t b0 = 1u << (q[0] & 31u), b1 = 1u << (q[1] & 31u);
+                const uint32_t ge1 = gt_carry(xa[w], p.one, ~T0, 0u), ge2 = gt_carry(xa[w], p.one, ~T1, 0u);
+                n3 = gt_carry(xa[w], p.one, ~T2, n3);
+                m[w] = ge2 * b1 + ge1 * b0;                  // wrong only when ge2 and b0 == b1: rebuilt in the slow region
+                dups += (uint64_t)ge2 * (b0 & b1);
             }
-            P1[w] = m;
+            if (n3 | (uint32_t)dups | (uint32_t)(dups >> 32)) {   // rare per task: find the words that need a third draw
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const int o0 = 10 * w, o1 = 10 * w + 5;
+                    const uint32_t q0 = o0 < 32 ? __funnelshift_r(B.x, B.y, o0) : B.y >> (o0 - 32);
+                    const uint32_t q1 = o1 < 32 ? __funnelshift_r(B.x, B.y, o1) : B.y >> (o1 - 32);
+                    const uint32_t b0 = 1u << (q0 & 31u), b1 = 1u << (q1 & 31u);
+                    const bool ge2 = xa[w] > T1, ge3 = xa[w] > T2;
+                    if (ge2) m[w] = b0 | b1;
+                    need |= (ge3 || (ge2 && b0 == b1)) ? (1u << w) : 0u;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const uint32_t q0 = 10 * w < 32 ? __funnelshift_r(B.x, B.y, 10 * w) : B.y >> (10 * w - 32);
+                const uint32_t q1 = 10 * w + 5 < 32 ? __funnelshift_r(B.x, B.y, 10 * w + 5) : B.y >> (10 * w + 5 - 32);
+                const uint32_t b0 = 1u << (q0 & 31u), b1 = 1u << (q1 & 31u);
+                const bool ge1 = xa[w] > T0, ge2 = xa[w] > T1, ge3 = xa[w] > T2;
+                m[w] = (ge1 ? b0 : 0u) | (ge2 ? b1 : 0u);
+                need |= (ge3 || (ge2 && b0 == b1)) ? (1u << w) : 0u;   // a third draw is due: overflow stream
+            }
         }
     }
-
-    // ---- spin-dependent part. p.zero is always 0: the data dependency keeps the loads in flight behind the RNG phase.
+    cbs_stream st; st.y0 = B.y >> 8; st.y1 = 0u; st.left = 3; st.call = 2;   // S >> 40
+    auto slot = [&]() -> uint32_t {     // next 7-bit slot of the task's overflow stream
+        if (st.left == 0) {
+            const uint2 r = cbs_refill(st.call | p.t_hi16, c1, c2, p.t_lo, p.rk[0][0], p.rk[0][1]);
+            st.call++; st.y0 = r.x; st.y1 = r.y; st.left = 9;
+        }
+        const uint32_t v = st.y0 & 127u;
+        st.y0 = __funnelshift_r(st.y0, st.y1, 7); st.y1 >>= 7; st.left--;
+        return v;
+    };
+    if (need) {
 #pragma unroll
-    for (int w = 0; w < 4; w++) sc[w] ^= P1[w] & p.zero;
-    uint32_t mc[4][3], fl[4];
-#pragma unroll
-    for (int w = 0; w < 4; w++) {
-        uint32_t u0, u1, u2;
-        unsat_planes<D>(sc[w], sn[w], jc, u0, u1, u2);
-        class_masks<D>(u0, u1, u2, mc[w]);
-        fl[w] = ~(mc[w][0] | mc[w][1] | mc[w][2]) | (mc[w][0] & P1[w]);
+        for (int w = 0; w < 4; w++)
+            if (need & (1u << w)) {
+                uint32_t mm = m[w]; int s = __popc(mm);
+                while (xa[w] > p.tbl[s]) {  // tbl[32] = 2^32-1 ends the scan
+                    const uint32_t nm = mm | (1u << (slot() & 31u));
+                    s += nm != mm;          // a duplicate position is redrawn
+                    mm = nm;
+                }
+                m[w] = mm;
+            }
     }
-    // classes 2..D: rare at the temperatures where this procedure is selected
-    if (D >= 2) {
-        const uint32_t xc[2] = { B.z, B.w };
+
+    // ---- spin-dependent part
+    uint32_t fl[4];
 #pragma unroll
-        for (int c = 2; c <= D; c++) {
-            const uint32_t *T = p.tbl + CBS_T1 + (c - 2) * CBS_TC;
-            if (xc[c - 2] > T[0]) {
-                uint32_t m[4] = { 0u, 0u, 0u, 0u };
+    for (int w = 0; w < 4; w++) fl[w] = (skip & 4) ? (m[w] ^ sn[w][0]) : cbs_flip_word<D>(sc[w], sn[w], neg, m[w]);
+    if (D >= 2) {   // classes 2..D: rare at the temperatures where this procedure is selected
+        const uint32_t xc[2] = { B.z, B.w };
+        bool rare = xc[0] > p.tbl[CBS_T1];
+        if (D == 3) rare = rare || xc[1] > p.tbl[CBS_T1 + CBS_TC];
+        if (rare && !(skip & 2)) {
+#pragma unroll
+            for (int c = 2; c <= D; c++) {
+                const uint32_t *T = p.tbl + CBS_T1 + (c - 2) * CBS_TC;
+                uint32_t pm[4] = { 0u, 0u, 0u, 0u };
                 int s = 0;
                 while (xc[c - 2] > T[s]) {  // T[128] = 2^32-1
                     const uint32_t pos = slot();
@@ -430,11 +561,16 @@ __global__ void __launch_bounds__(256, MINB) k_checkerboard_sparse(const __grid_
                     const int ww = (int)(pos >> 5);
                     bool dup = false;
 #pragma unroll
-                    for (int w = 0; w < 4; w++) if (w == ww) { dup = (m[w] & bit) != 0; m[w] |= bit; }
+                    for (int w = 0; w < 4; w++) if (w == ww) { dup = (pm[w] & bit) != 0; pm[w] |= bit; }
                     s += !dup;
                 }
 #pragma unroll
-                for (int w = 0; w < 4; w++) fl[w] |= mc[w][c - 1] & m[w];
+                for (int w = 0; w < 4; w++) {
+                    uint32_t u0, u1, u2, mc[3];
+                    unsat_planes_neg<D>(sc[w], sn[w], neg, u0, u1, u2);
+                    class_masks<D>(u0, u1, u2, mc);
+                    fl[w] |= mc[c - 1] & pm[w];
+                }
             }
         }
     }
@@ -444,7 +580,6 @@ __global__ void __launch_bounds__(256, MINB) k_checkerboard_sparse(const __grid_
         sc[w] ^= fl[w];
     }
     if (FULL) {
-        const uint32_t W4 = W >> 2;
         reinterpret_cast<uint4 *>(p.spins)[i * W4 + g] = make_uint4(sc[0], sc[1], sc[2], sc[3]);
         if (p.flips) reinterpret_cast<uint4 *>(p.flips)[i * W4 + g] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
     } else {
@@ -462,15 +597,17 @@ rrrmc_status_t launch_checkerboard_sparse(rrrmc_ctx *ctx, const cbs_params &p, i
 {
     const bool full = (p.W % 4) == 0;
     dim3 block(256), grid(div_up((int64_t)p.Lh * p.G, 256), D >= 2 ? p.L : 1, D >= 3 ? p.L : 1);
-#define LAUNCH(DD, FF, MB) k_checkerboard_sparse<DD, FF, MB><<<grid, block, 0, ctx->stream>>>(p, colour)
-    if (D == 1) { if (full) LAUNCH(1, true, 1); else LAUNCH(1, false, 1); }
-    else if (D == 2) { if (full) LAUNCH(2, true, 1); else LAUNCH(2, false, 1); }
+#define LAUNCH(DD, FF, MB, OP) k_checkerboard_sparse<DD, FF, MB, OP><<<grid, block, 0, ctx->stream>>>(p, colour)
+    if (D == 1) { if (full) LAUNCH(1, true, 1, 0); else LAUNCH(1, false, 1, 0); }
+    else if (D == 2) { if (full) LAUNCH(2, true, 1, 0); else LAUNCH(2, false, 1, 0); }
     else if (D == 3) {
-        if (!full) LAUNCH(3, false, 1);
-        else if ((p.variant & 7) == 1) LAUNCH(3, true, 4);
-        else if ((p.variant & 7) == 2) LAUNCH(3, true, 6);
-        else if ((p.variant & 7) == 3) LAUNCH(3, true, 8);
-        else LAUNCH(3, true, 5);
+        if (!full) LAUNCH(3, false, 1, 0);
+        else switch (p.variant & 3) {
+            case 1: LAUNCH(3, true, 4, 1); break;
+            case 2: LAUNCH(3, true, 4, 2); break;
+            case 3: LAUNCH(3, true, 4, 3); break;
+            default: LAUNCH(3, true, 4, 0); break;
+        }
     }
     else { rrrmc_set_error("checkerboard: D=%d unsupported (1..3)", D); return RRRMC_ERR_UNSUPPORTED; }
 #undef LAUNCH
