@@ -34,6 +34,7 @@ struct cbs_params {
     const uint8_t *jcode;   // [N]
     const uint4 *jmask;     // [N][2]: whole-word sign masks of the six bonds of a site (api.cu)
     int L, Lh, W, G;
+    int tpr;                // row-chunk kernel: threads per lattice row = (Lh/T)*G (set by the launcher)
     uint32_t t_lo, t_hi16;
     uint32_t rk[10][2];     // Philox round keys
     uint32_t one;           // always 1, opaque to ptxas: keeps compare-by-carry multiplies on the FMA pipe

@@ -392,19 +392,94 @@ __device__ __forceinline__ uint32_t cbs_flip_word(uint32_t sc, const uint32_t (&
     return lop3<LUT_MAJ>(k1, k2, f1) | f2;
 }
 
-// acc + [x > T] as the carry of x·1 + ~T into the high word of a 64-bit multiply-add: a compare on the FMA pipe
-__device__ __forceinline__ uint32_t gt_carry(uint32_t x, uint32_t one, uint32_t notT, uint32_t acc)
-{
-    uint64_t t;
-    const uint64_t c = ((uint64_t)acc << 32) | notT;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(t) : "r"(x), "r"(one), "l"(c));
-    return (uint32_t)(t >> 32);
-}
-
 #define CB_PHILOX(ctr0) philox4x32_10_rk((uint32_t)(ctr0) | p.t_hi16, c1, c2, p.t_lo, p)
-// OPT bit 0: class-1 counts compared on the FMA pipe (gt_carry) instead of ISETP/SEL on the ALU pipe
-// OPT bit 1: bond sign masks loaded from jmask instead of expanded from jcode bits
-template <int D, bool FULL, int MINB, int OPT>
+// One task of the sparse procedure: the flip masks fl[4] of (site c1, group c2) from the centre words sc, the
+// neighbour words sn and the bond sign masks neg. Shared by the generic and the row-chunk kernels.
+template <int D>
+__device__ __forceinline__ void cbs_task(const cbs_params &p, uint32_t c1, uint32_t c2, const uint32_t (&sc)[4],
+                                         const uint32_t (&sn)[4][2 * D], const uint32_t (&neg)[2 * D], uint32_t (&fl)[4])
+{
+    const int skip = p.variant >> 4;   // timing experiments only (tune_cb.py): bit 0 Philox, bit 1 class-1, bit 2 ΔE logic
+    // ---- spin-independent part: the sets of passing lanes of class 1
+    philox_out A, B;
+    if (skip & 1) { A.x = c1; A.y = c2; A.z = c1 ^ c2; A.w = c1 + c2; B = A; }
+    else { A = CB_PHILOX(0); B = CB_PHILOX(1); }
+    const uint32_t xa[4] = { A.x, A.y, A.z, A.w };
+    const uint32_t T0 = p.tbl[0], T1 = p.tbl[1], T2 = p.tbl[2];
+    uint32_t m[4] = { 0u, 0u, 0u, 0u }, need = 0;
+    if (!(skip & 2)) {
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            // static slots: bit offsets 10w and 10w+5 of S = B.x | B.y << 32
+            const uint32_t q0 = 10 * w < 32 ? __funnelshift_r(B.x, B.y, 10 * w) : B.y >> (10 * w - 32);
+            const uint32_t q1 = 10 * w + 5 < 32 ? __funnelshift_r(B.x, B.y, 10 * w + 5) : B.y >> (10 * w + 5 - 32);
+            const uint32_t b0 = 1u << (q0 & 31u), b1 = 1u << (q1 & 31u);
+            const bool ge1 = xa[w] > T0, ge2 = xa[w] > T1, ge3 = xa[w] > T2;
+            m[w] = (ge1 ? b0 : 0u) | (ge2 ? b1 : 0u);
+            need |= (ge3 || (ge2 && b0 == b1)) ? (1u << w) : 0u;   // a third draw is due: overflow stream
+        }
+    }
+    cbs_stream st; st.y0 = B.y >> 8; st.y1 = 0u; st.left = 3; st.call = 2;   // S >> 40
+    auto slot = [&]() -> uint32_t {     // next 7-bit slot of the task's overflow stream
+        if (st.left == 0) {
+            const uint2 r = cbs_refill(st.call | p.t_hi16, c1, c2, p.t_lo, p.rk[0][0], p.rk[0][1]);
+            st.call++; st.y0 = r.x; st.y1 = r.y; st.left = 9;
+        }
+        const uint32_t v = st.y0 & 127u;
+        st.y0 = __funnelshift_r(st.y0, st.y1, 7); st.y1 >>= 7; st.left--;
+        return v;
+    };
+    if (need) {
+#pragma unroll
+        for (int w = 0; w < 4; w++)
+            if (need & (1u << w)) {
+                uint32_t mm = m[w]; int s = __popc(mm);
+                while (xa[w] > p.tbl[s]) {  // tbl[32] = 2^32-1 ends the scan
+                    const uint32_t nm = mm | (1u << (slot() & 31u));
+                    s += nm != mm;          // a duplicate position is redrawn
+                    mm = nm;
+                }
+                m[w] = mm;
+            }
+    }
+    // ---- spin-dependent part
+#pragma unroll
+    for (int w = 0; w < 4; w++) fl[w] = (skip & 4) ? (m[w] ^ sn[w][0]) : cbs_flip_word<D>(sc[w], sn[w], neg, m[w]);
+    if (D >= 2) {   // classes 2..D: rare at the temperatures where this procedure is selected
+        const uint32_t xc[2] = { B.z, B.w };
+        bool rare = xc[0] > p.tbl[CBS_T1];
+        if (D == 3) rare = rare || xc[1] > p.tbl[CBS_T1 + CBS_TC];
+        if (rare && !(skip & 2)) {
+            uint32_t pm[2][4] = { { 0u, 0u, 0u, 0u }, { 0u, 0u, 0u, 0u } };
+#pragma unroll
+            for (int c = 2; c <= D; c++) {
+                const uint32_t *T = p.tbl + CBS_T1 + (c - 2) * CBS_TC;
+                int s = 0;
+                while (xc[c - 2] > T[s]) {  // T[128] = 2^32-1
+                    const uint32_t pos = slot();
+                    const uint32_t bit = 1u << (pos & 31u);
+                    const int ww = (int)(pos >> 5);
+                    bool dup = false;
+#pragma unroll
+                    for (int w = 0; w < 4; w++) if (w == ww) { dup = (pm[c - 2][w] & bit) != 0; pm[c - 2][w] |= bit; }
+                    s += !dup;
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < 4; w++)
+                if (pm[0][w] | pm[1][w]) {   // the ΔE planes are rebuilt only for the words that drew a position
+                    uint32_t u0, u1, u2, mc[3];
+                    unsat_planes_neg<D>(sc[w], sn[w], neg, u0, u1, u2);
+                    class_masks<D>(u0, u1, u2, mc);
+                    fl[w] |= (mc[1] & pm[0][w]) | (mc[2] & pm[1][w]);
+                }
+        }
+    }
+}
+#undef CB_PHILOX
+
+// generic kernel: one task per thread, any D <= 3, any R (multiple of 32)
+template <int D, bool FULL, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_checkerboard_sparse(const __grid_constant__ cbs_params p, int colour)
 {
     const int row_tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -451,129 +526,12 @@ __global__ void __launch_bounds__(256, MINB) k_checkerboard_sparse(const __grid_
         }
     }
     uint32_t neg[2 * D];
-    if (OPT & 2) {
-        const uint4 a = p.jmask[2 * i];
-        neg[0] = a.x; neg[1] = a.y;
-        if (D >= 2) { neg[2] = a.z; neg[3] = a.w; }
-        if (D >= 3) { const uint2 c = reinterpret_cast<const uint2 *>(p.jmask)[4 * i + 2]; neg[4] = c.x; neg[5] = c.y; }
-    } else {
-        const uint32_t jc = p.jcode[i];
+    const uint32_t jc = p.jcode[i];
 #pragma unroll
-        for (int k = 0; k < 2 * D; k++) neg[k] = 0u - ((jc >> k) & 1u);
-    }
-    const uint32_t c1 = i, c2 = (uint32_t)g;
-    const int skip = p.variant >> 4;   // timing experiments only (tune_cb.py): bit 0 Philox, bit 1 class-1, bit 2 ΔE logic
+    for (int k = 0; k < 2 * D; k++) neg[k] = 0u - ((jc >> k) & 1u);
 
-    // ---- spin-independent part: the sets of passing lanes of class 1
-    philox_out A, B;
-    if (skip & 1) { A.x = i; A.y = g; A.z = i ^ g; A.w = i + g; B = A; }
-    else { A = CB_PHILOX(0); B = CB_PHILOX(1); }
-    const uint32_t xa[4] = { A.x, A.y, A.z, A.w };
-    const uint32_t T0 = p.tbl[0], T1 = p.tbl[1], T2 = p.tbl[2];
-    uint32_t m[4] = { 0u, 0u, 0u, 0u }, need = 0;
-    if (!(skip & 2)) {
-        if (OPT & 1) {
-            uint32_t n3 = 0; uint64_t dups = 0;
-#pragma unroll
-            for (int w = 0; w < 4; w++) {
-                // static slots at bit offsets 10w and 10w+5 of S = B.x | B.y << 32; only the low 5 bits of a shift count
-                // are used, so a slot is extracted by one high-multiply (FMA pipe) wherever it does not straddle
-                uint32_t q[2];
-#pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    const int off = 10 * w + 5 * j;
-                    if (off == 0) q[j] = B.x;
-                    else if (off + 5 <= 32) q[j] = __umulhi(B.x, p.one << (32 - off));
-                    else if (off >= 32) q[j] = off == 32 ? B.y : __umulhi(B.y, p.one << (64 - off));
-                    else q[j] = __funnelshift_r(B.x, B.y, off);
-                }
-                const uint32_t b0 = 1u << (q[0] & 31u), b1 = 1u << (q[1] & 31u);
-                const uint32_t ge1 = gt_carry(xa[w], p.one, ~T0, 0u), ge2 = gt_carry(xa[w], p.one, ~T1, 0u);
-                n3 = gt_carry(xa[w], p.one, ~T2, n3);
-                m[w] = ge2 * b1 + ge1 * b0;                  // wrong only when ge2 and b0 == b1: rebuilt in the slow region
-                dups += (uint64_t)ge2 * (b0 & b1);
-            }
-            if (n3 | (uint32_t)dups | (uint32_t)(dups >> 32)) {   // rare per task: find the words that need a third draw
-#pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    const int o0 = 10 * w, o1 = 10 * w + 5;
-                    const uint32_t q0 = o0 < 32 ? __funnelshift_r(B.x, B.y, o0) : B.y >> (o0 - 32);
-                    const uint32_t q1 = o1 < 32 ? __funnelshift_r(B.x, B.y, o1) : B.y >> (o1 - 32);
-                    const uint32_t b0 = 1u << (q0 & 31u), b1 = 1u << (q1 & 31u);
-                    const bool ge2 = xa[w] > T1, ge3 = xa[w] > T2;
-                    if (ge2) m[w] = b0 | b1;
-                    need |= (ge3 || (ge2 && b0 == b1)) ? (1u << w) : 0u;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int w = 0; w < 4; w++) {
-                const uint32_t q0 = 10 * w < 32 ? __funnelshift_r(B.x, B.y, 10 * w) : B.y >> (10 * w - 32);
-                const uint32_t q1 = 10 * w + 5 < 32 ? __funnelshift_r(B.x, B.y, 10 * w + 5) : B.y >> (10 * w + 5 - 32);
-                const uint32_t b0 = 1u << (q0 & 31u), b1 = 1u << (q1 & 31u);
-                const bool ge1 = xa[w] > T0, ge2 = xa[w] > T1, ge3 = xa[w] > T2;
-                m[w] = (ge1 ? b0 : 0u) | (ge2 ? b1 : 0u);
-                need |= (ge3 || (ge2 && b0 == b1)) ? (1u << w) : 0u;   // a third draw is due: overflow stream
-            }
-        }
-    }
-    cbs_stream st; st.y0 = B.y >> 8; st.y1 = 0u; st.left = 3; st.call = 2;   // S >> 40
-    auto slot = [&]() -> uint32_t {     // next 7-bit slot of the task's overflow stream
-        if (st.left == 0) {
-            const uint2 r = cbs_refill(st.call | p.t_hi16, c1, c2, p.t_lo, p.rk[0][0], p.rk[0][1]);
-            st.call++; st.y0 = r.x; st.y1 = r.y; st.left = 9;
-        }
-        const uint32_t v = st.y0 & 127u;
-        st.y0 = __funnelshift_r(st.y0, st.y1, 7); st.y1 >>= 7; st.left--;
-        return v;
-    };
-    if (need) {
-#pragma unroll
-        for (int w = 0; w < 4; w++)
-            if (need & (1u << w)) {
-                uint32_t mm = m[w]; int s = __popc(mm);
-                while (xa[w] > p.tbl[s]) {  // tbl[32] = 2^32-1 ends the scan
-                    const uint32_t nm = mm | (1u << (slot() & 31u));
-                    s += nm != mm;          // a duplicate position is redrawn
-                    mm = nm;
-                }
-                m[w] = mm;
-            }
-    }
-
-    // ---- spin-dependent part
     uint32_t fl[4];
-#pragma unroll
-    for (int w = 0; w < 4; w++) fl[w] = (skip & 4) ? (m[w] ^ sn[w][0]) : cbs_flip_word<D>(sc[w], sn[w], neg, m[w]);
-    if (D >= 2) {   // classes 2..D: rare at the temperatures where this procedure is selected
-        const uint32_t xc[2] = { B.z, B.w };
-        bool rare = xc[0] > p.tbl[CBS_T1];
-        if (D == 3) rare = rare || xc[1] > p.tbl[CBS_T1 + CBS_TC];
-        if (rare && !(skip & 2)) {
-#pragma unroll
-            for (int c = 2; c <= D; c++) {
-                const uint32_t *T = p.tbl + CBS_T1 + (c - 2) * CBS_TC;
-                uint32_t pm[4] = { 0u, 0u, 0u, 0u };
-                int s = 0;
-                while (xc[c - 2] > T[s]) {  // T[128] = 2^32-1
-                    const uint32_t pos = slot();
-                    const uint32_t bit = 1u << (pos & 31u);
-                    const int ww = (int)(pos >> 5);
-                    bool dup = false;
-#pragma unroll
-                    for (int w = 0; w < 4; w++) if (w == ww) { dup = (pm[w] & bit) != 0; pm[w] |= bit; }
-                    s += !dup;
-                }
-#pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    uint32_t u0, u1, u2, mc[3];
-                    unsat_planes_neg<D>(sc[w], sn[w], neg, u0, u1, u2);
-                    class_masks<D>(u0, u1, u2, mc);
-                    fl[w] |= mc[c - 1] & pm[w];
-                }
-            }
-        }
-    }
+    cbs_task<D>(p, i, (uint32_t)g, sc, sn, neg, fl);
 #pragma unroll
     for (int w = 0; w < 4; w++) {
         if (!FULL && !(4 * g + w < W)) fl[w] = 0;
@@ -591,26 +549,98 @@ __global__ void __launch_bounds__(256, MINB) k_checkerboard_sparse(const __grid_
             }
     }
 }
-#undef CB_PHILOX
 
-rrrmc_status_t launch_checkerboard_sparse(rrrmc_ctx *ctx, const cbs_params &p, int D, int colour)
+// Row-chunk kernel (3D, R a multiple of 128): the kernel is bound by integer instruction issue, and a third of a
+// one-task thread is index arithmetic, address formation and parameter loads. Here a thread owns T consecutive
+// sites of the active colour along x for one replica group: the row geometry is computed once, task j's addresses
+// are the chunk base plus compile-time offsets (W4C = words-per-site/4 known at compile time), and the x+1
+// neighbour of task j is kept in registers as the x-1 neighbour of task j+1 (six loads per task instead of seven).
+// Tasks are the same (site, group) tasks as in the generic kernel: results are identical bit for bit.
+template <int T, int W4C, int MINB>
+__global__ void __launch_bounds__(64, MINB) k_checkerboard_sparse_row(const __grid_constant__ cbs_params p, int colour)
+{
+    constexpr int D = 3;
+    const int rt = blockIdx.x * blockDim.x + threadIdx.x;      // (chunk, group) within the row
+    if (rt >= p.tpr) return;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z;
+    int c, g;
+    if (p.Gshift >= 0) { c = rt >> p.Gshift; g = rt & (p.G - 1); }
+    else { c = rt / p.G; g = rt - c * p.G; }
+    const int L = p.L;
+    const int W4 = W4C ? W4C : (p.W >> 2);
+    const int x0 = 2 * c * T + ((y + z + colour) & 1);
+    const uint32_t i0 = (uint32_t)L * (uint32_t)(y + L * z) + x0;
+    // neighbour displacements in sites
+    const int dyp = y + 1 == L ? -(L - 1) * L : L, dym = y == 0 ? (L - 1) * L : -L;
+    const int dzp = z + 1 == L ? -(L - 1) * L * L : L * L, dzm = z == 0 ? (L - 1) * L * L : -L * L;
+    const int dxm0 = x0 == 0 ? L - 1 : -1;                       // x-1 of the first task
+    const int dxpl = x0 + 2 * T - 1 == L ? -(L - 1) : 1;         // x+1 of the last task, relative to that task's site
+    uint4 *P = reinterpret_cast<uint4 *>(p.spins) + ((size_t)i0 * W4 + g);
+    const uint4 *Pyp = P + (ptrdiff_t)dyp * W4, *Pym = P + (ptrdiff_t)dym * W4;
+    const uint4 *Pzp = P + (ptrdiff_t)dzp * W4, *Pzm = P + (ptrdiff_t)dzm * W4;
+    const uint4 *JM = p.jmask + 2 * (size_t)i0;
+    uint4 xm = P[(ptrdiff_t)dxm0 * W4];
+#pragma unroll
+    for (int j = 0; j < T; j++) {
+        const int o = 2 * j * W4;
+        const uint4 ce = P[o];
+        const uint4 xp = j == T - 1 ? P[o + (ptrdiff_t)dxpl * W4] : P[o + W4];
+        const uint4 yp = Pyp[o], ym = Pym[o], zp = Pzp[o], zm = Pzm[o];
+        const uint4 ja = JM[4 * j];
+        const uint2 jb = reinterpret_cast<const uint2 *>(JM)[8 * j + 2];
+        const uint32_t neg[6] = { ja.x, ja.y, ja.z, ja.w, jb.x, jb.y };
+        uint32_t sc[4] = { ce.x, ce.y, ce.z, ce.w };
+        const uint32_t sn[4][6] = { { xp.x, xm.x, yp.x, ym.x, zp.x, zm.x }, { xp.y, xm.y, yp.y, ym.y, zp.y, zm.y },
+                                    { xp.z, xm.z, yp.z, ym.z, zp.z, zm.z }, { xp.w, xm.w, yp.w, ym.w, zp.w, zm.w } };
+        uint32_t fl[4];
+        cbs_task<D>(p, i0 + 2 * j, (uint32_t)g, sc, sn, neg, fl);
+        P[o] = make_uint4(sc[0] ^ fl[0], sc[1] ^ fl[1], sc[2] ^ fl[2], sc[3] ^ fl[3]);
+        if (p.flips) (reinterpret_cast<uint4 *>(p.flips) + ((size_t)i0 * W4 + g))[o] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+        xm = xp;
+        asm volatile("" ::: "memory");   // keep the tasks of a thread in order (registers, not latency, are the constraint)
+    }
+}
+
+template <int T, int W4C>
+static void launch_row(const cbs_params &p, int colour, cudaStream_t stream)
+{
+    // 64-thread blocks: bx threads along the row (chunks x groups), by rows
+    int bx = p.tpr >= 64 ? 64 : p.tpr, by = 1;
+    if (p.tpr < 64) { by = 64 / p.tpr; while (by > 1 && p.L % by) by--; }
+    dim3 block(bx, by), grid(div_up(p.tpr, bx), p.L / by, p.L);
+    if (p.variant & 4) k_checkerboard_sparse_row<T, W4C, 16><<<grid, block, 0, stream>>>(p, colour);
+    else k_checkerboard_sparse_row<T, W4C, 12><<<grid, block, 0, stream>>>(p, colour);
+}
+
+rrrmc_status_t launch_checkerboard_sparse(rrrmc_ctx *ctx, cbs_params &p, int D, int colour)
 {
     const bool full = (p.W % 4) == 0;
-    dim3 block(256), grid(div_up((int64_t)p.Lh * p.G, 256), D >= 2 ? p.L : 1, D >= 3 ? p.L : 1);
-#define LAUNCH(DD, FF, MB, OP) k_checkerboard_sparse<DD, FF, MB, OP><<<grid, block, 0, ctx->stream>>>(p, colour)
-    if (D == 1) { if (full) LAUNCH(1, true, 1, 0); else LAUNCH(1, false, 1, 0); }
-    else if (D == 2) { if (full) LAUNCH(2, true, 1, 0); else LAUNCH(2, false, 1, 0); }
-    else if (D == 3) {
-        if (!full) LAUNCH(3, false, 1, 0);
-        else switch (p.variant & 3) {
-            case 1: LAUNCH(3, true, 4, 1); break;
-            case 2: LAUNCH(3, true, 4, 2); break;
-            case 3: LAUNCH(3, true, 4, 3); break;
-            default: LAUNCH(3, true, 4, 0); break;
-        }
+    // row-chunk kernel: 3D, whole 128-replica groups, T | L/2. It wins when the rare paths are really rare (its
+    // unrolled body is four tasks long: at warmer temperatures the divergent regions start missing the instruction
+    // cache), so by default it is used when the class-1 count is zero for > 80 % of the words (32·p1 < 0.22).
+    // RRRMC_CB_VARIANT (tuning/tests): bits 0-1 force T = 2, 8, 4; bit 2: 16 blocks/SM; bit 3: force the generic kernel.
+    int T = 0;
+    if (D == 3 && full && !(p.variant & 8)) {
+        const int sel = p.variant & 3;
+        const int want = sel == 1 ? 2 : (sel == 2 ? 8 : 4);
+        if (sel != 0 || p.tbl[0] > 0xCCCCCCCCu)
+            for (int t = want; t >= 2; t >>= 1) if (p.Lh % t == 0) { T = t; break; }
     }
-    else { rrrmc_set_error("checkerboard: D=%d unsupported (1..3)", D); return RRRMC_ERR_UNSUPPORTED; }
+    if (T) {
+        p.tpr = (p.Lh / T) * p.G;
+        const bool w8 = p.W == 32;
+        if (T == 8) { if (w8) launch_row<8, 8>(p, colour, ctx->stream); else launch_row<8, 0>(p, colour, ctx->stream); }
+        else if (T == 4) { if (w8) launch_row<4, 8>(p, colour, ctx->stream); else launch_row<4, 0>(p, colour, ctx->stream); }
+        else { if (w8) launch_row<2, 8>(p, colour, ctx->stream); else launch_row<2, 0>(p, colour, ctx->stream); }
+    } else {
+        dim3 block(256), grid(div_up((int64_t)p.Lh * p.G, 256), D >= 2 ? p.L : 1, D >= 3 ? p.L : 1);
+#define LAUNCH(DD, FF, MB) k_checkerboard_sparse<DD, FF, MB><<<grid, block, 0, ctx->stream>>>(p, colour)
+        if (D == 1) { if (full) LAUNCH(1, true, 1); else LAUNCH(1, false, 1); }
+        else if (D == 2) { if (full) LAUNCH(2, true, 1); else LAUNCH(2, false, 1); }
+        else if (D == 3) { if (full) LAUNCH(3, true, 4); else LAUNCH(3, false, 1); }
+        else { rrrmc_set_error("checkerboard: D=%d unsupported (1..3)", D); return RRRMC_ERR_UNSUPPORTED; }
 #undef LAUNCH
+    }
     ctx->launches++;
     RR_CUDA(cudaGetLastError());
     return RRRMC_OK;
