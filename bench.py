@@ -67,7 +67,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -134,7 +134,7 @@ def run_reference(args, rank, world):
     import rrrmc_b200 as rb  # host-side lattice helpers only (no device needed)
     A, J = synthetic_instance()
     cores = os.cpu_count() or 1
-    iters = 6_000_000  # per thread per step: a bounded sample of the workload (full step = 2.7e10 attempts/replica batch)
+    iters = 20_000_000  # per thread per step (~2 s): a bounded sample of the workload (a full step is 1.07e11 attempts per GPU)
     for _ in range(max(0, args.warmup)):
         cpu_reference_rate(A, J, 200_000, cores)
     rates, t_tot = [], 0.0
@@ -146,7 +146,10 @@ def run_reference(args, rank, world):
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u32 bit-sliced / int64 local fields", "data": "synthetic",
-           "config": {"workload": "EA3D L=64 ±J standardMC (reference algorithm, CPU)", "L": L, "D": D, "beta": BETA},
+           "config": {"workload": "GraphEA 3D L=64 ±J, checkerboard Metropolis, 1024 replicas per GPU (BASELINE configs[1])",
+                      "L": L, "D": D, "replicas_per_gpu": R_PER_GPU, "beta": BETA,
+                      "reference_sampler": "standardMC (random-site Metropolis, RRRMC.jl:81-127) — the reference has no checkerboard schedule; "
+                                           "one replica per host thread, bounded sample per step"},
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0,
@@ -270,7 +273,7 @@ def run_ours(args, rank, world, local_rank):
             except Exception:
                 traffic = None
         cores = os.cpu_count() or 1
-        cpu_iters = 4_000_000
+        cpu_iters = 100_000_000  # ~10 s on the box's host cores
         cpu_v, cpu_dt = cpu_reference_rate(A, J, cpu_iters, cores)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
