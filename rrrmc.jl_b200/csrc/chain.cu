@@ -16,57 +16,6 @@
 #include "kernels.cuh"
 #include "philox.cuh"
 
-constexpr int MAXL = 16;  // |allΔE| supported by the discrete cache
-constexpr int MAXDEG = 8; // neighbours of a discrete graph on this path: 2D <= 8 (EA), 2 (QT)
-constexpr unsigned FULLMASK = 0xffffffffu;
-
-struct chain_hdr {
-    double E, acc_rate, z, pdE;
-    double T[2 * MAXL + 1];
-    long long it, accepted, staged_its, nextstep, skip, rng_n;
-    int t[2 * MAXL + 1];
-    int pending, pmove, status, built, trefresh, done;
-};
-
-struct chain_store {
-    int64_t R = 0, N = 0, N2 = 0;
-    int levs = 0, nDE = 0;
-    bool f64 = false;             // fp64 local fields (EA F64, SK F64, QUANT over SK F64)
-    bool cont_ready = false, disc_ready = false;
-    int32_t *lfi = nullptr;       // [R][2][N] (EA: cur,last; SK family: per slice [2][Nk])
-    double *lfd = nullptr;
-    int32_t *ml = nullptr;        // [R][M] move_last per slice (0-based, -1 = none)
-    uint8_t *sw = nullptr;        // [R][M] SK family: which half of the slice's field pair is current
-    chain_hdr *hdr = nullptr;
-    int32_t *av = nullptr, *apos = nullptr;
-    uint8_t *cls = nullptr;
-    double *dEs = nullptr, *dv = nullptr, *dps = nullptr;
-    int32_t *csj = nullptr; double *csdE = nullptr, *csp = nullptr; // staged list of the continuous cache [R][N+1]
-    double *d_Es = nullptr; int64_t Es_rows = 0;
-    double *d_DE = nullptr, *d_beta = nullptr, *d_E = nullptr, *d_aux = nullptr; int64_t aux_len = 0;
-    uint8_t *d_tkind = nullptr; int64_t *d_tival = nullptr; double *d_tfval = nullptr; int64_t tcap = 0;
-};
-
-struct chain_params {
-    int kind, N, twoD, sampler, nDE, levs, cpw, coop;
-    int Nk, M, inner;
-    double fourK, sN;
-    int64_t R, N2, nchunks, chain0;
-    const int32_t *A; const int8_t *J8; const double *Jd; const uint8_t *Jb;
-    uint64_t *chunks;
-    int32_t *lfi; double *lfd; int32_t *ml; uint8_t *sw;
-    chain_hdr *hdr;
-    int32_t *av, *apos; uint8_t *cls;
-    double *dEs, *dv, *dps;
-    int32_t *csj; double *csdE, *csp;
-    const double *DE, *beta;
-    double *Es; int64_t Es_rows, quota;
-    long long iters, step;
-    uint64_t seed;
-    double staged_thr, staged_thr_fact;
-    const uint8_t *tkind; const int64_t *tival; const double *tfval; int64_t tlen;
-};
-
 // ------------------------------------------------------------------------------------------------
 // draw sources
 // ------------------------------------------------------------------------------------------------
@@ -841,6 +790,7 @@ void chain_free(rrrmc_state *s)
     cudaFree(c->csj); cudaFree(c->csdE); cudaFree(c->csp);
     cudaFree(c->d_Es); cudaFree(c->d_DE); cudaFree(c->d_beta); cudaFree(c->d_E); cudaFree(c->d_aux);
     cudaFree(c->d_tkind); cudaFree(c->d_tival); cudaFree(c->d_tfval);
+    cudaFree(c->ea_lf); cudaFree(c->ea_apos); cudaFree(c->ea_av);
     delete c;
     s->chain = nullptr;
 }
@@ -1068,7 +1018,7 @@ static rrrmc_status_t chain_drive(rrrmc_state *s, chain_params &P, rrrmc_hook_fn
     RR_CUDA(cudaEventRecord(e0, ctx->stream));
     int64_t nsamples = 0; bool stop = false;
     for (int guard = 0; !stop; guard++) {
-        k_chain_run<SRC><<<grid, 32, 0, ctx->stream>>>(P);
+        if (P.fast) RR_TRY(chain_ea_launch(s, P)); else k_chain_run<SRC><<<grid, 32, 0, ctx->stream>>>(P);
         ctx->launches++;
         s->ms_valid = false; s->chain_valid = true; // the chains own the configuration (a hook may have re-synced)
         RR_CUDA(cudaGetLastError());
@@ -1141,6 +1091,7 @@ rrrmc_status_t chain_run(rrrmc_state *s, int sampler, const double *beta, int64_
     RR_TRY(chain_energy_init(s, P, true));
     s->ms_valid = false; // chains now own the configuration
     sk_dense_invalidate(s);
+    if (chain_ea_eligible(s, sampler)) { RR_TRY(chain_ea_prepare(s, P)); s->chain_fields_valid = false; }
     RR_TRY(chain_drive<src_philox>(s, P, hook, user, Es, Es_cap, info));
     return RRRMC_OK;
 }

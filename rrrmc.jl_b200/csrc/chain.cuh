@@ -19,6 +19,69 @@ rrrmc_status_t chain_replay(rrrmc_state *s, int64_t replica, int sampler, double
                             const uint8_t *kind, const int64_t *ival, const double *fval, int64_t ndraws,
                             const rrrmc_opts_t *o, double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
 
+// ---- per-chain state shared by chain.cu and chain_ea.cu -------------------------------------------------------
+constexpr int MAXL = 16;  // |allΔE| supported by the discrete cache
+constexpr int MAXDEG = 8; // neighbours of a discrete graph on this path: 2D <= 8 (EA), 2 (QT)
+constexpr unsigned FULLMASK = 0xffffffffu;
+
+struct chain_hdr {
+    double E, acc_rate, z, pdE;
+    double T[2 * MAXL + 1];
+    long long it, accepted, staged_its, nextstep, skip, rng_n;
+    int t[2 * MAXL + 1];
+    int pending, pmove, status, built, trefresh, done;
+};
+
+struct chain_store {
+    int64_t R = 0, N = 0, N2 = 0;
+    int levs = 0, nDE = 0;
+    bool f64 = false;             // fp64 local fields (EA F64, SK F64, QUANT over SK F64)
+    bool cont_ready = false, disc_ready = false;
+    int32_t *lfi = nullptr;       // [R][2][N] (EA: cur,last; SK family: per slice [2][Nk])
+    double *lfd = nullptr;
+    int32_t *ml = nullptr;        // [R][M] move_last per slice (0-based, -1 = none)
+    uint8_t *sw = nullptr;        // [R][M] SK family: which half of the slice's field pair is current
+    chain_hdr *hdr = nullptr;
+    int32_t *av = nullptr, *apos = nullptr;
+    uint8_t *cls = nullptr;
+    double *dEs = nullptr, *dv = nullptr, *dps = nullptr;
+    int32_t *csj = nullptr; double *csdE = nullptr, *csp = nullptr; // staged list of the continuous cache [R][N+1]
+    double *d_Es = nullptr; int64_t Es_rows = 0;
+    double *d_DE = nullptr, *d_beta = nullptr, *d_E = nullptr, *d_aux = nullptr; int64_t aux_len = 0;
+    uint8_t *d_tkind = nullptr; int64_t *d_tival = nullptr; double *d_tfval = nullptr; int64_t tcap = 0;
+    // compact, L2-resident state of the GraphEA ±J fast path (chain_ea.cu)
+    int8_t *ea_lf = nullptr;      // [R][N] lfields (EA.jl:214), |value| <= 4D
+    uint16_t *ea_apos = nullptr;  // [R][N] 0-based position of a site inside its class set
+    uint16_t *ea_av = nullptr;    // [R][2L][N] class sets
+};
+
+struct chain_params {
+    int kind, N, twoD, sampler, nDE, levs, cpw, coop;
+    int Nk, M, inner;
+    double fourK, sN;
+    int64_t R, N2, nchunks, chain0;
+    const int32_t *A; const int8_t *J8; const double *Jd; const uint8_t *Jb;
+    uint64_t *chunks;
+    int32_t *lfi; double *lfd; int32_t *ml; uint8_t *sw;
+    chain_hdr *hdr;
+    int32_t *av, *apos; uint8_t *cls;
+    double *dEs, *dv, *dps;
+    int32_t *csj; double *csdE, *csp;
+    const double *DE, *beta;
+    double *Es; int64_t Es_rows, quota;
+    long long iters, step;
+    uint64_t seed;
+    double staged_thr, staged_thr_fact;
+    const uint8_t *tkind; const int64_t *tival; const double *tfval; int64_t tlen;
+    int fast;                     // 1: GraphEA ±J fast path (chain_ea.cu)
+    int8_t *ea_lf; uint16_t *ea_apos, *ea_av;
+};
+
+// GraphEA ±J fast path of rrrMC / bklMC (chain_ea.cu): same algorithm and draw stream as k_chain_run, compact state
+bool chain_ea_eligible(const rrrmc_state *s, int sampler);
+rrrmc_status_t chain_ea_prepare(rrrmc_state *s, chain_params &P);
+rrrmc_status_t chain_ea_launch(rrrmc_state *s, const chain_params &P);
+
 // dense GraphSKNormal kernels (sk_dense.cu): tensor-core local-field initialisation, lock-step Metropolis sweeps
 void sk_dense_free(rrrmc_state *s);
 void sk_dense_invalidate(rrrmc_state *s);

@@ -116,3 +116,47 @@ def test_per_replica_beta_on_chains():
         s = C0.chunks[r].copy()
         E, _ = ffi.standardMC(g, betas[r], 2000, s, ffi.PhiloxDraws(5, chain=r), step=500)
         assert np.array_equal(np.asarray(Es[:, r], np.float64), E) and np.array_equal(Cf.chunks[r], s)
+
+
+@pytest.mark.parametrize("sampler,ofn,iters", [("rrrMC", ffi.rrrMC, 6000), ("bklMC", ffi.bklMC, 60000)])
+@pytest.mark.parametrize("L,D", [(8, 3), (6, 2), (4, 1)])
+@pytest.mark.parametrize("generic", [False, True])
+def test_ea_fast_path_and_generic_kernel_agree_with_oracle(sampler, ofn, iters, L, D, generic, monkeypatch):
+    """GraphEA ±J runs rrrMC/bklMC on the compact-state kernel (chain_ea.cu); RRRMC_CHAIN_GENERIC forces the generic
+    one. Both must reproduce the oracle bit for bit (energies at every step, final Config, accepted counters), at low
+    temperature where the rejection-free samplers are meant to be used, with a hook pausing the kernels."""
+    if generic:
+        monkeypatch.setenv("RRRMC_CHAIN_GENERIC", "1")
+    R, beta, step = 6, 2.5, iters // 12
+    X, g = _mk(L, D, (-1, 1), R, seed=L + D)
+    C0 = rb.Config(X.N, R, rng=np.random.default_rng(12))
+    fn = {"rrrMC": rb.rrrMC, "bklMC": rb.bklMC}[sampler]
+    accs = []
+
+    def hook(it, X_, C, acc, E):
+        accs.append(np.array(acc))
+        return True
+    Es, Cf = fn(X, beta, iters, step=step, seed=2024, C0=C0, hook=hook, quiet=True)
+    wantE, wantC, res = _oracle_run(ofn, g, beta, iters, step, C0, 2024, R)
+    assert np.array_equal(np.asarray(Es, np.float64), wantE)
+    assert np.array_equal(Cf.chunks, wantC)
+    assert len(accs) == 12
+    # run without a hook (single launch) must give the same trajectory
+    Es2, Cf2 = fn(X, beta, iters, step=step, seed=2024, C0=C0, quiet=True)
+    assert np.array_equal(Es2, Es) and Cf2 == Cf
+    assert X.last_run.accepted_total == sum(r.accepted for r in res)
+
+
+def test_ea_fast_path_forced_modes_and_restart():
+    """Forced staged / eager modes (runtests.jl:140-191) on the fast path, then a second run continuing from the
+    final configuration of the first (fresh caches, same graph object)."""
+    R, beta = 3, 1.2
+    X, g = _mk(6, 3, (-1, 1), R, seed=17)
+    C0 = rb.Config(X.N, R, rng=np.random.default_rng(3))
+    for thr in (0.0, 1.0):
+        Es, Cf = rb.rrrMC(X, beta, 3000, step=100, seed=5, C0=C0, staged_thr=thr, quiet=True)
+        wantE, wantC, _ = _oracle_run(ffi.rrrMC, g, beta, 3000, 100, C0, 5, R, staged_thr=thr)
+        assert np.array_equal(np.asarray(Es, np.float64), wantE) and np.array_equal(Cf.chunks, wantC)
+    Es2, Cf2 = rb.bklMC(X, beta, 20000, step=1000, seed=6, C0=Cf, quiet=True)
+    wantE2, wantC2, _ = _oracle_run(ffi.bklMC, g, beta, 20000, 1000, Cf, 6, R)
+    assert np.array_equal(np.asarray(Es2, np.float64), wantE2) and np.array_equal(Cf2.chunks, wantC2)
