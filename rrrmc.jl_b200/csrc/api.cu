@@ -736,7 +736,6 @@ static rrrmc_status_t fill_cbs_params(rrrmc_state *s, const uint32_t *tbl, int t
     p.spins = s->d_spins; p.flips = nullptr; p.jcode = g->d_jcode; p.jmask = reinterpret_cast<const uint4 *>(g->d_jmask);
     p.L = g->L; p.Lh = g->L / 2; p.W = (int)s->W; p.G = (int)((s->W + 3) / 4);
     p.invG = 1.0f / (float)p.G;
-    p.one = 1u;
     p.Gshift = -1;
     for (int b = 0; b < 30; b++) if (p.G == (1 << b)) p.Gshift = b;
     { const char *v = getenv("RRRMC_CB_VARIANT"); p.variant = v ? atoi(v) : 0; }

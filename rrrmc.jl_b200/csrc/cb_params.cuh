@@ -37,7 +37,6 @@ struct cbs_params {
     int tpr;                // row-chunk kernel: threads per lattice row = (Lh/T)*G (set by the launcher)
     uint32_t t_lo, t_hi16;
     uint32_t rk[10][2];     // Philox round keys
-    uint32_t one;           // always 1, opaque to ptxas: keeps compare-by-carry multiplies on the FMA pipe
     float invG;
     int Gshift;             // log2(G) when G is a power of two, else -1
     int variant;

@@ -399,25 +399,20 @@ template <int D>
 __device__ __forceinline__ void cbs_task(const cbs_params &p, uint32_t c1, uint32_t c2, const uint32_t (&sc)[4],
                                          const uint32_t (&sn)[4][2 * D], const uint32_t (&neg)[2 * D], uint32_t (&fl)[4])
 {
-    const int skip = p.variant >> 4;   // timing experiments only (tune_cb.py): bit 0 Philox, bit 1 class-1, bit 2 ΔE logic
     // ---- spin-independent part: the sets of passing lanes of class 1
-    philox_out A, B;
-    if (skip & 1) { A.x = c1; A.y = c2; A.z = c1 ^ c2; A.w = c1 + c2; B = A; }
-    else { A = CB_PHILOX(0); B = CB_PHILOX(1); }
+    const philox_out A = CB_PHILOX(0), B = CB_PHILOX(1);
     const uint32_t xa[4] = { A.x, A.y, A.z, A.w };
     const uint32_t T0 = p.tbl[0], T1 = p.tbl[1], T2 = p.tbl[2];
-    uint32_t m[4] = { 0u, 0u, 0u, 0u }, need = 0;
-    if (!(skip & 2)) {
+    uint32_t m[4], need = 0;
 #pragma unroll
-        for (int w = 0; w < 4; w++) {
-            // static slots: bit offsets 10w and 10w+5 of S = B.x | B.y << 32
-            const uint32_t q0 = 10 * w < 32 ? __funnelshift_r(B.x, B.y, 10 * w) : B.y >> (10 * w - 32);
-            const uint32_t q1 = 10 * w + 5 < 32 ? __funnelshift_r(B.x, B.y, 10 * w + 5) : B.y >> (10 * w + 5 - 32);
-            const uint32_t b0 = 1u << (q0 & 31u), b1 = 1u << (q1 & 31u);
-            const bool ge1 = xa[w] > T0, ge2 = xa[w] > T1, ge3 = xa[w] > T2;
-            m[w] = (ge1 ? b0 : 0u) | (ge2 ? b1 : 0u);
-            need |= (ge3 || (ge2 && b0 == b1)) ? (1u << w) : 0u;   // a third draw is due: overflow stream
-        }
+    for (int w = 0; w < 4; w++) {
+        // static slots: bit offsets 10w and 10w+5 of S = B.x | B.y << 32
+        const uint32_t q0 = 10 * w < 32 ? __funnelshift_r(B.x, B.y, 10 * w) : B.y >> (10 * w - 32);
+        const uint32_t q1 = 10 * w + 5 < 32 ? __funnelshift_r(B.x, B.y, 10 * w + 5) : B.y >> (10 * w + 5 - 32);
+        const uint32_t b0 = 1u << (q0 & 31u), b1 = 1u << (q1 & 31u);
+        const bool ge1 = xa[w] > T0, ge2 = xa[w] > T1, ge3 = xa[w] > T2;
+        m[w] = (ge1 ? b0 : 0u) | (ge2 ? b1 : 0u);
+        need |= (ge3 || (ge2 && b0 == b1)) ? (1u << w) : 0u;   // a third draw is due: overflow stream
     }
     cbs_stream st; st.y0 = B.y >> 8; st.y1 = 0u; st.left = 3; st.call = 2;   // S >> 40
     auto slot = [&]() -> uint32_t {     // next 7-bit slot of the task's overflow stream
@@ -444,12 +439,12 @@ __device__ __forceinline__ void cbs_task(const cbs_params &p, uint32_t c1, uint3
     }
     // ---- spin-dependent part
 #pragma unroll
-    for (int w = 0; w < 4; w++) fl[w] = (skip & 4) ? (m[w] ^ sn[w][0]) : cbs_flip_word<D>(sc[w], sn[w], neg, m[w]);
+    for (int w = 0; w < 4; w++) fl[w] = cbs_flip_word<D>(sc[w], sn[w], neg, m[w]);
     if (D >= 2) {   // classes 2..D: rare at the temperatures where this procedure is selected
         const uint32_t xc[2] = { B.z, B.w };
         bool rare = xc[0] > p.tbl[CBS_T1];
         if (D == 3) rare = rare || xc[1] > p.tbl[CBS_T1 + CBS_TC];
-        if (rare && !(skip & 2)) {
+        if (rare) {
             uint32_t pm[2][4] = { { 0u, 0u, 0u, 0u }, { 0u, 0u, 0u, 0u } };
 #pragma unroll
             for (int c = 2; c <= D; c++) {

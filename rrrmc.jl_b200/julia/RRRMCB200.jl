@@ -141,7 +141,7 @@ update_cache!(X::Graph, C::Config, move::Integer) = nothing  # the device caches
 # ---- samplers (src/RRRMC.jl:81-127, 149-290, 311-359) ---------------------------------------------------
 struct Opts
     schedule::Cint; planes_K::Cint; count_accepted::Cint; staged_thr::Cdouble; staged_thr_fact::Cdouble
-    planes_M::Cint; reserved::NTuple{7,Cint}
+    planes_M::Cint; cb_method::Cint; reserved::NTuple{6,Cint}   # cb_method: 0 auto, 1 planes, 2 sparse (rrrmc_b200.h)
 end
 struct RunInfo
     nsamples::Int64; iters_done::Int64; launches::Int64; device_ms::Cfloat; accepted_total::Int64
@@ -158,7 +158,7 @@ function _run(sym::Symbol, X::Graph, β, iters::Integer; seed = 167432777111, st
     C0 === nothing ? check(ccall((:rrrmc_state_randomize, lib), Cint, (Ptr{Cvoid}, UInt64), X.state, seed > 0 ? seed : rand(UInt64))) :
                      upload!(X, C0)
     o = Ref{Opts}(); check(ccall((:rrrmc_opts_default, lib), Cint, (Ref{Opts},), o))
-    o[] = Opts(schedule, o[].planes_K, o[].count_accepted, staged_thr, staged_thr_fact, o[].planes_M, o[].reserved)
+    o[] = Opts(schedule, o[].planes_K, o[].count_accepted, staged_thr, staged_thr_fact, o[].planes_M, o[].cb_method, o[].reserved)
     cap = min(10^8, iters ÷ step)                                                          # RRRMC.jl:90
     Es = zeros(X.replicas, max(cap, 1)); info = Ref{RunInfo}()
     betas = fill(Float64(β), X.replicas)
