@@ -74,22 +74,34 @@ struct sk_tc_params {
     double scale;           // 2^-P
 };
 
+// Pipeline: a stage holds one 128-byte K chunk of all five digit planes of the A tile (5 x 16 KiB) and of the B tile
+// (8 KiB, loaded once per chunk instead of once per plane); two stages in dynamic shared memory. All threads fill
+// stage kc with cp.async (16-byte chunks straight into the 128-byte-swizzled layout, four full 128-byte lines per
+// warp instruction) while the tensor core consumes stage kc-1; a per-stage mbarrier armed by tcgen05.commit tells
+// the producers when the MMAs have drained a stage.
+constexpr int TC_STAGE_BYTES = (SKQ_SLICES * TC_M + TC_N) * TC_KB;   // 88 KiB
+constexpr int TC_STAGES = 2;
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(g) : "memory");
+}
 __global__ void __launch_bounds__(128, 1) k_sk_fields_tc(sk_tc_params P)
 {
-    __shared__ __align__(1024) uint8_t sA[TC_M * TC_KB];
-    __shared__ __align__(1024) uint8_t sB[TC_N * TC_KB];
-    __shared__ __align__(8) uint64_t mbar;
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t mbar[TC_STAGES];
     __shared__ uint32_t tmem_base_s;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int i0 = blockIdx.x * TC_M;
     const int64_t r0 = (int64_t)blockIdx.y * TC_N;
     constexpr uint32_t TMEM_COLS = 512;              // 5 accumulators x 64 columns, rounded up to a power of two
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
+#pragma unroll
+        for (int st = 0; st < TC_STAGES; st++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar[st])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -97,43 +109,64 @@ __global__ void __launch_bounds__(128, 1) k_sk_fields_tc(sk_tc_params P)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
     const uint32_t idesc = umma_idesc_s8(TC_M, TC_N);
-    const uint64_t descA = umma_desc_k_sw128(smem_u32(sA)), descB = umma_desc_k_sw128(smem_u32(sB));
-    uint32_t phase = 0;
     const int nkc = P.Npad / TC_KB;
-    for (int s = 0; s < SKQ_SLICES; s++) {
-        const int8_t *A = P.Jq + (size_t)s * P.Npad * P.Npad + (size_t)(i0 + tid) * P.Npad;   // thread = one row of the A tile
-        const int8_t *B = P.S8 + (size_t)(r0 + (tid & 63)) * P.Npad + (tid >> 6) * 64;        // thread = half a row of the B tile
-        for (int kc = 0; kc < nkc; kc++) {
-            const uint4 *ga = reinterpret_cast<const uint4 *>(A + (size_t)kc * TC_KB);
-            const uint4 *gb = reinterpret_cast<const uint4 *>(B + (size_t)kc * TC_KB);
-            uint4 va[8], vb[4];
+    const int c16 = lane & 7, rsub = lane >> 3;      // this lane's 16-byte chunk and row offset inside a 4-row group
+
+    auto fill = [&](int kc) {                        // all threads: stage kc % 2 <- K chunk kc
+        uint8_t *stg = base + (size_t)(kc % TC_STAGES) * TC_STAGE_BYTES;
 #pragma unroll
-            for (int c = 0; c < 8; c++) va[c] = ga[c];
+        for (int sl = 0; sl < SKQ_SLICES; sl++) {
+            const int8_t *A = P.Jq + (size_t)sl * P.Npad * P.Npad + (size_t)kc * TC_KB + c16 * 16;
+            const uint32_t sA = smem_u32(stg + (size_t)sl * TC_M * TC_KB);
 #pragma unroll
-            for (int c = 0; c < 4; c++) vb[c] = gb[c];
-#pragma unroll
-            for (int c = 0; c < 8; c++) *reinterpret_cast<uint4 *>(sA + sw128_off(tid, c)) = va[c];
-#pragma unroll
-            for (int c = 0; c < 4; c++) *reinterpret_cast<uint4 *>(sB + sw128_off(tid & 63, (tid >> 6) * 4 + c)) = vb[c];
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-            __syncthreads();
-            if (tid == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                for (int k = 0; k < TC_KB / 32; k++) {                    // K = 32 bytes per instruction for 8-bit operands
-                    const uint32_t accumulate = (kc | k) ? 1u : 0u;
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-                        :: "r"(tmem_base + (uint32_t)(s * TC_N)), "l"(descA + (uint64_t)(k * 32 >> 4)), "l"(descB + (uint64_t)(k * 32 >> 4)),
-                           "r"(idesc), "r"(accumulate) : "memory");
-                }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
+            for (int j = 0; j < 8; j++) {
+                const int row = warp * 32 + j * 4 + rsub;
+                cp_async16(sA + sw128_off(row, c16), A + (size_t)(i0 + row) * P.Npad);
             }
-            mbar_wait(smem_u32(&mbar), phase);                            // the MMAs have consumed sA/sB
-            phase ^= 1;
         }
+        const int8_t *B = P.S8 + (size_t)kc * TC_KB + c16 * 16;
+        const uint32_t sB = smem_u32(stg + (size_t)SKQ_SLICES * TC_M * TC_KB);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int row = warp * 16 + j * 4 + rsub;
+            cp_async16(sB + sw128_off(row, c16), B + (size_t)(r0 + row) * P.Npad);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto mma = [&](int kc) {                         // thread 0: 5 planes x 4 K-steps on stage kc % 2, then arm its mbarrier
+        const uint32_t stg = smem_u32(base + (size_t)(kc % TC_STAGES) * TC_STAGE_BYTES);
+        const uint64_t descB = umma_desc_k_sw128(stg + SKQ_SLICES * TC_M * TC_KB);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int sl = 0; sl < SKQ_SLICES; sl++) {
+            const uint64_t descA = umma_desc_k_sw128(stg + sl * TC_M * TC_KB);
+#pragma unroll
+            for (int k = 0; k < TC_KB / 32; k++) {   // K = 32 bytes per instruction for 8-bit operands
+                const uint32_t accumulate = (kc | k) ? 1u : 0u;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                    :: "r"(tmem_base + (uint32_t)(sl * TC_N)), "l"(descA + (uint64_t)(k * 32 >> 4)), "l"(descB + (uint64_t)(k * 32 >> 4)),
+                       "r"(idesc), "r"(accumulate) : "memory");
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar[kc % TC_STAGES])) : "memory");
+    };
+
+    fill(0);
+    for (int kc = 0; kc < nkc; kc++) {
+        if (kc + 1 < nkc) {
+            // stage (kc+1)%2 was last read by the MMAs of chunk kc-1: their commit is completion number (kc-1)/2 of that barrier
+            if (kc >= 1) mbar_wait(smem_u32(&mbar[(kc + 1) % TC_STAGES]), (uint32_t)(((kc - 1) / TC_STAGES) & 1));
+            fill(kc + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");     // chunk kc has landed (this thread's part)
+        } else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) mma(kc);
     }
+    // all MMAs done: the last commit of each stage's barrier
+    mbar_wait(smem_u32(&mbar[(nkc - 1) % TC_STAGES]), (uint32_t)(((nkc - 1) / TC_STAGES) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // epilogue: thread = TMEM lane = site i0+tid; columns = replicas. Recombine the five digit accumulators exactly.
     const int i = i0 + tid;
@@ -359,7 +392,9 @@ rrrmc_status_t sk_dense_fields_init(rrrmc_state *s, int use_tensor_cores, double
         k_spins_to_s8<<<div_up(s->R * d->Npad, 256), 256, 0, ctx->stream>>>(s->d_chunks, s->nchunks, s->R, N, d->Npad, d->S8);
         sk_tc_params P{ d->Jq, d->S8, d->lf, N, d->Npad, s->R, d->Rpad, d->scale };
         dim3 grid(d->Npad / TC_M, (unsigned)(d->Rpad / TC_N));
-        k_sk_fields_tc<<<grid, 128, 0, ctx->stream>>>(P);
+        const int tc_smem = TC_STAGES * TC_STAGE_BYTES + 1024;
+        RR_CUDA(cudaFuncSetAttribute(k_sk_fields_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem));
+        k_sk_fields_tc<<<grid, 128, tc_smem, ctx->stream>>>(P);
         ctx->launches += 2;
     } else {
         RR_CUDA(cudaEventRecord(e0, ctx->stream));
