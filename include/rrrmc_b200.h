@@ -139,9 +139,10 @@ typedef int (*rrrmc_hook_fn)(void *user, int64_t it, const double *E, const int6
 /* How a checkerboard task turns Philox bits into the Metropolis filter accept() of RRRMC.jl:39.
  * Both are exact per-(site,replica) Bernoulli(exp(-βΔE)) decisions, independent across lanes; they consume the
  * counter stream differently, so trajectories differ between procedures (each has its own CPU restatement). */
-#define RRRMC_CB_AUTO   0 /* sparse while 32·exp(-4β) <= 1.5 (β >~ 0.77), else planes                        */
+#define RRRMC_CB_AUTO   0 /* poisson while its static slots cover the hit count (β >~ 0.6), else sparse/planes  */
 #define RRRMC_CB_PLANES 1 /* bit-plane comparison of a (K+32)-bit uniform per lane against 64-bit thresholds */
 #define RRRMC_CB_SPARSE 2 /* binomial count of passing lanes per ΔE class + uniform distinct positions       */
+#define RRRMC_CB_POISSON 3 /* Poisson hit counts per task and level + uniform positions with replacement      */
 
 typedef struct {
     int    schedule;        /* RRRMC_SCHED_*; default checkerboard                                   */
@@ -151,7 +152,7 @@ typedef struct {
     double staged_thr_fact; /* rrrMC: default 5.0 (RRRMC.jl:155)                                       */
     int    planes_M;        /* checkerboard: merged bit planes after the full ones, four per Philox
                                call (default 4, a multiple of 4); planes_K + planes_M <= 32. See DESIGN.md §5.          */
-    int    cb_method;       /* checkerboard acceptance procedure: RRRMC_CB_AUTO (default), _PLANES, _SPARSE  */
+    int    cb_method;       /* checkerboard acceptance procedure: RRRMC_CB_AUTO (default), _PLANES, _SPARSE, _POISSON */
     int    reserved[6];
 } rrrmc_opts_t;
 rrrmc_status_t rrrmc_opts_default(rrrmc_opts_t *o);
@@ -199,6 +200,17 @@ rrrmc_status_t rrrmc_checkerboard_sweeps(rrrmc_state_t *s, const uint64_t *thr64
 rrrmc_status_t rrrmc_checkerboard_sparse_tables(const uint64_t *thr64, int nthr, uint32_t *tbl, int tbl_len);
 rrrmc_status_t rrrmc_checkerboard_sweeps_sparse(rrrmc_state_t *s, const uint32_t *tbl, int tbl_len,
                                                 uint64_t seed, uint64_t sweep0, int64_t nsweeps);
+
+/* The same loop with the poisson procedure (ea_poisson.cu). Every lane carries independent Poisson hit processes,
+ * level-l hits at rate lam_l - lam_{l+1} with lam_c = -log(1 - p_c); a lane of class c (ΔE = 4c) flips iff it got a hit
+ * of level >= c. tbl = TA[64] | TB0[32] | TB[32] | TC[32], entry k = round(P(count <= k)·2^32) - 1 for the per-task
+ * (128-lane) counts of level-1, level-2 (rescaled to [0, TC[0]] and plain) and level-3 hits: more than k hits iff
+ * x > T[k]. NW = static position words (1, 2, 4 or 6; 4·NW-1 level-1 hits are placed without branching);
+ * rrrmc_checkerboard_poisson_nw returns the smallest NW whose overflow probability per task is <= tol (0: none). */
+rrrmc_status_t rrrmc_checkerboard_poisson_tables(const uint64_t *thr64, int nthr, uint32_t *tbl, int tbl_len);
+int rrrmc_checkerboard_poisson_nw(const uint32_t *tbl, double tol);
+rrrmc_status_t rrrmc_checkerboard_sweeps_poisson(rrrmc_state_t *s, const uint32_t *tbl, int tbl_len, int NW,
+                                                 uint64_t seed, uint64_t sweep0, int64_t nsweeps);
 
 /* ---- dense GraphSKNormal path (BASELINE config 4) ----------------------------------------------
  * Local-field initialisation for the whole batch = the energy(X, C) contraction of SK.jl:212-237,

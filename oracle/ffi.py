@@ -100,6 +100,9 @@ def lib():
         "orc_checkerboard_sweeps_sparse": (None, [i32, i32, i64, p(np.uint32), p(np.int8), p(np.uint32),
                                                   C.c_uint64, C.c_uint64, i64, vp]),
         "orc_cb_sparse_tables": (None, [p(np.uint64), i32, p(np.uint32)]),
+        "orc_checkerboard_sweeps_poisson": (None, [i32, i32, i64, p(np.uint32), p(np.int8), p(np.uint32), i32,
+                                                   C.c_uint64, C.c_uint64, i64, vp]),
+        "orc_cb_poisson_tables": (None, [p(np.uint64), i32, p(np.uint32)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -382,3 +385,54 @@ def checkerboard_sweeps_sparse(L, D, R, spins, Jfwd, tbl, seed, sweep0, nsweeps,
     assert len(tbl) == CB_T1 + (D - 1) * CB_TC
     lib().orc_checkerboard_sweeps_sparse(L, D, R, spins, np.ascontiguousarray(Jfwd, np.int8),
                                          np.ascontiguousarray(tbl, np.uint32), seed, sweep0, nsweeps, acc_p)
+
+
+CBP_KA, CBP_KR = 64, 32
+CBP_LEN = CBP_KA + 3 * CBP_KR
+
+
+def cb_poisson_tables(thr):
+    """Count tables TA | TB0 | TB | TC of the poisson procedure (oracle's long-double build)."""
+    thr = np.ascontiguousarray(thr, np.uint64)
+    tbl = np.zeros(CBP_LEN, np.uint32)
+    lib().orc_cb_poisson_tables(thr, len(thr), tbl)
+    return tbl
+
+
+def cb_poisson_tables_exact(thr, digits=60):
+    """The same tables in high-precision decimal arithmetic (pins the long-double builds to within one unit)."""
+    from decimal import Decimal, getcontext, ROUND_HALF_EVEN
+    getcontext().prec = digits
+    lam = [Decimal(0)] * 5
+    for c, t in enumerate(thr, start=1):
+        lam[c] = -(1 - Decimal(int(t)) / Decimal(1 << 64)).ln()
+
+    def table(mu, scale, last, n):
+        out, pk, cdf = [], (-mu).exp(), Decimal(0)
+        for k in range(n):
+            cdf += pk
+            v = int((cdf * scale).to_integral_value(rounding=ROUND_HALF_EVEN))
+            out.append(last if (k == n - 1 or v > last) else max(v, 1) - 1)
+            pk = pk * mu / (k + 1)
+        return out
+    TA = table(128 * (lam[1] - lam[2]), Decimal(1 << 32), 0xffffffff, CBP_KA)
+    TB = table(128 * (lam[2] - lam[3]), Decimal(1 << 32), 0xffffffff, CBP_KR)
+    TC = table(128 * lam[3], Decimal(1 << 32), 0xffffffff, CBP_KR)
+    TB0 = table(128 * (lam[2] - lam[3]), Decimal(TC[0] + 1), TC[0], CBP_KR)
+    return np.array(TA + TB0 + TB + TC, dtype=np.uint32)
+
+
+def cb_poisson_nw(tbl, tol=1.5e-3):
+    """Smallest number of static position words NW in (1, 2, 4, 6) with P(level-1 count > 4·NW-1) <= tol, else 0."""
+    for nw in (1, 2, 4, 6):
+        if 1.0 - (float(tbl[4 * nw - 1]) + 1.0) / 2.0 ** 32 <= tol:
+            return nw
+    return 0
+
+
+def checkerboard_sweeps_poisson(L, D, R, spins, Jfwd, tbl, NW, seed, sweep0, nsweeps, accepted=None):
+    """CPU model of the engine's checkerboard sweeps with the poisson acceptance procedure."""
+    acc_p = accepted.ctypes.data if accepted is not None else None
+    assert len(tbl) == CBP_LEN and NW in (1, 2, 4, 6)
+    lib().orc_checkerboard_sweeps_poisson(L, D, R, spins, np.ascontiguousarray(Jfwd, np.int8),
+                                          np.ascontiguousarray(tbl, np.uint32), NW, seed, sweep0, nsweeps, acc_p)

@@ -1392,3 +1392,138 @@ void orc_checkerboard_sweeps_sparse(int L, int D, int64_t R, uint32_t *spins, co
             }
     }
 }
+
+/* ---- "poisson" acceptance procedure ------------------------------------------------------------------------------
+ * Each lane of a task carries D independent Poisson hit processes: "level l" hits arrive with rate
+ * lam_l - lam_{l+1}, lam_c = -log(1 - p_c), p_c = exp(-β·4c) (lam_{D+1} = 0). A lane of class c (ΔE = 4c) flips iff
+ * it received a hit of level >= c: probability 1 - exp(-lam_c) = p_c, independently across lanes — exactly accept()
+ * of RRRMC.jl:39. Hits are sampled per task (128 lanes): a Poisson COUNT per level by inverse CDF on a 32-bit
+ * uniform, then one uniform 7-bit POSITION per hit, WITH replacement (two hits on one lane are harmless, so nothing
+ * is ever redrawn and the common case has no data-dependent control flow).
+ * Random words of a task (Philox call q has ctr = (q | (t>>32)<<16, site, group, t&0xffffffff), key = seed):
+ *   call 0 = (X0, X1, P[0], P[1]); when NW > 2, call 1 = (P[2..5]).
+ *   X0: count a of level-1 hits: a > k iff X0 > TA[k].
+ *   X1: counts (b, c) of level-2 and level-3 hits: if X1 <= TC[0] then c = 0 and b > k iff X1 > TB0[k] (TB0 = the
+ *       CDF of b rescaled to [0, TC[0]]); else c > k iff X1 > TC[k] and b > k iff Y > TB[k], Y a fresh uniform.
+ *   static position slots: slot j = byte j&3 of P[j>>2], low 7 bits. Slots 0..NS-1 (NS = 4·NW-1) serve the first NS
+ *       level-1 hits; the last slot (byte 3 of P[NW-1]) serves the first level-2 hit.
+ *   overflow stream (rare): calls CO, CO+1, ... with CO = 1 if NW <= 2 else 2. Word 0 of call CO is Y; words 1..3 of
+ *       every overflow call hold twelve byte slots (low 7 bits each, LSB byte first). The stream serves, in order, the
+ *       level-1 hits NS.., the level-2 hits 1.., then all level-3 hits.
+ * tbl = TA[64] | TB0[32] | TB[32] | TC[32]; each table ends with the value that stops its scan. */
+typedef struct { uint32_t ctr[4], key[2], hi16, call, w[4], Y; int used, loaded; } orc_pstream;
+static void orc_pstream_fetch(orc_pstream *s)
+{
+    s->ctr[0] = s->call | s->hi16;
+    orc_philox4x32_10(s->ctr, s->key, s->w);
+    if (!s->loaded) s->Y = s->w[0];
+    s->loaded = 1; s->used = 0; s->call++;
+}
+static uint32_t orc_pstream_slot(orc_pstream *s)
+{
+    if (!s->loaded || s->used == 12) orc_pstream_fetch(s);
+    uint32_t v = (s->w[1 + s->used / 4] >> (8 * (s->used % 4))) & 127u;
+    s->used++;
+    return v;
+}
+static uint32_t orc_pstream_Y(orc_pstream *s)
+{
+    if (!s->loaded) orc_pstream_fetch(s);
+    return s->Y;
+}
+
+static void orc_poisson_table(long double mu, long double scale, uint32_t last, uint32_t *T, int n)
+{
+    long double pk = expl(-mu), cdf = 0.0L;
+    for (int k = 0; k < n; k++) {
+        cdf += pk;
+        long double v = rintl(cdf * scale);              /* count > k iff x > T[k] */
+        T[k] = (k == n - 1 || v > (long double)last) ? last : (v < 1.0L ? 0u : (uint32_t)(v - 1.0L));
+        pk = pk * mu / (long double)(k + 1);
+    }
+}
+void orc_cb_poisson_tables(const uint64_t *thr, int D, uint32_t *tbl)
+{
+    long double lam[5] = { 0, 0, 0, 0, 0 };
+    for (int c = 1; c <= D; c++) lam[c] = -log1pl(-(long double)thr[c - 1] / 18446744073709551616.0L);
+    uint32_t *TA = tbl, *TB0 = TA + ORC_CBP_KA, *TB = TB0 + ORC_CBP_KR, *TC = TB + ORC_CBP_KR;
+    orc_poisson_table(128.0L * (lam[1] - lam[2]), 4294967296.0L, 0xffffffffu, TA, ORC_CBP_KA);
+    orc_poisson_table(128.0L * (lam[2] - lam[3]), 4294967296.0L, 0xffffffffu, TB, ORC_CBP_KR);
+    orc_poisson_table(128.0L * lam[3], 4294967296.0L, 0xffffffffu, TC, ORC_CBP_KR);
+    orc_poisson_table(128.0L * (lam[2] - lam[3]), (long double)TC[0] + 1.0L, TC[0], TB0, ORC_CBP_KR);
+}
+
+void orc_checkerboard_sweeps_poisson(int L, int D, int64_t R, uint32_t *spins, const int8_t *Jfwd,
+                                     const uint32_t *tbl, int NW, uint64_t seed, uint64_t sweep0, int64_t nsweeps,
+                                     int64_t *accepted)
+{
+    int64_t N = 1; for (int d = 0; d < D; d++) N *= L;
+    int64_t W = R / 32, G = (R + 127) / 128;
+    const uint32_t *TA = tbl, *TB0 = TA + ORC_CBP_KA, *TB = TB0 + ORC_CBP_KR, *TC = TB + ORC_CBP_KR;
+    const int NS = 4 * NW - 1;
+    for (int64_t sw = 0; sw < nsweeps; sw++) {
+        uint64_t t = sweep0 + (uint64_t)sw;
+        for (int colour = 0; colour < 2; colour++)
+            for (int64_t i = 0; i < N; i++) {
+                int64_t co[3] = { 0, 0, 0 }, rem = i, par = 0;
+                for (int d = 0; d < D; d++) { co[d] = rem % L; rem /= L; par += co[d]; }
+                if ((par & 1) != colour) continue;
+                int64_t nbr[6]; int Jn[6]; int64_t stride = 1;
+                for (int d = 0; d < D; d++) {
+                    int64_t up = i + (((co[d] + 1) % L) - co[d]) * stride;
+                    int64_t dn = i + (((co[d] + L - 1) % L) - co[d]) * stride;
+                    nbr[2 * d] = up; Jn[2 * d] = Jfwd[i * D + d];
+                    nbr[2 * d + 1] = dn; Jn[2 * d + 1] = Jfwd[dn * D + d];
+                    stride *= L;
+                }
+                for (int64_t g = 0; g < G; g++) {
+                    int lvl[128];   /* highest level of a hit on the lane, 0 = none */
+                    memset(lvl, 0, sizeof lvl);
+                    orc_pstream st;
+                    uint32_t X[4], P[6] = { 0, 0, 0, 0, 0, 0 };
+                    memset(&st, 0, sizeof st);
+                    st.key[0] = (uint32_t)seed; st.key[1] = (uint32_t)(seed >> 32);
+                    st.ctr[1] = (uint32_t)i; st.ctr[2] = (uint32_t)g; st.ctr[3] = (uint32_t)t;
+                    st.hi16 = (uint32_t)(t >> 32) << 16;
+                    st.ctr[0] = 0u | st.hi16; orc_philox4x32_10(st.ctr, st.key, X);
+                    P[0] = X[2]; P[1] = X[3];
+                    if (NW > 2) { st.ctr[0] = 1u | st.hi16; orc_philox4x32_10(st.ctr, st.key, P + 2); }
+                    st.call = NW > 2 ? 2u : 1u;
+#define ORC_STATIC_SLOT(j) ((P[(j) >> 2] >> (8 * ((j) & 3))) & 127u)
+                    int a = 0, b = 0, c = 0;
+                    while (X[0] > TA[a]) a++;
+                    for (int j = 0; j < a; j++) {
+                        uint32_t pos = j < NS ? ORC_STATIC_SLOT(j) : orc_pstream_slot(&st);
+                        if (lvl[pos] < 1) lvl[pos] = 1;
+                    }
+                    if (X[1] <= TC[0]) { while (X[1] > TB0[b]) b++; }
+                    else {
+                        while (X[1] > TC[c]) c++;
+                        uint32_t Y = orc_pstream_Y(&st);
+                        while (Y > TB[b]) b++;
+                    }
+                    for (int j = 0; j < b; j++) {
+                        uint32_t pos = j == 0 ? ORC_STATIC_SLOT(NS) : orc_pstream_slot(&st);
+                        if (lvl[pos] < 2) lvl[pos] = 2;
+                    }
+                    for (int j = 0; j < c; j++) lvl[orc_pstream_slot(&st)] = 3;
+#undef ORC_STATIC_SLOT
+                    for (int l = 0; l < 128; l++) {
+                        int64_t r = 128 * g + l;
+                        if (r >= R) continue;
+                        int64_t w = r >> 5; int bb = (int)(r & 31);
+                        int sc = (spins[i * W + w] >> bb) & 1, acc = 0;
+                        for (int k = 0; k < 2 * D; k++) {
+                            int sk = (spins[nbr[k] * W + w] >> bb) & 1;
+                            acc += Jn[k] * (2 * sc - 1) * (2 * sk - 1);
+                        }
+                        int dE = 2 * acc;
+                        int flip = dE <= 0 ? 1 : (lvl[l] >= dE / 4);
+                        if (!flip) continue;
+                        spins[i * W + w] ^= (uint32_t)1 << bb;
+                        if (accepted) accepted[r]++;
+                    }
+                }
+            }
+    }
+}

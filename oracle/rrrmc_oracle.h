@@ -151,6 +151,18 @@ void orc_checkerboard_sweeps_sparse(int L, int D, int64_t R, uint32_t *spins, co
 /* Reference construction of those tables from the 64-bit fixed-point acceptance probabilities (long double). */
 void orc_cb_sparse_tables(const uint64_t *thr, int D, uint32_t *tbl);
 
+/* Same sweeps with the engine's "poisson" acceptance procedure: per task and hit level a Poisson count
+ * (inverse CDF on a 32-bit uniform) of uniformly placed hits, with replacement; a lane of class c flips iff it
+ * received a hit of level >= c. tbl = TA[64] | TB0[32] | TB[32] | TC[32] (see rrrmc_oracle.c); NW = number of static
+ * position words (1, 2, 4 or 6). */
+#define ORC_CBP_KA 64
+#define ORC_CBP_KR 32
+#define ORC_CBP_LEN (ORC_CBP_KA + 3 * ORC_CBP_KR)
+void orc_checkerboard_sweeps_poisson(int L, int D, int64_t R, uint32_t *spins, const int8_t *Jfwd,
+                                     const uint32_t *tbl, int NW, uint64_t seed, uint64_t sweep0, int64_t nsweeps,
+                                     int64_t *accepted /* [R] += */);
+void orc_cb_poisson_tables(const uint64_t *thr, int D, uint32_t *tbl);
+
 #ifdef __cplusplus
 }
 #endif

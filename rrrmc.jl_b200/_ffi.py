@@ -11,7 +11,7 @@ SO = os.path.join(HERE, "lib", "librrrmc_b200.so")
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4
 EA_PM1, EA_INT, EA_F64, SK_F64, SK_BIN, QT, QUANT, EMPTY = 1, 2, 3, 4, 5, 6, 7, 8
 SCHED_CHECKERBOARD, SCHED_RANDOM_SITE = 0, 1
-CB_AUTO, CB_PLANES, CB_SPARSE = 0, 1, 2
+CB_AUTO, CB_PLANES, CB_SPARSE, CB_POISSON = 0, 1, 2, 3
 CBS_T1, CBS_TC = 33, 129
 
 HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int64)
@@ -79,6 +79,9 @@ SIGNATURES = {
     "rrrmc_checkerboard_sweeps": (_i32, [_vp, _vp, _i32, _i32, _i32, _u64, _u64, _i64]),
     "rrrmc_checkerboard_sparse_tables": (_i32, [_vp, _i32, _vp, _i32]),
     "rrrmc_checkerboard_sweeps_sparse": (_i32, [_vp, _vp, _i32, _u64, _u64, _i64]),
+    "rrrmc_checkerboard_poisson_tables": (_i32, [_vp, _i32, _vp, _i32]),
+    "rrrmc_checkerboard_poisson_nw": (_i32, [_vp, C.c_double]),
+    "rrrmc_checkerboard_sweeps_poisson": (_i32, [_vp, _vp, _i32, _i32, _u64, _u64, _i64]),
 }
 
 _lib = None

@@ -53,6 +53,7 @@ extern "C" rrrmc_status_t rrrmc_ctx_destroy(rrrmc_ctx_t *c)
     if (!c) return RRRMC_OK;
     cudaSetDevice(c->device);
     if (c->flush_buf) cudaFree(c->flush_buf);
+    if (c->d_cbp_bucket) cudaFree(c->d_cbp_bucket);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -765,6 +766,115 @@ extern "C" rrrmc_status_t rrrmc_checkerboard_sweeps_sparse(rrrmc_state_t *s, con
     s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
     return RRRMC_OK;
 }
+// ---- "poisson" acceptance procedure: Poisson-count tables and sweeps (ea_poisson.cu:k_checkerboard_poisson)
+static void poisson_table(long double mu, long double scale, uint32_t last, uint32_t *T, int n)
+{
+    long double pk = expl(-mu), cdf = 0.0L;
+    for (int k = 0; k < n; k++) {
+        cdf += pk;
+        const long double v = rintl(cdf * scale);            // more than k hits iff x > T[k]
+        T[k] = (k == n - 1 || v > (long double)last) ? last : (v < 1.0L ? 0u : (uint32_t)(v - 1.0L));
+        pk = pk * mu / (long double)(k + 1);
+    }
+}
+extern "C" rrrmc_status_t rrrmc_checkerboard_poisson_tables(const uint64_t *thr64, int nthr, uint32_t *tbl, int tbl_len)
+{
+    RR_ARG(thr64 && tbl, "NULL argument");
+    RR_ARG(nthr >= 1 && nthr <= 3, "expected 1..3 acceptance thresholds, given %d", nthr);
+    RR_ARG(tbl_len >= CBP_LEN, "table buffer too small: %d < %d", tbl_len, CBP_LEN);
+    long double lam[5] = { 0, 0, 0, 0, 0 };
+    for (int c = 1; c <= nthr; c++) lam[c] = -log1pl(-(long double)thr64[c - 1] / 18446744073709551616.0L);
+    uint32_t *TA = tbl, *TB0 = TA + CBP_KA, *TB = TB0 + CBP_KR, *TC = TB + CBP_KR;
+    poisson_table(128.0L * (lam[1] - lam[2]), 4294967296.0L, 0xffffffffu, TA, CBP_KA);
+    poisson_table(128.0L * (lam[2] - lam[3]), 4294967296.0L, 0xffffffffu, TB, CBP_KR);
+    poisson_table(128.0L * lam[3], 4294967296.0L, 0xffffffffu, TC, CBP_KR);
+    poisson_table(128.0L * (lam[2] - lam[3]), (long double)TC[0] + 1.0L, TC[0], TB0, CBP_KR);
+    return RRRMC_OK;
+}
+// smallest NW in (1, 2, 4, 6) for which the level-1 count exceeds the static slots with probability <= tol; 0 if none
+extern "C" int rrrmc_checkerboard_poisson_nw(const uint32_t *tbl, double tol)
+{
+    if (!tbl) return 0;
+    if (tbl[CBP_KA - 2] != 0xffffffffu) return 0;   // the 64-entry table does not cover the count distribution
+    const int nws[4] = { 1, 2, 4, 6 };
+    for (int k = 0; k < 4; k++)
+        if (1.0 - ((double)tbl[4 * nws[k] - 1] + 1.0) / 4294967296.0 <= tol) return nws[k];
+    return 0;
+}
+
+static rrrmc_status_t fill_cbp_params(rrrmc_state *s, const uint32_t *tbl, int tbl_len, int NW, uint64_t seed, cbp_params &p)
+{
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    if (!(g->kind == RRRMC_EA_PM1 && g->d_jmask)) {
+        rrrmc_set_error("checkerboard sweeps need a ±J GraphEA with D<=3");
+        return RRRMC_ERR_UNSUPPORTED;
+    }
+    if (!g->bipartite) {
+        rrrmc_set_error("checkerboard sweeps need even L (a two-colourable lattice), given L=%d; use schedule=RANDOM_SITE", g->L);
+        return RRRMC_ERR_UNSUPPORTED;
+    }
+    RR_ARG(tbl_len == CBP_LEN, "expected a %d-entry count table, given %d", CBP_LEN, tbl_len);
+    RR_ARG(NW == 1 || NW == 2 || NW == 4 || NW == 6, "static position words NW must be 1, 2, 4 or 6, given %d", NW);
+    RR_ARG((int64_t)g->N * s->W < ((int64_t)1 << 31), "N*W = %lld words exceeds the kernel's 32-bit indexing", (long long)(g->N * s->W));
+    const uint32_t *TA = tbl, *TB0 = TA + CBP_KA, *TB = TB0 + CBP_KR, *TC = TB + CBP_KR;
+    RR_ARG(TA[CBP_KA - 1] == 0xffffffffu && TB[CBP_KR - 1] == 0xffffffffu && TC[CBP_KR - 1] == 0xffffffffu,
+           "count tables TA, TB, TC must end with 2^32-1");
+    RR_ARG(TB0[CBP_KR - 1] == TC[0], "count table TB0 must end with TC[0]");
+    for (int k = 1; k < CBP_KA; k++) RR_ARG(TA[k] >= TA[k - 1], "count table TA must be non-decreasing");
+    if (g->D < 3) RR_ARG(TC[0] == 0xffffffffu, "D=%d has no level-3 hits: TC[0] must be 2^32-1", g->D);
+    if (g->D < 2) RR_ARG(TB0[0] == 0xffffffffu && TB[0] == 0xffffffffu, "D=1 has no level-2 hits: TB0[0], TB[0] must be 2^32-1");
+    memset(&p, 0, sizeof p);
+    p.spins = s->d_spins; p.flips = nullptr; p.jmask = reinterpret_cast<const uint4 *>(g->d_jmask);
+    p.L = g->L; p.Lh = g->L / 2; p.W = (int)s->W; p.G = (int)((s->W + 3) / 4); p.NW = NW;
+    p.invG = 1.0f / (float)p.G;
+    p.Gshift = -1;
+    for (int b = 0; b < 30; b++) if (p.G == (1 << b)) p.Gshift = b;
+    { const char *v = getenv("RRRMC_CB_VARIANT"); p.variant = v ? atoi(v) : 0; }
+    memcpy(p.tbl, tbl, sizeof(uint32_t) * CBP_LEN);
+    p.tb0_0 = TB0[0]; p.tb0_1 = TB0[1];
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; r++) { p.rk[r][0] = k0 + (uint32_t)r * 0x9E3779B9u; p.rk[r][1] = k1 + (uint32_t)r * 0xBB67AE85u; }
+    // level-1 count lookup on the top 10 bits of the uniform: count = a0 + (x > T) inside a bucket
+    if (!ctx->d_cbp_bucket) RR_CUDA(cudaMalloc(&ctx->d_cbp_bucket, sizeof(uint2) * CBP_BUCKETS));
+    if (ctx->cbp_bucket_key.size() != (size_t)CBP_KA || memcmp(ctx->cbp_bucket_key.data(), TA, sizeof(uint32_t) * CBP_KA) != 0) {
+        std::vector<uint2> bk(CBP_BUCKETS);
+        for (uint32_t e = 0; e < (uint32_t)CBP_BUCKETS; e++) {
+            const uint32_t lo = e << 22, hi = lo + ((1u << 22) - 1u);
+            uint32_t below = 0, inside = 0, T = 0xffffffffu;
+            for (int k = 0; k < CBP_KA; k++) {
+                if (TA[k] < lo) below++;
+                else if (TA[k] < hi) { inside++; T = TA[k]; }
+            }
+            bk[e] = inside <= 1 ? make_uint2(T, below) : make_uint2(0u, 64u);
+        }
+        RR_CUDA(cudaStreamSynchronize(ctx->stream));   // no launch may still be reading the previous lookup
+        RR_CUDA(cudaMemcpy(ctx->d_cbp_bucket, bk.data(), sizeof(uint2) * CBP_BUCKETS, cudaMemcpyHostToDevice));
+        ctx->cbp_bucket_key.assign(TA, TA + CBP_KA);
+    }
+    p.bucket = ctx->d_cbp_bucket;
+    return RRRMC_OK;
+}
+static rrrmc_status_t run_sweep_poisson(rrrmc_state *s, cbp_params &p, uint64_t t)
+{
+    rrrmc_graph *g = s->g;
+    p.t_lo = (uint32_t)t; p.t_hi16 = (uint32_t)(t >> 32) << 16;
+    RR_TRY(launch_checkerboard_poisson(g->ctx, p, g->D, 0));
+    RR_TRY(launch_checkerboard_poisson(g->ctx, p, g->D, 1));
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_checkerboard_sweeps_poisson(rrrmc_state_t *s, const uint32_t *tbl, int tbl_len, int NW,
+                                                            uint64_t seed, uint64_t sweep0, int64_t nsweeps)
+{
+    RR_ARG(s && tbl, "NULL argument");
+    RR_ARG(nsweeps >= 0, "nsweeps must be >= 0");
+    RR_CUDA(cudaSetDevice(s->g->ctx->device));
+    RR_TRY(chain_sync_to_multispin(s));
+    cbp_params p;
+    RR_TRY(fill_cbp_params(s, tbl, tbl_len, NW, seed, p));
+    for (int64_t k = 0; k < nsweeps; k++) RR_TRY(run_sweep_poisson(s, p, sweep0 + (uint64_t)k));
+    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
+    return RRRMC_OK;
+}
 // AUTO: the sparse procedure wins while few lanes pass (expected passing lanes per 32-lane word <= 1.5)
 static bool cb_use_sparse(const rrrmc_opts_t *o, double p1)
 {
@@ -795,10 +905,20 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
     RR_TRY(chain_sync_to_multispin(s));
     uint64_t thr[3];
     for (int c = 1; c <= g->D; c++) thr[c - 1] = fixed64(exp(-beta * 4.0 * c));
-    RR_ARG(o->cb_method >= RRRMC_CB_AUTO && o->cb_method <= RRRMC_CB_SPARSE, "unknown cb_method %d", o->cb_method);
-    const bool sparse = cb_use_sparse(o, exp(-beta * 4.0));
-    cb_params p; cbs_params ps;
-    if (sparse) {
+    RR_ARG(o->cb_method >= RRRMC_CB_AUTO && o->cb_method <= RRRMC_CB_POISSON, "unknown cb_method %d", o->cb_method);
+    cb_params p; cbs_params ps; cbp_params pp;
+    // AUTO: poisson while its static position slots cover the level-1 hit count (β >~ 0.6), else sparse / planes
+    uint32_t ptbl[CBP_LEN];
+    RR_TRY(rrrmc_checkerboard_poisson_tables(thr, g->D, ptbl, CBP_LEN));
+    const int NW = rrrmc_checkerboard_poisson_nw(ptbl, CBP_NW_TOL);
+    if (o->cb_method == RRRMC_CB_POISSON && NW == 0) {
+        rrrmc_set_error("cb_method POISSON: β=%g is too warm for the procedure's static position slots (use AUTO, SPARSE or PLANES)", beta);
+        return RRRMC_ERR_UNSUPPORTED;
+    }
+    const bool poisson = o->cb_method == RRRMC_CB_POISSON || (o->cb_method == RRRMC_CB_AUTO && NW > 0);
+    const bool sparse = !poisson && cb_use_sparse(o, exp(-beta * 4.0));
+    if (poisson) RR_TRY(fill_cbp_params(s, ptbl, CBP_LEN, NW, seed, pp));
+    else if (sparse) {
         uint32_t tbl[CBS_T1 + 2 * CBS_TC];
         RR_TRY(rrrmc_checkerboard_sparse_tables(thr, g->D, tbl, CBS_T1 + 2 * CBS_TC));
         RR_TRY(fill_cbs_params(s, tbl, CBS_T1 + (g->D - 1) * CBS_TC, seed, ps));
@@ -808,7 +928,7 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
     const bool count = o->count_accepted != 0;
     if (count) {
         if (!s->d_flips) RR_CUDA(cudaMalloc(&s->d_flips, sizeof(uint32_t) * N * s->W));
-        p.flips = ps.flips = s->d_flips;
+        p.flips = ps.flips = pp.flips = s->d_flips;
         RR_CUDA(cudaMemsetAsync(s->d_acc, 0, sizeof(long long) * s->W * 32, ctx->stream));
     }
     const uint64_t l0 = ctx->launches;
@@ -820,7 +940,9 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
     RR_CUDA(cudaEventCreate(&e0)); RR_CUDA(cudaEventCreate(&e1));
     RR_CUDA(cudaEventRecord(e0, ctx->stream));
     for (int64_t sw = 1; sw <= nsweeps; sw++) {
-        if (sparse) RR_TRY(run_sweep_sparse(s, ps, (uint64_t)(sw - 1))); else RR_TRY(run_sweep(s, p, (uint64_t)(sw - 1)));
+        if (poisson) RR_TRY(run_sweep_poisson(s, pp, (uint64_t)(sw - 1)));
+        else if (sparse) RR_TRY(run_sweep_sparse(s, ps, (uint64_t)(sw - 1)));
+        else RR_TRY(run_sweep(s, p, (uint64_t)(sw - 1)));
         if (count) RR_TRY(launch_count_lanes(ctx, s->d_flips, N, (int)s->W, s->d_acc));
         done = sw;
         if (sw % step_sw == 0 && (hook || (Es && nsamples < Es_cap))) {

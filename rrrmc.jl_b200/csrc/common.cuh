@@ -29,6 +29,8 @@ struct rrrmc_ctx {
     uint64_t launches = 0;
     void *flush_buf = nullptr;
     size_t flush_bytes = 0;
+    uint2 *d_cbp_bucket = nullptr;   // poisson checkerboard procedure: level-1 count lookup (cb_params.cuh)
+    std::vector<uint32_t> cbp_bucket_key; // the TA table the lookup was built from
 };
 
 struct rrrmc_graph {

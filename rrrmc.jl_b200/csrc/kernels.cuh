@@ -4,8 +4,10 @@
 
 struct cb_params;
 struct cbs_params;
+struct cbp_params;
 rrrmc_status_t launch_checkerboard(rrrmc_ctx *ctx, const cb_params &p, int D, int colour);
 rrrmc_status_t launch_checkerboard_sparse(rrrmc_ctx *ctx, cbs_params &p, int D, int colour);
+rrrmc_status_t launch_checkerboard_poisson(rrrmc_ctx *ctx, cbp_params &p, int D, int colour);
 rrrmc_status_t launch_energy_pm1(rrrmc_state *s, int *d_unsat);
 rrrmc_status_t launch_count_lanes(rrrmc_ctx *ctx, const uint32_t *masks, int64_t N, int W, long long *d_out);
 rrrmc_status_t launch_delta_energy_site(rrrmc_state *s, int64_t site0, int *d_out);

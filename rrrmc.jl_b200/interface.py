@@ -516,7 +516,8 @@ def _opts(schedule=None, planes_K=None, count_accepted=None, staged_thr=None, st
     if planes_M is not None:
         o.planes_M = planes_M
     if cb_method is not None:
-        o.cb_method = {"auto": _ffi.CB_AUTO, "planes": _ffi.CB_PLANES, "sparse": _ffi.CB_SPARSE}[cb_method]
+        o.cb_method = {"auto": _ffi.CB_AUTO, "planes": _ffi.CB_PLANES, "sparse": _ffi.CB_SPARSE,
+                       "poisson": _ffi.CB_POISSON}[cb_method]
     if count_accepted is not None:
         o.count_accepted = int(count_accepted)
     if staged_thr is not None:
@@ -533,7 +534,7 @@ def standardMC(X, β, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, q
     schedule="random" is the reference's order (i = rand(1:N) per attempt, one chain per lane);
     schedule="checkerboard" (default where the lattice is two-colourable) updates all replicas in lock step,
     a whole sweep (N attempts) at a time — `iters`/`step` are rounded up to whole sweeps. cb_method selects how a
-    task turns Philox bits into accept() decisions: "planes", "sparse" or "auto" (include/rrrmc_b200.h)."""
+    task turns Philox bits into accept() decisions: "planes", "sparse", "poisson" or "auto" (include/rrrmc_b200.h)."""
     if schedule is None:
         schedule = "checkerboard" if (isinstance(X, GraphEA) and set(X.LEV) == {-1, 1} and X.L % 2 == 0 and X.D <= 3) else "random"
     return _run(lib().rrrmc_standard_mc, X, β, iters, seed, step, hook, C0, quiet,

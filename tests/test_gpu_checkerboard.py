@@ -98,6 +98,89 @@ def test_checkerboard_sparse_bit_exact_vs_cpu_model(L, D, R, beta):
     assert not (got == C0)
 
 
+def _poisson_tbl(beta, D):
+    thr = ffi.thresholds_fixed64(beta, D)
+    tbl = np.zeros(ffi.CBP_LEN, np.uint32)
+    check(lib().rrrmc_checkerboard_poisson_tables(ptr(thr), D, ptr(tbl), len(tbl)))
+    assert np.array_equal(tbl, ffi.cb_poisson_tables(thr))
+    return tbl
+
+
+@pytest.mark.parametrize("L,D,R,beta,NW", [(4, 2, 32, 0.5, 1), (6, 2, 96, 1.0, 2), (4, 3, 128, 0.7, 4), (6, 3, 160, 1.2, 2), (8, 3, 256, 0.5, 1),
+                                           (2, 3, 64, 0.9, 6), (4, 1, 32, 0.6, 2), (8, 3, 100, 2.0, 1), (8, 3, 512, 0.45, 2), (8, 3, 384, 1.0, 2),
+                                           (6, 3, 128, 0.6, 6), (8, 2, 1024, 1.0, 4), (16, 3, 1024, 1.0, 2), (8, 3, 256, 0.8, 4),
+                                           (8, 1, 128, 0.3, 1), (8, 2, 256, 0.4, 1)])
+def test_checkerboard_poisson_bit_exact_vs_cpu_model(L, D, R, beta, NW):
+    """Poisson acceptance procedure (hit counts + positions with replacement) against orc_checkerboard_sweeps_poisson.
+    Warm β with few static slots drives the overflow stream, the multi-hit level-2/3 paths and the ambiguous lookup
+    buckets hard; cold β is the branch-free path the benchmark runs."""
+    A, J = ea_instance(L, D, seed=L * 10 + D)
+    X = rb.GraphEA(L, D, replicas=R, A=A, J=J)
+    C0 = rb.Config(X.N, R, rng=np.random.default_rng(7))
+    tbl = _poisson_tbl(beta, D)
+    seed, nsw = 0xC0FFEE1234, 5
+    X._upload(C0)
+    check(lib().rrrmc_checkerboard_sweeps_poisson(X._state, ptr(tbl), len(tbl), NW, seed, (1 << 33) + 3, nsw))
+    got = X._download()
+    Rp = ((R + 31) // 32) * 32
+    sp = _multispin(C0)
+    ffi.checkerboard_sweeps_poisson(L, D, Rp, sp, _fwd(A, J, L, D), tbl, NW, seed, (1 << 33) + 3, nsw)
+    want = _from_multispin(sp, R)
+    assert got == want
+    assert not (got == C0)
+
+
+def test_checkerboard_poisson_argument_checks():
+    A, J = ea_instance(4, 3, seed=1)
+    X = rb.GraphEA(4, 3, replicas=32, A=A, J=J)
+    X._upload(rb.Config(X.N, 32, rng=np.random.default_rng(0)))
+    tbl = _poisson_tbl(1.0, 3)
+    for nw in (0, 3, 5, 7):
+        with pytest.raises(ValueError):
+            check(lib().rrrmc_checkerboard_sweeps_poisson(X._state, ptr(tbl), len(tbl), nw, 1, 0, 1))
+    with pytest.raises(ValueError):
+        check(lib().rrrmc_checkerboard_sweeps_poisson(X._state, ptr(tbl), len(tbl) - 1, 2, 1, 0, 1))
+    bad = tbl.copy(); bad[ffi.CBP_KA - 1] = 5
+    with pytest.raises(ValueError):
+        check(lib().rrrmc_checkerboard_sweeps_poisson(X._state, ptr(bad), len(bad), 2, 1, 0, 1))
+    # NW selection: colder needs fewer static slots; too warm has none
+    assert lib().rrrmc_checkerboard_poisson_nw(ptr(_poisson_tbl(2.0, 3)), 1.5e-3) == 1
+    assert lib().rrrmc_checkerboard_poisson_nw(ptr(tbl), 1.5e-3) == ffi.cb_poisson_nw(tbl) == 4
+    assert lib().rrrmc_checkerboard_poisson_nw(ptr(_poisson_tbl(0.3, 3)), 1.5e-3) == 0
+    with pytest.raises(NotImplementedError):
+        rb.standardMC(X, 0.3, 10 * X.N, quiet=True, cb_method="poisson")
+
+
+def test_standardMC_poisson_energies_and_accepted():
+    """standardMC through the public API with the default (auto -> poisson at β=1.1) procedure: energies, accepted
+    counters and configurations at every hook against the CPU model."""
+    L, D, R, beta = 6, 3, 64, 1.1
+    A, J = ea_instance(L, D, seed=3)
+    X = rb.GraphEA(L, D, replicas=R, A=A, J=J)
+    g = ffi.Graph.ea_int(A, J)
+    C0 = rb.Config(X.N, R, rng=np.random.default_rng(8))
+    seen = []
+
+    def hook(it, X_, C, acc, E):
+        seen.append((it, np.array(acc), np.array(E), C.chunks.copy()))
+        return True
+    N = X.N
+    Es, Cf = rb.standardMC(X, beta, 6 * N, step=2 * N, seed=77, C0=C0, hook=hook, quiet=True)
+    sp = _multispin(C0); acc = np.zeros(R, np.int64)
+    tbl = ffi.cb_poisson_tables(ffi.thresholds_fixed64(beta, D))
+    NW = ffi.cb_poisson_nw(tbl)
+    for k in range(3):
+        ffi.checkerboard_sweeps_poisson(L, D, R, sp, _fwd(A, J, L, D), tbl, NW, 77, 2 * k, 2, acc)
+        cfg = _from_multispin(sp, R)
+        assert np.array_equal(seen[k][3], cfg.chunks)
+        assert np.array_equal(seen[k][1], acc)
+        e = np.array([g.energy(cfg.chunks[r]) for r in range(R)])
+        assert np.array_equal(seen[k][2], e.astype(np.int64)) and np.array_equal(Es[k], e.astype(np.int64))
+    assert Cf == _from_multispin(sp, R)
+    Es2, _ = rb.standardMC(X, beta, 6 * N, step=2 * N, seed=77, C0=C0, quiet=True, cb_method="poisson")
+    assert np.array_equal(Es, Es2)
+
+
 def test_standardMC_sparse_energies_and_accepted():
     L, D, R, beta = 6, 3, 64, 1.1
     A, J = ea_instance(L, D, seed=3)
@@ -110,7 +193,7 @@ def test_standardMC_sparse_energies_and_accepted():
         seen.append((it, np.array(acc), np.array(E), C.chunks.copy()))
         return True
     N = X.N
-    Es, Cf = rb.standardMC(X, beta, 6 * N, step=2 * N, seed=77, C0=C0, hook=hook, quiet=True)  # auto -> sparse at β=1.1
+    Es, Cf = rb.standardMC(X, beta, 6 * N, step=2 * N, seed=77, C0=C0, hook=hook, quiet=True, cb_method="sparse")
     sp = _multispin(C0); acc = np.zeros(R, np.int64)
     tbl = ffi.cb_sparse_tables(ffi.thresholds_fixed64(beta, D))
     for k in range(3):
@@ -126,7 +209,8 @@ def test_standardMC_sparse_energies_and_accepted():
     assert not np.array_equal(Es, Es2)
 
 
-@pytest.mark.parametrize("method,beta", [("sparse", 1.0), ("sparse", 0.6), ("planes", 1.0)])
+@pytest.mark.parametrize("method,beta", [("sparse", 1.0), ("sparse", 0.6), ("planes", 1.0), ("poisson", 1.0), ("poisson", 0.65),
+                                         ("auto", 0.5)])
 def test_checkerboard_methods_statistics_vs_reference_sampler(method, beta):
     """⟨E⟩ after equilibration: each acceptance procedure vs the oracle's random-site standardMC within 3σ."""
     L, D = 6, 3
@@ -229,3 +313,11 @@ def test_full_size_properties_L64_R1024():
     for r in (1, 700):
         assert g.energy(C2.chunks[r]) == E2[r]
     assert E2.mean() < E.mean()
+    # poisson procedure at full size
+    ptbl = _poisson_tbl(1.0, D)
+    check(lib().rrrmc_checkerboard_sweeps_poisson(st, ptr(ptbl), len(ptbl), 2, 5, 0, 6))
+    E3 = np.zeros(R); check(lib().rrrmc_energy(st, ptr(E3)))
+    C3 = X._download()
+    for r in (2, 900):
+        assert g.energy(C3.chunks[r]) == E3[r]
+    assert E3.mean() < E2.mean()
