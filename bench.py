@@ -30,7 +30,7 @@ SWEEPS_PER_STEP = int(os.environ.get("BENCH_SWEEPS", "400"))
 BETA = 1.0
 PLANES_K = int(os.environ.get("BENCH_K", "5"))
 PLANES_M = int(os.environ.get("BENCH_M", "4"))
-METHOD = os.environ.get("BENCH_METHOD", "sparse")  # acceptance procedure of the checkerboard kernel: sparse | planes
+METHOD = os.environ.get("BENCH_METHOD", "poisson")  # acceptance procedure of the checkerboard kernel: poisson | sparse | planes
 SEED = 0x5EEDEA64
 METRIC = "spin-flip attempts/s, 3D EA L=64 ±J ×1024 replicas"
 UNIT = "attempts/s"
@@ -188,8 +188,14 @@ def run_ours(args, rank, world, local_rank):
     tbl = np.zeros(_ffi.CBS_T1 + (D - 1) * _ffi.CBS_TC, np.uint32)
     check(lib().rrrmc_checkerboard_sparse_tables(ptr(thr), D, ptr(tbl), len(tbl)))
 
+    ptbl = np.zeros(_ffi.CBP_LEN, np.uint32)
+    check(lib().rrrmc_checkerboard_poisson_tables(ptr(thr), D, ptr(ptbl), len(ptbl)))
+    NW = lib().rrrmc_checkerboard_poisson_nw(ptr(ptbl), 0.0)   # the library's default choice (what AUTO uses)
+
     def step(k):
-        if METHOD == "sparse":
+        if METHOD == "poisson":
+            check(lib().rrrmc_checkerboard_sweeps_poisson(st, ptr(ptbl), len(ptbl), NW, SEED + 1000 * rank, k * SWEEPS_PER_STEP, SWEEPS_PER_STEP))
+        elif METHOD == "sparse":
             check(lib().rrrmc_checkerboard_sweeps_sparse(st, ptr(tbl), len(tbl), SEED + 1000 * rank, k * SWEEPS_PER_STEP, SWEEPS_PER_STEP))
         else:
             check(lib().rrrmc_checkerboard_sweeps(st, ptr(thr), D, PLANES_K, PLANES_M, SEED + 1000 * rank, k * SWEEPS_PER_STEP, SWEEPS_PER_STEP))
@@ -235,7 +241,7 @@ def run_ours(args, rank, world, local_rank):
     opts.planes_K = PLANES_K
     opts.planes_M = PLANES_M
     opts.count_accepted = 0
-    opts.cb_method = _ffi.CB_SPARSE if METHOD == "sparse" else _ffi.CB_PLANES
+    opts.cb_method = {"poisson": _ffi.CB_POISSON, "sparse": _ffi.CB_SPARSE, "planes": _ffi.CB_PLANES}[METHOD]
     info = _ffi.RunInfo()
     iters = SWEEPS_PER_STEP * N_SITES
     gathered = [torch.empty(R_PER_GPU, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
@@ -281,17 +287,20 @@ def run_ours(args, rank, world, local_rank):
             "dtype": "u32 bit-sliced (multispin, 32 replicas/word)", "data": "synthetic",
             "config": {"workload": "GraphEA 3D L=64 ±J, checkerboard Metropolis, 1024 replicas per GPU (BASELINE configs[1])",
                        "L": L, "D": D, "replicas_per_gpu": R_PER_GPU, "beta": beta, "sweeps_per_step": SWEEPS_PER_STEP,
-                       "rng": ("Philox4x32-10; per task and ΔE class a binomial count of passing lanes (inverse CDF, 32-bit tables) + "
-                               "uniform distinct positions: exact per-(site,replica) Bernoulli(exp(-βΔE))") if METHOD == "sparse" else
-                              "Philox4x32-10, exact per-(site,replica) Bernoulli via %d full + %d merged bit planes + 32-bit tail" % (PLANES_K, PLANES_M),
+                       "rng": {"poisson": "Philox4x32-10; per task (128 replicas of a site) and hit level a Poisson count (inverse CDF, 32-bit tables) "
+                                          "+ uniform positions with replacement: exact per-(site,replica) Bernoulli(exp(-βΔE)); NW=%d static position words" % NW,
+                               "sparse": "Philox4x32-10; per task and ΔE class a binomial count of passing lanes (inverse CDF, 32-bit tables) + "
+                                         "uniform distinct positions: exact per-(site,replica) Bernoulli(exp(-βΔE))",
+                               "planes": "Philox4x32-10, exact per-(site,replica) Bernoulli via %d full + %d merged bit planes + 32-bit tail" % (PLANES_K, PLANES_M)}[METHOD],
                        "acceptance_procedure": METHOD,
                        "parallelism": f"replica-sharded x{world}", "l2": "flushed between timed steps (256 MiB write)",
                        "accepted_counters": "off in the timed loop"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_checkerboard_sparse<3,true>" if METHOD == "sparse" else "k_checkerboard<3,true>",
+                         "kernel": {"poisson": "k_checkerboard_poisson_persist<%d,3>" % NW, "sparse": "k_checkerboard_sparse<3,true>",
+                                    "planes": "k_checkerboard<3,true>"}[METHOD],
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_SWEEP // 2, "launch_ms": launch_ms,
-                         "note": "bound by integer instruction issue (ALU pipe ~67 % busy, ncu), not by HBM: the 32 MiB state is L2 resident (see DESIGN.md §5)"},
+                         "note": "bound by integer instruction issue (ALU pipe, ncu), not by HBM: the 32 MiB state is L2 resident (see DESIGN.md §5)"},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{cores} replicas (1/thread) x {cpu_iters} random-site attempts, same instance, beta={beta}; {cpu_dt:.1f}s"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(R_PER_GPU * nch * 8),

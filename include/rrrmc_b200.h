@@ -139,7 +139,7 @@ typedef int (*rrrmc_hook_fn)(void *user, int64_t it, const double *E, const int6
 /* How a checkerboard task turns Philox bits into the Metropolis filter accept() of RRRMC.jl:39.
  * Both are exact per-(site,replica) Bernoulli(exp(-βΔE)) decisions, independent across lanes; they consume the
  * counter stream differently, so trajectories differ between procedures (each has its own CPU restatement). */
-#define RRRMC_CB_AUTO   0 /* poisson while its static slots cover the hit count (β >~ 0.6), else sparse/planes  */
+#define RRRMC_CB_AUTO   0 /* poisson while its static slots cover the hit count (β >~ 0.5), else sparse/planes  */
 #define RRRMC_CB_PLANES 1 /* bit-plane comparison of a (K+32)-bit uniform per lane against 64-bit thresholds */
 #define RRRMC_CB_SPARSE 2 /* binomial count of passing lanes per ΔE class + uniform distinct positions       */
 #define RRRMC_CB_POISSON 3 /* Poisson hit counts per task and level + uniform positions with replacement      */
@@ -206,7 +206,8 @@ rrrmc_status_t rrrmc_checkerboard_sweeps_sparse(rrrmc_state_t *s, const uint32_t
  * of level >= c. tbl = TA[64] | TB0[32] | TB[32] | TC[32], entry k = round(P(count <= k)·2^32) - 1 for the per-task
  * (128-lane) counts of level-1, level-2 (rescaled to [0, TC[0]] and plain) and level-3 hits: more than k hits iff
  * x > T[k]. NW = static position words (1, 2, 4 or 6; 4·NW-1 level-1 hits are placed without branching);
- * rrrmc_checkerboard_poisson_nw returns the smallest NW whose overflow probability per task is <= tol (0: none). */
+ * rrrmc_checkerboard_poisson_nw returns the smallest NW whose overflow probability per task is <= tol (0: none;
+ * tol <= 0: the measured per-NW defaults that AUTO uses). */
 rrrmc_status_t rrrmc_checkerboard_poisson_tables(const uint64_t *thr64, int nthr, uint32_t *tbl, int tbl_len);
 int rrrmc_checkerboard_poisson_nw(const uint32_t *tbl, double tol);
 rrrmc_status_t rrrmc_checkerboard_sweeps_poisson(rrrmc_state_t *s, const uint32_t *tbl, int tbl_len, int NW,

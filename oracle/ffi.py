@@ -422,10 +422,13 @@ def cb_poisson_tables_exact(thr, digits=60):
     return np.array(TA + TB0 + TB + TC, dtype=np.uint32)
 
 
-def cb_poisson_nw(tbl, tol=1.5e-3):
-    """Smallest number of static position words NW in (1, 2, 4, 6) with P(level-1 count > 4·NW-1) <= tol, else 0."""
-    for nw in (1, 2, 4, 6):
-        if 1.0 - (float(tbl[4 * nw - 1]) + 1.0) / 2.0 ** 32 <= tol:
+def cb_poisson_nw(tbl, tol=None):
+    """Smallest number of static position words NW in (1, 2, 4, 6) with P(level-1 count > 4·NW-1) <= tol, else 0;
+    tol=None: the engine's per-NW defaults."""
+    if tbl[CBP_KA - 2] != 0xffffffff:
+        return 0
+    for nw, d in ((1, 0.03), (2, 0.2), (4, 0.06), (6, 0.05)):
+        if 1.0 - (float(tbl[4 * nw - 1]) + 1.0) / 2.0 ** 32 <= (d if tol is None else tol):
             return nw
     return 0
 

@@ -12,6 +12,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4
 EA_PM1, EA_INT, EA_F64, SK_F64, SK_BIN, QT, QUANT, EMPTY = 1, 2, 3, 4, 5, 6, 7, 8
 SCHED_CHECKERBOARD, SCHED_RANDOM_SITE = 0, 1
 CB_AUTO, CB_PLANES, CB_SPARSE, CB_POISSON = 0, 1, 2, 3
+CBP_LEN = 64 + 3 * 32   # count tables of the poisson procedure: TA[64] | TB0[32] | TB[32] | TC[32]
 CBS_T1, CBS_TC = 33, 129
 
 HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int64)

@@ -791,14 +791,17 @@ extern "C" rrrmc_status_t rrrmc_checkerboard_poisson_tables(const uint64_t *thr6
     poisson_table(128.0L * (lam[2] - lam[3]), (long double)TC[0] + 1.0L, TC[0], TB0, CBP_KR);
     return RRRMC_OK;
 }
-// smallest NW in (1, 2, 4, 6) for which the level-1 count exceeds the static slots with probability <= tol; 0 if none
+// Number of static position words: the smallest NW in (1, 2, 4, 6) whose overflow probability per task (level-1 count
+// above 4·NW-1) is <= tol; 0 if none. tol <= 0 selects the measured defaults: the second tier is cheap, so a word of
+// static slots (four to eight one-hot masks for every task) only pays off when it is needed often.
 extern "C" int rrrmc_checkerboard_poisson_nw(const uint32_t *tbl, double tol)
 {
     if (!tbl) return 0;
     if (tbl[CBP_KA - 2] != 0xffffffffu) return 0;   // the 64-entry table does not cover the count distribution
     const int nws[4] = { 1, 2, 4, 6 };
+    const double dflt[4] = { 0.03, 0.2, 0.06, 0.05 };
     for (int k = 0; k < 4; k++)
-        if (1.0 - ((double)tbl[4 * nws[k] - 1] + 1.0) / 4294967296.0 <= tol) return nws[k];
+        if (1.0 - ((double)tbl[4 * nws[k] - 1] + 1.0) / 4294967296.0 <= (tol > 0 ? tol : dflt[k])) return nws[k];
     return 0;
 }
 
@@ -831,7 +834,7 @@ static rrrmc_status_t fill_cbp_params(rrrmc_state *s, const uint32_t *tbl, int t
     for (int b = 0; b < 30; b++) if (p.G == (1 << b)) p.Gshift = b;
     { const char *v = getenv("RRRMC_CB_VARIANT"); p.variant = v ? atoi(v) : 0; }
     memcpy(p.tbl, tbl, sizeof(uint32_t) * CBP_LEN);
-    p.tb0_0 = TB0[0]; p.tb0_1 = TB0[1];
+    p.tb0_0 = TB0[0]; p.tb0_1 = TB0[1]; p.tc0 = TC[0]; p.one = 1u;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     for (int r = 0; r < 10; r++) { p.rk[r][0] = k0 + (uint32_t)r * 0x9E3779B9u; p.rk[r][1] = k1 + (uint32_t)r * 0xBB67AE85u; }
     // level-1 count lookup on the top 10 bits of the uniform: count = a0 + (x > T) inside a bucket
@@ -845,7 +848,7 @@ static rrrmc_status_t fill_cbp_params(rrrmc_state *s, const uint32_t *tbl, int t
                 if (TA[k] < lo) below++;
                 else if (TA[k] < hi) { inside++; T = TA[k]; }
             }
-            bk[e] = inside <= 1 ? make_uint2(T, below) : make_uint2(0u, 64u);
+            bk[e] = inside <= 1 ? make_uint2(T, below) : make_uint2(0xffffffffu, 64u + below);   // ambiguous: base count only
         }
         RR_CUDA(cudaStreamSynchronize(ctx->stream));   // no launch may still be reading the previous lookup
         RR_CUDA(cudaMemcpy(ctx->d_cbp_bucket, bk.data(), sizeof(uint2) * CBP_BUCKETS, cudaMemcpyHostToDevice));
@@ -907,10 +910,10 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
     for (int c = 1; c <= g->D; c++) thr[c - 1] = fixed64(exp(-beta * 4.0 * c));
     RR_ARG(o->cb_method >= RRRMC_CB_AUTO && o->cb_method <= RRRMC_CB_POISSON, "unknown cb_method %d", o->cb_method);
     cb_params p; cbs_params ps; cbp_params pp;
-    // AUTO: poisson while its static position slots cover the level-1 hit count (β >~ 0.6), else sparse / planes
+    // AUTO: poisson while its static position slots cover the level-1 hit count (β >~ 0.5), else sparse / planes
     uint32_t ptbl[CBP_LEN];
     RR_TRY(rrrmc_checkerboard_poisson_tables(thr, g->D, ptbl, CBP_LEN));
-    const int NW = rrrmc_checkerboard_poisson_nw(ptbl, CBP_NW_TOL);
+    const int NW = rrrmc_checkerboard_poisson_nw(ptbl, 0.0);
     if (o->cb_method == RRRMC_CB_POISSON && NW == 0) {
         rrrmc_set_error("cb_method POISSON: β=%g is too warm for the procedure's static position slots (use AUTO, SPARSE or PLANES)", beta);
         return RRRMC_ERR_UNSUPPORTED;

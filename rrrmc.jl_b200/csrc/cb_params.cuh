@@ -48,23 +48,26 @@ struct cbs_params {
 constexpr int CBP_KA = 64;
 constexpr int CBP_KR = 32;
 constexpr int CBP_LEN = CBP_KA + 3 * CBP_KR;
-constexpr double CBP_NW_TOL = 1.5e-3; // AUTO picks the fewest static slots whose overflow probability per task is below this
 constexpr int CBP_BUCKETS = 1024;  // lookup on the top 10 bits of the level-1 count uniform
 struct cbp_params {
     uint32_t *spins;        // [N][W]
     uint32_t *flips;        // [N][W] or nullptr
     const uint4 *jmask;     // [N][2]: whole-word sign masks of the six bonds of a site (api.cu)
-    const uint2 *bucket;    // [CBP_BUCKETS] {T, a0}: for x in bucket e the level-1 count is a0 + (x > T); a0 = 64 when
-                            // two table entries fall into the bucket (the task then takes the slow path)
+    const uint2 *bucket;    // [CBP_BUCKETS] {T, a0}: for x in bucket e the level-1 count is a0 + (x > T); when two table
+                            // entries fall into the bucket it holds {2^32-1, 64 + a0} (count >= a0: second tier)
     int L, Lh, W, G;
     int tpr;                // row-chunk kernel: threads per lattice row
     int NW;                 // static position words: 1, 2, 4 or 6
     int brick, sh_hbx, sh_by, bz; // brick mapping of blocks to sites (set by the launcher): log2(bx/2), log2(by), bz
+    int nbx, nby, nbricks;  // bricks along x, y and in total (persistent kernel)
+    float inv_nbx, inv_nby;
     uint32_t t_lo, t_hi16;
     uint32_t rk[10][2];     // Philox round keys
     float invG;
     int Gshift;             // log2(G) when G is a power of two, else -1
     int variant;
     uint32_t tb0_0, tb0_1;  // TB0[0], TB0[1]
+    uint32_t tc0;           // TC[0]
+    uint32_t one;           // always 1 (opaque to ptxas)
     uint32_t tbl[CBP_LEN];
 };

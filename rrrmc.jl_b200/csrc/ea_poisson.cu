@@ -132,19 +132,27 @@ __device__ __forceinline__ uint32_t cbp_flip_planes(const uint32_t (&b)[2 * D], 
     return lop3p<0xF8>(kc, ks, s3 | g);                                       // kc | (ks & (s3 | g))
 }
 
-// Spin-independent half of a task: the hit masks of (site c1, group c2). Returns true when the task took the rare
+// Spin-independent half of a task: the hit masks of (site c1, group c2). Returns true when the task left the fast
 // path (only then can h, the level-3 hits, be non-zero).
+// Three tiers. (1) The fast path above: branch free. (2) A lane with more hits than static slots would stall its whole
+// warp, so the second tier is entered by the WHOLE warp (one uniform branch when any lane needs it, ~15 % of the warps
+// at β = 1): every lane computes the first overflow call, and the extra hits — up to twelve per lane, level-1 hits
+// first, then level 2, then level 3, the oracle's order — are placed by a loop whose trip count is the warp's maximum
+// (one or two). (3) What is left (a count past the twelve overflow slots, an ambiguous lookup bucket whose base count
+// is below the static slots; probability < 1e-6) runs the complete scalar procedure cbp_slow().
 template <int D, int NW>
-__device__ __forceinline__ bool cbp_task_hits(const cbp_params &p, uint32_t c1, uint32_t c2, uint32_t (&m)[4], uint32_t (&g)[4], uint32_t (&h)[4])
+__device__ __forceinline__ bool cbp_task_hits(const cbp_params &p, const uint2 *__restrict__ bucket, uint32_t c1, uint32_t c2,
+                                              uint32_t (&m)[4], uint32_t (&g)[4], uint32_t (&h)[4])
 {
     constexpr int NS = 4 * NW - 1;
     const philox_out A = cbp_philox(p, 0u, c1, c2);
     uint32_t P[6] = { A.z, A.w, 0u, 0u, 0u, 0u };
     if (NW > 2) { const philox_out B = cbp_philox(p, 1u, c1, c2); P[2] = B.x; P[3] = B.y; P[4] = B.z; P[5] = B.w; }
-    const uint2 e = __ldg(p.bucket + (A.x >> 22));
+    const uint2 e = bucket[A.x >> 22];
     const uint32_t a = e.y + (A.x > e.x ? 1u : 0u);            // level-1 count (>= 64: ambiguous bucket, slow path)
     bool slow = a > (uint32_t)NS;
     if (D >= 2) slow = slow || A.y > p.tb0_1;
+    const uint32_t one = p.one;                                  // 1, opaque to ptxas: keeps amt·1 - 32w an IMAD (fma pipe)
     const uint32_t kv = (128u - a) * 0x01010101u;
     uint32_t f[NW];
 #pragma unroll
@@ -159,7 +167,7 @@ __device__ __forceinline__ bool cbp_task_hits(const cbp_params &p, uint32_t c1, 
 #pragma unroll
     for (int j = 0; j < NS; j++) {
         const uint32_t amt = (j & 3) == 3 ? f[j >> 2] >> 24 : __byte_perm(f[j >> 2], 0u, 0x4440u + (j & 3));
-        const uint32_t o[4] = { shl_clamp(amt), shl_clamp(amt - 32u), shl_clamp(amt - 64u), shl_clamp(amt - 96u) };
+        const uint32_t o[4] = { shl_clamp(amt), shl_clamp(amt * one - 32u), shl_clamp(amt * one - 64u), shl_clamp(amt * one - 96u) };
         // OR tree three inputs at a time: a pending one-hot waits in acc[w][1]
 #pragma unroll
         for (int w = 0; w < 4; w++) {
@@ -172,14 +180,59 @@ __device__ __forceinline__ bool cbp_task_hits(const cbp_params &p, uint32_t c1, 
     for (int w = 0; w < 4; w++) { g[w] = 0u; h[w] = 0u; }
     if (D >= 2) {
         const uint32_t amt = f[NW - 1] >> 24;
-        g[0] = shl_clamp(amt); g[1] = shl_clamp(amt - 32u); g[2] = shl_clamp(amt - 64u); g[3] = shl_clamp(amt - 96u);
+        g[0] = shl_clamp(amt); g[1] = shl_clamp(amt * one - 32u); g[2] = shl_clamp(amt * one - 64u); g[3] = shl_clamp(amt * one - 96u);
     }
 #pragma unroll
     for (int w = 0; w < 4; w++) m[w] = NS == 1 ? (acc[w][1] | g[w]) : lop3p<P_OR3>(acc[w][0], acc[w][1], g[w]);
-    if (slow) {
-        const cbp_hits r = cbp_slow<NW>(p, c1, c2, A.x, A.y, P[0], P[1], P[2], P[3], P[4], P[5]);
+    if (__any_sync(__activemask(), slow)) {
+        const uint32_t *TA = p.tbl, *TB0 = TA + CBP_KA, *TB = TB0 + CBP_KR, *TC = TB + CBP_KR;
+        const philox_out S = cbp_philox(p, NW > 2 ? 2u : 1u, c1, c2);   // first overflow call: Y, then twelve byte slots
+        uint32_t na = 0, nb = 0, nc = 0;
+        bool full = false;
+        if (slow) {
+            uint32_t at = a;
+            if (e.y >= 64u) {                     // ambiguous bucket: count on from the bucket's base
+                at = e.y - 64u;
+                if (at < (uint32_t)NS) full = true;
+                else while (A.x > TA[at]) at++;
+            }
+            na = at > (uint32_t)NS ? at - (uint32_t)NS : 0u;
+            if (D >= 2) {
+                uint32_t b = A.y > p.tb0_0 ? 1u : 0u;
+                if (D == 3 && A.y > p.tc0) {      // level-3 hits: their count from X1, the level-2 count from Y
+                    nc = 1u; while (A.y > TC[nc]) nc++;
+                    b = 0u; while (S.x > TB[b]) b++;
+                    if (b == 0u) { g[0] = g[1] = g[2] = g[3] = 0u; }   // the static level-2 slot was not a hit after all
+                } else if (A.y > p.tb0_1) { b = 2u; while (A.y > TB0[b]) b++; }
+                nb = b > 1u ? b - 1u : 0u;
+            }
+            if (na + nb + nc > 12u) full = true;
+            if (full) na = nb = nc = 0u;
+        }
+        const uint32_t n1 = na, n2 = na + nb, n3 = na + nb + nc;
+        const uint32_t nmax = __reduce_max_sync(__activemask(), n3);
+        uint32_t xm[4] = { 0u, 0u, 0u, 0u };
 #pragma unroll
-        for (int w = 0; w < 4; w++) { m[w] = r.m[w]; g[w] = r.g[w]; h[w] = r.h[w]; }
+        for (int sl = 0; sl < 12; sl++) {
+            if ((uint32_t)sl >= nmax) break;
+            const uint32_t wsl = sl < 4 ? S.y : (sl < 8 ? S.z : S.w);
+            const uint32_t pos = (wsl >> (8 * (sl & 3))) & 127u;
+            const uint32_t amt = (uint32_t)sl < n3 ? pos : 255u;
+            const uint32_t o[4] = { shl_clamp(amt), shl_clamp(amt - 32u), shl_clamp(amt - 64u), shl_clamp(amt - 96u) };
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                xm[w] |= o[w];
+                if ((uint32_t)sl >= n1) g[w] |= o[w];
+                if ((uint32_t)sl >= n2) h[w] |= o[w];
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < 4; w++) m[w] = acc[w][0] | acc[w][1] | g[w] | xm[w];
+        if (full) {
+            const cbp_hits r = cbp_slow<NW>(p, c1, c2, A.x, A.y, P[0], P[1], P[2], P[3], P[4], P[5]);
+#pragma unroll
+            for (int w = 0; w < 4; w++) { m[w] = r.m[w]; g[w] = r.g[w]; h[w] = r.h[w]; }
+        }
     }
     return slow;
 }
@@ -250,7 +303,7 @@ __global__ void __launch_bounds__(256, MINB) k_checkerboard_poisson(const __grid
         if (D >= 3) { const uint2 jb = __ldg(reinterpret_cast<const uint2 *>(p.jmask + 2 * (size_t)i + 1)); neg[4] = jb.x; neg[5] = jb.y; }
     }
     uint32_t m[4], gg[4], h[4];
-    const bool slow = cbp_task_hits<D, NW>(p, i, (uint32_t)g, m, gg, h);
+    const bool slow = cbp_task_hits<D, NW>(p, p.bucket, i, (uint32_t)g, m, gg, h);
 
     uint32_t sc[4], b[4][2 * D];
     if (FULL) {
@@ -293,6 +346,127 @@ __global__ void __launch_bounds__(256, MINB) k_checkerboard_poisson(const __grid
     }
 }
 
+// Persistent kernel (3D, whole groups, brick mapping): the grid is one wave of blocks and every block walks over
+// bricks b = blockIdx.x, blockIdx.x + gridDim.x, ... One iteration of a thread is one task, software-pipelined over a
+// single shared-memory stage: the spin words of task k+1 are requested (cp.async) as soon as those of task k have
+// been read into registers, so they travel under the flip logic of task k and the whole hit generation of task k+1.
+// The kernel is launched with programmatic stream serialization: its blocks may become resident while the previous
+// half-sweep drains, run the spin-independent hit generation of their first task, and only then wait for the
+// previous grid (griddepcontrol.wait) before touching the spins.
+template <int NW, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_checkerboard_poisson_persist(const __grid_constant__ cbp_params p, int colour)
+{
+    constexpr int D = 3;
+    __shared__ uint4 stage[2 * D + 1][256];
+    __shared__ uint2 sbucket[CBP_BUCKETS];   // level-1 count lookup: 8 KB, read once per block
+    const int t = threadIdx.x, L = p.L;
+#pragma unroll
+    for (int k = 0; k < CBP_BUCKETS / 256; k++) sbucket[t + 256 * k] = __ldg(p.bucket + t + 256 * k);
+    __syncthreads();
+    const int g = t & (p.G - 1), a = t >> p.Gshift;
+    const int ax = a & ((1 << p.sh_hbx) - 1), ay = (a >> p.sh_hbx) & ((1 << p.sh_by) - 1), az = a >> (p.sh_hbx + p.sh_by);
+    const uint32_t W4 = (uint32_t)p.W >> 2, LL = (uint32_t)L * L;
+    const uint4 *sp4 = reinterpret_cast<const uint4 *>(p.spins);
+    uint32_t i, nb[2 * D], neg[2 * D];
+    auto locate = [&](int b) {          // site and neighbours of this thread's task in brick b
+        const int q = __float2int_rz(((float)b + 0.5f) * p.inv_nbx);          // b / nbx, exact for b < 2^22
+        const int X = b - q * p.nbx;
+        const int Z = __float2int_rz(((float)q + 0.5f) * p.inv_nby), Y = q - Z * p.nby;
+        const int y = (Y << p.sh_by) + ay, z = Z * p.bz + az;
+        const int x = (X << (p.sh_hbx + 1)) + 2 * ax + ((y + z + colour) & 1);
+        const uint32_t row = (uint32_t)L * (uint32_t)(y + L * z);
+        i = row + x;
+        nb[0] = row + (x + 1 == L ? 0 : x + 1);
+        nb[1] = row + (x == 0 ? L - 1 : x - 1);
+        nb[2] = y + 1 == L ? i - (uint32_t)(L - 1) * L : i + L;
+        nb[3] = y == 0 ? i + (uint32_t)(L - 1) * L : i - L;
+        nb[4] = z + 1 == L ? i - (uint32_t)(L - 1) * LL : i + LL;
+        nb[5] = z == 0 ? i + (uint32_t)(L - 1) * LL : i - LL;
+    };
+    auto request = [&]() {              // spins of the located task -> shared-memory stage; bond signs -> registers
+        cp_async16(&stage[0][t], sp4 + (i * W4 + g));
+#pragma unroll
+        for (int k = 0; k < 2 * D; k++) cp_async16(&stage[1 + k][t], sp4 + (nb[k] * W4 + g));
+    };
+    auto signs = [&]() {
+        const uint4 ja = __ldg(p.jmask + 2 * (size_t)i);
+        const uint2 jb = __ldg(reinterpret_cast<const uint2 *>(p.jmask + 2 * (size_t)i + 1));
+        neg[0] = ja.x; neg[1] = ja.y; neg[2] = ja.z; neg[3] = ja.w; neg[4] = jb.x; neg[5] = jb.y;
+    };
+    int b = blockIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (b >= p.nbricks) return;
+    locate(b);
+    signs();
+    bool first = true;
+    for (;;) {
+        uint32_t m[4], gg[4], h[4];
+        const bool slow = cbp_task_hits<D, NW>(p, sbucket, i, (uint32_t)g, m, gg, h);
+        if (first) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");   // the previous half-sweep is complete and visible
+            request();
+            first = false;
+        }
+        cp_async_wait_all();
+        uint32_t sc[4], bp[4][2 * D];
+        {
+            const uint4 c = stage[0][t];
+            sc[0] = c.x; sc[1] = c.y; sc[2] = c.z; sc[3] = c.w;
+#pragma unroll
+            for (int k = 0; k < 2 * D; k++) {
+                const uint4 v = stage[1 + k][t];
+                bp[0][k] = lop3p<P_XOR3>(sc[0], v.x, neg[k]); bp[1][k] = lop3p<P_XOR3>(sc[1], v.y, neg[k]);
+                bp[2][k] = lop3p<P_XOR3>(sc[2], v.z, neg[k]); bp[3][k] = lop3p<P_XOR3>(sc[3], v.w, neg[k]);
+            }
+        }
+        const uint32_t icur = i;
+        b += gridDim.x;
+        const bool more = b < p.nbricks;
+        if (more) { locate(b); request(); signs(); }
+        uint32_t fl[4];
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            if (slow) bp[w][0] |= h[w];          // a level-3 hit flips every lane (m = g = 1 there, so u >= 1 suffices)
+            fl[w] = cbp_flip_planes<D>(bp[w], m[w], gg[w]);
+            sc[w] ^= fl[w];
+        }
+        reinterpret_cast<uint4 *>(p.spins)[icur * W4 + g] = make_uint4(sc[0], sc[1], sc[2], sc[3]);
+        if (p.flips) reinterpret_cast<uint4 *>(p.flips)[icur * W4 + g] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+        if (!more) break;
+    }
+}
+
+template <int NW, int MINB>
+static cudaError_t launch_persist_one(const cbp_params &p, int colour, int sm_count, cudaStream_t st)
+{
+    static int occ = 0;   // resident blocks per SM of this instantiation
+    if (!occ) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_checkerboard_poisson_persist<NW, MINB>, 256, 0);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) occ = 1;
+    }
+    int grid = sm_count * occ;
+    if (p.variant & 128) grid = 2;   // tests: many iterations per block
+    if (grid > p.nbricks) grid = p.nbricks;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (p.variant & 32) ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, k_checkerboard_poisson_persist<NW, MINB>, p, colour);
+}
+template <int MINB>
+static cudaError_t launch_persist(const cbp_params &p, int colour, int sm_count, cudaStream_t st)
+{
+    switch (p.NW) {
+    case 1: return launch_persist_one<1, MINB>(p, colour, sm_count, st);
+    case 2: return launch_persist_one<2, MINB>(p, colour, sm_count, st);
+    case 4: return launch_persist_one<4, MINB>(p, colour, sm_count, st);
+    default: return launch_persist_one<6, MINB>(p, colour, sm_count, st);
+    }
+}
+
 template <int D, bool FULL, int MINB>
 static void launch_nw(const cbp_params &p, int colour, dim3 grid, dim3 block, cudaStream_t st)
 {
@@ -325,7 +499,20 @@ rrrmc_status_t launch_checkerboard_poisson(rrrmc_ctx *ctx, cbp_params &p, int D,
         if (ok) {
             p.brick = 1; p.sh_hbx = sh[0] - 1; p.sh_by = sh[1]; p.bz = 1 << sh[2];
             grid = dim3(p.L >> sh[0], p.L >> sh[1], p.L >> sh[2]);
+            p.nbx = (int)grid.x; p.nby = (int)grid.y; p.nbricks = (int)(grid.x * grid.y * grid.z);
+            p.inv_nbx = 1.0f / (float)p.nbx; p.inv_nby = 1.0f / (float)p.nby;
         }
+    }
+    if (p.brick && p.nbricks < (1 << 22) && !(p.variant & 8)) {   // persistent, software-pipelined kernel
+        const int mb = p.variant & 3;   // RRRMC_CB_VARIANT (tuning): resident blocks per SM; 3 (80 registers) measured best
+        cudaError_t e = mb == 1 ? launch_persist<5>(p, colour, ctx->sm_count, ctx->stream)
+                      : mb == 2 ? launch_persist<2>(p, colour, ctx->sm_count, ctx->stream)
+                      : mb == 3 ? launch_persist<4>(p, colour, ctx->sm_count, ctx->stream)
+                                : launch_persist<3>(p, colour, ctx->sm_count, ctx->stream);
+        ctx->launches++;
+        RR_CUDA(e);
+        RR_CUDA(cudaGetLastError());
+        return RRRMC_OK;
     }
     if (D == 1) { if (full) launch_nw<1, true, 1>(p, colour, grid, block, ctx->stream); else launch_nw<1, false, 1>(p, colour, grid, block, ctx->stream); }
     else if (D == 2) { if (full) launch_nw<2, true, 1>(p, colour, grid, block, ctx->stream); else launch_nw<2, false, 1>(p, colour, grid, block, ctx->stream); }

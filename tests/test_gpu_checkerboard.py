@@ -130,6 +130,25 @@ def test_checkerboard_poisson_bit_exact_vs_cpu_model(L, D, R, beta, NW):
     assert not (got == C0)
 
 
+@pytest.mark.parametrize("variant", ["128", "8", "16", "32"])
+def test_checkerboard_poisson_kernel_variants_agree(variant, monkeypatch):
+    """The persistent kernel with two blocks (every block walks 32 bricks), the one-task-per-thread kernel, the row
+    mapping and the launch without programmatic serialization all produce the oracle's trajectory (warm β with one
+    static word: most tasks run the second tier)."""
+    L, D, R, beta, NW = 16, 3, 1024, 0.8, 1
+    A, J = ea_instance(L, D, seed=11)
+    X = rb.GraphEA(L, D, replicas=R, A=A, J=J)
+    C0 = rb.Config(X.N, R, rng=np.random.default_rng(17))
+    tbl = _poisson_tbl(beta, D)
+    X._upload(C0)
+    monkeypatch.setenv("RRRMC_CB_VARIANT", variant)
+    check(lib().rrrmc_checkerboard_sweeps_poisson(X._state, ptr(tbl), len(tbl), NW, 5, 0, 2))
+    got = X._download()
+    sp = _multispin(C0)
+    ffi.checkerboard_sweeps_poisson(L, D, R, sp, _fwd(A, J, L, D), tbl, NW, 5, 0, 2)
+    assert got == _from_multispin(sp, R)
+
+
 def test_checkerboard_poisson_argument_checks():
     A, J = ea_instance(4, 3, seed=1)
     X = rb.GraphEA(4, 3, replicas=32, A=A, J=J)
@@ -145,8 +164,9 @@ def test_checkerboard_poisson_argument_checks():
         check(lib().rrrmc_checkerboard_sweeps_poisson(X._state, ptr(bad), len(bad), 2, 1, 0, 1))
     # NW selection: colder needs fewer static slots; too warm has none
     assert lib().rrrmc_checkerboard_poisson_nw(ptr(_poisson_tbl(2.0, 3)), 1.5e-3) == 1
-    assert lib().rrrmc_checkerboard_poisson_nw(ptr(tbl), 1.5e-3) == ffi.cb_poisson_nw(tbl) == 4
-    assert lib().rrrmc_checkerboard_poisson_nw(ptr(_poisson_tbl(0.3, 3)), 1.5e-3) == 0
+    assert lib().rrrmc_checkerboard_poisson_nw(ptr(tbl), 1.5e-3) == ffi.cb_poisson_nw(tbl, 1.5e-3) == 4
+    assert lib().rrrmc_checkerboard_poisson_nw(ptr(tbl), 0.0) == ffi.cb_poisson_nw(tbl) == 2
+    assert lib().rrrmc_checkerboard_poisson_nw(ptr(_poisson_tbl(0.3, 3)), 0.0) == 0
     with pytest.raises(NotImplementedError):
         rb.standardMC(X, 0.3, 10 * X.N, quiet=True, cb_method="poisson")
 
