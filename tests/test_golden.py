@@ -84,3 +84,54 @@ def test_engine_checkerboard_reproduces_golden():
     got = X._download()
     want = np.unpackbits(GOLD["checkerboard/final"].view(np.uint8).reshape(X.N, R // 8), axis=1, bitorder="little").T
     assert np.array_equal(got.s, want.astype(bool))
+
+
+# ---- count-table acceptance procedures of the checkerboard kernels (tests/golden/checkerboard_v2.npz) ------------
+GOLD_CB = np.load(os.path.join(HERE, "golden", "checkerboard_v2.npz"))
+_spec_cb = importlib.util.spec_from_file_location("make_golden_cb", os.path.join(HERE, "golden", "make_golden_cb.py"))
+mgcb = importlib.util.module_from_spec(_spec_cb)
+_spec_cb.loader.exec_module(mgcb)
+
+
+def test_oracle_reproduces_checkerboard_golden():
+    now = mgcb.compute()
+    assert set(now) == set(GOLD_CB.files)
+    for k in GOLD_CB.files:
+        assert np.array_equal(np.asarray(now[k]), GOLD_CB[k]), k
+
+
+def test_library_tables_match_checkerboard_golden():
+    """Host-only entry points of the C ABI (no device): the table builders reproduce the committed tables."""
+    from rrrmc_b200._ffi import check, lib, ptr
+    for name in mgcb.CASES:
+        thr = np.ascontiguousarray(GOLD_CB[f"{name}/thr"]); want = GOLD_CB[f"{name}/tbl"]
+        tbl = np.zeros(len(want), np.uint32)
+        check(lib().rrrmc_checkerboard_poisson_tables(ptr(thr), mgcb.D, ptr(tbl), len(tbl)))
+        assert np.array_equal(tbl, want), name
+    thr = np.ascontiguousarray(GOLD_CB["sparse_b0.9/thr"]); want = GOLD_CB["sparse_b0.9/tbl"]
+    tbl = np.zeros(len(want), np.uint32)
+    check(lib().rrrmc_checkerboard_sparse_tables(ptr(thr), mgcb.D, ptr(tbl), len(tbl)))
+    assert np.array_equal(tbl, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(mgcb.CASES) + ["sparse_b0.9"])
+def test_engine_checkerboard_count_procedures_reproduce_golden(name):
+    """The CUDA kernels against the committed vectors, through the C ABI, without the oracle in the loop."""
+    import rrrmc_b200 as rb
+    from rrrmc_b200._ffi import check, lib, ptr
+    from tests.helpers import ea_instance
+    L, D, R = mgcb.L, mgcb.D, mgcb.R
+    A, J = ea_instance(L, D, seed=21)
+    X = rb.GraphEA(L, D, replicas=R, A=A, J=J)
+    sp = GOLD_CB["initial"]
+    bits = np.unpackbits(sp.view(np.uint8).reshape(X.N, R // 8), axis=1, bitorder="little").T
+    X._upload(rb.Config.from_bits(bits))
+    tbl = np.ascontiguousarray(GOLD_CB[f"{name}/tbl"])
+    if name.startswith("poisson"):
+        check(lib().rrrmc_checkerboard_sweeps_poisson(X._state, ptr(tbl), len(tbl), mgcb.CASES[name][1], mgcb.SEED, mgcb.SWEEP0, mgcb.NSW))
+    else:
+        check(lib().rrrmc_checkerboard_sweeps_sparse(X._state, ptr(tbl), len(tbl), mgcb.SEED, mgcb.SWEEP0, mgcb.NSW))
+    got = X._download()
+    want = np.unpackbits(GOLD_CB[f"{name}/final"].view(np.uint8).reshape(X.N, R // 8), axis=1, bitorder="little").T
+    assert np.array_equal(got.s, want.astype(bool))

@@ -109,7 +109,8 @@ def _poisson_tbl(beta, D):
 @pytest.mark.parametrize("L,D,R,beta,NW", [(4, 2, 32, 0.5, 1), (6, 2, 96, 1.0, 2), (4, 3, 128, 0.7, 4), (6, 3, 160, 1.2, 2), (8, 3, 256, 0.5, 1),
                                            (2, 3, 64, 0.9, 6), (4, 1, 32, 0.6, 2), (8, 3, 100, 2.0, 1), (8, 3, 512, 0.45, 2), (8, 3, 384, 1.0, 2),
                                            (6, 3, 128, 0.6, 6), (8, 2, 1024, 1.0, 4), (16, 3, 1024, 1.0, 2), (8, 3, 256, 0.8, 4),
-                                           (8, 1, 128, 0.3, 1), (8, 2, 256, 0.4, 1)])
+                                           (8, 1, 128, 0.3, 1), (8, 2, 256, 0.4, 1), (32, 3, 1024, 1.0, 2), (64, 3, 128, 1.1, 2),
+                                           (12, 3, 256, 0.9, 2), (20, 3, 1024, 1.0, 2)])
 def test_checkerboard_poisson_bit_exact_vs_cpu_model(L, D, R, beta, NW):
     """Poisson acceptance procedure (hit counts + positions with replacement) against orc_checkerboard_sweeps_poisson.
     Warm β with few static slots drives the overflow stream, the multi-hit level-2/3 paths and the ambiguous lookup
@@ -118,7 +119,7 @@ def test_checkerboard_poisson_bit_exact_vs_cpu_model(L, D, R, beta, NW):
     X = rb.GraphEA(L, D, replicas=R, A=A, J=J)
     C0 = rb.Config(X.N, R, rng=np.random.default_rng(7))
     tbl = _poisson_tbl(beta, D)
-    seed, nsw = 0xC0FFEE1234, 5
+    seed, nsw = 0xC0FFEE1234, (5 if L < 32 else 2)   # the big lattices walk several bricks per persistent block
     X._upload(C0)
     check(lib().rrrmc_checkerboard_sweeps_poisson(X._state, ptr(tbl), len(tbl), NW, seed, (1 << 33) + 3, nsw))
     got = X._download()
