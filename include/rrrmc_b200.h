@@ -66,6 +66,14 @@ rrrmc_status_t rrrmc_graph_ea_create(rrrmc_ctx_t *ctx, int L, int D, int couplin
 #define RRRMC_QT     6 /* GraphQT{fourK}: Trotter-direction ring couplings (QT.jl:42-121)              */
 #define RRRMC_QUANT  7 /* GraphQuant{fourK,G}: M Trotter slices of a classical graph (QT.jl:126-321)   */
 #define RRRMC_EMPTY  8 /* GraphEmpty as the inner graph of GraphQuant (GraphQ0T, QAliases.jl:19-31)    */
+#define RRRMC_EA_DISCR 9 /* GraphEANormalDiscretized{Int,LEV,2D} <: DoubleGraph (EA.jl:311-344); see below    */
+
+/* Replaces GraphEANormalDiscretized(L, D, LEV) with integer levels (EA.jl:311-344, e.g. (-1,0,1) as in test/runtests.jl:51)
+ * and explicit continuous couplings cJ [N*2D] (double, slot-aligned with A, symmetric; the constructor draws them with
+ * gen_J(randn), EA.jl:323-325). Every coupling is split by discretize (Common.jl:38-49) into a level (inner
+ * GraphEA{Int,LEV}: what rrrMC's ΔE classes see) and a Float64 residual (accepted by accept(c, -βΔE1), RRRMC.jl:262). */
+rrrmc_status_t rrrmc_graph_ea_discretized_create(rrrmc_ctx_t *ctx, int L, int D, const int64_t *A, const double *cJ,
+                                                 const int64_t *lev, int nlev, rrrmc_graph_t **out);
 
 /* Replaces GraphSKNormal(N) / GraphSK(N) with explicit couplings (SK.jl:181-199 / :28-49; the generators are
  * gen_J_gauss SK.jl:170-179 and gen_J SK.jl:17-26). J: [N*N] row-major, symmetric, zero diagonal; double for

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "librrrmc_oracle.so")
 
-EA_INT, EA_F64, SK_BIN, SK_F64, QT, QUANT, EMPTY = 1, 2, 3, 4, 5, 6, 7
+EA_INT, EA_F64, SK_BIN, SK_F64, QT, QUANT, EMPTY, EA_DISCR = 1, 2, 3, 4, 5, 6, 7, 8
 
 
 def build(force=False):
@@ -73,6 +73,7 @@ def lib():
         "orc_gen_J_f64": (i32, [i64, i32, p(np.int64), p(np.float64), i64, p(np.float64)]),
         "orc_ea_int_create": (vp, [i64, i32, p(np.int64), p(np.int64), p(np.int64), i32]),
         "orc_ea_f64_create": (vp, [i64, i32, p(np.int64), p(np.float64)]),
+        "orc_ea_discretized_create": (vp, [i64, i32, p(np.int64), p(np.float64), p(np.int64), i32]),
         "orc_sk_f64_create": (vp, [i64, p(np.float64)]),
         "orc_sk_bin_create": (vp, [i64, p(np.uint8)]),
         "orc_qt_create": (vp, [i64, i64, f64]),
@@ -235,6 +236,13 @@ class Graph:
     def ea_f64(cls, A, J):
         A = np.ascontiguousarray(A, np.int64); J = np.ascontiguousarray(J, np.float64)
         return cls(lib().orc_ea_f64_create(A.shape[0], A.shape[1], A, J))
+
+    @classmethod
+    def ea_discretized(cls, A, cJ, lev=(-1, 0, 1)):
+        """GraphEANormalDiscretized{Int,LEV,2D} from the continuous couplings cJ (EA.jl:311-344)."""
+        A = np.ascontiguousarray(A, np.int64); cJ = np.ascontiguousarray(cJ, np.float64)
+        lev = np.ascontiguousarray(lev, np.int64)
+        return cls(lib().orc_ea_discretized_create(A.shape[0], A.shape[1], A, cJ, lev, len(lev)))
 
     @classmethod
     def sk_f64(cls, J):

@@ -173,10 +173,10 @@ struct orc_graph {
 int orc_kind(const orc_graph *g) { return g->kind; }
 int64_t orc_getN(const orc_graph *g) { return g->N; }
 double orc_quant_fourK(const orc_graph *g) { return g->kind == ORC_QUANT ? g->X0->fourK : g->fourK; }
-orc_graph *orc_inner_graph(orc_graph *g) { return g->kind == ORC_QUANT ? g->X0 : g; } /* Interface.jl:239-240 */
+orc_graph *orc_inner_graph(orc_graph *g) { return (g->kind == ORC_QUANT || g->kind == ORC_EA_DISCR) ? g->X0 : g; } /* Interface.jl:239-240 */
 
 static int is_discr(const orc_graph *g) { return g->kind == ORC_EA_INT || g->kind == ORC_QT; }
-static int is_double(const orc_graph *g) { return g->kind == ORC_QUANT; }
+static int is_double(const orc_graph *g) { return g->kind == ORC_QUANT || g->kind == ORC_EA_DISCR; }
 
 /* gen_EA — src/graphs/EA.jl:24-43.  Column-major linear index, first coordinate fastest;
  * for every site and dimension one forward bond, recorded at both ends; rows sorted. */
@@ -286,6 +286,33 @@ static orc_graph *ea_f64_create_shared(int64_t N, int twoD, const int64_t *A, do
 }
 orc_graph *orc_ea_f64_create(int64_t N, int twoD, const int64_t *A, const double *J) { return ea_f64_create_shared(N, twoD, A, (double *)J, 1); }
 
+/* GraphEANormalDiscretized{Int,LEV,twoD} <: DoubleGraph{DiscrGraph{Int},Float64} — EA.jl:311-344 with explicit continuous
+ * couplings cJ (the constructor draws them with gen_J(randn)): every coupling is split by discretize (Common.jl:38-49:
+ * nearest level, the first one wins ties) into a level dJ, which goes to the inner GraphEA{Int,LEV}, and a residual
+ * rJ = cJ - dJ. The residual part has exactly the arithmetic of GraphEANormal on rJ (energy EA.jl:362-388 vs :584-611,
+ * update_cache_residual! :452-487 vs :613-653, delta_energy_residual :489-497 vs :655-663), so it is held as one. */
+orc_graph *orc_ea_discretized_create(int64_t N, int twoD, const int64_t *A, const double *cJ, const int64_t *lev, int nlev)
+{
+    orc_graph *g = (orc_graph *)calloc(1, sizeof(orc_graph));
+    g->kind = ORC_EA_DISCR; g->N = N; g->twoD = twoD; g->M = 1;
+    int64_t *dJ = (int64_t *)malloc((size_t)(N * twoD) * 8);
+    double *rJ = (double *)malloc((size_t)(N * twoD) * 8);
+    for (int64_t a = 0; a < N * twoD; a++) {
+        double x = cJ[a];
+        int64_t d = lev[0]; double r = x - (double)d;
+        for (int l = 1; l < nlev; l++) {
+            double r1 = x - (double)lev[l];
+            if (fabs(r1) < fabs(r)) { d = lev[l]; r = r1; }
+        }
+        dJ[a] = d; rJ[a] = r;
+    }
+    g->X0 = orc_ea_int_create(N, twoD, A, dJ, lev, nlev);
+    g->X1 = (orc_graph **)calloc(1, sizeof(orc_graph *));
+    g->X1[0] = orc_ea_f64_create(N, twoD, A, rJ);
+    free(dJ); free(rJ);
+    return g;
+}
+
 static orc_graph *sk_f64_create_shared(int64_t N, double *J, int own)
 {
     orc_graph *g = (orc_graph *)calloc(1, sizeof(orc_graph));
@@ -365,6 +392,7 @@ void orc_graph_free(orc_graph *g)
         for (int64_t k = g->M - 1; k >= 0; k--) { orc_graph_free(g->X1[k]); free(g->C1[k]); }
         free(g->X1); free(g->C1); orc_graph_free(g->X0);
     }
+    if (g->kind == ORC_EA_DISCR) { orc_graph_free(g->X1[0]); free(g->X1); orc_graph_free(g->X0); }
     free(g->A); free(g->uA); free(g->nuA);
     if (g->owns_J) { free(g->Ji); free(g->Jd); free(g->Jb); }
     free(g->lfi); free(g->lfi_last); free(g->lfd); free(g->lfd_last);
@@ -462,6 +490,11 @@ double orc_energy(orc_graph *g, const uint64_t *s)
         return (double)qt_energy0(g, s) * g->fourK / 4;
     case ORC_EMPTY:
         return 0.0;
+    case ORC_EA_DISCR: { /* EA.jl:362-388: convert(Float64, E0 + E1) */
+        double E0 = orc_energy(g->X0, s);
+        double E1 = orc_energy(g->X1[0], s);
+        return E0 + E1;
+    }
     case ORC_QUANT: { /* QT.jl:185-199 */
         double E = orc_energy(g->X0, s);
         for (int64_t k = 1; k <= g->M; k++) {
@@ -488,6 +521,7 @@ static void qt_neighbors(const orc_graph *g, int64_t i, int64_t *k1, int64_t *k2
 double orc_delta_energy_residual(orc_graph *g, const uint64_t *s, int64_t move) /* QT.jl:270-281 */
 {
     (void)s;
+    if (g->kind == ORC_EA_DISCR) return orc_delta_energy(g->X1[0], s, move); /* EA.jl:489-497: -lfields[move] */
     if (g->kind != ORC_QUANT) return 0.0;
     int64_t k = (move - 1) / g->Nk + 1, i = (move - 1) % g->Nk + 1;
     return orc_delta_energy(g->X1[k - 1], g->C1[k - 1], i) / (double)g->M;
@@ -508,6 +542,7 @@ double orc_delta_energy(orc_graph *g, const uint64_t *s, int64_t move)
     }
     case ORC_EMPTY: return 0.0;
     case ORC_QUANT: /* QT.jl:283-286 */
+    case ORC_EA_DISCR: /* EA.jl:519-523 */
         return orc_delta_energy(g->X0, s, move) + orc_delta_energy_residual(g, s, move);
     }
     return NAN;
@@ -608,6 +643,12 @@ static void update_cache(orc_graph *g, uint64_t *s, int64_t move)
         orc_spinflip(g->X1[k - 1], g->C1[k - 1], i);
         return;
     }
+    case ORC_EA_DISCR: /* EA.jl:390-450. When the two caches disagree on move_last the reference updates them one
+                        * after the other (:394-398); when they agree, its fused body performs the same two updates
+                        * (both swaps when move_last == move, both ordinary updates otherwise). */
+        update_cache(g->X0, s, move);
+        update_cache(g->X1[0], s, move); /* update_cache_residual! :452-487 */
+        return;
     }
 }
 
@@ -627,6 +668,7 @@ int orc_neighbors(const orc_graph *g, int64_t i, int64_t *out)
     }
     case ORC_QT: qt_neighbors(g, i, &out[0], &out[1]); return 2;
     case ORC_EMPTY: return 0;
+    case ORC_EA_DISCR: return orc_neighbors(g->X0, i, out); /* EA.jl:525 */
     case ORC_QUANT: {
         qt_neighbors(g->X0, i, &out[0], &out[1]);
         int64_t k = (i - 1) / g->Nk + 1, j = (i - 1) % g->Nk + 1;
@@ -640,7 +682,7 @@ int orc_neighbors(const orc_graph *g, int64_t i, int64_t *out)
 
 int orc_allDE(const orc_graph *g, double *out) /* Interface.jl:200-201,270 */
 {
-    const orc_graph *h = g->kind == ORC_QUANT ? g->X0 : g;
+    const orc_graph *h = (g->kind == ORC_QUANT || g->kind == ORC_EA_DISCR) ? g->X0 : g;
     if (!is_discr(h)) return -1;
     for (int k = 0; k < h->nDE; k++) out[k] = h->DE[k];
     return h->nDE;

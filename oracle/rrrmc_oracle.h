@@ -27,7 +27,8 @@ enum {
     ORC_SK_F64 = 4, /* GraphSKNormal           <: SimpleGraph{Float64} src/graphs/SK.jl:181-199 */
     ORC_QT     = 5, /* GraphQT{fourK}          <: DiscrGraph{Float64}  src/graphs/QT.jl:42-54   */
     ORC_QUANT  = 6, /* GraphQuant{fourK,G}     <: DoubleGraph          src/graphs/QT.jl:126-147 */
-    ORC_EMPTY  = 7  /* GraphEmpty              <: SimpleGraph{Int}     src/graphs/Empty.jl:14-31*/
+    ORC_EMPTY  = 7, /* GraphEmpty              <: SimpleGraph{Int}     src/graphs/Empty.jl:14-31*/
+    ORC_EA_DISCR = 8 /* GraphEANormalDiscretized{Int,LEV,twoD} <: DoubleGraph  src/graphs/EA.jl:311-344 */
 };
 
 typedef struct orc_graph orc_graph;
@@ -75,6 +76,8 @@ int     orc_gen_J_f64(int64_t N, int twoD, const int64_t *A, const double *draws
 /* ---- graph constructors (A, site indices are 1-based like the reference) ---- */
 orc_graph *orc_ea_int_create(int64_t N, int twoD, const int64_t *A, const int64_t *J, const int64_t *lev, int nlev);
 orc_graph *orc_ea_f64_create(int64_t N, int twoD, const int64_t *A, const double *J);
+/* GraphEANormalDiscretized with integer levels: cJ = the continuous couplings (slot-aligned with A, symmetric) */
+orc_graph *orc_ea_discretized_create(int64_t N, int twoD, const int64_t *A, const double *cJ, const int64_t *lev, int nlev);
 orc_graph *orc_sk_f64_create(int64_t N, const double *J /* [N*N] row-major, symmetric, zero diag */);
 orc_graph *orc_sk_bin_create(int64_t N, const uint8_t *J /* [N*N] 0/1, symmetric, zero diag */);
 orc_graph *orc_qt_create(int64_t N, int64_t M, double fourK);

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "lib", "librrrmc_b200.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4
-EA_PM1, EA_INT, EA_F64, SK_F64, SK_BIN, QT, QUANT, EMPTY = 1, 2, 3, 4, 5, 6, 7, 8
+EA_PM1, EA_INT, EA_F64, SK_F64, SK_BIN, QT, QUANT, EMPTY, EA_DISCR = 1, 2, 3, 4, 5, 6, 7, 8, 9
 SCHED_CHECKERBOARD, SCHED_RANDOM_SITE = 0, 1
 CB_AUTO, CB_PLANES, CB_SPARSE, CB_POISSON = 0, 1, 2, 3
 CBP_LEN = 64 + 3 * 32   # count tables of the poisson procedure: TA[64] | TB0[32] | TB[32] | TC[32]
@@ -44,6 +44,7 @@ SIGNATURES = {
     "rrrmc_ctx_launch_count": (_i32, [_vp, C.POINTER(C.c_uint64)]),
     "rrrmc_ctx_flush_l2": (_i32, [_vp]),
     "rrrmc_graph_ea_create": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _pp]),
+    "rrrmc_graph_ea_discretized_create": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _i32, _pp]),
     "rrrmc_graph_sk_create": (_i32, [_vp, _i64, _i32, _vp, _pp]),
     "rrrmc_graph_quant_create": (_i32, [_vp, _i64, _i64, _f64, _f64, _i32, _vp, _pp]),
     "rrrmc_graph_qt_create": (_i32, [_vp, _i64, _i64, _f64, _pp]),

@@ -344,6 +344,53 @@ extern "C" rrrmc_status_t rrrmc_graph_fourK(const rrrmc_graph_t *g, double *four
     return RRRMC_OK;
 }
 
+// GraphEANormalDiscretized{Int,LEV,2D} (EA.jl:311-344) from explicit continuous couplings cJ: discretize (Common.jl:38-49:
+// nearest level, the first wins ties) splits every coupling into a level dJ — the inner GraphEA{Int,LEV} — and a residual
+// rJ = cJ - dJ (Float64). allΔE is that of the inner graph for the FULL level tuple (EA.jl:295-309), used or not.
+extern "C" rrrmc_status_t rrrmc_graph_ea_discretized_create(rrrmc_ctx_t *ctx, int L, int D, const int64_t *A, const double *cJ,
+                                                            const int64_t *lev, int nlev, rrrmc_graph_t **out)
+{
+    RR_ARG(ctx && A && cJ && lev && out, "rrrmc_graph_ea_discretized_create: NULL argument");
+    RR_ARG(nlev >= 1 && nlev <= 16, "LEV must hold 1..16 levels, given %d", nlev);
+    RR_ARG(L >= 2, "L must be >= 2, given: %d", L);
+    RR_ARG(D >= 1 && D <= 4, "D must be in 1..4, given: %d", D);
+    for (int l = 0; l < nlev; l++) RR_ARG(lev[l] >= -127 && lev[l] <= 127, "levels must fit int8, given %lld", (long long)lev[l]);
+    const int twoD = 2 * D;
+    const int64_t N = ipow(L, D);
+    std::vector<int64_t> dJ((size_t)N * twoD);
+    std::vector<double> rJ((size_t)N * twoD);
+    for (int64_t a = 0; a < N * twoD; a++) {
+        const double x = cJ[a];
+        RR_ARG(std::isfinite(x), "cJ[%lld] is not finite", (long long)a);
+        int64_t d = lev[0]; double r = x - (double)d;
+        for (int l = 1; l < nlev; l++) {
+            const double r1 = x - (double)lev[l];
+            if (fabs(r1) < fabs(r)) { d = lev[l]; r = r1; }
+        }
+        dJ[a] = d; rJ[a] = r;
+    }
+    rrrmc_graph *g = nullptr;
+    RR_TRY(rrrmc_graph_ea_create(ctx, L, D, RRRMC_EA_INT, A, dJ.data(), &g));   // validates A and the symmetry of dJ
+    g->kind = RRRMC_EA_DISCR; g->M = 2;   // two local-field caches per chain: inner (integer) and residual (Float64)
+    g->Jd = rJ;
+    std::set<int64_t> es = { 0 };
+    for (int n = 0; n < twoD; n++) {
+        std::set<int64_t> nw;
+        for (int64_t e : es) for (int l = 0; l < nlev; l++) { nw.insert(e + lev[l]); nw.insert(e - lev[l]); }
+        es.swap(nw);
+    }
+    std::set<int64_t> de;
+    for (int64_t e : es) de.insert(2 * (e < 0 ? -e : e));
+    g->allDE.clear();
+    for (int64_t d : de) g->allDE.push_back((double)d);
+    if (g->allDE.size() > 64) { rrrmc_set_error("too many ΔE classes (%zu > 64)", g->allDE.size()); rrrmc_graph_destroy(g); return RRRMC_ERR_UNSUPPORTED; }
+    RR_CUDA(cudaMalloc(&g->d_Jd, sizeof(double) * N * twoD));
+    RR_CUDA(cudaMemcpy(g->d_Jd, g->Jd.data(), sizeof(double) * N * twoD, cudaMemcpyHostToDevice));
+    RR_CUDA(cudaDeviceSynchronize());
+    *out = g;
+    return RRRMC_OK;
+}
+
 extern "C" rrrmc_status_t rrrmc_graph_destroy(rrrmc_graph_t *g)
 {
     if (!g) return RRRMC_OK;
@@ -566,7 +613,7 @@ extern "C" rrrmc_status_t rrrmc_delta_energy_residual(rrrmc_state_t *s, int64_t 
     rrrmc_graph *g = s->g;
     RR_ARG(site >= 1 && site <= g->N, "site %lld out of range 1..%lld", (long long)site, (long long)g->N);
     RR_CUDA(cudaSetDevice(g->ctx->device));
-    if (g->kind != RRRMC_QUANT) { for (int64_t r = 0; r < s->R; r++) dE_out[r] = 0.0; return RRRMC_OK; } // Interface.jl:261
+    if (g->kind != RRRMC_QUANT && g->kind != RRRMC_EA_DISCR) { for (int64_t r = 0; r < s->R; r++) dE_out[r] = 0.0; return RRRMC_OK; } // Interface.jl:261
     RR_TRY(chain_sync_to_multispin(s));
     return chain_delta_energy_site(s, site - 1, 1, dE_out);
 }

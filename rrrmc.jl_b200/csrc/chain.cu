@@ -48,7 +48,7 @@ struct gview {
     int coop;                    // 1: a warp serves this chain (lane 0 leads)
 };
 __device__ __forceinline__ int sget(const uint64_t *s, int i) { return (int)((s[i >> 6] >> (i & 63)) & 1ull); }
-__device__ __forceinline__ bool is_ea(int kind) { return kind == RRRMC_EA_PM1 || kind == RRRMC_EA_INT || kind == RRRMC_EA_F64; }
+__device__ __forceinline__ bool is_ea(int kind) { return kind == RRRMC_EA_PM1 || kind == RRRMC_EA_INT || kind == RRRMC_EA_F64 || kind == RRRMC_EA_DISCR; }
 __device__ __forceinline__ bool is_sk(int kind) { return kind == RRRMC_SK_F64 || kind == RRRMC_SK_BIN; }
 
 // -- SK slice k of the view (SK proper: k = 0): current / last halves of the field pair
@@ -161,6 +161,8 @@ __device__ __forceinline__ double gv_delta_energy(const gview &c, int i, bool in
     switch (c.kind) {
     case RRRMC_EA_F64: return -c.lfd[i];                       // EA.jl:655-663
     case RRRMC_EA_PM1: case RRRMC_EA_INT: return -(double)c.lfi[i]; // EA.jl:266-275
+    case RRRMC_EA_DISCR:                                       // EA.jl:519-523: convert(Float64, ΔE0 + ΔE1)
+        return inner ? -(double)c.lfi[i] : __dadd_rn(-(double)c.lfi[i], -c.lfd[i]);
     case RRRMC_SK_F64: case RRRMC_SK_BIN: return sk_delta(c, c.kind, 0, i);
     case RRRMC_QT: return qt_delta(c, i);
     case RRRMC_QUANT: {                                        // QT.jl:283-286, residual :270-281
@@ -173,6 +175,7 @@ __device__ __forceinline__ double gv_delta_energy(const gview &c, int i, bool in
 }
 __device__ __forceinline__ double gv_delta_residual(const gview &c, int i) // Interface.jl:254-261; QT.jl:270-281
 {
+    if (c.kind == RRRMC_EA_DISCR) return -c.lfd[i];            // EA.jl:489-497
     if (c.kind != RRRMC_QUANT) return 0.0;
     return sk_delta(c, c.inner, i / c.Nk, i % c.Nk) / (double)c.M;
 }
@@ -204,16 +207,36 @@ __device__ void gv_spinflip(gview &c, int i, bool inner = false)
     if (c.kind == RRRMC_QT || (c.kind == RRRMC_QUANT && inner)) return;   // Interface.jl:87: no cache
     if (c.kind == RRRMC_QUANT) { sk_update_cache(c, c.inner, i / c.Nk, i % c.Nk); return; } // QT.jl:172-183
     if (is_sk(c.kind)) { sk_update_cache(c, c.kind, 0, i); return; }
-    // GraphEA update_cache! EA.jl:224-264 / :613-653
+    // GraphEA update_cache! EA.jl:224-264 / :613-653. GraphEANormalDiscretized (EA.jl:390-450) = the integer update of
+    // its inner GraphEA, then (unless only inner_graph(X) is being flipped) update_cache_residual! (:452-487), which is
+    // the GraphEANormal update on the residual couplings; each cache keeps its own move_last (ml[0], ml[1]).
     int U[MAXDEG], nU = 0;
     for (int k = 0; k < c.twoD; k++) {
         const int y = c.A[(int64_t)i * c.twoD + k];
         if (nU == 0 || U[nU - 1] != y) U[nU++] = y;
     }
     const int N = c.N;
-    if (c.kind == RRRMC_EA_F64) {
-        double *lf = c.lfd, *lfl = c.lfd + N;
+    if (c.kind != RRRMC_EA_F64) {
+        int32_t *lf = c.lfi, *lfl = c.lfi + N;
         if (c.ml[0] == i) {
+            for (int k = 0; k < nU; k++) { const int t = lf[U[k]]; lf[U[k]] = lfl[U[k]]; lfl[U[k]] = t; }
+            lf[i] = -lf[i]; lfl[i] = -lfl[i];
+        } else {
+            for (int k = 0; k < nU; k++) lfl[U[k]] = lf[U[k]];
+            const int sx = sget(c.s, i);
+            for (int k = 0; k < c.twoD; k++) {
+                const int y = c.A[(int64_t)i * c.twoD + k];
+                lf[y] -= 4 * (1 - 2 * (sx ^ sget(c.s, y))) * (int)c.J8[(int64_t)i * c.twoD + k];
+            }
+            const int lfm = lf[i];
+            lfl[i] = lfm; lf[i] = -lfm;
+            c.ml[0] = i;
+        }
+    }
+    if (c.kind == RRRMC_EA_F64 || (c.kind == RRRMC_EA_DISCR && !inner)) {
+        int32_t &ml = c.ml[c.kind == RRRMC_EA_DISCR ? 1 : 0];
+        double *lf = c.lfd, *lfl = c.lfd + N;
+        if (ml == i) {
             for (int k = 0; k < nU; k++) { const double t = lf[U[k]]; lf[U[k]] = lfl[U[k]]; lfl[U[k]] = t; }
             lf[i] = -lf[i]; lfl[i] = -lfl[i];
             return;
@@ -227,23 +250,8 @@ __device__ void gv_spinflip(gview &c, int i, bool inner = false)
         }
         const double lfm = lf[i];
         lfl[i] = lfm; lf[i] = -lfm;
-    } else {
-        int32_t *lf = c.lfi, *lfl = c.lfi + N;
-        if (c.ml[0] == i) {
-            for (int k = 0; k < nU; k++) { const int t = lf[U[k]]; lf[U[k]] = lfl[U[k]]; lfl[U[k]] = t; }
-            lf[i] = -lf[i]; lfl[i] = -lfl[i];
-            return;
-        }
-        for (int k = 0; k < nU; k++) lfl[U[k]] = lf[U[k]];
-        const int sx = sget(c.s, i);
-        for (int k = 0; k < c.twoD; k++) {
-            const int y = c.A[(int64_t)i * c.twoD + k];
-            lf[y] -= 4 * (1 - 2 * (sx ^ sget(c.s, y))) * (int)c.J8[(int64_t)i * c.twoD + k];
-        }
-        const int lfm = lf[i];
-        lfl[i] = lfm; lf[i] = -lfm;
+        ml = i;
     }
-    c.ml[0] = i;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -504,7 +512,7 @@ __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
     const int N = P.N;
     SRC src(P, r, h.rng_n);
     const double beta = P.beta[r];
-    const bool dbl = P.kind == RRRMC_QUANT;                                        // DoubleGraph
+    const bool dbl = P.kind == RRRMC_QUANT || P.kind == RRRMC_EA_DISCR;            // DoubleGraph
     const bool discr_full = P.kind == RRRMC_EA_PM1 || P.kind == RRRMC_EA_INT || P.kind == RRRMC_QT; // X <: DiscrGraph
     // rrrMC builds its cache on inner_graph(X) (RRRMC.jl:170-171, :239-240); bklMC on X itself (:325)
     const bool discr = P.sampler == CHAIN_RRR ? (discr_full || dbl) : discr_full;
@@ -644,7 +652,7 @@ __global__ void k_chain_lfields(chain_params P)
     if (P.kind == RRRMC_QT) return;
     if (is_ea(P.kind)) { // EA.jl:201-215 / :591-605
         const int sx = 2 * sget(s, x) - 1;
-        if (P.kind == RRRMC_EA_F64) {
+        if (P.kind == RRRMC_EA_F64 || P.kind == RRRMC_EA_DISCR) {   // DISCR: residual couplings (EA.jl:368-384)
             double lf = 0.0;
             for (int k = 0; k < P.twoD; k++) {
                 const int y = P.A[(int64_t)x * P.twoD + k];
@@ -652,7 +660,8 @@ __global__ void k_chain_lfields(chain_params P)
                 lf = __dsub_rn(lf, __dmul_rn(__dmul_rn(P.Jd[(int64_t)x * P.twoD + k], (double)sx), sy));
             }
             P.lfd[r * 2 * P.N + x] = 2 * lf; P.lfd[r * 2 * P.N + P.N + x] = 0.0;
-        } else {
+        }
+        if (P.kind != RRRMC_EA_F64) {
             int lf = 0;
             for (int k = 0; k < P.twoD; k++) {
                 const int y = P.A[(int64_t)x * P.twoD + k];
@@ -725,6 +734,11 @@ __global__ void k_chain_energy_sum(chain_params P, double *E_out, int mode)
         long long n = 0;
         for (int x = 0; x < P.N; x++) n += P.lfi[r * 2 * P.N + x] / 2;
         E = (double)n / 2.0;
+        if (P.kind == RRRMC_EA_DISCR) {   // EA.jl:362-388: E0 + E1, E1 as in GraphEANormal on the residuals
+            double e = 0.0;
+            for (int x = 0; x < P.N; x++) e = __dadd_rn(e, P.lfd[r * 2 * P.N + x] / 2);
+            E = __dadd_rn(E, e / 2);
+        }
     } else if (is_sk(P.kind)) E = sk_slice_energy(P, P.kind, r, 0, s);
     else if (P.kind == RRRMC_QT) E = (double)qt_energy0(P, s) * P.fourK / 4; // QT.jl:84
     else {                        // GraphQuant, QT.jl:185-199
@@ -832,7 +846,8 @@ static rrrmc_status_t chain_ensure(rrrmc_state *s, int cache)
         s->chain = c;
         const size_t RN = (size_t)s->R * g->N;
         if (graph_has_fields(g)) {
-            if (c->f64) RR_CUDA(cudaMalloc(&c->lfd, RN * 2 * 8)); else RR_CUDA(cudaMalloc(&c->lfi, RN * 2 * 4));
+            if (c->f64 || g->kind == RRRMC_EA_DISCR) RR_CUDA(cudaMalloc(&c->lfd, RN * 2 * 8));
+            if (!c->f64 || g->kind == RRRMC_EA_DISCR) RR_CUDA(cudaMalloc(&c->lfi, RN * 2 * 4));
         }
         RR_CUDA(cudaMalloc(&c->ml, sizeof(int32_t) * s->R * g->M));
         RR_CUDA(cudaMalloc(&c->sw, (size_t)s->R * g->M));
@@ -1061,7 +1076,7 @@ static rrrmc_status_t sampler_cache(const rrrmc_graph *g, int sampler, int *cach
 {
     const bool discr_full = g->kind == RRRMC_EA_PM1 || g->kind == RRRMC_EA_INT || g->kind == RRRMC_QT;
     if (sampler == CHAIN_STANDARD) *cache = 0;
-    else if (sampler == CHAIN_RRR) *cache = (discr_full || g->kind == RRRMC_QUANT) ? 1 : 2;
+    else if (sampler == CHAIN_RRR) *cache = (discr_full || g->kind == RRRMC_QUANT || g->kind == RRRMC_EA_DISCR) ? 1 : 2;
     else *cache = discr_full ? 1 : 2;
     return RRRMC_OK;
 }

@@ -285,6 +285,32 @@ class GraphEANormal(AbstractGraph):
         self._h = h
 
 
+class GraphEANormalDiscretized(AbstractGraph):
+    """GraphEANormalDiscretized(L, D, LEV) <: DoubleGraph{DiscrGraph{Int},Float64} (src/graphs/EA.jl:311-360) with integer
+    levels: unit-variance Gaussian couplings `cJ`, discretised to the nearest of LEV (inner GraphEA{Int,LEV}) plus Float64
+    residuals. Same energy as GraphEANormal on `cJ`; rrrMC samples the levels reduced-rejection and filters the residual
+    by accept(c, -βΔE1) (RRRMC.jl:221-290). Pass `A`, `cJ` to wrap an existing instance."""
+    ET = float
+
+    def __init__(self, L, D, LEV=(-1, 0, 1), replicas=1, A=None, cJ=None, rng=None, ctx=None):
+        if not all(float(l).is_integer() for l in LEV):
+            raise NotImplementedError("non-integer levels (DFloat64 path, EA.jl:360) are not on this engine's path yet")
+        if len(set(LEV)) != len(LEV):
+            raise ValueError(f"repeated levels in LEV: {LEV}")
+        self.L, self.D, self.LEV, self.replicas = L, D, tuple(int(l) for l in LEV), int(replicas)
+        self.ctx = ctx or Context.default()
+        self.A = gen_EA(L, D) if A is None else np.ascontiguousarray(A, np.int64)
+        self.N = self.A.shape[0]
+        if cJ is None:
+            rng = rng or np.random.default_rng()
+            cJ = gen_J(lambda n: rng.standard_normal(n), self.A)   # gen_J(Float64, N, A) do randn() end, EA.jl:323-325
+        self.cJ = np.ascontiguousarray(cJ, np.float64)
+        lev = np.ascontiguousarray(self.LEV, np.int64)
+        h = C.c_void_p()
+        check(lib().rrrmc_graph_ea_discretized_create(self.ctx.h, L, D, ptr(self.A), ptr(self.cJ), ptr(lev), len(lev), C.byref(h)))
+        self._h = h
+
+
 def gen_J_gauss(N, rng=None):
     """gen_J_gauss (src/graphs/SK.jl:170-179): symmetric N(0, 1/N) couplings, zero diagonal, as an (N, N) array."""
     rng = rng or np.random.default_rng()

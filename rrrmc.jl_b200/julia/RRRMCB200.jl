@@ -16,7 +16,7 @@ export standardMC, rrrMC, bklMC
 const lib = get(ENV, "RRRMC_B200_LIB", joinpath(@__DIR__, "..", "lib", "librrrmc_b200.so"))
 
 const RRRMC_OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = Cint(0), Cint(-1), Cint(-2), Cint(-3), Cint(-4)
-const EA_PM1, EA_INT, EA_F64, SK_F64, SK_BIN, QT, QUANT, EMPTY = Cint.(1:8)
+const EA_PM1, EA_INT, EA_F64, SK_F64, SK_BIN, QT, QUANT, EMPTY, EA_DISCR = Cint.(1:9)
 
 last_error() = unsafe_string(ccall((:rrrmc_last_error, lib), Cstring, ()))
 function check(st::Cint)
@@ -72,6 +72,15 @@ function GraphEA(L::Integer, D::Integer, A::Matrix{Int64}, J::Matrix; replicas::
     check(ccall((:rrrmc_graph_ea_create, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
                 ctx().h, L, D, kind, permutedims(A), Jc, r))
     _finish(r[], kind == EA_F64 ? Float64 : Int, replicas, kind)
+end
+"GraphEANormalDiscretized{Int,LEV,twoD} (src/graphs/EA.jl:311-360) from the continuous couplings cJ (N×2D, slot-aligned with A)."
+function GraphEANormalDiscretized(L::Integer, D::Integer, LEV::NTuple{K,Int}, A::Matrix{Int64}, cJ::Matrix{Float64}; replicas::Integer = 1) where {K}
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    lev = collect(Int64, LEV)
+    check(ccall((:rrrmc_graph_ea_discretized_create, lib), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Cint, Ref{Ptr{Cvoid}}),
+                ctx().h, L, D, permutedims(A), Matrix{Float64}(permutedims(cJ)), lev, length(lev), r))
+    _finish(r[], Float64, replicas, EA_DISCR)
 end
 "GraphEA(L, D) with ±1 couplings drawn here (src/graphs/EA.jl:181-191)."
 function GraphEA(L::Integer, D::Integer; replicas::Integer = 1)

@@ -22,6 +22,7 @@ CASES = {
     "EA(2,3)": lambda: ffi.Graph.ea_int(*ea_instance(2, 3, (-1, 1), 2), (-1, 1)),
     "EA(3,3,(-1,0,1))": lambda: ffi.Graph.ea_int(*ea_instance(3, 3, (-1, 0, 1), 3), (-1, 0, 1)),
     "EANormal(3,2)": lambda: ffi.Graph.ea_f64(*ea_instance(3, 2, seed=4, gaussian=True)),
+    "EANormalDiscretized(3,2,(-1,0,1))": lambda: ffi.Graph.ea_discretized(*ea_instance(3, 2, seed=14, gaussian=True), (-1, 0, 1)),
     "SK(10)": lambda: ffi.Graph.sk_bin(sk_binary(10, 5)),
     "SKNormal(10)": lambda: ffi.Graph.sk_f64(sk_gauss(10, 6)),
     "QT(12,4)": lambda: ffi.Graph.qt(12, 4, 0.73),
@@ -41,7 +42,7 @@ def compute():
         out[f"{name}/energy"] = np.array([g.energy(s0)])
         out[f"{name}/delta_energy"] = np.array([g.delta_energy(s0, i) for i in range(1, g.N + 1)])
         out[f"{name}/neighbors1"] = g.neighbors(1)
-        if g.kind in (ffi.EA_INT, ffi.QT, ffi.QUANT):
+        if g.kind in (ffi.EA_INT, ffi.QT, ffi.QUANT, ffi.EA_DISCR):
             out[f"{name}/allDE"] = g.allDE()
         for sname, fn in SAMPLERS.items():
             gg = mk(); s = s0.copy()

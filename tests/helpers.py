@@ -52,6 +52,8 @@ def reference_graphs(seed=1):
         out[f"EA({L},{D},(-1,0,1))"] = ffi.Graph.ea_int(A, J, (-1, 0, 1))
         A, J = ea_instance(L, D, seed=seed + 2, gaussian=True)
         out[f"EANormal({L},{D})"] = ffi.Graph.ea_f64(A, J)
+        A, cJ = ea_instance(L, D, seed=seed + 5, gaussian=True)
+        out[f"EANormalDiscretized({L},{D},(-1,0,1))"] = ffi.Graph.ea_discretized(A, cJ, (-1, 0, 1))
     out["SK(10)"] = ffi.Graph.sk_bin(sk_binary(10, seed))
     out["SKNormal(10)"] = ffi.Graph.sk_f64(sk_gauss(10, seed))
     out["Quant(10,8,Empty)"] = ffi.Graph.quant(10, 8, 0.5, 2.0, ffi.EMPTY)

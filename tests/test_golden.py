@@ -31,6 +31,8 @@ def _engine_graph(name, R):
         A, J = ea_instance(3, 3, (-1, 0, 1), 3); return rb.GraphEA(3, 3, (-1, 0, 1), replicas=R, A=A, J=J)
     if name == "EANormal(3,2)":
         A, J = ea_instance(3, 2, seed=4, gaussian=True); return rb.GraphEANormal(3, 2, replicas=R, A=A, J=J)
+    if name == "EANormalDiscretized(3,2,(-1,0,1))":
+        A, cJ = ea_instance(3, 2, seed=14, gaussian=True); return rb.GraphEANormalDiscretized(3, 2, (-1, 0, 1), replicas=R, A=A, cJ=cJ)
     if name == "SK(10)":
         return rb.GraphSK(10, replicas=R, J=sk_binary(10, 5))
     if name == "SKNormal(10)":

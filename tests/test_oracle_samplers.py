@@ -48,7 +48,7 @@ def test_energy_consistency_all_samplers(name):
         if thr == 1.0:  # acc_rate can round to exactly 1.0 for tiny N (λ=5/N), where `<` fails — reference behaviour
             assert r.staged_its > 0
 
-    if g.kind == ffi.QUANT:  # runtests.jl:165-190: samplers on inner_graph(X) as well
+    if g.kind in (ffi.QUANT, ffi.EA_DISCR):  # runtests.jl:165-190: samplers on inner_graph(X) as well
         g0 = g.inner()
         hook, bad = _check_hook(g0, s)
         ffi.bklMC(g0, BETA, ITERS, s, src, step=STEP, hook=hook)
@@ -151,3 +151,44 @@ def test_trace_record_replay_bit_exact(sampler):
     if sampler == "standard":
         assert kind[0] == 0
         assert (np.diff(np.flatnonzero(kind == 0)) <= 2).all()
+
+
+def test_discretized_splits_couplings_and_energy():
+    """GraphEANormalDiscretized (EA.jl:311-344): levels + residuals add up to the continuous couplings (discretize,
+    Common.jl:38-49: nearest level, first wins ties), energy = inner + residual = the GraphEANormal energy of cJ, and
+    delta_energy = energy(flipped) - energy (the generic definition, Interface.jl:130-138)."""
+    A, cJ = ea_instance(3, 3, seed=31, gaussian=True)
+    g = ffi.Graph.ea_discretized(A, cJ, (-1, 0, 1))
+    gn = ffi.Graph.ea_f64(A, cJ)
+    assert np.array_equal(g.allDE(), ffi.Graph.ea_int(A, np.zeros_like(cJ, dtype=np.int64), (-1, 0, 1)).allDE())
+    s = random_config(g.N, seed=2)
+    E = g.energy(s)
+    assert abs(E - gn.energy(s)) < 1e-12 * g.N
+    assert abs(E - (g.inner().energy(s) + (E - g.inner().energy(s)))) == 0
+    g.energy(s)
+    for i in range(1, g.N + 1):
+        d = g.delta_energy(s, i)
+        t = s.copy(); t[(i - 1) >> 6] ^= np.uint64(1 << ((i - 1) & 63))
+        assert abs(d - (gn.energy(t) - gn.energy(s))) < 1e-11
+    assert tuple(g.neighbors(1)) == tuple(gn.neighbors(1))
+
+
+def test_boltzmann_stationarity_discretized():
+    """rrrMC(::DoubleGraph) on GraphEANormalDiscretized samples exp(-βE) of the FULL energy (levels + residuals)."""
+    A, cJ = ea_instance(3, 2, seed=12, gaussian=True)
+    g = ffi.Graph.ea_discretized(A, cJ, (-1, 0, 1))
+    N, beta = 9, 0.8
+    p = _boltzmann(g, N, beta)
+    for thr in (float("nan"), 1.0):
+        src = ffi.PhiloxDraws(77, chain=2)
+        s = src.config(N)
+        counts = np.zeros(2 ** N)
+
+        def hook(it, E, acc):
+            counts[int(s[0])] += 1
+            return True
+        ffi.rrrMC(g, beta, 3_000_000, s, src, step=4, hook=hook, staged_thr=thr)
+        n = counts.sum()
+        big = p > 2e-3
+        rel = np.abs(counts[big] / n - p[big]) / p[big]
+        assert rel.max() < 0.1, (thr, rel.max())
