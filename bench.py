@@ -297,7 +297,7 @@ def run_ours(args, rank, world, local_rank):
                        "accepted_counters": "off in the timed loop"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": {"poisson": "k_checkerboard_poisson_persist<%d,3>" % NW, "sparse": "k_checkerboard_sparse<3,true>",
+                         "kernel": {"poisson": ("k_checkerboard_poisson_persist2<%d,4>" if NW >= 2 else "k_checkerboard_poisson_persist<%d,3>") % NW, "sparse": "k_checkerboard_sparse<3,true>",
                                     "planes": "k_checkerboard<3,true>"}[METHOD],
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_SWEEP // 2, "launch_ms": launch_ms,
                          "note": "bound by integer instruction issue (ALU pipe, ncu), not by HBM: the 32 MiB state is L2 resident (see DESIGN.md §5)"},

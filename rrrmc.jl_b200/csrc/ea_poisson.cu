@@ -140,14 +140,27 @@ __device__ __forceinline__ uint32_t cbp_flip_planes(const uint32_t (&b)[2 * D], 
 // first, then level 2, then level 3, the oracle's order — are placed by a loop whose trip count is the warp's maximum
 // (one or two). (3) What is left (a count past the twelve overflow slots, an ambiguous lookup bucket whose base count
 // is below the static slots; probability < 1e-6) runs the complete scalar procedure cbp_slow().
+// the random words of a task's fast path: call 0 = (X0, X1, P[0], P[1]), call 1 = P[2..5] when NW > 2
+template <int NW> struct cbp_words { philox_out A; uint32_t P[NW > 2 ? 6 : 2]; };
+template <int NW>
+__device__ __forceinline__ cbp_words<NW> cbp_draw(const cbp_params &p, uint32_t c1, uint32_t c2)
+{
+    cbp_words<NW> r;
+    r.A = cbp_philox(p, 0u, c1, c2);
+    r.P[0] = r.A.z; r.P[1] = r.A.w;
+    if (NW > 2) { const philox_out B = cbp_philox(p, 1u, c1, c2); r.P[2] = B.x; r.P[3] = B.y; r.P[4] = B.z; r.P[5] = B.w; }
+    return r;
+}
+
 template <int D, int NW>
 __device__ __forceinline__ bool cbp_task_hits(const cbp_params &p, const uint2 *__restrict__ bucket, uint32_t c1, uint32_t c2,
-                                              uint32_t (&m)[4], uint32_t (&g)[4], uint32_t (&h)[4])
+                                              const cbp_words<NW> &rw, uint32_t (&m)[4], uint32_t (&g)[4], uint32_t (&h)[4])
 {
     constexpr int NS = 4 * NW - 1;
-    const philox_out A = cbp_philox(p, 0u, c1, c2);
-    uint32_t P[6] = { A.z, A.w, 0u, 0u, 0u, 0u };
-    if (NW > 2) { const philox_out B = cbp_philox(p, 1u, c1, c2); P[2] = B.x; P[3] = B.y; P[4] = B.z; P[5] = B.w; }
+    const philox_out A = rw.A;
+    uint32_t P[6] = { 0u, 0u, 0u, 0u, 0u, 0u };
+#pragma unroll
+    for (int q = 0; q < (NW > 2 ? 6 : 2); q++) P[q] = rw.P[q];
     const uint2 e = bucket[A.x >> 22];
     const uint32_t a = e.y + (A.x > e.x ? 1u : 0u);            // level-1 count (>= 64: ambiguous bucket, slow path)
     bool slow = a > (uint32_t)NS;
@@ -303,7 +316,7 @@ __global__ void __launch_bounds__(256, MINB) k_checkerboard_poisson(const __grid
         if (D >= 3) { const uint2 jb = __ldg(reinterpret_cast<const uint2 *>(p.jmask + 2 * (size_t)i + 1)); neg[4] = jb.x; neg[5] = jb.y; }
     }
     uint32_t m[4], gg[4], h[4];
-    const bool slow = cbp_task_hits<D, NW>(p, p.bucket, i, (uint32_t)g, m, gg, h);
+    const bool slow = cbp_task_hits<D, NW>(p, p.bucket, i, (uint32_t)g, cbp_draw<NW>(p, i, (uint32_t)g), m, gg, h);
 
     uint32_t sc[4], b[4][2 * D];
     if (FULL) {
@@ -401,7 +414,7 @@ __global__ void __launch_bounds__(256, MINB) k_checkerboard_poisson_persist(cons
     bool first = true;
     for (;;) {
         uint32_t m[4], gg[4], h[4];
-        const bool slow = cbp_task_hits<D, NW>(p, sbucket, i, (uint32_t)g, m, gg, h);
+        const bool slow = cbp_task_hits<D, NW>(p, sbucket, i, (uint32_t)g, cbp_draw<NW>(p, i, (uint32_t)g), m, gg, h);
         if (first) {
             asm volatile("griddepcontrol.wait;" ::: "memory");   // the previous half-sweep is complete and visible
             request();
@@ -433,6 +446,132 @@ __global__ void __launch_bounds__(256, MINB) k_checkerboard_poisson_persist(cons
         reinterpret_cast<uint4 *>(p.spins)[icur * W4 + g] = make_uint4(sc[0], sc[1], sc[2], sc[3]);
         if (p.flips) reinterpret_cast<uint4 *>(p.flips)[icur * W4 + g] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
         if (!more) break;
+    }
+}
+
+// Two tasks per thread: the same site for two replica groups (g and g + G/2). A third of a task's instructions is
+// not Monte Carlo at all — brick decoding, neighbour indices, 64-bit address formation, the loop — and all of it is a
+// function of the site only, so the pair shares it (the second task's addresses are the first's plus a constant).
+// 128 threads per block cover the same 256-task brick as k_checkerboard_poisson_persist; same results bit for bit.
+template <int NW, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_checkerboard_poisson_persist2(const __grid_constant__ cbp_params p, int colour)
+{
+    constexpr int D = 3, NT = 128;
+    __shared__ uint4 stage[2][2 * D + 1][NT];
+    __shared__ uint2 sbucket[CBP_BUCKETS];
+    const int t = threadIdx.x, L = p.L;
+#pragma unroll
+    for (int k = 0; k < CBP_BUCKETS / NT; k++) sbucket[t + NT * k] = __ldg(p.bucket + t + NT * k);
+    __syncthreads();
+    const int Gh = p.G >> 1;                                   // groups per half: the thread owns g0 and g0 + Gh
+    const int g0 = t & (Gh - 1), a = t >> (p.Gshift - 1);
+    const int ax = a & ((1 << p.sh_hbx) - 1), ay = (a >> p.sh_hbx) & ((1 << p.sh_by) - 1), az = a >> (p.sh_hbx + p.sh_by);
+    const uint32_t W4 = (uint32_t)p.W >> 2, LL = (uint32_t)L * L;
+    const uint4 *sp4 = reinterpret_cast<const uint4 *>(p.spins);
+    uint32_t i, nb[2 * D], neg[2 * D];
+    auto locate = [&](int b) {
+        const int q = __float2int_rz(((float)b + 0.5f) * p.inv_nbx);
+        const int X = b - q * p.nbx;
+        const int Z = __float2int_rz(((float)q + 0.5f) * p.inv_nby), Y = q - Z * p.nby;
+        const int y = (Y << p.sh_by) + ay, z = Z * p.bz + az;
+        const int x = (X << (p.sh_hbx + 1)) + 2 * ax + ((y + z + colour) & 1);
+        const uint32_t row = (uint32_t)L * (uint32_t)(y + L * z);
+        i = row + x;
+        nb[0] = row + (x + 1 == L ? 0 : x + 1);
+        nb[1] = row + (x == 0 ? L - 1 : x - 1);
+        nb[2] = y + 1 == L ? i - (uint32_t)(L - 1) * L : i + L;
+        nb[3] = y == 0 ? i + (uint32_t)(L - 1) * L : i - L;
+        nb[4] = z + 1 == L ? i - (uint32_t)(L - 1) * LL : i + LL;
+        nb[5] = z == 0 ? i + (uint32_t)(L - 1) * LL : i - LL;
+    };
+    auto request = [&]() {
+        const uint4 *c = sp4 + (i * W4 + g0);
+        cp_async16(&stage[0][0][t], c); cp_async16(&stage[1][0][t], c + Gh);
+#pragma unroll
+        for (int k = 0; k < 2 * D; k++) {
+            const uint4 *n = sp4 + (nb[k] * W4 + g0);
+            cp_async16(&stage[0][1 + k][t], n); cp_async16(&stage[1][1 + k][t], n + Gh);
+        }
+    };
+    auto signs = [&]() {
+        const uint4 ja = __ldg(p.jmask + 2 * (size_t)i);
+        const uint2 jb = __ldg(reinterpret_cast<const uint2 *>(p.jmask + 2 * (size_t)i + 1));
+        neg[0] = ja.x; neg[1] = ja.y; neg[2] = ja.z; neg[3] = ja.w; neg[4] = jb.x; neg[5] = jb.y;
+    };
+    int b = blockIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (b >= p.nbricks) return;
+    locate(b);
+    signs();
+    bool first = true;
+    for (;;) {
+        uint32_t m[2][4], gg[2][4], h[2][4];
+        bool slow[2];
+        // both Philox chains in one basic block: their rounds interleave (each chain alone waits on its own latency)
+        const cbp_words<NW> rw0 = cbp_draw<NW>(p, i, (uint32_t)g0), rw1 = cbp_draw<NW>(p, i, (uint32_t)(g0 + Gh));
+        slow[0] = cbp_task_hits<D, NW>(p, sbucket, i, (uint32_t)g0, rw0, m[0], gg[0], h[0]);
+        slow[1] = cbp_task_hits<D, NW>(p, sbucket, i, (uint32_t)(g0 + Gh), rw1, m[1], gg[1], h[1]);
+        if (first) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            request();
+            first = false;
+        }
+        cp_async_wait_all();
+        uint4 *out = reinterpret_cast<uint4 *>(p.spins) + (i * W4 + g0);
+        uint4 *outf = p.flips ? reinterpret_cast<uint4 *>(p.flips) + (i * W4 + g0) : nullptr;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const uint4 c = stage[j][0][t];
+            uint32_t sc[4] = { c.x, c.y, c.z, c.w }, bp[4][2 * D], fl[4];
+#pragma unroll
+            for (int k = 0; k < 2 * D; k++) {
+                const uint4 v = stage[j][1 + k][t];
+                bp[0][k] = lop3p<P_XOR3>(sc[0], v.x, neg[k]); bp[1][k] = lop3p<P_XOR3>(sc[1], v.y, neg[k]);
+                bp[2][k] = lop3p<P_XOR3>(sc[2], v.z, neg[k]); bp[3][k] = lop3p<P_XOR3>(sc[3], v.w, neg[k]);
+            }
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                if (slow[j]) bp[w][0] |= h[j][w];
+                fl[w] = cbp_flip_planes<D>(bp[w], m[j][w], gg[j][w]);
+                sc[w] ^= fl[w];
+            }
+            out[j * Gh] = make_uint4(sc[0], sc[1], sc[2], sc[3]);
+            if (outf) outf[j * Gh] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+        }
+        b += gridDim.x;
+        if (b >= p.nbricks) break;
+        locate(b); request(); signs();
+    }
+}
+
+template <int NW, int MINB>
+static cudaError_t launch_persist2_one(const cbp_params &p, int colour, int sm_count, cudaStream_t st)
+{
+    static int occ = 0;
+    if (!occ) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_checkerboard_poisson_persist2<NW, MINB>, 128, 0);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) occ = 1;
+    }
+    int grid = sm_count * occ;
+    if (p.variant & 128) grid = 2;
+    if (grid > p.nbricks) grid = p.nbricks;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (p.variant & 32) ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, k_checkerboard_poisson_persist2<NW, MINB>, p, colour);
+}
+template <int MINB>
+static cudaError_t launch_persist2(const cbp_params &p, int colour, int sm_count, cudaStream_t st)
+{
+    switch (p.NW) {
+    case 1: return launch_persist2_one<1, MINB>(p, colour, sm_count, st);
+    case 2: return launch_persist2_one<2, MINB>(p, colour, sm_count, st);
+    case 4: return launch_persist2_one<4, MINB>(p, colour, sm_count, st);
+    default: return launch_persist2_one<6, MINB>(p, colour, sm_count, st);
     }
 }
 
@@ -505,6 +644,18 @@ rrrmc_status_t launch_checkerboard_poisson(rrrmc_ctx *ctx, cbp_params &p, int D,
     }
     if (p.brick && p.nbricks < (1 << 22) && !(p.variant & 8)) {   // persistent, software-pipelined kernel
         const int mb = p.variant & 3;   // RRRMC_CB_VARIANT (tuning): resident blocks per SM; 3 (80 registers) measured best
+        // two tasks (groups g, g + G/2) per thread: measured 3-4 % faster where the hit generation is long (NW >= 2),
+        // slower where it is short. RRRMC_CB_VARIANT bit 9 forces it, bit 10 forbids it (tuning, tests).
+        if (p.G >= 2 && !(p.variant & 1024) && (p.NW >= 2 || (p.variant & 512))) {
+            cudaError_t e2 = mb == 1 ? launch_persist2<6>(p, colour, ctx->sm_count, ctx->stream)
+                           : mb == 2 ? launch_persist2<5>(p, colour, ctx->sm_count, ctx->stream)
+                           : mb == 3 ? launch_persist2<3>(p, colour, ctx->sm_count, ctx->stream)
+                                     : launch_persist2<4>(p, colour, ctx->sm_count, ctx->stream);
+            ctx->launches++;
+            RR_CUDA(e2);
+            RR_CUDA(cudaGetLastError());
+            return RRRMC_OK;
+        }
         cudaError_t e = mb == 1 ? launch_persist<5>(p, colour, ctx->sm_count, ctx->stream)
                       : mb == 2 ? launch_persist<2>(p, colour, ctx->sm_count, ctx->stream)
                       : mb == 3 ? launch_persist<4>(p, colour, ctx->sm_count, ctx->stream)

@@ -131,11 +131,11 @@ def test_checkerboard_poisson_bit_exact_vs_cpu_model(L, D, R, beta, NW):
     assert not (got == C0)
 
 
-@pytest.mark.parametrize("variant", ["128", "8", "16", "32"])
+@pytest.mark.parametrize("variant", ["128", "8", "16", "32", "512", "640", "1024", "1152"])
 def test_checkerboard_poisson_kernel_variants_agree(variant, monkeypatch):
-    """The persistent kernel with two blocks (every block walks 32 bricks), the one-task-per-thread kernel, the row
-    mapping and the launch without programmatic serialization all produce the oracle's trajectory (warm β with one
-    static word: most tasks run the second tier)."""
+    """The persistent kernels (one task per thread; two tasks = two replica groups of a site per thread) with two blocks
+    (every block walks 32 bricks), the one-task-per-thread kernel, the row mapping and the launch without programmatic
+    serialization all produce the oracle's trajectory (warm β with one static word: most tasks run the second tier)."""
     L, D, R, beta, NW = 16, 3, 1024, 0.8, 1
     A, J = ea_instance(L, D, seed=11)
     X = rb.GraphEA(L, D, replicas=R, A=A, J=J)
