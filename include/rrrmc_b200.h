@@ -84,6 +84,11 @@ rrrmc_status_t rrrmc_graph_sk_create(rrrmc_ctx_t *ctx, int64_t N, int coupling_k
  * (GraphQ0T, :19-31; J_inner NULL). All M slices share J_inner [Nk*Nk]; fourK = round(2/β·log coth(βΓ/M), digits=8). */
 rrrmc_status_t rrrmc_graph_quant_create(rrrmc_ctx_t *ctx, int64_t Nk, int64_t M, double Gamma, double beta,
                                         int inner_kind, const void *J_inner, rrrmc_graph_t **out);
+/* Replaces GraphQEAT (QAliases.jl:51-81) = GraphQuant(N, M, Γ, β, GraphEANormal{2D}, L, A, J): the transverse-field
+ * Edwards-Anderson model, M Trotter slices of one GraphEANormal instance (A, J in the reference layout, as for
+ * rrrmc_graph_ea_create with RRRMC_EA_F64). */
+rrrmc_status_t rrrmc_graph_quant_ea_create(rrrmc_ctx_t *ctx, int L, int D, int64_t M, double Gamma, double beta,
+                                           const int64_t *A, const double *J, rrrmc_graph_t **out);
 /* Replaces GraphQT{fourK}(N, M) (QT.jl:46-54) = inner_graph(X::GraphQuant) (Interface.jl:239-240). */
 rrrmc_status_t rrrmc_graph_qt_create(rrrmc_ctx_t *ctx, int64_t N, int64_t M, double fourK, rrrmc_graph_t **out);
 /* the fourK type parameter of a GraphQuant / GraphQT (QT.jl:42,165) */

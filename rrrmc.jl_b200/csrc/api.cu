@@ -336,6 +336,27 @@ extern "C" rrrmc_status_t rrrmc_graph_quant_create(rrrmc_ctx_t *ctx, int64_t Nk,
     *out = g;
     return RRRMC_OK;
 }
+// GraphQEAT (QAliases.jl:51-81): GraphQuant(N, M, Γ, β, GraphEANormal{2D}, L, A, J) — M Trotter slices of one
+// GraphEANormal instance (QT.jl:139-147: the slices share A and J and keep separate local-field caches).
+extern "C" rrrmc_status_t rrrmc_graph_quant_ea_create(rrrmc_ctx_t *ctx, int L, int D, int64_t M, double Gamma, double beta,
+                                                      const int64_t *A, const double *J, rrrmc_graph_t **out)
+{
+    RR_ARG(ctx && A && J && out, "rrrmc_graph_quant_ea_create: NULL argument");
+    RR_ARG(Gamma >= 0, "Γ must be non-negative, given: %g", Gamma);                           // QT.jl:164
+    RR_ARG(M > 2, "M must be greater than 2, given: %lld", (long long)M);
+    RR_ARG(std::isfinite(beta) && beta > 0, "β must be finite and positive, given: %g", beta);
+    rrrmc_graph *e = nullptr;
+    RR_TRY(rrrmc_graph_ea_create(ctx, L, D, RRRMC_EA_F64, A, J, &e));   // validates A and J, uploads d_A and d_Jd
+    const int64_t Nk = e->N;
+    if (!(Nk * M < ((int64_t)1 << 31))) { rrrmc_graph_destroy(e); rrrmc_set_error("Nk = %lld, M = %lld out of range", (long long)Nk, (long long)M); return RRRMC_ERR_ARG; }
+    e->kind = RRRMC_QUANT; e->inner = RRRMC_EA_F64; e->Nk = Nk; e->M = M; e->N = Nk * M;
+    e->Gamma = Gamma; e->beta = beta; e->sN = sqrt((double)Nk); e->bipartite = false;
+    e->fourK = nearbyint(2.0 / beta * log(1.0 / tanh(beta * Gamma / (double)M)) * 1e8) / 1e8;  // QT.jl:165
+    e->allDE = { 0.0, e->fourK };                                                              // QT.jl:111
+    e->max_deg = 2 + e->twoD;
+    *out = e;
+    return RRRMC_OK;
+}
 extern "C" rrrmc_status_t rrrmc_graph_fourK(const rrrmc_graph_t *g, double *fourK)
 {
     RR_ARG(g && fourK, "NULL argument");
@@ -417,7 +438,10 @@ extern "C" rrrmc_status_t rrrmc_neighbors(const rrrmc_graph_t *g, int64_t site, 
         out[m++] = site + g->Nk - (site + g->Nk > g->N ? g->N : 0);
         if (g->kind == RRRMC_QUANT && g->inner != RRRMC_EMPTY) {
             const int64_t k = (site - 1) / g->Nk, i = (site - 1) % g->Nk + 1;
-            for (int64_t j = 1; j <= g->Nk; j++) if (j != i) out[m++] = k * g->Nk + j;
+            if (g->inner == RRRMC_EA_F64)            // GraphQEAT: the slice graph's uA row, shifted to the slice
+                for (int q = 0; q < g->nuA[i - 1]; q++) out[m++] = k * g->Nk + g->uA0[(i - 1) * g->twoD + q] + 1;
+            else
+                for (int64_t j = 1; j <= g->Nk; j++) if (j != i) out[m++] = k * g->Nk + j;
         }
     } else {
         m = g->nuA[site - 1];

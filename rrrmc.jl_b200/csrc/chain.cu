@@ -58,6 +58,7 @@ __device__ __forceinline__ double sk_delta(const gview &c, int skind, int k, int
 {
     if (skind == RRRMC_SK_F64) return c.lfd[sk_cur_off(c, k) + i];
     if (skind == RRRMC_SK_BIN) return (double)c.lfi[sk_cur_off(c, k) + i] / c.sN;
+    if (skind == RRRMC_EA_F64) return -c.lfd[(int64_t)k * 2 * c.Nk + i]; // GraphEANormal slice (GraphQEAT), EA.jl:655-663
     return 0.0; // GraphEmpty (Empty.jl:28-31)
 }
 // part of update_cache! that every lane of the serving warp runs: sites j = lane, lane+nl, ... of slice k
@@ -114,6 +115,31 @@ enum { COOP_EXIT = 0, COOP_SK_UPDATE = 1 };
 __device__ void sk_update_cache(gview &c, int skind, int k, int i)
 {
     if (skind == RRRMC_EMPTY) return;
+    if (skind == RRRMC_EA_F64) {   // GraphEANormal slice of a GraphQEAT (QAliases.jl:51): update_cache! EA.jl:613-653
+        double *lf = c.lfd + (int64_t)k * 2 * c.Nk, *lfl = lf + c.Nk;
+        const int64_t off = (int64_t)k * c.Nk;
+        int U[MAXDEG], nU = 0;
+        for (int q = 0; q < c.twoD; q++) {
+            const int y = c.A[(int64_t)i * c.twoD + q];
+            if (nU == 0 || U[nU - 1] != y) U[nU++] = y;
+        }
+        if (c.ml[k] == i) {
+            for (int q = 0; q < nU; q++) { const double t = lf[U[q]]; lf[U[q]] = lfl[U[q]]; lfl[U[q]] = t; }
+            lf[i] = -lf[i]; lfl[i] = -lfl[i];
+            return;
+        }
+        for (int q = 0; q < nU; q++) lfl[U[q]] = lf[U[q]];
+        const int sx = sget(c.s, (int)(off + i));
+        for (int q = 0; q < c.twoD; q++) {
+            const int y = c.A[(int64_t)i * c.twoD + q];
+            const double f = (double)(4 * (1 - 2 * (sx ^ sget(c.s, (int)(off + y)))));
+            lf[y] = __dsub_rn(lf[y], __dmul_rn(f, c.Jd[(int64_t)i * c.twoD + q]));
+        }
+        const double lfm = lf[i];
+        lfl[i] = lfm; lf[i] = -lfm;
+        c.ml[k] = i;
+        return;
+    }
     if (c.ml[k] == i) { c.sw[k] ^= 1; return; } // swap lfields <-> lfields_last (SK.jl:247-250)
     const int si = sget(c.s, (int)((int64_t)k * c.Nk + i));
     double lfm_d = 0; int lfm_i = 0;
@@ -196,7 +222,15 @@ template <class F> __device__ __forceinline__ void gv_for_neighbors(const gview 
         f(k1); f(k2);
         if (c.kind == RRRMC_QUANT && !inner && c.inner != RRRMC_EMPTY) {
             const int base = (i / c.Nk) * c.Nk, ii = i - base;
-            for (int j = 0; j < c.Nk; j++) if (j != ii) f(base + j);
+            if (c.inner == RRRMC_EA_F64) {              // neighbors(X1[k], j) = uA[j], shifted to the slice (QT.jl:288-321)
+                int prev = -1;
+                for (int q = 0; q < c.twoD; q++) {
+                    const int y = c.A[(int64_t)ii * c.twoD + q];
+                    if (y != prev) f(base + y);
+                    prev = y;
+                }
+            } else
+                for (int j = 0; j < c.Nk; j++) if (j != ii) f(base + j);
         }
     }
 }
@@ -677,6 +711,16 @@ __global__ void k_chain_lfields(chain_params P)
     const int k = x / P.Nk, i = x % P.Nk;
     const int64_t off = (int64_t)k * P.Nk, cur = r * 2 * P.N + (int64_t)k * 2 * P.Nk;
     const int si = sget(s, (int)(off + i));
+    if (skind == RRRMC_EA_F64) { // GraphEANormal slice, EA.jl:591-605
+        double lf = 0.0;
+        for (int q = 0; q < P.twoD; q++) {
+            const int y = P.A[(int64_t)i * P.twoD + q];
+            const double sy = (double)(2 * sget(s, (int)(off + y)) - 1);
+            lf = __dsub_rn(lf, __dmul_rn(__dmul_rn(P.Jd[(int64_t)i * P.twoD + q], (double)(2 * si - 1)), sy));
+        }
+        P.lfd[cur + i] = 2 * lf; P.lfd[cur + P.Nk + i] = 0.0;
+        return;
+    }
     if (skind == RRRMC_SK_F64) { // SK.jl:218-231
         double lf = 0.0;
         for (int j = 0; j < P.Nk; j++) lf = __dadd_rn(lf, __dmul_rn((double)(1 - 2 * (si ^ sget(s, (int)(off + j)))), P.Jd[(int64_t)j * P.Nk + i]));
@@ -696,6 +740,11 @@ __device__ double sk_slice_energy(const chain_params &P, int skind, int64_t r, i
         double n = 0.0;
         for (int i = 0; i < P.Nk; i++) n = __dsub_rn(n, P.lfd[cur + i] / 2);
         return n / 2;
+    }
+    if (skind == RRRMC_EA_F64) {   // EA.jl:606-611
+        double e = 0.0;
+        for (int i = 0; i < P.Nk; i++) e = __dadd_rn(e, P.lfd[cur + i] / 2);
+        return e / 2;
     }
     if (skind == RRRMC_SK_BIN) {
         long long sums = 0, n;
@@ -827,7 +876,7 @@ rrrmc_status_t chain_sync_from_multispin(rrrmc_state *s)
 
 static bool graph_f64_fields(const rrrmc_graph *g)
 {
-    return g->kind == RRRMC_EA_F64 || g->kind == RRRMC_SK_F64 || (g->kind == RRRMC_QUANT && g->inner == RRRMC_SK_F64);
+    return g->kind == RRRMC_EA_F64 || g->kind == RRRMC_SK_F64 || (g->kind == RRRMC_QUANT && (g->inner == RRRMC_SK_F64 || g->inner == RRRMC_EA_F64));
 }
 static bool graph_has_fields(const rrrmc_graph *g)
 {
@@ -905,7 +954,7 @@ static void chain_fill_params(rrrmc_state *s, chain_params &P)
     P.DE = c->d_DE; P.beta = c->d_beta;
     P.step = 1;
     // a warp per chain where an accepted flip costs O(N) (SK and GraphQuant over SK)
-    P.coop = (is_sk_kind(g->kind) || (g->kind == RRRMC_QUANT && g->inner != RRRMC_EMPTY)) ? 1 : 0;
+    P.coop = (is_sk_kind(g->kind) || (g->kind == RRRMC_QUANT && g->inner != RRRMC_EMPTY && g->inner != RRRMC_EA_F64)) ? 1 : 0;
 }
 
 static rrrmc_status_t chain_energy_init(rrrmc_state *s, chain_params &P, bool start_run = false)

@@ -396,6 +396,29 @@ class GraphQuant(AbstractGraph):
         return GraphQT(self.N, self.M, self.fourK, replicas=self.replicas, ctx=self.ctx)
 
 
+class GraphQEAT(GraphQuant):
+    """GraphQEAT(L, D, M, Γ, β) (src/QAliases.jl:51-81): GraphQuant over GraphEANormal{2D} — the transverse-field
+    Edwards-Anderson model. Couplings uniform in [-2, 2) (4*rand() - 2, QAliases.jl:62-64) unless `A`, `J` are given."""
+
+    def __init__(self, L, D, M, Γ, β, replicas=1, A=None, J=None, rng=None, ctx=None):
+        self.L, self.D = int(L), int(D)
+        self.A = gen_EA(L, D) if A is None else np.ascontiguousarray(A, np.int64)
+        self.Nk, self.M = self.A.shape[0], int(M)
+        self.N, self.Γ, self.β, self.replicas = self.Nk * self.M, float(Γ), float(β), int(replicas)
+        self.ctx = ctx or Context.default()
+        self.inner = "EANormal"
+        if J is None:
+            rng = rng or np.random.default_rng()
+            J = gen_J(lambda n: 4 * rng.random(n) - 2, self.A)
+        self.J = np.ascontiguousarray(J, np.float64)
+        h = C.c_void_p()
+        check(lib().rrrmc_graph_quant_ea_create(self.ctx.h, self.L, self.D, self.M, self.Γ, self.β, ptr(self.A), ptr(self.J), C.byref(h)))
+        self._h = h
+        fk = C.c_double()
+        check(lib().rrrmc_graph_fourK(self._h, C.byref(fk)))
+        self.fourK = fk.value
+
+
 def GraphQSKT(N, M, Γ, β, **kw):
     """GraphQSKT(N, M, Γ, β) (src/QAliases.jl:34-43)."""
     return GraphQuant(N, M, Γ, β, "SK", **kw)

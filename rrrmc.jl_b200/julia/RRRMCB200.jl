@@ -82,6 +82,14 @@ function GraphEANormalDiscretized(L::Integer, D::Integer, LEV::NTuple{K,Int}, A:
                 ctx().h, L, D, permutedims(A), Matrix{Float64}(permutedims(cJ)), lev, length(lev), r))
     _finish(r[], Float64, replicas, EA_DISCR)
 end
+"GraphQEAT (src/QAliases.jl:51-81): GraphQuant over GraphEANormal{2D}; A, J as N×2D matrices (reference layout)."
+function GraphQEAT(L::Integer, D::Integer, M::Integer, Γ::Float64, β::Float64, A::Matrix{Int64}, J::Matrix{Float64}; replicas::Integer = 1)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:rrrmc_graph_quant_ea_create, lib), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Int64, Cdouble, Cdouble, Ptr{Int64}, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+                ctx().h, L, D, M, Γ, β, permutedims(A), Matrix{Float64}(permutedims(J)), r))
+    _finish(r[], Float64, replicas, QUANT)
+end
 "GraphEA(L, D) with ±1 couplings drawn here (src/graphs/EA.jl:181-191)."
 function GraphEA(L::Integer, D::Integer; replicas::Integer = 1)
     N = L^D

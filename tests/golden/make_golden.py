@@ -29,6 +29,7 @@ CASES = {
     "Quant(6,4,SK)": lambda: ffi.Graph.quant(6, 4, 0.5, 2.0, ffi.SK_BIN, sk_binary(6, 7)),
     "Quant(6,4,SKNormal)": lambda: ffi.Graph.quant(6, 4, 0.5, 2.0, ffi.SK_F64, sk_gauss(6, 8)),
     "Quant(6,4,Empty)": lambda: ffi.Graph.quant(6, 4, 0.5, 2.0, ffi.EMPTY),
+    "QEAT(3,2,4)": lambda: (lambda AJ: ffi.Graph.quant(9, 4, 0.5, 2.0, ffi.EA_F64, AJ[1], AJ[0]))(ea_instance(3, 2, seed=15, gaussian=True)),
 }
 SAMPLERS = {"standardMC": ffi.standardMC, "rrrMC": ffi.rrrMC, "bklMC": ffi.bklMC}
 BETA, ITERS, STEP, SEED = 1.7, 600, 50, 20261017

@@ -59,4 +59,6 @@ def reference_graphs(seed=1):
     out["Quant(10,8,Empty)"] = ffi.Graph.quant(10, 8, 0.5, 2.0, ffi.EMPTY)
     out["Quant(10,8,SK)"] = ffi.Graph.quant(10, 8, 0.5, 2.0, ffi.SK_BIN, sk_binary(10, seed + 3))
     out["Quant(10,8,SKNormal)"] = ffi.Graph.quant(10, 8, 0.5, 2.0, ffi.SK_F64, sk_gauss(10, seed + 4))
+    A, J = ea_instance(3, 2, seed=seed + 6, gaussian=True)
+    out["QEAT(3,2,5)"] = ffi.Graph.quant(9, 5, 0.5, 2.0, ffi.EA_F64, J, A)   # GraphQEAT, QAliases.jl:51-81
     return out

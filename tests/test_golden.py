@@ -43,6 +43,8 @@ def _engine_graph(name, R):
         return rb.GraphQSKT(6, 4, 0.5, 2.0, replicas=R, J=sk_binary(6, 7))
     if name == "Quant(6,4,SKNormal)":
         return rb.GraphQSKNormalT(6, 4, 0.5, 2.0, replicas=R, J=sk_gauss(6, 8))
+    if name == "QEAT(3,2,4)":
+        A, J = ea_instance(3, 2, seed=15, gaussian=True); return rb.GraphQEAT(3, 2, 4, 0.5, 2.0, replicas=R, A=A, J=J)
     if name == "Quant(6,4,Empty)":
         return rb.GraphQ0T(6, 4, 0.5, 2.0, replicas=R)
     raise KeyError(name)

@@ -8,7 +8,7 @@ import pytest
 
 import rrrmc_b200 as rb
 from oracle import ffi
-from tests.helpers import sk_binary, sk_gauss
+from tests.helpers import ea_instance, sk_binary, sk_gauss
 
 pytestmark = pytest.mark.gpu
 
@@ -24,6 +24,11 @@ def _mk(name, R, seed=0):
     if name.startswith("QT"):
         N, M = [int(v) for v in name.split("(")[1][:-1].split(",")]
         return rb.GraphQT(N, M, 0.73, replicas=R), (lambda: ffi.Graph.qt(N, M, 0.73))
+    if name.startswith("QEAT"):   # GraphQEAT(L, D, M): GraphQuant over GraphEANormal (QAliases.jl:51-81)
+        L, D, M = [int(v) for v in name.split("(")[1][:-1].split(",")]
+        A, J = ea_instance(L, D, seed=seed + 6, gaussian=True)
+        return (rb.GraphQEAT(L, D, M, 0.5, 2.0, replicas=R, A=A, J=J),
+                (lambda: ffi.Graph.quant(L ** D, M, 0.5, 2.0, ffi.EA_F64, J, A)))
     # Quant(Nk,M,inner)
     a = name.split("(")[1][:-1].split(",")
     Nk, M, inner = int(a[0]), int(a[1]), a[2]
@@ -38,7 +43,7 @@ def _mk(name, R, seed=0):
 
 
 GRAPHS = ["SK(10)", "SKNormal(10)", "SK(37)", "SKNormal(33)", "QT(24,4)", "Quant(10,8,Empty)", "Quant(10,8,SK)",
-          "Quant(10,8,SKNormal)", "Quant(17,5,SK)"]
+          "Quant(10,8,SKNormal)", "Quant(17,5,SK)", "QEAT(3,2,5)", "QEAT(2,3,4)", "QEAT(4,3,6)"]
 
 
 @pytest.mark.parametrize("name", GRAPHS)
@@ -61,7 +66,7 @@ def test_interface_queries_match_oracle(name):
     g.energy(C0.chunks[2])
     all_dE = rb.all_delta_energy(X, C0, 2)
     assert all(all_dE[i] == g.delta_energy(C0.chunks[2], i + 1) for i in range(X.N))
-    if name.startswith(("QT", "Quant")):
+    if name.startswith(("QT", "Quant", "QEAT")):
         assert tuple(g.allDE()) == rb.allDeltaE(X)
     # ΔE ≡ energy(flipped) − energy (generic fallback Interface.jl:130-138), to rounding
     i = 3
@@ -70,7 +75,7 @@ def test_interface_queries_match_oracle(name):
     assert np.allclose(d, np.atleast_1d(rb.delta_energy(X, C0, i)), rtol=1e-9, atol=1e-9)
 
 
-@pytest.mark.parametrize("name", ["Quant(10,8,Empty)", "Quant(10,8,SK)", "Quant(10,8,SKNormal)", "Quant(9,7,SK)"])
+@pytest.mark.parametrize("name", ["Quant(10,8,Empty)", "Quant(10,8,SK)", "Quant(10,8,SKNormal)", "Quant(9,7,SK)", "QEAT(3,2,6)"])
 def test_quant_observables_match_oracle(name):
     R = 4
     X, mk = _mk(name, R)
