@@ -193,6 +193,13 @@ rrrmc_status_t rrrmc_bkl_mc(rrrmc_state_t *s, const double *beta, int64_t iters,
                             rrrmc_hook_fn hook, void *user, const rrrmc_opts_t *opts,
                             double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
 
+/* wtmMC(X, β, samples; step::Float64, seed, hook, C0) (RRRMC.jl:376-430): the rejection-free waiting-time method of
+ * Dall and Sibani on src/WaitingTimes.jl. `step` is an interval of the sampler's global time (divided by N inside,
+ * RRRMC.jl:394); at most `samples` rows of Es are produced, one per interval. The hook's `it` is the sample index k
+ * (the reference passes the time k·step/N); its `accepted` is the number of moves so far. */
+rrrmc_status_t rrrmc_wtm_mc(rrrmc_state_t *s, const double *beta, int64_t samples, double step, uint64_t seed,
+                            rrrmc_hook_fn hook, void *user, double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
+
 /* Replay: feed one chain the typed draw stream the reference consumed
  * (kind 0 = rand(1:n) value, 1 = rand() value) and reproduce its trajectory.
  * sampler: 0 standardMC, 1 rrrMC, 2 bklMC. Es: [Es_cap] energies at every `step`. */

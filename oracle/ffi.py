@@ -95,6 +95,7 @@ def lib():
         "orc_standardMC": (Result, [vp, f64, i64, i64, p(np.uint64), Draws, HOOK, vp, vp, i64]),
         "orc_rrrMC": (Result, [vp, f64, i64, i64, p(np.uint64), Draws, f64, f64, HOOK, vp, vp, i64]),
         "orc_bklMC": (Result, [vp, f64, i64, i64, p(np.uint64), Draws, HOOK, vp, vp, i64]),
+        "orc_wtmMC": (Result, [vp, f64, i64, f64, p(np.uint64), Draws, HOOK, vp, vp, i64]),
         "orc_check_discrete_cache": (i32, [vp, p(np.uint64), f64, p(np.int64), i64]),
         "orc_checkerboard_sweeps": (None, [i32, i32, i64, p(np.uint32), p(np.int8), p(np.uint64), i32, i32,
                                            C.c_uint64, C.c_uint64, i64, vp]),
@@ -339,6 +340,16 @@ def rrrMC(g, beta, iters, s, src, step=1, hook=None, staged_thr=float("nan"), st
 
 def bklMC(g, beta, iters, s, src, step=1, hook=None):
     return _run(lib().orc_bklMC, g, beta, iters, step, s, src, hook)
+
+
+def wtmMC(g, beta, samples, s, src, step=1.0, hook=None):
+    """wtmMC(X, β, samples; step::Float64) (RRRMC.jl:376-430); the hook's first argument is the sample index."""
+    cap = min(10 ** 8, samples)
+    Es = np.zeros(max(cap, 1), np.float64)
+    h, keep = _mk_hook(hook)
+    res = lib().orc_wtmMC(g.h, float(beta), int(samples), float(step), s, src.draws, h, None, Es.ctypes.data, cap)
+    assert res.status == 0, res.status
+    return Es[:min(res.nsamples, cap)].copy(), res
 
 
 def thresholds_fixed64(beta, D):

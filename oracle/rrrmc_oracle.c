@@ -1216,6 +1216,87 @@ orc_result orc_bklMC(orc_graph *X, double beta, int64_t iters, int64_t step, uin
 }
 
 /* ------------------------------------------------------------------------------------------
+ * wtmMC — RRRMC.jl:376-430: the rejection-free waiting-time method (Dall & Sibani) on src/WaitingTimes.jl.
+ * Every spin holds the absolute time of its next flip in a mutable binary min-heap (DataStructures.jl's
+ * MutableBinaryMinHeap, a third-party dependency that is not vendored in the reference: only the minimum and the
+ * update! of a handle's value are used, so any correct min-heap gives the same trajectory — flip times are
+ * continuous and ties have probability zero). τ_i = max(1, exp(βΔE_i)) (WaitingTimes.jl:15-16), waiting time
+ * -τ·log1p(-rand()) (:17-21). Draw order: N draws for the initial heap in site order (:25-35); per move one draw for
+ * the moved spin, then one per neighbour in neighbors() order (:39-51). `step` is a Float64 global-time interval,
+ * divided by N (:394); the hook receives the sample index k (the reference passes the time k·step/N).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { int64_t N; double *v; int64_t *node, *pos; } theap;   /* v[h], node[h] in heap order; pos[site] = h */
+static void th_swap(theap *H, int64_t a, int64_t b)
+{
+    double tv = H->v[a]; H->v[a] = H->v[b]; H->v[b] = tv;
+    int64_t tn = H->node[a]; H->node[a] = H->node[b]; H->node[b] = tn;
+    H->pos[H->node[a]] = a; H->pos[H->node[b]] = b;
+}
+static void th_up(theap *H, int64_t h) { while (h > 0) { int64_t q = (h - 1) / 2; if (!(H->v[h] < H->v[q])) break; th_swap(H, h, q); h = q; } }
+static void th_down(theap *H, int64_t h, int64_t n)
+{
+    for (;;) {
+        int64_t l = 2 * h + 1, r = l + 1, m = h;
+        if (l < n && H->v[l] < H->v[m]) m = l;
+        if (r < n && H->v[r] < H->v[m]) m = r;
+        if (m == h) break;
+        th_swap(H, h, m); h = m;
+    }
+}
+static void th_update(theap *H, int64_t site, double val)
+{
+    int64_t h = H->pos[site];
+    double old = H->v[h];
+    H->v[h] = val;
+    if (val < old) th_up(H, h); else th_down(H, h, H->N);
+}
+static inline double wt_tau(double beta, double dE) { double e = exp(beta * dE); return e > 1.0 ? e : 1.0; } /* max(1.0, exp(βΔE)) */
+static inline double wt_gen(double tau, orc_draws d) { return -tau * log1p(-d.f64(d.user)); }
+
+orc_result orc_wtmMC(orc_graph *X, double beta, int64_t samples, double step, uint64_t *s,
+                     orc_draws d, orc_hook hook, void *user, double *Es, int64_t Es_cap)
+{
+    orc_result res = { 0, 0, 0, 0, 0 };
+    int64_t N = X->N;
+    double E = orc_energy(X, s);
+    theap H; H.N = N;
+    H.v = (double *)malloc((size_t)N * 8); H.node = (int64_t *)malloc((size_t)N * 8); H.pos = (int64_t *)malloc((size_t)N * 8);
+    int64_t *nb = (int64_t *)malloc((size_t)(N + 2) * 8);
+    double *taus = (double *)malloc((size_t)N * 8);
+    for (int64_t i = 1; i <= N; i++) taus[i - 1] = wt_tau(beta, orc_delta_energy(X, s, i));   /* WaitingTimes.jl:28 */
+    for (int64_t i = 0; i < N; i++) { H.v[i] = wt_gen(taus[i], d); H.node[i] = i; H.pos[i] = i; th_up(&H, i); } /* push! */
+    free(taus);
+    step /= (double)N;
+    int64_t num_moves = 0;
+    double tmax = step * (double)samples, t = 0.0, nextstep = step;
+    while (t < tmax) {
+        double tp = H.v[0]; int64_t move = H.node[0] + 1;                                      /* top_with_handle */
+        int out = 0;
+        while (tp >= nextstep) {
+            PUSH_SAMPLE();
+            if (hook && !hook(user, res.nsamples, E, num_moves)) { out = 1; break; }
+            nextstep += step;
+            if (nextstep > tmax + 1e-10) { out = 1; break; }
+        }
+        if (out) break;
+        t = tp;
+        double dE = orc_delta_energy(X, s, move);                                              /* update_heap! :39-51 */
+        orc_spinflip(X, s, move);
+        th_update(&H, move - 1, t + wt_gen(wt_tau(beta, -dE), d));
+        int n = orc_neighbors(X, move, nb);
+        for (int a = 0; a < n; a++) {
+            int64_t j = nb[a];
+            th_update(&H, j - 1, t + wt_gen(wt_tau(beta, orc_delta_energy(X, s, j)), d));
+        }
+        E += dE;
+        num_moves++;
+    }
+    free(H.v); free(H.node); free(H.pos); free(nb);
+    res.iters_done = num_moves; res.accepted = num_moves;
+    return res;
+}
+
+/* ------------------------------------------------------------------------------------------
  * CPU model of the engine's checkerboard Metropolis (new-engine feature).
  * Deliberately scalar: per (site, replica) ΔE from the ±J definition (EA.jl:277-289 naive form),
  * acceptance = Metropolis (RRRMC.jl:39) with U drawn by the engine's per-task bit procedure:

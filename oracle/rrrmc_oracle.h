@@ -125,6 +125,10 @@ orc_result orc_rrrMC(orc_graph *g, double beta, int64_t iters, int64_t step, uin
 orc_result orc_bklMC(orc_graph *g, double beta, int64_t iters, int64_t step, uint64_t *chunks,
                      orc_draws d, orc_hook hook, void *user, double *Es, int64_t Es_cap);
 
+/* wtmMC(X, β, samples; step::Float64) — RRRMC.jl:376-430 + WaitingTimes.jl. The hook's `it` is the sample index. */
+orc_result orc_wtmMC(orc_graph *g, double beta, int64_t samples, double step, uint64_t *chunks,
+                     orc_draws d, orc_hook hook, void *user, double *Es, int64_t Es_cap);
+
 /* ΔE-class cache consistency (DeltaE.jl:120-136, ArraySets.jl:27-42); exposed for tests:
  * builds a cache for (g,chunks,beta), applies `nmoves` eager apply_move! calls on sites[], checks
  * consistency after each, and returns 0 when consistent. */

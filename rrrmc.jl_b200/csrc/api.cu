@@ -1085,6 +1085,14 @@ extern "C" rrrmc_status_t rrrmc_bkl_mc(rrrmc_state_t *s, const double *beta, int
     if (info) memset(info, 0, sizeof *info);
     return chain_run(s, CHAIN_BKL, beta, iters, step, seed, hook, user, &o, Es, Es_cap, info);
 }
+extern "C" rrrmc_status_t rrrmc_wtm_mc(rrrmc_state_t *s, const double *beta, int64_t samples, double step, uint64_t seed,
+                                       rrrmc_hook_fn hook, void *user, double *Es, int64_t Es_cap, rrrmc_run_info_t *info)
+{
+    RR_ARG(s, "state is NULL");
+    RR_CUDA(cudaSetDevice(s->g->ctx->device));
+    if (info) memset(info, 0, sizeof *info);
+    return chain_run_wtm(s, beta, samples, step, seed, hook, user, Es, Es_cap, info);
+}
 extern "C" rrrmc_status_t rrrmc_replay(rrrmc_state_t *s, int64_t replica, int sampler, double beta, int64_t iters, int64_t step,
                                        const uint8_t *kind, const int64_t *ival, const double *fval, int64_t ndraws,
                                        const rrrmc_opts_t *opts, double *Es, int64_t Es_cap, rrrmc_run_info_t *info)

@@ -512,6 +512,38 @@ __device__ double cc_apply_move(ccache &c, gview &X, int move, bool inner) // De
     return z / c.z;
 }
 
+// ------------------------------------------------------------------------------------------------
+// wtmMC (RRRMC.jl:376-430, WaitingTimes.jl): mutable binary min-heap of the spins' next flip times. The reference
+// uses DataStructures.MutableBinaryMinHeap; only its minimum and update! are observable, so any min-heap reproduces
+// the trajectory (flip times are continuous: ties have probability zero).
+// ------------------------------------------------------------------------------------------------
+struct wheap { int N; double *v; int32_t *node, *pos; };
+__device__ __forceinline__ void wh_swap(wheap &H, int a, int b)
+{
+    const double tv = H.v[a]; H.v[a] = H.v[b]; H.v[b] = tv;
+    const int tn = H.node[a]; H.node[a] = H.node[b]; H.node[b] = tn;
+    H.pos[H.node[a]] = a; H.pos[H.node[b]] = b;
+}
+__device__ void wh_up(wheap &H, int h) { while (h > 0) { const int q = (h - 1) / 2; if (!(H.v[h] < H.v[q])) break; wh_swap(H, h, q); h = q; } }
+__device__ void wh_down(wheap &H, int h)
+{
+    for (;;) {
+        const int l = 2 * h + 1, r = l + 1; int m = h;
+        if (l < H.N && H.v[l] < H.v[m]) m = l;
+        if (r < H.N && H.v[r] < H.v[m]) m = r;
+        if (m == h) break;
+        wh_swap(H, h, m); h = m;
+    }
+}
+__device__ void wh_update(wheap &H, int site, double val)
+{
+    const int h = H.pos[site];
+    const double old = H.v[h];
+    H.v[h] = val;
+    if (val < old) wh_up(H, h); else wh_down(H, h);
+}
+__device__ __forceinline__ double wt_tau(double beta, double dE) { const double e = exp(__dmul_rn(beta, dE)); return e > 1.0 ? e : 1.0; } // WaitingTimes.jl:15
+
 __device__ __forceinline__ gview make_view(const chain_params &P, int64_t r)
 {
     gview X;
@@ -556,7 +588,7 @@ __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
     double *Es = P.Es;
 
     dcache dc; ccache cc;
-    if (P.sampler != CHAIN_STANDARD) {
+    if (P.sampler != CHAIN_STANDARD && P.sampler != CHAIN_WTM) {
         if (discr) {
             dc.N = N; dc.L = P.nDE; dc.DE = P.DE; dc.t = h.t; dc.T = dc.Ta; dc.Tp = dc.Tb;
             dc.av = P.av + r * (int64_t)(2 * P.nDE) * N; dc.apos = P.apos + r * N; dc.cls = P.cls + r * N;
@@ -637,6 +669,35 @@ __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
             h.acc_rate = h.acc_rate * (1 - lambda) + acc * lambda;
             if (src.err) { h.done = 1; break; }
         }
+    } else if (P.sampler == CHAIN_WTM) { // RRRMC.jl:389-422
+        wheap H; H.N = N; H.v = P.wt_v + r * (int64_t)N; H.node = P.wt_node + r * (int64_t)N; H.pos = P.wt_pos + r * (int64_t)N;
+        auto gen_wt = [&](double tau) -> double { return __dmul_rn(-tau, log1p(-src.f64())); };   // WaitingTimes.jl:17-21
+        if (!h.built) {                  // THeap(X, C, β): all τ first, then N draws in site order (WaitingTimes.jl:25-35)
+            for (int i = 0; i < N; i++) H.v[i] = wt_tau(beta, gv_delta_energy(X, i));
+            for (int i = 0; i < N; i++) { H.v[i] = gen_wt(H.v[i]); H.node[i] = i; H.pos[i] = i; wh_up(H, i); }
+            h.built = 1;
+        }
+        for (;;) {
+            const double tp = H.v[0]; const int move = H.node[0];   // top_with_handle
+            bool out = false, paused = false;
+            while (tp >= h.wt_next) {
+                if (h.pending == 2) h.pending = 1; // resuming right after the hook of this sample
+                else { EMIT_SAMPLE(); if (emitted >= P.quota) { h.pending = 2; paused = true; break; } }
+                h.wt_next = __dadd_rn(h.wt_next, P.wt_step);
+                if (h.wt_next > P.wt_tmax + 1e-10) { out = true; break; }
+            }
+            if (paused) break;
+            if (out || src.err) { h.done = 1; break; }
+            h.pending = 0;
+            const double dE = gv_delta_energy(X, move);               // update_heap!, WaitingTimes.jl:39-51
+            gv_spinflip(X, move);
+            wh_update(H, move, __dadd_rn(tp, gen_wt(wt_tau(beta, -dE))));
+            gv_for_neighbors(X, move, false, [&](int j) {
+                wh_update(H, j, __dadd_rn(tp, gen_wt(wt_tau(beta, gv_delta_energy(X, j)))));
+            });
+            h.E += dE;
+            h.accepted++; h.it++;
+        }
     } else { // bklMC, RRRMC.jl:332-350
         for (;;) {
             if (!h.pending) {
@@ -663,7 +724,7 @@ __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
     }
 #undef EMIT_SAMPLE
     if (P.coop) __shfl_sync(FULLMASK, (int)COOP_EXIT, 0);
-    if (P.sampler != CHAIN_STANDARD) {
+    if (P.sampler != CHAIN_STANDARD && P.sampler != CHAIN_WTM) {
         if (discr) { for (int k = 0; k <= 2 * dc.L; k++) h.T[k] = dc.T[k]; h.z = dc.z; }
         else { h.z = cc.z; h.trefresh = cc.trefresh; }
     }
@@ -806,6 +867,7 @@ __global__ void k_chain_hdr_reset(chain_params P, int keep_rng)
     h.it = 0; h.accepted = 0; h.staged_its = 0; h.nextstep = P.step; h.skip = 0;
     if (!keep_rng) h.rng_n = 0;
     h.pending = 0; h.pmove = 0; h.status = 0; h.built = 0; h.trefresh = 0; h.done = 0;
+    h.wt_next = P.wt_step;
 }
 // delta_energy straight from the caches: what = 0 delta_energy(X,C,i), 1 residual; all replicas of one site
 __global__ void k_chain_delta_site(chain_params P, int site, int what, double *out)
@@ -854,6 +916,7 @@ void chain_free(rrrmc_state *s)
     cudaFree(c->d_Es); cudaFree(c->d_DE); cudaFree(c->d_beta); cudaFree(c->d_E); cudaFree(c->d_aux);
     cudaFree(c->d_tkind); cudaFree(c->d_tival); cudaFree(c->d_tfval);
     cudaFree(c->ea_lf); cudaFree(c->ea_apos); cudaFree(c->ea_av);
+    cudaFree(c->wt_v); cudaFree(c->wt_node); cudaFree(c->wt_pos);
     delete c;
     s->chain = nullptr;
 }
@@ -918,6 +981,12 @@ static rrrmc_status_t chain_ensure(rrrmc_state *s, int cache)
         RR_CUDA(cudaMalloc(&c->cls, RN));
         c->disc_ready = true;
     }
+    if (cache == 3 && !c->wtm_ready) {
+        RR_CUDA(cudaMalloc(&c->wt_v, RN * 8));
+        RR_CUDA(cudaMalloc(&c->wt_node, RN * 4));
+        RR_CUDA(cudaMalloc(&c->wt_pos, RN * 4));
+        c->wtm_ready = true;
+    }
     if (cache == 2 && !c->cont_ready) {
         c->levs = 0; while (((int64_t)1 << c->levs) < g->N) c->levs++;
         c->N2 = (int64_t)1 << c->levs;
@@ -952,6 +1021,7 @@ static void chain_fill_params(rrrmc_state *s, chain_params &P)
     P.hdr = c->hdr; P.av = c->av; P.apos = c->apos; P.cls = c->cls;
     P.dEs = c->dEs; P.dv = c->dv; P.dps = c->dps; P.csj = c->csj; P.csdE = c->csdE; P.csp = c->csp;
     P.DE = c->d_DE; P.beta = c->d_beta;
+    P.wt_v = c->wt_v; P.wt_node = c->wt_node; P.wt_pos = c->wt_pos;
     P.step = 1;
     // a warp per chain where an accepted flip costs O(N) (SK and GraphQuant over SK)
     P.coop = (is_sk_kind(g->kind) || (g->kind == RRRMC_QUANT && g->inner != RRRMC_EMPTY && g->inner != RRRMC_EA_F64)) ? 1 : 0;
@@ -1156,6 +1226,32 @@ rrrmc_status_t chain_run(rrrmc_state *s, int sampler, const double *beta, int64_
     s->ms_valid = false; // chains now own the configuration
     sk_dense_invalidate(s);
     if (chain_ea_eligible(s, sampler)) { RR_TRY(chain_ea_prepare(s, P)); s->chain_fields_valid = false; }
+    RR_TRY(chain_drive<src_philox>(s, P, hook, user, Es, Es_cap, info));
+    return RRRMC_OK;
+}
+
+rrrmc_status_t chain_run_wtm(rrrmc_state *s, const double *beta, int64_t samples, double step, uint64_t seed,
+                             rrrmc_hook_fn hook, void *user, double *Es, int64_t Es_cap, rrrmc_run_info_t *info)
+{
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    RR_ARG(beta, "beta is NULL");
+    for (int64_t r = 0; r < s->R; r++) RR_ARG(std::isfinite(beta[r]), "β must be finite, given: %g", beta[r]);
+    RR_ARG(samples >= 0, "samples must be >= 0, given %lld", (long long)samples);
+    RR_ARG(std::isfinite(step) && step > 0, "step must be a positive global-time interval, given %g", step);
+    RR_TRY(chain_ensure(s, 3));
+    RR_TRY(chain_sync_from_multispin(s));
+    chain_store *c = s->chain;
+    chain_params P; chain_fill_params(s, P);
+    P.sampler = CHAIN_WTM; P.iters = samples; P.step = 1; P.seed = seed;   // one row of Es per sample
+    P.wt_step = step / (double)g->N;                                        // step /= N, RRRMC.jl:394
+    P.wt_tmax = P.wt_step * (double)samples;                                // tmax = step * samples, :397
+    RR_CUDA(cudaMemcpyAsync(c->d_beta, beta, 8 * s->R, cudaMemcpyHostToDevice, ctx->stream));
+    k_chain_hdr_reset<<<div_up(P.R, 64), 64, 0, ctx->stream>>>(P, seed == 0);
+    ctx->launches++;
+    RR_TRY(chain_energy_init(s, P, true));
+    s->ms_valid = false;
+    sk_dense_invalidate(s);
+    if (samples == 0) { if (info) { info->nsamples = 0; info->iters_done = 0; info->launches = 0; info->device_ms = 0; info->accepted_total = 0; } return RRRMC_OK; }
     RR_TRY(chain_drive<src_philox>(s, P, hook, user, Es, Es_cap, info));
     return RRRMC_OK;
 }

@@ -3,7 +3,7 @@
 #pragma once
 #include "common.cuh"
 
-enum { CHAIN_STANDARD = 0, CHAIN_RRR = 1, CHAIN_BKL = 2 };
+enum { CHAIN_STANDARD = 0, CHAIN_RRR = 1, CHAIN_BKL = 2, CHAIN_WTM = 3 };
 static inline bool is_sk_kind(int k) { return k == RRRMC_SK_F64 || k == RRRMC_SK_BIN; }
 
 void chain_free(rrrmc_state *s);
@@ -15,6 +15,9 @@ rrrmc_status_t chain_quant_observable(rrrmc_state *s, int what, double arg, doub
 rrrmc_status_t chain_delta_energy_replica(rrrmc_state *s, int64_t replica, double *out);
 rrrmc_status_t chain_run(rrrmc_state *s, int sampler, const double *beta, int64_t iters, int64_t step, uint64_t seed,
                          rrrmc_hook_fn hook, void *user, const rrrmc_opts_t *o, double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
+// wtmMC(X, β, samples; step::Float64) (RRRMC.jl:376-430): `step` in units of the global time, before the division by N
+rrrmc_status_t chain_run_wtm(rrrmc_state *s, const double *beta, int64_t samples, double step, uint64_t seed,
+                             rrrmc_hook_fn hook, void *user, double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
 rrrmc_status_t chain_replay(rrrmc_state *s, int64_t replica, int sampler, double beta, int64_t iters, int64_t step,
                             const uint8_t *kind, const int64_t *ival, const double *fval, int64_t ndraws,
                             const rrrmc_opts_t *o, double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
@@ -30,13 +33,15 @@ struct chain_hdr {
     long long it, accepted, staged_its, nextstep, skip, rng_n;
     int t[2 * MAXL + 1];
     int pending, pmove, status, built, trefresh, done;
+    double wt_next;               // wtmMC: global time of the next sample (RRRMC.jl:396)
 };
 
 struct chain_store {
     int64_t R = 0, N = 0, N2 = 0;
     int levs = 0, nDE = 0;
     bool f64 = false;             // fp64 local fields (EA F64, SK F64, QUANT over SK F64)
-    bool cont_ready = false, disc_ready = false;
+    bool cont_ready = false, disc_ready = false, wtm_ready = false;
+    double *wt_v = nullptr; int32_t *wt_node = nullptr, *wt_pos = nullptr; // wtmMC heap [R][N]: times / sites in heap order, heap position of a site
     int32_t *lfi = nullptr;       // [R][2][N] (EA: cur,last; SK family: per slice [2][Nk])
     double *lfd = nullptr;
     int32_t *ml = nullptr;        // [R][M] move_last per slice (0-based, -1 = none)
@@ -73,6 +78,7 @@ struct chain_params {
     uint64_t seed;
     double staged_thr, staged_thr_fact;
     const uint8_t *tkind; const int64_t *tival; const double *tfval; int64_t tlen;
+    double *wt_v; int32_t *wt_node, *wt_pos; double wt_step, wt_tmax;  // wtmMC: heap, step/N, step/N·samples
     int fast;                     // 1: GraphEA ±J fast path (chain_ea.cu)
     int8_t *ea_lf; uint16_t *ea_apos, *ea_av;
 };

@@ -604,6 +604,49 @@ def bklMC(X, β, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, quiet=
     return _run(lib().rrrmc_bkl_mc, X, β, iters, seed, step, hook, C0, quiet, _opts(), "bklMC")
 
 
+def wtmMC(X, β, samples, *, seed=DEFAULT_SEED, step=1.0, hook=None, C0=None, quiet=False):
+    """wtmMC(X, β, samples; seed, step::Float64, hook, C0, quiet) (src/RRRMC.jl:376-430): the rejection-free waiting-time
+    method. `step` is measured in the sampler's global time (scaled by N inside); the hook receives the global time
+    k·step/N of sample k as its first argument, like the reference's."""
+    if not step > 0:
+        raise ValueError("step must be > 0")
+    st = X._ensure_state()
+    if C0 is None:
+        check(lib().rrrmc_state_randomize(st, seed if seed > 0 else np.random.SeedSequence().entropy & (2 ** 63 - 1)))
+    else:
+        X._upload(C0)
+    R = X.replicas
+    betas = np.ascontiguousarray(np.broadcast_to(np.asarray(β, np.float64), (R,)))
+    cap = min(10 ** 8, int(samples))
+    Es = np.zeros((max(cap, 1), R), np.float64)
+    info = _ffi.RunInfo()
+    last = {}
+
+    def _hook(user, k, E, acc, n):
+        Ev = np.ctypeslib.as_array(E, (n,)).copy()
+        av = np.ctypeslib.as_array(acc, (n,)).copy()
+        try:
+            ok = hook(k * (float(step) / X.N), X, _LazyConfig(X), av if R > 1 else int(av[0]), _scalarize(X, Ev))
+        except Exception as e:  # propagate after the C call returns
+            last["exc"] = e
+            return 0
+        return 1 if ok else 0
+    cb = _ffi.HOOK(_hook) if hook is not None else C.cast(None, _ffi.HOOK)
+    check(lib().rrrmc_wtm_mc(st, ptr(betas), int(samples), float(step), int(seed) if seed > 0 else 0, cb, None,
+                             ptr(Es), cap, C.byref(info)))
+    if "exc" in last:
+        raise last["exc"]
+    Cout = X._download()
+    Es = Es[:info.nsamples]
+    if X.ET is int:
+        Es = np.rint(Es).astype(np.int64)
+    if not quiet:
+        print("samples =", info.nsamples)
+        print("num_moves =", info.iters_done)
+    X.last_run = info
+    return (Es[:, 0] if R == 1 else Es), Cout
+
+
 def replay(X, C0, sampler, β, iters, kind, ival, fval, *, step=1, replica=0, staged_thr=float("nan"), staged_thr_fact=5.0):
     """Feed chain `replica` the typed draw stream the reference consumed -> (Es, C)."""
     X._upload(C0)

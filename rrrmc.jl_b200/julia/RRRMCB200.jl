@@ -11,7 +11,7 @@
 #     Es, C = standardMC(X, 1.0, 10^3 * X.N; step = 10 * X.N)
 module RRRMCB200
 
-export standardMC, rrrMC, bklMC
+export standardMC, rrrMC, bklMC, wtmMC
 
 const lib = get(ENV, "RRRMC_B200_LIB", joinpath(@__DIR__, "..", "lib", "librrrmc_b200.so"))
 
@@ -193,5 +193,21 @@ standardMC(X::Graph, β::Real, iters::Integer; schedule::Integer = (X.kind == EA
 rrrMC(X::Graph, β::Real, iters::Integer; kw...) = _run(:rrrmc_rrr_mc, X, β, iters; kw...)
 "bklMC(X, β, iters; seed, step, hook, C0, quiet) (src/RRRMC.jl:311-359)"
 bklMC(X::Graph, β::Real, iters::Integer; kw...) = _run(:rrrmc_bkl_mc, X, β, iters; kw...)
+"wtmMC(X, β, samples; seed, step::Float64, hook, C0, quiet) (src/RRRMC.jl:376-430); hook(t, X, C, num_moves, E) gets the global time."
+function wtmMC(X::Graph, β::Real, samples::Integer; seed = 167432777111, step::Float64 = 1.0, hook = (x...) -> true,
+               C0::Union{Config,Nothing} = nothing, quiet::Bool = false)
+    C0 === nothing ? check(ccall((:rrrmc_state_randomize, lib), Cint, (Ptr{Cvoid}, UInt64), X.state, seed > 0 ? seed : rand(UInt64))) :
+                     upload!(X, C0)
+    cap = min(10^8, samples)
+    Es = zeros(X.replicas, max(cap, 1)); info = Ref{RunInfo}()
+    betas = fill(Float64(β), X.replicas)
+    timed = (k, X_, C, acc, E) -> hook(k * step / X.N, X_, C, acc, E)      # sample index -> global time (RRRMC.jl:405)
+    ud = Ref((timed, X)); cb = @cfunction(_hook_tramp, Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Int64}, Int64))
+    GC.@preserve ud check(ccall((:rrrmc_wtm_mc, lib), Cint,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Cdouble, UInt64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cdouble}, Int64, Ref{RunInfo}),
+        X.state, betas, samples, step, seed > 0 ? seed : 0, cb, pointer_from_objref(ud), Es, cap, info))
+    quiet || (println("samples = ", info[].nsamples); println("num_moves = ", info[].iters_done))
+    Es[:, 1:info[].nsamples], download(X)
+end
 
 end # module

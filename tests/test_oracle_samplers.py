@@ -192,3 +192,35 @@ def test_boltzmann_stationarity_discretized():
         big = p > 2e-3
         rel = np.abs(counts[big] / n - p[big]) / p[big]
         assert rel.max() < 0.1, (thr, rel.max())
+
+
+@pytest.mark.parametrize("name", list(reference_graphs().keys()))
+def test_wtmMC_energy_consistency(name):
+    """wtmMC (RRRMC.jl:376-430) under the reference's check-energy hook (test/runtests.jl:140-150)."""
+    g = reference_graphs()[name]
+    src = ffi.PhiloxDraws(seed=77, chain=3)
+    s = src.config(g.N)
+    hook, bad = _check_hook(g, s)
+    Es, r = ffi.wtmMC(g, BETA, 80, s, src, step=0.8 * g.N, hook=hook)
+    assert not bad, bad[:3]
+    assert len(Es) == 80 and r.iters_done > 0
+
+
+def test_wtmMC_boltzmann_stationarity():
+    """Samples taken at equal intervals of the global time of the waiting-time method follow exp(-βE)."""
+    A, J = ea_instance(3, 2, seed=11)
+    g = ffi.Graph.ea_int(A, J)
+    N, beta = 9, 0.7
+    p = _boltzmann(g, N, beta)
+    src = ffi.PhiloxDraws(12345, chain=7)
+    s = src.config(N)
+    counts = np.zeros(2 ** N)
+
+    def hook(it, E, acc):
+        counts[int(s[0])] += 1
+        return True
+    ffi.wtmMC(g, beta, 200_000, s, src, step=float(N), hook=hook)
+    n = counts.sum()
+    big = p > 2e-3
+    rel = np.abs(counts[big] / n - p[big]) / p[big]
+    assert rel.max() < 0.12, rel.max()
