@@ -250,6 +250,82 @@ extern "C" rrrmc_status_t rrrmc_graph_ea_create(rrrmc_ctx_t *ctx, int L, int D, 
     return RRRMC_OK;
 }
 
+// GraphRRG{Int,LEV,K}(A, J) (RRG.jl:112-137) / GraphRRGNormal (RRG.jl, continuous couplings): a K-regular graph with an
+// explicit adjacency (the reference draws it with the Bollobás pairing model, gen_RRG RRG.jl:27-68). energy,
+// update_cache!, delta_energy and neighbors (RRG.jl:165-250) are those of GraphEA on a general adjacency when all
+// couplings are non-zero (uA = the whole row, RRG.jl:130) and the neighbours of a site are distinct, so the graph runs
+// on the chain engine's EA kinds; zero levels (which drop entries from neighbors()) are not supported.
+extern "C" rrrmc_status_t rrrmc_graph_rrg_create(rrrmc_ctx_t *ctx, int64_t N, int K, int kind,
+                                                 const int64_t *A, const void *J, rrrmc_graph_t **out)
+{
+    RR_ARG(ctx && A && J && out, "rrrmc_graph_rrg_create: NULL argument");
+    RR_ARG(kind == RRRMC_EA_PM1 || kind == RRRMC_EA_INT || kind == RRRMC_EA_F64, "unknown coupling kind %d", kind);
+    RR_ARG(K >= 1 && K <= 8, "K must be in 1..8 on this engine, given: %d", K);
+    RR_ARG(N >= 2 && N < ((int64_t)1 << 31) && (N * K) % 2 == 0, "N * K must be even and N in range, given N=%lld, K=%d", (long long)N, K); // RRG.jl:29
+    rrrmc_graph *g = new rrrmc_graph();
+    g->ctx = ctx; g->kind = kind; g->L = 0; g->D = 0; g->twoD = K; g->N = N; g->Nk = N; g->M = 1; g->max_deg = K;
+    g->bipartite = false;
+    g->A0.resize(N * K); g->uA0.resize(N * K); g->nuA.assign(N, K);
+    for (int64_t i = 0; i < N; i++)
+        for (int k = 0; k < K; k++) {
+            const int64_t y = A[i * K + k];
+            if (y < 1 || y > N || y == i + 1 || (k > 0 && y <= A[i * K + k - 1])) {
+                rrrmc_set_error("invalid A: row %lld must hold K distinct neighbours in ascending order, none equal to the site", (long long)i + 1);
+                delete g; return RRRMC_ERR_ARG;
+            }
+            g->A0[i * K + k] = (int32_t)(y - 1); g->uA0[i * K + k] = (int32_t)(y - 1);
+        }
+    if (kind == RRRMC_EA_F64) g->Jd.assign((const double *)J, (const double *)J + N * K);
+    else g->Ji.assign((const int64_t *)J, (const int64_t *)J + N * K);
+    auto Jat = [&](int64_t idx) { return kind == RRRMC_EA_F64 ? g->Jd[idx] : (double)g->Ji[idx]; };
+    for (int64_t i = 0; i < N; i++)
+        for (int k = 0; k < K; k++) {
+            const int64_t y = g->A0[i * K + k];
+            int l = -1;
+            for (int m = 0; m < K; m++) if (g->A0[y * K + m] == i) l = m;
+            if (l < 0 || Jat(i * K + k) != Jat(y * K + l)) {
+                rrrmc_set_error("A / J are not symmetric at bond (%lld,%lld)", (long long)i + 1, (long long)y + 1);
+                delete g; return RRRMC_ERR_ARG;
+            }
+        }
+    if (kind != RRRMC_EA_F64) {
+        std::set<int64_t> levels;
+        for (int64_t v : g->Ji) {
+            if ((kind == RRRMC_EA_PM1 && v != 1 && v != -1) || v == 0 || v < -127 || v > 127) {
+                rrrmc_set_error("the given J is incompatible with the levels of this kind (non-zero int8; ±1 for PM1): found %lld", (long long)v);
+                delete g; return RRRMC_ERR_ARG;
+            }
+            levels.insert(v);
+        }
+        if (kind == RRRMC_EA_PM1) levels = { -1, 1 };
+        std::set<int64_t> es = { 0 };                      // allΔE, RRG.jl:252-270: sums of K signed levels
+        for (int n = 0; n < K; n++) {
+            std::set<int64_t> nw;
+            for (int64_t e : es) for (int64_t l : levels) { nw.insert(e + l); nw.insert(e - l); }
+            es.swap(nw);
+        }
+        std::set<int64_t> de;
+        for (int64_t e : es) de.insert(2 * (e < 0 ? -e : e));
+        for (int64_t d : de) g->allDE.push_back((double)d);
+        if (g->allDE.size() > 64) { rrrmc_set_error("too many ΔE classes (%zu > 64)", g->allDE.size()); delete g; return RRRMC_ERR_UNSUPPORTED; }
+    }
+    RR_CUDA(cudaSetDevice(ctx->device));
+    RR_CUDA(cudaMalloc(&g->d_A, sizeof(int32_t) * N * K));
+    RR_CUDA(cudaMemcpy(g->d_A, g->A0.data(), sizeof(int32_t) * N * K, cudaMemcpyHostToDevice));
+    if (kind == RRRMC_EA_F64) {
+        RR_CUDA(cudaMalloc(&g->d_Jd, sizeof(double) * N * K));
+        RR_CUDA(cudaMemcpy(g->d_Jd, g->Jd.data(), sizeof(double) * N * K, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<int8_t> j8(N * K);
+        for (int64_t k = 0; k < N * K; k++) j8[k] = (int8_t)g->Ji[k];
+        RR_CUDA(cudaMalloc(&g->d_J8, N * K));
+        RR_CUDA(cudaMemcpy(g->d_J8, j8.data(), N * K, cudaMemcpyHostToDevice));
+    }
+    RR_CUDA(cudaDeviceSynchronize());
+    *out = g;
+    return RRRMC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // SK / QT / GraphQuant host logic
 // ------------------------------------------------------------------------------------------------
@@ -976,6 +1052,14 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
                                                double *Es, int64_t Es_cap, rrrmc_run_info_t *info)
 {
     rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    if (!(g->kind == RRRMC_EA_PM1 && g->d_jcode)) {
+        rrrmc_set_error("checkerboard sweeps need a ±J GraphEA lattice with D<=3; use schedule=RANDOM_SITE");
+        return RRRMC_ERR_UNSUPPORTED;
+    }
+    if (!g->bipartite) {
+        rrrmc_set_error("checkerboard sweeps need even L (a two-colourable lattice), given L=%d; use schedule=RANDOM_SITE", g->L);
+        return RRRMC_ERR_UNSUPPORTED;
+    }
     RR_TRY(chain_sync_to_multispin(s));
     uint64_t thr[3];
     for (int c = 1; c <= g->D; c++) thr[c - 1] = fixed64(exp(-beta * 4.0 * c));

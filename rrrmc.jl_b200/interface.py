@@ -285,6 +285,78 @@ class GraphEANormal(AbstractGraph):
         self._h = h
 
 
+def gen_RRG(N, K, rng=None, max_attempts=100_000):
+    """gen_RRG (src/graphs/RRG.jl:27-68): a random K-regular simple graph by the Bollobás pairing model, as an (N, K) array
+    of 1-based neighbours, rows ascending. Restarts until there is neither a self-loop nor a double edge."""
+    if (N * K) % 2:
+        raise ValueError(f"N * K must be even, given N={N}, K={K}")
+    rng = rng or np.random.default_rng()
+    for _ in range(max_attempts):
+        stubs = rng.permutation(np.repeat(np.arange(N), K))
+        a, b = stubs[0::2], stubs[1::2]
+        if (a == b).any():
+            continue
+        lo, hi = np.minimum(a, b), np.maximum(a, b)
+        if len(np.unique(lo * N + hi)) != len(lo):
+            continue
+        nbrs = [[] for _ in range(N)]
+        for x, y in zip(a, b):
+            nbrs[x].append(y + 1); nbrs[y].append(x + 1)
+        return np.array([sorted(r) for r in nbrs], dtype=np.int64)
+    raise RuntimeError("gen_RRG failed (K too large?)")
+
+
+def gen_J_graph(f, A):
+    """gen_J for a general adjacency (src/graphs/RRG.jl:70-96): one draw per bond (x < y) in row order, mirrored."""
+    A = np.asarray(A); N, K = A.shape
+    nb = int((A > np.arange(1, N + 1)[:, None]).sum())
+    draws = np.asarray(f(nb), np.float64)
+    J = np.zeros((N, K)); t = 0
+    for x in range(N):
+        for k in range(K):
+            y = A[x, k] - 1
+            if x < y:
+                J[x, k] = draws[t]; t += 1
+                J[y, int(np.flatnonzero(A[y] == x + 1)[0])] = J[x, k]
+    return J
+
+
+class GraphRRG(AbstractGraph):
+    """GraphRRG(N, K, LEV=(-1,1)) <: DiscrGraph (src/graphs/RRG.jl:112-160) with non-zero integer levels."""
+    ET = int
+
+    def __init__(self, N, K, LEV=(-1, 1), replicas=1, A=None, J=None, rng=None, ctx=None):
+        if not all(float(l).is_integer() and l != 0 for l in LEV):
+            raise NotImplementedError("GraphRRG on this engine needs non-zero integer levels (zero couplings change neighbors(), RRG.jl:130)")
+        rng = rng or np.random.default_rng()
+        self.N, self.K, self.LEV, self.replicas = int(N), int(K), tuple(int(l) for l in LEV), int(replicas)
+        self.ctx = ctx or Context.default()
+        self.A = gen_RRG(N, K, rng) if A is None else np.ascontiguousarray(A, np.int64)
+        if J is None:
+            lev = np.asarray(self.LEV, np.float64)
+            J = gen_J_graph(lambda n: rng.choice(lev, n), self.A)
+        self.J = np.ascontiguousarray(np.rint(J), np.int64)
+        kind = _ffi.EA_PM1 if set(self.LEV) == {-1, 1} else _ffi.EA_INT
+        h = C.c_void_p()
+        check(lib().rrrmc_graph_rrg_create(self.ctx.h, self.N, self.K, kind, ptr(self.A), ptr(self.J), C.byref(h)))
+        self._h = h
+
+
+class GraphRRGNormal(AbstractGraph):
+    """GraphRRGNormal(N, K) <: SimpleGraph{Float64} (src/graphs/RRG.jl): unit-variance Gaussian couplings."""
+    ET = float
+
+    def __init__(self, N, K, replicas=1, A=None, J=None, rng=None, ctx=None):
+        rng = rng or np.random.default_rng()
+        self.N, self.K, self.replicas = int(N), int(K), int(replicas)
+        self.ctx = ctx or Context.default()
+        self.A = gen_RRG(N, K, rng) if A is None else np.ascontiguousarray(A, np.int64)
+        self.J = np.ascontiguousarray(gen_J_graph(lambda n: rng.standard_normal(n), self.A) if J is None else J, np.float64)
+        h = C.c_void_p()
+        check(lib().rrrmc_graph_rrg_create(self.ctx.h, self.N, self.K, _ffi.EA_F64, ptr(self.A), ptr(self.J), C.byref(h)))
+        self._h = h
+
+
 class GraphEANormalDiscretized(AbstractGraph):
     """GraphEANormalDiscretized(L, D, LEV) <: DoubleGraph{DiscrGraph{Int},Float64} (src/graphs/EA.jl:311-360) with integer
     levels: unit-variance Gaussian couplings `cJ`, discretised to the nearest of LEV (inner GraphEA{Int,LEV}) plus Float64

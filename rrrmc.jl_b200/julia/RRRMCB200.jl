@@ -82,6 +82,16 @@ function GraphEANormalDiscretized(L::Integer, D::Integer, LEV::NTuple{K,Int}, A:
                 ctx().h, L, D, permutedims(A), Matrix{Float64}(permutedims(cJ)), lev, length(lev), r))
     _finish(r[], Float64, replicas, EA_DISCR)
 end
+"GraphRRG{Int,LEV,K}(A, J) / GraphRRGNormal (src/graphs/RRG.jl:112-137): explicit K-regular adjacency, A and J as N×K matrices."
+function GraphRRG(A::Matrix{Int64}, J::Matrix; replicas::Integer = 1)
+    N, K = size(A)
+    kind = eltype(J) <: AbstractFloat ? EA_F64 : (all(abs.(J) .== 1) ? EA_PM1 : EA_INT)
+    Jc = eltype(J) <: AbstractFloat ? Matrix{Float64}(permutedims(J)) : Matrix{Int64}(permutedims(J))
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:rrrmc_graph_rrg_create, lib), Cint, (Ptr{Cvoid}, Int64, Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+                ctx().h, N, K, kind, permutedims(A), Jc, r))
+    _finish(r[], kind == EA_F64 ? Float64 : Int, replicas, kind)
+end
 "GraphQEAT (src/QAliases.jl:51-81): GraphQuant over GraphEANormal{2D}; A, J as N×2D matrices (reference layout)."
 function GraphQEAT(L::Integer, D::Integer, M::Integer, Γ::Float64, β::Float64, A::Matrix{Int64}, J::Matrix{Float64}; replicas::Integer = 1)
     r = Ref{Ptr{Cvoid}}(C_NULL)
