@@ -3,7 +3,10 @@
   C3: GraphEA 3D L=32 ±J, rrrMC and bklMC at β=3, 256 replicas              -> iterations/s and executed moves/s
   C4: GraphSKNormal N=4096, 512 replicas: tensor-core field init + lock-step Metropolis sweeps
   C5: GraphQSKT Nk=1024, M=64, Γ=0.3, rrrMC, 64 replicas
-usage: python scripts/bench_configs.py [c3] [c4] [c5] [--quick]"""
+  rrg: the benchmark of the RRR paper (reference scripts/scripts.jl:23-40): GraphRRG N=10^4, K=3, ±J, β=2 with all four
+       samplers (met = standardMC in the reference's random-site order, bkl, rrr, wtm), 256 replicas, and the CPU oracle
+       on one host core beside each
+usage: python scripts/bench_configs.py [c3] [c4] [c5] [rrg] [--quick]"""
 import json
 import os
 import sys
@@ -15,7 +18,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import rrrmc_b200 as rb
 
 quick = "--quick" in sys.argv
-which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c3", "c4", "c5"]
+which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c3", "c4", "c5", "rrg"]
 
 
 def emit(**kw):
@@ -69,3 +72,39 @@ if "c5" in which:
     emit(config="C5", sampler="rrrMC(DoubleGraph)", Nk=Nk, M=M, Gamma=G, beta=beta, replicas=R, iters_per_replica=iters,
          iterations_per_s=R * iters / (info.device_ms * 1e-3), accepted_per_s=info.accepted_total / (info.device_ms * 1e-3),
          device_ms=info.device_ms, wall_s=dt, Qenergy_mean=float(np.mean(rb.Qenergy(X, C2))))
+
+if "rrg" in which:
+    from oracle import ffi   # CPU restatement: the baseline leg of this script only
+    N, K, R, beta = 10_000, 3, int(os.environ.get("RRG_R", "256")), 2.0
+    rng = np.random.default_rng(8370000274 % 2 ** 32)
+    A = rb.gen_RRG(N, K, rng)
+    J = rb.gen_J_graph(lambda n: rng.choice([-1.0, 1.0], n), A).astype(np.int64)
+    X = rb.GraphRRG(N, K, replicas=R, A=A, J=J)
+    _, C = rb.standardMC(X, beta, 300 * N, step=300 * N, seed=1, quiet=True, schedule="random")   # equilibrate
+    scale = 10 if quick else 1
+    runs = (("standardMC", lambda it, **kw: rb.standardMC(X, beta, it, schedule="random", **kw), 20_000_000 // scale),
+            ("rrrMC", lambda it, **kw: rb.rrrMC(X, beta, it, **kw), 2_000_000 // scale),
+            ("bklMC", lambda it, **kw: rb.bklMC(X, beta, it, **kw), 40_000_000 // scale))
+    for name, fn, iters in runs:
+        fn(iters // 20, step=iters // 20, seed=2, C0=C, quiet=True)
+        Es, _ = fn(iters, step=iters, seed=3, C0=C, quiet=True)
+        info = X.last_run
+        g = ffi.Graph.ea_int(A, J); s0 = C.chunks[0].copy()
+        cpu_it = iters // 10
+        t0 = time.perf_counter()
+        _, res = getattr(ffi, name)(g, beta, cpu_it, s0, ffi.PhiloxDraws(3, chain=0), step=cpu_it)
+        cdt = time.perf_counter() - t0
+        emit(config="RRG", sampler=name, N=N, K=K, replicas=R, beta=beta, iters_per_replica=iters,
+             iterations_per_s=R * iters / (info.device_ms * 1e-3), executed_moves_per_s=info.accepted_total / (info.device_ms * 1e-3),
+             device_ms=info.device_ms, cpu_oracle_1core_iterations_per_s=cpu_it / cdt, cpu_oracle_1core_moves_per_s=res.accepted / cdt)
+    samples = 40 // (4 if quick else 1)
+    rb.wtmMC(X, beta, 4, step=50.0 * N, seed=2, C0=C, quiet=True)
+    rb.wtmMC(X, beta, samples, step=50.0 * N, seed=3, C0=C, quiet=True)
+    info = X.last_run
+    g = ffi.Graph.ea_int(A, J); s0 = C.chunks[0].copy()
+    t0 = time.perf_counter()
+    _, res = ffi.wtmMC(g, beta, max(1, samples // 4), s0, ffi.PhiloxDraws(3, chain=0), step=50.0 * N)
+    cdt = time.perf_counter() - t0
+    emit(config="RRG", sampler="wtmMC", N=N, K=K, replicas=R, beta=beta, samples=samples, global_time_per_sample=50.0,
+         executed_moves_per_s=info.accepted_total / (info.device_ms * 1e-3), device_ms=info.device_ms,
+         cpu_oracle_1core_moves_per_s=res.accepted / cdt)
