@@ -10,7 +10,7 @@
 //    equivalent) and no class array (the class is a function of lfields and the spin, DeltaE.jl:108-118);
 //  * the loads of a move that do not depend on each other (neighbour list, couplings, the seven fields, spins and
 //    set positions) are issued together, so a move costs a handful of L2 round trips instead of ~20.
-// Eligibility (chain_ea_eligible): GraphEA{Int,(-1,1)} with pairwise distinct neighbours (L >= 3), N < 65536,
+// Eligibility (chain_ea_eligible): GraphEA{Int,(-1,1)} / GraphRRG{Int,(-1,1),K} with 2..6 pairwise distinct neighbours, N < 65536,
 // Philox draw source. Everything else runs on the generic kernel.
 #include <algorithm>
 #include <cmath>
@@ -310,7 +310,7 @@ bool chain_ea_eligible(const rrrmc_state *s, int sampler)
     const rrrmc_graph *g = s->g;
     if (getenv("RRRMC_CHAIN_GENERIC")) return false;   // tests: force the generic kernel
     if (!(sampler == CHAIN_RRR || sampler == CHAIN_BKL)) return false;
-    if (g->kind != RRRMC_EA_PM1 || !(g->twoD == 2 || g->twoD == 4 || g->twoD == 6) || g->N >= 65536 || (int)g->allDE.size() > EA_MAXL) return false;
+    if (g->kind != RRRMC_EA_PM1 || g->twoD < 2 || g->twoD > EA_MAXDEG || g->N >= 65536 || (int)g->allDE.size() > EA_MAXL) return false;
     for (int64_t i = 0; i < g->N; i++)                 // all neighbours distinct (L >= 3): uA == A (EA.jl:158)
         for (int k = 0; k + 1 < g->twoD; k++)
             if (g->A0[i * g->twoD + k] == g->A0[i * g->twoD + k + 1]) return false;
@@ -337,7 +337,9 @@ rrrmc_status_t chain_ea_launch(rrrmc_state *s, const chain_params &P)
 {
     cudaStream_t st = s->g->ctx->stream;
     if (P.twoD == 6) k_chain_ea<6><<<(unsigned)P.R, 32, 0, st>>>(P);
+    else if (P.twoD == 5) k_chain_ea<5><<<(unsigned)P.R, 32, 0, st>>>(P);      // odd degrees: GraphRRG (RRG.jl), ΔE ∈ {2, 6, ..}
     else if (P.twoD == 4) k_chain_ea<4><<<(unsigned)P.R, 32, 0, st>>>(P);
+    else if (P.twoD == 3) k_chain_ea<3><<<(unsigned)P.R, 32, 0, st>>>(P);
     else k_chain_ea<2><<<(unsigned)P.R, 32, 0, st>>>(P);
     RR_CUDA(cudaGetLastError());
     return RRRMC_OK;
