@@ -68,12 +68,16 @@ rrrmc_status_t rrrmc_graph_ea_create(rrrmc_ctx_t *ctx, int L, int D, int couplin
 #define RRRMC_EMPTY  8 /* GraphEmpty as the inner graph of GraphQuant (GraphQ0T, QAliases.jl:19-31)    */
 #define RRRMC_EA_DISCR 9 /* GraphEANormalDiscretized{Int,LEV,2D} <: DoubleGraph (EA.jl:311-344); see below    */
 
-/* Replaces GraphRRG{Int,LEV,K}(A, J) (src/graphs/RRG.jl:112-137, ±J or small non-zero integer levels) and GraphRRGNormal
+/* Replaces GraphRRG{Int,LEV,K}(A, J) (src/graphs/RRG.jl:112-137, ±J or small integer levels) and GraphRRGNormal
  * (continuous couplings) on an explicit K-regular adjacency A [N*K] (1-based, rows ascending; the reference draws it with
  * gen_RRG, RRG.jl:27-68) with slot-aligned symmetric couplings J (int64 / double by coupling_kind, as for
- * rrrmc_graph_ea_create). K <= 8. Samplers run on the chain engine (schedule RANDOM_SITE for standardMC). */
+ * rrrmc_graph_ea_create). K <= 8. neighbors() lists the entries with a non-zero coupling (RRG.jl:133). Samplers run on
+ * the chain engine (schedule RANDOM_SITE for standardMC). */
 rrrmc_status_t rrrmc_graph_rrg_create(rrrmc_ctx_t *ctx, int64_t N, int K, int coupling_kind,
                                       const int64_t *A, const void *J, rrrmc_graph_t **out);
+/* Replaces GraphRRGNormalDiscretized{Int,LEV,K} (RRG.jl:274-310), integer levels, continuous couplings cJ [N*K] passed in. */
+rrrmc_status_t rrrmc_graph_rrg_discretized_create(rrrmc_ctx_t *ctx, int64_t N, int K, const int64_t *A, const double *cJ,
+                                                  const int64_t *lev, int nlev, rrrmc_graph_t **out);
 
 /* Replaces GraphEANormalDiscretized(L, D, LEV) with integer levels (EA.jl:311-344, e.g. (-1,0,1) as in test/runtests.jl:51)
  * and explicit continuous couplings cJ [N*2D] (double, slot-aligned with A, symmetric; the constructor draws them with

@@ -74,6 +74,8 @@ def lib():
         "orc_ea_int_create": (vp, [i64, i32, p(np.int64), p(np.int64), p(np.int64), i32]),
         "orc_ea_f64_create": (vp, [i64, i32, p(np.int64), p(np.float64)]),
         "orc_ea_discretized_create": (vp, [i64, i32, p(np.int64), p(np.float64), p(np.int64), i32]),
+        "orc_rrg_int_create": (vp, [i64, i32, p(np.int64), p(np.int64), p(np.int64), i32]),
+        "orc_rrg_discretized_create": (vp, [i64, i32, p(np.int64), p(np.float64), p(np.int64), i32]),
         "orc_sk_f64_create": (vp, [i64, p(np.float64)]),
         "orc_sk_bin_create": (vp, [i64, p(np.uint8)]),
         "orc_qt_create": (vp, [i64, i64, f64]),
@@ -244,6 +246,18 @@ class Graph:
         A = np.ascontiguousarray(A, np.int64); cJ = np.ascontiguousarray(cJ, np.float64)
         lev = np.ascontiguousarray(lev, np.int64)
         return cls(lib().orc_ea_discretized_create(A.shape[0], A.shape[1], A, cJ, lev, len(lev)))
+
+    @classmethod
+    def rrg_int(cls, A, J, lev=(-1, 1)):
+        """GraphRRG{Int,LEV,K}(A, J) (RRG.jl:112-137): neighbors() skips zero couplings."""
+        A = np.ascontiguousarray(A, np.int64); J = np.ascontiguousarray(J, np.int64); lev = np.ascontiguousarray(lev, np.int64)
+        return cls(lib().orc_rrg_int_create(A.shape[0], A.shape[1], A, J, lev, len(lev)))
+
+    @classmethod
+    def rrg_discretized(cls, A, cJ, lev=(-1, 0, 1)):
+        """GraphRRGNormalDiscretized{Int,LEV,K} from the continuous couplings cJ (RRG.jl:274-310)."""
+        A = np.ascontiguousarray(A, np.int64); cJ = np.ascontiguousarray(cJ, np.float64); lev = np.ascontiguousarray(lev, np.int64)
+        return cls(lib().orc_rrg_discretized_create(A.shape[0], A.shape[1], A, cJ, lev, len(lev)))
 
     @classmethod
     def sk_f64(cls, J):

@@ -286,12 +286,36 @@ static orc_graph *ea_f64_create_shared(int64_t N, int twoD, const int64_t *A, do
 }
 orc_graph *orc_ea_f64_create(int64_t N, int twoD, const int64_t *A, const double *J) { return ea_f64_create_shared(N, twoD, A, (double *)J, 1); }
 
+/* GraphRRG{Int,LEV,K}(A, J) — RRG.jl:112-137: GraphEA's arithmetic on a K-regular adjacency (energy :165-190, update_cache!
+ * :192-237, delta_energy :239-259), except that neighbors() lists only the entries with a non-zero coupling (:133, :261). */
+orc_graph *orc_rrg_int_create(int64_t N, int K, const int64_t *A, const int64_t *J, const int64_t *lev, int nlev)
+{
+    orc_graph *g = orc_ea_int_create(N, K, A, J, lev, nlev);
+    for (int64_t x = 0; x < N; x++) {
+        int n = 0;
+        for (int k = 0; k < K; k++) if (J[x * K + k] != 0) g->uA[x * K + n++] = A[x * K + k];
+        g->nuA[x] = n;
+    }
+    return g;
+}
+
 /* GraphEANormalDiscretized{Int,LEV,twoD} <: DoubleGraph{DiscrGraph{Int},Float64} — EA.jl:311-344 with explicit continuous
  * couplings cJ (the constructor draws them with gen_J(randn)): every coupling is split by discretize (Common.jl:38-49:
  * nearest level, the first one wins ties) into a level dJ, which goes to the inner GraphEA{Int,LEV}, and a residual
  * rJ = cJ - dJ. The residual part has exactly the arithmetic of GraphEANormal on rJ (energy EA.jl:362-388 vs :584-611,
  * update_cache_residual! :452-487 vs :613-653, delta_energy_residual :489-497 vs :655-663), so it is held as one. */
+static orc_graph *discretized_create(int64_t N, int twoD, const int64_t *A, const double *cJ, const int64_t *lev, int nlev, int rrg);
 orc_graph *orc_ea_discretized_create(int64_t N, int twoD, const int64_t *A, const double *cJ, const int64_t *lev, int nlev)
+{
+    return discretized_create(N, twoD, A, cJ, lev, nlev, 0);
+}
+/* GraphRRGNormalDiscretized{Int,LEV,K} — RRG.jl:274-310: the same construction over GraphRRG; neighbors(X) is the whole
+ * row A[i] (:499) while neighbors(inner_graph(X)) skips the zero levels (:133). */
+orc_graph *orc_rrg_discretized_create(int64_t N, int K, const int64_t *A, const double *cJ, const int64_t *lev, int nlev)
+{
+    return discretized_create(N, K, A, cJ, lev, nlev, 1);
+}
+static orc_graph *discretized_create(int64_t N, int twoD, const int64_t *A, const double *cJ, const int64_t *lev, int nlev, int rrg)
 {
     orc_graph *g = (orc_graph *)calloc(1, sizeof(orc_graph));
     g->kind = ORC_EA_DISCR; g->N = N; g->twoD = twoD; g->M = 1;
@@ -306,7 +330,7 @@ orc_graph *orc_ea_discretized_create(int64_t N, int twoD, const int64_t *A, cons
         }
         dJ[a] = d; rJ[a] = r;
     }
-    g->X0 = orc_ea_int_create(N, twoD, A, dJ, lev, nlev);
+    g->X0 = rrg ? orc_rrg_int_create(N, twoD, A, dJ, lev, nlev) : orc_ea_int_create(N, twoD, A, dJ, lev, nlev);
     g->X1 = (orc_graph **)calloc(1, sizeof(orc_graph *));
     g->X1[0] = orc_ea_f64_create(N, twoD, A, rJ);
     free(dJ); free(rJ);
@@ -668,7 +692,7 @@ int orc_neighbors(const orc_graph *g, int64_t i, int64_t *out)
     }
     case ORC_QT: qt_neighbors(g, i, &out[0], &out[1]); return 2;
     case ORC_EMPTY: return 0;
-    case ORC_EA_DISCR: return orc_neighbors(g->X0, i, out); /* EA.jl:525 */
+    case ORC_EA_DISCR: return orc_neighbors(g->X1[0], i, out); /* EA.jl:525 (uA), RRG.jl:499 (A[i]): the distinct entries of the row */
     case ORC_QUANT: {
         qt_neighbors(g->X0, i, &out[0], &out[1]);
         int64_t k = (i - 1) / g->Nk + 1, j = (i - 1) % g->Nk + 1;

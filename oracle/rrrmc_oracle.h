@@ -78,6 +78,9 @@ orc_graph *orc_ea_int_create(int64_t N, int twoD, const int64_t *A, const int64_
 orc_graph *orc_ea_f64_create(int64_t N, int twoD, const int64_t *A, const double *J);
 /* GraphEANormalDiscretized with integer levels: cJ = the continuous couplings (slot-aligned with A, symmetric) */
 orc_graph *orc_ea_discretized_create(int64_t N, int twoD, const int64_t *A, const double *cJ, const int64_t *lev, int nlev);
+/* GraphRRG{Int,LEV,K} (neighbors() = entries with non-zero coupling, RRG.jl:133) and GraphRRGNormalDiscretized (RRG.jl:274-310) */
+orc_graph *orc_rrg_int_create(int64_t N, int K, const int64_t *A, const int64_t *J, const int64_t *lev, int nlev);
+orc_graph *orc_rrg_discretized_create(int64_t N, int K, const int64_t *A, const double *cJ, const int64_t *lev, int nlev);
 orc_graph *orc_sk_f64_create(int64_t N, const double *J /* [N*N] row-major, symmetric, zero diag */);
 orc_graph *orc_sk_bin_create(int64_t N, const uint8_t *J /* [N*N] 0/1, symmetric, zero diag */);
 orc_graph *orc_qt_create(int64_t N, int64_t M, double fourK);

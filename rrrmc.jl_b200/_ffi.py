@@ -45,6 +45,7 @@ SIGNATURES = {
     "rrrmc_ctx_flush_l2": (_i32, [_vp]),
     "rrrmc_graph_ea_create": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _pp]),
     "rrrmc_graph_rrg_create": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _pp]),
+    "rrrmc_graph_rrg_discretized_create": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _pp]),
     "rrrmc_graph_ea_discretized_create": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _i32, _pp]),
     "rrrmc_graph_quant_ea_create": (_i32, [_vp, _i32, _i32, _i64, _f64, _f64, _vp, _vp, _pp]),
     "rrrmc_graph_sk_create": (_i32, [_vp, _i64, _i32, _vp, _pp]),

@@ -253,8 +253,8 @@ extern "C" rrrmc_status_t rrrmc_graph_ea_create(rrrmc_ctx_t *ctx, int L, int D, 
 // GraphRRG{Int,LEV,K}(A, J) (RRG.jl:112-137) / GraphRRGNormal (RRG.jl, continuous couplings): a K-regular graph with an
 // explicit adjacency (the reference draws it with the Bollobás pairing model, gen_RRG RRG.jl:27-68). energy,
 // update_cache!, delta_energy and neighbors (RRG.jl:165-250) are those of GraphEA on a general adjacency when all
-// couplings are non-zero (uA = the whole row, RRG.jl:130) and the neighbours of a site are distinct, so the graph runs
-// on the chain engine's EA kinds; zero levels (which drop entries from neighbors()) are not supported.
+// neighbours of a site are distinct, so the graph runs on the chain engine's EA kinds; the one difference is that
+// neighbors() lists only the entries with a non-zero coupling (uA, RRG.jl:133), which the engine applies as a filter.
 extern "C" rrrmc_status_t rrrmc_graph_rrg_create(rrrmc_ctx_t *ctx, int64_t N, int K, int kind,
                                                  const int64_t *A, const void *J, rrrmc_graph_t **out)
 {
@@ -291,13 +291,21 @@ extern "C" rrrmc_status_t rrrmc_graph_rrg_create(rrrmc_ctx_t *ctx, int64_t N, in
     if (kind != RRRMC_EA_F64) {
         std::set<int64_t> levels;
         for (int64_t v : g->Ji) {
-            if ((kind == RRRMC_EA_PM1 && v != 1 && v != -1) || v == 0 || v < -127 || v > 127) {
-                rrrmc_set_error("the given J is incompatible with the levels of this kind (non-zero int8; ±1 for PM1): found %lld", (long long)v);
+            if ((kind == RRRMC_EA_PM1 && v != 1 && v != -1) || v < -127 || v > 127) {
+                rrrmc_set_error("the given J is incompatible with the levels of this kind (int8; ±1 for PM1): found %lld", (long long)v);
                 delete g; return RRRMC_ERR_ARG;
             }
             levels.insert(v);
         }
         if (kind == RRRMC_EA_PM1) levels = { -1, 1 };
+        if (levels.count(0)) {                             // neighbors() = the entries with a non-zero coupling (RRG.jl:133)
+            g->nz_neighbors = true;
+            for (int64_t i = 0; i < N; i++) {
+                int n = 0;
+                for (int k = 0; k < K; k++) if (g->Ji[i * K + k] != 0) g->uA0[i * K + n++] = g->A0[i * K + k];
+                g->nuA[i] = n;
+            }
+        }
         std::set<int64_t> es = { 0 };                      // allΔE, RRG.jl:252-270: sums of K signed levels
         for (int n = 0; n < K; n++) {
             std::set<int64_t> nw;
@@ -483,6 +491,54 @@ extern "C" rrrmc_status_t rrrmc_graph_ea_discretized_create(rrrmc_ctx_t *ctx, in
     if (g->allDE.size() > 64) { rrrmc_set_error("too many ΔE classes (%zu > 64)", g->allDE.size()); rrrmc_graph_destroy(g); return RRRMC_ERR_UNSUPPORTED; }
     RR_CUDA(cudaMalloc(&g->d_Jd, sizeof(double) * N * twoD));
     RR_CUDA(cudaMemcpy(g->d_Jd, g->Jd.data(), sizeof(double) * N * twoD, cudaMemcpyHostToDevice));
+    RR_CUDA(cudaDeviceSynchronize());
+    *out = g;
+    return RRRMC_OK;
+}
+
+// GraphRRGNormalDiscretized{Int,LEV,K} (RRG.jl:274-310): GraphEANormalDiscretized's construction over a K-regular adjacency.
+// neighbors(X) is the whole row (RRG.jl:499); neighbors(inner_graph(X)) skips the couplings discretised to zero (:133).
+extern "C" rrrmc_status_t rrrmc_graph_rrg_discretized_create(rrrmc_ctx_t *ctx, int64_t N, int K, const int64_t *A, const double *cJ,
+                                                             const int64_t *lev, int nlev, rrrmc_graph_t **out)
+{
+    RR_ARG(ctx && A && cJ && lev && out, "rrrmc_graph_rrg_discretized_create: NULL argument");
+    RR_ARG(nlev >= 1 && nlev <= 16, "LEV must hold 1..16 levels, given %d", nlev);
+    RR_ARG(K >= 1 && K <= 8 && N >= 2, "K must be in 1..8 and N >= 2");
+    for (int l = 0; l < nlev; l++) RR_ARG(lev[l] >= -127 && lev[l] <= 127, "levels must fit int8, given %lld", (long long)lev[l]);
+    std::vector<int64_t> dJ((size_t)N * K);
+    std::vector<double> rJ((size_t)N * K);
+    for (int64_t a = 0; a < N * K; a++) {
+        const double x = cJ[a];
+        RR_ARG(std::isfinite(x), "cJ[%lld] is not finite", (long long)a);
+        int64_t d = lev[0]; double r = x - (double)d;
+        for (int l = 1; l < nlev; l++) {
+            const double r1 = x - (double)lev[l];
+            if (fabs(r1) < fabs(r)) { d = lev[l]; r = r1; }
+        }
+        dJ[a] = d; rJ[a] = r;
+    }
+    rrrmc_graph *g = nullptr;
+    RR_TRY(rrrmc_graph_rrg_create(ctx, N, K, RRRMC_EA_INT, A, dJ.data(), &g));
+    g->kind = RRRMC_EA_DISCR; g->M = 2;
+    g->nz_neighbors = true;                                // harmless when no coupling was discretised to zero
+    for (int64_t i = 0; i < N; i++) {                      // neighbors(X, i) = A[i] (RRG.jl:499)
+        for (int k = 0; k < K; k++) g->uA0[i * K + k] = g->A0[i * K + k];
+        g->nuA[i] = K;
+    }
+    g->Jd = rJ;
+    std::set<int64_t> es = { 0 };
+    for (int n = 0; n < K; n++) {
+        std::set<int64_t> nw;
+        for (int64_t e : es) for (int l = 0; l < nlev; l++) { nw.insert(e + lev[l]); nw.insert(e - lev[l]); }
+        es.swap(nw);
+    }
+    std::set<int64_t> de;
+    for (int64_t e : es) de.insert(2 * (e < 0 ? -e : e));
+    g->allDE.clear();
+    for (int64_t d : de) g->allDE.push_back((double)d);
+    if (g->allDE.size() > 64) { rrrmc_set_error("too many ΔE classes (%zu > 64)", g->allDE.size()); rrrmc_graph_destroy(g); return RRRMC_ERR_UNSUPPORTED; }
+    RR_CUDA(cudaMalloc(&g->d_Jd, sizeof(double) * N * K));
+    RR_CUDA(cudaMemcpy(g->d_Jd, g->Jd.data(), sizeof(double) * N * K, cudaMemcpyHostToDevice));
     RR_CUDA(cudaDeviceSynchronize());
     *out = g;
     return RRRMC_OK;

@@ -43,7 +43,7 @@ struct gview {
     uint64_t *s;
     int32_t *lfi; double *lfd;   // EA: [2][N] = (lfields, lfields_last). SK family: [M][2][Nk], halves swapped by sw[k]
     int32_t *ml; uint8_t *sw;
-    int Nk, M, inner;
+    int Nk, M, inner, nz;
     double fourK, sN;
     int coop;                    // 1: a warp serves this chain (lane 0 leads)
 };
@@ -209,10 +209,13 @@ __device__ __forceinline__ double gv_delta_residual(const gview &c, int i) // In
 template <class F> __device__ __forceinline__ void gv_for_neighbors(const gview &c, int i, bool inner, F f)
 {
     if (is_ea(c.kind)) {
+        // GraphRRG (RRG.jl:133, :261): the integer graph's neighbours are the entries with a non-zero coupling; the
+        // DoubleGraph over it (GraphRRGNormalDiscretized, RRG.jl:499) lists the whole row
+        const bool skip0 = c.nz && (c.kind == RRRMC_EA_INT || (c.kind == RRRMC_EA_DISCR && inner));
         int prev = -1;
         for (int k = 0; k < c.twoD; k++) {
             const int y = c.A[(int64_t)i * c.twoD + k];
-            if (y != prev) f(y);
+            if (y != prev && !(skip0 && c.J8[(int64_t)i * c.twoD + k] == 0)) f(y);
             prev = y;
         }
     } else if (is_sk(c.kind)) {
@@ -552,7 +555,7 @@ __device__ __forceinline__ gview make_view(const chain_params &P, int64_t r)
     X.lfi = P.lfi ? P.lfi + r * 2 * (int64_t)P.N : nullptr;
     X.lfd = P.lfd ? P.lfd + r * 2 * (int64_t)P.N : nullptr;
     X.ml = P.ml + r * P.M; X.sw = P.sw + r * P.M;
-    X.Nk = P.Nk; X.M = P.M; X.inner = P.inner; X.fourK = P.fourK; X.sN = P.sN;
+    X.Nk = P.Nk; X.M = P.M; X.inner = P.inner; X.nz = P.nz; X.fourK = P.fourK; X.sN = P.sN;
     X.coop = P.coop;
     return X;
 }
@@ -1013,7 +1016,7 @@ static void chain_fill_params(rrrmc_state *s, chain_params &P)
     rrrmc_graph *g = s->g; chain_store *c = s->chain;
     memset(&P, 0, sizeof P);
     P.kind = g->kind; P.N = (int)g->N; P.twoD = g->twoD; P.nDE = c->nDE; P.levs = c->levs; P.N2 = c->N2;
-    P.Nk = (int)g->Nk; P.M = (int)g->M; P.inner = g->inner; P.fourK = g->fourK; P.sN = g->sN;
+    P.Nk = (int)g->Nk; P.M = (int)g->M; P.inner = g->inner; P.nz = g->nz_neighbors ? 1 : 0; P.fourK = g->fourK; P.sN = g->sN;
     P.R = s->R; P.nchunks = s->nchunks; P.chain0 = 0;
     P.A = g->d_A; P.J8 = g->d_J8; P.Jd = g->d_Jd; P.Jb = g->d_Jb;
     P.chunks = s->d_chunks;

@@ -63,6 +63,7 @@ struct chain_store {
 struct chain_params {
     int kind, N, twoD, sampler, nDE, levs, cpw, coop;
     int Nk, M, inner;
+    int nz;                       // 1: GraphRRG semantics — neighbors() of the integer graph skips zero couplings (RRG.jl:133)
     double fourK, sN;
     int64_t R, N2, nchunks, chain0;
     const int32_t *A; const int8_t *J8; const double *Jd; const uint8_t *Jb;

@@ -57,6 +57,7 @@ struct rrrmc_graph {
     int inner = 0;                   // QUANT: kind of the inner graph (RRRMC_SK_F64 / RRRMC_SK_BIN / RRRMC_EMPTY)
     double fourK = 0, Gamma = 0, beta = 0, sN = 1;
     int max_deg = 0;                 // upper bound of |neighbors(X, i)|
+    bool nz_neighbors = false;       // GraphRRG family: neighbors() of the integer graph lists non-zero couplings only (RRG.jl:133)
 };
 
 struct rrrmc_state {

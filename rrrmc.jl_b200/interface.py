@@ -322,12 +322,12 @@ def gen_J_graph(f, A):
 
 
 class GraphRRG(AbstractGraph):
-    """GraphRRG(N, K, LEV=(-1,1)) <: DiscrGraph (src/graphs/RRG.jl:112-160) with non-zero integer levels."""
+    """GraphRRG(N, K, LEV=(-1,1)) <: DiscrGraph (src/graphs/RRG.jl:112-160), integer levels; neighbors() skips zero couplings."""
     ET = int
 
     def __init__(self, N, K, LEV=(-1, 1), replicas=1, A=None, J=None, rng=None, ctx=None):
-        if not all(float(l).is_integer() and l != 0 for l in LEV):
-            raise NotImplementedError("GraphRRG on this engine needs non-zero integer levels (zero couplings change neighbors(), RRG.jl:130)")
+        if not all(float(l).is_integer() for l in LEV):
+            raise NotImplementedError("non-integer levels (DFloat64 path) are not on this engine's path yet")
         rng = rng or np.random.default_rng()
         self.N, self.K, self.LEV, self.replicas = int(N), int(K), tuple(int(l) for l in LEV), int(replicas)
         self.ctx = ctx or Context.default()
@@ -339,6 +339,26 @@ class GraphRRG(AbstractGraph):
         kind = _ffi.EA_PM1 if set(self.LEV) == {-1, 1} else _ffi.EA_INT
         h = C.c_void_p()
         check(lib().rrrmc_graph_rrg_create(self.ctx.h, self.N, self.K, kind, ptr(self.A), ptr(self.J), C.byref(h)))
+        self._h = h
+
+
+class GraphRRGNormalDiscretized(AbstractGraph):
+    """GraphRRGNormalDiscretized(N, K, LEV) <: DoubleGraph{DiscrGraph{Int},Float64} (src/graphs/RRG.jl:274-330), integer levels."""
+    ET = float
+
+    def __init__(self, N, K, LEV=(-1, 0, 1), replicas=1, A=None, cJ=None, rng=None, ctx=None):
+        if not all(float(l).is_integer() for l in LEV):
+            raise NotImplementedError("non-integer levels (DFloat64 path) are not on this engine's path yet")
+        if len(set(LEV)) != len(LEV):
+            raise ValueError(f"repeated levels in LEV: {LEV}")
+        rng = rng or np.random.default_rng()
+        self.N, self.K, self.LEV, self.replicas = int(N), int(K), tuple(int(l) for l in LEV), int(replicas)
+        self.ctx = ctx or Context.default()
+        self.A = gen_RRG(N, K, rng) if A is None else np.ascontiguousarray(A, np.int64)
+        self.cJ = np.ascontiguousarray(gen_J_graph(lambda n: rng.standard_normal(n), self.A) if cJ is None else cJ, np.float64)
+        lev = np.ascontiguousarray(self.LEV, np.int64)
+        h = C.c_void_p()
+        check(lib().rrrmc_graph_rrg_discretized_create(self.ctx.h, self.N, self.K, ptr(self.A), ptr(self.cJ), ptr(lev), len(lev), C.byref(h)))
         self._h = h
 
 

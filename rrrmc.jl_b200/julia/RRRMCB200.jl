@@ -92,6 +92,15 @@ function GraphRRG(A::Matrix{Int64}, J::Matrix; replicas::Integer = 1)
                 ctx().h, N, K, kind, permutedims(A), Jc, r))
     _finish(r[], kind == EA_F64 ? Float64 : Int, replicas, kind)
 end
+"GraphRRGNormalDiscretized{Int,LEV,K} (src/graphs/RRG.jl:274-330) from the continuous couplings cJ (N×K, slot-aligned with A)."
+function GraphRRGNormalDiscretized(LEV::NTuple{M,Int}, A::Matrix{Int64}, cJ::Matrix{Float64}; replicas::Integer = 1) where {M}
+    N, K = size(A)
+    r = Ref{Ptr{Cvoid}}(C_NULL); lev = collect(Int64, LEV)
+    check(ccall((:rrrmc_graph_rrg_discretized_create, lib), Cint,
+                (Ptr{Cvoid}, Int64, Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Cint, Ref{Ptr{Cvoid}}),
+                ctx().h, N, K, permutedims(A), Matrix{Float64}(permutedims(cJ)), lev, length(lev), r))
+    _finish(r[], Float64, replicas, EA_DISCR)
+end
 "GraphQEAT (src/QAliases.jl:51-81): GraphQuant over GraphEANormal{2D}; A, J as N×2D matrices (reference layout)."
 function GraphQEAT(L::Integer, D::Integer, M::Integer, Γ::Float64, β::Float64, A::Matrix{Int64}, J::Matrix{Float64}; replicas::Integer = 1)
     r = Ref{Ptr{Cvoid}}(C_NULL)

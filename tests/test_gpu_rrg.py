@@ -22,11 +22,19 @@ def _mk(name, R):
     if kind == "int":
         J = rb.gen_J_graph(lambda n: rng.choice([-2.0, -1.0, 1.0, 2.0], n), A).astype(np.int64)
         return rb.GraphRRG(N, K, (-2, -1, 1, 2), replicas=R, A=A, J=J), (lambda: ffi.Graph.ea_int(A, J, (-2, -1, 1, 2)))
+    if kind == "int0":   # zero level: neighbors() skips the zero couplings (RRG.jl:133)
+        J = rb.gen_J_graph(lambda n: rng.choice([-1.0, 0.0, 1.0], n), A).astype(np.int64)
+        assert (J == 0).any()
+        return rb.GraphRRG(N, K, (-1, 0, 1), replicas=R, A=A, J=J), (lambda: ffi.Graph.rrg_int(A, J, (-1, 0, 1)))
+    if kind == "disc":   # GraphRRGNormalDiscretized (RRG.jl:274-330)
+        cJ = rb.gen_J_graph(lambda n: rng.standard_normal(n), A)
+        return rb.GraphRRGNormalDiscretized(N, K, (-1, 0, 1), replicas=R, A=A, cJ=cJ), (lambda: ffi.Graph.rrg_discretized(A, cJ, (-1, 0, 1)))
     J = rb.gen_J_graph(lambda n: rng.standard_normal(n), A)
     return rb.GraphRRGNormal(N, K, replicas=R, A=A, J=J), (lambda: ffi.Graph.ea_f64(A, J))
 
 
-GRAPHS = ["pm1,10,3", "pm1,40,4", "pm1,64,6", "pm1,30,5", "int,20,3", "normal,10,3", "normal,36,4"]
+GRAPHS = ["pm1,10,3", "pm1,40,4", "pm1,64,6", "pm1,30,5", "int,20,3", "normal,10,3", "normal,36,4", "int0,10,3", "int0,30,4",
+          "disc,10,3", "disc,24,5"]
 
 
 @pytest.mark.parametrize("name", GRAPHS)
@@ -42,7 +50,11 @@ def test_interface_matches_oracle(name):
     dE = np.asarray(rb.all_delta_energy(X, C0, 1), np.float64)
     assert np.array_equal(dE, np.array([g.delta_energy(C0.chunks[1], i) for i in range(1, X.N + 1)]))
     for i in (1, X.N):
-        assert tuple(rb.neighbors(X, i)) == tuple(g.neighbors(i)) == tuple(X.A[i - 1])
+        assert tuple(rb.neighbors(X, i)) == tuple(g.neighbors(i))
+        if name.startswith("int0"):
+            assert tuple(rb.neighbors(X, i)) == tuple(X.A[i - 1][X.J[i - 1] != 0])
+        else:
+            assert tuple(rb.neighbors(X, i)) == tuple(X.A[i - 1])
     if not name.startswith("normal"):
         assert np.array_equal(np.asarray(rb.allDeltaE(X), np.float64), g.allDE())
         if name.startswith("pm1"):   # RRG.jl:252-255: (0,4,..) for even K, (2,6,..) for odd K
@@ -86,7 +98,7 @@ def test_argument_errors():
     with pytest.raises(ValueError):
         rb.GraphRRG(10, 3, A=A, J=bad)                     # not symmetric
     with pytest.raises(NotImplementedError):
-        rb.GraphRRG(10, 3, (-1, 0, 1), A=A, J=J)           # zero level
+        rb.GraphRRG(10, 3, (-1.5, 0.5), A=A, J=J)          # fractional levels (DFloat64)
     Ab = A.copy(); Ab[0, 0], Ab[0, 1] = Ab[0, 1], Ab[0, 0]
     with pytest.raises(ValueError):
         rb.GraphRRG(10, 3, A=Ab, J=J)                      # rows must ascend
