@@ -59,6 +59,14 @@ def reference_graphs(seed=1):
     out["Quant(10,8,Empty)"] = ffi.Graph.quant(10, 8, 0.5, 2.0, ffi.EMPTY)
     out["Quant(10,8,SK)"] = ffi.Graph.quant(10, 8, 0.5, 2.0, ffi.SK_BIN, sk_binary(10, seed + 3))
     out["Quant(10,8,SKNormal)"] = ffi.Graph.quant(10, 8, 0.5, 2.0, ffi.SK_F64, sk_gauss(10, seed + 4))
+    # random regular graphs, test/runtests.jl:35-44
+    import rrrmc_b200 as rb   # host-side generators only (gen_RRG, gen_J_graph)
+    rng = np.random.default_rng(seed + 7)
+    Ar = rb.gen_RRG(10, 3, rng)
+    out["RRG(10,3)"] = ffi.Graph.rrg_int(Ar, rb.gen_J_graph(lambda n: rng.choice([-1.0, 1.0], n), Ar).astype(np.int64))
+    out["RRG(10,3,(-1,0,1))"] = ffi.Graph.rrg_int(Ar, rb.gen_J_graph(lambda n: rng.choice([-1.0, 0.0, 1.0], n), Ar).astype(np.int64), (-1, 0, 1))
+    out["RRGNormalDiscretized(10,3,(-1,0,1))"] = ffi.Graph.rrg_discretized(Ar, rb.gen_J_graph(lambda n: rng.standard_normal(n), Ar), (-1, 0, 1))
+    out["RRGNormal(10,3)"] = ffi.Graph.ea_f64(Ar, rb.gen_J_graph(lambda n: rng.standard_normal(n), Ar))
     A, J = ea_instance(3, 2, seed=seed + 6, gaussian=True)
     out["QEAT(3,2,5)"] = ffi.Graph.quant(9, 5, 0.5, 2.0, ffi.EA_F64, J, A)   # GraphQEAT, QAliases.jl:51-81
     return out
