@@ -211,6 +211,22 @@ rrrmc_status_t rrrmc_bkl_mc(rrrmc_state_t *s, const double *beta, int64_t iters,
 rrrmc_status_t rrrmc_wtm_mc(rrrmc_state_t *s, const double *beta, int64_t samples, double step, uint64_t seed,
                             rrrmc_hook_fn hook, void *user, double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
 
+/* extremal_opt(X, τ, iters; step, seed, hook, C0) (RRRMC.jl:468-521): τ-extremal optimisation on the EOCache of
+ * DeltaE.jl:413-543 — spins ranked by ΔE class, rank drawn from the power law j^-τ, the chosen spin always flips.
+ * DiscrGraph models only (GraphEA / GraphRRG with integer levels, GraphQT); others return RRRMC_ERR_UNSUPPORTED (the
+ * reference's generic EOCacheCont re-sorts all N spins per move, DeltaE.jl:545-635).
+ * ftau: fτ = cumsum(j^-τ, j = 1..N) (DeltaE.jl:443), computed by the host language so that its own `^` and `cumsum`
+ * bits are used; ftau_stride = 0: one table [N] for all chains, else chain r reads ftau + r·ftau_stride (per-chain τ).
+ * The final configurations stay in the state (rrrmc_state_download). Outputs (any may be NULL): Emin_out[R],
+ * itmin_out[R], Cmin_chunks[R][nchunks] (reference BitVector layout) — the reference's return values (C, Emin, Cmin,
+ * itmin); Es[Es_cap][R]: energies at the hook instants (an aid, the reference returns no energy vector).
+ * hook(it, X, C, E, Emin)::Bool of RRRMC.jl:499, batched over the chains. */
+typedef int (*rrrmc_eo_hook_fn)(void *user, int64_t it, const double *E, const double *Emin, int64_t R);
+rrrmc_status_t rrrmc_extremal_opt(rrrmc_state_t *s, const double *ftau, int64_t ftau_stride, int64_t iters, int64_t step,
+                                  uint64_t seed, rrrmc_eo_hook_fn hook, void *user,
+                                  double *Emin_out, int64_t *itmin_out, uint64_t *Cmin_chunks,
+                                  double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
+
 /* Replay: feed one chain the typed draw stream the reference consumed
  * (kind 0 = rand(1:n) value, 1 = rand() value) and reproduce its trajectory.
  * sampler: 0 standardMC, 1 rrrMC, 2 bklMC. Es: [Es_cap] energies at every `step`. */

@@ -51,6 +51,14 @@ class Result(C.Structure):
 
 HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_int64)
 
+
+class EOResult(C.Structure):
+    _fields_ = [("nsamples", C.c_int64), ("iters_done", C.c_int64), ("itmin", C.c_int64),
+                ("Emin", C.c_double), ("status", C.c_int), ("Efinal", C.c_double)]
+
+
+EOHOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_double)
+
 _lib = None
 
 
@@ -98,6 +106,7 @@ def lib():
         "orc_rrrMC": (Result, [vp, f64, i64, i64, p(np.uint64), Draws, f64, f64, HOOK, vp, vp, i64]),
         "orc_bklMC": (Result, [vp, f64, i64, i64, p(np.uint64), Draws, HOOK, vp, vp, i64]),
         "orc_wtmMC": (Result, [vp, f64, i64, f64, p(np.uint64), Draws, HOOK, vp, vp, i64]),
+        "orc_extremal_opt": (EOResult, [vp, p(np.float64), i64, i64, p(np.uint64), vp, Draws, EOHOOK, vp, vp, i64]),
         "orc_check_discrete_cache": (i32, [vp, p(np.uint64), f64, p(np.int64), i64]),
         "orc_checkerboard_sweeps": (None, [i32, i32, i64, p(np.uint32), p(np.int8), p(np.uint64), i32, i32,
                                            C.c_uint64, C.c_uint64, i64, vp]),
@@ -364,6 +373,25 @@ def wtmMC(g, beta, samples, s, src, step=1.0, hook=None):
     res = lib().orc_wtmMC(g.h, float(beta), int(samples), float(step), s, src.draws, h, None, Es.ctypes.data, cap)
     assert res.status == 0, res.status
     return Es[:min(res.nsamples, cap)].copy(), res
+
+
+def extremal_opt(g, ftau, iters, s, src, step=1, hook=None):
+    """extremal_opt(X, τ, iters; step, hook) (RRRMC.jl:468-521) given fτ = cumsum(j^-τ); s is updated in place.
+    Returns (Es at the hook instants, Cmin chunks, result struct with Emin / itmin / Efinal)."""
+    cap = min(10 ** 8, iters // step)
+    Es = np.zeros(max(cap, 1), np.float64)
+    Cmin = np.zeros_like(s)
+    if hook is None:
+        h = EOHOOK(0)
+    else:
+        def _h(user, it, E, Emin):
+            return 1 if hook(it, E, Emin) else 0
+        h = EOHOOK(_h)
+    ftau = np.ascontiguousarray(ftau, np.float64)
+    assert ftau.shape == (g.N,)
+    res = lib().orc_extremal_opt(g.h, ftau, int(iters), int(step), s, Cmin.ctypes.data, src.draws, h, None, Es.ctypes.data, cap)
+    assert res.status == 0, res.status
+    return Es[:min(res.nsamples, cap)].copy(), Cmin, res
 
 
 def thresholds_fixed64(beta, D):

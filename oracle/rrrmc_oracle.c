@@ -1321,6 +1321,77 @@ orc_result orc_wtmMC(orc_graph *X, double beta, int64_t samples, double step, ui
 }
 
 /* ------------------------------------------------------------------------------------------
+ * extremal_opt — RRRMC.jl:468-521 on the EOCache of DeltaE.jl:413-543 (τ-EO, Boettcher & Percus): the spins are
+ * ranked by ΔE (classes in ascending ΔE, findks :413-422: K = 2L − has_zero classes, ΔE = 0 is ONE class here, unlike
+ * DeltaECache), a rank i is drawn from the power law j^−τ (r = (1 − rand())·z, i = searchsortedfirst(fτ, r), :483-487),
+ * the class holding rank i is found by walking the class sizes (:500-505) and a uniform member of it is flipped
+ * unconditionally (:514); neighbours and the moved spin are re-classified (apply_move! :519-543). DiscrGraph only
+ * (the generic EOCacheCont re-sorts all N spins per move, :545-635 — "very sub-optimal" in the reference's words).
+ * fτ = cumsum(j^−τ) is an input: the host language computes it (Julia's cumsum is pairwise, its `^` is its own pow).
+ * Draw order per move: one f64, one range(|class|).
+ * ---------------------------------------------------------------------------------------- */
+static int eo_findks(const decache *c, double dE, int has_zero) /* DeltaE.jl:413-422 */
+{
+    int ak = findk(c, dE);
+    return dE >= 0 ? ak + c->L - has_zero : c->L + 1 - ak;
+}
+orc_eo_result orc_extremal_opt(orc_graph *X, const double *ftau, int64_t iters, int64_t step, uint64_t *s,
+                               uint64_t *Cmin, orc_draws d, orc_eo_hook hook, void *user, double *Es, int64_t Es_cap)
+{
+    orc_eo_result res = { 0, 0, 0, 0.0, 0, 0.0 };
+    if (!is_discr(X)) { res.status = -2; return res; }
+    const int64_t N = X->N, nch = (N + 63) / 64;
+    decache c0; memset(&c0, 0, sizeof c0);
+    decache *c = &c0;
+    c->N = N; c->L = orc_allDE(X, c->DE);
+    const int L = c->L, has_zero = c->DE[0] == 0.0, K = 2 * L - has_zero;
+    double E = orc_energy(X, s), Emin = E;
+    int64_t itmin = 0, it = 0;
+    if (Cmin) memcpy(Cmin, s, (size_t)nch * 8);
+    arrayset *as = (arrayset *)calloc((size_t)K + 1, sizeof(arrayset));
+    int64_t *pos = (int64_t *)calloc((size_t)N + 1, 8), nb[64];
+    for (int k = 1; k <= K; k++) as_init(&as[k], N);
+    for (int64_t i = 1; i <= N; i++) {                    /* EOCache ctor, DeltaE.jl:433-441 */
+        int ki = eo_findks(c, orc_delta_energy(X, s, i), has_zero);
+        pos[i] = ki; as_push(&as[ki], i);
+    }
+    const double z = ftau[N - 1];
+    while (it < iters) {
+        it++;
+        if (it % step == 0) {
+            if (res.nsamples < Es_cap && Es) Es[res.nsamples] = E;
+            res.nsamples++;
+            if (hook && !hook(user, it, E, Emin)) break;
+        }
+        /* rand_move, DeltaE.jl:480-517 */
+        const double r = (1 - d.f64(d.user)) * z;
+        int64_t lo = 0, hi = N;                          /* searchsortedfirst: first i (1-based) with fτ[i] >= r */
+        while (lo < hi) { int64_t m = (lo + hi) >> 1; if (ftau[m] < r) lo = m + 1; else hi = m; }
+        const int64_t i = lo + 1;
+        if (i < 1 || i > N) { res.status = -4; break; }  /* @assert 1 ≤ i ≤ N */
+        int k = 0; int64_t t = 0;
+        while (i > t) { k++; t += as[k].t; }
+        const double dE = k <= L ? -c->DE[L - k] : c->DE[k - L + has_zero - 1];
+        const int64_t move = as[k].v[d.range(d.user, as[k].t)];
+        /* apply_move!, DeltaE.jl:519-543 */
+        orc_spinflip(X, s, move);
+        const int n = orc_neighbors(X, move, nb);
+        for (int a = 0; a <= n; a++) {
+            const int64_t j = a < n ? nb[a] : move;
+            const int k0 = (int)pos[j], k1 = eo_findks(c, orc_delta_energy(X, s, j), has_zero);
+            if (k0 == k1) continue;
+            as_delete(&as[k0], j); as_push(&as[k1], j); pos[j] = k1;
+        }
+        E += dE;
+        if (E < Emin) { Emin = E; itmin = it; if (Cmin) memcpy(Cmin, s, (size_t)nch * 8); }
+    }
+    for (int k = 1; k <= K; k++) { if (!res.status && as_check(&as[k])) res.status = -5; as_free(&as[k]); }
+    free(as); free(pos);
+    res.iters_done = it; res.itmin = itmin; res.Emin = Emin; res.Efinal = E;
+    return res;
+}
+
+/* ------------------------------------------------------------------------------------------
  * CPU model of the engine's checkerboard Metropolis (new-engine feature).
  * Deliberately scalar: per (site, replica) ΔE from the ±J definition (EA.jl:277-289 naive form),
  * acceptance = Metropolis (RRRMC.jl:39) with U drawn by the engine's per-task bit procedure:

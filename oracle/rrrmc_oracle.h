@@ -132,6 +132,14 @@ orc_result orc_bklMC(orc_graph *g, double beta, int64_t iters, int64_t step, uin
 orc_result orc_wtmMC(orc_graph *g, double beta, int64_t samples, double step, uint64_t *chunks,
                      orc_draws d, orc_hook hook, void *user, double *Es, int64_t Es_cap);
 
+/* extremal_opt(X, τ, iters; step, hook) — RRRMC.jl:468-521 on EOCache (DeltaE.jl:413-543); DiscrGraph only.
+ * ftau[N] = cumsum(j^-τ, j = 1..N), computed by the caller. Cmin (may be NULL) receives the configuration of minimum
+ * energy. Es (may be NULL) records E at every hook instant — a test aid, the reference returns no energy vector. */
+typedef int (*orc_eo_hook)(void *user, int64_t it, double E, double Emin);
+typedef struct { int64_t nsamples, iters_done, itmin; double Emin; int status; double Efinal; } orc_eo_result;
+orc_eo_result orc_extremal_opt(orc_graph *g, const double *ftau, int64_t iters, int64_t step, uint64_t *chunks,
+                               uint64_t *Cmin, orc_draws d, orc_eo_hook hook, void *user, double *Es, int64_t Es_cap);
+
 /* ΔE-class cache consistency (DeltaE.jl:120-136, ArraySets.jl:27-42); exposed for tests:
  * builds a cache for (g,chunks,beta), applies `nmoves` eager apply_move! calls on sites[], checks
  * consistency after each, and returns 0 when consistent. */

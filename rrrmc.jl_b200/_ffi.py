@@ -16,6 +16,7 @@ CBP_LEN = 64 + 3 * 32   # count tables of the poisson procedure: TA[64] | TB0[32
 CBS_T1, CBS_TC = 33, 129
 
 HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int64)
+EOHOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int64)
 
 
 class Opts(C.Structure):
@@ -81,6 +82,7 @@ SIGNATURES = {
     "rrrmc_rrr_mc": (_i32, _SAMPLER),
     "rrrmc_bkl_mc": (_i32, _SAMPLER),
     "rrrmc_wtm_mc": (_i32, [_vp, _vp, _i64, _f64, _u64, HOOK, _vp, _vp, _i64, C.POINTER(RunInfo)]),
+    "rrrmc_extremal_opt": (_i32, [_vp, _vp, _i64, _i64, _i64, _u64, EOHOOK, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(RunInfo)]),
     "rrrmc_replay": (_i32, [_vp, _i64, _i32, _f64, _i64, _i64, _vp, _vp, _vp, _i64, C.POINTER(Opts), _vp, _i64, C.POINTER(RunInfo)]),
     "rrrmc_checkerboard_sweeps": (_i32, [_vp, _vp, _i32, _i32, _i32, _u64, _u64, _i64]),
     "rrrmc_checkerboard_sparse_tables": (_i32, [_vp, _i32, _vp, _i32]),

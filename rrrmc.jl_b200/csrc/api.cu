@@ -1233,6 +1233,17 @@ extern "C" rrrmc_status_t rrrmc_wtm_mc(rrrmc_state_t *s, const double *beta, int
     if (info) memset(info, 0, sizeof *info);
     return chain_run_wtm(s, beta, samples, step, seed, hook, user, Es, Es_cap, info);
 }
+extern "C" rrrmc_status_t rrrmc_extremal_opt(rrrmc_state_t *s, const double *ftau, int64_t ftau_stride, int64_t iters, int64_t step,
+                                             uint64_t seed, rrrmc_eo_hook_fn hook, void *user,
+                                             double *Emin_out, int64_t *itmin_out, uint64_t *Cmin_chunks,
+                                             double *Es, int64_t Es_cap, rrrmc_run_info_t *info)
+{
+    RR_ARG(s, "state is NULL");
+    RR_ARG(iters >= 0 && step >= 1, "iters must be >= 0 and step >= 1");
+    RR_CUDA(cudaSetDevice(s->g->ctx->device));
+    if (info) memset(info, 0, sizeof *info);
+    return chain_run_eo(s, ftau, ftau_stride, iters, step, seed, hook, user, Emin_out, itmin_out, Cmin_chunks, Es, Es_cap, info);
+}
 extern "C" rrrmc_status_t rrrmc_replay(rrrmc_state_t *s, int64_t replica, int sampler, double beta, int64_t iters, int64_t step,
                                        const uint8_t *kind, const int64_t *ival, const double *fval, int64_t ndraws,
                                        const rrrmc_opts_t *opts, double *Es, int64_t Es_cap, rrrmc_run_info_t *info)

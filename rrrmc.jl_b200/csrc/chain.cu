@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
     double *Es = P.Es;
 
     dcache dc; ccache cc;
-    if (P.sampler != CHAIN_STANDARD && P.sampler != CHAIN_WTM) {
+    if (P.sampler != CHAIN_STANDARD && P.sampler != CHAIN_WTM && P.sampler != CHAIN_EO) {
         if (discr) {
             dc.N = N; dc.L = P.nDE; dc.DE = P.DE; dc.t = h.t; dc.T = dc.Ta; dc.Tp = dc.Tb;
             dc.av = P.av + r * (int64_t)(2 * P.nDE) * N; dc.apos = P.apos + r * N; dc.cls = P.cls + r * N;
@@ -701,6 +701,58 @@ __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
             h.E += dE;
             h.accepted++; h.it++;
         }
+    } else if (P.sampler == CHAIN_EO) { // extremal_opt, RRRMC.jl:494-513 on EOCache (DeltaE.jl:413-543)
+        // classes in ascending ΔE (findks, DeltaE.jl:413-422): K = 2L - has_zero, ΔE = 0 is one class
+        dc.N = N; dc.L = P.nDE; dc.DE = P.DE; dc.t = h.t;
+        dc.av = P.av + r * (int64_t)(2 * P.nDE) * N; dc.apos = P.apos + r * N; dc.cls = P.cls + r * N;
+        const int L = dc.L, hz = dc.DE[0] == 0.0 ? 1 : 0, K = 2 * L - hz;
+        const double *ft = P.eo_ftau + r * P.eo_stride;
+        const double z = ft[N - 1];
+        uint64_t *cmin = P.eo_cmin + r * P.nchunks;
+        auto findks = [&](int j) -> int {
+            const double dE = gv_delta_energy(X, j);
+            const int ak = dc_findk(dc, dE);
+            return dE >= 0 ? ak + L - hz : L + 1 - ak;
+        };
+        if (!h.built) {                  // EOCache ctor, DeltaE.jl:433-441; Emin = E, Cmin = copy(C), RRRMC.jl:480-482
+            for (int k = 0; k <= 2 * L; k++) dc.t[k] = 0;
+            for (int i = 0; i < N; i++) { const int ki = findks(i); dc.cls[i] = (uint8_t)ki; as_push(dc, ki, i); }
+            h.Emin = h.E; h.itmin = 0;
+            for (int64_t w = 0; w < P.nchunks; w++) cmin[w] = X.s[w];
+            h.built = 1;
+        }
+        for (;;) {
+            if (!h.pending) {
+                if (h.it >= iters) { h.done = 1; break; }
+                h.it++;
+                if (h.it % step == 0) { EMIT_SAMPLE(); if (emitted >= P.quota) { h.pending = 1; break; } }
+            }
+            h.pending = 0;
+            const double rr = (1 - src.f64()) * z;                      // rand_move, DeltaE.jl:480-517
+            int lo = 0, hi = N;                                         // searchsortedfirst(fτ, r)
+            while (lo < hi) { const int m = (lo + hi) >> 1; if (ft[m] < rr) lo = m + 1; else hi = m; }
+            const int i = lo + 1;
+            if (i > N || src.err) { if (!src.err) h.status = 3; h.done = 1; break; }
+            int k = 0, t = 0;
+            while (i > t && k < K) { k++; t += dc.t[k]; }
+            const double dE = k <= L ? -dc.DE[L - k] : dc.DE[k - L + hz - 1];
+            const int move = dc.av[(int64_t)(k - 1) * N + src.range(dc.t[k]) - 1];
+            if (src.err) { h.done = 1; break; }
+            gv_spinflip(X, move);                                       // apply_move!, DeltaE.jl:519-543
+            auto reclass = [&](int j) {
+                const int k0 = dc.cls[j], k1 = findks(j);
+                if (k0 == k1) return;
+                as_delete(dc, k0, j); as_push(dc, k1, j); dc.cls[j] = (uint8_t)k1;
+            };
+            gv_for_neighbors(X, move, false, reclass);
+            reclass(move);
+            h.E += dE;
+            h.accepted++;
+            if (h.E < h.Emin) {
+                h.Emin = h.E; h.itmin = h.it;
+                for (int64_t w = 0; w < P.nchunks; w++) cmin[w] = X.s[w];
+            }
+        }
     } else { // bklMC, RRRMC.jl:332-350
         for (;;) {
             if (!h.pending) {
@@ -727,7 +779,7 @@ __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
     }
 #undef EMIT_SAMPLE
     if (P.coop) __shfl_sync(FULLMASK, (int)COOP_EXIT, 0);
-    if (P.sampler != CHAIN_STANDARD && P.sampler != CHAIN_WTM) {
+    if (P.sampler != CHAIN_STANDARD && P.sampler != CHAIN_WTM && P.sampler != CHAIN_EO) {
         if (discr) { for (int k = 0; k <= 2 * dc.L; k++) h.T[k] = dc.T[k]; h.z = dc.z; }
         else { h.z = cc.z; h.trefresh = cc.trefresh; }
     }
@@ -871,6 +923,7 @@ __global__ void k_chain_hdr_reset(chain_params P, int keep_rng)
     if (!keep_rng) h.rng_n = 0;
     h.pending = 0; h.pmove = 0; h.status = 0; h.built = 0; h.trefresh = 0; h.done = 0;
     h.wt_next = P.wt_step;
+    h.Emin = 0; h.itmin = 0;
 }
 // delta_energy straight from the caches: what = 0 delta_energy(X,C,i), 1 residual; all replicas of one site
 __global__ void k_chain_delta_site(chain_params P, int site, int what, double *out)
@@ -920,6 +973,7 @@ void chain_free(rrrmc_state *s)
     cudaFree(c->d_tkind); cudaFree(c->d_tival); cudaFree(c->d_tfval);
     cudaFree(c->ea_lf); cudaFree(c->ea_apos); cudaFree(c->ea_av);
     cudaFree(c->wt_v); cudaFree(c->wt_node); cudaFree(c->wt_pos);
+    cudaFree(c->eo_ftau); cudaFree(c->eo_cmin);
     delete c;
     s->chain = nullptr;
 }
@@ -1149,6 +1203,7 @@ static rrrmc_status_t chain_drive(rrrmc_state *s, chain_params &P, rrrmc_hook_fn
     std::vector<double> row((size_t)P.R * rows_per_launch);
     std::vector<chain_hdr> hh(P.R);
     std::vector<int64_t> acc(P.R);
+    std::vector<double> emin(P.sampler == CHAIN_EO ? P.R : 0);
     const uint64_t l0 = ctx->launches;
     cudaEvent_t e0, e1;
     RR_CUDA(cudaEventCreate(&e0)); RR_CUDA(cudaEventCreate(&e1));
@@ -1174,6 +1229,11 @@ static rrrmc_status_t chain_drive(rrrmc_state *s, chain_params &P, rrrmc_hook_fn
             if (nsamples < want_rows) memcpy(Es + nsamples * P.R, row.data() + k * P.R, 8 * P.R);
             nsamples++;
             if (hook) {
+                if (P.sampler == CHAIN_EO) {   // hook(it, X, C, E, Emin), RRRMC.jl:499
+                    for (int64_t r = 0; r < P.R; r++) emin[r] = hh[r].Emin;
+                    if (!reinterpret_cast<rrrmc_eo_hook_fn>(hook)(user, nsamples * P.step, row.data() + k * P.R, emin.data(), P.R)) stop = true;
+                    continue;
+                }
                 for (int64_t r = 0; r < P.R; r++) acc[r] = hh[r].accepted;
                 if (!hook(user, nsamples * P.step, row.data() + k * P.R, acc.data(), P.R)) stop = true;
             }
@@ -1256,6 +1316,54 @@ rrrmc_status_t chain_run_wtm(rrrmc_state *s, const double *beta, int64_t samples
     sk_dense_invalidate(s);
     if (samples == 0) { if (info) { info->nsamples = 0; info->iters_done = 0; info->launches = 0; info->device_ms = 0; info->accepted_total = 0; } return RRRMC_OK; }
     RR_TRY(chain_drive<src_philox>(s, P, hook, user, Es, Es_cap, info));
+    return RRRMC_OK;
+}
+
+rrrmc_status_t chain_run_eo(rrrmc_state *s, const double *ftau, int64_t ftau_stride, int64_t iters, int64_t step, uint64_t seed,
+                            rrrmc_eo_hook_fn hook, void *user, double *Emin_out, int64_t *itmin_out, uint64_t *Cmin_chunks,
+                            double *Es, int64_t Es_cap, rrrmc_run_info_t *info)
+{
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    const bool discr_full = g->kind == RRRMC_EA_PM1 || g->kind == RRRMC_EA_INT || g->kind == RRRMC_QT;
+    if (!discr_full) {   // gen_EOcache(X::AbstractGraph) = EOCacheCont re-sorts all N spins per move (DeltaE.jl:545-635)
+        rrrmc_set_error("extremal_opt: only DiscrGraph models (GraphEA / GraphRRG with integer levels, GraphQT) are on this path");
+        return RRRMC_ERR_UNSUPPORTED;
+    }
+    RR_ARG(ftau, "ftau is NULL");
+    RR_ARG(ftau_stride == 0 || ftau_stride >= g->N, "ftau_stride must be 0 (one table for all chains) or >= N, given %lld", (long long)ftau_stride);
+    const int64_t ntab = ftau_stride ? s->R : 1, tstride = ftau_stride ? ftau_stride : 0;
+    for (int64_t q = 0; q < ntab; q++) {
+        const double *f = ftau + q * tstride;
+        RR_ARG(std::isfinite(f[g->N - 1]) && f[0] > 0, "ftau must hold the positive cumulative sums of j^-tau");
+        for (int64_t j = 1; j < g->N; j++) RR_ARG(f[j] >= f[j - 1], "ftau must be non-decreasing (cumsum of j^-tau)");
+    }
+    RR_TRY(chain_ensure(s, 1));
+    RR_TRY(chain_sync_from_multispin(s));
+    chain_store *c = s->chain;
+    if (c->eo_ftau_len < ntab * g->N) {
+        cudaFree(c->eo_ftau); c->eo_ftau = nullptr;
+        RR_CUDA(cudaMalloc(&c->eo_ftau, 8 * ntab * g->N)); c->eo_ftau_len = ntab * g->N;
+    }
+    if (!c->eo_cmin) RR_CUDA(cudaMalloc(&c->eo_cmin, 8 * s->R * s->nchunks));
+    if (tstride == 0 || tstride == g->N) RR_CUDA(cudaMemcpyAsync(c->eo_ftau, ftau, 8 * ntab * g->N, cudaMemcpyHostToDevice, ctx->stream));
+    else RR_CUDA(cudaMemcpy2DAsync(c->eo_ftau, 8 * g->N, ftau, 8 * tstride, 8 * g->N, ntab, cudaMemcpyHostToDevice, ctx->stream));
+    chain_params P; chain_fill_params(s, P);
+    P.sampler = CHAIN_EO; P.iters = iters; P.step = step; P.seed = seed;
+    P.eo_ftau = c->eo_ftau; P.eo_stride = ftau_stride ? g->N : 0; P.eo_cmin = c->eo_cmin;
+    k_chain_hdr_reset<<<div_up(P.R, 64), 64, 0, ctx->stream>>>(P, seed == 0);
+    ctx->launches++;
+    RR_TRY(chain_energy_init(s, P, true));
+    s->ms_valid = false;
+    sk_dense_invalidate(s);
+    RR_TRY(chain_drive<src_philox>(s, P, reinterpret_cast<rrrmc_hook_fn>(hook), user, Es, Es_cap, info));
+    std::vector<chain_hdr> hh(s->R);
+    RR_CUDA(cudaMemcpyAsync(hh.data(), c->hdr, sizeof(chain_hdr) * s->R, cudaMemcpyDeviceToHost, ctx->stream));
+    if (Cmin_chunks) RR_CUDA(cudaMemcpyAsync(Cmin_chunks, c->eo_cmin, 8 * s->R * s->nchunks, cudaMemcpyDeviceToHost, ctx->stream));
+    RR_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int64_t r = 0; r < s->R; r++) {
+        if (Emin_out) Emin_out[r] = hh[r].Emin;
+        if (itmin_out) itmin_out[r] = hh[r].itmin;
+    }
     return RRRMC_OK;
 }
 

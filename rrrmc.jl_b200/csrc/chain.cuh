@@ -3,7 +3,7 @@
 #pragma once
 #include "common.cuh"
 
-enum { CHAIN_STANDARD = 0, CHAIN_RRR = 1, CHAIN_BKL = 2, CHAIN_WTM = 3 };
+enum { CHAIN_STANDARD = 0, CHAIN_RRR = 1, CHAIN_BKL = 2, CHAIN_WTM = 3, CHAIN_EO = 4 };
 static inline bool is_sk_kind(int k) { return k == RRRMC_SK_F64 || k == RRRMC_SK_BIN; }
 
 void chain_free(rrrmc_state *s);
@@ -18,6 +18,10 @@ rrrmc_status_t chain_run(rrrmc_state *s, int sampler, const double *beta, int64_
 // wtmMC(X, β, samples; step::Float64) (RRRMC.jl:376-430): `step` in units of the global time, before the division by N
 rrrmc_status_t chain_run_wtm(rrrmc_state *s, const double *beta, int64_t samples, double step, uint64_t seed,
                              rrrmc_hook_fn hook, void *user, double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
+// extremal_opt(X, τ, iters; step, hook) (RRRMC.jl:468-521) on the EOCache of DeltaE.jl:413-543; DiscrGraph only
+rrrmc_status_t chain_run_eo(rrrmc_state *s, const double *ftau, int64_t ftau_stride, int64_t iters, int64_t step, uint64_t seed,
+                            rrrmc_eo_hook_fn hook, void *user, double *Emin_out, int64_t *itmin_out, uint64_t *Cmin_chunks,
+                            double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
 rrrmc_status_t chain_replay(rrrmc_state *s, int64_t replica, int sampler, double beta, int64_t iters, int64_t step,
                             const uint8_t *kind, const int64_t *ival, const double *fval, int64_t ndraws,
                             const rrrmc_opts_t *o, double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
@@ -34,6 +38,7 @@ struct chain_hdr {
     int t[2 * MAXL + 1];
     int pending, pmove, status, built, trefresh, done;
     double wt_next;               // wtmMC: global time of the next sample (RRRMC.jl:396)
+    double Emin; long long itmin; // extremal_opt: minimum energy found and its iteration (RRRMC.jl:480-482)
 };
 
 struct chain_store {
@@ -41,6 +46,7 @@ struct chain_store {
     int levs = 0, nDE = 0;
     bool f64 = false;             // fp64 local fields (EA F64, SK F64, QUANT over SK F64)
     bool cont_ready = false, disc_ready = false, wtm_ready = false;
+    double *eo_ftau = nullptr; int64_t eo_ftau_len = 0; uint64_t *eo_cmin = nullptr; // extremal_opt: fτ table(s), Cmin [R][nchunks]
     double *wt_v = nullptr; int32_t *wt_node = nullptr, *wt_pos = nullptr; // wtmMC heap [R][N]: times / sites in heap order, heap position of a site
     int32_t *lfi = nullptr;       // [R][2][N] (EA: cur,last; SK family: per slice [2][Nk])
     double *lfd = nullptr;
@@ -80,6 +86,7 @@ struct chain_params {
     double staged_thr, staged_thr_fact;
     const uint8_t *tkind; const int64_t *tival; const double *tfval; int64_t tlen;
     double *wt_v; int32_t *wt_node, *wt_pos; double wt_step, wt_tmax;  // wtmMC: heap, step/N, step/N·samples
+    const double *eo_ftau; int64_t eo_stride; uint64_t *eo_cmin;            // extremal_opt: fτ [N] (stride 0) or [R][N], Cmin
     int fast;                     // 1: GraphEA ±J fast path (chain_ea.cu)
     int8_t *ea_lf; uint16_t *ea_apos, *ea_av;
 };

@@ -284,6 +284,58 @@ class GraphEANormal(AbstractGraph):
         check(lib().rrrmc_graph_ea_create(self.ctx.h, L, D, _ffi.EA_F64, ptr(self.A), ptr(self.J), C.byref(h)))
         self._h = h
 
+    @classmethod
+    def from_file(cls, fname, replicas=1, ctx=None):
+        """GraphEANormal(fname::AbstractString) (src/graphs/EA.jl:576-580): a 2D instance in gen_AJ's file format."""
+        L, D, A, J = gen_AJ(fname)
+        return cls(L, D, replicas=replicas, A=A, J=J, ctx=ctx)
+
+
+def gen_AJ(fname):
+    """gen_AJ(fname) (src/graphs/EA.jl:73-118): the reference's on-disk instance format, 2D lattices only — three header
+    lines `type: …`, `size: L`, `name: …`, then one `x y Jxy` line per bond (1-based sites of gen_EA(L, 2)); every bond
+    must appear exactly once and be a lattice bond. Returns (L, D, A, J) with J slot-aligned with A (float64)."""
+    D = 2
+    with open(fname) as f:
+        if not f.readline().strip().startswith("type:"):
+            raise ValueError(f"{fname}: first line must start with 'type:'")
+        ls = f.readline().split()
+        if len(ls) != 2 or ls[0] != "size:":
+            raise ValueError(f"{fname}: second line must be 'size: L'")
+        L = int(ls[1])
+        if not f.readline().strip().startswith("name:"):
+            raise ValueError(f"{fname}: third line must start with 'name:'")
+        A = gen_EA(L, D)
+        N = A.shape[0]
+        J = np.full((N, 2 * D), np.nan)            # NaN plays the reference's sentinel (EA.jl:88-90)
+        for ln, l in enumerate(f, 4):
+            ls = l.split()
+            if len(ls) != 3:
+                raise ValueError(f"{fname}:{ln}: expected 'x y Jxy'")
+            x, y, Jxy = int(ls[0]), int(ls[1]), float(ls[2])
+            if not (1 <= x <= N and 1 <= y <= N):
+                raise ValueError(f"{fname}:{ln}: site out of range 1..{N}")
+            for a, b in ((x, y), (y, x)):
+                k = np.flatnonzero(A[a - 1] == b)  # findfirst(Ax, y), EA.jl:98-107
+                if len(k) == 0:
+                    raise ValueError(f"{fname}:{ln}: {a} and {b} are not neighbours on the {L}x{L} lattice")
+                if not np.isnan(J[a - 1, k[0]]):
+                    raise ValueError(f"{fname}:{ln}: bond {x}-{y} given twice")
+                J[a - 1, k[0]] = Jxy
+        if np.isnan(J).any():
+            raise ValueError(f"{fname}: {int(np.isnan(J).sum()) // 2} bond(s) missing")  # EA.jl:110
+    return L, D, A, J
+
+
+def write_AJ(fname, L, A, J, name="instance", kind="EA2D"):
+    """Writes an (A, J) 2D instance in the format gen_AJ reads (the reference ships a reader only)."""
+    with open(fname, "w") as f:
+        f.write(f"type: {kind}\nsize: {L}\nname: {name}\n")
+        for x in range(A.shape[0]):
+            for k in range(A.shape[1]):
+                if A[x, k] > x + 1:
+                    f.write(f"{x + 1} {A[x, k]} {float(J[x, k])!r}\n")
+
 
 def gen_RRG(N, K, rng=None, max_attempts=100_000):
     """gen_RRG (src/graphs/RRG.jl:27-68): a random K-regular simple graph by the Bollobás pairing model, as an (N, K) array
@@ -737,6 +789,88 @@ def wtmMC(X, β, samples, *, seed=DEFAULT_SEED, step=1.0, hook=None, C0=None, qu
         print("num_moves =", info.iters_done)
     X.last_run = info
     return (Es[:, 0] if R == 1 else Es), Cout
+
+
+def eo_ftau(N, τ):
+    """fτ = cumsum([j^(-τ) for j = 1:N]) (src/DeltaE.jl:443), summed the way Julia's `cumsum` sums a Float64 vector:
+    Base.accumulate_pairwise! (blocks of < 128 elements accumulated left to right, block sums combined pairwise).
+    The powers come from this host's libm `pow`; a Julia host passes its own table (julia/RRRMCB200.jl)."""
+    v = np.arange(1, int(N) + 1, dtype=np.float64) ** (-float(τ))
+    out = np.empty_like(v)
+    if len(v) == 0:
+        return out
+    out[0] = v[0]
+
+    def rec(s, i1, n):
+        if n < 128:
+            s_ = v[i1]
+            out[i1] = s + s_
+            for i in range(i1 + 1, i1 + n):
+                s_ = s_ + v[i]
+                out[i] = s + s_
+            return s_
+        n2 = n >> 1
+        s1 = rec(s, i1, n2)
+        s2 = rec(s + s1, i1 + n2, n - n2)
+        return s1 + s2
+    if len(v) > 1:
+        rec(v[0], 1, len(v) - 1)
+    return out
+
+
+def extremal_opt(X, τ, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, quiet=False, ftau=None, return_Es=False):
+    """extremal_opt(X, τ, iters; seed, step, hook, C0, quiet) (src/RRRMC.jl:468-521) -> (C, Emin, Cmin, itmin), batched
+    over the replicas (Emin, itmin are arrays when the batch holds more than one chain; τ may be one value per chain).
+    hook(it, X, C, E, Emin)::Bool. DiscrGraph models only. `ftau` overrides the table built by `eo_ftau`;
+    `return_Es=True` appends the energies at the hook instants (a test aid, not in the reference)."""
+    if step < 1:
+        raise ValueError("step must be ≥ 1")
+    st = X._ensure_state()
+    if C0 is None:
+        check(lib().rrrmc_state_randomize(st, seed if seed > 0 else np.random.SeedSequence().entropy & (2 ** 63 - 1)))
+    else:
+        X._upload(C0)
+    R = X.replicas
+    if ftau is None:
+        taus = np.atleast_1d(np.asarray(τ, np.float64))
+        ftau = eo_ftau(X.N, taus[0]) if len(taus) == 1 else np.stack([eo_ftau(X.N, t) for t in taus])
+    ftau = np.ascontiguousarray(ftau, np.float64)
+    if ftau.shape not in ((X.N,), (R, X.N)):
+        raise ValueError(f"ftau must have shape ({X.N},) or ({R}, {X.N})")
+    stride = 0 if ftau.ndim == 1 else X.N
+    cap = min(10 ** 8, int(iters) // int(step))
+    Es = np.zeros((max(cap, 1), R), np.float64)
+    Emin = np.zeros(R, np.float64); itmin = np.zeros(R, np.int64)
+    Cmin = Config(X.N, R, init=False)
+    info = _ffi.RunInfo()
+    last = {}
+
+    def _hook(user, it, E, Em, n):
+        Ev = np.ctypeslib.as_array(E, (n,)).copy()
+        Mv = np.ctypeslib.as_array(Em, (n,)).copy()
+        try:
+            ok = hook(it, X, _LazyConfig(X), _scalarize(X, Ev), _scalarize(X, Mv))
+        except Exception as e:  # propagate after the C call returns
+            last["exc"] = e
+            return 0
+        return 1 if ok else 0
+    cb = _ffi.EOHOOK(_hook) if hook is not None else C.cast(None, _ffi.EOHOOK)
+    check(lib().rrrmc_extremal_opt(st, ptr(ftau), stride, int(iters), int(step), int(seed) if seed > 0 else 0, cb, None,
+                                   ptr(Emin), ptr(itmin), ptr(Cmin.chunks), ptr(Es), cap, C.byref(info)))
+    if "exc" in last:
+        raise last["exc"]
+    Cout = X._download()
+    X.last_run = info
+    if not quiet:
+        print("iters =", info.iters_done)
+        print(f"min [it = {itmin if R > 1 else int(itmin[0])}] = {_scalarize(X, Emin)}")
+    out = (Cout, _scalarize(X, Emin), Cmin, itmin if R > 1 else int(itmin[0]))
+    if return_Es:
+        Es = Es[:info.nsamples]
+        if X.ET is int:
+            Es = np.rint(Es).astype(np.int64)
+        out = out + ((Es[:, 0] if R == 1 else Es),)
+    return out
 
 
 def replay(X, C0, sampler, β, iters, kind, ival, fval, *, step=1, replica=0, staged_thr=float("nan"), staged_thr_fact=5.0):

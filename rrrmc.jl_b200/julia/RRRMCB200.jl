@@ -11,7 +11,7 @@
 #     Es, C = standardMC(X, 1.0, 10^3 * X.N; step = 10 * X.N)
 module RRRMCB200
 
-export standardMC, rrrMC, bklMC, wtmMC
+export standardMC, rrrMC, bklMC, wtmMC, extremal_opt
 
 const lib = get(ENV, "RRRMC_B200_LIB", joinpath(@__DIR__, "..", "lib", "librrrmc_b200.so"))
 
@@ -73,6 +73,33 @@ function GraphEA(L::Integer, D::Integer, A::Matrix{Int64}, J::Matrix; replicas::
                 ctx().h, L, D, kind, permutedims(A), Jc, r))
     _finish(r[], kind == EA_F64 ? Float64 : Int, replicas, kind)
 end
+"gen_AJ(fname) (src/graphs/EA.jl:73-118): `type:`/`size: L`/`name:` header, then `x y Jxy` per bond of the L×L lattice -> (L, D, A, J) as N×2D matrices."
+function gen_AJ(fname::AbstractString)
+    D = 2
+    open(fname) do f
+        startswith(strip(readline(f)), "type:") || throw(ArgumentError("$fname: first line must start with type:"))
+        ls = split(readline(f)); (length(ls) == 2 && ls[1] == "size:") || throw(ArgumentError("$fname: second line must be `size: L`"))
+        L = parse(Int, ls[2])
+        startswith(strip(readline(f)), "name:") || throw(ArgumentError("$fname: third line must start with name:"))
+        N = L^D; At = zeros(Int64, 2D, N)
+        check(ccall((:rrrmc_gen_ea_adjacency, lib), Cint, (Cint, Cint, Ptr{Int64}), L, D, At))
+        A = permutedims(At); J = fill(NaN, N, 2D)
+        for l in eachline(f)
+            ls = split(l); length(ls) == 3 || throw(ArgumentError("$fname: expected `x y Jxy`, got: $l"))
+            x, y, Jxy = parse(Int, ls[1]), parse(Int, ls[2]), parse(Float64, ls[3])
+            for (a, b) in ((x, y), (y, x))
+                k = findfirst(==(b), view(A, a, :))
+                k === nothing && throw(ArgumentError("$fname: $a and $b are not neighbours"))
+                isnan(J[a, k]) || throw(ArgumentError("$fname: bond $x-$y given twice"))
+                J[a, k] = Jxy
+            end
+        end
+        any(isnan, J) && throw(ArgumentError("$fname: bonds missing"))
+        L, D, A, J
+    end
+end
+"GraphEANormal(fname) (src/graphs/EA.jl:576-580)"
+GraphEANormal(fname::AbstractString; replicas::Integer = 1) = ((L, D, A, J) = gen_AJ(fname); GraphEA(L, D, A, J; replicas = replicas))
 "GraphEANormalDiscretized{Int,LEV,twoD} (src/graphs/EA.jl:311-360) from the continuous couplings cJ (N×2D, slot-aligned with A)."
 function GraphEANormalDiscretized(L::Integer, D::Integer, LEV::NTuple{K,Int}, A::Matrix{Int64}, cJ::Matrix{Float64}; replicas::Integer = 1) where {K}
     r = Ref{Ptr{Cvoid}}(C_NULL)
@@ -227,6 +254,27 @@ function wtmMC(X::Graph, β::Real, samples::Integer; seed = 167432777111, step::
         X.state, betas, samples, step, seed > 0 ? seed : 0, cb, pointer_from_objref(ud), Es, cap, info))
     quiet || (println("samples = ", info[].nsamples); println("num_moves = ", info[].iters_done))
     Es[:, 1:info[].nsamples], download(X)
+end
+
+# hook(it, X, C, E, Emin)::Bool of RRRMC.jl:499
+function _eo_hook_tramp(user::Ptr{Cvoid}, it::Int64, E::Ptr{Cdouble}, Emin::Ptr{Cdouble}, R::Int64)::Cint
+    f, X = unsafe_pointer_to_objref(user)::Tuple{Function,Graph}
+    Cint(f(it, X, download(X), unsafe_wrap(Array, E, R), unsafe_wrap(Array, Emin, R)) ? 1 : 0)
+end
+"extremal_opt(X, τ, iters; seed, step, hook, C0, quiet) (src/RRRMC.jl:468-521) -> (C, Emin, Cmin, itmin), one entry per replica; DiscrGraph models only."
+function extremal_opt(X::Graph, τ::Real, iters::Integer; seed = 167432777111, step::Integer = 1, hook = (x...) -> true,
+                      C0::Union{Config,Nothing} = nothing, quiet::Bool = false)
+    C0 === nothing ? check(ccall((:rrrmc_state_randomize, lib), Cint, (Ptr{Cvoid}, UInt64), X.state, seed > 0 ? seed : rand(UInt64))) :
+                     upload!(X, C0)
+    fτ = cumsum([j^(-Float64(τ)) for j = 1:X.N])                           # DeltaE.jl:443: Julia's own `^` and pairwise cumsum
+    Emin = zeros(X.replicas); itmin = zeros(Int64, X.replicas); Cmin = Config(X.N, X.replicas); info = Ref{RunInfo}()
+    ud = Ref((hook, X)); cb = @cfunction(_eo_hook_tramp, Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Int64))
+    GC.@preserve ud check(ccall((:rrrmc_extremal_opt, lib), Cint,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Int64, Int64, UInt64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Int64}, Ptr{UInt64},
+         Ptr{Cdouble}, Int64, Ref{RunInfo}),
+        X.state, fτ, 0, iters, step, seed > 0 ? seed : 0, cb, pointer_from_objref(ud), Emin, itmin, Cmin.chunks, C_NULL, 0, info))
+    quiet || (println("iters = ", info[].iters_done); println("min [it = $itmin] = $Emin"))
+    download(X), Emin, Cmin, itmin
 end
 
 end # module

@@ -6,7 +6,8 @@
   rrg: the benchmark of the RRR paper (reference scripts/scripts.jl:23-40): GraphRRG N=10^4, K=3, ±J, β=2 with all four
        samplers (met = standardMC in the reference's random-site order, bkl, rrr, wtm), 256 replicas, and the CPU oracle
        on one host core beside each
-usage: python scripts/bench_configs.py [c3] [c4] [c5] [rrg] [--quick]"""
+  eo:  extremal_opt (τ = 1.3) on the same RRG instance family, moves/s beside the CPU oracle on one core
+usage: python scripts/bench_configs.py [c3] [c4] [c5] [rrg] [eo] [--quick]"""
 import json
 import os
 import sys
@@ -108,3 +109,25 @@ if "rrg" in which:
     emit(config="RRG", sampler="wtmMC", N=N, K=K, replicas=R, beta=beta, samples=samples, global_time_per_sample=50.0,
          executed_moves_per_s=info.accepted_total / (info.device_ms * 1e-3), device_ms=info.device_ms,
          cpu_oracle_1core_moves_per_s=res.accepted / cdt)
+
+if "eo" in which:
+    # extremal_opt (τ-EO, RRRMC.jl:468-521) on the RRG instance family of the paper's benchmark: moves/s, one B200 vs one host core
+    from oracle import ffi   # CPU restatement: the baseline leg of this script only
+    N, K, R, tau = 10_000, 3, int(os.environ.get("RRG_R", "256")), 1.3
+    rng = np.random.default_rng(8370000274 % 2 ** 32)
+    A = rb.gen_RRG(N, K, rng)
+    J = rb.gen_J_graph(lambda n: rng.choice([-1.0, 1.0], n), A).astype(np.int64)
+    X = rb.GraphRRG(N, K, replicas=R, A=A, J=J)
+    C0 = rb.Config(N, R, rng=np.random.default_rng(4))
+    iters = 200_000 if quick else 2_000_000
+    rb.extremal_opt(X, tau, iters // 20, step=iters // 20, seed=2, C0=C0, quiet=True)
+    _, Emin, _, itmin = rb.extremal_opt(X, tau, iters, step=iters, seed=3, C0=C0, quiet=True)
+    info = X.last_run
+    g = ffi.Graph.rrg_int(A, J); s0 = C0.chunks[0].copy()
+    cpu_it = iters // 4
+    t0 = time.perf_counter()
+    _, _, res = ffi.extremal_opt(g, rb.eo_ftau(N, tau), cpu_it, s0, ffi.PhiloxDraws(3, chain=0), step=cpu_it)
+    cdt = time.perf_counter() - t0
+    emit(config="RRG", sampler="extremal_opt", N=N, K=K, replicas=R, tau=tau, iters_per_replica=iters,
+         moves_per_s=R * iters / (info.device_ms * 1e-3), device_ms=info.device_ms, Emin_mean_per_spin=float(np.mean(Emin)) / N,
+         cpu_oracle_1core_moves_per_s=cpu_it / cdt)

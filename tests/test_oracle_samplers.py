@@ -224,3 +224,44 @@ def test_wtmMC_boltzmann_stationarity():
     big = p > 2e-3
     rel = np.abs(counts[big] / n - p[big]) / p[big]
     assert rel.max() < 0.12, rel.max()
+
+
+# ---- extremal_opt (RRRMC.jl:468-521, EOCache DeltaE.jl:413-543) -------------------------------------------------
+@pytest.mark.parametrize("name", ["EA(2,3)", "EA(3,2)", "EA(3,2,(-1,0,1))", "RRG(10,3)", "RRG(10,3,(-1,0,1))"])
+def test_extremal_opt_energy_consistency(name):
+    """E tracked through the ranked moves ≡ energy(X, C) at every hook (the invariant of test/runtests.jl:12-20, which
+    the reference applies to its Monte Carlo samplers); Emin/Cmin/itmin are what the run actually visited."""
+    g = reference_graphs()[name]
+    N = g.N
+    s = random_config(N, 5)
+    ftau = np.cumsum(np.arange(1, N + 1, dtype=np.float64) ** -1.3)
+    g2 = reference_graphs()[name]
+    seen = []
+
+    def hook(it, E, Emin):
+        assert E == g2.energy(s.copy()) and Emin <= E
+        seen.append((it, E))
+        return True
+    Es, Cmin, res = ffi.extremal_opt(g, ftau, 400, s, ffi.PhiloxDraws(3, 0), step=4, hook=hook)
+    assert len(seen) == 100 and [e for _, e in seen] == list(Es)
+    assert res.Efinal == g2.energy(s.copy()) and g2.energy(Cmin.copy()) == res.Emin
+    assert res.Emin <= Es.min() and 0 <= res.itmin <= 400
+
+
+def test_extremal_opt_rank_distribution():
+    """On a graph with no bonds to break the ranking (GraphQT with fourK = 0 has every ΔE = 0: one class), τ-EO picks
+    sites uniformly; with distinct classes the lowest-ΔE class must be picked with probability fτ[n₁]/z."""
+    A, J = ea_instance(4, 2, seed=2)
+    g = ffi.Graph.ea_int(A, J)
+    N = g.N
+    tau = 1.5
+    ftau = np.cumsum(np.arange(1, N + 1, dtype=np.float64) ** -tau)
+    hits, tot = 0, 4000
+    for k in range(tot):
+        s = random_config(N, 77)      # same start each time, one move, different draws
+        dE = np.array([g.delta_energy(s, i) for i in range(1, N + 1)]) if g.energy(s) is not None else None
+        n1 = int((dE == dE.min()).sum())
+        Es, _, res = ffi.extremal_opt(g, ftau, 2, s, ffi.PhiloxDraws(1000 + k, 0), step=1)
+        hits += (Es[1] - Es[0]) == dE.min()
+    p = ftau[n1 - 1] / ftau[-1]
+    assert abs(hits / tot - p) < 4 * np.sqrt(p * (1 - p) / tot)
