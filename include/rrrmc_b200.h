@@ -151,6 +151,13 @@ rrrmc_status_t rrrmc_Qenergy(rrrmc_state_t *s, double *out);
 rrrmc_status_t rrrmc_Renergies(rrrmc_state_t *s, double *out);
 rrrmc_status_t rrrmc_overlaps(rrrmc_state_t *s, double *out);
 
+/* A GraphQuant batch as a parallel-tempering ladder: replica r sits at beta[r], hence at its own
+ * fourK(β) = round(2/β·log coth(βΓ/M), digits=8) — a type parameter of GraphQuant{fourK,G} in the reference
+ * (QT.jl:126,165), so there every β is a distinct graph; here it is per-replica state. Affects energy, delta_energy,
+ * allΔE of the inner GraphQT inside the samplers, transverse_mag and Qenergy. beta = NULL restores the graph's β.
+ * fourK_out (may be NULL) receives the R values. The β passed to a sampler must be the same vector. */
+rrrmc_status_t rrrmc_state_set_quant_betas(rrrmc_state_t *s, const double *beta, double *fourK_out);
+
 /* ---- samplers ------------------------------------------------------------------------------ */
 /* hook(it, X, C, accepted, E)::Bool of RRRMC.jl:61-64,104-109, batched: E[R], accepted[R]
  * (accepted[r] = -1 when counting is disabled). Return 0 to stop the run. Called on the host

@@ -82,6 +82,7 @@ SIGNATURES = {
     "rrrmc_rrr_mc": (_i32, _SAMPLER),
     "rrrmc_bkl_mc": (_i32, _SAMPLER),
     "rrrmc_wtm_mc": (_i32, [_vp, _vp, _i64, _f64, _u64, HOOK, _vp, _vp, _i64, C.POINTER(RunInfo)]),
+    "rrrmc_state_set_quant_betas": (_i32, [_vp, _vp, _vp]),
     "rrrmc_extremal_opt": (_i32, [_vp, _vp, _i64, _i64, _i64, _u64, EOHOOK, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(RunInfo)]),
     "rrrmc_replay": (_i32, [_vp, _i64, _i32, _f64, _i64, _i64, _vp, _vp, _vp, _i64, C.POINTER(Opts), _vp, _i64, C.POINTER(RunInfo)]),
     "rrrmc_checkerboard_sweeps": (_i32, [_vp, _vp, _i32, _i32, _i32, _u64, _u64, _i64]),

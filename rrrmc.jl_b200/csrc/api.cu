@@ -441,6 +441,26 @@ extern "C" rrrmc_status_t rrrmc_graph_quant_ea_create(rrrmc_ctx_t *ctx, int L, i
     *out = e;
     return RRRMC_OK;
 }
+extern "C" rrrmc_status_t rrrmc_state_set_quant_betas(rrrmc_state_t *s, const double *beta, double *fourK_out)
+{
+    RR_ARG(s, "state is NULL");
+    rrrmc_graph *g = s->g;
+    RR_ARG(g->kind == RRRMC_QUANT, "a per-replica β ladder applies to GraphQuant only (fourK is a function of β, QT.jl:165)");
+    RR_CUDA(cudaSetDevice(g->ctx->device));
+    s->energy_valid = false;
+    if (!beta) { s->q_beta.clear(); s->q_fourK.clear(); cudaFree(s->d_q_fourK); s->d_q_fourK = nullptr; return RRRMC_OK; }
+    std::vector<double> b(beta, beta + s->R), fk(s->R);
+    for (int64_t r = 0; r < s->R; r++) {
+        RR_ARG(std::isfinite(b[r]) && b[r] > 0, "β must be finite and positive, given: %g (replica %lld)", b[r], (long long)r);
+        fk[r] = nearbyint(2.0 / b[r] * log(1.0 / tanh(b[r] * g->Gamma / (double)g->M)) * 1e8) / 1e8;   // QT.jl:165
+    }
+    if (!s->d_q_fourK) RR_CUDA(cudaMalloc(&s->d_q_fourK, 8 * s->R));
+    RR_CUDA(cudaMemcpyAsync(s->d_q_fourK, fk.data(), 8 * s->R, cudaMemcpyHostToDevice, g->ctx->stream));
+    RR_CUDA(cudaStreamSynchronize(g->ctx->stream));
+    if (fourK_out) memcpy(fourK_out, fk.data(), 8 * s->R);
+    s->q_beta.swap(b); s->q_fourK.swap(fk);
+    return RRRMC_OK;
+}
 extern "C" rrrmc_status_t rrrmc_graph_fourK(const rrrmc_graph_t *g, double *fourK)
 {
     RR_ARG(g && fourK, "NULL argument");
@@ -621,7 +641,7 @@ extern "C" rrrmc_status_t rrrmc_state_destroy(rrrmc_state_t *s)
     cudaSetDevice(s->g->ctx->device);
     cudaStreamSynchronize(s->g->ctx->stream);
     cudaFree(s->d_spins); cudaFree(s->d_chunks); cudaFree(s->d_ibuf); cudaFree(s->d_acc);
-    cudaFree(s->d_flips); cudaFree(s->d_mask);
+    cudaFree(s->d_flips); cudaFree(s->d_mask); cudaFree(s->d_q_fourK);
     chain_free(s);
     sk_dense_free(s);
     delete s;

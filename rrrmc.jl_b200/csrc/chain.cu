@@ -555,7 +555,7 @@ __device__ __forceinline__ gview make_view(const chain_params &P, int64_t r)
     X.lfi = P.lfi ? P.lfi + r * 2 * (int64_t)P.N : nullptr;
     X.lfd = P.lfd ? P.lfd + r * 2 * (int64_t)P.N : nullptr;
     X.ml = P.ml + r * P.M; X.sw = P.sw + r * P.M;
-    X.Nk = P.Nk; X.M = P.M; X.inner = P.inner; X.nz = P.nz; X.fourK = P.fourK; X.sN = P.sN;
+    X.Nk = P.Nk; X.M = P.M; X.inner = P.inner; X.nz = P.nz; X.fourK = P.fourK_r ? P.fourK_r[r] : P.fourK; X.sN = P.sN;
     X.coop = P.coop;
     return X;
 }
@@ -590,10 +590,11 @@ __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
     const long long iters = P.iters, step = P.step;
     double *Es = P.Es;
 
-    dcache dc; ccache cc;
+    dcache dc; ccache cc; double de_q[2];
     if (P.sampler != CHAIN_STANDARD && P.sampler != CHAIN_WTM && P.sampler != CHAIN_EO) {
         if (discr) {
             dc.N = N; dc.L = P.nDE; dc.DE = P.DE; dc.t = h.t; dc.T = dc.Ta; dc.Tp = dc.Tb;
+            if (P.fourK_r) { de_q[0] = 0.0; de_q[1] = X.fourK; dc.DE = de_q; }   // allΔE of this replica's GraphQT, QT.jl:111
             dc.av = P.av + r * (int64_t)(2 * P.nDE) * N; dc.apos = P.apos + r * N; dc.cls = P.cls + r * N;
             for (int k = 0; k < dc.L; k++) dc.ft[k] = exp(-beta * dc.DE[k]);
             for (int k = 0; k <= 2 * dc.L; k++) dc.T[k] = h.T[k];
@@ -907,7 +908,7 @@ __global__ void k_chain_energy_sum(chain_params P, double *E_out, int mode)
     } else if (is_sk(P.kind)) E = sk_slice_energy(P, P.kind, r, 0, s);
     else if (P.kind == RRRMC_QT) E = (double)qt_energy0(P, s) * P.fourK / 4; // QT.jl:84
     else {                        // GraphQuant, QT.jl:185-199
-        E = (double)qt_energy0(P, s) * P.fourK / 4;
+        E = (double)qt_energy0(P, s) * (P.fourK_r ? P.fourK_r[r] : P.fourK) / 4;
         for (int k = 0; k < P.M; k++) E = __dadd_rn(E, sk_slice_energy(P, P.inner, r, k, s) / (double)P.M);
     }
     E_out[r] = E;
@@ -1071,6 +1072,7 @@ static void chain_fill_params(rrrmc_state *s, chain_params &P)
     memset(&P, 0, sizeof P);
     P.kind = g->kind; P.N = (int)g->N; P.twoD = g->twoD; P.nDE = c->nDE; P.levs = c->levs; P.N2 = c->N2;
     P.Nk = (int)g->Nk; P.M = (int)g->M; P.inner = g->inner; P.nz = g->nz_neighbors ? 1 : 0; P.fourK = g->fourK; P.sN = g->sN;
+    P.fourK_r = g->kind == RRRMC_QUANT ? s->d_q_fourK : nullptr;
     P.R = s->R; P.nchunks = s->nchunks; P.chain0 = 0;
     P.A = g->d_A; P.J8 = g->d_J8; P.Jd = g->d_Jd; P.Jb = g->d_Jb;
     P.chunks = s->d_chunks;
@@ -1169,9 +1171,10 @@ rrrmc_status_t chain_quant_observable(rrrmc_state *s, int what, double arg, doub
     RR_CUDA(cudaGetLastError());
     RR_CUDA(cudaStreamSynchronize(ctx->stream));
     if (what == 2) { memcpy(out, re.data(), 8 * R * M); return RRRMC_OK; }
-    const double beta = what == 0 ? arg : g->beta;
     for (int64_t r = 0; r < R; r++) {
-        const double p = -e0[r] / (double)g->N, x = beta * g->fourK / 2;
+        const double beta = what == 0 ? arg : (s->q_beta.empty() ? g->beta : s->q_beta[r]);
+        const double fourK = s->q_fourK.empty() ? g->fourK : s->q_fourK[r];
+        const double p = -e0[r] / (double)g->N, x = beta * fourK / 2;
         const double tm = cosh(x) - p * sinh(x);                 // QT.jl:113-121
         if (what == 0) { out[r] = tm; continue; }
         double E = -g->Gamma * tm;                               // QT.jl:253-268

@@ -71,6 +71,7 @@ struct chain_params {
     int Nk, M, inner;
     int nz;                       // 1: GraphRRG semantics — neighbors() of the integer graph skips zero couplings (RRG.jl:133)
     double fourK, sN;
+    const double *fourK_r;        // [R] per-replica fourK of a GraphQuant β ladder (NULL: the graph's)
     int64_t R, N2, nchunks, chain0;
     const int32_t *A; const int8_t *J8; const double *Jd; const uint8_t *Jb;
     uint64_t *chunks;

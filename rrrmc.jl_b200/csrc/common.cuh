@@ -78,6 +78,9 @@ struct rrrmc_state {
     bool ms_valid = true;            // multispin copy is current
     bool chain_valid = false;        // d_chunks copy is current
     bool chain_fields_valid = false; // the chains' local-field caches match d_chunks
+    // a GraphQuant batch whose replicas sit at different β (a parallel-tempering ladder): fourK is a function of β
+    // (QT.jl:165), so every replica carries its own; empty = all replicas at the graph's β
+    std::vector<double> q_beta, q_fourK; double *d_q_fourK = nullptr;
     struct chain_store *chain = nullptr;
     struct sk_dense_store *skd = nullptr; // dense GraphSKNormal kernels (sk_dense.cu)
 };

@@ -535,6 +535,20 @@ class GraphQuant(AbstractGraph):
         check(lib().rrrmc_graph_fourK(self._h, C.byref(fk)))
         self.fourK = fk.value
 
+    def set_betas(self, betas):
+        """Turns the batch into a β ladder: replica r at betas[r] with its own fourK(β) (QT.jl:165; in the reference each
+        β is a separate GraphQuant{fourK,G}). None restores the graph's β. Returns the per-replica fourK."""
+        st = self._ensure_state()
+        if betas is None:
+            check(lib().rrrmc_state_set_quant_betas(st, None, None))
+            self.betas = None
+            return None
+        b = np.ascontiguousarray(np.broadcast_to(np.asarray(betas, np.float64), (self.replicas,)))
+        fk = np.zeros(self.replicas, np.float64)
+        check(lib().rrrmc_state_set_quant_betas(st, ptr(b), ptr(fk)))
+        self.betas = b.copy()
+        return fk
+
     def inner_graph(self):
         """inner_graph(X) (Interface.jl:239-240; QT.jl:148): the GraphQT part, on its own replica batch."""
         return GraphQT(self.N, self.M, self.fourK, replicas=self.replicas, ctx=self.ctx)

@@ -256,6 +256,11 @@ function wtmMC(X::Graph, β::Real, samples::Integer; seed = 167432777111, step::
     Es[:, 1:info[].nsamples], download(X)
 end
 
+"set_betas!(X, betas): a GraphQuant batch as a β ladder — replica r at betas[r] with its own fourK(β) (QT.jl:165); returns the fourK vector."
+function set_betas!(X::Graph, betas::Vector{Float64})
+    fk = zeros(X.replicas)
+    check(ccall((:rrrmc_state_set_quant_betas, lib), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), X.state, betas, fk)); fk
+end
 # hook(it, X, C, E, Emin)::Bool of RRRMC.jl:499
 function _eo_hook_tramp(user::Ptr{Cvoid}, it::Int64, E::Ptr{Cdouble}, Emin::Ptr{Cdouble}, R::Int64)::Cint
     f, X = unsafe_pointer_to_objref(user)::Tuple{Function,Graph}

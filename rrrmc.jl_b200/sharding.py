@@ -71,6 +71,18 @@ def quantum_action(M, Gamma):
     return action
 
 
+def quant_terms(X, C):
+    """(e0, E_cl) of every local replica of a GraphQuant batch for `quantum_action`: E_cl = Σ_k E_classical(slice k)
+    (Renergies, QT.jl:201-211) and e0 = −Σ_{Trotter bonds} σσ′ recovered from E = fourK/4·e0 + E_cl/M (QT.jl:185-199)
+    with the replica's own fourK."""
+    import rrrmc_b200 as rb
+    E = np.atleast_1d(np.asarray(rb.energy(X, C), np.float64))
+    ecl = np.asarray(rb.Renergies(X), np.float64).reshape(X.replicas, X.M).sum(axis=1)
+    fk = np.full(X.replicas, X.fourK) if getattr(X, "betas", None) is None else \
+        np.round(2.0 / X.betas * np.log(1.0 / np.tanh(X.betas * X.Γ / X.M)), 8)
+    return np.rint((E - ecl / X.M) * 4.0 / fk), ecl
+
+
 class TemperingLadder:
     """Parallel tempering by label exchange. `order[k]` is the replica currently holding the k-th inverse
     temperature of `betas` (ascending ladder). Every rank owns an identical copy and updates it identically."""
@@ -134,8 +146,13 @@ def tempered_run(X, ladder, shard, rounds, iters_per_round, sampler, *, seed=1, 
     hist = []
     for rd in range(rounds):
         beta_local = shard.local(ladder.beta_of_replica())
+        if hasattr(X, "set_betas"):   # GraphQuant: fourK follows the β a replica currently holds (QT.jl:165)
+            X.set_betas(beta_local)
         Es, C = sampler(X, beta_local, iters_per_round, step=iters_per_round, seed=seed + 7919 * rd, C0=C, quiet=True, **kw)
-        E_local = np.asarray(Es[-1], np.float64).reshape(-1)
+        # the swap weighs the configurations as they are now: the last sample of Es predates the last move (the hook
+        # instant of RRRMC.jl:104 is before the move), so take energy(X, C) of the returned configuration
+        import rrrmc_b200 as rb
+        E_local = np.atleast_1d(np.asarray(rb.energy(X, C), np.float64)).reshape(-1)
         if terms_fn is None:
             E_all = all_gather(E_local)
             ladder.swap(E_all, rd)
