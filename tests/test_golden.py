@@ -139,3 +139,42 @@ def test_engine_checkerboard_count_procedures_reproduce_golden(name):
     got = X._download()
     want = np.unpackbits(GOLD_CB[f"{name}/final"].view(np.uint8).reshape(X.N, R // 8), axis=1, bitorder="little").T
     assert np.array_equal(got.s, want.astype(bool))
+
+
+# ---- extremal_opt (tests/golden/eo_v1.npz, made by tests/golden/make_golden_eo.py) -----------------------------------
+GOLD_EO = np.load(os.path.join(HERE, "golden", "eo_v1.npz"))
+_spec_eo = importlib.util.spec_from_file_location("make_golden_eo", os.path.join(HERE, "golden", "make_golden_eo.py"))
+mge = importlib.util.module_from_spec(_spec_eo)
+_spec_eo.loader.exec_module(mge)
+
+
+def test_oracle_reproduces_eo_golden():
+    now = mge.compute({name: GOLD_EO[f"{name}/ftau"] for name in mge.CASES})
+    assert set(now) == set(GOLD_EO.files)
+    for k in GOLD_EO.files:
+        assert np.array_equal(np.asarray(now[k]), GOLD_EO[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(mge.CASES))
+def test_engine_reproduces_eo_golden(name):
+    import rrrmc_b200 as rb
+    from tests.helpers import ea_instance, random_config
+    R = 3  # the golden chain is Philox chain 2 = replica 2 of the batch
+    if name == "EA(4,3)":
+        A, J = ea_instance(4, 3, (-1, 1), 21); X = rb.GraphEA(4, 3, replicas=R, A=A, J=J)
+    elif name == "EA(2,3)":
+        A, J = ea_instance(2, 3, (-1, 1), 22); X = rb.GraphEA(2, 3, replicas=R, A=A, J=J)
+    elif name == "EA(5,2,(-1,0,1))":
+        A, J = ea_instance(5, 2, (-1, 0, 1), 23); X = rb.GraphEA(5, 2, (-1, 0, 1), replicas=R, A=A, J=J)
+    elif name == "EA(4,2,(-2,-1,1,2))":
+        A, J = ea_instance(4, 2, (-2, -1, 1, 2), 24); X = rb.GraphEA(4, 2, (-2, -1, 1, 2), replicas=R, A=A, J=J)
+    else:
+        X = rb.GraphQT(12, 4, 0.73, replicas=R)
+    s0 = random_config(X.N, seed=12)
+    C0 = rb.Config(X.N, R, chunks=np.tile(s0, (R, 1)))
+    Cf, Emin, Cmin, itmin, Es = rb.extremal_opt(X, mge.TAU, mge.ITERS, step=mge.STEP, seed=mge.SEED, C0=C0, quiet=True,
+                                                ftau=GOLD_EO[f"{name}/ftau"], return_Es=True)
+    assert np.array_equal(np.asarray(Es, np.float64)[:, 2], GOLD_EO[f"{name}/Es"])
+    assert np.array_equal(Cf.chunks[2], GOLD_EO[f"{name}/final"]) and np.array_equal(Cmin.chunks[2], GOLD_EO[f"{name}/Cmin"])
+    assert float(np.atleast_1d(Emin)[2]) == GOLD_EO[f"{name}/Emin_itmin"][0] and int(np.atleast_1d(itmin)[2]) == GOLD_EO[f"{name}/Emin_itmin"][1]
