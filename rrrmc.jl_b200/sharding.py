@@ -138,7 +138,7 @@ class ReplicaShard:
         return np.asarray(x_global)[self.lo:self.hi]
 
 
-def tempered_run(X, ladder, shard, rounds, iters_per_round, sampler, *, seed=1, C0=None, terms_fn=None, **kw):
+def tempered_run(X, ladder, shard, rounds, iters_per_round, sampler, *, seed=1, C0=None, terms_fn=None, energy_fn=None, **kw):
     """Runs `sampler(X, β_local, iters_per_round, ...)` on this rank's batch for `rounds` rounds with a label swap
     after each: energies are all-gathered, every rank applies the same swaps, the local β vector is refreshed.
     -> (E_history (rounds, R_total), final Config of the local batch)."""
@@ -151,8 +151,10 @@ def tempered_run(X, ladder, shard, rounds, iters_per_round, sampler, *, seed=1, 
         Es, C = sampler(X, beta_local, iters_per_round, step=iters_per_round, seed=seed + 7919 * rd, C0=C, quiet=True, **kw)
         # the swap weighs the configurations as they are now: the last sample of Es predates the last move (the hook
         # instant of RRRMC.jl:104 is before the move), so take energy(X, C) of the returned configuration
-        import rrrmc_b200 as rb
-        E_local = np.atleast_1d(np.asarray(rb.energy(X, C), np.float64)).reshape(-1)
+        if energy_fn is None:
+            import rrrmc_b200 as rb
+            energy_fn = rb.energy
+        E_local = np.atleast_1d(np.asarray(energy_fn(X, C), np.float64)).reshape(-1)
         if terms_fn is None:
             E_all = all_gather(E_local)
             ladder.swap(E_all, rd)

@@ -94,3 +94,63 @@ def test_world_size_2_gloo_gather_and_identical_swaps():
     assert np.array_equal(b0, b1)                                          # every rank took the same swap decisions
     assert np.array_equal(np.concatenate([bl0, bl1]), b0)
     assert not np.array_equal(b0, np.linspace(0.5, 2.0, 384))
+
+
+class _ToyEngine:
+    """Stand-in for a GraphQuant batch in the tempered driver: the 'configuration' is one number per replica that
+    relaxes towards −β (so colder labels end lower), observable terms are simple functions of it."""
+
+    def __init__(self, n):
+        self.replicas, self.M, self.betas_seen = n, 4, []
+
+    def set_betas(self, b):
+        self.betas_seen.append(np.array(b, np.float64))
+
+
+def _toy_sampler(X, b, iters, *, step, seed, C0, quiet):
+    x = np.zeros(X.replicas) if C0 is None else C0
+    rng = np.random.default_rng(seed)           # same seed on every rank: the shards differ through b
+    x = 0.5 * x - 0.5 * np.asarray(b) * 10 + rng.normal(size=X.replicas) * 0.01
+    return x[None, :], x
+
+
+def _pt_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        total = 256
+        shard = sh.ReplicaShard(total)
+        X = _ToyEngine(shard.count)
+        ladder = sh.TemperingLadder(np.geomspace(0.5, 4.0, total), seed=11, action=sh.quantum_action(X.M, 0.3))
+        hist, C = sh.tempered_run(X, ladder, shard, 5, 100, _toy_sampler, seed=3, energy_fn=lambda X_, c: c,
+                                  terms_fn=lambda X_, c: (np.rint(c), 2.0 * c))
+        q.put((rank, hist, ladder.order.copy(), ladder.accepts.copy(), [b.copy() for b in X.betas_seen], shard.lo, shard.hi))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_tempered_run_quantum_ladder():
+    """The tempered driver over two ranks: identical swap decisions everywhere, each rank's engine is told the β its
+    replicas hold before every round (GraphQuant's fourK follows the label), histories are the all-gathered energies."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    ps = [ctx.Process(target=_pt_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in ps], key=lambda t: t[0])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, h0, o0, a0, seen0, lo0, hi0), (_, h1, o1, a1, seen1, lo1, hi1) = res
+    assert np.array_equal(h0, h1) and h0.shape == (5, 256)
+    assert np.array_equal(o0, o1) and np.array_equal(a0, a1) and a0.sum() > 0
+    assert (lo0, hi0, lo1, hi1) == (0, 128, 128, 256)
+    assert len(seen0) == 5 and len(seen1) == 5
+    assert np.array_equal(np.concatenate([seen0[0], seen1[0]]), np.geomspace(0.5, 4.0, 256))   # round 0: the initial ladder
+    moved = [not np.array_equal(np.concatenate([a, b]), np.geomspace(0.5, 4.0, 256)) for a, b in zip(seen0[1:], seen1[1:])]
+    assert any(moved)
+    for a, b in zip(seen0, seen1):      # every round the two shards together hold each rung exactly once
+        assert np.array_equal(np.sort(np.concatenate([a, b])), np.geomspace(0.5, 4.0, 256))
