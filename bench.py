@@ -280,6 +280,8 @@ def run_ours(args, rank, world, local_rank):
                 traffic = None
         cores = os.cpu_count() or 1
         cpu_iters = 100_000_000  # ~10 s on the box's host cores
+        if args.no_cpu_baseline:
+            cpu_iters = 1_000_000
         cpu_v, cpu_dt = cpu_reference_rate(A, J, cpu_iters, cores)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -321,7 +323,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--beta", type=float, default=BETA, help="inverse temperature (BASELINE configs[1] sweeps 0.5-2.0; headline: 1.0)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (β-sweep runs)")
     args = ap.parse_args()
+    globals()["BETA"] = args.beta
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
