@@ -173,10 +173,50 @@ class AbstractGraph:
             pass
 
 
+MAXDIGITS = 5  # src/DFloats.jl:12: a DFloat64 is the integer round(x·10^5)
+
+
+def dfloat_levels(LEV):
+    """Levels with a fractional part are DFloat64 in the reference (GraphEA(L, D, LEV::Tuple{Float64,…}), EA.jl:191;
+    src/DFloats.jl): fixed-point integers with five decimal digits, all arithmetic exact. Returns (integer levels,
+    g) with levels = round(LEV·10^5) / g, g the gcd of the fixed-point values — so the model is an integer-level graph whose
+    energies are counted in units of u = g / 10^5."""
+    import math
+    ints = []
+    for l in LEV:
+        v = round(float(l) * 10 ** MAXDIGITS)
+        if abs(float(l) * 10 ** MAXDIGITS - v) > 1e-6:
+            raise ValueError(f"up to {MAXDIGITS} decimal digits supported in levels, given: {LEV}")  # EA.jl:133
+        ints.append(int(v))
+    g = 0
+    for v in ints:
+        g = math.gcd(g, abs(v))
+    if g == 0:
+        raise ValueError(f"all levels are zero: {LEV}")
+    lev = tuple(v // g for v in ints)
+    if max(abs(v) for v in lev) > 127:
+        raise NotImplementedError(f"levels {LEV} need integer couplings beyond int8 after reduction ({lev})")
+    return lev, g
+
+
+def _out(X, a):
+    """Engine energies -> the graph's energy type: Int for integer levels, Float64(DFloat64) = units·u for DFloat64
+    levels (the division by 10^5 of DFloats.jl:28 folded into u), Float64 as is."""
+    g = getattr(X, "dfloat_g", None)
+    if g is not None:
+        return np.rint(a) * g / 10 ** MAXDIGITS   # Float64(x::DFloat64) = d2i(x) / dfact, one rounding (DFloats.jl:28)
+    return np.rint(a).astype(np.int64) if X.ET is int else a
+
+
+def _beta_in(X, beta):
+    """β as the engine sees it: integer-unit graphs of DFloat64 levels run at β·u (β·ΔE = (β·u)·ΔE_units; the reference
+    evaluates β·(ΔE_units·u), equal up to the last ulp of the exponent — the chain law is the same)."""
+    g = getattr(X, "dfloat_g", None)
+    return beta if g is None else np.asarray(beta, np.float64) * (g / 10 ** MAXDIGITS)
+
+
 def _scalarize(X, a):
-    a = np.asarray(a)
-    if X.ET is int:
-        a = np.rint(a).astype(np.int64)
+    a = _out(X, np.asarray(a))
     return a[0] if X.replicas == 1 else a
 
 
@@ -203,7 +243,7 @@ def all_delta_energy(X, Cfg, replica=0):
     X._upload(Cfg)
     dE = np.zeros(X.N, np.float64)
     check(lib().rrrmc_all_delta_energy(X._state, replica, ptr(dE)))
-    return np.rint(dE).astype(np.int64) if X.ET is int else dE
+    return _out(X, dE)
 
 
 def neighbors(X, i):
@@ -220,6 +260,7 @@ def allDeltaE(X):
     out = np.zeros(64, np.float64); n = C.c_int()
     check(lib().rrrmc_allDE(X._h, ptr(out), C.byref(n)))
     vals = out[:n.value]
+    vals = _out(X, vals)
     return tuple(int(v) for v in vals) if X.ET is int else tuple(float(v) for v in vals)
 
 
@@ -246,10 +287,15 @@ class GraphEA(AbstractGraph):
     ET = int
 
     def __init__(self, L, D, LEV=(-1, 1), replicas=1, A=None, J=None, rng=None, ctx=None):
-        if not all(float(l).is_integer() for l in LEV):
-            raise NotImplementedError("non-integer levels (DFloat64 path, EA.jl:193) are not on this engine's path yet")
         if len(set(LEV)) != len(LEV):
             raise ValueError(f"repeated levels in LEV: {LEV}")  # EA.jl:122
+        if not all(float(l).is_integer() for l in LEV):
+            # DFloat64 levels (EA.jl:191, src/DFloats.jl): an integer-level graph in units of u; J is given/drawn in real units
+            ilev, self.dfloat_g = dfloat_levels(LEV)
+            self.ET, self.LEV_real = float, tuple(float(l) for l in LEV)
+            if J is not None:
+                J = np.rint(np.asarray(J, np.float64) * 10 ** MAXDIGITS / self.dfloat_g)
+            LEV = ilev
         self.L, self.D, self.LEV, self.replicas = L, D, tuple(int(l) for l in LEV), int(replicas)
         self.ctx = ctx or Context.default()
         self.A = gen_EA(L, D) if A is None else np.ascontiguousarray(A, np.int64)
@@ -678,7 +724,7 @@ def _run(fn, X, beta, iters, seed, step, hook, C0, quiet, opts, name):
     else:
         X._upload(C0)
     R = X.replicas
-    betas = np.ascontiguousarray(np.broadcast_to(np.asarray(beta, np.float64), (R,)))
+    betas = np.ascontiguousarray(np.broadcast_to(np.asarray(_beta_in(X, beta), np.float64), (R,)))
     cap = min(10 ** 8, iters // step)  # RRRMC.jl:90
     Es = np.zeros((max(cap, 1), R), np.float64)
     info = _ffi.RunInfo()
@@ -700,9 +746,7 @@ def _run(fn, X, beta, iters, seed, step, hook, C0, quiet, opts, name):
     if "exc" in last:
         raise last["exc"]
     Cout = X._download()
-    Es = Es[:info.nsamples]
-    if X.ET is int:
-        Es = np.rint(Es).astype(np.int64)
+    Es = _out(X, Es[:info.nsamples])
     if not quiet:
         print("samples =", info.nsamples)
         print("iters =", info.iters_done)
@@ -774,7 +818,7 @@ def wtmMC(X, β, samples, *, seed=DEFAULT_SEED, step=1.0, hook=None, C0=None, qu
     else:
         X._upload(C0)
     R = X.replicas
-    betas = np.ascontiguousarray(np.broadcast_to(np.asarray(β, np.float64), (R,)))
+    betas = np.ascontiguousarray(np.broadcast_to(np.asarray(_beta_in(X, β), np.float64), (R,)))
     cap = min(10 ** 8, int(samples))
     Es = np.zeros((max(cap, 1), R), np.float64)
     info = _ffi.RunInfo()
@@ -795,9 +839,7 @@ def wtmMC(X, β, samples, *, seed=DEFAULT_SEED, step=1.0, hook=None, C0=None, qu
     if "exc" in last:
         raise last["exc"]
     Cout = X._download()
-    Es = Es[:info.nsamples]
-    if X.ET is int:
-        Es = np.rint(Es).astype(np.int64)
+    Es = _out(X, Es[:info.nsamples])
     if not quiet:
         print("samples =", info.nsamples)
         print("num_moves =", info.iters_done)
@@ -880,9 +922,7 @@ def extremal_opt(X, τ, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None,
         print(f"min [it = {itmin if R > 1 else int(itmin[0])}] = {_scalarize(X, Emin)}")
     out = (Cout, _scalarize(X, Emin), Cmin, itmin if R > 1 else int(itmin[0]))
     if return_Es:
-        Es = Es[:info.nsamples]
-        if X.ET is int:
-            Es = np.rint(Es).astype(np.int64)
+        Es = _out(X, Es[:info.nsamples])
         out = out + ((Es[:, 0] if R == 1 else Es),)
     return out
 
@@ -896,8 +936,8 @@ def replay(X, C0, sampler, β, iters, kind, ival, fval, *, step=1, replica=0, st
     info = _ffi.RunInfo()
     o = _opts(staged_thr=staged_thr, staged_thr_fact=staged_thr_fact)
     code = {"standardMC": 0, "rrrMC": 1, "bklMC": 2}[sampler]
-    check(lib().rrrmc_replay(X._state, replica, code, float(β), int(iters), int(step), ptr(kind), ptr(ival), ptr(fval),
+    check(lib().rrrmc_replay(X._state, replica, code, float(_beta_in(X, β)), int(iters), int(step), ptr(kind), ptr(ival), ptr(fval),
                              len(kind), C.byref(o), ptr(Es), cap, C.byref(info)))
     Es = Es[:info.nsamples]
     X.last_run = info
-    return (np.rint(Es).astype(np.int64) if X.ET is int else Es), X._download()
+    return _out(X, Es), X._download()

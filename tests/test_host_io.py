@@ -68,3 +68,15 @@ def test_eo_ftau_pairwise_cumsum(N):
         assert np.array_equal(f, want)
     import math
     assert abs(f[-1] - math.fsum(v)) <= 4 * np.spacing(f[-1])
+
+
+def test_dfloat_levels_reduce_to_integer_units():
+    """DFloat64 levels (src/DFloats.jl: round(x·10^5) as Int64) -> small integer levels and the gcd unit."""
+    assert rb.interface.dfloat_levels((-1.5, 0.5, 1.5)) == ((-3, 1, 3), 50000)
+    assert rb.interface.dfloat_levels((-1.0, 0.25)) == ((-4, 1), 25000)
+    assert rb.interface.dfloat_levels((0.1, -0.3, 0.7)) == ((1, -3, 7), 10000)
+    assert rb.interface.dfloat_levels((0.00001, 0.00127)) == ((1, 127), 1)
+    with pytest.raises(ValueError):
+        rb.interface.dfloat_levels((0.123456, 1.0))          # more than 5 decimal digits (EA.jl:133)
+    with pytest.raises(NotImplementedError):
+        rb.interface.dfloat_levels((0.00001, 1.0))           # would need couplings beyond int8
