@@ -16,4 +16,4 @@ RRG_R=4096 timeout 250 python scripts/bench_configs.py eo --quick >> gpurun_out/
 timeout 300 python scripts/bench_c5_pt.py > gpurun_out/${tag}_c5_pt_n1.json 2> gpurun_out/${tag}_c5_pt.err
 tail -4 gpurun_out/${tag}_pytest.txt; cat gpurun_out/${tag}_smoke.txt | tail -2
 cut -c1-260 gpurun_out/${tag}_bench.json; cut -c1-200 gpurun_out/${tag}_beta_sweep.jsonl
-cat gpurun_out/${tag}_configs_eo.jsonl gpurun_out/${tag}_c5_pt_n1.json; tail -3 gpurun_out/${tag}_eo.err gpurun_out/${tag}_c5_pt.err gpurun_out/${tag}_bench.err
+cat gpurun_out/${tag}_configs_eo.jsonl gpurun_out/${tag}_c5_pt_n1.json; for f in eo c5_pt bench; do tail -n 3 gpurun_out/${tag}_$f.err; done; true
