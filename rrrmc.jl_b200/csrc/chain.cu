@@ -722,6 +722,10 @@ __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
             for (int64_t w = 0; w < P.nchunks; w++) cmin[w] = X.s[w];
             h.built = 1;
         }
+        // copy!(Cmin, C) (RRRMC.jl:508-512) is deferred while the chain keeps improving: during a descent every move
+        // lowers Emin and only the last configuration of the streak survives, so Cmin is written when the chain is
+        // about to leave its minimum (or the kernel returns), not at every improvement
+        bool at_min = false;
         for (;;) {
             if (!h.pending) {
                 if (h.it >= iters) { h.done = 1; break; }
@@ -739,6 +743,7 @@ __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
             const double dE = k <= L ? -dc.DE[L - k] : dc.DE[k - L + hz - 1];
             const int move = dc.av[(int64_t)(k - 1) * N + src.range(dc.t[k]) - 1];
             if (src.err) { h.done = 1; break; }
+            if (at_min && !(h.E + dE < h.Emin)) { for (int64_t w = 0; w < P.nchunks; w++) cmin[w] = X.s[w]; at_min = false; }
             gv_spinflip(X, move);                                       // apply_move!, DeltaE.jl:519-543
             auto reclass = [&](int j) {
                 const int k0 = dc.cls[j], k1 = findks(j);
@@ -749,11 +754,9 @@ __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
             reclass(move);
             h.E += dE;
             h.accepted++;
-            if (h.E < h.Emin) {
-                h.Emin = h.E; h.itmin = h.it;
-                for (int64_t w = 0; w < P.nchunks; w++) cmin[w] = X.s[w];
-            }
+            if (h.E < h.Emin) { h.Emin = h.E; h.itmin = h.it; at_min = true; }
         }
+        if (at_min) for (int64_t w = 0; w < P.nchunks; w++) cmin[w] = X.s[w];
     } else { // bklMC, RRRMC.jl:332-350
         for (;;) {
             if (!h.pending) {
