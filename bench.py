@@ -38,10 +38,17 @@ UNIT = "attempts/s"
 ALG_BYTES_PER_SWEEP = 2 * N_SITES * R_PER_GPU // 8 + 3 * N_SITES // 8
 
 
-def synthetic_instance():
-    """3 forward bonds/site iid uniform{-1,+1}; one instance shared by all replicas and ranks."""
-    import rrrmc_b200 as rb
+def synthetic_instance(reference_arm=False):
+    """3 forward bonds/site iid uniform{-1,+1}; one instance shared by all replicas and ranks.
+    The reference arm builds it with the oracle's gen_EA/gen_J so that it never maps the product library; both give
+    the same instance (same draw order, EA.jl:45-71; tests/test_oracle_basic.py checks the two generators agree)."""
     rng = np.random.default_rng(SEED)
+    if reference_arm:
+        from oracle import ffi
+        A = ffi.gen_EA(L, D)
+        nb = int((A > np.arange(1, len(A) + 1)[:, None]).sum())
+        return A, ffi.gen_J(A, rng.choice(np.array([-1.0, 1.0]), nb)).astype(np.int64)
+    import rrrmc_b200 as rb
     A = rb.gen_EA(L, D)
     J = rb.gen_J(lambda n: rng.choice(np.array([-1.0, 1.0]), n), A)
     return A, J.astype(np.int64)
@@ -131,8 +138,7 @@ def cpu_reference_rate(A, J, iters_per_thread, nthreads):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    import rrrmc_b200 as rb  # host-side lattice helpers only (no device needed)
-    A, J = synthetic_instance()
+    A, J = synthetic_instance(reference_arm=True)   # oracle helpers only: this arm must not load librrrmc_b200.so
     cores = os.cpu_count() or 1
     iters = 20_000_000  # per thread per step (~2 s): a bounded sample of the workload (a full step is 1.07e11 attempts per GPU)
     for _ in range(max(0, args.warmup)):
@@ -241,6 +247,7 @@ def run_ours(args, rank, world, local_rank):
     opts.planes_K = PLANES_K
     opts.planes_M = PLANES_M
     opts.count_accepted = 0
+    opts.schedule = _ffi.SCHED_CHECKERBOARD   # opt-in: the library default is the reference order
     opts.cb_method = {"poisson": _ffi.CB_POISSON, "sparse": _ffi.CB_SPARSE, "planes": _ffi.CB_PLANES}[METHOD]
     info = _ffi.RunInfo()
     iters = SWEEPS_PER_STEP * N_SITES

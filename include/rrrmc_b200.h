@@ -176,7 +176,7 @@ typedef int (*rrrmc_hook_fn)(void *user, int64_t it, const double *E, const int6
 #define RRRMC_CB_POISSON 3 /* Poisson hit counts per task and level + uniform positions with replacement      */
 
 typedef struct {
-    int    schedule;        /* RRRMC_SCHED_*; default checkerboard                                   */
+    int    schedule;        /* RRRMC_SCHED_*; default RANDOM_SITE (the reference contract)           */
     int    planes_K;        /* checkerboard: full random bit planes, one Philox call each (default 5)  */
     int    count_accepted;  /* 1: exact per-replica accepted counters; 0: hook gets accepted = -1      */
     double staged_thr;      /* rrrMC: NaN = reference default (RRRMC.jl:163-165)                       */

@@ -108,6 +108,8 @@ def lib():
         "orc_wtmMC": (Result, [vp, f64, i64, f64, p(np.uint64), Draws, HOOK, vp, vp, i64]),
         "orc_extremal_opt": (EOResult, [vp, p(np.float64), i64, i64, p(np.uint64), vp, Draws, EOHOOK, vp, vp, i64]),
         "orc_check_discrete_cache": (i32, [vp, p(np.uint64), f64, p(np.int64), i64]),
+        "orc_ds_probe": (i32, [i64, p(np.float64), i64, p(np.int64), p(np.float64), p(np.float64), p(np.float64), i64, p(np.float64), p(np.int64)]),
+        "orc_arrayset_probe": (i64, [i64, i64, p(np.int64), p(np.int64)]),
         "orc_checkerboard_sweeps": (None, [i32, i32, i64, p(np.uint32), p(np.int8), p(np.uint64), i32, i32,
                                            C.c_uint64, C.c_uint64, i64, vp]),
         "orc_checkerboard_sweeps_sparse": (None, [i32, i32, i64, p(np.uint32), p(np.int8), p(np.uint32),

@@ -1026,6 +1026,32 @@ static void ds_set(dynsmp *d, int64_t i, double x) /* DynamicSamplers.jl:159-176
     ds_add_path(d, i, dd);
 }
 
+/* Test probes (tests/test_oracle_pins.py): the two container types exposed on their own, so that their state can be
+ * compared with values derived by hand from the reference source. */
+/* DynamicSampler(v) -> apply sets (1-based index, value) -> ps[1..N2-1], z; getel for each query x in [0,1) */
+int orc_ds_probe(int64_t N, const double *v, int64_t nset, const int64_t *set_i, const double *set_x,
+                 double *ps_out, double *z_out, int64_t nq, const double *xq, int64_t *el_out)
+{
+    dynsmp *d = ds_new(N, v);
+    for (int64_t a = 0; a < nset; a++) ds_set(d, set_i[a], set_x[a]);
+    for (int64_t k = 1; k < d->N2; k++) ps_out[k - 1] = d->ps[k];
+    *z_out = d->z;
+    int err = 0;
+    for (int64_t q = 0; q < nq && !err; q++) el_out[q] = ds_getel(d, xq[q], &err);
+    ds_free(d);
+    return err;
+}
+/* ArraySet(N): op[a] > 0 push!(op[a]), op[a] < 0 delete!(-op[a]) -> v[1..t] in storage order, t */
+int64_t orc_arrayset_probe(int64_t N, int64_t nops, const int64_t *op, int64_t *v_out)
+{
+    arrayset a; as_init(&a, N);
+    for (int64_t k = 0; k < nops; k++) { if (op[k] > 0) as_push(&a, op[k]); else as_delete(&a, -op[k]); }
+    const int64_t t = as_check(&a) ? -1 : a.t;
+    for (int64_t k = 1; k <= a.t; k++) v_out[k - 1] = a.v[k];
+    as_free(&a);
+    return t;
+}
+
 /* ------------------------------------------------------------------------------------------
  * DeltaECacheCont — src/DeltaE.jl:297-410
  * ---------------------------------------------------------------------------------------- */

@@ -143,6 +143,10 @@ orc_eo_result orc_extremal_opt(orc_graph *g, const double *ftau, int64_t iters, 
 /* ΔE-class cache consistency (DeltaE.jl:120-136, ArraySets.jl:27-42); exposed for tests:
  * builds a cache for (g,chunks,beta), applies `nmoves` eager apply_move! calls on sites[], checks
  * consistency after each, and returns 0 when consistent. */
+/* test probes of the container types (DynamicSamplers.jl:18-176, ArraySets.jl:58-85) */
+int orc_ds_probe(int64_t N, const double *v, int64_t nset, const int64_t *set_i, const double *set_x,
+                 double *ps_out, double *z_out, int64_t nq, const double *xq, int64_t *el_out);
+int64_t orc_arrayset_probe(int64_t N, int64_t nops, const int64_t *op, int64_t *v_out);
 int orc_check_discrete_cache(orc_graph *g, uint64_t *chunks, double beta, const int64_t *sites, int64_t nmoves);
 
 /* ---- CPU model of the engine's checkerboard Metropolis (NOT in the reference).

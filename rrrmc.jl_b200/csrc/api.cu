@@ -10,6 +10,7 @@
 #include "kernels.cuh"
 #include "cb_params.cuh"
 #include "chain.cuh"
+#include "ea_tma.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -644,6 +645,7 @@ extern "C" rrrmc_status_t rrrmc_state_destroy(rrrmc_state_t *s)
     cudaFree(s->d_flips); cudaFree(s->d_mask); cudaFree(s->d_q_fourK);
     chain_free(s);
     sk_dense_free(s);
+    checkerboard_tma_free(s);
     delete s;
     return RRRMC_OK;
 }
@@ -656,7 +658,8 @@ extern "C" rrrmc_status_t rrrmc_state_randomize(rrrmc_state_t *s, uint64_t seed)
 {
     RR_ARG(s, "state is NULL");
     RR_CUDA(cudaSetDevice(s->g->ctx->device));
-    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
+    // the fresh configuration is written in the multispin layout: that copy is current, the chain copy is stale
+    s->energy_valid = false; s->ms_valid = true; s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
     return launch_randomize(s, seed);
 }
 extern "C" rrrmc_status_t rrrmc_state_upload(rrrmc_state_t *s, int64_t first, int64_t count, const uint64_t *chunks)
@@ -837,7 +840,7 @@ extern "C" rrrmc_status_t rrrmc_opts_default(rrrmc_opts_t *o)
 {
     RR_ARG(o, "opts is NULL");
     memset(o, 0, sizeof *o);
-    o->schedule = RRRMC_SCHED_CHECKERBOARD;
+    o->schedule = RRRMC_SCHED_RANDOM_SITE;   // the reference order and sampling contract; lattice sweeps are opt-in
     o->planes_K = 5;
     o->planes_M = 4;
     o->cb_method = RRRMC_CB_AUTO;
@@ -1080,10 +1083,33 @@ static rrrmc_status_t fill_cbp_params(rrrmc_state *s, const uint32_t *tbl, int t
     p.bucket = ctx->d_cbp_bucket;
     return RRRMC_OK;
 }
-static rrrmc_status_t run_sweep_poisson(rrrmc_state *s, cbp_params &p, uint64_t t)
+// The poisson procedure has two kernels with identical results: the TMA-staged brick kernel (ea_tma.cu: 3D, whole
+// 1024-replica slabs, L a multiple of 8) and the cp.async kernels of ea_poisson.cu (everything else).
+// RRRMC_CB_VARIANT bit 11 (2048) forbids the TMA kernel (A/B timing, tests of the other path).
+struct cbp_run {
+    cbp_params p;
+    cbt_params *tma = nullptr;      // non-null: launch the TMA kernel
+    ~cbp_run() { delete tma; }
+};
+static rrrmc_status_t prepare_poisson_run(rrrmc_state *s, const uint32_t *tbl, int tbl_len, int NW, uint64_t seed, cbp_run &run)
+{
+    RR_TRY(fill_cbp_params(s, tbl, tbl_len, NW, seed, run.p));
+    if (checkerboard_tma_eligible(s) && !(run.p.variant & 2048)) {
+        run.tma = new cbt_params();
+        RR_TRY(checkerboard_tma_prepare(s, run.p, *run.tma));
+    }
+    return RRRMC_OK;
+}
+static rrrmc_status_t run_sweep_poisson(rrrmc_state *s, cbp_run &run, uint64_t t)
 {
     rrrmc_graph *g = s->g;
+    cbp_params &p = run.tma ? run.tma->p : run.p;
     p.t_lo = (uint32_t)t; p.t_hi16 = (uint32_t)(t >> 32) << 16;
+    if (run.tma) {
+        RR_TRY(launch_checkerboard_tma(g->ctx, *run.tma, 0));
+        RR_TRY(launch_checkerboard_tma(g->ctx, *run.tma, 1));
+        return RRRMC_OK;
+    }
     RR_TRY(launch_checkerboard_poisson(g->ctx, p, g->D, 0));
     RR_TRY(launch_checkerboard_poisson(g->ctx, p, g->D, 1));
     return RRRMC_OK;
@@ -1095,9 +1121,9 @@ extern "C" rrrmc_status_t rrrmc_checkerboard_sweeps_poisson(rrrmc_state_t *s, co
     RR_ARG(nsweeps >= 0, "nsweeps must be >= 0");
     RR_CUDA(cudaSetDevice(s->g->ctx->device));
     RR_TRY(chain_sync_to_multispin(s));
-    cbp_params p;
-    RR_TRY(fill_cbp_params(s, tbl, tbl_len, NW, seed, p));
-    for (int64_t k = 0; k < nsweeps; k++) RR_TRY(run_sweep_poisson(s, p, sweep0 + (uint64_t)k));
+    cbp_run run;
+    RR_TRY(prepare_poisson_run(s, tbl, tbl_len, NW, seed, run));
+    for (int64_t k = 0; k < nsweeps; k++) RR_TRY(run_sweep_poisson(s, run, sweep0 + (uint64_t)k));
     s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
     return RRRMC_OK;
 }
@@ -1140,7 +1166,7 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
     uint64_t thr[3];
     for (int c = 1; c <= g->D; c++) thr[c - 1] = fixed64(exp(-beta * 4.0 * c));
     RR_ARG(o->cb_method >= RRRMC_CB_AUTO && o->cb_method <= RRRMC_CB_POISSON, "unknown cb_method %d", o->cb_method);
-    cb_params p; cbs_params ps; cbp_params pp;
+    cb_params p; cbs_params ps; cbp_run pp;
     // AUTO: poisson while its static position slots cover the level-1 hit count (β >~ 0.5), else sparse / planes
     uint32_t ptbl[CBP_LEN];
     RR_TRY(rrrmc_checkerboard_poisson_tables(thr, g->D, ptbl, CBP_LEN));
@@ -1151,7 +1177,7 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
     }
     const bool poisson = o->cb_method == RRRMC_CB_POISSON || (o->cb_method == RRRMC_CB_AUTO && NW > 0);
     const bool sparse = !poisson && cb_use_sparse(o, exp(-beta * 4.0));
-    if (poisson) RR_TRY(fill_cbp_params(s, ptbl, CBP_LEN, NW, seed, pp));
+    if (poisson) RR_TRY(prepare_poisson_run(s, ptbl, CBP_LEN, NW, seed, pp));
     else if (sparse) {
         uint32_t tbl[CBS_T1 + 2 * CBS_TC];
         RR_TRY(rrrmc_checkerboard_sparse_tables(thr, g->D, tbl, CBS_T1 + 2 * CBS_TC));
@@ -1162,7 +1188,8 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
     const bool count = o->count_accepted != 0;
     if (count) {
         if (!s->d_flips) RR_CUDA(cudaMalloc(&s->d_flips, sizeof(uint32_t) * N * s->W));
-        p.flips = ps.flips = pp.flips = s->d_flips;
+        p.flips = ps.flips = pp.p.flips = s->d_flips;
+        if (pp.tma) pp.tma->p.flips = s->d_flips;
         RR_CUDA(cudaMemsetAsync(s->d_acc, 0, sizeof(long long) * s->W * 32, ctx->stream));
     }
     const uint64_t l0 = ctx->launches;
@@ -1170,8 +1197,9 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
     std::vector<long long> acc_h(s->W * 32);
     std::vector<int64_t> acc(s->R, -1);
     int64_t nsamples = 0, done = 0;
-    cudaEvent_t e0, e1;
-    RR_CUDA(cudaEventCreate(&e0)); RR_CUDA(cudaEventCreate(&e1));
+    event_pair ev;                     // destroyed on every return path (a hook that stops the run, an error)
+    RR_CUDA(ev.create());
+    cudaEvent_t e0 = ev.e0, e1 = ev.e1;
     RR_CUDA(cudaEventRecord(e0, ctx->stream));
     for (int64_t sw = 1; sw <= nsweeps; sw++) {
         if (poisson) RR_TRY(run_sweep_poisson(s, pp, (uint64_t)(sw - 1)));
@@ -1194,7 +1222,6 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
     RR_CUDA(cudaEventRecord(e1, ctx->stream));
     RR_CUDA(cudaEventSynchronize(e1));
     float ms = 0; RR_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
     if (info) { info->nsamples = std::min(nsamples, Es ? Es_cap : nsamples); info->iters_done = done * N; info->launches = (int64_t)(ctx->launches - l0); info->device_ms = ms; info->accepted_total = -1; }
     return RRRMC_OK;

@@ -83,6 +83,18 @@ struct rrrmc_state {
     std::vector<double> q_beta, q_fourK; double *d_q_fourK = nullptr;
     struct chain_store *chain = nullptr;
     struct sk_dense_store *skd = nullptr; // dense GraphSKNormal kernels (sk_dense.cu)
+    struct cb_tma_store *tma = nullptr;   // TMA-staged checkerboard kernel: tensor maps, brick-ordered bond masks (ea_tma.cu)
+};
+
+// a pair of timing events that cannot leak: created on demand, destroyed when the scope ends
+struct event_pair {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t create()
+    {
+        cudaError_t e = cudaEventCreate(&e0);
+        return e != cudaSuccess ? e : cudaEventCreate(&e1);
+    }
+    ~event_pair() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
 };
 
 static inline unsigned div_up(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }

@@ -1,0 +1,358 @@
+// Checkerboard Metropolis half-sweep for GraphEA ±J, "poisson" acceptance procedure, TMA-staged bricks.
+//
+// Same procedure, same Philox counters and therefore the same trajectories, bit for bit, as ea_poisson.cu (the CPU
+// restatement is oracle/rrrmc_oracle.c:orc_checkerboard_sweeps_poisson); what changes is how a task gets its seven
+// spin words. ea_poisson.cu has every thread form seven 64-bit addresses and issue seven cp.async per task — a third
+// of its instructions, on the ALU pipe that bounds the kernel. Here the lattice is a rank-5 tensor
+// [z][y][x][slab][32 words] (a slab = 1024 replicas = one 128-byte row per site) and a dedicated producer warp
+// brings a whole 8x4x4 brick plus its halo into shared memory with a handful of cp.async.bulk.tensor operations per
+// brick; 256 consumer threads then read their words with LDS.128 at addresses that are compile-time offsets from
+// one per-thread constant (y and z neighbours) or two per-thread constants (x neighbours), and write the updated
+// centre word straight to global memory. No per-task address arithmetic is left beside one IMAD.WIDE for the store.
+//
+// Shared-memory stage (43 008 B, two stages per block, two blocks per SM):
+//   planes   6 planes (z' = z+1 = 0..5) x 48 rows (x = 0..7, y' = y+1 = 0..5) x 128 B. Planes 1..4 are the brick with its
+//            y halo: one box (8 x, 6 y) per plane, or two/three boxes when the halo wraps around the lattice (the
+//            split is along the slowest box dimension, so the pieces land where the single box would have).
+//            Planes 0 and 5 are the z halo: one box (8 x, 4 y) each, at rows y' = 1..4.
+//   x faces  2 x 16 rows (y + 4 z): the sites at x0-1 and x0+8 (periodic), one box (1 x, 4 y, 4 z) each
+//   bonds    64 x 32 B: the six whole-word sign masks of the brick's 64 active sites, brick-ordered copy of jmask
+//            (one 1-D bulk copy)
+// A quarter warp (8 lanes) reads the 8 groups of ONE site = one 128-byte row, so every LDS.128 is conflict free
+// without swizzling. The producer/consumer handshake is the usual full/empty mbarrier pair per stage; consumers
+// generate the (spin-independent) hit masks of a brick's two tasks BEFORE waiting for its data.
+#include <cuda.h>
+#include "kernels.cuh"
+#include "ea_poisson_core.cuh"
+#include "ea_tma.cuh"
+
+namespace {
+
+constexpr int BX = CBT_BX, BY = CBT_BY, BZ = CBT_BZ;
+constexpr int ROWB = 128;                              // bytes of one site's slab row
+constexpr int PLANE_ROWS = BX * (BY + 2);              // 48
+constexpr int PLANE_BYTES = PLANE_ROWS * ROWB;         // 6144
+constexpr int XF_OFF = PLANE_BYTES * (BZ + 2);         // 36864
+constexpr int XF_BYTES = BY * BZ * ROWB;               // 2048 per face
+constexpr int JM_OFF = XF_OFF + 2 * XF_BYTES;          // 40960
+constexpr int NACT = CBT_NACT;                         // 64 active sites per brick
+constexpr int STAGE_BYTES = JM_OFF + NACT * 32;        // 43008
+constexpr int TX_BYTES = BZ * PLANE_BYTES + 2 * BX * BY * ROWB + 2 * XF_BYTES + NACT * 32; // bytes landing per brick
+constexpr int NSTAGE = 2;
+constexpr int NCONS = 256;                             // consumer threads (8 warps); warp 8 is the producer
+constexpr int SM_BUCKET = NSTAGE * STAGE_BYTES;
+constexpr int SM_BARS = SM_BUCKET + CBP_BUCKETS * 8;
+constexpr int SMEM_BYTES = SM_BARS + 64;
+static_assert(NACT == 2 * (NCONS / 8), "two tasks per consumer thread and brick");
+static_assert(STAGE_BYTES % 128 == 0 && XF_OFF % 128 == 0 && JM_OFF % 128 == 0, "TMA destinations are 128-byte aligned");
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n"
+                 "W_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@!p bra W_%=;\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load5(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3, int c4)
+{
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+template <int OFF> __device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int OFF> __device__ __forceinline__ uint2 lds64(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(addr), "n"(OFF));
+    return v;
+}
+
+// brick b' of this launch -> slab and lattice origin (exact float reciprocals for b' < 2^22, as in ea_poisson.cu)
+struct brick_pos { int slab, x0, y0, z0, b; };
+__device__ __forceinline__ brick_pos locate_brick(const cbt_params &P, int bb)
+{
+    brick_pos r;
+    r.slab = __float2int_rz(((float)bb + 0.5f) * P.inv_nbricks);
+    r.b = bb - r.slab * P.nbricks;
+    const int q = __float2int_rz(((float)r.b + 0.5f) * P.inv_nbx);
+    const int X = r.b - q * P.nbx;
+    const int Z = __float2int_rz(((float)q + 0.5f) * P.inv_nby), Y = q - Z * P.nby;
+    r.x0 = X * BX; r.y0 = Y * BY; r.z0 = Z * BZ;
+    return r;
+}
+
+template <int NW, int MINB>
+__global__ void __launch_bounds__(NCONS + 32, MINB) k_checkerboard_tma(const __grid_constant__ cbt_params P, int colour)
+{
+    constexpr int D = 3;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const cbp_params &p = P.p;
+    const int t = threadIdx.x, L = p.L;
+    const uint32_t sm0 = smem_u32(smem);
+    const uint32_t bars = sm0 + SM_BARS;                 // full[s] at bars + 8 s, empty[s] at bars + 16 + 8 s
+    uint2 *sbucket = reinterpret_cast<uint2 *>(smem + SM_BUCKET);
+    for (int k = t; k < CBP_BUCKETS; k += NCONS + 32) sbucket[k] = __ldg(p.bucket + k);
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; s++) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 16 + 8 * s, NCONS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int total = P.nbricks * P.nslab;
+
+    if (t >= NCONS) {
+        // ---------------- producer: one lane issues the bulk copies of every brick this block owns ----------------
+        if (t != NCONS) return;
+        asm volatile("griddepcontrol.wait;" ::: "memory");   // the previous half-sweep is complete and visible
+        int k = 0;
+        for (int bb = blockIdx.x; bb < total; bb += gridDim.x, k++) {
+            const int s = k & 1;
+            const uint32_t sb = sm0 + s * STAGE_BYTES, full = bars + 8 * s, empty = bars + 16 + 8 * s;
+            if (k >= NSTAGE) mbar_wait(empty, ((k >> 1) - 1) & 1);
+            const brick_pos r = locate_brick(P, bb);
+            mbar_expect_tx(full, TX_BYTES);
+            const bool wrap_lo = r.y0 == 0, wrap_hi = r.y0 + BY == L;
+#pragma unroll
+            for (int zz = 0; zz < BZ; zz++) {
+                const uint32_t dst = sb + (zz + 1) * PLANE_BYTES;
+                const int z = r.z0 + zz;
+                if (!wrap_lo && !wrap_hi) tma_load5(dst, &P.m_y6, full, 0, r.slab, r.x0, r.y0 - 1, z);
+                else {
+                    // rows y' = 0 | 1..4 | 5; a wrapped halo row is its own box, the rest stays one box
+                    if (wrap_lo) tma_load5(dst, &P.m_y1, full, 0, r.slab, r.x0, L - 1, z);
+                    if (wrap_hi) tma_load5(dst + 5 * BX * ROWB, &P.m_y1, full, 0, r.slab, r.x0, 0, z);
+                    if (wrap_lo && wrap_hi) tma_load5(dst + BX * ROWB, &P.m_y4, full, 0, r.slab, r.x0, r.y0, z);
+                    else if (wrap_lo) tma_load5(dst + BX * ROWB, &P.m_y5, full, 0, r.slab, r.x0, r.y0, z);
+                    else tma_load5(dst, &P.m_y5, full, 0, r.slab, r.x0, r.y0 - 1, z);
+                }
+            }
+            tma_load5(sb + BX * ROWB, &P.m_y4, full, 0, r.slab, r.x0, r.y0, r.z0 == 0 ? L - 1 : r.z0 - 1);
+            tma_load5(sb + (BZ + 1) * PLANE_BYTES + BX * ROWB, &P.m_y4, full, 0, r.slab, r.x0, r.y0, r.z0 + BZ == L ? 0 : r.z0 + BZ);
+            tma_load5(sb + XF_OFF, &P.m_xf, full, 0, r.slab, r.x0 == 0 ? L - 1 : r.x0 - 1, r.y0, r.z0);
+            tma_load5(sb + XF_OFF + XF_BYTES, &P.m_xf, full, 0, r.slab, r.x0 + BX == L ? 0 : r.x0 + BX, r.y0, r.z0);
+            bulk_load(sb + JM_OFF, P.jbrick + ((size_t)colour * P.nbricks + r.b) * (NACT * 2), NACT * 32, full);
+        }
+        return;
+    }
+
+    // ---------------- consumers: thread = (active-site slot s and s + 32, group g8) ----------------
+    const int g8 = t & 7, sl = t >> 3;
+    const int xh = sl & 3, y = (sl >> 2) & 3, z = sl >> 4;               // z in {0, 1}; the second task sits at z + 2
+    const int x = 2 * xh + ((y + z + colour) & 1);                        // brick origins are even in y and z
+    const uint32_t offc = (uint32_t)(x + BX * ((y + 1) + (BY + 2) * (z + 1))) * ROWB + g8 * 16;
+    const uint32_t offxf = XF_OFF + (uint32_t)(y + BY * z) * ROWB + g8 * 16;
+    constexpr int DZ2 = 2 * PLANE_BYTES, DXF2 = 2 * BY * ROWB;            // the same offsets for the second task
+    const uint32_t xm0 = x > 0 ? offc - ROWB : offxf, xm1 = x > 0 ? offc - ROWB + DZ2 : offxf + DXF2;
+    const uint32_t xp0 = x < BX - 1 ? offc + ROWB : offxf + XF_BYTES, xp1 = x < BX - 1 ? offc + ROWB + DZ2 : offxf + XF_BYTES + DXF2;
+    const uint32_t jmo = JM_OFF + (uint32_t)sl * 32;
+    const uint32_t soff = (uint32_t)x + (uint32_t)L * ((uint32_t)y + (uint32_t)L * (uint32_t)z), LL2 = 2u * (uint32_t)L * (uint32_t)L;
+    const uint32_t W4 = (uint32_t)p.W >> 2;
+    uint4 *const spins4 = reinterpret_cast<uint4 *>(p.spins);
+    uint4 *const flips4 = reinterpret_cast<uint4 *>(p.flips);
+
+    int k = 0;
+    for (int bb = blockIdx.x; bb < total; bb += gridDim.x, k++) {
+        const int s = k & 1;
+        const uint32_t sb = sm0 + s * STAGE_BYTES, full = bars + 8 * s, empty = bars + 16 + 8 * s;
+        const brick_pos r = locate_brick(P, bb);
+        const uint32_t i0 = (uint32_t)r.x0 + (uint32_t)L * ((uint32_t)r.y0 + (uint32_t)L * (uint32_t)r.z0) + soff, i1 = i0 + LL2;
+        const uint32_t grp = (uint32_t)(r.slab * 8 + g8);
+        uint32_t m[2][4], gg[2][4], h[2][4];
+        bool slow[2];
+        // both Philox chains in one basic block: their rounds interleave
+        const cbp_words<NW> rw0 = cbp_draw<NW>(p, i0, grp), rw1 = cbp_draw<NW>(p, i1, grp);
+        slow[0] = cbp_task_hits<D, NW>(p, sbucket, i0, grp, rw0, m[0], gg[0], h[0]);
+        slow[1] = cbp_task_hits<D, NW>(p, sbucket, i1, grp, rw1, m[1], gg[1], h[1]);
+        if (k == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+        mbar_wait(full, (k >> 1) & 1);
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            // a0 = the z-1 neighbour's word (the lowest address this task reads in the planes): offsets are >= 0
+            const uint32_t a0 = sb + offc - PLANE_BYTES, axm = sb + (j ? xm1 : xm0), axp = sb + (j ? xp1 : xp0), aj = sb + jmo;
+            uint4 c, v[6], ja; uint2 jb;
+            if (j == 0) {
+                c = lds128<PLANE_BYTES>(a0);
+                v[0] = lds128<0>(axp); v[1] = lds128<0>(axm);
+                v[2] = lds128<PLANE_BYTES + BX * ROWB>(a0); v[3] = lds128<PLANE_BYTES - BX * ROWB>(a0);
+                v[4] = lds128<2 * PLANE_BYTES>(a0); v[5] = lds128<0>(a0);
+                ja = lds128<0>(aj); jb = lds64<16>(aj);
+            } else {
+                c = lds128<DZ2 + PLANE_BYTES>(a0);
+                v[0] = lds128<0>(axp); v[1] = lds128<0>(axm);
+                v[2] = lds128<DZ2 + PLANE_BYTES + BX * ROWB>(a0); v[3] = lds128<DZ2 + PLANE_BYTES - BX * ROWB>(a0);
+                v[4] = lds128<DZ2 + 2 * PLANE_BYTES>(a0); v[5] = lds128<DZ2>(a0);
+                ja = lds128<32 * 32>(aj); jb = lds64<32 * 32 + 16>(aj);
+                mbar_arrive(empty);                      // this thread has read everything it needs from the stage
+            }
+            const uint32_t neg[6] = { ja.x, ja.y, ja.z, ja.w, jb.x, jb.y };
+            uint32_t sc[4] = { c.x, c.y, c.z, c.w }, bp[4][2 * D], fl[4];
+#pragma unroll
+            for (int q = 0; q < 2 * D; q++) {
+                bp[0][q] = lop3p<P_XOR3>(sc[0], v[q].x, neg[q]); bp[1][q] = lop3p<P_XOR3>(sc[1], v[q].y, neg[q]);
+                bp[2][q] = lop3p<P_XOR3>(sc[2], v[q].z, neg[q]); bp[3][q] = lop3p<P_XOR3>(sc[3], v[q].w, neg[q]);
+            }
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                if (slow[j]) bp[w][0] |= h[j][w];        // a level-3 hit flips every lane (m = g = 1 there, so u >= 1 suffices)
+                fl[w] = cbp_flip_planes<D>(bp[w], m[j][w], gg[j][w]);
+                sc[w] ^= fl[w];
+            }
+            const uint32_t idx = (j ? i1 : i0) * W4 + grp;
+            spins4[idx] = make_uint4(sc[0], sc[1], sc[2], sc[3]);
+            if (flips4) flips4[idx] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+        }
+    }
+}
+
+// brick-ordered copy of the bond masks: jbrick[colour][brick][slot][8], slot = xh + 4 (y + 4 z)
+__global__ void k_build_jbrick(const uint4 *__restrict__ jmask, uint4 *__restrict__ jbrick, int L, int nbx, int nby, int nbricks)
+{
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;       // (colour, brick, slot)
+    if (id >= 2 * nbricks * NACT) return;
+    const int a = id % NACT, b = (id / NACT) % nbricks, colour = id / (NACT * nbricks);
+    const int X = b % nbx, Y = (b / nbx) % nby, Z = b / (nbx * nby);
+    const int xh = a & 3, y = (a >> 2) & 3, z = a >> 4;
+    const int x = 2 * xh + ((y + z + colour) & 1);
+    const size_t i = (size_t)(X * BX + x) + (size_t)L * ((size_t)(Y * BY + y) + (size_t)L * (size_t)(Z * BZ + z));
+    jbrick[2 * (size_t)id] = jmask[2 * i];
+    jbrick[2 * (size_t)id + 1] = jmask[2 * i + 1];
+}
+
+typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                              const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+rrrmc_status_t encode_map(encode_fn enc, CUtensorMap *m, void *base, int L, int W, int bx, int by, int bz)
+{
+    const cuuint64_t dims[5] = { 32, (cuuint64_t)(W / 32), (cuuint64_t)L, (cuuint64_t)L, (cuuint64_t)L };
+    const cuuint64_t strides[4] = { 128, (cuuint64_t)W * 4, (cuuint64_t)W * 4 * L, (cuuint64_t)W * 4 * L * L };
+    const cuuint32_t box[5] = { 32, 1, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz };
+    const cuuint32_t es[5] = { 1, 1, 1, 1, 1 };
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { rrrmc_set_error("cuTensorMapEncodeTiled failed (%d) for box %dx%dx%d", (int)r, bx, by, bz); return RRRMC_ERR_CUDA; }
+    return RRRMC_OK;
+}
+
+template <int NW, int MINB>
+cudaError_t launch_one(const cbt_params &P, int colour, int sm_count, cudaStream_t st)
+{
+    static int configured = 0;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_checkerboard_tma<NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_checkerboard_tma<NW, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_checkerboard_tma<NW, MINB>, NCONS + 32, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = occ < 1 ? 1 : occ;
+    }
+    const int total = P.nbricks * P.nslab;
+    int grid = sm_count * configured;
+    if (P.p.variant & 128) grid = 2;     // tests: many bricks per block
+    if (grid > total) grid = total;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NCONS + 32); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (P.p.variant & 32) ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, k_checkerboard_tma<NW, MINB>, P, colour);
+}
+template <int MINB>
+cudaError_t launch_nw(const cbt_params &P, int colour, int sm_count, cudaStream_t st)
+{
+    switch (P.p.NW) {
+    case 1: return launch_one<1, MINB>(P, colour, sm_count, st);
+    case 2: return launch_one<2, MINB>(P, colour, sm_count, st);
+    case 4: return launch_one<4, MINB>(P, colour, sm_count, st);
+    default: return launch_one<6, MINB>(P, colour, sm_count, st);
+    }
+}
+
+} // namespace
+
+bool checkerboard_tma_eligible(const rrrmc_state *s)
+{
+    const rrrmc_graph *g = s->g;
+    if (!(g->kind == RRRMC_EA_PM1 && g->D == 3 && g->d_jmask && g->bipartite)) return false;
+    if (s->W % 32 != 0 || g->L % BX != 0 || g->L % BY != 0 || g->L % BZ != 0) return false;
+    const int64_t nbricks = (int64_t)(g->L / BX) * (g->L / BY) * (g->L / BZ);
+    return nbricks * (s->W / 32) < ((int64_t)1 << 22) && g->N * s->W < ((int64_t)1 << 31);
+}
+
+void checkerboard_tma_free(rrrmc_state *s)
+{
+    if (s->tma) { cudaFree(s->tma->d_jbrick); delete s->tma; s->tma = nullptr; }
+}
+
+// Fills the TMA half of the launch parameters: tensor maps over the state's spin array (encoded once per state) and
+// the brick-ordered bond masks (built once per state from the graph's jmask).
+rrrmc_status_t checkerboard_tma_prepare(rrrmc_state *s, const cbp_params &p, cbt_params &P)
+{
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    const int L = g->L, W = (int)s->W;
+    if (!s->tma) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        RR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+        if (!fn || qr != cudaDriverEntryPointSuccess) { rrrmc_set_error("cuTensorMapEncodeTiled is not available in this driver"); return RRRMC_ERR_CUDA; }
+        cb_tma_store *c = new cb_tma_store();
+        encode_fn enc = reinterpret_cast<encode_fn>(fn);
+        rrrmc_status_t st = RRRMC_OK;
+        if ((st = encode_map(enc, &c->m_y6, s->d_spins, L, W, BX, BY + 2, 1)) != RRRMC_OK ||
+            (st = encode_map(enc, &c->m_y5, s->d_spins, L, W, BX, BY + 1, 1)) != RRRMC_OK ||
+            (st = encode_map(enc, &c->m_y4, s->d_spins, L, W, BX, BY, 1)) != RRRMC_OK ||
+            (st = encode_map(enc, &c->m_y1, s->d_spins, L, W, BX, 1, 1)) != RRRMC_OK ||
+            (st = encode_map(enc, &c->m_xf, s->d_spins, L, W, 1, BY, BZ)) != RRRMC_OK) { delete c; return st; }
+        c->nbx = L / BX; c->nby = L / BY; c->nbricks = c->nbx * c->nby * (L / BZ);
+        const size_t n = (size_t)2 * c->nbricks * NACT;
+        if (cudaMalloc(&c->d_jbrick, n * 32) != cudaSuccess) { delete c; rrrmc_set_error("cudaMalloc of the brick-ordered bond masks failed"); return RRRMC_ERR_CUDA; }
+        k_build_jbrick<<<div_up((int64_t)n, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4 *>(g->d_jmask), c->d_jbrick, L, c->nbx, c->nby, c->nbricks);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) { cudaFree(c->d_jbrick); delete c; rrrmc_set_error("k_build_jbrick launch failed"); return RRRMC_ERR_CUDA; }
+        s->tma = c;
+    }
+    const cb_tma_store *c = s->tma;
+    P.p = p;
+    P.m_y6 = c->m_y6; P.m_y5 = c->m_y5; P.m_y4 = c->m_y4; P.m_y1 = c->m_y1; P.m_xf = c->m_xf;
+    P.jbrick = c->d_jbrick;
+    P.nbx = c->nbx; P.nby = c->nby; P.nbricks = c->nbricks; P.nslab = W / 32;
+    P.inv_nbx = 1.0f / (float)c->nbx; P.inv_nby = 1.0f / (float)c->nby; P.inv_nbricks = 1.0f / (float)c->nbricks;
+    return RRRMC_OK;
+}
+
+rrrmc_status_t launch_checkerboard_tma(rrrmc_ctx *ctx, cbt_params &P, int colour)
+{
+    const int mb = P.p.variant & 3;      // RRRMC_CB_VARIANT (tuning): resident blocks per SM
+    cudaError_t e = mb == 1 ? launch_nw<1>(P, colour, ctx->sm_count, ctx->stream) : launch_nw<2>(P, colour, ctx->sm_count, ctx->stream);
+    ctx->launches++;
+    RR_CUDA(e);
+    RR_CUDA(cudaGetLastError());
+    return RRRMC_OK;
+}

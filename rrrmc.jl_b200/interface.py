@@ -278,7 +278,14 @@ def spinflip(X, Cfg, move, replica_mask=None):
     Cfg.chunks[...] = X._download().chunks
 
 
-update_cache = spinflip  # the device batch has no separately visible cache; update_cache! ≡ post-flip refresh
+def update_cache(X, Cfg, move):
+    """update_cache!(X, C, move) (Interface.jl:69-86): invoked AFTER the caller flipped spin `move` in `Cfg`; it must
+    not flip again. The device batch holds no cache the caller can see beside the configuration itself, so the update
+    is to make the device copy equal to the (already flipped) `Cfg`; the local-field caches of the sequential samplers
+    are rebuilt from it on their next use, like the reference's caches after `energy`."""
+    if not (1 <= int(move) <= X.N):
+        raise ValueError(f"move out of range: {move}")
+    X._upload(Cfg)
 
 
 class GraphEA(AbstractGraph):
@@ -782,12 +789,14 @@ def standardMC(X, β, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, q
                schedule=None, planes_K=None, planes_M=None, count_accepted=None, cb_method=None):
     """standardMC(X, β, iters; seed, step, hook, C0, quiet) (src/RRRMC.jl:81-127) -> (Es, C).
 
-    schedule="random" is the reference's order (i = rand(1:N) per attempt, one chain per lane);
-    schedule="checkerboard" (default where the lattice is two-colourable) updates all replicas in lock step,
-    a whole sweep (N attempts) at a time — `iters`/`step` are rounded up to whole sweeps. cb_method selects how a
-    task turns Philox bits into accept() decisions: "planes", "sparse", "poisson" or "auto" (include/rrrmc_b200.h)."""
+    schedule="random" (default) is the reference's order and sampling contract: i = rand(1:N) per attempt, `Es` has
+    iters÷step rows, sample `it` is taken before the move of iteration `it` (RRRMC.jl:100-119).
+    schedule="checkerboard" (opt-in; implied by giving cb_method / planes_K / planes_M) updates all replicas of a
+    two-colourable ±J lattice in lock step, a whole sweep (N attempts) at a time — `iters`/`step` are rounded up to
+    whole sweeps and samples are post-sweep energies. cb_method selects how a task turns Philox bits into accept()
+    decisions: "planes", "sparse", "poisson" or "auto" (include/rrrmc_b200.h)."""
     if schedule is None:
-        schedule = "checkerboard" if (isinstance(X, GraphEA) and set(X.LEV) == {-1, 1} and X.L % 2 == 0 and X.D <= 3) else "random"
+        schedule = "checkerboard" if (cb_method is not None or planes_K is not None or planes_M is not None) else "random"
     return _run(lib().rrrmc_standard_mc, X, β, iters, seed, step, hook, C0, quiet,
                 _opts(schedule, planes_K, count_accepted, planes_M=planes_M, cb_method=cb_method), "standardMC")
 

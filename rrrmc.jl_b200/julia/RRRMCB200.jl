@@ -209,14 +209,29 @@ end
 struct RunInfo
     nsamples::Int64; iters_done::Int64; launches::Int64; device_ms::Cfloat; accepted_total::Int64
 end
-# hook(it, X, C, accepted, E)::Bool of RRRMC.jl:61-64 arrives through a C callback; `user` carries the closure
-function _hook_tramp(user::Ptr{Cvoid}, it::Int64, E::Ptr{Cdouble}, acc::Ptr{Int64}, R::Int64)::Cint
-    f, X = unsafe_pointer_to_objref(user)::Tuple{Function,Graph}
-    Cint(f(it, X, download(X), unsafe_wrap(Array, acc, R), unsafe_wrap(Array, E, R)) ? 1 : 0)
+# hook(it, X, C, accepted, E)::Bool of RRRMC.jl:61-64 arrives through a C callback; `user` points at a mutable box
+# that carries the closure (a mutable struct has a stable address under GC.@preserve; a Ref of a tuple would hand the
+# callback a RefValue, not the tuple). An exception inside the hook must not unwind through the C frames of the
+# library: it is parked in the box, the run is stopped (hook result false) and the exception is rethrown by _run.
+mutable struct _HookBox
+    hook::Any
+    X::Any
+    err::Any
 end
-function _run(sym::Symbol, X::Graph, β, iters::Integer; seed = 167432777111, step::Integer = 1, hook = (x...) -> true,
+const _default_hook = (x...) -> true
+function _hook_tramp(user::Ptr{Cvoid}, it::Int64, E::Ptr{Cdouble}, acc::Ptr{Int64}, R::Int64)::Cint
+    box = unsafe_pointer_to_objref(user)::_HookBox
+    try
+        ok = box.hook(it, box.X, download(box.X), unsafe_wrap(Array, acc, R), unsafe_wrap(Array, E, R))
+        return Cint(ok ? 1 : 0)
+    catch e
+        box.err = e
+        return Cint(0)
+    end
+end
+function _run(sym::Symbol, X::Graph, β, iters::Integer; seed = 167432777111, step::Integer = 1, hook = _default_hook,
               C0::Union{Config,Nothing} = nothing, quiet::Bool = false, staged_thr::Real = NaN, staged_thr_fact::Real = 5.0,
-              schedule::Integer = 0)
+              schedule::Integer = 1)
     isfinite(β) || throw(ArgumentError("β must be finite, given: $β"))                    # RRRMC.jl:159
     C0 === nothing ? check(ccall((:rrrmc_state_randomize, lib), Cint, (Ptr{Cvoid}, UInt64), X.state, seed > 0 ? seed : rand(UInt64))) :
                      upload!(X, C0)
@@ -225,14 +240,17 @@ function _run(sym::Symbol, X::Graph, β, iters::Integer; seed = 167432777111, st
     cap = min(10^8, iters ÷ step)                                                          # RRRMC.jl:90
     Es = zeros(X.replicas, max(cap, 1)); info = Ref{RunInfo}()
     betas = fill(Float64(β), X.replicas)
-    ud = Ref((hook, X)); cb = @cfunction(_hook_tramp, Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Int64}, Int64))
-    GC.@preserve ud check(ccall((sym, lib), Cint,
+    # the default hook is not passed at all: no callback, no per-sample download of the whole batch
+    box = _HookBox(hook, X, nothing)
+    cb = hook === _default_hook ? C_NULL : @cfunction(_hook_tramp, Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Int64}, Int64))
+    GC.@preserve box check(ccall((sym, lib), Cint,
         (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Int64, UInt64, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Opts}, Ptr{Cdouble}, Int64, Ref{RunInfo}),
-        X.state, betas, iters, step, seed > 0 ? seed : 0, cb, pointer_from_objref(ud), o, Es, cap, info))
+        X.state, betas, iters, step, seed > 0 ? seed : 0, cb, pointer_from_objref(box), o, Es, cap, info))
+    box.err === nothing || throw(box.err)
     quiet || (println("samples = ", info[].nsamples); println("iters = ", info[].iters_done))
     Es[:, 1:info[].nsamples], download(X)
 end
-"standardMC(X, β, iters; seed, step, hook, C0, quiet) (src/RRRMC.jl:81-127); schedule=0 checkerboard sweeps, 1 the reference's rand(1:N) order."
+"standardMC(X, β, iters; seed, step, hook, C0, quiet) (src/RRRMC.jl:81-127); schedule=1 (default) the reference's rand(1:N) order, 0 checkerboard lattice sweeps (opt-in)."
 standardMC(X::Graph, β::Real, iters::Integer; schedule::Integer = (X.kind == EA_PM1 ? 0 : 1), kw...) =
     _run(:rrrmc_standard_mc, X, β, iters; schedule = schedule, kw...)
 "rrrMC(X, β, iters; seed, step, hook, C0, staged_thr, staged_thr_fact, quiet) (src/RRRMC.jl:149-290)"
@@ -248,10 +266,11 @@ function wtmMC(X::Graph, β::Real, samples::Integer; seed = 167432777111, step::
     Es = zeros(X.replicas, max(cap, 1)); info = Ref{RunInfo}()
     betas = fill(Float64(β), X.replicas)
     timed = (k, X_, C, acc, E) -> hook(k * step / X.N, X_, C, acc, E)      # sample index -> global time (RRRMC.jl:405)
-    ud = Ref((timed, X)); cb = @cfunction(_hook_tramp, Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Int64}, Int64))
-    GC.@preserve ud check(ccall((:rrrmc_wtm_mc, lib), Cint,
+    box = _HookBox(timed, X, nothing); cb = @cfunction(_hook_tramp, Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Int64}, Int64))
+    GC.@preserve box check(ccall((:rrrmc_wtm_mc, lib), Cint,
         (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Cdouble, UInt64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cdouble}, Int64, Ref{RunInfo}),
-        X.state, betas, samples, step, seed > 0 ? seed : 0, cb, pointer_from_objref(ud), Es, cap, info))
+        X.state, betas, samples, step, seed > 0 ? seed : 0, cb, pointer_from_objref(box), Es, cap, info))
+    box.err === nothing || throw(box.err)
     quiet || (println("samples = ", info[].nsamples); println("num_moves = ", info[].iters_done))
     Es[:, 1:info[].nsamples], download(X)
 end
@@ -263,8 +282,13 @@ function set_betas!(X::Graph, betas::Vector{Float64})
 end
 # hook(it, X, C, E, Emin)::Bool of RRRMC.jl:499
 function _eo_hook_tramp(user::Ptr{Cvoid}, it::Int64, E::Ptr{Cdouble}, Emin::Ptr{Cdouble}, R::Int64)::Cint
-    f, X = unsafe_pointer_to_objref(user)::Tuple{Function,Graph}
-    Cint(f(it, X, download(X), unsafe_wrap(Array, E, R), unsafe_wrap(Array, Emin, R)) ? 1 : 0)
+    box = unsafe_pointer_to_objref(user)::_HookBox
+    try
+        return Cint(box.hook(it, box.X, download(box.X), unsafe_wrap(Array, E, R), unsafe_wrap(Array, Emin, R)) ? 1 : 0)
+    catch e
+        box.err = e
+        return Cint(0)
+    end
 end
 "extremal_opt(X, τ, iters; seed, step, hook, C0, quiet) (src/RRRMC.jl:468-521) -> (C, Emin, Cmin, itmin), one entry per replica; DiscrGraph models only."
 function extremal_opt(X::Graph, τ::Real, iters::Integer; seed = 167432777111, step::Integer = 1, hook = (x...) -> true,
@@ -273,11 +297,12 @@ function extremal_opt(X::Graph, τ::Real, iters::Integer; seed = 167432777111, s
                      upload!(X, C0)
     fτ = cumsum([j^(-Float64(τ)) for j = 1:X.N])                           # DeltaE.jl:443: Julia's own `^` and pairwise cumsum
     Emin = zeros(X.replicas); itmin = zeros(Int64, X.replicas); Cmin = Config(X.N, X.replicas); info = Ref{RunInfo}()
-    ud = Ref((hook, X)); cb = @cfunction(_eo_hook_tramp, Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Int64))
-    GC.@preserve ud check(ccall((:rrrmc_extremal_opt, lib), Cint,
+    box = _HookBox(hook, X, nothing); cb = @cfunction(_eo_hook_tramp, Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Int64))
+    GC.@preserve box check(ccall((:rrrmc_extremal_opt, lib), Cint,
         (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Int64, Int64, UInt64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Int64}, Ptr{UInt64},
          Ptr{Cdouble}, Int64, Ref{RunInfo}),
-        X.state, fτ, 0, iters, step, seed > 0 ? seed : 0, cb, pointer_from_objref(ud), Emin, itmin, Cmin.chunks, C_NULL, 0, info))
+        X.state, fτ, 0, iters, step, seed > 0 ? seed : 0, cb, pointer_from_objref(box), Emin, itmin, Cmin.chunks, C_NULL, 0, info))
+    box.err === nothing || throw(box.err)
     quiet || (println("iters = ", info[].iters_done); println("min [it = $itmin] = $Emin"))
     download(X), Emin, Cmin, itmin
 end

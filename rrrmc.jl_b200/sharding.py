@@ -120,6 +120,9 @@ class TemperingLadder:
         return self.beta_of_replica()
 
 
+RANK_SEED_STRIDE = 1_000_003   # seed offset per global replica index of a shard's first replica (tempered_run)
+
+
 class ReplicaShard:
     """This rank's slice of a replica batch of `total` chains."""
 
@@ -144,11 +147,17 @@ def tempered_run(X, ladder, shard, rounds, iters_per_round, sampler, *, seed=1, 
     -> (E_history (rounds, R_total), final Config of the local batch)."""
     C = C0
     hist = []
+    # The engine keys its counter RNG by (seed, LOCAL chain index) and draws the initial configuration from the seed
+    # alone, so the shards must not share a seed: replica r of every rank would start from the same configuration and
+    # consume the same stream, and the swap rule assumes independent chains. The offset is a function of the shard's
+    # first GLOBAL replica, so a replica's stream does not depend on how many ranks the batch is spread over... as long
+    # as the shard boundaries are the same.
+    rank_seed = seed + RANK_SEED_STRIDE * shard.lo
     for rd in range(rounds):
         beta_local = shard.local(ladder.beta_of_replica())
         if hasattr(X, "set_betas"):   # GraphQuant: fourK follows the β a replica currently holds (QT.jl:165)
             X.set_betas(beta_local)
-        Es, C = sampler(X, beta_local, iters_per_round, step=iters_per_round, seed=seed + 7919 * rd, C0=C, quiet=True, **kw)
+        Es, C = sampler(X, beta_local, iters_per_round, step=iters_per_round, seed=rank_seed + 7919 * rd, C0=C, quiet=True, **kw)
         # the swap weighs the configurations as they are now: the last sample of Es predates the last move (the hook
         # instant of RRRMC.jl:104 is before the move), so take energy(X, C) of the returned configuration
         if energy_fn is None:

@@ -30,7 +30,7 @@ if "c3" in which:
     L, D, R, beta = 32, 3, 256, 3.0
     X = rb.GraphEA(L, D, replicas=R, rng=np.random.default_rng(1))
     # equilibrate with checkerboard sweeps so that the low-T rejection-free samplers start from a typical state
-    _, C = rb.standardMC(X, beta, 200 * X.N, step=200 * X.N, seed=1, quiet=True)
+    _, C = rb.standardMC(X, beta, 200 * X.N, step=200 * X.N, seed=1, quiet=True, schedule="checkerboard")
     for name, fn, iters in (("rrrMC", rb.rrrMC, 200_000 if quick else 2_000_000), ("bklMC", rb.bklMC, 10_000_000 if quick else 200_000_000)):
         fn(X, beta, iters // 20, step=iters // 20, seed=2, C0=C, quiet=True)
         t0 = time.perf_counter()

@@ -1,5 +1,5 @@
 """Workload for ncu captures of the checkerboard kernels: equilibrate, then run a few sweeps of one procedure.
-usage: python scripts/prof_cb.py [beta] [sparse|planes] [nsweeps]"""
+usage: python scripts/prof_cb.py [beta] [sparse|planes|poisson] [nsweeps]"""
 import os
 import sys
 
@@ -19,7 +19,12 @@ thr = np.array([min(int(np.exp(-beta * 4 * c) * 2.0 ** 64), 2 ** 64 - 1) for c i
 tbl = np.zeros(33 + 2 * 129, np.uint32)
 check(lib().rrrmc_checkerboard_sparse_tables(ptr(thr), 3, ptr(tbl), len(tbl)))
 check(lib().rrrmc_checkerboard_sweeps(st, ptr(thr), 3, 5, 4, 1, 0, 200))       # equilibrate (planes kernel)
-if method == "sparse":
+if method == "poisson":
+    ptbl = np.zeros(160, np.uint32)
+    check(lib().rrrmc_checkerboard_poisson_tables(ptr(thr), 3, ptr(ptbl), 160))
+    NW = lib().rrrmc_checkerboard_poisson_nw(ptr(ptbl), 0.0)
+    check(lib().rrrmc_checkerboard_sweeps_poisson(st, ptr(ptbl), 160, NW, 1, 200, nsw))
+elif method == "sparse":
     check(lib().rrrmc_checkerboard_sweeps_sparse(st, ptr(tbl), len(tbl), 1, 200, nsw))
 else:
     check(lib().rrrmc_checkerboard_sweeps(st, ptr(thr), 3, 5, 4, 1, 200, nsw))

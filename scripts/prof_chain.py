@@ -13,7 +13,7 @@ iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
 R = int(sys.argv[3]) if len(sys.argv) > 3 else 256
 L, D, beta = 32, 3, 3.0
 X = rb.GraphEA(L, D, replicas=R, rng=np.random.default_rng(1))
-_, C = rb.standardMC(X, beta, 200 * X.N, step=200 * X.N, seed=1, quiet=True)
+_, C = rb.standardMC(X, beta, 200 * X.N, step=200 * X.N, seed=1, quiet=True, schedule="checkerboard")
 fn = {"rrrMC": rb.rrrMC, "bklMC": rb.bklMC}[name]
 Es, C2 = fn(X, beta, iters, step=iters, seed=3, C0=C, quiet=True)
 info = X.last_run

@@ -33,7 +33,8 @@ def test_version_and_opts_default():
     import ctypes as C
     o = _ffi.Opts()
     assert _ffi.lib().rrrmc_opts_default(C.byref(o)) == 0
-    assert o.planes_K == 5 and o.planes_M == 4 and o.staged_thr_fact == 5.0 and np.isnan(o.staged_thr) and o.schedule == 0
+    assert o.planes_K == 5 and o.planes_M == 4 and o.staged_thr_fact == 5.0 and np.isnan(o.staged_thr)
+    assert o.schedule == _ffi.SCHED_RANDOM_SITE   # the reference order and sampling contract is the default; lattice sweeps are opt-in
 
 
 def test_no_device_fails_loudly():

@@ -150,6 +150,85 @@ def test_checkerboard_poisson_kernel_variants_agree(variant, monkeypatch):
     assert got == _from_multispin(sp, R)
 
 
+def _poisson_run_vs_oracle(L, R, beta, NW, nsw, seed, sweep0, A=None, J=None, Jfwd=None, cfg_seed=7):
+    """-> (device configuration, oracle configuration) after nsw poisson sweeps from the same start."""
+    D = 3
+    if A is None:
+        A, J = ea_instance(L, D, seed=L * 10 + D)
+    X = rb.GraphEA(L, D, replicas=R, A=A, J=J)
+    C0 = rb.Config(X.N, R, rng=np.random.default_rng(cfg_seed))
+    tbl = _poisson_tbl(beta, D)
+    X._upload(C0)
+    l0 = X.ctx.launch_count()
+    check(lib().rrrmc_checkerboard_sweeps_poisson(X._state, ptr(tbl), len(tbl), NW, seed, sweep0, nsw))
+    launches = X.ctx.launch_count() - l0
+    got = X._download()
+    sp = _multispin(C0)
+    ffi.checkerboard_sweeps_poisson(L, D, R, sp, _fwd(A, J, L, D) if Jfwd is None else Jfwd, tbl, NW, seed, sweep0, nsw)
+    return got, _from_multispin(sp, R), launches
+
+
+# the TMA-staged brick kernel (ea_tma.cu) is what AUTO runs for 3D lattices with L % 8 == 0 and whole 1024-replica slabs.
+# L = 8: one brick along x (both x faces wrap onto the brick itself), two along y and z (every halo wraps); L = 16, 24:
+# interior bricks; R = 2048, 3072: several slabs; NW = 4, 6: the second static Philox call; warm β: second tier.
+@pytest.mark.parametrize("L,R,beta,NW", [(8, 1024, 1.0, 2), (8, 2048, 0.8, 1), (16, 1024, 0.6, 4), (16, 3072, 1.0, 2),
+                                         (24, 1024, 1.2, 1), (16, 1024, 0.5, 6), (32, 1024, 1.0, 2)])
+def test_checkerboard_tma_bit_exact_vs_cpu_model(L, R, beta, NW, monkeypatch):
+    monkeypatch.delenv("RRRMC_CB_VARIANT", raising=False)
+    nsw = 4 if L <= 16 else 2
+    got, want, launches = _poisson_run_vs_oracle(L, R, beta, NW, nsw, 0xC0FFEE1234, (1 << 33) + 3)
+    assert got == want
+    assert launches in (2 * nsw, 2 * nsw + 1)       # two colour launches per sweep (+ the one-off bond-mask reorder)
+    # the cp.async kernels (TMA forbidden) give the same trajectory
+    monkeypatch.setenv("RRRMC_CB_VARIANT", "2048")
+    got2, _, _ = _poisson_run_vs_oracle(L, R, beta, NW, nsw, 0xC0FFEE1234, (1 << 33) + 3)
+    assert got2 == want
+
+
+@pytest.mark.parametrize("variant", ["128", "1", "32", "129"])
+def test_checkerboard_tma_kernel_variants_agree(variant, monkeypatch):
+    """TMA kernel with two blocks only (every block walks 16 bricks through its two-stage ring: stage reuse, barrier
+    phases), one block per SM, and without programmatic dependent launch."""
+    monkeypatch.setenv("RRRMC_CB_VARIANT", variant)
+    got, want, _ = _poisson_run_vs_oracle(16, 1024, 0.8, 1, 3, 5, 0)
+    assert got == want
+
+
+@pytest.mark.parametrize("variant,NW", [("2176", 2), ("2688", 2), ("2048", 2), ("3200", 1)])
+def test_checkerboard_persist2_multibrick_bit_exact(variant, NW, monkeypatch):
+    """The cp.async persistent kernels in the regime round 1 benched them in: NW = 2 (two tasks per thread) with many
+    bricks per block. L = 32, R = 1024 has 512 bricks; bit 7 (128) launches two blocks (256 bricks each through the
+    software pipeline), bit 9 (512) forces the two-task kernel, bit 10 (1024) the one-task kernel; bit 11 keeps TMA off."""
+    monkeypatch.setenv("RRRMC_CB_VARIANT", variant)
+    got, want, _ = _poisson_run_vs_oracle(32, 1024, 1.0, NW, 2, 77, 5)
+    assert got == want
+
+
+@pytest.mark.parametrize("variant", [None, "2048"])
+def test_checkerboard_poisson_full_size_bit_exact(variant, monkeypatch):
+    """BASELINE configs[1] at size: L = 64, D = 3, R = 1024, β = 1, NW = 2 (what bench.py runs), two sweeps against
+    orc_checkerboard_sweeps_poisson — the TMA kernel (2048 bricks over 296 blocks: ~7 bricks per block) and the
+    round-1 kernel k_checkerboard_poisson_persist2<2,4> (4096 bricks over 740 blocks)."""
+    if variant is None:
+        monkeypatch.delenv("RRRMC_CB_VARIANT", raising=False)
+    else:
+        monkeypatch.setenv("RRRMC_CB_VARIANT", variant)
+    L, D, R = 64, 3, 1024
+    rng = np.random.default_rng(64)
+    A = ffi.gen_EA(L, D)
+    idx = np.arange(L ** D)
+    Jf = rng.choice(np.array([-1, 1], np.int8), (L ** D, D))
+    # reference (A, J) layout from the forward bonds: slot of i+e_d in A[i] and of i in A[i+e_d]
+    J = np.zeros(A.shape, np.int64)
+    for d in range(D):
+        c = (idx // L ** d) % L
+        up = idx + (((c + 1) % L) - c) * L ** d
+        J[idx, (A == (up + 1)[:, None]).argmax(axis=1)] = Jf[:, d]
+        J[up, (A[up] == (idx + 1)[:, None]).argmax(axis=1)] = Jf[:, d]
+    got, want, _ = _poisson_run_vs_oracle(L, R, 1.0, 2, 2, 0x5EEDEA64, 0, A=A, J=J, Jfwd=Jf, cfg_seed=1)
+    assert got == want
+
+
 def test_checkerboard_poisson_argument_checks():
     A, J = ea_instance(4, 3, seed=1)
     X = rb.GraphEA(4, 3, replicas=32, A=A, J=J)
@@ -186,7 +265,7 @@ def test_standardMC_poisson_energies_and_accepted():
         seen.append((it, np.array(acc), np.array(E), C.chunks.copy()))
         return True
     N = X.N
-    Es, Cf = rb.standardMC(X, beta, 6 * N, step=2 * N, seed=77, C0=C0, hook=hook, quiet=True)
+    Es, Cf = rb.standardMC(X, beta, 6 * N, step=2 * N, seed=77, C0=C0, hook=hook, quiet=True, schedule="checkerboard")
     sp = _multispin(C0); acc = np.zeros(R, np.int64)
     tbl = ffi.cb_poisson_tables(ffi.thresholds_fixed64(beta, D))
     NW = ffi.cb_poisson_nw(tbl)
@@ -288,7 +367,7 @@ def test_checkerboard_statistics_vs_reference_sampler():
     R = 256
     X = rb.GraphEA(L, D, replicas=R, A=A, J=J)
     N = X.N
-    Es, _ = rb.standardMC(X, beta, 400 * N, step=400 * N, seed=5, quiet=True)
+    Es, _ = rb.standardMC(X, beta, 400 * N, step=400 * N, seed=5, quiet=True, schedule="checkerboard")
     e_gpu = Es[-1] / N
     g = ffi.Graph.ea_int(A, J)
     e_cpu = []

@@ -69,6 +69,42 @@ def test_spinflip_and_update():
     assert C == ref
 
 
+def test_update_cache_does_not_flip_again():
+    """update_cache!(X, C, move) runs AFTER the caller flipped the spin (Interface.jl:69-92): it refreshes the device
+    copy and must leave `C` as the caller made it; ΔE of the moved site changes sign, as after spinflip!."""
+    X, g = _graph(4, 3, (-1, 1), 40)
+    C = rb.Config(X.N, 40, rng=np.random.default_rng(8))
+    before = np.atleast_1d(rb.delta_energy(X, C, 17))
+    C.chunks[:, 0] ^= np.uint64(1 << 16)          # spinflip!(C, 17) on the host copy
+    flipped = C.copy()
+    rb.update_cache(X, C, 17)
+    assert C == flipped
+    assert X._download() == flipped
+    assert np.array_equal(np.atleast_1d(rb.delta_energy(X, C, 17)), -before)
+    with pytest.raises(ValueError):
+        rb.update_cache(X, C, X.N + 1)
+
+
+def test_randomize_after_chain_run_is_not_lost():
+    """C ABI: a chain sampler leaves the chain layout current; rrrmc_state_randomize then writes the multispin copy and
+    must mark it current, or the next query re-transposes the stale chain copy over it."""
+    from rrrmc_b200._ffi import check, lib, ptr
+    X, g = _graph(4, 3, (-1, 1), 64)
+    C = rb.Config(X.N, 64, rng=np.random.default_rng(9))
+    X._upload(C)
+    st = X._state
+    betas = np.full(64, 1.0)
+    check(lib().rrrmc_rrr_mc(st, ptr(betas), 50, 50, 11, rb._ffi.C.cast(None, rb._ffi.HOOK), None, None, None, 0, None))
+    check(lib().rrrmc_state_randomize(st, 12345))
+    got1 = X._download()
+    check(lib().rrrmc_state_randomize(st, 12345))
+    got2 = X._download()
+    assert got1 == got2                               # the randomisation is what the state holds ...
+    want = np.array([g.energy(got1.chunks[r]) for r in range(64)])
+    Eo = np.zeros(64); check(lib().rrrmc_energy(st, ptr(Eo)))
+    assert np.array_equal(Eo, want.astype(np.float64))  # ... and what energy() sees
+
+
 @pytest.mark.parametrize("L,D,R", [(4, 2, 3), (4, 3, 40), (3, 3, 8), (2, 3, 4)])
 def test_float_couplings_within_1e6(L, D, R):
     A, J = ea_instance(L, D, seed=4, gaussian=True)

@@ -101,7 +101,7 @@ class _ToyEngine:
     relaxes towards −β (so colder labels end lower), observable terms are simple functions of it."""
 
     def __init__(self, n):
-        self.replicas, self.M, self.betas_seen = n, 4, []
+        self.replicas, self.M, self.betas_seen, self.seeds_seen = n, 4, [], []
 
     def set_betas(self, b):
         self.betas_seen.append(np.array(b, np.float64))
@@ -109,7 +109,8 @@ class _ToyEngine:
 
 def _toy_sampler(X, b, iters, *, step, seed, C0, quiet):
     x = np.zeros(X.replicas) if C0 is None else C0
-    rng = np.random.default_rng(seed)           # same seed on every rank: the shards differ through b
+    X.seeds_seen.append(seed)
+    rng = np.random.default_rng(seed)
     x = 0.5 * x - 0.5 * np.asarray(b) * 10 + rng.normal(size=X.replicas) * 0.01
     return x[None, :], x
 
@@ -125,7 +126,7 @@ def _pt_worker(rank, world, port, q):
         ladder = sh.TemperingLadder(np.geomspace(0.5, 4.0, total), seed=11, action=sh.quantum_action(X.M, 0.3))
         hist, C = sh.tempered_run(X, ladder, shard, 5, 100, _toy_sampler, seed=3, energy_fn=lambda X_, c: c,
                                   terms_fn=lambda X_, c: (np.rint(c), 2.0 * c))
-        q.put((rank, hist, ladder.order.copy(), ladder.accepts.copy(), [b.copy() for b in X.betas_seen], shard.lo, shard.hi))
+        q.put((rank, hist, ladder.order.copy(), ladder.accepts.copy(), [b.copy() for b in X.betas_seen], shard.lo, shard.hi, list(X.seeds_seen)))
     finally:
         dist.destroy_process_group()
 
@@ -144,7 +145,11 @@ def test_world_size_2_gloo_tempered_run_quantum_ladder():
     for p in ps:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (_, h0, o0, a0, seen0, lo0, hi0), (_, h1, o1, a1, seen1, lo1, hi1) = res
+    (_, h0, o0, a0, seen0, lo0, hi0, sd0), (_, h1, o1, a1, seen1, lo1, hi1, sd1) = res
+    # the shards' sampler seeds differ in every round (independent chains and initial configurations across ranks),
+    # and are reproducible functions of (seed, round, first global replica of the shard)
+    assert len(sd0) == 5 and len(sd1) == 5 and not set(sd0) & set(sd1)
+    assert sd0 == [3 + 7919 * rd for rd in range(5)] and sd1 == [3 + sh.RANK_SEED_STRIDE * 128 + 7919 * rd for rd in range(5)]
     assert np.array_equal(h0, h1) and h0.shape == (5, 256)
     assert np.array_equal(o0, o1) and np.array_equal(a0, a1) and a0.sum() > 0
     assert (lo0, hi0, lo1, hi1) == (0, 128, 128, 256)
