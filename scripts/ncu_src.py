@@ -5,8 +5,14 @@ import sys
 
 raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-hdr = rows[1]
-body = rows[2:]
+h0 = next(i for i, r in enumerate(rows) if r and r[0] == "Address")          # first kernel's table
+hdr = rows[h0]
+body = []
+for r in rows[h0 + 1:]:
+    if not r or r[0] in ("Kernel Name", "Address"):
+        break
+    if len(r) >= len(hdr):
+        body.append(r)
 isamp, isrc, iexe = hdr.index("# Samples"), hdr.index("Source"), hdr.index("Instructions Executed")
 stalls = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 tot = sum(int(r[isamp] or 0) for r in body)
