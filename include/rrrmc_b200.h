@@ -197,13 +197,17 @@ typedef struct {
 } rrrmc_run_info_t;
 
 /* standardMC(X, β, iters; seed, step, hook, C0) (RRRMC.jl:81-127) on the batch. C0 is the state's
- * current contents (upload or randomize first). beta[R]: per-replica inverse temperature (must be
- * constant inside each 32-replica word). Es: [Es_cap][R] row-major or NULL. With the checkerboard
- * schedule `iters` and `step` are rounded up to whole sweeps (N attempts per replica). */
+ * current contents (upload or randomize first). beta[R]: per-replica inverse temperature. Es: [Es_cap][R] row-major
+ * or NULL. With the checkerboard schedule `iters` and `step` are rounded up to whole sweeps (N attempts per replica),
+ * samples are post-sweep energies, and on ±J lattices β must be constant inside each group of 128 consecutive
+ * replicas (the acceptance procedure draws one hit count per 128-lane task); GraphEANormal lattices take any β[r]. */
 rrrmc_status_t rrrmc_standard_mc(rrrmc_state_t *s, const double *beta, int64_t iters, int64_t step, uint64_t seed,
                                  rrrmc_hook_fn hook, void *user, const rrrmc_opts_t *opts,
                                  double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
-/* rrrMC(X, β, iters; ...) (RRRMC.jl:149-290) and bklMC(X, β, iters; ...) (RRRMC.jl:311-359). */
+/* rrrMC(X, β, iters; ...) (RRRMC.jl:149-290) and bklMC(X, β, iters; ...) (RRRMC.jl:311-359).
+ * Es has iters ÷ step rows for every sampler. One documented deviation: with step > iters the reference's bklMC still
+ * pushes ONE sample when a skip crosses `step` before the loop ends (RRRMC.jl:339-344 runs before the `it < iters`
+ * test); whether that happens differs from chain to chain, a batch cannot return ragged rows, so no row is emitted. */
 rrrmc_status_t rrrmc_rrr_mc(rrrmc_state_t *s, const double *beta, int64_t iters, int64_t step, uint64_t seed,
                             rrrmc_hook_fn hook, void *user, const rrrmc_opts_t *opts,
                             double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
@@ -266,6 +270,14 @@ rrrmc_status_t rrrmc_checkerboard_poisson_tables(const uint64_t *thr64, int nthr
 int rrrmc_checkerboard_poisson_nw(const uint32_t *tbl, double tol);
 rrrmc_status_t rrrmc_checkerboard_sweeps_poisson(rrrmc_state_t *s, const uint32_t *tbl, int tbl_len, int NW,
                                                  uint64_t seed, uint64_t sweep0, int64_t nsweeps);
+
+/* Checkerboard Metropolis for continuous couplings: GraphEANormal (EA.jl:534-680) on the replica batch (ea_normal.cu).
+ * Per (site, replica): ΔE = -2·lf with lf accumulated in Float64 in the slot order of energy() (EA.jl:590-603), i.e. the
+ * value delta_energy() (EA.jl:665-672) returns on freshly initialised caches, then accept(-βΔE) of RRRMC.jl:39 with a
+ * 53-bit uniform from Philox4x32-10(counter = (sweep_hi<<16, site, replica, sweep_lo), key = seed). beta[R] is per
+ * replica. Also reached through rrrmc_standard_mc with schedule = RRRMC_SCHED_CHECKERBOARD on a GraphEANormal lattice
+ * (even L). CPU restatement: oracle/rrrmc_oracle.c:orc_checkerboard_sweeps_f64. */
+rrrmc_status_t rrrmc_checkerboard_sweeps_f64(rrrmc_state_t *s, const double *beta, uint64_t seed, uint64_t sweep0, int64_t nsweeps);
 
 /* ---- dense GraphSKNormal path (BASELINE config 4) ----------------------------------------------
  * Local-field initialisation for the whole batch = the energy(X, C) contraction of SK.jl:212-237,

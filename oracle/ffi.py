@@ -118,6 +118,8 @@ def lib():
         "orc_checkerboard_sweeps_poisson": (None, [i32, i32, i64, p(np.uint32), p(np.int8), p(np.uint32), i32,
                                                    C.c_uint64, C.c_uint64, i64, vp]),
         "orc_cb_poisson_tables": (None, [p(np.uint64), i32, p(np.uint32)]),
+        "orc_checkerboard_sweeps_f64": (None, [i32, i32, i64, p(np.uint32), p(np.int64), p(np.float64), p(np.float64),
+                                               C.c_uint64, C.c_uint64, i64, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -502,3 +504,11 @@ def checkerboard_sweeps_poisson(L, D, R, spins, Jfwd, tbl, NW, seed, sweep0, nsw
     assert len(tbl) == CBP_LEN and NW in (1, 2, 4, 6)
     lib().orc_checkerboard_sweeps_poisson(L, D, R, spins, np.ascontiguousarray(Jfwd, np.int8),
                                           np.ascontiguousarray(tbl, np.uint32), NW, seed, sweep0, nsweeps, acc_p)
+
+
+def checkerboard_sweeps_f64(L, D, R, spins, A, J, beta, seed, sweep0, nsweeps, accepted=None):
+    """CPU model of the engine's checkerboard sweeps for continuous couplings (GraphEANormal)."""
+    acc_p = accepted.ctypes.data if accepted is not None else None
+    b = np.ascontiguousarray(np.broadcast_to(np.asarray(beta, np.float64), (R,)))
+    lib().orc_checkerboard_sweeps_f64(L, D, R, spins, np.ascontiguousarray(A, np.int64), np.ascontiguousarray(J, np.float64),
+                                      b, seed, sweep0, nsweeps, acc_p)

@@ -1771,3 +1771,49 @@ void orc_checkerboard_sweeps_poisson(int L, int D, int64_t R, uint32_t *spins, c
             }
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Checkerboard Metropolis for continuous couplings (GraphEANormal, EA.jl:534-680), CPU model of
+ * rrrmc.jl_b200/csrc/ea_normal.cu. Same two-colour schedule as the ±J kernels; per (site, replica):
+ *   lf = 0; for k = 1..2D: lf -= J[x][k]·σx·σy  (the slot order of energy(), EA.jl:590-603); ΔE = -2·lf
+ *   accept(-βΔE): ΔE <= 0 flips, else u < exp(-βΔE) (RRRMC.jl:39), u = 53-bit uniform from
+ *   Philox4x32-10(counter = (t_hi<<16, site, replica, t_lo), key = seed): (y:x) >> 11 · 2^-53.
+ * A, J: the reference layout (1-based neighbours, slot-aligned couplings). beta: per replica.
+ * ---------------------------------------------------------------------------------------- */
+void orc_checkerboard_sweeps_f64(int L, int D, int64_t R, uint32_t *spins, const int64_t *A, const double *J,
+                                 const double *beta, uint64_t seed, uint64_t sweep0, int64_t nsweeps, int64_t *accepted)
+{
+    int64_t N = 1; for (int d = 0; d < D; d++) N *= L;
+    const int64_t W = (R + 31) / 32; const int twoD = 2 * D;
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    for (int64_t sw = 0; sw < nsweeps; sw++) {
+        const uint64_t t = sweep0 + (uint64_t)sw;
+        for (int colour = 0; colour < 2; colour++)
+            for (int64_t i = 0; i < N; i++) {
+                int64_t rem = i, par = 0;
+                for (int d = 0; d < D; d++) { par += rem % L; rem /= L; }
+                if ((par & 1) != colour) continue;
+                for (int64_t r = 0; r < R; r++) {
+                    const int64_t w = r >> 5; const int bb = (int)(r & 31);
+                    const int sx = (spins[i * W + w] >> bb) & 1;
+                    double lf = 0.0;
+                    for (int k = 0; k < twoD; k++) {
+                        const int64_t y = A[i * twoD + k] - 1;
+                        const int sy = (spins[y * W + w] >> bb) & 1;
+                        lf -= J[i * twoD + k] * (double)((2 * sx - 1) * (2 * sy - 1));
+                    }
+                    const double dE = -2.0 * lf, x = -beta[r] * dE;
+                    int flip = x >= 0;
+                    if (!flip) {
+                        uint32_t ctr[4] = { (uint32_t)(t >> 32) << 16, (uint32_t)i, (uint32_t)r, (uint32_t)t }, o[4];
+                        orc_philox4x32_10(ctr, key, o);
+                        const double u = (double)((((uint64_t)o[1] << 32) | o[0]) >> 11) * 0x1.0p-53;
+                        flip = u < exp(x);
+                    }
+                    if (!flip) continue;
+                    spins[i * W + w] ^= (uint32_t)1 << bb;
+                    if (accepted) accepted[r]++;
+                }
+            }
+    }
+}

@@ -185,6 +185,10 @@ void orc_checkerboard_sweeps_poisson(int L, int D, int64_t R, uint32_t *spins, c
                                      int64_t *accepted /* [R] += */);
 void orc_cb_poisson_tables(const uint64_t *thr, int D, uint32_t *tbl);
 
+/* checkerboard Metropolis for continuous couplings (GraphEANormal): CPU model of csrc/ea_normal.cu */
+void orc_checkerboard_sweeps_f64(int L, int D, int64_t R, uint32_t *spins, const int64_t *A, const double *J,
+                                 const double *beta, uint64_t seed, uint64_t sweep0, int64_t nsweeps, int64_t *accepted);
+
 #ifdef __cplusplus
 }
 #endif

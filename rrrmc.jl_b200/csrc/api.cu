@@ -11,6 +11,7 @@
 #include "cb_params.cuh"
 #include "chain.cuh"
 #include "ea_tma.cuh"
+#include "ea_normal.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -642,7 +643,7 @@ extern "C" rrrmc_status_t rrrmc_state_destroy(rrrmc_state_t *s)
     cudaSetDevice(s->g->ctx->device);
     cudaStreamSynchronize(s->g->ctx->stream);
     cudaFree(s->d_spins); cudaFree(s->d_chunks); cudaFree(s->d_ibuf); cudaFree(s->d_acc);
-    cudaFree(s->d_flips); cudaFree(s->d_mask); cudaFree(s->d_q_fourK);
+    cudaFree(s->d_flips); cudaFree(s->d_mask); cudaFree(s->d_q_fourK); cudaFree(s->d_beta);
     chain_free(s);
     sk_dense_free(s);
     checkerboard_tma_free(s);
@@ -1127,6 +1128,107 @@ extern "C" rrrmc_status_t rrrmc_checkerboard_sweeps_poisson(rrrmc_state_t *s, co
     s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
     return RRRMC_OK;
 }
+// ---- continuous couplings (GraphEANormal): per-lane Float64 checkerboard sweeps (ea_normal.cu)
+static rrrmc_status_t fill_cbn_params(rrrmc_state *s, const double *beta, uint64_t seed, cbn_params &p)
+{
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    if (!(g->kind == RRRMC_EA_F64 && g->L > 0 && g->d_Jd && g->d_A)) {
+        rrrmc_set_error("continuous-coupling checkerboard sweeps need a GraphEANormal lattice");
+        return RRRMC_ERR_UNSUPPORTED;
+    }
+    if (!g->bipartite) {
+        rrrmc_set_error("checkerboard sweeps need even L (a two-colourable lattice), given L=%d; use schedule=RANDOM_SITE", g->L);
+        return RRRMC_ERR_UNSUPPORTED;
+    }
+    RR_ARG(beta, "beta is NULL");
+    for (int64_t r = 0; r < s->R; r++)
+        RR_ARG(std::isfinite(beta[r]) && beta[r] >= 0, "β must be finite and >= 0, given: %g (replica %lld)", beta[r], (long long)r);
+    RR_ARG(g->N * s->W < ((int64_t)1 << 40), "N*W too large");
+    if (!s->d_beta) RR_CUDA(cudaMalloc(&s->d_beta, sizeof(double) * s->W * 32));
+    RR_CUDA(cudaMemcpyAsync(s->d_beta, beta, sizeof(double) * s->R, cudaMemcpyHostToDevice, ctx->stream));
+    RR_CUDA(cudaStreamSynchronize(ctx->stream));      // `beta` is a caller buffer
+    memset(&p, 0, sizeof p);
+    p.spins = s->d_spins; p.flips = nullptr; p.A = g->d_A; p.J = g->d_Jd; p.beta = s->d_beta;
+    p.L = g->L; p.D = g->D; p.twoD = g->twoD; p.W = (int)s->W; p.R = s->R;
+    p.nwg = (int)((s->W + 3) / 4); p.ntasks = (g->N / 2) * p.nwg;
+    p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32);
+    return RRRMC_OK;
+}
+static rrrmc_status_t run_sweep_f64(rrrmc_state *s, cbn_params &p, uint64_t t)
+{
+    p.t_lo = (uint32_t)t; p.t_hi16 = (uint32_t)(t >> 32) << 16;
+    RR_TRY(launch_checkerboard_f64(s->g->ctx, p, 0));
+    RR_TRY(launch_checkerboard_f64(s->g->ctx, p, 1));
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_checkerboard_sweeps_f64(rrrmc_state_t *s, const double *beta, uint64_t seed, uint64_t sweep0, int64_t nsweeps)
+{
+    RR_ARG(s, "state is NULL");
+    RR_ARG(nsweeps >= 0, "nsweeps must be >= 0");
+    RR_CUDA(cudaSetDevice(s->g->ctx->device));
+    RR_TRY(chain_sync_to_multispin(s));
+    cbn_params p;
+    RR_TRY(fill_cbn_params(s, beta, seed, p));
+    for (int64_t k = 0; k < nsweeps; k++) RR_TRY(run_sweep_f64(s, p, sweep0 + (uint64_t)k));
+    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
+    return RRRMC_OK;
+}
+// standardMC with schedule = CHECKERBOARD on a GraphEANormal lattice: whole sweeps, per-replica β, samples every
+// ceil(step/N) sweeps (energies through the chain layout's sequential sum, which rounds like the reference's loop).
+static rrrmc_status_t standard_mc_checkerboard_f64(rrrmc_state *s, const double *beta, int64_t iters, int64_t step, uint64_t seed,
+                                                   rrrmc_hook_fn hook, void *user, const rrrmc_opts_t *o,
+                                                   double *Es, int64_t Es_cap, rrrmc_run_info_t *info)
+{
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    RR_TRY(chain_sync_to_multispin(s));
+    cbn_params p;
+    RR_TRY(fill_cbn_params(s, beta, seed, p));
+    const int64_t N = g->N;
+    const int64_t nsweeps = (iters + N - 1) / N, step_sw = std::max<int64_t>(1, (step + N - 1) / N);
+    const bool count = o->count_accepted != 0;
+    if (count) {
+        if (!s->d_flips) RR_CUDA(cudaMalloc(&s->d_flips, sizeof(uint32_t) * N * s->W));
+        p.flips = s->d_flips;
+        RR_CUDA(cudaMemsetAsync(s->d_acc, 0, sizeof(long long) * s->W * 32, ctx->stream));
+    }
+    const uint64_t l0 = ctx->launches;
+    std::vector<double> E(s->R);
+    std::vector<long long> acc_h(s->W * 32);
+    std::vector<int64_t> acc(s->R, -1);
+    int64_t nsamples = 0, done = 0;
+    event_pair ev;
+    RR_CUDA(ev.create());
+    RR_CUDA(cudaEventRecord(ev.e0, ctx->stream));
+    for (int64_t sw = 1; sw <= nsweeps; sw++) {
+        p.spins = s->d_spins;
+        RR_TRY(run_sweep_f64(s, p, (uint64_t)(sw - 1)));
+        s->ms_valid = true; s->chain_valid = false; s->chain_fields_valid = false; s->energy_valid = false;
+        if (count) {
+            // both colours wrote their accept masks into disjoint halves of d_flips during this sweep
+            RR_TRY(launch_count_lanes(ctx, s->d_flips, N, (int)s->W, s->d_acc));
+        }
+        done = sw;
+        if (sw % step_sw == 0 && (hook || (Es && nsamples < Es_cap))) {
+            RR_TRY(chain_energy(s, E.data()));
+            if (count) {
+                RR_CUDA(cudaMemcpyAsync(acc_h.data(), s->d_acc, sizeof(long long) * s->W * 32, cudaMemcpyDeviceToHost, ctx->stream));
+                RR_CUDA(cudaStreamSynchronize(ctx->stream));
+                for (int64_t r = 0; r < s->R; r++) acc[r] = acc_h[r];
+            }
+            if (Es && nsamples < Es_cap) memcpy(Es + nsamples * s->R, E.data(), sizeof(double) * s->R);
+            nsamples++;
+            if (hook && !hook(user, sw * N, E.data(), acc.data(), s->R)) break;
+            RR_TRY(chain_sync_to_multispin(s));      // a hook may have run a chain-layout query
+        }
+    }
+    RR_CUDA(cudaEventRecord(ev.e1, ctx->stream));
+    RR_CUDA(cudaEventSynchronize(ev.e1));
+    float ms = 0; RR_CUDA(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
+    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
+    if (info) { info->nsamples = std::min(nsamples, Es ? Es_cap : nsamples); info->iters_done = done * N; info->launches = (int64_t)(ctx->launches - l0); info->device_ms = ms; info->accepted_total = -1; }
+    return RRRMC_OK;
+}
+
 // AUTO: the sparse procedure wins while few lanes pass (expected passing lanes per 32-lane word <= 1.5)
 static bool cb_use_sparse(const rrrmc_opts_t *o, double p1)
 {
@@ -1238,6 +1340,8 @@ extern "C" rrrmc_status_t rrrmc_standard_mc(rrrmc_state_t *s, const double *beta
     if (opts) o = *opts; else rrrmc_opts_default(&o);
     RR_CUDA(cudaSetDevice(s->g->ctx->device));
     if (info) memset(info, 0, sizeof *info);
+    if (o.schedule == RRRMC_SCHED_CHECKERBOARD && s->g->kind == RRRMC_EA_F64 && s->g->L > 0)
+        return standard_mc_checkerboard_f64(s, beta, iters, step, seed, hook, user, &o, Es, Es_cap, info);
     if (o.schedule == RRRMC_SCHED_CHECKERBOARD) {
         double b; RR_TRY(uniform_beta(s, beta, &b));
         return standard_mc_checkerboard(s, b, iters, step, seed, hook, user, &o, Es, Es_cap, info);

@@ -73,6 +73,7 @@ struct rrrmc_state {
     long long *d_acc = nullptr;      // [W*32] accepted counters
     uint32_t *d_flips = nullptr;     // [N][W] accept masks of the last sweep (count_accepted)
     uint32_t *d_mask = nullptr;      // [W] replica mask staging
+    double *d_beta = nullptr;        // [W*32] per-replica β of the continuous-coupling checkerboard kernel
     bool energy_valid = false;
     // chain layout (sequential samplers): d_chunks is the spin state, one BitVector per chain
     bool ms_valid = true;            // multispin copy is current

@@ -706,6 +706,17 @@ def sk_metropolis_sweeps(X, β, nsweeps, *, seed=DEFAULT_SEED, sweep0=0, C0=None
     return E, acc, X._download()
 
 
+def checkerboard_sweeps_normal(X, β, nsweeps, *, seed=DEFAULT_SEED, sweep0=0, C0=None):
+    """Checkerboard Metropolis sweeps on a GraphEANormal batch (continuous couplings, per-replica β): the kernel of
+    csrc/ea_normal.cu behind rrrmc_checkerboard_sweeps_f64. -> C"""
+    st = X._ensure_state()
+    if C0 is not None:
+        X._upload(C0)
+    betas = np.ascontiguousarray(np.broadcast_to(np.asarray(β, np.float64), (X.replicas,)))
+    check(lib().rrrmc_checkerboard_sweeps_f64(st, ptr(betas), int(seed), int(sweep0), int(nsweeps)))
+    return X._download()
+
+
 # ----------------------------------------------------------------------------------------------------
 class _LazyConfig:
     """The `C` a hook sees: downloads the batch from the device on first access."""
