@@ -21,6 +21,16 @@ __device__ __forceinline__ uint32_t shl_clamp(uint32_t amt)
     asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(1u), "r"(amt));
     return r;
 }
+// one-hot of position amt in 128 lanes (four words), 0 for amt >= 128: two 64-bit shifts (shl.b64 clamps amounts above
+// 63; SASS: SHF.L.U32 + SHF.L.U64.HI each), so a hit costs four ALU-pipe instructions and ONE subtraction, which is
+// written amt·one - 64 to stay an IMAD (fma pipe) — the four 32-bit shifts it replaces needed three
+__device__ __forceinline__ void onehot128(uint32_t amt, uint32_t one, uint32_t (&o)[4])
+{
+    uint64_t lo, hi;
+    asm("shl.b64 %0, %1, %2;" : "=l"(lo) : "l"(1ull), "r"(amt));
+    asm("shl.b64 %0, %1, %2;" : "=l"(hi) : "l"(1ull), "r"(amt * one - 64u));
+    o[0] = (uint32_t)lo; o[1] = (uint32_t)(lo >> 32); o[2] = (uint32_t)hi; o[3] = (uint32_t)(hi >> 32);
+}
 
 __device__ __forceinline__ philox_out cbp_philox(const cbp_params &p, uint32_t ctr0, uint32_t c1, uint32_t c2)
 {
@@ -132,7 +142,8 @@ __device__ __forceinline__ cbp_words<NW> cbp_draw(const cbp_params &p, uint32_t 
 
 template <int D, int NW>
 __device__ __forceinline__ bool cbp_task_hits(const cbp_params &p, const uint2 *__restrict__ bucket, uint32_t c1, uint32_t c2,
-                                              const cbp_words<NW> &rw, uint32_t (&m)[4], uint32_t (&g)[4], uint32_t (&h)[4])
+                                              const cbp_words<NW> &rw, uint32_t (&m)[4], uint32_t (&g)[4], uint32_t (&h)[4],
+                                              bool *warp_slow = nullptr)
 {
     constexpr int NS = 4 * NW - 1;
     const philox_out A = rw.A;
@@ -158,7 +169,8 @@ __device__ __forceinline__ bool cbp_task_hits(const cbp_params &p, const uint2 *
 #pragma unroll
     for (int j = 0; j < NS; j++) {
         const uint32_t amt = (j & 3) == 3 ? f[j >> 2] >> 24 : __byte_perm(f[j >> 2], 0u, 0x4440u + (j & 3));
-        const uint32_t o[4] = { shl_clamp(amt), shl_clamp(amt * one - 32u), shl_clamp(amt * one - 64u), shl_clamp(amt * one - 96u) };
+        uint32_t o[4];
+        onehot128(amt, one, o);
         // OR tree three inputs at a time: a pending one-hot waits in acc[w][1]
 #pragma unroll
         for (int w = 0; w < 4; w++) {
@@ -171,11 +183,13 @@ __device__ __forceinline__ bool cbp_task_hits(const cbp_params &p, const uint2 *
     for (int w = 0; w < 4; w++) { g[w] = 0u; h[w] = 0u; }
     if (D >= 2) {
         const uint32_t amt = f[NW - 1] >> 24;
-        g[0] = shl_clamp(amt); g[1] = shl_clamp(amt * one - 32u); g[2] = shl_clamp(amt * one - 64u); g[3] = shl_clamp(amt * one - 96u);
+        onehot128(amt, one, g);
     }
 #pragma unroll
     for (int w = 0; w < 4; w++) m[w] = NS == 1 ? (acc[w][1] | g[w]) : lop3p<P_OR3>(acc[w][0], acc[w][1], g[w]);
-    if (__any_sync(__activemask(), slow)) {
+    const bool any_slow = __any_sync(__activemask(), slow);   // warp-uniform: some lane left the fast path
+    if (warp_slow) *warp_slow = any_slow;
+    if (any_slow) {
         const uint32_t *TA = p.tbl, *TB0 = TA + CBP_KA, *TB = TB0 + CBP_KR, *TC = TB + CBP_KR;
         const philox_out S = cbp_philox(p, NW > 2 ? 2u : 1u, c1, c2);   // first overflow call: Y, then twelve byte slots
         uint32_t na = 0, nb = 0, nc = 0;
@@ -209,7 +223,8 @@ __device__ __forceinline__ bool cbp_task_hits(const cbp_params &p, const uint2 *
             const uint32_t wsl = sl < 4 ? S.y : (sl < 8 ? S.z : S.w);
             const uint32_t pos = (wsl >> (8 * (sl & 3))) & 127u;
             const uint32_t amt = (uint32_t)sl < n3 ? pos : 255u;
-            const uint32_t o[4] = { shl_clamp(amt), shl_clamp(amt - 32u), shl_clamp(amt - 64u), shl_clamp(amt - 96u) };
+            uint32_t o[4];
+            onehot128(amt, 1u, o);
 #pragma unroll
             for (int w = 0; w < 4; w++) {
                 xm[w] |= o[w];

@@ -22,6 +22,7 @@
 // without swizzling. The producer/consumer handshake is the usual full/empty mbarrier pair per stage; consumers
 // generate the (spin-independent) hit masks of a brick's two tasks BEFORE waiting for its data.
 #include <cuda.h>
+#include <vector>
 #include "kernels.cuh"
 #include "ea_poisson_core.cuh"
 #include "ea_tma.cuh"
@@ -174,19 +175,22 @@ __global__ void __launch_bounds__(NCONS + 32, MINB) k_checkerboard_tma(const __g
     uint4 *const spins4 = reinterpret_cast<uint4 *>(p.spins);
     uint4 *const flips4 = reinterpret_cast<uint4 *>(p.flips);
 
+    // {first site of the brick, slab} comes from a table built once per state: decoding the brick index costs ~35
+    // instructions per brick and thread; the entry of the NEXT brick is requested one iteration ahead
+    uint2 org = __ldg(P.origin + min((int)blockIdx.x, total - 1));
     int k = 0;
     for (int bb = blockIdx.x; bb < total; bb += gridDim.x, k++) {
         const int s = k & 1;
         const uint32_t sb = sm0 + s * STAGE_BYTES, full = bars + 8 * s, empty = bars + 16 + 8 * s;
-        const brick_pos r = locate_brick(P, bb);
-        const uint32_t i0 = (uint32_t)r.x0 + (uint32_t)L * ((uint32_t)r.y0 + (uint32_t)L * (uint32_t)r.z0) + soff, i1 = i0 + LL2;
-        const uint32_t grp = (uint32_t)(r.slab * 8 + g8);
+        const uint32_t i0 = org.x + soff, i1 = i0 + LL2;
+        const uint32_t grp = org.y * 8u + (uint32_t)g8;
+        org = __ldg(P.origin + min(bb + (int)gridDim.x, total - 1));
         uint32_t m[2][4], gg[2][4], h[2][4];
-        bool slow[2];
+        bool slow[2], wslow[2];      // wslow: warp-uniform "some lane of the warp left the fast path" (only then can h be set)
         // both Philox chains in one basic block: their rounds interleave
         const cbp_words<NW> rw0 = cbp_draw<NW>(p, i0, grp), rw1 = cbp_draw<NW>(p, i1, grp);
-        slow[0] = cbp_task_hits<D, NW>(p, sbucket, i0, grp, rw0, m[0], gg[0], h[0]);
-        slow[1] = cbp_task_hits<D, NW>(p, sbucket, i1, grp, rw1, m[1], gg[1], h[1]);
+        slow[0] = cbp_task_hits<D, NW>(p, sbucket, i0, grp, rw0, m[0], gg[0], h[0], &wslow[0]);
+        slow[1] = cbp_task_hits<D, NW>(p, sbucket, i1, grp, rw1, m[1], gg[1], h[1], &wslow[1]);
         if (k == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
         mbar_wait(full, (k >> 1) & 1);
 #pragma unroll
@@ -216,11 +220,16 @@ __global__ void __launch_bounds__(NCONS + 32, MINB) k_checkerboard_tma(const __g
                 bp[2][q] = lop3p<P_XOR3>(sc[2], v[q].z, neg[q]); bp[3][q] = lop3p<P_XOR3>(sc[3], v[q].w, neg[q]);
             }
 #pragma unroll
-            for (int w = 0; w < 4; w++) {
-                if (slow[j]) bp[w][0] |= h[j][w];        // a level-3 hit flips every lane (m = g = 1 there, so u >= 1 suffices)
-                fl[w] = cbp_flip_planes<D>(bp[w], m[j][w], gg[j][w]);
-                sc[w] ^= fl[w];
+            for (int w = 0; w < 4; w++) fl[w] = cbp_flip_planes<D>(bp[w], m[j][w], gg[j][w]);
+            if (wslow[j]) {                              // a uniform branch, taken by ~13 % of the warps at β = 1
+                asm volatile("" ::: "memory");           // (kept a branch: predicating it would cost every task 8 instructions)
+                if (slow[j]) {
+#pragma unroll
+                    for (int w = 0; w < 4; w++) fl[w] |= h[j][w];   // a level-3 hit flips its lane whatever the bonds say
+                }
             }
+#pragma unroll
+            for (int w = 0; w < 4; w++) sc[w] ^= fl[w];
             const uint32_t idx = (j ? i1 : i0) * W4 + grp;
             spins4[idx] = make_uint4(sc[0], sc[1], sc[2], sc[3]);
             if (flips4) flips4[idx] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
@@ -308,7 +317,7 @@ bool checkerboard_tma_eligible(const rrrmc_state *s)
 
 void checkerboard_tma_free(rrrmc_state *s)
 {
-    if (s->tma) { cudaFree(s->tma->d_jbrick); delete s->tma; s->tma = nullptr; }
+    if (s->tma) { cudaFree(s->tma->d_jbrick); cudaFree(s->tma->d_origin); delete s->tma; s->tma = nullptr; }
 }
 
 // Fills the TMA half of the launch parameters: tensor maps over the state's spin array (encoded once per state) and
@@ -336,12 +345,24 @@ rrrmc_status_t checkerboard_tma_prepare(rrrmc_state *s, const cbp_params &p, cbt
         k_build_jbrick<<<div_up((int64_t)n, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4 *>(g->d_jmask), c->d_jbrick, L, c->nbx, c->nby, c->nbricks);
         ctx->launches++;
         if (cudaGetLastError() != cudaSuccess) { cudaFree(c->d_jbrick); delete c; rrrmc_set_error("k_build_jbrick launch failed"); return RRRMC_ERR_CUDA; }
+        // first site and slab of every brick of a launch, in launch order
+        std::vector<uint2> org((size_t)c->nbricks * (W / 32));
+        for (int slab = 0; slab < W / 32; slab++)
+            for (int b = 0; b < c->nbricks; b++) {
+                const int X = b % c->nbx, Y = (b / c->nbx) % c->nby, Z = b / (c->nbx * c->nby);
+                org[(size_t)slab * c->nbricks + b] = make_uint2((uint32_t)(X * BX) + (uint32_t)L * ((uint32_t)(Y * BY) + (uint32_t)L * (uint32_t)(Z * BZ)), (uint32_t)slab);
+            }
+        if (cudaMalloc(&c->d_origin, org.size() * sizeof(uint2)) != cudaSuccess ||
+            cudaMemcpyAsync(c->d_origin, org.data(), org.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            cudaFree(c->d_jbrick); cudaFree(c->d_origin); delete c; rrrmc_set_error("upload of the brick table failed"); return RRRMC_ERR_CUDA;
+        }
         s->tma = c;
     }
     const cb_tma_store *c = s->tma;
     P.p = p;
     P.m_y6 = c->m_y6; P.m_y5 = c->m_y5; P.m_y4 = c->m_y4; P.m_y1 = c->m_y1; P.m_xf = c->m_xf;
-    P.jbrick = c->d_jbrick;
+    P.jbrick = c->d_jbrick; P.origin = c->d_origin;
     P.nbx = c->nbx; P.nby = c->nby; P.nbricks = c->nbricks; P.nslab = W / 32;
     P.inv_nbx = 1.0f / (float)c->nbx; P.inv_nby = 1.0f / (float)c->nby; P.inv_nbricks = 1.0f / (float)c->nbricks;
     return RRRMC_OK;

@@ -11,6 +11,7 @@ struct alignas(64) cbt_params {
     CUtensorMap m_xf;                     // box (32, 1, 1 x, 4 y, 4 z): an x face of a brick
     cbp_params p;                         // the poisson procedure's parameters (tables, Philox keys, spins, flips)
     const uint4 *jbrick;                  // [2 colours][nbricks][64 slots][2]: bond masks of the active sites, brick order
+    const uint2 *origin;                  // [nslab * nbricks] {first site of the brick, slab} in launch order
     int nbx, nby, nbricks, nslab;         // bricks along x, y, per slab; 1024-replica slabs
     float inv_nbx, inv_nby, inv_nbricks;
 };
@@ -18,6 +19,7 @@ struct alignas(64) cbt_params {
 struct cb_tma_store {
     CUtensorMap m_y6, m_y5, m_y4, m_y1, m_xf;
     uint4 *d_jbrick = nullptr;
+    uint2 *d_origin = nullptr;
     int nbx = 0, nby = 0, nbricks = 0;
 };
 
