@@ -1115,6 +1115,14 @@ static rrrmc_status_t run_sweep_poisson(rrrmc_state *s, cbp_run &run, uint64_t t
     RR_TRY(launch_checkerboard_poisson(g->ctx, p, g->D, 1));
     return RRRMC_OK;
 }
+// n whole sweeps: one launch of the multi-sweep kernel when the TMA path applies (RRRMC_CB_VARIANT bit 12 (4096) keeps
+// the per-colour launches for A/B timing and tests), else two launches per sweep.
+static rrrmc_status_t run_sweeps_poisson(rrrmc_state *s, cbp_run &run, uint64_t t0, int64_t n)
+{
+    if (run.tma && !(run.p.variant & 4096)) return launch_checkerboard_flow(s, *run.tma, t0, n, nullptr, nullptr, 0);
+    for (int64_t k = 0; k < n; k++) RR_TRY(run_sweep_poisson(s, run, t0 + (uint64_t)k));
+    return RRRMC_OK;
+}
 extern "C" rrrmc_status_t rrrmc_checkerboard_sweeps_poisson(rrrmc_state_t *s, const uint32_t *tbl, int tbl_len, int NW,
                                                             uint64_t seed, uint64_t sweep0, int64_t nsweeps)
 {
@@ -1124,7 +1132,7 @@ extern "C" rrrmc_status_t rrrmc_checkerboard_sweeps_poisson(rrrmc_state_t *s, co
     RR_TRY(chain_sync_to_multispin(s));
     cbp_run run;
     RR_TRY(prepare_poisson_run(s, tbl, tbl_len, NW, seed, run));
-    for (int64_t k = 0; k < nsweeps; k++) RR_TRY(run_sweep_poisson(s, run, sweep0 + (uint64_t)k));
+    RR_TRY(run_sweeps_poisson(s, run, sweep0, nsweeps));
     s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
     return RRRMC_OK;
 }
@@ -1303,8 +1311,16 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
     RR_CUDA(ev.create());
     cudaEvent_t e0 = ev.e0, e1 = ev.e1;
     RR_CUDA(cudaEventRecord(e0, ctx->stream));
+    // sweeps between two samples go out as one batch (one launch of the multi-sweep kernel) unless accepted moves
+    // are counted, which reads the flip masks after every sweep
+    const bool sample = hook || Es;
     for (int64_t sw = 1; sw <= nsweeps; sw++) {
-        if (poisson) RR_TRY(run_sweep_poisson(s, pp, (uint64_t)(sw - 1)));
+        if (poisson && !count) {
+            int64_t last = sample ? std::min(nsweeps, ((sw - 1) / step_sw + 1) * step_sw) : nsweeps;
+            RR_TRY(run_sweeps_poisson(s, pp, (uint64_t)(sw - 1), last - sw + 1));
+            sw = last;
+        }
+        else if (poisson) RR_TRY(run_sweep_poisson(s, pp, (uint64_t)(sw - 1)));
         else if (sparse) RR_TRY(run_sweep_sparse(s, ps, (uint64_t)(sw - 1)));
         else RR_TRY(run_sweep(s, p, (uint64_t)(sw - 1)));
         if (count) RR_TRY(launch_count_lanes(ctx, s->d_flips, N, (int)s->W, s->d_acc));

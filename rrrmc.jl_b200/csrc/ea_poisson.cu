@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256, MINB) k_checkerboard_poisson(const __grid
         if (D >= 3) { const uint2 jb = __ldg(reinterpret_cast<const uint2 *>(p.jmask + 2 * (size_t)i + 1)); neg[4] = jb.x; neg[5] = jb.y; }
     }
     uint32_t m[4], gg[4], h[4];
-    const bool slow = cbp_task_hits<D, NW>(p, p.bucket, i, (uint32_t)g, cbp_draw<NW>(p, i, (uint32_t)g), m, gg, h);
+    const bool slow = cbp_task_hits<D, NW>(p, cbp_env_of(p, p.bucket), i, (uint32_t)g, cbp_draw<NW>(p, cbp_env_of(p, p.bucket), i, (uint32_t)g), m, gg, h);
 
     uint32_t sc[4], b[4][2 * D];
     if (FULL) {
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256, MINB) k_checkerboard_poisson_persist(cons
     bool first = true;
     for (;;) {
         uint32_t m[4], gg[4], h[4];
-        const bool slow = cbp_task_hits<D, NW>(p, sbucket, i, (uint32_t)g, cbp_draw<NW>(p, i, (uint32_t)g), m, gg, h);
+        const bool slow = cbp_task_hits<D, NW>(p, cbp_env_of(p, sbucket), i, (uint32_t)g, cbp_draw<NW>(p, cbp_env_of(p, sbucket), i, (uint32_t)g), m, gg, h);
         if (first) {
             asm volatile("griddepcontrol.wait;" ::: "memory");   // the previous half-sweep is complete and visible
             request();
@@ -289,9 +289,10 @@ __global__ void __launch_bounds__(128, MINB) k_checkerboard_poisson_persist2(con
         uint32_t m[2][4], gg[2][4], h[2][4];
         bool slow[2];
         // both Philox chains in one basic block: their rounds interleave (each chain alone waits on its own latency)
-        const cbp_words<NW> rw0 = cbp_draw<NW>(p, i, (uint32_t)g0), rw1 = cbp_draw<NW>(p, i, (uint32_t)(g0 + Gh));
-        slow[0] = cbp_task_hits<D, NW>(p, sbucket, i, (uint32_t)g0, rw0, m[0], gg[0], h[0]);
-        slow[1] = cbp_task_hits<D, NW>(p, sbucket, i, (uint32_t)(g0 + Gh), rw1, m[1], gg[1], h[1]);
+        const cbp_env env = cbp_env_of(p, sbucket);
+        const cbp_words<NW> rw0 = cbp_draw<NW>(p, env, i, (uint32_t)g0), rw1 = cbp_draw<NW>(p, env, i, (uint32_t)(g0 + Gh));
+        slow[0] = cbp_task_hits<D, NW>(p, env, i, (uint32_t)g0, rw0, m[0], gg[0], h[0]);
+        slow[1] = cbp_task_hits<D, NW>(p, env, i, (uint32_t)(g0 + Gh), rw1, m[1], gg[1], h[1]);
         if (first) {
             asm volatile("griddepcontrol.wait;" ::: "memory");
             request();

@@ -32,9 +32,25 @@ __device__ __forceinline__ void onehot128(uint32_t amt, uint32_t one, uint32_t (
     o[0] = (uint32_t)lo; o[1] = (uint32_t)(lo >> 32); o[2] = (uint32_t)hi; o[3] = (uint32_t)(hi >> 32);
 }
 
-__device__ __forceinline__ philox_out cbp_philox(const cbp_params &p, uint32_t ctr0, uint32_t c1, uint32_t c2)
+// What a task's hit generation reads besides the Philox round keys: the sweep counter and the count tables. The
+// one-half-sweep kernels fill it from the launch parameters (cbp_env_of); the multi-sweep kernel (ea_flow.cu) advances
+// the counter itself and, for a β ladder, points every 128-replica group at its own tables.
+struct cbp_env {
+    uint32_t t_lo, t_hi16;              // sweep counter: low 32 bits, (high bits) << 16
+    uint32_t tb0_0, tb0_1, tc0;         // TB0[0], TB0[1], TC[0]
+    const uint32_t *tbl;                // TA | TB0 | TB | TC (second and third tier only)
+    const uint2 *bucket;                // level-1 count lookup (shared or global memory)
+};
+__device__ __forceinline__ cbp_env cbp_env_of(const cbp_params &p, const uint2 *bucket)
 {
-    uint32_t c0 = ctr0 | p.t_hi16, c3 = p.t_lo;
+    cbp_env e;
+    e.t_lo = p.t_lo; e.t_hi16 = p.t_hi16; e.tb0_0 = p.tb0_0; e.tb0_1 = p.tb0_1; e.tc0 = p.tc0; e.tbl = p.tbl; e.bucket = bucket;
+    return e;
+}
+
+__device__ __forceinline__ philox_out cbp_philox(const cbp_params &p, const cbp_env &e, uint32_t ctr0, uint32_t c1, uint32_t c2)
+{
+    uint32_t c0 = ctr0 | e.t_hi16, c3 = e.t_lo;
 #pragma unroll
     for (int r = 0; r < 10; r++) {
         const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
@@ -52,18 +68,19 @@ struct cbp_hits { uint32_t m[4], g[4], h[4]; };
 
 // The complete procedure, as the oracle states it (rare path: the fast path's masks are discarded).
 template <int NW>
-__device__ __noinline__ cbp_hits cbp_slow(const cbp_params &p, uint32_t c1, uint32_t c2, uint32_t X0, uint32_t X1,
+__device__ __noinline__ cbp_hits cbp_slow(const cbp_params &p, const uint32_t *tbl, uint32_t t_lo, uint32_t t_hi16,
+                                          uint32_t c1, uint32_t c2, uint32_t X0, uint32_t X1,
                                           uint32_t P0, uint32_t P1, uint32_t P2, uint32_t P3, uint32_t P4, uint32_t P5)
 {
     constexpr int NS = 4 * NW - 1;
-    const uint32_t *TA = p.tbl, *TB0 = TA + CBP_KA, *TB = TB0 + CBP_KR, *TC = TB + CBP_KR;
+    const uint32_t *TA = tbl, *TB0 = TA + CBP_KA, *TB = TB0 + CBP_KR, *TC = TB + CBP_KR;
     cbp_hits r;
 #pragma unroll
     for (int w = 0; w < 4; w++) r.m[w] = r.g[w] = r.h[w] = 0u;
     uint32_t sw1 = 0, sw2 = 0, sw3 = 0, Y = 0, call = NW > 2 ? 2u : 1u;
     int used = 0; bool loaded = false;
     auto fetch = [&]() {
-        const philox_out o = philox4x32_10(call | p.t_hi16, c1, c2, p.t_lo, p.rk[0][0], p.rk[0][1]);
+        const philox_out o = philox4x32_10(call | t_hi16, c1, c2, t_lo, p.rk[0][0], p.rk[0][1]);
         if (!loaded) Y = o.x;
         sw1 = o.y; sw2 = o.z; sw3 = o.w; loaded = true; used = 0; call++;
     };
@@ -120,6 +137,18 @@ __device__ __forceinline__ uint32_t cbp_flip_planes(const uint32_t (&b)[2 * D], 
     return lop3p<0xF8>(kc, ks, s3 | g);                                       // kc | (ks & (s3 | g))
 }
 
+// The same decision in two halves for D = 3: flip = kc | tt. A caller that does not need the flip mask forms the new
+// spin word with one more LOP3, sc ^ (kc | tt), instead of two (flip, then xor).
+__device__ __forceinline__ void cbp_flip_parts(const uint32_t (&b)[6], uint32_t m, uint32_t g, uint32_t &kc, uint32_t &tt)
+{
+    const uint32_t s1 = lop3p<P_XOR3>(b[0], b[1], b[2]), k1 = lop3p<P_MAJ>(b[0], b[1], b[2]);
+    const uint32_t s2 = lop3p<P_XOR3>(b[3], b[4], b[5]), k2 = lop3p<P_MAJ>(b[3], b[4], b[5]);
+    const uint32_t s3 = lop3p<P_XOR3>(s1, s2, m), k3 = lop3p<P_MAJ>(s1, s2, m);
+    const uint32_t ks = lop3p<P_XOR3>(k1, k2, k3);
+    kc = lop3p<P_MAJ>(k1, k2, k3);
+    tt = lop3p<0xE0>(ks, s3, g);                                              // ks & (s3 | g)
+}
+
 // Spin-independent half of a task: the hit masks of (site c1, group c2). Returns true when the task left the fast
 // path (only then can h, the level-3 hits, be non-zero).
 // Three tiers. (1) The fast path above: branch free. (2) A lane with more hits than static slots would stall its whole
@@ -131,17 +160,17 @@ __device__ __forceinline__ uint32_t cbp_flip_planes(const uint32_t (&b)[2 * D], 
 // the random words of a task's fast path: call 0 = (X0, X1, P[0], P[1]), call 1 = P[2..5] when NW > 2
 template <int NW> struct cbp_words { philox_out A; uint32_t P[NW > 2 ? 6 : 2]; };
 template <int NW>
-__device__ __forceinline__ cbp_words<NW> cbp_draw(const cbp_params &p, uint32_t c1, uint32_t c2)
+__device__ __forceinline__ cbp_words<NW> cbp_draw(const cbp_params &p, const cbp_env &e, uint32_t c1, uint32_t c2)
 {
     cbp_words<NW> r;
-    r.A = cbp_philox(p, 0u, c1, c2);
+    r.A = cbp_philox(p, e, 0u, c1, c2);
     r.P[0] = r.A.z; r.P[1] = r.A.w;
-    if (NW > 2) { const philox_out B = cbp_philox(p, 1u, c1, c2); r.P[2] = B.x; r.P[3] = B.y; r.P[4] = B.z; r.P[5] = B.w; }
+    if (NW > 2) { const philox_out B = cbp_philox(p, e, 1u, c1, c2); r.P[2] = B.x; r.P[3] = B.y; r.P[4] = B.z; r.P[5] = B.w; }
     return r;
 }
 
 template <int D, int NW>
-__device__ __forceinline__ bool cbp_task_hits(const cbp_params &p, const uint2 *__restrict__ bucket, uint32_t c1, uint32_t c2,
+__device__ __forceinline__ bool cbp_task_hits(const cbp_params &p, const cbp_env &env, uint32_t c1, uint32_t c2,
                                               const cbp_words<NW> &rw, uint32_t (&m)[4], uint32_t (&g)[4], uint32_t (&h)[4],
                                               bool *warp_slow = nullptr)
 {
@@ -150,10 +179,10 @@ __device__ __forceinline__ bool cbp_task_hits(const cbp_params &p, const uint2 *
     uint32_t P[6] = { 0u, 0u, 0u, 0u, 0u, 0u };
 #pragma unroll
     for (int q = 0; q < (NW > 2 ? 6 : 2); q++) P[q] = rw.P[q];
-    const uint2 e = bucket[A.x >> 22];
+    const uint2 e = env.bucket[A.x >> 22];
     const uint32_t a = e.y + (A.x > e.x ? 1u : 0u);            // level-1 count (>= 64: ambiguous bucket, slow path)
     bool slow = a > (uint32_t)NS;
-    if (D >= 2) slow = slow || A.y > p.tb0_1;
+    if (D >= 2) slow = slow || A.y > env.tb0_1;
     const uint32_t one = p.one;                                  // 1, opaque to ptxas: keeps amt·1 - 32w an IMAD (fma pipe)
     const uint32_t kv = (128u - a) * 0x01010101u;
     uint32_t f[NW];
@@ -163,7 +192,7 @@ __device__ __forceinline__ bool cbp_task_hits(const cbp_params &p, const uint2 *
         f[q] = lop3p<0xD8>(P[q], X, q == NW - 1 ? 0x00808080u : 0x80808080u); // (P & ~mask) | (X & mask)
     }
     // last static slot: first level-2 hit, valid iff b >= 1
-    if (D >= 2) { if (!(A.y > p.tb0_0)) f[NW - 1] |= 0x80000000u; else f[NW - 1] &= 0x7fffffffu; }
+    if (D >= 2) { if (!(A.y > env.tb0_0)) f[NW - 1] |= 0x80000000u; else f[NW - 1] &= 0x7fffffffu; }
     else f[NW - 1] |= 0x80000000u;
     uint32_t acc[4][2] = { { 0u, 0u }, { 0u, 0u }, { 0u, 0u }, { 0u, 0u } };
 #pragma unroll
@@ -190,8 +219,8 @@ __device__ __forceinline__ bool cbp_task_hits(const cbp_params &p, const uint2 *
     const bool any_slow = __any_sync(__activemask(), slow);   // warp-uniform: some lane left the fast path
     if (warp_slow) *warp_slow = any_slow;
     if (any_slow) {
-        const uint32_t *TA = p.tbl, *TB0 = TA + CBP_KA, *TB = TB0 + CBP_KR, *TC = TB + CBP_KR;
-        const philox_out S = cbp_philox(p, NW > 2 ? 2u : 1u, c1, c2);   // first overflow call: Y, then twelve byte slots
+        const uint32_t *TA = env.tbl, *TB0 = TA + CBP_KA, *TB = TB0 + CBP_KR, *TC = TB + CBP_KR;
+        const philox_out S = cbp_philox(p, env, NW > 2 ? 2u : 1u, c1, c2);   // first overflow call: Y, then twelve byte slots
         uint32_t na = 0, nb = 0, nc = 0;
         bool full = false;
         if (slow) {
@@ -203,12 +232,12 @@ __device__ __forceinline__ bool cbp_task_hits(const cbp_params &p, const uint2 *
             }
             na = at > (uint32_t)NS ? at - (uint32_t)NS : 0u;
             if (D >= 2) {
-                uint32_t b = A.y > p.tb0_0 ? 1u : 0u;
-                if (D == 3 && A.y > p.tc0) {      // level-3 hits: their count from X1, the level-2 count from Y
+                uint32_t b = A.y > env.tb0_0 ? 1u : 0u;
+                if (D == 3 && A.y > env.tc0) {      // level-3 hits: their count from X1, the level-2 count from Y
                     nc = 1u; while (A.y > TC[nc]) nc++;
                     b = 0u; while (S.x > TB[b]) b++;
                     if (b == 0u) { g[0] = g[1] = g[2] = g[3] = 0u; }   // the static level-2 slot was not a hit after all
-                } else if (A.y > p.tb0_1) { b = 2u; while (A.y > TB0[b]) b++; }
+                } else if (A.y > env.tb0_1) { b = 2u; while (A.y > TB0[b]) b++; }
                 nb = b > 1u ? b - 1u : 0u;
             }
             if (na + nb + nc > 12u) full = true;
@@ -235,7 +264,7 @@ __device__ __forceinline__ bool cbp_task_hits(const cbp_params &p, const uint2 *
 #pragma unroll
         for (int w = 0; w < 4; w++) m[w] = acc[w][0] | acc[w][1] | g[w] | xm[w];
         if (full) {
-            const cbp_hits r = cbp_slow<NW>(p, c1, c2, A.x, A.y, P[0], P[1], P[2], P[3], P[4], P[5]);
+            const cbp_hits r = cbp_slow<NW>(p, env.tbl, env.t_lo, env.t_hi16, c1, c2, A.x, A.y, P[0], P[1], P[2], P[3], P[4], P[5]);
 #pragma unroll
             for (int w = 0; w < 4; w++) { m[w] = r.m[w]; g[w] = r.g[w]; h[w] = r.h[w]; }
         }

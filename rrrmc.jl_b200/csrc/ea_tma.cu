@@ -188,9 +188,10 @@ __global__ void __launch_bounds__(NCONS + 32, MINB) k_checkerboard_tma(const __g
         uint32_t m[2][4], gg[2][4], h[2][4];
         bool slow[2], wslow[2];      // wslow: warp-uniform "some lane of the warp left the fast path" (only then can h be set)
         // both Philox chains in one basic block: their rounds interleave
-        const cbp_words<NW> rw0 = cbp_draw<NW>(p, i0, grp), rw1 = cbp_draw<NW>(p, i1, grp);
-        slow[0] = cbp_task_hits<D, NW>(p, sbucket, i0, grp, rw0, m[0], gg[0], h[0], &wslow[0]);
-        slow[1] = cbp_task_hits<D, NW>(p, sbucket, i1, grp, rw1, m[1], gg[1], h[1], &wslow[1]);
+        const cbp_env env = cbp_env_of(p, sbucket);
+        const cbp_words<NW> rw0 = cbp_draw<NW>(p, env, i0, grp), rw1 = cbp_draw<NW>(p, env, i1, grp);
+        slow[0] = cbp_task_hits<D, NW>(p, env, i0, grp, rw0, m[0], gg[0], h[0], &wslow[0]);
+        slow[1] = cbp_task_hits<D, NW>(p, env, i1, grp, rw1, m[1], gg[1], h[1], &wslow[1]);
         if (k == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
         mbar_wait(full, (k >> 1) & 1);
 #pragma unroll
@@ -233,6 +234,278 @@ __global__ void __launch_bounds__(NCONS + 32, MINB) k_checkerboard_tma(const __g
             const uint32_t idx = (j ? i1 : i0) * W4 + grp;
             spins4[idx] = make_uint4(sc[0], sc[1], sc[2], sc[3]);
             if (flips4) flips4[idx] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-sweep kernel: every half-sweep of a run in ONE launch.
+//
+// The per-colour launches above cost a launch boundary per half-sweep: blocks drain, the next grid's blocks run their
+// prologue and wait for their first brick (measured: 1.5 of 16.3 µs per half-sweep at L = 64, R = 1024). Here the grid
+// is persistent and co-resident (cooperative launch), block b owns bricks b, b + grid, ... of EVERY half-sweep, and a
+// brick of half-sweep h is loaded as soon as the seven bricks it reads (itself and its six face neighbours) have
+// completed half-sweep h - 1: done[brick] counts the half-sweeps completed on a brick since the state was created.
+// The same condition orders the writes: a neighbour overwrites the halo a brick reads only in half-sweep h + 1, which
+// it starts after this brick has published h. No deadlock: the oldest unfinished half-sweep always has a brick whose
+// neighbours are complete, blocks walk their bricks in order, and every block is resident.
+//
+// Roles of a block: warps 0-7 consumers (as above); warp 8 lane 0 issuer (waits for the gate and for a free stage, then
+// fence.proxy.async and the TMA loads); warp 9 lane 0 publisher (waits until the 256 consumers have stored a brick —
+// mbarrier, release.cta/acquire.cta — then st.release.gpu of the brick's counter; cumulativity makes the consumers'
+// stores visible before the counter); warp 10 lane 0 gatekeeper (polls the counters a brick depends on with relaxed
+// loads, one acquire fence, then opens the gate in shared memory). Three lanes because each of the three costs an L2
+// round trip or a gpu-scope fence per brick (measured together: as long as a brick's compute), and because a block
+// that waits for a neighbour must still publish — the neighbour may in turn wait for THIS block's counter. Results are bit-identical to the per-colour launches: same
+// Philox counters (site, group, sweep), same procedure.
+constexpr int NFLOW = NCONS + 128;      // + one warpgroup of helpers: issuer, publisher and gatekeeper warps (the fourth idles)
+constexpr int FLOW_REGS_HELPER = 32, FLOW_REGS_CONSUMER = 104;   // setmaxnreg: 2 blocks x 384 threads start with 80 each
+constexpr int SMF_BARS = SM_BUCKET + CBP_BUCKETS * 8;      // full[2] | empty[2] | stored[4] | published
+constexpr int SMEMF_BYTES = SMF_BARS + 128;
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *a)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *a)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t *a, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_volatile(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_volatile(uint32_t a, uint32_t v)
+{
+    asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+
+template <int NW, int MINB, bool PERGROUP, bool FLIPS>
+__global__ void __launch_bounds__(NFLOW, MINB) k_checkerboard_flow(const __grid_constant__ cbf_params F)
+{
+    constexpr int D = 3;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const cbt_params &P = F.T;
+    const cbp_params &p = P.p;
+    const int t = threadIdx.x, L = p.L;
+    const uint32_t sm0 = smem_u32(smem);
+    const uint32_t bars = sm0 + SMF_BARS;                // full[s] +8s, empty[s] +16+8s, stored[i] +32+8i, published +64
+    const uint32_t pub = bars + 64, gate = bars + 72;
+    uint2 *sbucket = reinterpret_cast<uint2 *>(smem + SM_BUCKET);
+    if (!PERGROUP) for (int k = t; k < CBP_BUCKETS; k += NFLOW) sbucket[k] = __ldg(p.bucket + k);
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; s++) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 16 + 8 * s, NCONS); }
+#pragma unroll
+        for (int i = 0; i < 4; i++) mbar_init(bars + 32 + 8 * i, NCONS);
+        sts_volatile(pub, 0u);
+        sts_volatile(gate, 0u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const int total = P.nbricks * P.nslab, grid = (int)gridDim.x;
+    const int nk = (total - (int)blockIdx.x + grid - 1) / grid;          // bricks of this block per half-sweep (>= 1)
+    const uint32_t nhalf = F.nhalf;
+
+    if (t >= NCONS) {
+        // the helpers need few registers: hand the rest of the warpgroup's share to the consumers
+        if (MINB == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(FLOW_REGS_HELPER));
+        if (t & 31) return;
+        if (t == NCONS) {
+            // ---------------- issuer: waits for the gate and the stage, then sends the brick's bulk copies ----------------
+            uint32_t q = 0;
+            const uint4 *ent = reinterpret_cast<const uint4 *>(F.bricks + blockIdx.x);
+            uint4 e0 = __ldg(ent);
+            for (uint32_t hs = 0; hs < nhalf; hs++) {
+                const int colour = (int)((F.half0 + hs) & 1ull);
+                for (int k = 0; k < nk; k++, q++) {
+                    const int s = (int)(q & 1u);
+                    const uint32_t sb = sm0 + s * STAGE_BYTES, full = bars + 8 * s, empty = bars + 16 + 8 * s;
+                    if (hs > 0u) {
+                        while ((int32_t)(lds_volatile(gate) - (q + 1u)) < 0) __nanosleep(64);
+                        asm volatile("fence.acq_rel.cta;" ::: "memory");          // the gatekeeper's acquire, handed on
+                        asm volatile("fence.proxy.async.global;" ::: "memory");   // the neighbours' generic-proxy stores, then TMA reads
+                    }
+                    if (q >= 2u) mbar_wait(empty, ((q >> 1) - 1u) & 1u);
+                    if (q >= 3u) while ((int32_t)(lds_volatile(pub) - (q - 2u)) < 0) { }   // the publisher is at most 3 bricks behind
+                    const int slab = (int)e0.y, b = (int)e0.z;
+                    const int x0 = (int)(e0.w & 1023u), y0 = (int)((e0.w >> 10) & 1023u), z0 = (int)(e0.w >> 20);
+                    {
+                        const int kn = k + 1 < nk ? k + 1 : 0;
+                        e0 = __ldg(reinterpret_cast<const uint4 *>(F.bricks + ((int)blockIdx.x + kn * grid)));
+                    }
+                    mbar_expect_tx(full, TX_BYTES);
+                    const bool wrap_lo = y0 == 0, wrap_hi = y0 + BY == L;
+                    if (!wrap_lo && !wrap_hi) tma_load5(sb + PLANE_BYTES, &F.m_y6z, full, 0, slab, x0, y0 - 1, z0);   // four planes, one box
+                    else {
+#pragma unroll
+                        for (int zz = 0; zz < BZ; zz++) {
+                            const uint32_t dst = sb + (zz + 1) * PLANE_BYTES;
+                            const int z = z0 + zz;
+                            if (wrap_lo) tma_load5(dst, &P.m_y1, full, 0, slab, x0, L - 1, z);
+                            if (wrap_hi) tma_load5(dst + 5 * BX * ROWB, &P.m_y1, full, 0, slab, x0, 0, z);
+                            if (wrap_lo && wrap_hi) tma_load5(dst + BX * ROWB, &P.m_y4, full, 0, slab, x0, y0, z);
+                            else if (wrap_lo) tma_load5(dst + BX * ROWB, &P.m_y5, full, 0, slab, x0, y0, z);
+                            else tma_load5(dst, &P.m_y5, full, 0, slab, x0, y0 - 1, z);
+                        }
+                    }
+                    tma_load5(sb + BX * ROWB, &P.m_y4, full, 0, slab, x0, y0, z0 == 0 ? L - 1 : z0 - 1);
+                    tma_load5(sb + (BZ + 1) * PLANE_BYTES + BX * ROWB, &P.m_y4, full, 0, slab, x0, y0, z0 + BZ == L ? 0 : z0 + BZ);
+                    tma_load5(sb + XF_OFF, &P.m_xf, full, 0, slab, x0 == 0 ? L - 1 : x0 - 1, y0, z0);
+                    tma_load5(sb + XF_OFF + XF_BYTES, &P.m_xf, full, 0, slab, x0 + BX == L ? 0 : x0 + BX, y0, z0);
+                    bulk_load(sb + JM_OFF, P.jbrick + ((size_t)colour * P.nbricks + b) * (NACT * 2), NACT * 32, full);
+                }
+            }
+        } else if (t == NCONS + 32) {
+            // ---------------- publisher ----------------
+            uint32_t q = 0;
+            for (uint32_t hs = 0; hs < nhalf; hs++)
+                for (int k = 0; k < nk; k++, q++) {
+                    mbar_wait(bars + 32 + 8 * (q & 3u), (q >> 2) & 1u);
+                    st_release_gpu(F.done + ((int)blockIdx.x + k * grid), F.epoch0 + hs + 1u);
+                    sts_volatile(pub, q + 1u);
+                }
+        } else if (t == NCONS + 64) {
+            // ---------------- gatekeeper: opens the gate for bricks whose seven counters have arrived ----------------
+            // Up to two bricks per round: their 14 relaxed loads are in flight together and ONE acquire fence covers
+            // the bricks that passed (a poll is an L2 round trip, ~1600 cycles under load, the fence ~1400: per brick
+            // they would take most of a brick's compute time; the counters are normally satisfied several bricks ahead).
+            const uint32_t nq = nhalf * (uint32_t)nk;
+            uint32_t gq = (uint32_t)nk, ghs = 1u; int gk = 0;
+            while (gq < nq) {
+                uint32_t v[2][7], need[2]; bool valid[2];
+                {
+                    uint32_t hs = ghs; int k = gk;
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        valid[j] = gq + (uint32_t)j < nq;
+                        need[j] = F.epoch0 + hs;
+                        const uint4 *ent = reinterpret_cast<const uint4 *>(F.bricks + ((int)blockIdx.x + k * grid));
+                        const uint4 e1 = __ldg(ent + 1), e2 = __ldg(ent + 2);
+                        const uint32_t ids[7] = { e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, e2.z };
+#pragma unroll
+                        for (int i = 0; i < 7; i++) v[j][i] = valid[j] ? ld_relaxed_gpu(F.done + ids[i]) : need[j];
+                        if (++k == nk) { k = 0; hs++; }
+                    }
+                }
+                int n = 0;
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    int32_t worst = 0;
+#pragma unroll
+                    for (int i = 0; i < 7; i++) worst = min(worst, (int32_t)(v[j][i] - need[j]));
+                    if (valid[j] && worst >= 0 && n == j) n = j + 1;
+                }
+                if (n == 0) { __nanosleep(200); continue; }     // at the frontier: do not compete with the consumers for issue slots
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                gq += (uint32_t)n;
+                for (int j = 0; j < n; j++) if (++gk == nk) { gk = 0; ghs++; }
+                sts_volatile(gate, gq);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers: thread = (active-site slot s and s + 32, group g8) ----------------
+    if (MINB == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(FLOW_REGS_CONSUMER));
+    const int g8 = t & 7, sl = t >> 3;
+    const int xh = sl & 3, y = (sl >> 2) & 3, z = sl >> 4;
+    const uint32_t offxf = XF_OFF + (uint32_t)(y + BY * z) * ROWB + g8 * 16;
+    constexpr int DZ2 = 2 * PLANE_BYTES, DXF2 = 2 * BY * ROWB;
+    const uint32_t jmo = JM_OFF + (uint32_t)sl * 32;
+    const uint32_t LL2 = 2u * (uint32_t)L * (uint32_t)L;
+    const uint32_t W4 = (uint32_t)p.W >> 2;
+    uint4 *const spins4 = reinterpret_cast<uint4 *>(p.spins);
+    uint4 *const flips4 = reinterpret_cast<uint4 *>(p.flips);
+
+    cbp_env env = cbp_env_of(p, sbucket);
+    uint32_t cur_slab = 0xffffffffu;
+    uint2 org = __ldg(reinterpret_cast<const uint2 *>(F.bricks + blockIdx.x));
+    uint32_t q = 0;
+    for (uint32_t hs = 0; hs < nhalf; hs++) {
+        const uint64_t half = F.half0 + hs;
+        const int colour = (int)(half & 1ull);
+        env.t_lo = (uint32_t)(half >> 1); env.t_hi16 = (uint32_t)(half >> 33) << 16;
+        const int x = 2 * xh + ((y + z + colour) & 1);                        // brick origins are even in y and z
+        const uint32_t offc = (uint32_t)(x + BX * ((y + 1) + (BY + 2) * (z + 1))) * ROWB + g8 * 16;
+        const uint32_t xm0 = x > 0 ? offc - ROWB : offxf, xm1 = x > 0 ? offc - ROWB + DZ2 : offxf + DXF2;
+        const uint32_t xp0 = x < BX - 1 ? offc + ROWB : offxf + XF_BYTES, xp1 = x < BX - 1 ? offc + ROWB + DZ2 : offxf + XF_BYTES + DXF2;
+        const uint32_t soff = (uint32_t)x + (uint32_t)L * ((uint32_t)y + (uint32_t)L * (uint32_t)z);
+        for (int k = 0; k < nk; k++, q++) {
+            const int s = (int)(q & 1u);
+            const uint32_t sb = sm0 + s * STAGE_BYTES, full = bars + 8 * s, empty = bars + 16 + 8 * s;
+            const uint32_t i0 = org.x + soff, i1 = i0 + LL2;
+            const uint32_t grp = org.y * 8u + (uint32_t)g8;
+            if (PERGROUP && org.y != cur_slab) {
+                cur_slab = org.y;
+                const cbp_group *G = F.groups + grp;
+                env.tb0_0 = __ldg(&G->tb0_0); env.tb0_1 = __ldg(&G->tb0_1); env.tc0 = __ldg(&G->tc0);
+                env.tbl = G->tbl; env.bucket = F.gbucket + (size_t)grp * CBP_BUCKETS;
+            }
+            {   // table entry of the next brick of this block (the first one again after the last of a half-sweep)
+                const int kn = k + 1 < nk ? k + 1 : 0;
+                org = __ldg(reinterpret_cast<const uint2 *>(F.bricks + ((int)blockIdx.x + kn * grid)));
+            }
+            uint32_t m[2][4], gg[2][4], h[2][4];
+            bool slow[2], wslow[2];
+            const cbp_words<NW> rw0 = cbp_draw<NW>(p, env, i0, grp), rw1 = cbp_draw<NW>(p, env, i1, grp);
+            slow[0] = cbp_task_hits<D, NW>(p, env, i0, grp, rw0, m[0], gg[0], h[0], &wslow[0]);
+            slow[1] = cbp_task_hits<D, NW>(p, env, i1, grp, rw1, m[1], gg[1], h[1], &wslow[1]);
+            mbar_wait(full, (q >> 1) & 1u);
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const uint32_t a0 = sb + offc - PLANE_BYTES, axm = sb + (j ? xm1 : xm0), axp = sb + (j ? xp1 : xp0), aj = sb + jmo;
+                uint4 c, v[6], ja; uint2 jb;
+                if (j == 0) {
+                    c = lds128<PLANE_BYTES>(a0);
+                    v[0] = lds128<0>(axp); v[1] = lds128<0>(axm);
+                    v[2] = lds128<PLANE_BYTES + BX * ROWB>(a0); v[3] = lds128<PLANE_BYTES - BX * ROWB>(a0);
+                    v[4] = lds128<2 * PLANE_BYTES>(a0); v[5] = lds128<0>(a0);
+                    ja = lds128<0>(aj); jb = lds64<16>(aj);
+                } else {
+                    c = lds128<DZ2 + PLANE_BYTES>(a0);
+                    v[0] = lds128<0>(axp); v[1] = lds128<0>(axm);
+                    v[2] = lds128<DZ2 + PLANE_BYTES + BX * ROWB>(a0); v[3] = lds128<DZ2 + PLANE_BYTES - BX * ROWB>(a0);
+                    v[4] = lds128<DZ2 + 2 * PLANE_BYTES>(a0); v[5] = lds128<DZ2>(a0);
+                    ja = lds128<32 * 32>(aj); jb = lds64<32 * 32 + 16>(aj);
+                    mbar_arrive(empty);                      // this thread has read everything it needs from the stage
+                }
+                const uint32_t neg[6] = { ja.x, ja.y, ja.z, ja.w, jb.x, jb.y };
+                uint32_t sc[4] = { c.x, c.y, c.z, c.w }, bp[4][2 * D], kc[4], tt[4], ns[4];
+#pragma unroll
+                for (int qq = 0; qq < 2 * D; qq++) {
+                    bp[0][qq] = lop3p<P_XOR3>(sc[0], v[qq].x, neg[qq]); bp[1][qq] = lop3p<P_XOR3>(sc[1], v[qq].y, neg[qq]);
+                    bp[2][qq] = lop3p<P_XOR3>(sc[2], v[qq].z, neg[qq]); bp[3][qq] = lop3p<P_XOR3>(sc[3], v[qq].w, neg[qq]);
+                }
+                // flip = kc | tt (cbp_flip_parts); the new word is formed straight from the two halves: sc ^ (kc | tt)
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    cbp_flip_parts(bp[w], m[j][w], gg[j][w], kc[w], tt[w]);
+                    ns[w] = lop3p<0x1E>(sc[w], kc[w], tt[w]);
+                }
+                if (wslow[j]) {                              // a uniform branch, taken by ~13 % of the warps at β = 1
+                    asm volatile("" ::: "memory");
+                    if (slow[j]) {
+#pragma unroll
+                        for (int w = 0; w < 4; w++) { tt[w] |= h[j][w]; ns[w] = lop3p<0x1E>(sc[w], kc[w], tt[w]); }   // a level-3 hit flips its lane whatever the bonds say
+                    }
+                }
+                const uint32_t idx = (j ? i1 : i0) * W4 + grp;
+                spins4[idx] = make_uint4(ns[0], ns[1], ns[2], ns[3]);
+                if (FLIPS) flips4[idx] = make_uint4(kc[0] | tt[0], kc[1] | tt[1], kc[2] | tt[2], kc[3] | tt[3]);
+            }
+            mbar_arrive(bars + 32 + 8 * (q & 3u));           // both words of this thread are stored (release.cta)
         }
     }
 }
@@ -317,7 +590,11 @@ bool checkerboard_tma_eligible(const rrrmc_state *s)
 
 void checkerboard_tma_free(rrrmc_state *s)
 {
-    if (s->tma) { cudaFree(s->tma->d_jbrick); cudaFree(s->tma->d_origin); delete s->tma; s->tma = nullptr; }
+    if (s->tma) {
+        cudaFree(s->tma->d_jbrick); cudaFree(s->tma->d_origin); cudaFree(s->tma->d_bricks); cudaFree(s->tma->d_done);
+        cudaFree(s->tma->d_groups); cudaFree(s->tma->d_gbucket);
+        delete s->tma; s->tma = nullptr;
+    }
 }
 
 // Fills the TMA half of the launch parameters: tensor maps over the state's spin array (encoded once per state) and
@@ -338,7 +615,8 @@ rrrmc_status_t checkerboard_tma_prepare(rrrmc_state *s, const cbp_params &p, cbt
             (st = encode_map(enc, &c->m_y5, s->d_spins, L, W, BX, BY + 1, 1)) != RRRMC_OK ||
             (st = encode_map(enc, &c->m_y4, s->d_spins, L, W, BX, BY, 1)) != RRRMC_OK ||
             (st = encode_map(enc, &c->m_y1, s->d_spins, L, W, BX, 1, 1)) != RRRMC_OK ||
-            (st = encode_map(enc, &c->m_xf, s->d_spins, L, W, 1, BY, BZ)) != RRRMC_OK) { delete c; return st; }
+            (st = encode_map(enc, &c->m_xf, s->d_spins, L, W, 1, BY, BZ)) != RRRMC_OK ||
+            (st = encode_map(enc, &c->m_y6z, s->d_spins, L, W, BX, BY + 2, BZ)) != RRRMC_OK) { delete c; return st; }
         c->nbx = L / BX; c->nby = L / BY; c->nbricks = c->nbx * c->nby * (L / BZ);
         const size_t n = (size_t)2 * c->nbricks * NACT;
         if (cudaMalloc(&c->d_jbrick, n * 32) != cudaSuccess) { delete c; rrrmc_set_error("cudaMalloc of the brick-ordered bond masks failed"); return RRRMC_ERR_CUDA; }
@@ -352,11 +630,40 @@ rrrmc_status_t checkerboard_tma_prepare(rrrmc_state *s, const cbp_params &p, cbt
                 const int X = b % c->nbx, Y = (b / c->nbx) % c->nby, Z = b / (c->nbx * c->nby);
                 org[(size_t)slab * c->nbricks + b] = make_uint2((uint32_t)(X * BX) + (uint32_t)L * ((uint32_t)(Y * BY) + (uint32_t)L * (uint32_t)(Z * BZ)), (uint32_t)slab);
             }
+        // the multi-sweep kernel's table: position and face neighbours of every brick, and its progress counter.
+        // Its launch order FOLDS the z layers (0, nbz-1, 1, nbz-2, ...): block b owns ranks b, b + grid, ... and all
+        // blocks move through their lists at about the same pace, so a brick's neighbours should sit at about the
+        // same rank — in natural order the periodic wrap would make the first bricks of a half-sweep wait for the
+        // last bricks of the previous one. Folded, neighbouring bricks are at most three layers apart in rank.
+        const int nbz = L / BZ, layer = c->nbx * c->nby;
+        std::vector<cbf_brick> bt(org.size());
+        auto rank = [&](int slab, int xx, int yy, int zz) {
+            xx = (xx + c->nbx) % c->nbx; yy = (yy + c->nby) % c->nby; zz = (zz + nbz) % nbz;
+            const int zr = zz < (nbz + 1) / 2 ? 2 * zz : 2 * (nbz - 1 - zz) + 1;
+            return (uint32_t)(slab * c->nbricks + zr * layer + xx + c->nbx * yy);
+        };
+        for (int slab = 0; slab < W / 32; slab++)
+            for (int b = 0; b < c->nbricks; b++) {
+                const int X = b % c->nbx, Y = (b / c->nbx) % c->nby, Z = b / layer;
+                cbf_brick &e = bt[rank(slab, X, Y, Z)];
+                e.site0 = org[(size_t)slab * c->nbricks + b].x; e.slab = (uint32_t)slab; e.b = (uint32_t)b;
+                e.xyz = (uint32_t)(X * BX) | (uint32_t)(Y * BY) << 10 | (uint32_t)(Z * BZ) << 20;
+                e.nbr[0] = rank(slab, X + 1, Y, Z); e.nbr[1] = rank(slab, X - 1, Y, Z);
+                e.nbr[2] = rank(slab, X, Y + 1, Z); e.nbr[3] = rank(slab, X, Y - 1, Z);
+                e.nbr[4] = rank(slab, X, Y, Z + 1); e.nbr[5] = rank(slab, X, Y, Z - 1);
+                e.nbr[6] = e.nbr[7] = rank(slab, X, Y, Z);
+            }
         if (cudaMalloc(&c->d_origin, org.size() * sizeof(uint2)) != cudaSuccess ||
+            cudaMalloc(&c->d_bricks, bt.size() * sizeof(cbf_brick)) != cudaSuccess ||
+            cudaMalloc(&c->d_done, bt.size() * sizeof(uint32_t)) != cudaSuccess ||
             cudaMemcpyAsync(c->d_origin, org.data(), org.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(c->d_bricks, bt.data(), bt.size() * sizeof(cbf_brick), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemsetAsync(c->d_done, 0, bt.size() * sizeof(uint32_t), ctx->stream) != cudaSuccess ||
             cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
-            cudaFree(c->d_jbrick); cudaFree(c->d_origin); delete c; rrrmc_set_error("upload of the brick table failed"); return RRRMC_ERR_CUDA;
+            cudaFree(c->d_jbrick); cudaFree(c->d_origin); cudaFree(c->d_bricks); cudaFree(c->d_done); delete c;
+            rrrmc_set_error("upload of the brick table failed"); return RRRMC_ERR_CUDA;
         }
+        c->epoch = 0;
         s->tma = c;
     }
     const cb_tma_store *c = s->tma;
@@ -375,5 +682,94 @@ rrrmc_status_t launch_checkerboard_tma(rrrmc_ctx *ctx, cbt_params &P, int colour
     ctx->launches++;
     RR_CUDA(e);
     RR_CUDA(cudaGetLastError());
+    return RRRMC_OK;
+}
+
+namespace {
+
+template <int NW, int MINB, bool PERGROUP, bool FLIPS>
+cudaError_t flow_one(const cbf_params &F, int sm_count, cudaStream_t st)
+{
+    static int configured = 0;
+    auto kern = k_checkerboard_flow<NW, MINB, PERGROUP, FLIPS>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMF_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NFLOW, SMEMF_BYTES);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        configured = occ;
+    }
+    const int total = F.T.nbricks * F.T.nslab;
+    int grid = sm_count * configured;            // every block must be resident: the launch is cooperative
+    if (F.T.p.variant & 128) grid = 2;           // tests: many bricks per block
+    if (grid > total) grid = total;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NFLOW); cfg.dynamicSmemBytes = SMEMF_BYTES; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, F);
+}
+template <int MINB, bool PERGROUP, bool FLIPS>
+cudaError_t flow_nw(const cbf_params &F, int sm_count, cudaStream_t st)
+{
+    switch (F.T.p.NW) {
+    case 1: return flow_one<1, MINB, PERGROUP, FLIPS>(F, sm_count, st);
+    case 2: return flow_one<2, MINB, PERGROUP, FLIPS>(F, sm_count, st);
+    case 4: return flow_one<4, MINB, PERGROUP, FLIPS>(F, sm_count, st);
+    default: return flow_one<6, MINB, PERGROUP, FLIPS>(F, sm_count, st);
+    }
+}
+
+} // namespace
+
+rrrmc_status_t launch_checkerboard_flow(rrrmc_state *s, cbt_params &P, uint64_t sweep0, int64_t nsweeps,
+                                        const cbp_group *groups, const uint2 *gbucket, int ngroups)
+{
+    rrrmc_ctx *ctx = s->g->ctx;
+    cb_tma_store *c = s->tma;
+    if (!c || !c->d_bricks) { rrrmc_set_error("launch_checkerboard_flow: the state has no brick table"); return RRRMC_ERR_STATE; }
+    if (groups) {
+        if (ngroups != (int)(s->W / 4)) { rrrmc_set_error("β ladder tables: expected %d groups, given %d", (int)(s->W / 4), ngroups); return RRRMC_ERR_ARG; }
+        if (c->ngroups_alloc < ngroups) {
+            cudaFree(c->d_groups); cudaFree(c->d_gbucket); c->d_groups = nullptr; c->d_gbucket = nullptr; c->ngroups_alloc = 0;
+            RR_CUDA(cudaMalloc(&c->d_groups, sizeof(cbp_group) * ngroups));
+            RR_CUDA(cudaMalloc(&c->d_gbucket, sizeof(uint2) * CBP_BUCKETS * ngroups));
+            c->ngroups_alloc = ngroups;
+        }
+        RR_CUDA(cudaMemcpyAsync(c->d_groups, groups, sizeof(cbp_group) * ngroups, cudaMemcpyHostToDevice, ctx->stream));
+        RR_CUDA(cudaMemcpyAsync(c->d_gbucket, gbucket, sizeof(uint2) * CBP_BUCKETS * ngroups, cudaMemcpyHostToDevice, ctx->stream));
+        RR_CUDA(cudaStreamSynchronize(ctx->stream));   // caller buffers
+    }
+    cbf_params F;
+    memset(&F, 0, sizeof F);
+    F.T = P; F.m_y6z = c->m_y6z; F.bricks = c->d_bricks; F.done = c->d_done;
+    F.groups = groups ? c->d_groups : nullptr; F.gbucket = groups ? c->d_gbucket : nullptr;
+    const bool flips = P.p.flips != nullptr;
+    const int mb = P.p.variant & 3;
+    int64_t left = nsweeps;
+    uint64_t sw = sweep0;
+    while (left > 0) {
+        const int64_t n = left < (1 << 22) ? left : (1 << 22);      // keeps the counters far from wrapping inside one launch
+        F.epoch0 = c->epoch; F.nhalf = (uint32_t)(2 * n); F.half0 = 2 * sw;
+        cudaError_t e;
+        if (groups) e = flips ? flow_nw<2, true, true>(F, ctx->sm_count, ctx->stream) : flow_nw<2, true, false>(F, ctx->sm_count, ctx->stream);
+        else if (mb == 1) e = flips ? flow_nw<1, false, true>(F, ctx->sm_count, ctx->stream) : flow_nw<1, false, false>(F, ctx->sm_count, ctx->stream);
+        else e = flips ? flow_nw<2, false, true>(F, ctx->sm_count, ctx->stream) : flow_nw<2, false, false>(F, ctx->sm_count, ctx->stream);
+        ctx->launches++;
+        if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+            // the counters are only meaningful after a complete launch: start over
+            cudaMemsetAsync(c->d_done, 0, sizeof(uint32_t) * (size_t)c->nbricks * (s->W / 32), ctx->stream); c->epoch = 0;
+            RR_CUDA(e);
+            return RRRMC_ERR_CUDA;
+        }
+        c->epoch += F.nhalf;
+        left -= n; sw += (uint64_t)n;
+    }
     return RRRMC_OK;
 }

@@ -178,14 +178,19 @@ def test_checkerboard_tma_bit_exact_vs_cpu_model(L, R, beta, NW, monkeypatch):
     nsw = 4 if L <= 16 else 2
     got, want, launches = _poisson_run_vs_oracle(L, R, beta, NW, nsw, 0xC0FFEE1234, (1 << 33) + 3)
     assert got == want
-    assert launches in (2 * nsw, 2 * nsw + 1)       # two colour launches per sweep (+ the one-off bond-mask reorder)
+    assert launches in (1, 2)                        # ONE launch of the multi-sweep kernel (+ the one-off bond-mask reorder)
+    # the per-colour TMA launches (bit 12 forbids the multi-sweep kernel): two launches per sweep, same trajectory
+    monkeypatch.setenv("RRRMC_CB_VARIANT", "4096")
+    got1, _, launches1 = _poisson_run_vs_oracle(L, R, beta, NW, nsw, 0xC0FFEE1234, (1 << 33) + 3)
+    assert got1 == want
+    assert launches1 in (2 * nsw, 2 * nsw + 1)
     # the cp.async kernels (TMA forbidden) give the same trajectory
     monkeypatch.setenv("RRRMC_CB_VARIANT", "2048")
     got2, _, _ = _poisson_run_vs_oracle(L, R, beta, NW, nsw, 0xC0FFEE1234, (1 << 33) + 3)
     assert got2 == want
 
 
-@pytest.mark.parametrize("variant", ["128", "1", "32", "129"])
+@pytest.mark.parametrize("variant", ["128", "1", "129", "4224", "4097", "4128", "4225"])
 def test_checkerboard_tma_kernel_variants_agree(variant, monkeypatch):
     """TMA kernel with two blocks only (every block walks 16 bricks through its two-stage ring: stage reuse, barrier
     phases), one block per SM, and without programmatic dependent launch."""
@@ -204,7 +209,7 @@ def test_checkerboard_persist2_multibrick_bit_exact(variant, NW, monkeypatch):
     assert got == want
 
 
-@pytest.mark.parametrize("variant", [None, "2048"])
+@pytest.mark.parametrize("variant", [None, "4096", "2048"])
 def test_checkerboard_poisson_full_size_bit_exact(variant, monkeypatch):
     """BASELINE configs[1] at size: L = 64, D = 3, R = 1024, β = 1, NW = 2 (what bench.py runs), two sweeps against
     orc_checkerboard_sweeps_poisson — the TMA kernel (2048 bricks over 296 blocks: ~7 bricks per block) and the
