@@ -67,6 +67,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
                  "@!p bra W_%=;\n\t}" :: "r"(bar), "r"(parity) : "memory");
 }
+// the helper lanes' wait: backs off between polls, so that a lane that waits for most of a brick's time does not
+// compete with the consumer warps of its scheduler for issue slots (measured: 58 polls per brick without it)
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity)
+{
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(128);
+    }
+}
 __device__ __forceinline__ void tma_load5(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3, int c4)
 {
     asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
@@ -337,8 +350,8 @@ __global__ void __launch_bounds__(NFLOW, MINB) k_checkerboard_flow(const __grid_
                         asm volatile("fence.acq_rel.cta;" ::: "memory");          // the gatekeeper's acquire, handed on
                         asm volatile("fence.proxy.async.global;" ::: "memory");   // the neighbours' generic-proxy stores, then TMA reads
                     }
-                    if (q >= 2u) mbar_wait(empty, ((q >> 1) - 1u) & 1u);
-                    if (q >= 3u) while ((int32_t)(lds_volatile(pub) - (q - 2u)) < 0) { }   // the publisher is at most 3 bricks behind
+                    if (q >= 2u) mbar_wait_sleep(empty, ((q >> 1) - 1u) & 1u);
+                    if (q >= 3u) while ((int32_t)(lds_volatile(pub) - (q - 2u)) < 0) __nanosleep(64);   // the publisher is at most 3 bricks behind
                     const int slab = (int)e0.y, b = (int)e0.z;
                     const int x0 = (int)(e0.w & 1023u), y0 = (int)((e0.w >> 10) & 1023u), z0 = (int)(e0.w >> 20);
                     {
@@ -372,7 +385,7 @@ __global__ void __launch_bounds__(NFLOW, MINB) k_checkerboard_flow(const __grid_
             uint32_t q = 0;
             for (uint32_t hs = 0; hs < nhalf; hs++)
                 for (int k = 0; k < nk; k++, q++) {
-                    mbar_wait(bars + 32 + 8 * (q & 3u), (q >> 2) & 1u);
+                    mbar_wait_sleep(bars + 32 + 8 * (q & 3u), (q >> 2) & 1u);
                     st_release_gpu(F.done + ((int)blockIdx.x + k * grid), F.epoch0 + hs + 1u);
                     sts_volatile(pub, q + 1u);
                 }
@@ -407,7 +420,7 @@ __global__ void __launch_bounds__(NFLOW, MINB) k_checkerboard_flow(const __grid_
                     for (int i = 0; i < 7; i++) worst = min(worst, (int32_t)(v[j][i] - need[j]));
                     if (valid[j] && worst >= 0 && n == j) n = j + 1;
                 }
-                if (n == 0) { __nanosleep(200); continue; }     // at the frontier: do not compete with the consumers for issue slots
+                if (n == 0) { __nanosleep(400); continue; }     // at the frontier: do not compete with the consumers for issue slots
                 asm volatile("fence.acq_rel.gpu;" ::: "memory");
                 gq += (uint32_t)n;
                 for (int j = 0; j < n; j++) if (++gk == nk) { gk = 0; ghs++; }
