@@ -270,6 +270,14 @@ rrrmc_status_t rrrmc_checkerboard_poisson_tables(const uint64_t *thr64, int nthr
 int rrrmc_checkerboard_poisson_nw(const uint32_t *tbl, double tol);
 rrrmc_status_t rrrmc_checkerboard_sweeps_poisson(rrrmc_state_t *s, const uint32_t *tbl, int tbl_len, int NW,
                                                  uint64_t seed, uint64_t sweep0, int64_t nsweeps);
+/* The same sweeps on a β ladder: tbls[ngroups][160], one table set per group of 128 consecutive replicas (ngroups =
+ * replicas / 128), one NW for all (the warmest group's). Same Philox counters and procedure as the one-β entry: a group
+ * evolves exactly as it would in a one-β batch with its table. Runs on the multi-sweep brick kernel only (D = 3, L a
+ * multiple of 8, replicas a multiple of 1024), else RRRMC_ERR_UNSUPPORTED. This is what rrrmc_standard_mc runs when
+ * beta[] differs between groups (parallel tempering on the checkerboard schedule; the reference tempers by running one
+ * standardMC per β, RRRMC.jl:81-127). CPU restatement: oracle/rrrmc_oracle.c:orc_checkerboard_sweeps_poisson_ladder. */
+rrrmc_status_t rrrmc_checkerboard_sweeps_poisson_ladder(rrrmc_state_t *s, const uint32_t *tbls, int ngroups, int NW,
+                                                        uint64_t seed, uint64_t sweep0, int64_t nsweeps);
 
 /* Checkerboard Metropolis for continuous couplings: GraphEANormal (EA.jl:534-680) on the replica batch (ea_normal.cu).
  * Per (site, replica): ΔE = -2·lf with lf accumulated in Float64 in the slot order of energy() (EA.jl:590-603), i.e. the

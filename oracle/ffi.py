@@ -117,6 +117,8 @@ def lib():
         "orc_cb_sparse_tables": (None, [p(np.uint64), i32, p(np.uint32)]),
         "orc_checkerboard_sweeps_poisson": (None, [i32, i32, i64, p(np.uint32), p(np.int8), p(np.uint32), i32,
                                                    C.c_uint64, C.c_uint64, i64, vp]),
+        "orc_checkerboard_sweeps_poisson_ladder": (None, [i32, i32, i64, p(np.uint32), p(np.int8), p(np.uint32), i32,
+                                                          C.c_uint64, C.c_uint64, i64, vp]),
         "orc_cb_poisson_tables": (None, [p(np.uint64), i32, p(np.uint32)]),
         "orc_checkerboard_sweeps_f64": (None, [i32, i32, i64, p(np.uint32), p(np.int64), p(np.float64), p(np.float64),
                                                C.c_uint64, C.c_uint64, i64, vp]),
@@ -504,6 +506,15 @@ def checkerboard_sweeps_poisson(L, D, R, spins, Jfwd, tbl, NW, seed, sweep0, nsw
     assert len(tbl) == CBP_LEN and NW in (1, 2, 4, 6)
     lib().orc_checkerboard_sweeps_poisson(L, D, R, spins, np.ascontiguousarray(Jfwd, np.int8),
                                           np.ascontiguousarray(tbl, np.uint32), NW, seed, sweep0, nsweeps, acc_p)
+
+
+def checkerboard_sweeps_poisson_ladder(L, D, R, spins, Jfwd, tbls, NW, seed, sweep0, nsweeps, accepted=None):
+    """The same procedure on a β ladder: tbls[G][CBP_LEN], one table set per 128-replica group."""
+    acc_p = accepted.ctypes.data if accepted is not None else None
+    tbls = np.ascontiguousarray(tbls, np.uint32)
+    assert tbls.shape == ((R + 127) // 128, CBP_LEN) and NW in (1, 2, 4, 6)
+    lib().orc_checkerboard_sweeps_poisson_ladder(L, D, R, spins, np.ascontiguousarray(Jfwd, np.int8), tbls, NW, seed, sweep0,
+                                                 nsweeps, acc_p)
 
 
 def checkerboard_sweeps_f64(L, D, R, spins, A, J, beta, seed, sweep0, nsweeps, accepted=None):

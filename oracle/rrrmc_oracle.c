@@ -1697,13 +1697,14 @@ void orc_cb_poisson_tables(const uint64_t *thr, int D, uint32_t *tbl)
     orc_poisson_table(128.0L * (lam[2] - lam[3]), (long double)TC[0] + 1.0L, TC[0], TB0, ORC_CBP_KR);
 }
 
-void orc_checkerboard_sweeps_poisson(int L, int D, int64_t R, uint32_t *spins, const int8_t *Jfwd,
-                                     const uint32_t *tbl, int NW, uint64_t seed, uint64_t sweep0, int64_t nsweeps,
-                                     int64_t *accepted)
+/* tbl_stride = 0: one β, every 128-replica group reads tbl; tbl_stride = ORC_CBP_KA + 3 ORC_CBP_KR: a β ladder, group g
+   reads tbl + g * tbl_stride (same Philox counters, same procedure, its own count tables) */
+static void orc_checkerboard_sweeps_poisson_impl(int L, int D, int64_t R, uint32_t *spins, const int8_t *Jfwd,
+                                                 const uint32_t *tbl, int64_t tbl_stride, int NW, uint64_t seed, uint64_t sweep0,
+                                                 int64_t nsweeps, int64_t *accepted)
 {
     int64_t N = 1; for (int d = 0; d < D; d++) N *= L;
     int64_t W = R / 32, G = (R + 127) / 128;
-    const uint32_t *TA = tbl, *TB0 = TA + ORC_CBP_KA, *TB = TB0 + ORC_CBP_KR, *TC = TB + ORC_CBP_KR;
     const int NS = 4 * NW - 1;
     for (int64_t sw = 0; sw < nsweeps; sw++) {
         uint64_t t = sweep0 + (uint64_t)sw;
@@ -1721,6 +1722,7 @@ void orc_checkerboard_sweeps_poisson(int L, int D, int64_t R, uint32_t *spins, c
                     stride *= L;
                 }
                 for (int64_t g = 0; g < G; g++) {
+                    const uint32_t *TA = tbl + g * tbl_stride, *TB0 = TA + ORC_CBP_KA, *TB = TB0 + ORC_CBP_KR, *TC = TB + ORC_CBP_KR;
                     int lvl[128];   /* highest level of a hit on the lane, 0 = none */
                     memset(lvl, 0, sizeof lvl);
                     orc_pstream st;
@@ -1770,6 +1772,20 @@ void orc_checkerboard_sweeps_poisson(int L, int D, int64_t R, uint32_t *spins, c
                 }
             }
     }
+}
+
+void orc_checkerboard_sweeps_poisson(int L, int D, int64_t R, uint32_t *spins, const int8_t *Jfwd,
+                                     const uint32_t *tbl, int NW, uint64_t seed, uint64_t sweep0, int64_t nsweeps,
+                                     int64_t *accepted)
+{
+    orc_checkerboard_sweeps_poisson_impl(L, D, R, spins, Jfwd, tbl, 0, NW, seed, sweep0, nsweeps, accepted);
+}
+/* β ladder: tbls[G][ORC_CBP_KA + 3 ORC_CBP_KR], one table set per 128-replica group */
+void orc_checkerboard_sweeps_poisson_ladder(int L, int D, int64_t R, uint32_t *spins, const int8_t *Jfwd,
+                                            const uint32_t *tbls, int NW, uint64_t seed, uint64_t sweep0, int64_t nsweeps,
+                                            int64_t *accepted)
+{
+    orc_checkerboard_sweeps_poisson_impl(L, D, R, spins, Jfwd, tbls, ORC_CBP_KA + 3 * ORC_CBP_KR, NW, seed, sweep0, nsweeps, accepted);
 }
 
 /* ------------------------------------------------------------------------------------------

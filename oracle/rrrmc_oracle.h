@@ -183,6 +183,10 @@ void orc_cb_sparse_tables(const uint64_t *thr, int D, uint32_t *tbl);
 void orc_checkerboard_sweeps_poisson(int L, int D, int64_t R, uint32_t *spins, const int8_t *Jfwd,
                                      const uint32_t *tbl, int NW, uint64_t seed, uint64_t sweep0, int64_t nsweeps,
                                      int64_t *accepted /* [R] += */);
+/* β ladder: one table set per 128-replica group, tbls[G][ORC_CBP_LEN] */
+void orc_checkerboard_sweeps_poisson_ladder(int L, int D, int64_t R, uint32_t *spins, const int8_t *Jfwd,
+                                            const uint32_t *tbls, int NW, uint64_t seed, uint64_t sweep0, int64_t nsweeps,
+                                            int64_t *accepted /* [R] += */);
 void orc_cb_poisson_tables(const uint64_t *thr, int D, uint32_t *tbl);
 
 /* checkerboard Metropolis for continuous couplings (GraphEANormal): CPU model of csrc/ea_normal.cu */

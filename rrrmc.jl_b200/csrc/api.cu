@@ -1032,6 +1032,20 @@ extern "C" int rrrmc_checkerboard_poisson_nw(const uint32_t *tbl, double tol)
     return 0;
 }
 
+// level-1 count lookup on the top 10 bits of the uniform: inside bucket e the count is a0 + (x > T); a bucket that holds
+// two or more table entries stores {2^32-1, 64 + a0} (count >= a0: second tier)
+static void cbp_build_bucket(const uint32_t *TA, uint2 *bk)
+{
+    for (uint32_t e = 0; e < (uint32_t)CBP_BUCKETS; e++) {
+        const uint32_t lo = e << 22, hi = lo + ((1u << 22) - 1u);
+        uint32_t below = 0, inside = 0, T = 0xffffffffu;
+        for (int k = 0; k < CBP_KA; k++) {
+            if (TA[k] < lo) below++;
+            else if (TA[k] < hi) { inside++; T = TA[k]; }
+        }
+        bk[e] = inside <= 1 ? make_uint2(T, below) : make_uint2(0xffffffffu, 64u + below);   // ambiguous: base count only
+    }
+}
 static rrrmc_status_t fill_cbp_params(rrrmc_state *s, const uint32_t *tbl, int tbl_len, int NW, uint64_t seed, cbp_params &p)
 {
     rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
@@ -1068,15 +1082,7 @@ static rrrmc_status_t fill_cbp_params(rrrmc_state *s, const uint32_t *tbl, int t
     if (!ctx->d_cbp_bucket) RR_CUDA(cudaMalloc(&ctx->d_cbp_bucket, sizeof(uint2) * CBP_BUCKETS));
     if (ctx->cbp_bucket_key.size() != (size_t)CBP_KA || memcmp(ctx->cbp_bucket_key.data(), TA, sizeof(uint32_t) * CBP_KA) != 0) {
         std::vector<uint2> bk(CBP_BUCKETS);
-        for (uint32_t e = 0; e < (uint32_t)CBP_BUCKETS; e++) {
-            const uint32_t lo = e << 22, hi = lo + ((1u << 22) - 1u);
-            uint32_t below = 0, inside = 0, T = 0xffffffffu;
-            for (int k = 0; k < CBP_KA; k++) {
-                if (TA[k] < lo) below++;
-                else if (TA[k] < hi) { inside++; T = TA[k]; }
-            }
-            bk[e] = inside <= 1 ? make_uint2(T, below) : make_uint2(0xffffffffu, 64u + below);   // ambiguous: base count only
-        }
+        cbp_build_bucket(TA, bk.data());
         RR_CUDA(cudaStreamSynchronize(ctx->stream));   // no launch may still be reading the previous lookup
         RR_CUDA(cudaMemcpy(ctx->d_cbp_bucket, bk.data(), sizeof(uint2) * CBP_BUCKETS, cudaMemcpyHostToDevice));
         ctx->cbp_bucket_key.assign(TA, TA + CBP_KA);
@@ -1090,6 +1096,8 @@ static rrrmc_status_t fill_cbp_params(rrrmc_state *s, const uint32_t *tbl, int t
 struct cbp_run {
     cbp_params p;
     cbt_params *tma = nullptr;      // non-null: launch the TMA kernel
+    std::vector<cbp_group> groups;  // β ladder: one table set per 128-replica group (multi-sweep kernel only)
+    std::vector<uint2> gbucket;
     ~cbp_run() { delete tma; }
 };
 static rrrmc_status_t prepare_poisson_run(rrrmc_state *s, const uint32_t *tbl, int tbl_len, int NW, uint64_t seed, cbp_run &run)
@@ -1119,8 +1127,49 @@ static rrrmc_status_t run_sweep_poisson(rrrmc_state *s, cbp_run &run, uint64_t t
 // the per-colour launches for A/B timing and tests), else two launches per sweep.
 static rrrmc_status_t run_sweeps_poisson(rrrmc_state *s, cbp_run &run, uint64_t t0, int64_t n)
 {
+    if (!run.groups.empty())
+        return launch_checkerboard_flow(s, *run.tma, t0, n, run.groups.data(), run.gbucket.data(), (int)run.groups.size());
     if (run.tma && !(run.p.variant & 4096)) return launch_checkerboard_flow(s, *run.tma, t0, n, nullptr, nullptr, 0);
     for (int64_t k = 0; k < n; k++) RR_TRY(run_sweep_poisson(s, run, t0 + (uint64_t)k));
+    return RRRMC_OK;
+}
+// β ladder: tbls[ngroups][CBP_LEN], one validated table set per 128-replica group. Only the multi-sweep TMA kernel
+// reads per-group tables (3D, L a multiple of 8, whole 1024-replica slabs).
+static rrrmc_status_t prepare_poisson_ladder(rrrmc_state *s, const uint32_t *tbls, int ngroups, int NW, uint64_t seed, cbp_run &run)
+{
+    RR_ARG(ngroups == (int)((s->W + 3) / 4), "expected one table set per 128-replica group (%d), given %d", (int)((s->W + 3) / 4), ngroups);
+    if (!checkerboard_tma_eligible(s)) {
+        rrrmc_set_error("a β ladder on the checkerboard schedule needs the brick kernel: D=3, L a multiple of 8, replicas a multiple of 1024 "
+                        "(given L=%d, D=%d, R=%lld)", s->g->L, s->g->D, (long long)s->R);
+        return RRRMC_ERR_UNSUPPORTED;
+    }
+    for (int gI = 0; gI < ngroups; gI++) {
+        cbp_params tmp;                                  // validates the group's tables (same checks as the one-β entry)
+        RR_TRY(fill_cbp_params(s, tbls + (size_t)gI * CBP_LEN, CBP_LEN, NW, seed, gI == 0 ? run.p : tmp));
+    }
+    run.tma = new cbt_params();
+    RR_TRY(checkerboard_tma_prepare(s, run.p, *run.tma));
+    run.groups.resize(ngroups); run.gbucket.resize((size_t)ngroups * CBP_BUCKETS);
+    for (int gI = 0; gI < ngroups; gI++) {
+        const uint32_t *T = tbls + (size_t)gI * CBP_LEN;
+        cbp_group &G = run.groups[gI];
+        memcpy(G.tbl, T, sizeof(uint32_t) * CBP_LEN);
+        G.tb0_0 = T[CBP_KA]; G.tb0_1 = T[CBP_KA + 1]; G.tc0 = T[CBP_KA + 2 * CBP_KR]; G.pad = 0;
+        cbp_build_bucket(T, run.gbucket.data() + (size_t)gI * CBP_BUCKETS);
+    }
+    return RRRMC_OK;
+}
+extern "C" rrrmc_status_t rrrmc_checkerboard_sweeps_poisson_ladder(rrrmc_state_t *s, const uint32_t *tbls, int ngroups, int NW,
+                                                                   uint64_t seed, uint64_t sweep0, int64_t nsweeps)
+{
+    RR_ARG(s && tbls, "NULL argument");
+    RR_ARG(nsweeps >= 0, "nsweeps must be >= 0");
+    RR_CUDA(cudaSetDevice(s->g->ctx->device));
+    RR_TRY(chain_sync_to_multispin(s));
+    cbp_run run;
+    RR_TRY(prepare_poisson_ladder(s, tbls, ngroups, NW, seed, run));
+    RR_TRY(run_sweeps_poisson(s, run, sweep0, nsweeps));
+    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
     return RRRMC_OK;
 }
 extern "C" rrrmc_status_t rrrmc_checkerboard_sweeps_poisson(rrrmc_state_t *s, const uint32_t *tbl, int tbl_len, int NW,
@@ -1245,21 +1294,27 @@ static bool cb_use_sparse(const rrrmc_opts_t *o, double p1)
     return 32.0 * p1 <= 1.5;
 }
 
-static rrrmc_status_t uniform_beta(const rrrmc_state *s, const double *beta, double *b)
+// β of every 128-replica group (the ±J acceptance procedures draw one hit count per 128-lane task, so β must be
+// constant inside a group); ladder = the groups differ
+static rrrmc_status_t group_betas(const rrrmc_state *s, const double *beta, std::vector<double> &gb, bool &ladder)
 {
     RR_ARG(beta, "beta is NULL");
+    gb.assign((size_t)((s->R + 127) / 128), 0.0);
+    ladder = false;
     for (int64_t r = 0; r < s->R; r++) {
         RR_ARG(std::isfinite(beta[r]) && beta[r] >= 0, "β must be finite and >= 0, given: %g (replica %lld)", beta[r], (long long)r);
-        if (beta[r] != beta[0]) {
-            rrrmc_set_error("per-replica β ladders are not implemented for this sampler yet (replica %lld differs)", (long long)r);
+        if (r % 128 == 0) gb[(size_t)(r / 128)] = beta[r];
+        else if (beta[r] != gb[(size_t)(r / 128)]) {
+            rrrmc_set_error("checkerboard schedule on a ±J lattice: β must be constant inside each group of 128 consecutive replicas "
+                            "(replica %lld has %g, its group %g)", (long long)r, beta[r], gb[(size_t)(r / 128)]);
             return RRRMC_ERR_UNSUPPORTED;
         }
+        if (beta[r] != beta[0]) ladder = true;
     }
-    *b = beta[0];
     return RRRMC_OK;
 }
 
-static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int64_t iters, int64_t step, uint64_t seed,
+static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, const std::vector<double> &gb, bool ladder, int64_t iters, int64_t step, uint64_t seed,
                                                rrrmc_hook_fn hook, void *user, const rrrmc_opts_t *o,
                                                double *Es, int64_t Es_cap, rrrmc_run_info_t *info)
 {
@@ -1273,6 +1328,7 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
         return RRRMC_ERR_UNSUPPORTED;
     }
     RR_TRY(chain_sync_to_multispin(s));
+    const double beta = gb[0];
     uint64_t thr[3];
     for (int c = 1; c <= g->D; c++) thr[c - 1] = fixed64(exp(-beta * 4.0 * c));
     RR_ARG(o->cb_method >= RRRMC_CB_AUTO && o->cb_method <= RRRMC_CB_POISSON, "unknown cb_method %d", o->cb_method);
@@ -1280,14 +1336,34 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
     // AUTO: poisson while its static position slots cover the level-1 hit count (β >~ 0.5), else sparse / planes
     uint32_t ptbl[CBP_LEN];
     RR_TRY(rrrmc_checkerboard_poisson_tables(thr, g->D, ptbl, CBP_LEN));
-    const int NW = rrrmc_checkerboard_poisson_nw(ptbl, 0.0);
+    int NW = rrrmc_checkerboard_poisson_nw(ptbl, 0.0);
+    std::vector<uint32_t> ltbl;                         // β ladder: one table set per group, one NW (the warmest group's)
+    if (ladder) {
+        if (o->cb_method != RRRMC_CB_AUTO && o->cb_method != RRRMC_CB_POISSON) {
+            rrrmc_set_error("a β ladder on the checkerboard schedule runs the poisson procedure only (cb_method AUTO or POISSON)");
+            return RRRMC_ERR_UNSUPPORTED;
+        }
+        ltbl.resize(gb.size() * CBP_LEN);
+        for (size_t gI = 0; gI < gb.size(); gI++) {
+            uint64_t th[3];
+            for (int c = 1; c <= g->D; c++) th[c - 1] = fixed64(exp(-gb[gI] * 4.0 * c));
+            RR_TRY(rrrmc_checkerboard_poisson_tables(th, g->D, ltbl.data() + gI * CBP_LEN, CBP_LEN));
+            const int nw = rrrmc_checkerboard_poisson_nw(ltbl.data() + gI * CBP_LEN, 0.0);
+            if (nw == 0) {
+                rrrmc_set_error("β ladder: β=%g (group %d) is too warm for the poisson procedure's static position slots", gb[gI], (int)gI);
+                return RRRMC_ERR_UNSUPPORTED;
+            }
+            if (gI == 0 || nw > NW) NW = nw;
+        }
+    }
     if (o->cb_method == RRRMC_CB_POISSON && NW == 0) {
         rrrmc_set_error("cb_method POISSON: β=%g is too warm for the procedure's static position slots (use AUTO, SPARSE or PLANES)", beta);
         return RRRMC_ERR_UNSUPPORTED;
     }
-    const bool poisson = o->cb_method == RRRMC_CB_POISSON || (o->cb_method == RRRMC_CB_AUTO && NW > 0);
+    const bool poisson = ladder || o->cb_method == RRRMC_CB_POISSON || (o->cb_method == RRRMC_CB_AUTO && NW > 0);
     const bool sparse = !poisson && cb_use_sparse(o, exp(-beta * 4.0));
-    if (poisson) RR_TRY(prepare_poisson_run(s, ptbl, CBP_LEN, NW, seed, pp));
+    if (ladder) RR_TRY(prepare_poisson_ladder(s, ltbl.data(), (int)gb.size(), NW, seed, pp));
+    else if (poisson) RR_TRY(prepare_poisson_run(s, ptbl, CBP_LEN, NW, seed, pp));
     else if (sparse) {
         uint32_t tbl[CBS_T1 + 2 * CBS_TC];
         RR_TRY(rrrmc_checkerboard_sparse_tables(thr, g->D, tbl, CBS_T1 + 2 * CBS_TC));
@@ -1320,7 +1396,7 @@ static rrrmc_status_t standard_mc_checkerboard(rrrmc_state *s, double beta, int6
             RR_TRY(run_sweeps_poisson(s, pp, (uint64_t)(sw - 1), last - sw + 1));
             sw = last;
         }
-        else if (poisson) RR_TRY(run_sweep_poisson(s, pp, (uint64_t)(sw - 1)));
+        else if (poisson) RR_TRY(run_sweeps_poisson(s, pp, (uint64_t)(sw - 1), 1));
         else if (sparse) RR_TRY(run_sweep_sparse(s, ps, (uint64_t)(sw - 1)));
         else RR_TRY(run_sweep(s, p, (uint64_t)(sw - 1)));
         if (count) RR_TRY(launch_count_lanes(ctx, s->d_flips, N, (int)s->W, s->d_acc));
@@ -1359,8 +1435,9 @@ extern "C" rrrmc_status_t rrrmc_standard_mc(rrrmc_state_t *s, const double *beta
     if (o.schedule == RRRMC_SCHED_CHECKERBOARD && s->g->kind == RRRMC_EA_F64 && s->g->L > 0)
         return standard_mc_checkerboard_f64(s, beta, iters, step, seed, hook, user, &o, Es, Es_cap, info);
     if (o.schedule == RRRMC_SCHED_CHECKERBOARD) {
-        double b; RR_TRY(uniform_beta(s, beta, &b));
-        return standard_mc_checkerboard(s, b, iters, step, seed, hook, user, &o, Es, Es_cap, info);
+        std::vector<double> gb; bool ladder = false;
+        RR_TRY(group_betas(s, beta, gb, ladder));
+        return standard_mc_checkerboard(s, gb, ladder, iters, step, seed, hook, user, &o, Es, Es_cap, info);
     }
     if (o.schedule == RRRMC_SCHED_RANDOM_SITE)
         return chain_run(s, CHAIN_STANDARD, beta, iters, step, seed, hook, user, &o, Es, Es_cap, info);

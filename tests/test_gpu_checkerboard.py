@@ -426,3 +426,53 @@ def test_full_size_properties_L64_R1024():
     for r in (2, 900):
         assert g.energy(C3.chunks[r]) == E3[r]
     assert E3.mean() < E2.mean()
+
+
+# ---- β ladder on the checkerboard schedule: one β per 128-replica group (multi-sweep brick kernel) ----
+def _ladder_tbls(betas, D=3):
+    return np.stack([_poisson_tbl(float(b), D) for b in betas])
+
+
+@pytest.mark.parametrize("L,R,betas,NW", [(8, 1024, [0.6, 0.7, 0.8, 0.9, 1.0, 1.2, 1.5, 2.0], 4),
+                                          (16, 1024, [2.0, 0.9, 1.0, 1.1, 0.8, 1.3, 1.4, 0.75], 2),
+                                          (16, 2048, list(np.linspace(0.7, 2.2, 16)), 2)])
+def test_checkerboard_ladder_bit_exact_vs_cpu_model(L, R, betas, NW, monkeypatch):
+    """Every 128-replica group runs at its own β (eight or sixteen distinct values in one batch): bit-exact against the
+    oracle's ladder restatement, and each group equals the one-β run of a batch that holds that β everywhere."""
+    monkeypatch.delenv("RRRMC_CB_VARIANT", raising=False)
+    D, nsw, seed, sweep0 = 3, 3, 0xBEEF77, 11
+    A, J = ea_instance(L, D, seed=L + 5)
+    X = rb.GraphEA(L, D, replicas=R, A=A, J=J)
+    C0 = rb.Config(X.N, R, rng=np.random.default_rng(23))
+    tbls = _ladder_tbls(betas)
+    X._upload(C0)
+    check(lib().rrrmc_checkerboard_sweeps_poisson_ladder(X._state, ptr(tbls), len(betas), NW, seed, sweep0, nsw))
+    got = X._download()
+    sp = _multispin(C0)
+    ffi.checkerboard_sweeps_poisson_ladder(L, D, R, sp, _fwd(A, J, L, D), tbls, NW, seed, sweep0, nsw)
+    assert got == _from_multispin(sp, R)
+    # group g of the ladder == group g of a one-β batch at betas[g] (same counters, same tables)
+    g = 3
+    X._upload(C0)
+    check(lib().rrrmc_checkerboard_sweeps_poisson(X._state, ptr(tbls[g]), ffi.CBP_LEN, NW, seed, sweep0, nsw))
+    one = X._download()
+    assert np.array_equal(np.asarray(got.chunks)[128 * g:128 * (g + 1)], np.asarray(one.chunks)[128 * g:128 * (g + 1)])
+
+
+def test_standard_mc_checkerboard_ladder_and_errors():
+    """standardMC(schedule=checkerboard) with a per-replica β vector: constant inside 128-replica groups runs the ladder
+    (colder groups end at lower energy); a β that changes inside a group and a lattice the brick kernel cannot take are
+    rejected with a message."""
+    L, D, R = 8, 3, 1024
+    X = rb.GraphEA(L, D, replicas=R, rng=np.random.default_rng(3))
+    betas = np.repeat(np.array([0.6, 0.7, 0.8, 0.9, 1.0, 1.2, 1.5, 2.5]), 128)
+    Es, C = rb.standardMC(X, betas, 60 * X.N, step=60 * X.N, seed=4, schedule="checkerboard", C0=rb.Config(X.N, R, rng=np.random.default_rng(5)))
+    e = np.asarray(Es)[-1].reshape(8, 128).mean(axis=1)
+    assert np.array_equal(rb.energy(X, C), np.asarray(Es)[-1])
+    assert e[0] > e[3] > e[7]
+    bad = betas.copy(); bad[5] = 0.61
+    with pytest.raises(Exception, match="constant inside each group"):
+        rb.standardMC(X, bad, X.N, schedule="checkerboard")
+    X2 = rb.GraphEA(6, 3, replicas=256, rng=np.random.default_rng(3))
+    with pytest.raises(Exception, match="brick kernel"):
+        rb.standardMC(X2, np.repeat([1.0, 1.1], 128), X2.N, schedule="checkerboard")
