@@ -279,6 +279,17 @@ rrrmc_status_t rrrmc_checkerboard_sweeps_poisson(rrrmc_state_t *s, const uint32_
 rrrmc_status_t rrrmc_checkerboard_sweeps_poisson_ladder(rrrmc_state_t *s, const uint32_t *tbls, int ngroups, int NW,
                                                         uint64_t seed, uint64_t sweep0, int64_t nsweeps);
 
+/* Parallel-tempering exchange for a β ladder laid over the 128-replica groups of a ±J GraphEA batch (tempering.cu): lane l
+ * of every group is one ladder, group g its rung at beta_group[g]. One round: energies on the device, then for the pairs
+ * (g, g+1) with g ≡ round (mod 2) and every lane l: ΔS = (β_g − β_{g+1})(E_b − E_a), accept iff ΔS <= 0 or u < exp(−ΔS)
+ * with u = 53 bits of Philox4x32-10(counter = (round_lo, round_hi, g, l), key = seed); accepted pairs exchange their
+ * configurations (β stays constant inside a group, which the ladder sweeps need). Nothing crosses PCIe but beta_group.
+ * accepted: NULL, or [ngroups-1] = exchanges accepted per pair since the last call that read them (reading synchronises).
+ * The reference has no tempering (one standardMC per β, RRRMC.jl:81-127); this is the north-star's optional swap step.
+ * CPU restatement of the decisions: oracle/rrrmc_oracle.c:orc_tempering_decide. */
+rrrmc_status_t rrrmc_tempering_exchange(rrrmc_state_t *s, const double *beta_group, int ngroups, uint64_t seed, uint64_t round,
+                                        int64_t *accepted);
+
 /* Checkerboard Metropolis for continuous couplings: GraphEANormal (EA.jl:534-680) on the replica batch (ea_normal.cu).
  * Per (site, replica): ΔE = -2·lf with lf accumulated in Float64 in the slot order of energy() (EA.jl:590-603), i.e. the
  * value delta_energy() (EA.jl:665-672) returns on freshly initialised caches, then accept(-βΔE) of RRRMC.jl:39 with a

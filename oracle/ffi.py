@@ -120,6 +120,7 @@ def lib():
         "orc_checkerboard_sweeps_poisson_ladder": (None, [i32, i32, i64, p(np.uint32), p(np.int8), p(np.uint32), i32,
                                                           C.c_uint64, C.c_uint64, i64, vp]),
         "orc_cb_poisson_tables": (None, [p(np.uint64), i32, p(np.uint32)]),
+        "orc_tempering_decide": (None, [i64, p(np.float64), p(np.float64), C.c_uint64, C.c_uint64, p(np.uint8)]),
         "orc_checkerboard_sweeps_f64": (None, [i32, i32, i64, p(np.uint32), p(np.int64), p(np.float64), p(np.float64),
                                                C.c_uint64, C.c_uint64, i64, vp]),
     }
@@ -515,6 +516,16 @@ def checkerboard_sweeps_poisson_ladder(L, D, R, spins, Jfwd, tbls, NW, seed, swe
     assert tbls.shape == ((R + 127) // 128, CBP_LEN) and NW in (1, 2, 4, 6)
     lib().orc_checkerboard_sweeps_poisson_ladder(L, D, R, spins, np.ascontiguousarray(Jfwd, np.int8), tbls, NW, seed, sweep0,
                                                  nsweeps, acc_p)
+
+
+def tempering_decide(beta_group, E, seed, round_):
+    """Exchange decisions of one tempering round -> uint8 [(G-1), 128] (CPU model of tempering.cu)."""
+    bg = np.ascontiguousarray(beta_group, np.float64)
+    E = np.ascontiguousarray(E, np.float64)
+    assert len(E) == 128 * len(bg)
+    swap = np.zeros((len(bg) - 1) * 128, np.uint8)
+    lib().orc_tempering_decide(len(bg), bg, E, seed, round_, swap)
+    return swap.reshape(len(bg) - 1, 128)
 
 
 def checkerboard_sweeps_f64(L, D, R, spins, A, J, beta, seed, sweep0, nsweeps, accepted=None):

@@ -1833,3 +1833,30 @@ void orc_checkerboard_sweeps_f64(int L, int D, int64_t R, uint32_t *spins, const
             }
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Parallel-tempering exchange decisions, CPU model of rrrmc.jl_b200/csrc/tempering.cu:k_pt_decide.
+ * A β ladder lies over the 128-replica groups of a batch: lane l of every group is one ladder, group g its rung.
+ * Pairs (g, g+1) with g ≡ round (mod 2): a = replica 128 g + l, b = replica 128 (g+1) + l,
+ *   ΔS = (β_g − β_{g+1})·(E_b − E_a); accept iff ΔS <= 0 or u < exp(−ΔS),
+ *   u = ((y:x) >> 11)·2^-53 from Philox4x32-10(counter = (round_lo, round_hi, g, l), key = seed).
+ * E[R]: energies (integers for ±J lattices, so E_b − E_a is exact). swap[(G-1)*128] = 1 where the pair exchanges.
+ * The reference has no tempering (RRRMC.jl:81-127 runs one β); this is the rule of sharding.TemperingLadder.swap.
+ * ---------------------------------------------------------------------------------------- */
+void orc_tempering_decide(int64_t G, const double *beta_group, const double *E, uint64_t seed, uint64_t round, uint8_t *swap)
+{
+    memset(swap, 0, (size_t)((G - 1) * 128));
+    for (int64_t g = (int64_t)(round & 1u); g + 1 < G; g += 2)
+        for (int l = 0; l < 128; l++) {
+            double dS = (beta_group[g] - beta_group[g + 1]) * (E[128 * (g + 1) + l] - E[128 * g + l]);
+            int acc = dS <= 0.0;
+            if (!acc) {
+                uint32_t ctr[4] = { (uint32_t)round, (uint32_t)(round >> 32), (uint32_t)g, (uint32_t)l };
+                uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) }, o[4];
+                orc_philox4x32_10(ctr, key, o);
+                double u = (double)((((uint64_t)o[1] << 32) | o[0]) >> 11) * 0x1.0p-53;
+                acc = u < exp(-dS);
+            }
+            swap[g * 128 + l] = (uint8_t)acc;
+        }
+}

@@ -196,4 +196,7 @@ void orc_checkerboard_sweeps_f64(int L, int D, int64_t R, uint32_t *spins, const
 #ifdef __cplusplus
 }
 #endif
+/* parallel-tempering exchange decisions: CPU model of csrc/tempering.cu */
+void orc_tempering_decide(int64_t G, const double *beta_group, const double *E, uint64_t seed, uint64_t round, uint8_t *swap);
+
 #endif

@@ -93,6 +93,7 @@ SIGNATURES = {
     "rrrmc_checkerboard_sweeps_poisson": (_i32, [_vp, _vp, _i32, _i32, _u64, _u64, _i64]),
     "rrrmc_checkerboard_sweeps_poisson_ladder": (_i32, [_vp, _vp, _i32, _i32, _u64, _u64, _i64]),
     "rrrmc_checkerboard_sweeps_f64": (_i32, [_vp, _vp, _u64, _u64, _i64]),
+    "rrrmc_tempering_exchange": (_i32, [_vp, _vp, _i32, _u64, _u64, _vp]),
 }
 
 _lib = None

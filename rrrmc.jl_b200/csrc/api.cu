@@ -644,6 +644,7 @@ extern "C" rrrmc_status_t rrrmc_state_destroy(rrrmc_state_t *s)
     cudaStreamSynchronize(s->g->ctx->stream);
     cudaFree(s->d_spins); cudaFree(s->d_chunks); cudaFree(s->d_ibuf); cudaFree(s->d_acc);
     cudaFree(s->d_flips); cudaFree(s->d_mask); cudaFree(s->d_q_fourK); cudaFree(s->d_beta);
+    cudaFree(s->d_pt_beta); cudaFree(s->d_pt_masks); cudaFree(s->d_pt_acc);
     chain_free(s);
     sk_dense_free(s);
     checkerboard_tma_free(s);
@@ -1046,9 +1047,9 @@ static void cbp_build_bucket(const uint32_t *TA, uint2 *bk)
         bk[e] = inside <= 1 ? make_uint2(T, below) : make_uint2(0xffffffffu, 64u + below);   // ambiguous: base count only
     }
 }
-static rrrmc_status_t fill_cbp_params(rrrmc_state *s, const uint32_t *tbl, int tbl_len, int NW, uint64_t seed, cbp_params &p)
+static rrrmc_status_t validate_cbp_tables(const rrrmc_state *s, const uint32_t *tbl, int tbl_len, int NW)
 {
-    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    const rrrmc_graph *g = s->g;
     if (!(g->kind == RRRMC_EA_PM1 && g->d_jmask)) {
         rrrmc_set_error("checkerboard sweeps need a ±J GraphEA with D<=3");
         return RRRMC_ERR_UNSUPPORTED;
@@ -1067,6 +1068,13 @@ static rrrmc_status_t fill_cbp_params(rrrmc_state *s, const uint32_t *tbl, int t
     for (int k = 1; k < CBP_KA; k++) RR_ARG(TA[k] >= TA[k - 1], "count table TA must be non-decreasing");
     if (g->D < 3) RR_ARG(TC[0] == 0xffffffffu, "D=%d has no level-3 hits: TC[0] must be 2^32-1", g->D);
     if (g->D < 2) RR_ARG(TB0[0] == 0xffffffffu && TB[0] == 0xffffffffu, "D=1 has no level-2 hits: TB0[0], TB[0] must be 2^32-1");
+    return RRRMC_OK;
+}
+static rrrmc_status_t fill_cbp_params(rrrmc_state *s, const uint32_t *tbl, int tbl_len, int NW, uint64_t seed, cbp_params &p)
+{
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    RR_TRY(validate_cbp_tables(s, tbl, tbl_len, NW));
+    const uint32_t *TA = tbl, *TB0 = TA + CBP_KA, *TC = TB0 + 2 * CBP_KR;
     memset(&p, 0, sizeof p);
     p.spins = s->d_spins; p.flips = nullptr; p.jmask = reinterpret_cast<const uint4 *>(g->d_jmask);
     p.L = g->L; p.Lh = g->L / 2; p.W = (int)s->W; p.G = (int)((s->W + 3) / 4); p.NW = NW;
@@ -1128,7 +1136,7 @@ static rrrmc_status_t run_sweep_poisson(rrrmc_state *s, cbp_run &run, uint64_t t
 static rrrmc_status_t run_sweeps_poisson(rrrmc_state *s, cbp_run &run, uint64_t t0, int64_t n)
 {
     if (!run.groups.empty())
-        return launch_checkerboard_flow(s, *run.tma, t0, n, run.groups.data(), run.gbucket.data(), (int)run.groups.size());
+        return launch_checkerboard_flow(s, *run.tma, t0, n, run.groups.data(), run.gbucket.empty() ? nullptr : run.gbucket.data(), (int)run.groups.size());
     if (run.tma && !(run.p.variant & 4096)) return launch_checkerboard_flow(s, *run.tma, t0, n, nullptr, nullptr, 0);
     for (int64_t k = 0; k < n; k++) RR_TRY(run_sweep_poisson(s, run, t0 + (uint64_t)k));
     return RRRMC_OK;
@@ -1143,13 +1151,15 @@ static rrrmc_status_t prepare_poisson_ladder(rrrmc_state *s, const uint32_t *tbl
                         "(given L=%d, D=%d, R=%lld)", s->g->L, s->g->D, (long long)s->R);
         return RRRMC_ERR_UNSUPPORTED;
     }
-    for (int gI = 0; gI < ngroups; gI++) {
-        cbp_params tmp;                                  // validates the group's tables (same checks as the one-β entry)
-        RR_TRY(fill_cbp_params(s, tbls + (size_t)gI * CBP_LEN, CBP_LEN, NW, seed, gI == 0 ? run.p : tmp));
-    }
+    for (int gI = 1; gI < ngroups; gI++) RR_TRY(validate_cbp_tables(s, tbls + (size_t)gI * CBP_LEN, CBP_LEN, NW));
+    RR_TRY(fill_cbp_params(s, tbls, CBP_LEN, NW, seed, run.p));
     run.tma = new cbt_params();
     RR_TRY(checkerboard_tma_prepare(s, run.p, *run.tma));
-    run.groups.resize(ngroups); run.gbucket.resize((size_t)ngroups * CBP_BUCKETS);
+    run.groups.resize(ngroups);
+    // the device copy of the ladder's tables survives between calls (a tempering loop sends the same ladder every round)
+    cb_tma_store *c = s->tma;
+    if (c->ladder_key.size() == (size_t)ngroups * CBP_LEN && memcmp(c->ladder_key.data(), tbls, sizeof(uint32_t) * CBP_LEN * ngroups) == 0) return RRRMC_OK;
+    run.gbucket.resize((size_t)ngroups * CBP_BUCKETS);
     for (int gI = 0; gI < ngroups; gI++) {
         const uint32_t *T = tbls + (size_t)gI * CBP_LEN;
         cbp_group &G = run.groups[gI];
@@ -1183,6 +1193,42 @@ extern "C" rrrmc_status_t rrrmc_checkerboard_sweeps_poisson(rrrmc_state_t *s, co
     RR_TRY(prepare_poisson_run(s, tbl, tbl_len, NW, seed, run));
     RR_TRY(run_sweeps_poisson(s, run, sweep0, nsweeps));
     s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
+    return RRRMC_OK;
+}
+// ---- parallel-tempering exchange on the device (tempering.cu)
+extern "C" rrrmc_status_t rrrmc_tempering_exchange(rrrmc_state_t *s, const double *beta_group, int ngroups, uint64_t seed,
+                                                   uint64_t round, int64_t *accepted)
+{
+    RR_ARG(s && beta_group, "NULL argument");
+    rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
+    if (!(g->kind == RRRMC_EA_PM1 && g->d_jcode)) {
+        rrrmc_set_error("rrrmc_tempering_exchange: implemented for ±J GraphEA lattices in the multispin layout");
+        return RRRMC_ERR_UNSUPPORTED;
+    }
+    RR_ARG(s->R % 128 == 0, "the ladder lies over whole 128-replica groups: replicas must be a multiple of 128, given %lld", (long long)s->R);
+    const int G = (int)(s->W / 4);
+    RR_ARG(ngroups == G, "expected one β per 128-replica group (%d), given %d", G, ngroups);
+    for (int k = 0; k < G; k++) RR_ARG(std::isfinite(beta_group[k]) && beta_group[k] >= 0, "β must be finite and >= 0, given: %g (group %d)", beta_group[k], k);
+    RR_CUDA(cudaSetDevice(ctx->device));
+    RR_TRY(chain_sync_to_multispin(s));
+    if (!s->d_pt_beta) {
+        RR_CUDA(cudaMalloc(&s->d_pt_beta, sizeof(double) * G));
+        RR_CUDA(cudaMalloc(&s->d_pt_masks, sizeof(uint32_t) * 4 * G));
+        RR_CUDA(cudaMalloc(&s->d_pt_acc, sizeof(long long) * G));
+        RR_CUDA(cudaMemsetAsync(s->d_pt_acc, 0, sizeof(long long) * G, ctx->stream));
+    }
+    RR_CUDA(cudaMemsetAsync(s->d_pt_masks, 0, sizeof(uint32_t) * 4 * G, ctx->stream));
+    // (a pageable source of a few bytes is staged before cudaMemcpyAsync returns: no synchronisation needed)
+    RR_CUDA(cudaMemcpyAsync(s->d_pt_beta, beta_group, sizeof(double) * G, cudaMemcpyHostToDevice, ctx->stream));
+    RR_TRY(launch_tempering_exchange(s, s->d_pt_beta, s->d_pt_masks, s->d_pt_acc, seed, round));
+    s->energy_valid = false; s->chain_valid = false; s->chain_fields_valid = false; sk_dense_invalidate(s);
+    if (accepted) {      // exchanges accepted per pair (g, g+1) since the last read; reading synchronises
+        std::vector<long long> h(G);
+        RR_CUDA(cudaMemcpyAsync(h.data(), s->d_pt_acc, sizeof(long long) * G, cudaMemcpyDeviceToHost, ctx->stream));
+        RR_CUDA(cudaMemsetAsync(s->d_pt_acc, 0, sizeof(long long) * G, ctx->stream));
+        RR_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int k = 0; k + 1 < G; k++) accepted[k] = (int64_t)h[k];
+    }
     return RRRMC_OK;
 }
 // ---- continuous couplings (GraphEANormal): per-lane Float64 checkerboard sweeps (ea_normal.cu)

@@ -74,6 +74,9 @@ struct rrrmc_state {
     uint32_t *d_flips = nullptr;     // [N][W] accept masks of the last sweep (count_accepted)
     uint32_t *d_mask = nullptr;      // [W] replica mask staging
     double *d_beta = nullptr;        // [W*32] per-replica β of the continuous-coupling checkerboard kernel
+    double *d_pt_beta = nullptr;     // tempering exchange (tempering.cu): [W/4] β of the 128-replica groups,
+    uint32_t *d_pt_masks = nullptr;  //   [W] exchange masks of the last round, [W/4] accepted exchanges per pair since the last read
+    long long *d_pt_acc = nullptr;
     bool energy_valid = false;
     // chain layout (sequential samplers): d_chunks is the spin state, one BitVector per chain
     bool ms_valid = true;            // multispin copy is current

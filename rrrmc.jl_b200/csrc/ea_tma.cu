@@ -750,14 +750,19 @@ rrrmc_status_t launch_checkerboard_flow(rrrmc_state *s, cbt_params &P, uint64_t 
     if (groups) {
         if (ngroups != (int)(s->W / 4)) { rrrmc_set_error("β ladder tables: expected %d groups, given %d", (int)(s->W / 4), ngroups); return RRRMC_ERR_ARG; }
         if (c->ngroups_alloc < ngroups) {
+            if (!gbucket) { rrrmc_set_error("launch_checkerboard_flow: no device copy of the ladder tables"); return RRRMC_ERR_STATE; }
             cudaFree(c->d_groups); cudaFree(c->d_gbucket); c->d_groups = nullptr; c->d_gbucket = nullptr; c->ngroups_alloc = 0;
             RR_CUDA(cudaMalloc(&c->d_groups, sizeof(cbp_group) * ngroups));
             RR_CUDA(cudaMalloc(&c->d_gbucket, sizeof(uint2) * CBP_BUCKETS * ngroups));
             c->ngroups_alloc = ngroups;
         }
-        RR_CUDA(cudaMemcpyAsync(c->d_groups, groups, sizeof(cbp_group) * ngroups, cudaMemcpyHostToDevice, ctx->stream));
-        RR_CUDA(cudaMemcpyAsync(c->d_gbucket, gbucket, sizeof(uint2) * CBP_BUCKETS * ngroups, cudaMemcpyHostToDevice, ctx->stream));
-        RR_CUDA(cudaStreamSynchronize(ctx->stream));   // caller buffers
+        if (gbucket) {
+            RR_CUDA(cudaMemcpyAsync(c->d_groups, groups, sizeof(cbp_group) * ngroups, cudaMemcpyHostToDevice, ctx->stream));
+            RR_CUDA(cudaMemcpyAsync(c->d_gbucket, gbucket, sizeof(uint2) * CBP_BUCKETS * ngroups, cudaMemcpyHostToDevice, ctx->stream));
+            RR_CUDA(cudaStreamSynchronize(ctx->stream));   // caller buffers
+            c->ladder_key.resize((size_t)ngroups * CBP_LEN);
+            for (int k = 0; k < ngroups; k++) memcpy(c->ladder_key.data() + (size_t)k * CBP_LEN, groups[k].tbl, sizeof(uint32_t) * CBP_LEN);
+        }
     }
     cbf_params F;
     memset(&F, 0, sizeof F);

@@ -1,6 +1,7 @@
 // Launch parameters and per-state cache of the TMA-staged checkerboard kernel (ea_tma.cu).
 #pragma once
 #include <cuda.h>
+#include <vector>
 #include "cb_params.cuh"
 
 constexpr int CBT_BX = 8, CBT_BY = 4, CBT_BZ = 4;            // brick of sites handled per pipeline stage
@@ -54,6 +55,7 @@ struct cb_tma_store {
     cbp_group *d_groups = nullptr;        // β ladder tables (uploaded per run)
     uint2 *d_gbucket = nullptr;
     int ngroups_alloc = 0;
+    std::vector<uint32_t> ladder_key;     // the tables d_groups / d_gbucket were built from
     int nbx = 0, nby = 0, nbricks = 0;
 };
 
@@ -61,7 +63,7 @@ bool checkerboard_tma_eligible(const rrrmc_state *s);
 void checkerboard_tma_free(rrrmc_state *s);
 rrrmc_status_t checkerboard_tma_prepare(rrrmc_state *s, const cbp_params &p, cbt_params &P);
 rrrmc_status_t launch_checkerboard_tma(rrrmc_ctx *ctx, cbt_params &P, int colour);
-// nsweeps whole sweeps starting with sweep counter sweep0 in one launch. groups/gbucket: host tables of a β ladder
-// (ngroups = W/4 entries) or nullptr.
+// nsweeps whole sweeps starting with sweep counter sweep0 in one launch. groups: host tables of a β ladder (ngroups =
+// W/4 entries) or nullptr; gbucket: their level-1 lookups, or nullptr when the state's device copy is current.
 rrrmc_status_t launch_checkerboard_flow(rrrmc_state *s, cbt_params &P, uint64_t sweep0, int64_t nsweeps,
                                         const cbp_group *groups, const uint2 *gbucket, int ngroups);

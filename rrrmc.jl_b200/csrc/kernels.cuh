@@ -17,3 +17,5 @@ rrrmc_status_t launch_randomize(rrrmc_state *s, uint64_t seed);
 rrrmc_status_t launch_upload_transpose(rrrmc_state *s, int64_t first, int64_t count);
 rrrmc_status_t launch_download_transpose(rrrmc_state *s, int64_t first, int64_t count);
 rrrmc_status_t launch_flush(rrrmc_ctx *ctx);
+rrrmc_status_t launch_tempering_exchange(rrrmc_state *s, const double *d_beta_group, uint32_t *d_masks, long long *d_accepted,
+                                         uint64_t seed, uint64_t round);

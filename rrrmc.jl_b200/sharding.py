@@ -174,3 +174,40 @@ def tempered_run(X, ladder, shard, rounds, iters_per_round, sampler, *, seed=1, 
             ladder.swap(t_all, rd)
             hist.append(all_gather(E_local))
     return np.array(hist), C
+
+
+def tempered_checkerboard(X, beta_group, rounds, sweeps_per_round, *, seed=1, C0=None, read_every=0):
+    """Parallel tempering of a ±J GraphEA batch on the checkerboard schedule, entirely on the device: the β ladder lies
+    over the 128-replica groups (lane l of every group is one ladder, group g its rung at beta_group[g]); a round is
+    `sweeps_per_round` ladder sweeps (one launch of the multi-sweep brick kernel, rrrmc_checkerboard_sweeps_poisson_ladder)
+    followed by rrrmc_tempering_exchange (energies, decisions and the exchange of configurations are kernels). The host
+    only launches; nothing crosses PCIe between rounds but the eight-or-so β values. Replica shards of a multi-GPU job
+    hold whole ladders, so there is no collective in the loop (reductions of the observables happen after it).
+    -> (exchanges accepted per neighbouring pair, summed over the 128 ladders; rounds attempted per pair)."""
+    from . import _ffi
+    from ._ffi import check, lib, ptr
+    st = X._ensure_state()
+    if C0 is not None:
+        X._upload(C0)
+    bg = np.ascontiguousarray(beta_group, np.float64)
+    G = len(bg)
+    D = X.D
+    tbls = np.zeros((G, _ffi.CBP_LEN), np.uint32)
+    NW = 0
+    for g in range(G):
+        thr = np.array([min(int(np.exp(-bg[g] * 4 * c) * 2.0 ** 64), 2 ** 64 - 1) for c in range(1, D + 1)], dtype=np.uint64)
+        check(lib().rrrmc_checkerboard_poisson_tables(ptr(thr), D, ptr(tbls[g]), _ffi.CBP_LEN))
+        nw = lib().rrrmc_checkerboard_poisson_nw(ptr(tbls[g]), 0.0)
+        if nw == 0:
+            raise ValueError(f"β={bg[g]} (group {g}) is too warm for the poisson procedure")
+        NW = max(NW, nw)
+    acc = np.zeros(G - 1, np.int64)
+    got = np.zeros(G - 1, np.int64)
+    for rd in range(rounds):
+        check(lib().rrrmc_checkerboard_sweeps_poisson_ladder(st, ptr(tbls), G, NW, seed, rd * sweeps_per_round, sweeps_per_round))
+        last = rd == rounds - 1 or (read_every and (rd + 1) % read_every == 0)
+        check(lib().rrrmc_tempering_exchange(st, ptr(bg), G, seed + 0x9E3779B97F4A7C15 & (2 ** 64 - 1), rd, ptr(got) if last else None))
+        if last:
+            acc += got
+    attempts = np.array([sum(1 for rd in range(rounds) if rd % 2 == g % 2) for g in range(G - 1)], np.int64) * 128
+    return acc, attempts

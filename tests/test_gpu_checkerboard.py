@@ -476,3 +476,50 @@ def test_standard_mc_checkerboard_ladder_and_errors():
     X2 = rb.GraphEA(6, 3, replicas=256, rng=np.random.default_rng(3))
     with pytest.raises(Exception, match="brick kernel"):
         rb.standardMC(X2, np.repeat([1.0, 1.1], 128), X2.N, schedule="checkerboard")
+
+
+def test_tempering_exchange_vs_cpu_model():
+    """rrrmc_tempering_exchange: the device's decisions equal orc_tempering_decide on the same energies, and accepted
+    pairs exchange exactly their configurations (both parities; counters accumulate until read)."""
+    L, D, R = 8, 3, 1024
+    X = rb.GraphEA(L, D, replicas=R, rng=np.random.default_rng(9))
+    bg = np.array([0.5, 0.6, 0.75, 0.9, 1.1, 1.3, 1.6, 2.0])
+    C0 = rb.Config(X.N, R, rng=np.random.default_rng(10))
+    X._upload(C0)
+    # a few ladder sweeps so that the energies of neighbouring groups differ in both directions
+    tbls = _ladder_tbls(bg)
+    check(lib().rrrmc_checkerboard_sweeps_poisson_ladder(X._state, ptr(tbls), 8, 4, 3, 0, 5))
+    total = np.zeros(7, np.int64)
+    for rd in (0, 1, 2):
+        before = X._download()
+        E = rb.energy(X, before)
+        want = ffi.tempering_decide(bg, E, 77, rd).astype(np.int64)
+        acc = np.zeros(7, np.int64)
+        check(lib().rrrmc_tempering_exchange(X._state, ptr(bg), 8, 77, rd, ptr(acc) if rd != 1 else None))
+        after = X._download()
+        perm = np.arange(R)
+        for g in range(7):
+            for l in np.nonzero(want[g])[0]:
+                perm[128 * g + l], perm[128 * (g + 1) + l] = perm[128 * (g + 1) + l], perm[128 * g + l]
+        assert np.array_equal(np.asarray(after.chunks), np.asarray(before.chunks)[perm])
+        total += want.sum(axis=1)
+        if rd == 0:
+            assert np.array_equal(acc, want.sum(axis=1))
+            total[:] = 0
+        if rd == 2:
+            assert np.array_equal(acc, total)      # rounds 1 and 2 together: round 1 did not read the counters
+    assert want.sum() > 0 and (1 - want[::2]).sum() > 0
+
+
+def test_tempered_checkerboard_orders_the_ladder():
+    """sharding.tempered_checkerboard: after tempering, colder rungs sit at lower energy and neighbouring rungs exchange
+    at a sensible rate."""
+    from rrrmc_b200 import sharding
+    L, D, R = 8, 3, 1024
+    X = rb.GraphEA(L, D, replicas=R, rng=np.random.default_rng(2))
+    bg = np.linspace(0.6, 1.3, 8)
+    acc, att = sharding.tempered_checkerboard(X, bg, rounds=40, sweeps_per_round=5, seed=5, C0=rb.Config(X.N, R, rng=np.random.default_rng(6)))
+    E = rb.energy(X, X._download()).reshape(8, 128).mean(axis=1)
+    assert np.all(np.diff(E) < 0)
+    rate = acc / att
+    assert np.all(rate > 0.05) and np.all(rate <= 1.0)
