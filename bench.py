@@ -253,43 +253,91 @@ def run_ours(args, rank, world, local_rank):
     iters = SWEEPS_PER_STEP * N_SITES
     gathered = [torch.empty(R_PER_GPU, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
 
-    def e2e_step(k):
-        check(lib().rrrmc_state_upload(st, 0, R_PER_GPU, h_in.data_ptr()))
+    pending = []
+
+    def e2e_step(k, phases=None):
+        t = [time.perf_counter()]
+
+        def mark():
+            if phases is not None:
+                ctx.sync()
+                t.append(time.perf_counter())
+        check(lib().rrrmc_state_upload(st, 0, R_PER_GPU, h_in.data_ptr())); mark()
         check(lib().rrrmc_standard_mc(st, ptr(betas), iters, iters, SEED + 17 * k + 1000 * rank, C.cast(None, _ffi.HOOK), None,
-                                      C.byref(opts), h_E.data_ptr(), 1, C.byref(info)))
-        check(lib().rrrmc_state_download(st, 0, R_PER_GPU, h_out.data_ptr()))
-        if world > 1:  # the observable reduction behind `hook`: per-replica energies of every rank
-            dist.all_gather(gathered, h_E[0].cuda(non_blocking=True))
+                                      C.byref(opts), h_E.data_ptr(), 1, C.byref(info))); mark()
+        check(lib().rrrmc_state_download(st, 0, R_PER_GPU, h_out.data_ptr())); mark()
+        if world > 1:  # the observable reduction behind `hook`: per-replica energies of every rank. Asynchronous: a rank does
+            # not wait for the others inside a step (the handles are waited for before the timed region ends)
+            out = [torch.empty(R_PER_GPU, dtype=torch.float64, device="cuda") for _ in range(world)]
+            pending.append((dist.all_gather(out, h_E[0].cuda(non_blocking=True), async_op=True), out))
+            if phases is not None:
+                pending[-1][0].wait(); torch.cuda.synchronize(); t.append(time.perf_counter())
+        if phases is not None:
+            names = ["h2d_upload_transpose", "standard_mc_sweeps_energy_d2h", "download_transpose_d2h", "all_gather"]
+            for n, a, b in zip(names, t[:-1], t[1:]):
+                phases[n] = phases.get(n, 0.0) + 1e3 * (b - a)
+            phases["sweep_kernels_device_ms"] = phases.get("sweep_kernels_device_ms", 0.0) + float(info.device_ms)
     e2e_step(0)
+    for w, _ in pending:
+        w.wait()
+    pending.clear()
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
         e2e_step(1 + k)
+    for w, _ in pending:
+        w.wait()
     barrier()
     t_e2e = time.perf_counter() - t0
+    pending.clear()
     if world > 1:
         t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
+    # per-phase breakdown of the end-to-end step (two extra steps outside the timed region, a sync after every phase)
+    phases = {}
+    for k in range(2):
+        e2e_step(100 + k, phases)
+    phases = {n: v / 2 for n, v in phases.items()}
+    if world > 1:
+        keys = sorted(phases)
+        t = torch.tensor([phases[n] for n in keys], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        phases = {n: float(v) for n, v in zip(keys, t.tolist())}
     e2e_value = world * attempts_per_step * args.steps / t_e2e
     assert float(h_E.mean()) < -1.0 * N_SITES, "e2e energies look wrong"
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        launch_ms = ms_total / (args.steps * 2 * SWEEPS_PER_STEP)  # two colour launches per sweep
-        achieved = (ALG_BYTES_PER_SWEEP / 2) / (launch_ms * 1e-3) / 1e9
+        # the dominant kernel's launches inside the timed region (counted by the library): ONE launch of the multi-sweep
+        # kernel per step for the poisson procedure on the brick path, two colour launches per sweep otherwise
+        launches_per_step = max(1, int(round(launches / max(1, args.steps))))
+        launch_ms = ms_total / (args.steps * launches_per_step)
+        alg_bytes_per_launch = ALG_BYTES_PER_SWEEP * SWEEPS_PER_STEP / launches_per_step
+        achieved = alg_bytes_per_launch / (launch_ms * 1e-3) / 1e9
+        flow = launches_per_step == 1
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "checkerboard_traffic.json")
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at this configuration, from the ncu
+        # capture scripts/round_check.sh takes of this very command (profiles/r2_checkerboard_traffic.json names the
+        # capture and the library it was taken with); null when the capture is of another kernel / launch shape
+        tp = os.path.join(ROOT, "profiles", "r2_checkerboard_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                if tj.get("sweeps_per_launch") == (SWEEPS_PER_STEP if flow else 0.5) and tj.get("method") == METHOD and abs(tj.get("beta", -1) - beta) < 1e-9:
+                    traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         cores = os.cpu_count() or 1
-        cpu_iters = 100_000_000  # ~10 s on the box's host cores
+        # the same sample as one step of the reference arm (bench.py --impl reference), after the same warm-up call, so
+        # that the two CPU figures of a box agree; five of them, ~10 s
+        cpu_iters = 20_000_000
         if args.no_cpu_baseline:
             cpu_iters = 1_000_000
-        cpu_v, cpu_dt = cpu_reference_rate(A, J, cpu_iters, cores)
+        cpu_reference_rate(A, J, 200_000, cores)
+        reps = 1 if args.no_cpu_baseline else 5
+        cpu_runs = [cpu_reference_rate(A, J, cpu_iters, cores) for _ in range(reps)]
+        cpu_v, cpu_dt = float(np.mean([r for r, _ in cpu_runs])), float(sum(d for _, d in cpu_runs))
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -306,15 +354,17 @@ def run_ours(args, rank, world, local_rank):
                        "accepted_counters": "off in the timed loop"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": {"poisson": ("k_checkerboard_poisson_persist2<%d,4>" if NW >= 2 else "k_checkerboard_poisson_persist<%d,3>") % NW, "sparse": "k_checkerboard_sparse<3,true>",
+                         "kernel": {"poisson": ("k_checkerboard_flow<%d,2,false,false>" if flow else "k_checkerboard_tma<%d,2>") % NW, "sparse": "k_checkerboard_sparse<3,true>",
                                     "planes": "k_checkerboard<3,true>"}[METHOD],
-                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_SWEEP // 2, "launch_ms": launch_ms,
+                         "algorithmic_bytes_per_launch": int(alg_bytes_per_launch), "launch_ms": launch_ms,
+                         "launches_per_step": launches_per_step, "sweeps_per_launch": SWEEPS_PER_STEP / launches_per_step,
                          "note": "bound by integer instruction issue (ALU pipe, ncu), not by HBM: the 32 MiB state is L2 resident (see DESIGN.md §5)"},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{cores} replicas (1/thread) x {cpu_iters} random-site attempts, same instance, beta={beta}; {cpu_dt:.1f}s"},
+                             "sample": f"{reps} x ({cores} replicas (1/thread) x {cpu_iters} random-site attempts), same instance, beta={beta}; {cpu_dt:.1f}s"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(R_PER_GPU * nch * 8),
                     "d2h_bytes_per_step": int(R_PER_GPU * nch * 8 + R_PER_GPU * 8),
-                    "api": "rrrmc_state_upload + rrrmc_standard_mc + rrrmc_state_download (host pinned buffers)"},
+                    "api": "rrrmc_state_upload + rrrmc_standard_mc + rrrmc_state_download (host pinned buffers)",
+                    "phases_ms_max_over_ranks": phases},
             "gpu_launches": int(launches),
             "clocks": clk,
             "wall_s_timed_region": t_wall,
