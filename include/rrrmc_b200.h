@@ -175,6 +175,8 @@ typedef int (*rrrmc_hook_fn)(void *user, int64_t it, const double *E, const int6
 #define RRRMC_CB_SPARSE 2 /* binomial count of passing lanes per ΔE class + uniform distinct positions       */
 #define RRRMC_CB_POISSON 3 /* Poisson hit counts per task and level + uniform positions with replacement      */
 
+#define RRRMC_PICK_REFERENCE 0
+#define RRRMC_PICK_RANK 1
 typedef struct {
     int    schedule;        /* RRRMC_SCHED_*; default RANDOM_SITE (the reference contract)           */
     int    planes_K;        /* checkerboard: full random bit planes, one Philox call each (default 5)  */
@@ -184,7 +186,12 @@ typedef struct {
     int    planes_M;        /* checkerboard: merged bit planes after the full ones, four per Philox
                                call (default 4, a multiple of 4); planes_K + planes_M <= 32. See DESIGN.md §5.          */
     int    cb_method;       /* checkerboard acceptance procedure: RRRMC_CB_AUTO (default), _PLANES, _SPARSE, _POISSON */
-    int    reserved[6];
+    int    site_pick;       /* rrrMC / bklMC: which member of the drawn ΔE class rand(1:t) picks. RRRMC_PICK_REFERENCE (default): the
+                               reference's ArraySet order (ArraySets.jl:58-85) — bit-exact with the reference-order oracle and the
+                               replay mode. RRRMC_PICK_RANK: the p-th member in site order, on the warp-cooperative kernel
+                               (chain_warp.cu: one chain per warp in shared memory; ±J GraphEA lattices): the same chain law,
+                               other trajectories; CPU model oracle/rrrmc_oracle.c:orc_rank_rrrMC / orc_rank_bklMC. */
+    int    reserved[5];
 } rrrmc_opts_t;
 rrrmc_status_t rrrmc_opts_default(rrrmc_opts_t *o);
 

@@ -106,6 +106,8 @@ def lib():
         "orc_rrrMC": (Result, [vp, f64, i64, i64, p(np.uint64), Draws, f64, f64, HOOK, vp, vp, i64]),
         "orc_bklMC": (Result, [vp, f64, i64, i64, p(np.uint64), Draws, HOOK, vp, vp, i64]),
         "orc_wtmMC": (Result, [vp, f64, i64, f64, p(np.uint64), Draws, HOOK, vp, vp, i64]),
+        "orc_rank_rrrMC": (Result, [vp, f64, i64, i64, p(np.uint64), Draws, HOOK, vp, vp, i64]),
+        "orc_rank_bklMC": (Result, [vp, f64, i64, i64, p(np.uint64), Draws, HOOK, vp, vp, i64]),
         "orc_extremal_opt": (EOResult, [vp, p(np.float64), i64, i64, p(np.uint64), vp, Draws, EOHOOK, vp, vp, i64]),
         "orc_check_discrete_cache": (i32, [vp, p(np.uint64), f64, p(np.int64), i64]),
         "orc_ds_probe": (i32, [i64, p(np.float64), i64, p(np.int64), p(np.float64), p(np.float64), p(np.float64), i64, p(np.float64), p(np.int64)]),
@@ -370,6 +372,15 @@ def rrrMC(g, beta, iters, s, src, step=1, hook=None, staged_thr=float("nan"), st
 
 def bklMC(g, beta, iters, s, src, step=1, hook=None):
     return _run(lib().orc_bklMC, g, beta, iters, step, s, src, hook)
+
+
+def rank_rrrMC(g, beta, iters, s, src, step=1, hook=None):
+    """rrrMC with the rank-select member pick (CPU model of csrc/chain_warp.cu)."""
+    return _run(lib().orc_rank_rrrMC, g, beta, iters, step, s, src, hook)
+
+
+def rank_bklMC(g, beta, iters, s, src, step=1, hook=None):
+    return _run(lib().orc_rank_bklMC, g, beta, iters, step, s, src, hook)
 
 
 def wtmMC(g, beta, samples, s, src, step=1.0, hook=None):

@@ -1860,3 +1860,164 @@ void orc_tempering_decide(int64_t G, const double *beta_group, const double *E, 
             swap[g * 128 + l] = (uint8_t)acc;
         }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Rank-select rrrMC / bklMC for GraphEA ±J: CPU model of rrrmc.jl_b200/csrc/chain_warp.cu.
+ *
+ * The same Markov chains as rrrMC (RRRMC.jl:149-219) and bklMC (RRRMC.jl:311-359) on the ΔE classes of DeltaE.jl:63-118,
+ * with two implementation choices changed so that a warp can run one chain out of shared memory:
+ *  (1) the member of class k that rand(1:t[k]) picks is the p-th member IN SITE ORDER (a rank query on the class
+ *      bitmap) instead of the p-th entry of the ArraySet (ArraySets.jl:58-85, insertion order with hole filling).
+ *      Either is a uniform pick among the t[k] members (DeltaE.jl:146-167 only needs that), so the chains have the
+ *      same law; the trajectories for a given draw stream differ from the reference-order kernels.
+ *  (2) the class weights are T[k] = t[k]·f(k) recomputed from the integer counts, their cumulative sums come from a
+ *      fixed 8-lane scan (rk_scan; missing classes count 0) and z is its last element, instead of the reference's
+ *      running sums (DeltaE.jl:184-200, 248-283), whose rounding depends on the order in which neighbours are re-filed.
+ * Everything else is the reference's: class of a site from ΔE and its spin (DeltaE.jl:108-118), f(k) = 1 for the
+ * down half, exp(-β·ΔE) for the up half (:83-95), the class scan of rand_move with its fallback (:146-167), the
+ * acceptance rand() < z/z' (RRRMC.jl:131-138; evaluated as rand()·z' < z), rand_skip (DeltaE.jl:141-144), the sampling instants of the two drivers.
+ * Draw order: rrrMC: rand() (class), rand(1:t[k]) (member), rand() (accept). bklMC: rand() (skip), rand(), rand(1:t[k]).
+ * X: an ORC_EA_INT graph with couplings ±1 (any degree 2D <= 6, allΔE = 0, 4, .., 4D or the odd-degree set).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    orc_graph *X; const uint64_t *s; int64_t N; int L, twoD;
+    int *u;          /* unsatisfied bonds of a site */
+    int *cls;        /* class 1..2L */
+    int64_t t[17]; double f[17], z;
+} rk_cache;
+static inline int rk_spin(const uint64_t *s, int64_t i) { return (int)((s[i >> 6] >> (i & 63)) & 1u); }
+static int rk_class(const rk_cache *c, int u, int sb)
+{
+    /* ΔE = 2·(satisfied − unsatisfied) = 2·(2D − 2u); class index from |ΔE| through allΔE (DeltaE.jl:108-118) */
+    double dE = 2.0 * (double)(c->twoD - 2 * u);
+    double a = dE < 0 ? -dE : dE;
+    int k = 0; while (k < c->L && c->X->DE[k] != a) k++;
+    int up = dE > 0 || (dE == 0 && sb == 1);
+    return k + 1 + c->L * up;
+}
+/* cumulative class weights cT[1..8] by the 8-lane Hillis-Steele scan the warp runs (steps 1, 2, 4): the association of
+   every partial sum is fixed by the scan, cT[8] is the tree ((T1+T2)+(T3+T4))+((T5+T6)+(T7+T8)); returns z = cT[8] */
+static double rk_scan(const rk_cache *c, const int64_t *t, double *cT)
+{
+    for (int k = 1; k <= 8; k++) cT[k] = k <= 2 * c->L ? (double)t[k] * c->f[k] : 0.0;
+    for (int o = 1; o < 8; o <<= 1)
+        for (int k = 8; k > o; k--) cT[k] = cT[k] + cT[k - o];
+    return cT[8];
+}
+static double rk_z(const rk_cache *c, const int64_t *t) { double cT[9]; return rk_scan(c, t, cT); }
+static rk_cache *rk_new(orc_graph *X, const uint64_t *s, double beta)
+{
+    rk_cache *c = (rk_cache *)calloc(1, sizeof *c);
+    c->X = X; c->s = s; c->N = X->N; c->L = X->nDE; c->twoD = X->twoD;
+    c->u = (int *)malloc((size_t)c->N * sizeof(int)); c->cls = (int *)malloc((size_t)c->N * sizeof(int));
+    for (int k = 1; k <= 2 * c->L; k++) c->f[k] = k > c->L ? exp(-beta * X->DE[k - c->L - 1]) : 1.0;
+    for (int64_t i = 0; i < c->N; i++) {
+        int u = 0, si = rk_spin(s, i);
+        for (int q = 0; q < c->twoD; q++) {
+            int64_t y = X->A[i * c->twoD + q] - 1;
+            int neg = X->Ji[i * c->twoD + q] < 0;
+            u += (si ^ rk_spin(s, y)) ^ neg;
+        }
+        c->u[i] = u; c->cls[i] = rk_class(c, u, si); c->t[c->cls[i]]++;
+    }
+    c->z = rk_z(c, c->t);
+    return c;
+}
+static void rk_free(rk_cache *c) { free(c->u); free(c->cls); free(c); }
+static int64_t rk_rand_move(rk_cache *c, orc_draws d, double *dE)   /* DeltaE.jl:146-167, member = rank in site order */
+{
+    int L = c->L;
+    double cT[9];
+    rk_scan(c, c->t, cT);
+    double r = d.f64(d.user) * c->z;
+    int k = 1, broke = 0;
+    for (; k <= 2 * L; k++) if (r < cT[k]) { broke = 1; break; }
+    if (!broke) { k = 2 * L; while (c->t[k] == 0) k--; }
+    *dE = k <= L ? -c->X->DE[k - 1] : c->X->DE[k - L - 1];
+    int64_t p = d.range(d.user, c->t[k]);
+    for (int64_t i = 0; i < c->N; i++) if (c->cls[i] == k && --p == 0) return i;
+    return -1;
+}
+/* counts after flipping `move` (nothing is modified); returns z' */
+static double rk_plan(const rk_cache *c, int64_t move, int64_t *tp)
+{
+    memcpy(tp, c->t, sizeof c->t);
+    int sm = rk_spin(c->s, move);
+    for (int q = 0; q < c->twoD; q++) {
+        int64_t y = c->X->A[move * c->twoD + q] - 1;
+        int neg = c->X->Ji[move * c->twoD + q] < 0, sy = rk_spin(c->s, y);
+        int unsat = (sm ^ sy) ^ neg;
+        int k1 = rk_class(c, c->u[y] + (unsat ? -1 : 1), sy);
+        tp[c->cls[y]]--; tp[k1]++;
+    }
+    tp[c->cls[move]]--; tp[rk_class(c, c->twoD - c->u[move], sm ^ 1)]++;
+    return rk_z(c, tp);
+}
+static void rk_commit(rk_cache *c, uint64_t *s, int64_t move, const int64_t *tp, double zp)
+{
+    int sm = rk_spin(s, move);
+    for (int q = 0; q < c->twoD; q++) {
+        int64_t y = c->X->A[move * c->twoD + q] - 1;
+        int neg = c->X->Ji[move * c->twoD + q] < 0, sy = rk_spin(s, y);
+        int unsat = (sm ^ sy) ^ neg;
+        c->u[y] += unsat ? -1 : 1;
+        c->cls[y] = rk_class(c, c->u[y], sy);
+    }
+    s[move >> 6] ^= (uint64_t)1 << (move & 63);
+    c->u[move] = c->twoD - c->u[move];
+    c->cls[move] = rk_class(c, c->u[move], sm ^ 1);
+    memcpy(c->t, tp, sizeof c->t);
+    c->z = zp;
+}
+orc_result orc_rank_rrrMC(orc_graph *X, double beta, int64_t iters, int64_t step, uint64_t *s,
+                          orc_draws d, orc_hook hook, void *user, double *Es, int64_t Es_cap)
+{
+    orc_result res = { 0, 0, 0, 0, 0 };
+    if (!isfinite(beta) || X->kind != ORC_EA_INT) { res.status = -1; return res; }
+    double E = orc_energy(X, s);
+    rk_cache *c = rk_new(X, s, beta);
+    int64_t it = 0, accepted = 0, tp[17];
+    while (it < iters) {
+        it++;
+        if (it % step == 0) {
+            PUSH_SAMPLE();
+            if (hook && !hook(user, it, E, accepted)) break;
+        }
+        double dE0, z = c->z;
+        int64_t move = rk_rand_move(c, d, &dE0);
+        double zp = rk_plan(c, move, tp);
+        if (d.f64(d.user) * zp < z) { rk_commit(c, s, move, tp, zp); E += dE0; accepted++; }   /* rand() < z/z' (RRRMC.jl:131-138), as a product */
+    }
+    rk_free(c);
+    res.iters_done = it; res.accepted = accepted; res.staged_its = it;
+    return res;
+}
+orc_result orc_rank_bklMC(orc_graph *X, double beta, int64_t iters, int64_t step, uint64_t *s,
+                          orc_draws d, orc_hook hook, void *user, double *Es, int64_t Es_cap)
+{
+    orc_result res = { 0, 0, 0, 0, 0 };
+    if (!isfinite(beta) || X->kind != ORC_EA_INT) { res.status = -1; return res; }
+    double E = orc_energy(X, s);
+    rk_cache *c = rk_new(X, s, beta);
+    int64_t it = 0, accepted = 0, nextstep = step, tp[17];
+    while (it < iters) {
+        int64_t skip = (int64_t)floor(log1p(-d.f64(d.user)) / log1p(-c->z / (double)c->N));   /* DeltaE.jl:141-144 */
+        double dE; int64_t move = rk_rand_move(c, d, &dE);
+        int out = 0;
+        while (it + skip + 1 >= nextstep) {
+            PUSH_SAMPLE();
+            if (hook && !hook(user, nextstep, E, accepted)) { out = 1; break; }
+            nextstep += step;
+            if (nextstep > iters) { out = 1; break; }
+        }
+        if (out) break;
+        double zp = rk_plan(c, move, tp);
+        rk_commit(c, s, move, tp, zp);
+        it += skip + 1;
+        E += dE;
+        accepted++;
+    }
+    rk_free(c);
+    res.iters_done = it; res.accepted = accepted;
+    return res;
+}

@@ -199,4 +199,10 @@ void orc_checkerboard_sweeps_f64(int L, int D, int64_t R, uint32_t *spins, const
 /* parallel-tempering exchange decisions: CPU model of csrc/tempering.cu */
 void orc_tempering_decide(int64_t G, const double *beta_group, const double *E, uint64_t seed, uint64_t round, uint8_t *swap);
 
+/* rank-select rrrMC / bklMC for GraphEA ±J: CPU model of csrc/chain_warp.cu (see rrrmc_oracle.c) */
+orc_result orc_rank_rrrMC(orc_graph *g, double beta, int64_t iters, int64_t step, uint64_t *chunks,
+                          orc_draws d, orc_hook hook, void *user, double *Es, int64_t Es_cap);
+orc_result orc_rank_bklMC(orc_graph *g, double beta, int64_t iters, int64_t step, uint64_t *chunks,
+                          orc_draws d, orc_hook hook, void *user, double *Es, int64_t Es_cap);
+
 #endif

@@ -12,6 +12,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4
 EA_PM1, EA_INT, EA_F64, SK_F64, SK_BIN, QT, QUANT, EMPTY, EA_DISCR = 1, 2, 3, 4, 5, 6, 7, 8, 9
 SCHED_CHECKERBOARD, SCHED_RANDOM_SITE = 0, 1
 CB_AUTO, CB_PLANES, CB_SPARSE, CB_POISSON = 0, 1, 2, 3
+PICK_REFERENCE, PICK_RANK = 0, 1
 CBP_LEN = 64 + 3 * 32   # count tables of the poisson procedure: TA[64] | TB0[32] | TB[32] | TC[32]
 CBS_T1, CBS_TC = 33, 129
 
@@ -22,7 +23,7 @@ EOHOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.PO
 class Opts(C.Structure):
     _fields_ = [("schedule", C.c_int), ("planes_K", C.c_int), ("count_accepted", C.c_int),
                 ("staged_thr", C.c_double), ("staged_thr_fact", C.c_double), ("planes_M", C.c_int), ("cb_method", C.c_int),
-                ("reserved", C.c_int * 6)]
+                ("site_pick", C.c_int), ("reserved", C.c_int * 5)]
 
 
 class RunInfo(C.Structure):

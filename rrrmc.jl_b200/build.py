@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 SO = os.path.join(LIBDIR, "librrrmc_b200.so")
-SOURCES = ["api.cu", "ea_multispin.cu", "ea_poisson.cu", "ea_tma.cu", "ea_normal.cu", "tempering.cu", "chain.cu", "chain_trace.cu", "chain_ea.cu", "sk_dense.cu"]
+SOURCES = ["api.cu", "ea_multispin.cu", "ea_poisson.cu", "ea_tma.cu", "ea_normal.cu", "tempering.cu", "chain.cu", "chain_trace.cu", "chain_ea.cu", "chain_warp.cu", "sk_dense.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=false", "-Xptxas", "-v"]
 

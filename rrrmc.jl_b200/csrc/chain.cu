@@ -447,7 +447,8 @@ static rrrmc_status_t chain_drive(rrrmc_state *s, chain_params &P, rrrmc_hook_fn
     RR_CUDA(cudaEventRecord(e0, ctx->stream));
     int64_t nsamples = 0; bool stop = false;
     for (int guard = 0; !stop; guard++) {
-        if (P.fast) RR_TRY(chain_ea_launch(s, P));
+        if (P.fast == 2) RR_TRY(chain_warp_launch(s, P));
+        else if (P.fast) RR_TRY(chain_ea_launch(s, P));
         else if constexpr (std::is_same<SRC, src_trace>::value) chain_launch_run_trace(P, grid, ctx->stream);
         else k_chain_run<SRC><<<grid, 32, 0, ctx->stream>>>(P);
         ctx->launches++;
@@ -526,7 +527,18 @@ rrrmc_status_t chain_run(rrrmc_state *s, int sampler, const double *beta, int64_
     RR_TRY(chain_energy_init(s, P, true));
     s->ms_valid = false; // chains now own the configuration
     sk_dense_invalidate(s);
-    if (chain_ea_eligible(s, sampler)) { RR_TRY(chain_ea_prepare(s, P)); s->chain_fields_valid = false; }
+    if (o->site_pick == RRRMC_PICK_RANK) {
+        if (!chain_warp_eligible(s, sampler)) {
+            rrrmc_set_error("site_pick = RANK (the warp-cooperative kernel) takes rrrMC / bklMC on a ±J GraphEA lattice with L >= 3, D <= 3 "
+                            "whose chain state fits shared memory (N <= ~110000)");
+            return RRRMC_ERR_UNSUPPORTED;
+        }
+        P.fast = 2; P.jcode = g->d_jcode; P.latL = g->L;
+        s->chain_fields_valid = false;
+    } else {
+        RR_ARG(o->site_pick == RRRMC_PICK_REFERENCE, "unknown site_pick %d", o->site_pick);
+        if (chain_ea_eligible(s, sampler)) { RR_TRY(chain_ea_prepare(s, P)); s->chain_fields_valid = false; }
+    }
     RR_TRY(chain_drive<src_philox>(s, P, hook, user, Es, Es_cap, info));
     return RRRMC_OK;
 }

@@ -88,7 +88,8 @@ struct chain_params {
     const uint8_t *tkind; const int64_t *tival; const double *tfval; int64_t tlen;
     double *wt_v; int32_t *wt_node, *wt_pos; double wt_step, wt_tmax;  // wtmMC: heap, step/N, step/N·samples
     const double *eo_ftau; int64_t eo_stride; uint64_t *eo_cmin;            // extremal_opt: fτ [N] (stride 0) or [R][N], Cmin
-    int fast;                     // 1: GraphEA ±J fast path (chain_ea.cu)
+    int fast;                     // 1: GraphEA ±J fast path (chain_ea.cu); 2: warp-cooperative rank-select kernel (chain_warp.cu)
+    const uint8_t *jcode; int latL; // chain_warp.cu: forward bond signs of the lattice, its side
     int8_t *ea_lf; uint16_t *ea_apos, *ea_av;
 };
 
@@ -96,6 +97,10 @@ struct chain_params {
 bool chain_ea_eligible(const rrrmc_state *s, int sampler);
 rrrmc_status_t chain_ea_prepare(rrrmc_state *s, chain_params &P);
 rrrmc_status_t chain_ea_launch(rrrmc_state *s, const chain_params &P);
+
+// warp-cooperative rrrMC / bklMC with the rank-select member pick (chain_warp.cu): GraphEA ±J lattices, L >= 3, D <= 3
+bool chain_warp_eligible(const rrrmc_state *s, int sampler);
+rrrmc_status_t chain_warp_launch(rrrmc_state *s, const chain_params &P);
 
 // dense GraphSKNormal kernels (sk_dense.cu): tensor-core local-field initialisation, lock-step Metropolis sweeps
 void sk_dense_free(rrrmc_state *s);

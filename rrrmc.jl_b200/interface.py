@@ -775,7 +775,7 @@ def _run(fn, X, beta, iters, seed, step, hook, C0, quiet, opts, name):
 
 
 def _opts(schedule=None, planes_K=None, count_accepted=None, staged_thr=None, staged_thr_fact=None, planes_M=None,
-          cb_method=None):
+          cb_method=None, site_pick=None):
     o = _ffi.Opts()
     check(lib().rrrmc_opts_default(C.byref(o)))
     if schedule is not None:
@@ -793,6 +793,8 @@ def _opts(schedule=None, planes_K=None, count_accepted=None, staged_thr=None, st
         o.staged_thr = staged_thr
     if staged_thr_fact is not None:
         o.staged_thr_fact = staged_thr_fact
+    if site_pick is not None:
+        o.site_pick = {"reference": _ffi.PICK_REFERENCE, "rank": _ffi.PICK_RANK}[site_pick]
     return o
 
 
@@ -813,17 +815,18 @@ def standardMC(X, β, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, q
 
 
 def rrrMC(X, β, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, staged_thr=float("nan"),
-          staged_thr_fact=5.0, quiet=False):
-    """rrrMC(X, β, iters; ...) (src/RRRMC.jl:149-219)."""
+          staged_thr_fact=5.0, quiet=False, site_pick=None):
+    """rrrMC(X, β, iters; ...) (src/RRRMC.jl:149-219). site_pick="rank" runs the warp-cooperative kernel (±J GraphEA
+    lattices; the same chain law, the member of a ΔE class is picked by rank in site order instead of ArraySet order)."""
     if not np.all(np.isfinite(β)):
         raise ValueError(f"β must be finite, given: {β}")  # RRRMC.jl:159
     return _run(lib().rrrmc_rrr_mc, X, β, iters, seed, step, hook, C0, quiet,
-                _opts(staged_thr=staged_thr, staged_thr_fact=staged_thr_fact), "rrrMC")
+                _opts(staged_thr=staged_thr, staged_thr_fact=staged_thr_fact, site_pick=site_pick), "rrrMC")
 
 
-def bklMC(X, β, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, quiet=False):
-    """bklMC(X, β, iters; ...) (src/RRRMC.jl:311-359)."""
-    return _run(lib().rrrmc_bkl_mc, X, β, iters, seed, step, hook, C0, quiet, _opts(), "bklMC")
+def bklMC(X, β, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, quiet=False, site_pick=None):
+    """bklMC(X, β, iters; ...) (src/RRRMC.jl:311-359). site_pick: see rrrMC."""
+    return _run(lib().rrrmc_bkl_mc, X, β, iters, seed, step, hook, C0, quiet, _opts(site_pick=site_pick), "bklMC")
 
 
 def wtmMC(X, β, samples, *, seed=DEFAULT_SEED, step=1.0, hook=None, C0=None, quiet=False):

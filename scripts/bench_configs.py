@@ -27,19 +27,22 @@ def emit(**kw):
 
 
 if "c3" in which:
-    L, D, R, beta = 32, 3, 256, 3.0
+    L, D, R, beta = 32, 3, int(os.environ.get("C3_R", "256")), 3.0
     X = rb.GraphEA(L, D, replicas=R, rng=np.random.default_rng(1))
     # equilibrate with checkerboard sweeps so that the low-T rejection-free samplers start from a typical state
     _, C = rb.standardMC(X, beta, 200 * X.N, step=200 * X.N, seed=1, quiet=True, schedule="checkerboard")
-    for name, fn, iters in (("rrrMC", rb.rrrMC, 200_000 if quick else 2_000_000), ("bklMC", rb.bklMC, 10_000_000 if quick else 200_000_000)):
-        fn(X, beta, iters // 20, step=iters // 20, seed=2, C0=C, quiet=True)
-        t0 = time.perf_counter()
-        Es, C2 = fn(X, beta, iters, step=iters, seed=3, C0=C, quiet=True)
-        dt = time.perf_counter() - t0
-        info = X.last_run
-        emit(config="C3", sampler=name, L=L, D=D, replicas=R, beta=beta, iters_per_replica=iters,
-             iterations_per_s=R * iters / (info.device_ms * 1e-3), executed_moves_per_s=info.accepted_total / (info.device_ms * 1e-3),
-             device_ms=info.device_ms, wall_s=dt, launches=info.launches)
+    for pick in ("reference", "rank"):      # ArraySet order on one lane (chain_ea.cu) / rank-select on a warp (chain_warp.cu)
+        for name, fn, iters in (("rrrMC", rb.rrrMC, 200_000 if quick else 2_000_000), ("bklMC", rb.bklMC, 10_000_000 if quick else 200_000_000)):
+            fn(X, beta, iters // 20, step=iters // 20, seed=2, C0=C, quiet=True, site_pick=pick)
+            t0 = time.perf_counter()
+            Es, C2 = fn(X, beta, iters, step=iters, seed=3, C0=C, quiet=True, site_pick=pick)
+            dt = time.perf_counter() - t0
+            info = X.last_run
+            emit(config="C3", sampler=name, site_pick=pick, kernel="k_chain_warp<3>" if pick == "rank" else "k_chain_ea<6>",
+                 L=L, D=D, replicas=R, beta=beta, iters_per_replica=iters,
+                 iterations_per_s=R * iters / (info.device_ms * 1e-3), executed_moves_per_s=info.accepted_total / (info.device_ms * 1e-3),
+                 us_per_move_per_chain=info.device_ms * 1e3 * R / max(1, info.accepted_total),
+                 device_ms=info.device_ms, wall_s=dt, launches=info.launches)
 
 if "c4" in which:
     N, R, beta = 4096, 512, 1.0
