@@ -11,6 +11,7 @@
 //  * Lock-step Metropolis sweeps (new engine; the reference's per-flip update_cache! SK.jl:239-276 is the axpy):
 //    all replicas attempt site i = 1..N in order; an accepted flip streams row i of J once per CTA and updates the
 //    local fields of the CTA's replicas held in shared memory.
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -313,6 +314,120 @@ __global__ void __launch_bounds__(512, 1) k_sk_lockstep(sk_ls_params P)
     if (tid < RPC && rbase + tid < P.R) { P.E[rbase + tid] = E; P.acc[rbase + tid] = nacc; }
 }
 
+// The same sweeps with the coupling rows staged by the TMA engine: row i+1 of J (N doubles, one 1-D bulk copy) lands in
+// a second shared-memory buffer while the block decides and updates site i, so the L2/HBM latency of the row — which the
+// kernel above pays in full between its two barriers of every site — is hidden behind the previous site's work.
+// Identical arithmetic and draw stream (bit-identical results). Needs N even (16-byte bulk copies) and room for two rows.
+__device__ __forceinline__ uint32_t sk_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int RPC>
+__global__ void __launch_bounds__(512, 1) k_sk_lockstep_tma(sk_ls_params P)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int N = P.N, tid = threadIdx.x, nt = blockDim.x;
+    double *Jb = reinterpret_cast<double *>(smem_raw);                     // [2][N] coupling rows
+    double *lf = Jb + 2 * (size_t)N;                                       // [RPC][N]
+    uint32_t *sp = reinterpret_cast<uint32_t *>(lf + (size_t)RPC * N);     // [RPC][nw]
+    const int nw = (N + 31) / 32;
+    __shared__ int flag[RPC];
+    __shared__ int snew[RPC];
+    __shared__ __align__(8) uint64_t bar[2];
+    const uint32_t rowbytes = (uint32_t)N * 8u;
+    const int64_t rbase = (int64_t)blockIdx.x * RPC;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(sk_smem_u32(&bar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(sk_smem_u32(&bar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (int rp = 0; rp < RPC; rp++) {
+        const int64_t r = rbase + rp;
+        for (int j = tid; j < N; j += nt) lf[(size_t)rp * N + j] = r < P.R ? P.lf[r * N + j] : 0.0;
+        for (int w = tid; w < nw; w += nt) {
+            const uint64_t c = r < P.R ? P.chunks[r * P.nchunks + (w >> 1)] : 0ull;
+            sp[rp * nw + w] = (uint32_t)(c >> ((w & 1) * 32));
+        }
+    }
+    double E = 0.0, beta = 0.0; long long nacc = 0;
+    if (tid < RPC && rbase + tid < P.R) { E = P.E[rbase + tid]; beta = P.beta[rbase + tid]; nacc = P.acc[rbase + tid]; }
+    __syncthreads();
+    auto fetch_row = [&](int row, int buf) {      // thread 0: row -> Jb[buf], completion on bar[buf]
+        const uint32_t b = sk_smem_u32(&bar[buf]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(rowbytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(sk_smem_u32(Jb + (size_t)buf * N)), "l"(P.J + (size_t)row * N), "r"(rowbytes), "r"(b) : "memory");
+    };
+    if (tid == 0) fetch_row(0, 0);
+    const long long nsteps = (long long)P.nsweeps * N;
+    long long g = 0;
+    for (int sw = 0; sw < P.nsweeps; sw++) {
+        const uint64_t t = P.sweep0 + (uint64_t)sw;
+        for (int i = 0; i < N; i++, g++) {
+            // Jb[(g+1)&1] was last read in step g-1, which ended with a barrier: request the next row now
+            if (tid == 0 && g + 1 < nsteps) fetch_row(i + 1 < N ? i + 1 : 0, (int)((g + 1) & 1));
+            if (tid < RPC) {                                   // Metropolis decision, accept() of RRRMC.jl:39
+                const int64_t r = rbase + tid;
+                int ok = 0;
+                if (r < P.R) {
+                    const double dE = lf[(size_t)tid * N + i];                      // ΔE_i = +lfields[i], SK.jl:278-284
+                    const double x = -beta * dE;
+                    if (x >= 0) ok = 1;
+                    else {
+                        const philox_out u = philox4x32_10((uint32_t)i, (uint32_t)r, (uint32_t)t, (uint32_t)(t >> 32) ^ 0x534b4c53u,
+                                                           (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+                        const double U = (double)((((uint64_t)u.y << 32) | u.x) >> 11) * 0x1.0p-53;
+                        ok = U < exp(x);
+                    }
+                    if (ok) { E += dE; nacc++; }
+                }
+                flag[tid] = ok;
+                snew[tid] = 1 ^ (int)((sp[tid * nw + (i >> 5)] >> (i & 31)) & 1u);
+            }
+            __syncthreads();
+            {   // every thread observes the row's arrival (also when no replica accepted: the barrier's phases stay in step)
+                const uint32_t b = sk_smem_u32(&bar[g & 1]), parity = (uint32_t)((g >> 1) & 1);
+                asm volatile("{\n\t.reg .pred p;\nW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra W_%=;\n\t}" :: "r"(b), "r"(parity) : "memory");
+            }
+            bool any = false;
+#pragma unroll
+            for (int rp = 0; rp < RPC; rp++) any |= flag[rp] != 0;
+            if (any) {                                         // update_cache!, SK.jl:252-265, for the accepted replicas
+                // two sites per thread and iteration (16-byte accesses); 4·(±1·J) is formed as ±(4·J): scaling by four
+                // and the sign are exact, so the sum is bit-identical to the reference's expression
+                const double2 *Ji2 = reinterpret_cast<const double2 *>(Jb + (size_t)(g & 1) * N);
+                for (int j2 = tid; j2 < N / 2; j2 += nt) {
+                    const double2 Jv = Ji2[j2];
+                    const double a0 = 4 * Jv.x, a1 = 4 * Jv.y;
+                    const int j = 2 * j2;
+#pragma unroll
+                    for (int rp = 0; rp < RPC; rp++) {
+                        if (!flag[rp]) continue;
+                        const uint32_t w = sp[rp * nw + (j >> 5)] >> (j & 31);
+                        const int s0 = snew[rp] ^ (int)(w & 1u), s1 = snew[rp] ^ (int)((w >> 1) & 1u);
+                        double2 *p = reinterpret_cast<double2 *>(&lf[(size_t)rp * N + j]);
+                        double2 v = *p;
+                        v.x = j == i ? -v.x : __dadd_rn(v.x, s0 ? -a0 : a0);
+                        v.y = j + 1 == i ? -v.y : __dadd_rn(v.y, s1 ? -a1 : a1);
+                        *p = v;
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid < RPC && flag[tid]) sp[tid * nw + (i >> 5)] ^= 1u << (i & 31);
+        }
+    }
+    __syncthreads();
+    for (int rp = 0; rp < RPC; rp++) {
+        const int64_t r = rbase + rp;
+        if (r >= P.R) continue;
+        for (int j = tid; j < N; j += nt) P.lf[r * N + j] = lf[(size_t)rp * N + j];
+        for (int c = tid; c < (int)P.nchunks; c += nt) {
+            const uint64_t lo = sp[rp * nw + 2 * c], hi = 2 * c + 1 < nw ? sp[rp * nw + 2 * c + 1] : 0u;
+            P.chunks[r * P.nchunks + c] = lo | (hi << 32);
+        }
+    }
+    if (tid < RPC && rbase + tid < P.R) { P.E[rbase + tid] = E; P.acc[rbase + tid] = nacc; }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -438,8 +553,16 @@ rrrmc_status_t sk_dense_sweeps(rrrmc_state *s, const double *beta, uint64_t seed
     const unsigned grid = div_up(s->R, rpc);
 #define LS(RP) do { RR_CUDA(cudaFuncSetAttribute(k_sk_lockstep<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
                     k_sk_lockstep<RP><<<grid, 512, smem, ctx->stream>>>(P); } while (0)
-    if (rpc == 4) LS(4); else if (rpc == 2) LS(2); else LS(1);
+    // the TMA-staged kernel when two coupling rows fit beside the fields (RRRMC_SK_VARIANT=1 keeps the plain loads)
+    const size_t smem_tma = smem + 2 * (size_t)N * 8;
+    const char *skv = getenv("RRRMC_SK_VARIANT");
+    const bool tma = N % 2 == 0 && smem_tma <= (size_t)225 * 1024 && !(skv && atoi(skv) == 1);
+#define LST(RP) do { RR_CUDA(cudaFuncSetAttribute(k_sk_lockstep_tma<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma)); \
+                     k_sk_lockstep_tma<RP><<<grid, 512, smem_tma, ctx->stream>>>(P); } while (0)
+    if (tma) { if (rpc == 4) LST(4); else if (rpc == 2) LST(2); else LST(1); }
+    else if (rpc == 4) LS(4); else if (rpc == 2) LS(2); else LS(1);
 #undef LS
+#undef LST
     ctx->launches++;
     RR_CUDA(cudaGetLastError());
     s->ms_valid = false; s->chain_valid = true; s->chain_fields_valid = false; s->energy_valid = false;
