@@ -251,6 +251,17 @@ rrrmc_status_t rrrmc_extremal_opt(rrrmc_state_t *s, const double *ftau, int64_t 
 rrrmc_status_t rrrmc_replay(rrrmc_state_t *s, int64_t replica, int sampler, double beta, int64_t iters, int64_t step,
                             const uint8_t *draw_kind, const int64_t *draw_ival, const double *draw_fval, int64_t ndraws,
                             const rrrmc_opts_t *opts, double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
+/* Replay of wtmMC (RRRMC.jl:376-430: rand() draws only — N for the initial heap, then one for the moved spin and one per
+ * neighbour, WaitingTimes.jl:25-51) and of extremal_opt (RRRMC.jl:468-521: rand() for the rank, rand(1:n) for the class
+ * member) from a dumped draw stream; one chain. Es: [Es_cap] energies at the sampling instants. The extremal_opt replay
+ * also returns the chain's Emin, itmin and Cmin[nchunks]. */
+rrrmc_status_t rrrmc_replay_wtm(rrrmc_state_t *s, int64_t replica, double beta, int64_t samples, double step,
+                                const uint8_t *kind, const int64_t *ival, const double *fval, int64_t ndraws,
+                                double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
+rrrmc_status_t rrrmc_replay_extremal_opt(rrrmc_state_t *s, int64_t replica, const double *ftau, int64_t iters, int64_t step,
+                                         const uint8_t *kind, const int64_t *ival, const double *fval, int64_t ndraws,
+                                         double *Emin_out, int64_t *itmin_out, uint64_t *Cmin_chunks,
+                                         double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
 
 /* Device-resident sweep loop without host round trips (what bench.py times as `value`):
  * runs `nsweeps` checkerboard sweeps starting at sweep counter `sweep0`. thr64: per-class

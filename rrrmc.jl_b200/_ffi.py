@@ -86,6 +86,8 @@ SIGNATURES = {
     "rrrmc_state_set_quant_betas": (_i32, [_vp, _vp, _vp]),
     "rrrmc_extremal_opt": (_i32, [_vp, _vp, _i64, _i64, _i64, _u64, EOHOOK, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(RunInfo)]),
     "rrrmc_replay": (_i32, [_vp, _i64, _i32, _f64, _i64, _i64, _vp, _vp, _vp, _i64, C.POINTER(Opts), _vp, _i64, C.POINTER(RunInfo)]),
+    "rrrmc_replay_wtm": (_i32, [_vp, _i64, _f64, _i64, _f64, _vp, _vp, _vp, _i64, _vp, _i64, C.POINTER(RunInfo)]),
+    "rrrmc_replay_extremal_opt": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, C.POINTER(RunInfo)]),
     "rrrmc_checkerboard_sweeps": (_i32, [_vp, _vp, _i32, _i32, _i32, _u64, _u64, _i64]),
     "rrrmc_checkerboard_sparse_tables": (_i32, [_vp, _i32, _vp, _i32]),
     "rrrmc_checkerboard_sweeps_sparse": (_i32, [_vp, _vp, _i32, _u64, _u64, _i64]),

@@ -1534,6 +1534,34 @@ extern "C" rrrmc_status_t rrrmc_extremal_opt(rrrmc_state_t *s, const double *fta
     if (info) memset(info, 0, sizeof *info);
     return chain_run_eo(s, ftau, ftau_stride, iters, step, seed, hook, user, Emin_out, itmin_out, Cmin_chunks, Es, Es_cap, info);
 }
+extern "C" rrrmc_status_t rrrmc_replay_wtm(rrrmc_state_t *s, int64_t replica, double beta, int64_t samples, double step,
+                                           const uint8_t *kind, const int64_t *ival, const double *fval, int64_t ndraws,
+                                           double *Es, int64_t Es_cap, rrrmc_run_info_t *info)
+{
+    RR_ARG(s && kind && ival && fval, "NULL argument");
+    RR_CUDA(cudaSetDevice(s->g->ctx->device));
+    if (info) memset(info, 0, sizeof *info);
+    std::vector<double> b(s->R, beta);
+    const chain_trace_in tr{ replica, kind, ival, fval, ndraws };
+    return chain_run_wtm(s, b.data(), samples, step, 1, nullptr, nullptr, Es, Es_cap, info, &tr);
+}
+extern "C" rrrmc_status_t rrrmc_replay_extremal_opt(rrrmc_state_t *s, int64_t replica, const double *ftau, int64_t iters, int64_t step,
+                                                    const uint8_t *kind, const int64_t *ival, const double *fval, int64_t ndraws,
+                                                    double *Emin_out, int64_t *itmin_out, uint64_t *Cmin_chunks,
+                                                    double *Es, int64_t Es_cap, rrrmc_run_info_t *info)
+{
+    RR_ARG(s && kind && ival && fval, "NULL argument");
+    RR_ARG(iters >= 0 && step >= 1, "iters must be >= 0 and step >= 1");
+    RR_CUDA(cudaSetDevice(s->g->ctx->device));
+    if (info) memset(info, 0, sizeof *info);
+    const chain_trace_in tr{ replica, kind, ival, fval, ndraws };
+    std::vector<double> emin(s->R); std::vector<int64_t> itmin(s->R); std::vector<uint64_t> cmin((size_t)s->R * s->nchunks);
+    RR_TRY(chain_run_eo(s, ftau, 0, iters, step, 1, nullptr, nullptr, emin.data(), itmin.data(), cmin.data(), Es, Es_cap, info, &tr));
+    if (Emin_out) *Emin_out = emin[replica];
+    if (itmin_out) *itmin_out = itmin[replica];
+    if (Cmin_chunks) memcpy(Cmin_chunks, cmin.data() + (size_t)replica * s->nchunks, 8 * s->nchunks);
+    return RRRMC_OK;
+}
 extern "C" rrrmc_status_t rrrmc_replay(rrrmc_state_t *s, int64_t replica, int sampler, double beta, int64_t iters, int64_t step,
                                        const uint8_t *kind, const int64_t *ival, const double *fval, int64_t ndraws,
                                        const rrrmc_opts_t *opts, double *Es, int64_t Es_cap, rrrmc_run_info_t *info)

@@ -507,6 +507,25 @@ static double default_staged_thr(const rrrmc_graph *g)
     return simple ? 0.8 : 0.5; // RRRMC.jl:163-165 (SimpleGraph 0.8, else 0.5), :226 (DoubleGraph 0.5)
 }
 
+// replay mode: one chain fed a dumped typed draw stream instead of the Philox counter stream
+static rrrmc_status_t chain_use_trace(rrrmc_state *s, chain_params &P, const chain_trace_in &tr)
+{
+    rrrmc_ctx *ctx = s->g->ctx; chain_store *c = s->chain;
+    RR_ARG(tr.kind && tr.ival && tr.fval && tr.n >= 0, "replay: NULL draw trace");
+    RR_ARG(tr.replica >= 0 && tr.replica < s->R, "replica out of range");
+    if (c->tcap < tr.n) {
+        cudaFree(c->d_tkind); cudaFree(c->d_tival); cudaFree(c->d_tfval);
+        c->tcap = std::max<int64_t>(tr.n, 1);
+        RR_CUDA(cudaMalloc(&c->d_tkind, c->tcap)); RR_CUDA(cudaMalloc(&c->d_tival, 8 * c->tcap)); RR_CUDA(cudaMalloc(&c->d_tfval, 8 * c->tcap));
+    }
+    RR_CUDA(cudaMemcpyAsync(c->d_tkind, tr.kind, tr.n, cudaMemcpyHostToDevice, ctx->stream));
+    RR_CUDA(cudaMemcpyAsync(c->d_tival, tr.ival, 8 * tr.n, cudaMemcpyHostToDevice, ctx->stream));
+    RR_CUDA(cudaMemcpyAsync(c->d_tfval, tr.fval, 8 * tr.n, cudaMemcpyHostToDevice, ctx->stream));
+    P.tkind = c->d_tkind; P.tival = c->d_tival; P.tfval = c->d_tfval; P.tlen = tr.n;
+    P.chain0 = tr.replica; P.R = 1;       // run only the requested chain
+    return RRRMC_OK;
+}
+
 rrrmc_status_t chain_run(rrrmc_state *s, int sampler, const double *beta, int64_t iters, int64_t step, uint64_t seed,
                          rrrmc_hook_fn hook, void *user, const rrrmc_opts_t *o, double *Es, int64_t Es_cap, rrrmc_run_info_t *info)
 {
@@ -544,7 +563,8 @@ rrrmc_status_t chain_run(rrrmc_state *s, int sampler, const double *beta, int64_
 }
 
 rrrmc_status_t chain_run_wtm(rrrmc_state *s, const double *beta, int64_t samples, double step, uint64_t seed,
-                             rrrmc_hook_fn hook, void *user, double *Es, int64_t Es_cap, rrrmc_run_info_t *info)
+                             rrrmc_hook_fn hook, void *user, double *Es, int64_t Es_cap, rrrmc_run_info_t *info,
+                             const chain_trace_in *tr)
 {
     rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
     RR_ARG(beta, "beta is NULL");
@@ -565,13 +585,14 @@ rrrmc_status_t chain_run_wtm(rrrmc_state *s, const double *beta, int64_t samples
     s->ms_valid = false;
     sk_dense_invalidate(s);
     if (samples == 0) { if (info) { info->nsamples = 0; info->iters_done = 0; info->launches = 0; info->device_ms = 0; info->accepted_total = 0; } return RRRMC_OK; }
+    if (tr) { RR_TRY(chain_use_trace(s, P, *tr)); RR_TRY(chain_drive<src_trace>(s, P, nullptr, nullptr, Es, Es_cap, info)); return RRRMC_OK; }
     RR_TRY(chain_drive<src_philox>(s, P, hook, user, Es, Es_cap, info));
     return RRRMC_OK;
 }
 
 rrrmc_status_t chain_run_eo(rrrmc_state *s, const double *ftau, int64_t ftau_stride, int64_t iters, int64_t step, uint64_t seed,
                             rrrmc_eo_hook_fn hook, void *user, double *Emin_out, int64_t *itmin_out, uint64_t *Cmin_chunks,
-                            double *Es, int64_t Es_cap, rrrmc_run_info_t *info)
+                            double *Es, int64_t Es_cap, rrrmc_run_info_t *info, const chain_trace_in *tr)
 {
     rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
     const bool discr_full = g->kind == RRRMC_EA_PM1 || g->kind == RRRMC_EA_INT || g->kind == RRRMC_QT;
@@ -605,7 +626,8 @@ rrrmc_status_t chain_run_eo(rrrmc_state *s, const double *ftau, int64_t ftau_str
     RR_TRY(chain_energy_init(s, P, true));
     s->ms_valid = false;
     sk_dense_invalidate(s);
-    RR_TRY(chain_drive<src_philox>(s, P, reinterpret_cast<rrrmc_hook_fn>(hook), user, Es, Es_cap, info));
+    if (tr) { RR_TRY(chain_use_trace(s, P, *tr)); RR_TRY(chain_drive<src_trace>(s, P, nullptr, nullptr, Es, Es_cap, info)); }
+    else RR_TRY(chain_drive<src_philox>(s, P, reinterpret_cast<rrrmc_hook_fn>(hook), user, Es, Es_cap, info));
     std::vector<chain_hdr> hh(s->R);
     RR_CUDA(cudaMemcpyAsync(hh.data(), c->hdr, sizeof(chain_hdr) * s->R, cudaMemcpyDeviceToHost, ctx->stream));
     if (Cmin_chunks) RR_CUDA(cudaMemcpyAsync(Cmin_chunks, c->eo_cmin, 8 * s->R * s->nchunks, cudaMemcpyDeviceToHost, ctx->stream));
@@ -627,19 +649,10 @@ rrrmc_status_t chain_replay(rrrmc_state *s, int64_t replica, int sampler, double
     RR_TRY(chain_ensure(s, cache));
     RR_TRY(chain_sync_from_multispin(s));
     chain_store *c = s->chain;
-    if (c->tcap < ndraws) {
-        cudaFree(c->d_tkind); cudaFree(c->d_tival); cudaFree(c->d_tfval);
-        c->tcap = std::max<int64_t>(ndraws, 1);
-        RR_CUDA(cudaMalloc(&c->d_tkind, c->tcap)); RR_CUDA(cudaMalloc(&c->d_tival, 8 * c->tcap)); RR_CUDA(cudaMalloc(&c->d_tfval, 8 * c->tcap));
-    }
-    RR_CUDA(cudaMemcpyAsync(c->d_tkind, kind, ndraws, cudaMemcpyHostToDevice, ctx->stream));
-    RR_CUDA(cudaMemcpyAsync(c->d_tival, ival, 8 * ndraws, cudaMemcpyHostToDevice, ctx->stream));
-    RR_CUDA(cudaMemcpyAsync(c->d_tfval, fval, 8 * ndraws, cudaMemcpyHostToDevice, ctx->stream));
     chain_params P; chain_fill_params(s, P);
     P.sampler = sampler; P.iters = iters; P.step = step; P.seed = 0;
     P.staged_thr = std::isnan(o->staged_thr) ? default_staged_thr(g) : o->staged_thr;
     P.staged_thr_fact = o->staged_thr_fact;
-    P.tkind = c->d_tkind; P.tival = c->d_tival; P.tfval = c->d_tfval; P.tlen = ndraws;
     std::vector<double> b(s->R, beta);
     RR_CUDA(cudaMemcpyAsync(c->d_beta, b.data(), 8 * s->R, cudaMemcpyHostToDevice, ctx->stream));
     k_chain_hdr_reset<<<div_up(P.R, 64), 64, 0, ctx->stream>>>(P, 0);
@@ -647,8 +660,8 @@ rrrmc_status_t chain_replay(rrrmc_state *s, int64_t replica, int sampler, double
     RR_TRY(chain_energy_init(s, P, true));
     s->ms_valid = false;
     sk_dense_invalidate(s);
-    // run only the requested chain
-    P.chain0 = replica; P.R = 1;
+    const chain_trace_in tr{ replica, kind, ival, fval, ndraws };
+    RR_TRY(chain_use_trace(s, P, tr));
     P.beta = c->d_beta; // all equal
     RR_TRY(chain_drive<src_trace>(s, P, nullptr, nullptr, Es, Es_cap, info));
     return RRRMC_OK;

@@ -6,6 +6,9 @@
 enum { CHAIN_STANDARD = 0, CHAIN_RRR = 1, CHAIN_BKL = 2, CHAIN_WTM = 3, CHAIN_EO = 4 };
 static inline bool is_sk_kind(int k) { return k == RRRMC_SK_F64 || k == RRRMC_SK_BIN; }
 
+// replay mode: the typed draw stream one chain consumes (kind 0 = rand(1:n) value, 1 = rand() value)
+struct chain_trace_in { int64_t replica; const uint8_t *kind; const int64_t *ival; const double *fval; int64_t n; };
+
 void chain_free(rrrmc_state *s);
 rrrmc_status_t chain_sync_to_multispin(rrrmc_state *s);   // make the multispin copy current
 rrrmc_status_t chain_sync_from_multispin(rrrmc_state *s); // make the chain copy (d_chunks) current
@@ -17,11 +20,12 @@ rrrmc_status_t chain_run(rrrmc_state *s, int sampler, const double *beta, int64_
                          rrrmc_hook_fn hook, void *user, const rrrmc_opts_t *o, double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
 // wtmMC(X, β, samples; step::Float64) (RRRMC.jl:376-430): `step` in units of the global time, before the division by N
 rrrmc_status_t chain_run_wtm(rrrmc_state *s, const double *beta, int64_t samples, double step, uint64_t seed,
-                             rrrmc_hook_fn hook, void *user, double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
+                             rrrmc_hook_fn hook, void *user, double *Es, int64_t Es_cap, rrrmc_run_info_t *info,
+                             const chain_trace_in *tr = nullptr);
 // extremal_opt(X, τ, iters; step, hook) (RRRMC.jl:468-521) on the EOCache of DeltaE.jl:413-543; DiscrGraph only
 rrrmc_status_t chain_run_eo(rrrmc_state *s, const double *ftau, int64_t ftau_stride, int64_t iters, int64_t step, uint64_t seed,
                             rrrmc_eo_hook_fn hook, void *user, double *Emin_out, int64_t *itmin_out, uint64_t *Cmin_chunks,
-                            double *Es, int64_t Es_cap, rrrmc_run_info_t *info);
+                            double *Es, int64_t Es_cap, rrrmc_run_info_t *info, const chain_trace_in *tr = nullptr);
 rrrmc_status_t chain_replay(rrrmc_state *s, int64_t replica, int sampler, double beta, int64_t iters, int64_t step,
                             const uint8_t *kind, const int64_t *ival, const double *fval, int64_t ndraws,
                             const rrrmc_opts_t *o, double *Es, int64_t Es_cap, rrrmc_run_info_t *info);

@@ -964,3 +964,32 @@ def replay(X, C0, sampler, β, iters, kind, ival, fval, *, step=1, replica=0, st
     Es = Es[:info.nsamples]
     X.last_run = info
     return _out(X, Es), X._download()
+
+
+def replay_wtm(X, C0, β, samples, kind, ival, fval, *, step=1.0, replica=0):
+    """wtmMC (RRRMC.jl:376-430) of chain `replica` fed a dumped draw stream -> (Es, C)."""
+    X._upload(C0)
+    kind = np.ascontiguousarray(kind, np.uint8); ival = np.ascontiguousarray(ival, np.int64); fval = np.ascontiguousarray(fval, np.float64)
+    cap = int(samples)
+    Es = np.zeros(max(cap, 1), np.float64)
+    info = _ffi.RunInfo()
+    check(lib().rrrmc_replay_wtm(X._state, replica, float(_beta_in(X, β)), int(samples), float(step), ptr(kind), ptr(ival), ptr(fval),
+                                 len(kind), ptr(Es), cap, C.byref(info)))
+    X.last_run = info
+    return Es[:info.nsamples], X._download()
+
+
+def replay_extremal_opt(X, C0, τ, iters, kind, ival, fval, *, step=1, replica=0):
+    """extremal_opt (RRRMC.jl:468-521) of chain `replica` fed a dumped draw stream -> (Es, C, Emin, Cmin chunks, itmin)."""
+    X._upload(C0)
+    kind = np.ascontiguousarray(kind, np.uint8); ival = np.ascontiguousarray(ival, np.int64); fval = np.ascontiguousarray(fval, np.float64)
+    ftau = np.cumsum(np.arange(1, X.N + 1, dtype=np.float64) ** (-float(τ)))      # fτ = cumsum(j^-τ), RRRMC.jl:483
+    cap = int(iters) // int(step)
+    Es = np.zeros(max(cap, 1), np.float64)
+    nch = (X.N + 63) // 64
+    emin = np.zeros(1, np.float64); itmin = np.zeros(1, np.int64); cmin = np.zeros(nch, np.uint64)
+    info = _ffi.RunInfo()
+    check(lib().rrrmc_replay_extremal_opt(X._state, replica, ptr(ftau), int(iters), int(step), ptr(kind), ptr(ival), ptr(fval), len(kind),
+                                          ptr(emin), ptr(itmin), ptr(cmin), ptr(Es), cap, C.byref(info)))
+    X.last_run = info
+    return Es[:info.nsamples], X._download(), float(emin[0]), cmin, int(itmin[0])

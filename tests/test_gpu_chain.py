@@ -99,6 +99,31 @@ def test_replay_reference_trace(sampler, ofn, L, D, lev):
     assert np.array_equal(Cf.chunks[0], C0.chunks[0]) and np.array_equal(Cf.chunks[2], C0.chunks[2])
 
 
+@pytest.mark.parametrize("L,D,lev", [(4, 3, (-1, 1)), (5, 2, (-1, 1)), (3, 3, (-1, 0, 1))])
+def test_replay_wtm_and_extremal_opt(L, D, lev):
+    """Replay entries of wtmMC (RRRMC.jl:376-430) and extremal_opt (RRRMC.jl:468-521): a typed draw stream recorded from
+    the oracle drives one GPU chain to the same energies, final configuration and (extremal_opt) Emin / Cmin / itmin."""
+    X, g = _mk(L, D, lev, 3, seed=5)
+    C0 = rb.Config(X.N, 3, rng=np.random.default_rng(8))
+    rec = ffi.Recorder(ffi.PhiloxDraws(4711, chain=3, tag=2))
+    s = C0.chunks[2].copy()
+    wantE, _ = ffi.wtmMC(g, 1.4, 60, s, rec, step=2.5)
+    kind, ival, fval = rec.arrays()
+    Es, Cf = rb.replay_wtm(X, C0, 1.4, 60, kind, ival, fval, step=2.5, replica=2)
+    assert np.array_equal(np.asarray(Es, np.float64), wantE)
+    assert np.array_equal(Cf.chunks[2], s) and np.array_equal(Cf.chunks[0], C0.chunks[0])
+    tau = 1.3
+    ftau = np.cumsum(np.arange(1, X.N + 1, dtype=np.float64) ** (-tau))
+    rec = ffi.Recorder(ffi.PhiloxDraws(99, chain=1, tag=7))
+    s = C0.chunks[1].copy()
+    wantE, wantCmin, res = ffi.extremal_opt(g, ftau, 3000, s, rec, step=100)
+    kind, ival, fval = rec.arrays()
+    Es, Cf, Emin, Cmin, itmin = rb.replay_extremal_opt(X, C0, tau, 3000, kind, ival, fval, step=100, replica=1)
+    assert np.array_equal(np.asarray(Es, np.float64), wantE)
+    assert np.array_equal(Cf.chunks[1], s) and np.array_equal(Cmin, wantCmin)
+    assert Emin == res.Emin and itmin == res.itmin
+
+
 def test_replay_rejects_wrong_trace():
     X, g = _mk(4, 2, (-1, 1), 1)
     C0 = rb.Config(X.N, 1, rng=np.random.default_rng(4))
