@@ -122,6 +122,10 @@ def lib():
         "orc_checkerboard_sweeps_poisson_ladder": (None, [i32, i32, i64, p(np.uint32), p(np.int8), p(np.uint32), i32,
                                                           C.c_uint64, C.c_uint64, i64, vp]),
         "orc_cb_poisson_tables": (None, [p(np.uint64), i32, p(np.uint32)]),
+        "orc_dfloat_from_f64": (i64, [f64]),
+        "orc_dfloat_to_f64": (f64, [i64]),
+        "orc_dfloat_div_int": (i64, [i64, i64]),
+        "orc_dfloat_ea_energy": (f64, [i64, i32, p(np.int64), p(np.float64), p(np.uint64), vp]),
         "orc_tempering_decide": (None, [i64, p(np.float64), p(np.float64), C.c_uint64, C.c_uint64, p(np.uint8)]),
         "orc_checkerboard_sweeps_f64": (None, [i32, i32, i64, p(np.uint32), p(np.int64), p(np.float64), p(np.float64),
                                                C.c_uint64, C.c_uint64, i64, vp]),
@@ -527,6 +531,16 @@ def checkerboard_sweeps_poisson_ladder(L, D, R, spins, Jfwd, tbls, NW, seed, swe
     assert tbls.shape == ((R + 127) // 128, CBP_LEN) and NW in (1, 2, 4, 6)
     lib().orc_checkerboard_sweeps_poisson_ladder(L, D, R, spins, np.ascontiguousarray(Jfwd, np.int8), tbls, NW, seed, sweep0,
                                                  nsweeps, acc_p)
+
+
+def dfloat_ea_energy(A, J, s, fields=False):
+    """energy(::GraphEA{DFloat64}) (EA.jl:195-222 on src/DFloats.jl arithmetic) for real couplings J in the reference
+    (A, J) layout (zero entries of A = no neighbour) -> Float64 energy [, local fields 2·lf as Float64]."""
+    A = np.ascontiguousarray(A, np.int64); J = np.ascontiguousarray(J, np.float64)
+    N, twoD = A.shape
+    lf2 = np.zeros(N, np.int64)
+    E = lib().orc_dfloat_ea_energy(N, twoD, A, J, s, lf2.ctypes.data if fields else None)
+    return (E, lf2 / 1e5) if fields else E
 
 
 def tempering_decide(beta_group, E, seed, round_):

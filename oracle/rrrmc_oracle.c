@@ -2021,3 +2021,39 @@ orc_result orc_rank_bklMC(orc_graph *X, double beta, int64_t iters, int64_t step
     res.iters_done = it; res.accepted = accepted;
     return res;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * DFloat64 — src/DFloats.jl:11-62: "a Real type which is actually an integer in disguise", the value x is held as the
+ * Int64 round(x·10^5) and every operation the graphs use is exact integer arithmetic.
+ *   convert(DFloat64, x::Real) = round(Int64, x·dfact)   (:24, Julia's round = nearest, ties to even)
+ *   Float64(x::DFloat64) = d2i(x) / dfact                 (:28)
+ *   x ± y, -x: integer ±; Integer·x: integer product; x / Integer: integer quotient ÷ (truncating) (:30-39)
+ * orc_dfloat_ea_energy restates energy(::GraphEA{DFloat64}) (EA.jl:195-222) with these operations on real-valued
+ * couplings J (each converted once, like the graph constructor does, EA.jl:191): the engine's fractional-level graphs
+ * (an integer-level graph in units of gcd/10^5) are tested against it.
+ * ---------------------------------------------------------------------------------------- */
+#define ORC_DFACT 100000
+int64_t orc_dfloat_from_f64(double x) { return (int64_t)nearbyint(x * (double)ORC_DFACT); }   /* round-to-nearest-even mode */
+double orc_dfloat_to_f64(int64_t d) { return (double)d / (double)ORC_DFACT; }
+int64_t orc_dfloat_add(int64_t a, int64_t b) { return a + b; }
+int64_t orc_dfloat_sub(int64_t a, int64_t b) { return a - b; }
+int64_t orc_dfloat_mul_int(int64_t k, int64_t a) { return k * a; }
+int64_t orc_dfloat_div_int(int64_t a, int64_t k) { return a / k; }                         /* ÷: truncation toward zero */
+/* A: [N*twoD] 1-based neighbours (0 = no neighbour: ragged rows), J: [N*twoD] real couplings; -> Float64(energy) and,
+   when lf2 != NULL, the local fields discr(ET, 2 lf) as DFloat64 integers (EA.jl:214) */
+double orc_dfloat_ea_energy(int64_t N, int twoD, const int64_t *A, const double *J, const uint64_t *s, int64_t *lf2)
+{
+    int64_t n = 0;
+    for (int64_t x = 0; x < N; x++) {
+        int64_t sx = 2 * (int64_t)((s[x >> 6] >> (x & 63)) & 1u) - 1, lf = 0;
+        for (int k = 0; k < twoD; k++) {
+            int64_t y = A[x * twoD + k] - 1;
+            if (y < 0) continue;
+            int64_t sy = 2 * (int64_t)((s[y >> 6] >> (y & 63)) & 1u) - 1;
+            lf = orc_dfloat_sub(lf, orc_dfloat_mul_int(sx * sy, orc_dfloat_from_f64(J[x * twoD + k])));
+        }
+        n = orc_dfloat_add(n, lf);
+        if (lf2) lf2[x] = orc_dfloat_mul_int(2, lf);
+    }
+    return orc_dfloat_to_f64(orc_dfloat_div_int(n, 2));
+}

@@ -205,4 +205,13 @@ orc_result orc_rank_rrrMC(orc_graph *g, double beta, int64_t iters, int64_t step
 orc_result orc_rank_bklMC(orc_graph *g, double beta, int64_t iters, int64_t step, uint64_t *chunks,
                           orc_draws d, orc_hook hook, void *user, double *Es, int64_t Es_cap);
 
+/* DFloat64 (src/DFloats.jl:11-62): five-digit fixed point as Int64; energy(::GraphEA{DFloat64}) (EA.jl:195-222) */
+int64_t orc_dfloat_from_f64(double x);
+double orc_dfloat_to_f64(int64_t d);
+int64_t orc_dfloat_add(int64_t a, int64_t b);
+int64_t orc_dfloat_sub(int64_t a, int64_t b);
+int64_t orc_dfloat_mul_int(int64_t k, int64_t a);
+int64_t orc_dfloat_div_int(int64_t a, int64_t k);
+double orc_dfloat_ea_energy(int64_t N, int twoD, const int64_t *A, const double *J, const uint64_t *s, int64_t *lf2);
+
 #endif

@@ -203,6 +203,8 @@ def _out(X, a):
     """Engine energies -> the graph's energy type: Int for integer levels, Float64(DFloat64) = units·u for DFloat64
     levels (the division by 10^5 of DFloats.jl:28 folded into u), Float64 as is."""
     g = getattr(X, "dfloat_g", None)
+    if g is not None and getattr(X, "dfloat_mixed", False):
+        return np.asarray(a, np.float64) * (g / 10 ** MAXDIGITS)   # DoubleGraph: DFloat64 levels + Float64 residuals, in units of u
     if g is not None:
         return np.rint(a) * g / 10 ** MAXDIGITS   # Float64(x::DFloat64) = d2i(x) / dfact, one rounding (DFloats.jl:28)
     return np.rint(a).astype(np.int64) if X.ET is int else a
@@ -432,7 +434,12 @@ class GraphRRG(AbstractGraph):
 
     def __init__(self, N, K, LEV=(-1, 1), replicas=1, A=None, J=None, rng=None, ctx=None):
         if not all(float(l).is_integer() for l in LEV):
-            raise NotImplementedError("non-integer levels (DFloat64 path) are not on this engine's path yet")
+            # DFloat64 levels (RRG.jl:162, src/DFloats.jl): the integer-level graph in units of u = gcd/10^5, as in GraphEA
+            ilev, self.dfloat_g = dfloat_levels(LEV)
+            self.ET, self.LEV_real = float, tuple(float(l) for l in LEV)
+            if J is not None:
+                J = np.rint(np.asarray(J, np.float64) * 10 ** MAXDIGITS / self.dfloat_g)
+            LEV = ilev
         rng = rng or np.random.default_rng()
         self.N, self.K, self.LEV, self.replicas = int(N), int(K), tuple(int(l) for l in LEV), int(replicas)
         self.ctx = ctx or Context.default()
@@ -441,6 +448,8 @@ class GraphRRG(AbstractGraph):
             lev = np.asarray(self.LEV, np.float64)
             J = gen_J_graph(lambda n: rng.choice(lev, n), self.A)
         self.J = np.ascontiguousarray(np.rint(J), np.int64)
+        if not np.isin(self.J[self.J != 0], self.LEV).all():
+            raise ValueError(f"the given J is incompatible with levels {LEV}")
         kind = _ffi.EA_PM1 if set(self.LEV) == {-1, 1} else _ffi.EA_INT
         h = C.c_void_p()
         check(lib().rrrmc_graph_rrg_create(self.ctx.h, self.N, self.K, kind, ptr(self.A), ptr(self.J), C.byref(h)))
@@ -452,18 +461,24 @@ class GraphRRGNormalDiscretized(AbstractGraph):
     ET = float
 
     def __init__(self, N, K, LEV=(-1, 0, 1), replicas=1, A=None, cJ=None, rng=None, ctx=None):
-        if not all(float(l).is_integer() for l in LEV):
-            raise NotImplementedError("non-integer levels (DFloat64 path) are not on this engine's path yet")
         if len(set(LEV)) != len(LEV):
             raise ValueError(f"repeated levels in LEV: {LEV}")
+        unit = 1.0
+        if not all(float(l).is_integer() for l in LEV):
+            # DFloat64 levels (RRG.jl:330): the whole DoubleGraph in units of u = gcd/10^5 — integer levels LEV/u, couplings
+            # cJ/u (the nearest level and the residual scale with it), β·u; energies come back multiplied by u
+            ilev, self.dfloat_g = dfloat_levels(LEV)
+            self.dfloat_mixed, self.LEV_real = True, tuple(float(l) for l in LEV)
+            unit, LEV = self.dfloat_g / 10 ** MAXDIGITS, ilev
         rng = rng or np.random.default_rng()
         self.N, self.K, self.LEV, self.replicas = int(N), int(K), tuple(int(l) for l in LEV), int(replicas)
         self.ctx = ctx or Context.default()
         self.A = gen_RRG(N, K, rng) if A is None else np.ascontiguousarray(A, np.int64)
         self.cJ = np.ascontiguousarray(gen_J_graph(lambda n: rng.standard_normal(n), self.A) if cJ is None else cJ, np.float64)
         lev = np.ascontiguousarray(self.LEV, np.int64)
+        cJu = np.ascontiguousarray(self.cJ / unit)
         h = C.c_void_p()
-        check(lib().rrrmc_graph_rrg_discretized_create(self.ctx.h, self.N, self.K, ptr(self.A), ptr(self.cJ), ptr(lev), len(lev), C.byref(h)))
+        check(lib().rrrmc_graph_rrg_discretized_create(self.ctx.h, self.N, self.K, ptr(self.A), ptr(cJu), ptr(lev), len(lev), C.byref(h)))
         self._h = h
 
 
@@ -490,10 +505,14 @@ class GraphEANormalDiscretized(AbstractGraph):
     ET = float
 
     def __init__(self, L, D, LEV=(-1, 0, 1), replicas=1, A=None, cJ=None, rng=None, ctx=None):
-        if not all(float(l).is_integer() for l in LEV):
-            raise NotImplementedError("non-integer levels (DFloat64 path, EA.jl:360) are not on this engine's path yet")
         if len(set(LEV)) != len(LEV):
             raise ValueError(f"repeated levels in LEV: {LEV}")
+        unit = 1.0
+        if not all(float(l).is_integer() for l in LEV):
+            # DFloat64 levels (EA.jl:360): the whole DoubleGraph in units of u = gcd/10^5 (see GraphRRGNormalDiscretized)
+            ilev, self.dfloat_g = dfloat_levels(LEV)
+            self.dfloat_mixed, self.LEV_real = True, tuple(float(l) for l in LEV)
+            unit, LEV = self.dfloat_g / 10 ** MAXDIGITS, ilev
         self.L, self.D, self.LEV, self.replicas = L, D, tuple(int(l) for l in LEV), int(replicas)
         self.ctx = ctx or Context.default()
         self.A = gen_EA(L, D) if A is None else np.ascontiguousarray(A, np.int64)
@@ -503,8 +522,9 @@ class GraphEANormalDiscretized(AbstractGraph):
             cJ = gen_J(lambda n: rng.standard_normal(n), self.A)   # gen_J(Float64, N, A) do randn() end, EA.jl:323-325
         self.cJ = np.ascontiguousarray(cJ, np.float64)
         lev = np.ascontiguousarray(self.LEV, np.int64)
+        cJu = np.ascontiguousarray(self.cJ / unit)
         h = C.c_void_p()
-        check(lib().rrrmc_graph_ea_discretized_create(self.ctx.h, L, D, ptr(self.A), ptr(self.cJ), ptr(lev), len(lev), C.byref(h)))
+        check(lib().rrrmc_graph_ea_discretized_create(self.ctx.h, L, D, ptr(self.A), ptr(cJu), ptr(lev), len(lev), C.byref(h)))
         self._h = h
 
 

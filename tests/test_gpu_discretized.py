@@ -84,8 +84,10 @@ def test_energy_consistency_hook_like_the_reference_tests():
 
 def test_argument_errors():
     A, cJ = ea_instance(3, 2, seed=1, gaussian=True)
+    Xf = rb.GraphEANormalDiscretized(3, 2, (-1.5, 0.0, 1.5), A=A, cJ=cJ)    # DFloat64 levels: runs in units of 1.5
+    assert Xf.LEV == (-1, 0, 1) and Xf.dfloat_g == 150000
     with pytest.raises(NotImplementedError):
-        rb.GraphEANormalDiscretized(3, 2, (-1.5, 0.0, 1.5), A=A, cJ=cJ)
+        rb.GraphEANormalDiscretized(3, 2, (0.00001, 1.0), A=A, cJ=cJ)       # would need couplings beyond int8
     with pytest.raises(ValueError):
         rb.GraphEANormalDiscretized(3, 2, (-1, -1, 1), A=A, cJ=cJ)
     bad = cJ.copy(); bad[0, 0] += 1.0   # breaks the symmetry of the discretised couplings

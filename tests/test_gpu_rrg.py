@@ -97,8 +97,8 @@ def test_argument_errors():
     bad = J.copy(); bad[0, 0] = -bad[0, 0]
     with pytest.raises(ValueError):
         rb.GraphRRG(10, 3, A=A, J=bad)                     # not symmetric
-    with pytest.raises(NotImplementedError):
-        rb.GraphRRG(10, 3, (-1.5, 0.5), A=A, J=J)          # fractional levels (DFloat64)
+    with pytest.raises(ValueError):
+        rb.GraphRRG(10, 3, (-1.5, 0.5), A=A, J=J)          # fractional levels (DFloat64): J = ±1 are not levels
     Ab = A.copy(); Ab[0, 0], Ab[0, 1] = Ab[0, 1], Ab[0, 0]
     with pytest.raises(ValueError):
         rb.GraphRRG(10, 3, A=Ab, J=J)                      # rows must ascend
