@@ -12,6 +12,7 @@
 module RRRMCB200
 
 export standardMC, rrrMC, bklMC, wtmMC, extremal_opt
+export transverse_mag, Qenergy, Renergies, overlaps, GraphQT, replay, replay_wtm, tempering_exchange!
 
 const lib = get(ENV, "RRRMC_B200_LIB", joinpath(@__DIR__, "..", "lib", "librrrmc_b200.so"))
 
@@ -204,7 +205,7 @@ update_cache!(X::Graph, C::Config, move::Integer) = nothing  # the device caches
 # ---- samplers (src/RRRMC.jl:81-127, 149-290, 311-359) ---------------------------------------------------
 struct Opts
     schedule::Cint; planes_K::Cint; count_accepted::Cint; staged_thr::Cdouble; staged_thr_fact::Cdouble
-    planes_M::Cint; cb_method::Cint; reserved::NTuple{6,Cint}   # cb_method: 0 auto, 1 planes, 2 sparse (rrrmc_b200.h)
+    planes_M::Cint; cb_method::Cint; site_pick::Cint; reserved::NTuple{5,Cint}   # cb_method: 0 auto, 1 planes, 2 sparse, 3 poisson; site_pick: 0 reference (ArraySet order), 1 rank (rrrmc_b200.h)
 end
 struct RunInfo
     nsamples::Int64; iters_done::Int64; launches::Int64; device_ms::Cfloat; accepted_total::Int64
@@ -305,6 +306,62 @@ function extremal_opt(X::Graph, τ::Real, iters::Integer; seed = 167432777111, s
     box.err === nothing || throw(box.err)
     quiet || (println("iters = ", info[].iters_done); println("min [it = $itmin] = $Emin"))
     download(X), Emin, Cmin, itmin
+end
+
+# ---- GraphQT and the observables of the quantum graphs (QT.jl:46-54, 113-121, 201-268) ------------------------
+function GraphQT(N::Integer, M::Integer, fourK::Float64; replicas::Integer = 1)     # GraphQT{fourK}(N, M), QT.jl:46-54
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:rrrmc_graph_qt_create, lib), Cint, (Ptr{Cvoid}, Int64, Int64, Cdouble, Ref{Ptr{Cvoid}}), ctx().h, N, M, fourK, r))
+    _finish(r[], Float64, replicas, QT)
+end
+function transverse_mag(X::Graph, C::Config, β::Float64)                             # QT.jl:113-121
+    upload!(X, C); out = zeros(X.replicas)
+    check(ccall((:rrrmc_transverse_mag, lib), Cint, (Ptr{Cvoid}, Cdouble, Ptr{Cdouble}), X.state, β, out)); out
+end
+function Qenergy(X::Graph, C::Config)                                                # QT.jl:253-268
+    upload!(X, C); out = zeros(X.replicas)
+    check(ccall((:rrrmc_Qenergy, lib), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), X.state, out)); out
+end
+function Renergies(X::Graph, M::Integer)                                             # QT.jl:201-211 (after energy(X, C))
+    out = zeros(M, X.replicas)
+    check(ccall((:rrrmc_Renergies, lib), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), X.state, out)); out
+end
+function overlaps(X::Graph, M::Integer)                                              # QT.jl:213-251
+    out = zeros(M ÷ 2, X.replicas)
+    check(ccall((:rrrmc_overlaps, lib), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), X.state, out)); out
+end
+
+# ---- replay mode (SURVEY Appendix B): one chain fed the typed draw stream a run of RRRMC.jl consumed ---------------
+# kind[k] = 0 for a rand(1:n) value (ival[k]), 1 for a rand() value (fval[k]); scripts/dump_julia_trace.jl writes them
+function replay(X::Graph, C0::Config, sampler::Symbol, β::Float64, iters::Integer, kind::Vector{UInt8}, ival::Vector{Int64},
+                fval::Vector{Float64}; step::Integer = 1, replica::Integer = 0)
+    upload!(X, C0)
+    o = Ref{Opts}(); check(ccall((:rrrmc_opts_default, lib), Cint, (Ref{Opts},), o))
+    Es = zeros(max(iters ÷ step, 1)); info = Ref{RunInfo}()
+    code = Dict(:standardMC => 0, :rrrMC => 1, :bklMC => 2)[sampler]
+    check(ccall((:rrrmc_replay, lib), Cint,
+        (Ptr{Cvoid}, Int64, Cint, Cdouble, Int64, Int64, Ptr{UInt8}, Ptr{Int64}, Ptr{Cdouble}, Int64, Ref{Opts}, Ptr{Cdouble}, Int64, Ref{RunInfo}),
+        X.state, replica, code, β, iters, step, kind, ival, fval, length(kind), o, Es, length(Es), info))
+    Es[1:info[].nsamples], download(X)
+end
+function replay_wtm(X::Graph, C0::Config, β::Float64, samples::Integer, kind::Vector{UInt8}, ival::Vector{Int64}, fval::Vector{Float64};
+                    step::Float64 = 1.0, replica::Integer = 0)
+    upload!(X, C0)
+    Es = zeros(max(samples, 1)); info = Ref{RunInfo}()
+    check(ccall((:rrrmc_replay_wtm, lib), Cint,
+        (Ptr{Cvoid}, Int64, Cdouble, Int64, Cdouble, Ptr{UInt8}, Ptr{Int64}, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Int64, Ref{RunInfo}),
+        X.state, replica, β, samples, step, kind, ival, fval, length(kind), Es, length(Es), info))
+    Es[1:info[].nsamples], download(X)
+end
+
+# ---- parallel tempering on the checkerboard schedule (new engine; the reference runs one standardMC per β) -------
+# standardMC(X, βs, ...) with opts.schedule = checkerboard takes a β vector that is constant inside each group of 128
+# replicas; tempering_exchange! then swaps the configurations of neighbouring groups on the device.
+function tempering_exchange!(X::Graph, β_group::Vector{Float64}, seed::Integer, round::Integer; read::Bool = false)
+    acc = zeros(Int64, max(length(β_group) - 1, 1))
+    check(ccall((:rrrmc_tempering_exchange, lib), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Cint, UInt64, UInt64, Ptr{Int64}),
+                X.state, β_group, length(β_group), seed, round, read ? pointer(acc) : C_NULL))
+    acc
 end
 
 end # module
