@@ -152,6 +152,9 @@ class AbstractGraph:
         return self._state
 
     def _upload(self, Cfg):
+        if Cfg is ON_DEVICE:
+            self._ensure_state()
+            return
         if Cfg.N != self.N:
             raise ValueError(f"Invalid C0, wrong N, expected {self.N}, given: {Cfg.N}")  # RRRMC.jl:94
         if Cfg.R != self.replicas:
@@ -172,6 +175,17 @@ class AbstractGraph:
         except Exception:
             pass
 
+
+class _OnDevice:
+    """Sentinel for `C0` / `Cfg`: the configuration the device batch currently holds (no host round trip). Samplers
+    called with C0=ON_DEVICE continue from it and return it as their Config without downloading; energy(X, ON_DEVICE)
+    evaluates it in place. Used by the tempering drivers, which only need energies between rounds."""
+
+    def __repr__(self):
+        return "ON_DEVICE"
+
+
+ON_DEVICE = _OnDevice()
 
 MAXDIGITS = 5  # src/DFloats.jl:12: a DFloat64 is the integer round(x·10^5)
 
@@ -783,7 +797,7 @@ def _run(fn, X, beta, iters, seed, step, hook, C0, quiet, opts, name):
              ptr(Es), cap, C.byref(info)))
     if "exc" in last:
         raise last["exc"]
-    Cout = X._download()
+    Cout = ON_DEVICE if C0 is ON_DEVICE else X._download()
     Es = _out(X, Es[:info.nsamples])
     if not quiet:
         print("samples =", info.nsamples)
@@ -881,7 +895,7 @@ def wtmMC(X, β, samples, *, seed=DEFAULT_SEED, step=1.0, hook=None, C0=None, qu
                              ptr(Es), cap, C.byref(info)))
     if "exc" in last:
         raise last["exc"]
-    Cout = X._download()
+    Cout = ON_DEVICE if C0 is ON_DEVICE else X._download()
     Es = _out(X, Es[:info.nsamples])
     if not quiet:
         print("samples =", info.nsamples)

@@ -141,11 +141,22 @@ class ReplicaShard:
         return np.asarray(x_global)[self.lo:self.hi]
 
 
-def tempered_run(X, ladder, shard, rounds, iters_per_round, sampler, *, seed=1, C0=None, terms_fn=None, energy_fn=None, **kw):
+def tempered_run(X, ladder, shard, rounds, iters_per_round, sampler, *, seed=1, C0=None, terms_fn=None, energy_fn=None,
+                 on_device=False, **kw):
     """Runs `sampler(X, β_local, iters_per_round, ...)` on this rank's batch for `rounds` rounds with a label swap
     after each: energies are all-gathered, every rank applies the same swaps, the local β vector is refreshed.
-    -> (E_history (rounds, R_total), final Config of the local batch)."""
+    -> (E_history (rounds, R_total), final Config of the local batch). on_device=True keeps the configuration on the
+    device between rounds (interface.ON_DEVICE): only energies and β labels cross PCIe and the batch is downloaded once
+    at the end (the default round-trips it through the host three times per round: sampler result, energy(X, C), C0)."""
     C = C0
+    if on_device:
+        import rrrmc_b200 as rb
+        if C0 is not None:
+            X._upload(C0)
+        else:
+            from ._ffi import check, lib
+            check(lib().rrrmc_state_randomize(X._ensure_state(), seed + RANK_SEED_STRIDE * shard.lo))
+        C = rb.ON_DEVICE
     hist = []
     # The engine keys its counter RNG by (seed, LOCAL chain index) and draws the initial configuration from the seed
     # alone, so the shards must not share a seed: replica r of every rank would start from the same configuration and
@@ -173,7 +184,7 @@ def tempered_run(X, ladder, shard, rounds, iters_per_round, sampler, *, seed=1, 
             t_all = tuple(all_gather(t) for t in t_local)
             ladder.swap(t_all, rd)
             hist.append(all_gather(E_local))
-    return np.array(hist), C
+    return np.array(hist), (X._download() if on_device else C)
 
 
 def tempered_checkerboard(X, beta_group, rounds, sweeps_per_round, *, seed=1, C0=None, read_every=0):

@@ -7,7 +7,6 @@ decisions from a shared counter RNG, and a replica's fourK follows the β it hol
   python scripts/bench_c5_pt.py                                   # 1 GPU
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P scripts/bench_c5_pt.py
 env: C5_R (replicas per GPU, default 128), C5_ROUNDS (default 6), C5_ITERS (iterations per round, default 20000)"""
-import importlib.util
 import json
 import os
 import sys
@@ -27,9 +26,7 @@ if world > 1:
 os.environ.setdefault("RRRMC_DEVICE", str(local))
 import rrrmc_b200 as rb
 
-_spec = importlib.util.spec_from_file_location("rrrmc_sharding", os.path.join(ROOT, "rrrmc.jl_b200", "sharding.py"))
-sh = importlib.util.module_from_spec(_spec)
-_spec.loader.exec_module(sh)
+from rrrmc_b200 import sharding as sh
 
 Nk, M, G = 1024, 64, 0.3
 Rl = int(os.environ.get("C5_R", "128")); R = Rl * world
@@ -48,13 +45,13 @@ def sampler(X_, b, it, **kw):
     return out
 
 
-sh.tempered_run(X, ladder, shard, 1, iters // 10, sampler, seed=1, terms_fn=sh.quant_terms)      # warm-up round
+sh.tempered_run(X, ladder, shard, 1, iters // 10, sampler, seed=1, terms_fn=sh.quant_terms, on_device=True)      # warm-up round
 dev_ms.clear()
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
 t0 = time.perf_counter()
-hist, C = sh.tempered_run(X, ladder, shard, rounds, iters, sampler, seed=100, terms_fn=sh.quant_terms)
+hist, C = sh.tempered_run(X, ladder, shard, rounds, iters, sampler, seed=100, terms_fn=sh.quant_terms, on_device=True)
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()

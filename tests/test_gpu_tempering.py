@@ -117,3 +117,18 @@ def test_quant_tempered_run_swaps_follow_quantum_action():
         E = g.energy(C.chunks[r])
         assert abs(E - (g.fourK() / 4 * e0[r] + ecl[r] / M)) <= 1e-9 * max(1.0, abs(E))
         assert abs(hist[-1, r] - E) <= 1e-9 * max(1.0, abs(E))
+
+
+def test_tempered_run_on_device_matches_host_round_trips():
+    """tempered_run(on_device=True) keeps the batch on the device between rounds (ON_DEVICE sentinel): same energies,
+    swaps and final configuration as the default path that round-trips the configuration through the host."""
+    from rrrmc_b200 import sharding as sh
+    X = rb.GraphEA(4, 3, replicas=128, rng=np.random.default_rng(3))
+    C0 = rb.Config(X.N, 128, rng=np.random.default_rng(4))
+    out = []
+    for on_dev in (False, True):
+        ladder = sh.TemperingLadder(np.geomspace(0.5, 3.0, 128), seed=5)
+        shard = sh.ReplicaShard(128, rank=0, world=1)
+        hist, C = sh.tempered_run(X, ladder, shard, 4, 500, rb.rrrMC, seed=9, C0=C0, on_device=on_dev)
+        out.append((hist, np.asarray(C.chunks).copy(), ladder.order.copy()))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
