@@ -299,7 +299,10 @@ __global__ void __launch_bounds__(32) k_chain_warp(chain_params P)
         for (;;) {
             if (!h.pending) {
                 if (h.it >= iters) { done = true; break; }
-                h.skip = (long long)floor(log1p(-src.f64(lane)) / log1p(-z / (double)N));   // DeltaE.jl:141-144
+                // DeltaE.jl:141-144: floor(log1p(-rand()) / log1p(-z/N)); the two logarithms in ONE call, on two lanes
+                const double us = src.f64(lane);
+                const double ly = log1p(lane == 0 ? -us : -z / (double)N);
+                h.skip = (long long)floor(__shfl_sync(FULLMASK, ly, 0) / __shfl_sync(FULLMASK, ly, 1));
                 h.pmove = rand_move(h.pdE);
                 h.pending = 1;
             }
