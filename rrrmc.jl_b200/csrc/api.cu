@@ -1137,7 +1137,10 @@ static rrrmc_status_t run_sweeps_poisson(rrrmc_state *s, cbp_run &run, uint64_t 
 {
     if (!run.groups.empty())
         return launch_checkerboard_flow(s, *run.tma, t0, n, run.groups.data(), run.gbucket.empty() ? nullptr : run.gbucket.data(), (int)run.groups.size());
-    if (run.tma && !(run.p.variant & 4096)) return launch_checkerboard_flow(s, *run.tma, t0, n, nullptr, nullptr, 0);
+    if (run.tma && !(run.p.variant & 4096) && !s->tma->flow_unavailable) {
+        const rrrmc_status_t st = launch_checkerboard_flow(s, *run.tma, t0, n, nullptr, nullptr, 0);
+        if (!(st == RRRMC_ERR_UNSUPPORTED && s->tma->flow_unavailable)) return st;
+    }
     for (int64_t k = 0; k < n; k++) RR_TRY(run_sweep_poisson(s, run, t0 + (uint64_t)k));
     return RRRMC_OK;
 }

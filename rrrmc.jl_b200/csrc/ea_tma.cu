@@ -783,6 +783,13 @@ rrrmc_status_t launch_checkerboard_flow(rrrmc_state *s, cbt_params &P, uint64_t 
         if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) {
             // the counters are only meaningful after a complete launch: start over
             cudaMemsetAsync(c->d_done, 0, sizeof(uint32_t) * (size_t)c->nbricks * (s->W / 32), ctx->stream); c->epoch = 0;
+            if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported || e == cudaErrorLaunchOutOfResources) {
+                // the grid cannot be made co-resident here (a shared or partitioned device): the caller falls back to
+                // the per-colour launches of the same kernel family — another GPU path, same results
+                c->flow_unavailable = true;
+                rrrmc_set_error("the multi-sweep kernel needs a co-resident grid: %s", cudaGetErrorString(e));
+                return RRRMC_ERR_UNSUPPORTED;
+            }
             RR_CUDA(e);
             return RRRMC_ERR_CUDA;
         }

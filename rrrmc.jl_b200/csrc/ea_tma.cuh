@@ -52,6 +52,7 @@ struct cb_tma_store {
     cbf_brick *d_bricks = nullptr;
     uint32_t *d_done = nullptr;
     uint32_t epoch = 0;                   // host mirror of done[]
+    bool flow_unavailable = false;        // a cooperative launch failed for lack of co-residency: use the per-colour launches
     cbp_group *d_groups = nullptr;        // β ladder tables (uploaded per run)
     uint2 *d_gbucket = nullptr;
     int ngroups_alloc = 0;
