@@ -251,61 +251,88 @@ def run_ours(args, rank, world, local_rank):
     opts.cb_method = {"poisson": _ffi.CB_POISSON, "sparse": _ffi.CB_SPARSE, "planes": _ffi.CB_PLANES}[METHOD]
     info = _ffi.RunInfo()
     iters = SWEEPS_PER_STEP * N_SITES
-    gathered = [torch.empty(R_PER_GPU, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
 
-    pending = []
+    # Two pipelines per GPU: a second context (= a second stream), state and set of pinned buffers, each driven by its
+    # own host thread through the same three public calls. While one pipeline's sweeps run, the other one's H2D/D2H
+    # copies and transposes proceed — every step still uploads its input and downloads its result inside the timed
+    # region, but the copies of step k+1 hide behind the sweeps of step k (a sampling service keeps the GPU busy this way).
+    NPIPE = 2
+    pipes = [{"ctx": ctx, "X": X, "st": st, "h_in": h_in, "h_out": h_out, "h_E": h_E, "info": info}]
+    for _ in range(NPIPE - 1):
+        c2 = rb.Context(local_rank)
+        X2 = rb.GraphEA(L, D, replicas=R_PER_GPU, A=A, J=J, ctx=c2)
+        hi2 = torch.empty((R_PER_GPU, nch), dtype=torch.int64).pin_memory()
+        hi2.copy_(h_in)
+        pipes.append({"ctx": c2, "X": X2, "st": X2._ensure_state(), "h_in": hi2,
+                      "h_out": torch.empty((R_PER_GPU, nch), dtype=torch.int64).pin_memory(),
+                      "h_E": torch.empty((1, R_PER_GPU), dtype=torch.float64).pin_memory(), "info": _ffi.RunInfo()})
 
-    def e2e_step(k, phases=None):
+    def e2e_step(P, k, phases=None):
         t = [time.perf_counter()]
 
         def mark():
             if phases is not None:
-                ctx.sync()
+                P["ctx"].sync()
                 t.append(time.perf_counter())
-        check(lib().rrrmc_state_upload(st, 0, R_PER_GPU, h_in.data_ptr())); mark()
-        check(lib().rrrmc_standard_mc(st, ptr(betas), iters, iters, SEED + 17 * k + 1000 * rank, C.cast(None, _ffi.HOOK), None,
-                                      C.byref(opts), h_E.data_ptr(), 1, C.byref(info))); mark()
-        check(lib().rrrmc_state_download(st, 0, R_PER_GPU, h_out.data_ptr())); mark()
-        if world > 1:  # the observable reduction behind `hook`: per-replica energies of every rank. Asynchronous: a rank does
-            # not wait for the others inside a step (the handles are waited for before the timed region ends)
-            out = [torch.empty(R_PER_GPU, dtype=torch.float64, device="cuda") for _ in range(world)]
-            pending.append((dist.all_gather(out, h_E[0].cuda(non_blocking=True), async_op=True), out))
-            if phases is not None:
-                pending[-1][0].wait(); torch.cuda.synchronize(); t.append(time.perf_counter())
+        check(lib().rrrmc_state_upload(P["st"], 0, R_PER_GPU, P["h_in"].data_ptr())); mark()
+        check(lib().rrrmc_standard_mc(P["st"], ptr(betas), iters, iters, SEED + 17 * k + 1000 * rank, C.cast(None, _ffi.HOOK), None,
+                                      C.byref(opts), P["h_E"].data_ptr(), 1, C.byref(P["info"]))); mark()
+        check(lib().rrrmc_state_download(P["st"], 0, R_PER_GPU, P["h_out"].data_ptr())); mark()
         if phases is not None:
-            names = ["h2d_upload_transpose", "standard_mc_sweeps_energy_d2h", "download_transpose_d2h", "all_gather"]
+            names = ["h2d_upload_transpose", "standard_mc_sweeps_energy_d2h", "download_transpose_d2h"]
             for n, a, b in zip(names, t[:-1], t[1:]):
                 phases[n] = phases.get(n, 0.0) + 1e3 * (b - a)
-            phases["sweep_kernels_device_ms"] = phases.get("sweep_kernels_device_ms", 0.0) + float(info.device_ms)
-    e2e_step(0)
-    for w, _ in pending:
-        w.wait()
-    pending.clear()
+            phases["sweep_kernels_device_ms"] = phases.get("sweep_kernels_device_ms", 0.0) + float(P["info"].device_ms)
+        return P["h_E"][0].clone()
+
+    def run_steps(ks):
+        """steps ks spread over the pipelines (step k on pipeline k % NPIPE), one host thread per pipeline -> energies"""
+        Es = {}
+        errs = []
+
+        def work(p):
+            try:
+                for k in ks[p::NPIPE]:
+                    Es[k] = e2e_step(pipes[p], k)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=work, args=(p,)) for p in range(NPIPE)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        if errs:
+            raise errs[0]
+        if world > 1:   # the observable reduction behind `hook`: per-replica energies of every rank, step by step
+            hs = []
+            for k in ks:
+                out = [torch.empty(R_PER_GPU, dtype=torch.float64, device="cuda") for _ in range(world)]
+                hs.append((dist.all_gather(out, Es[k].cuda(non_blocking=True), async_op=True), out))
+            for w, _ in hs:
+                w.wait()
+        return Es
+    run_steps([0, 1])
     barrier()
     t0 = time.perf_counter()
-    for k in range(args.steps):
-        e2e_step(1 + k)
-    for w, _ in pending:
-        w.wait()
+    Es_all = run_steps([2 + k for k in range(args.steps)])
     barrier()
     t_e2e = time.perf_counter() - t0
-    pending.clear()
     if world > 1:
         t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
-    # per-phase breakdown of the end-to-end step (two extra steps outside the timed region, a sync after every phase)
+    # per-phase breakdown of ONE pipeline's step (two extra steps outside the timed region, a sync after every phase)
     phases = {}
     for k in range(2):
-        e2e_step(100 + k, phases)
+        e2e_step(pipes[0], 100 + k, phases)
     phases = {n: v / 2 for n, v in phases.items()}
     if world > 1:
         keys = sorted(phases)
         t = torch.tensor([phases[n] for n in keys], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         phases = {n: float(v) for n, v in zip(keys, t.tolist())}
+    assert all(float(e.mean()) < -1.0 * N_SITES for e in Es_all.values()), "e2e energies look wrong"
     e2e_value = world * attempts_per_step * args.steps / t_e2e
-    assert float(h_E.mean()) < -1.0 * N_SITES, "e2e energies look wrong"
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -363,7 +390,9 @@ def run_ours(args, rank, world, local_rank):
                              "sample": f"{reps} x ({cores} replicas (1/thread) x {cpu_iters} random-site attempts), same instance, beta={beta}; {cpu_dt:.1f}s"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(R_PER_GPU * nch * 8),
                     "d2h_bytes_per_step": int(R_PER_GPU * nch * 8 + R_PER_GPU * 8),
-                    "api": "rrrmc_state_upload + rrrmc_standard_mc + rrrmc_state_download (host pinned buffers)",
+                    "api": "rrrmc_state_upload + rrrmc_standard_mc + rrrmc_state_download (host pinned buffers); two pipelines per GPU "
+                           "(two contexts/states, one host thread each) so that a step's copies overlap the other pipeline's sweeps",
+                    "pipelines_per_gpu": NPIPE,
                     "phases_ms_max_over_ranks": phases},
             "gpu_launches": int(launches),
             "clocks": clk,
