@@ -231,8 +231,11 @@ rrrmc_status_t rrrmc_wtm_mc(rrrmc_state_t *s, const double *beta, int64_t sample
 
 /* extremal_opt(X, τ, iters; step, seed, hook, C0) (RRRMC.jl:468-521): τ-extremal optimisation on the EOCache of
  * DeltaE.jl:413-543 — spins ranked by ΔE class, rank drawn from the power law j^-τ, the chosen spin always flips.
- * DiscrGraph models only (GraphEA / GraphRRG with integer levels, GraphQT); others return RRRMC_ERR_UNSUPPORTED (the
- * reference's generic EOCacheCont re-sorts all N spins per move, DeltaE.jl:545-635).
+ * DiscrGraph models (GraphEA / GraphRRG with integer levels, GraphQT) run on EOCache; the Float64 SimpleGraphs
+ * (GraphEANormal, GraphRRGNormal, GraphSKNormal) on EOCacheCont (DeltaE.jl:555-635): ΔE of every spin kept in sorted
+ * order (an insertion pass per move where the reference calls sortperm!), ONE draw per move, ties keep their order
+ * (rankshuffle!, :608-633, only acts on equal ΔEs, which continuous couplings do not produce). DoubleGraphs return
+ * RRRMC_ERR_UNSUPPORTED.
  * ftau: fτ = cumsum(j^-τ, j = 1..N) (DeltaE.jl:443), computed by the host language so that its own `^` and `cumsum`
  * bits are used; ftau_stride = 0: one table [N] for all chains, else chain r reads ftau + r·ftau_stride (per-chain τ).
  * The final configurations stay in the state (rrrmc_state_download). Outputs (any may be NULL): Emin_out[R],

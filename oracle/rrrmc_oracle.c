@@ -1361,11 +1361,65 @@ static int eo_findks(const decache *c, double dE, int has_zero) /* DeltaE.jl:413
     int ak = findk(c, dE);
     return dE >= 0 ? ak + c->L - has_zero : c->L + 1 - ak;
 }
+/* extremal_opt on EOCacheCont (DeltaE.jl:555-635): the graphs that are not DiscrGraph (GraphEANormal, GraphSKNormal, ...).
+ * ΔEs[i] = delta_energy(X, C, i) for every spin, rank = sortperm(ΔEs) (:562-563); rand_move picks rank[i] with
+ * i = searchsortedfirst(fτ, (1 - rand())·z) (:575-587) — ONE draw per move, no member draw; apply_move! flips, refreshes
+ * ΔEs of the move and its neighbours and re-sorts (sortperm!(rank, ΔEs, initialized=true), :589-606). With continuous
+ * couplings two spins never share a ΔE, so the sorted order is unique and rankshuffle! (:608-633, a shuffle inside groups
+ * of equal ΔE that would consume further draws) does nothing; this restatement keeps equal values in their current
+ * order (a stable insertion pass) and so differs from the reference only on ties. */
+static orc_eo_result orc_extremal_opt_cont(orc_graph *X, const double *ftau, int64_t iters, int64_t step, uint64_t *s,
+                                           uint64_t *Cmin, orc_draws d, orc_eo_hook hook, void *user, double *Es, int64_t Es_cap)
+{
+    orc_eo_result res = { 0, 0, 0, 0.0, 0, 0.0 };
+    const int64_t N = X->N, nch = (N + 63) / 64;
+    double E = orc_energy(X, s), Emin = E;
+    int64_t itmin = 0, it = 0;
+    if (Cmin) memcpy(Cmin, s, (size_t)nch * 8);
+    double *dEs = (double *)malloc((size_t)N * 8);
+    int64_t *rank = (int64_t *)malloc((size_t)N * 8), *nb = (int64_t *)malloc((size_t)(N + 2) * 8);
+    for (int64_t i = 0; i < N; i++) { dEs[i] = orc_delta_energy(X, s, i + 1); rank[i] = i; }
+    for (int64_t p = 1; p < N; p++) {                     /* sortperm: stable insertion sort (ascending ΔE) */
+        int64_t key = rank[p], q = p - 1; double kv = dEs[key];
+        while (q >= 0 && dEs[rank[q]] > kv) { rank[q + 1] = rank[q]; q--; }
+        rank[q + 1] = key;
+    }
+    const double z = ftau[N - 1];
+    while (it < iters) {
+        it++;
+        if (it % step == 0) {
+            if (res.nsamples < Es_cap && Es) Es[res.nsamples] = E;
+            res.nsamples++;
+            if (hook && !hook(user, it, E, Emin)) break;
+        }
+        const double r = (1 - d.f64(d.user)) * z;        /* rand_move, DeltaE.jl:575-587 */
+        int64_t lo = 0, hi = N;
+        while (lo < hi) { int64_t m = (lo + hi) >> 1; if (ftau[m] < r) lo = m + 1; else hi = m; }
+        const int64_t i = lo + 1;
+        if (i < 1 || i > N) { res.status = -4; break; }
+        const int64_t move = rank[i - 1] + 1;
+        const double dE = dEs[move - 1];
+        orc_spinflip(X, s, move);                         /* apply_move!, DeltaE.jl:589-606 */
+        dEs[move - 1] = orc_delta_energy(X, s, move);
+        const int n = orc_neighbors(X, move, nb);
+        for (int a = 0; a < n; a++) dEs[nb[a] - 1] = orc_delta_energy(X, s, nb[a]);
+        for (int64_t p = 1; p < N; p++) {                 /* sortperm!(rank, ΔEs, initialized=true) */
+            int64_t key = rank[p], q = p - 1; double kv = dEs[key];
+            while (q >= 0 && dEs[rank[q]] > kv) { rank[q + 1] = rank[q]; q--; }
+            rank[q + 1] = key;
+        }
+        E += dE;
+        if (E < Emin) { Emin = E; itmin = it; if (Cmin) memcpy(Cmin, s, (size_t)nch * 8); }
+    }
+    free(dEs); free(rank); free(nb);
+    res.iters_done = it; res.itmin = itmin; res.Emin = Emin; res.Efinal = E;
+    return res;
+}
 orc_eo_result orc_extremal_opt(orc_graph *X, const double *ftau, int64_t iters, int64_t step, uint64_t *s,
                                uint64_t *Cmin, orc_draws d, orc_eo_hook hook, void *user, double *Es, int64_t Es_cap)
 {
     orc_eo_result res = { 0, 0, 0, 0.0, 0, 0.0 };
-    if (!is_discr(X)) { res.status = -2; return res; }
+    if (!is_discr(X)) return orc_extremal_opt_cont(X, ftau, iters, step, s, Cmin, d, hook, user, Es, Es_cap);
     const int64_t N = X->N, nch = (N + 63) / 64;
     decache c0; memset(&c0, 0, sizeof c0);
     decache *c = &c0;

@@ -167,6 +167,15 @@ __global__ void k_chain_delta_site(chain_params P, int site, int what, double *o
     const gview X = make_view(P, r);
     out[r] = what ? gv_delta_residual(X, site) : gv_delta_energy(X, site);
 }
+// delta_energy(X, C, i) of every spin of every chain: out[r][i]
+__global__ void k_chain_delta_all(chain_params P, double *out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = blockIdx.y;
+    if (x >= P.N) return;
+    const gview X = make_view(P, P.chain0 + r);
+    out[(P.chain0 + r) * P.N + x] = gv_delta_energy(X, x);
+}
 __global__ void k_chain_delta_replica(chain_params P, int64_t r, double *out)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -596,8 +605,10 @@ rrrmc_status_t chain_run_eo(rrrmc_state *s, const double *ftau, int64_t ftau_str
 {
     rrrmc_graph *g = s->g; rrrmc_ctx *ctx = g->ctx;
     const bool discr_full = g->kind == RRRMC_EA_PM1 || g->kind == RRRMC_EA_INT || g->kind == RRRMC_QT;
-    if (!discr_full) {   // gen_EOcache(X::AbstractGraph) = EOCacheCont re-sorts all N spins per move (DeltaE.jl:545-635)
-        rrrmc_set_error("extremal_opt: only DiscrGraph models (GraphEA / GraphRRG with integer levels, GraphQT) are on this path");
+    const bool simple_f64 = g->kind == RRRMC_EA_F64 || g->kind == RRRMC_SK_F64;   // EOCacheCont (DeltaE.jl:555-635)
+    if (!discr_full && !simple_f64) {
+        rrrmc_set_error("extremal_opt: DiscrGraph models (GraphEA / GraphRRG with integer levels, GraphQT) and the Float64 SimpleGraphs "
+                        "(GraphEANormal, GraphRRGNormal, GraphSKNormal) are on this path");
         return RRRMC_ERR_UNSUPPORTED;
     }
     RR_ARG(ftau, "ftau is NULL");
@@ -608,7 +619,7 @@ rrrmc_status_t chain_run_eo(rrrmc_state *s, const double *ftau, int64_t ftau_str
         RR_ARG(std::isfinite(f[g->N - 1]) && f[0] > 0, "ftau must hold the positive cumulative sums of j^-tau");
         for (int64_t j = 1; j < g->N; j++) RR_ARG(f[j] >= f[j - 1], "ftau must be non-decreasing (cumsum of j^-tau)");
     }
-    RR_TRY(chain_ensure(s, 1));
+    RR_TRY(chain_ensure(s, discr_full ? 1 : 2));
     RR_TRY(chain_sync_from_multispin(s));
     chain_store *c = s->chain;
     if (c->eo_ftau_len < ntab * g->N) {
@@ -626,6 +637,26 @@ rrrmc_status_t chain_run_eo(rrrmc_state *s, const double *ftau, int64_t ftau_str
     RR_TRY(chain_energy_init(s, P, true));
     s->ms_valid = false;
     sk_dense_invalidate(s);
+    if (!discr_full) {
+        // EOCacheCont ctor (DeltaE.jl:560-568): ΔEs = [delta_energy(X, C, i) for i = 1:N] on the device, rank = sortperm(ΔEs)
+        // on the host (once per run; the kernel keeps the order with an insertion pass per move)
+        const int64_t R = s->R, N = g->N;
+        k_chain_delta_all<<<dim3(div_up(N, 128), (unsigned)R), 128, 0, ctx->stream>>>(P, c->dEs);
+        ctx->launches++;
+        RR_CUDA(cudaGetLastError());
+        std::vector<double> hd((size_t)R * N);
+        RR_CUDA(cudaMemcpyAsync(hd.data(), c->dEs, 8 * (size_t)R * N, cudaMemcpyDeviceToHost, ctx->stream));
+        RR_CUDA(cudaStreamSynchronize(ctx->stream));
+        std::vector<int32_t> hr((size_t)R * (N + 1), 0);
+        for (int64_t r = 0; r < R; r++) {
+            int32_t *rk = hr.data() + r * (N + 1);
+            const double *v = hd.data() + r * N;
+            for (int64_t i = 0; i < N; i++) rk[i] = (int32_t)i;
+            std::stable_sort(rk, rk + N, [v](int32_t a, int32_t b) { return v[a] < v[b]; });
+        }
+        RR_CUDA(cudaMemcpyAsync(c->csj, hr.data(), 4 * (size_t)R * (N + 1), cudaMemcpyHostToDevice, ctx->stream));
+        RR_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     if (tr) { RR_TRY(chain_use_trace(s, P, *tr)); RR_TRY(chain_drive<src_trace>(s, P, nullptr, nullptr, Es, Es_cap, info)); }
     else RR_TRY(chain_drive<src_philox>(s, P, reinterpret_cast<rrrmc_hook_fn>(hook), user, Es, Es_cap, info));
     std::vector<chain_hdr> hh(s->R);

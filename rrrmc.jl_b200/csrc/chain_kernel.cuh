@@ -697,6 +697,49 @@ __global__ void __launch_bounds__(32) k_chain_run(chain_params P)
             h.E += dE;
             h.accepted++; h.it++;
         }
+    } else if (P.sampler == CHAIN_EO && !discr_full) {
+        // extremal_opt on EOCacheCont (DeltaE.jl:555-635): graphs that are not DiscrGraph. ΔEs of every spin and their
+        // sorted order `rank` (set up by the host: ΔEs from k_chain_delta_all, the initial sortperm on the host);
+        // rand_move is ONE draw — rank[searchsortedfirst(fτ, (1 - rand())·z)] (:575-587); apply_move! refreshes ΔEs of
+        // the move and its neighbours and re-sorts (sortperm!(rank, ΔEs, initialized=true), :589-606): an adaptive
+        // insertion pass over the nearly sorted permutation. With continuous couplings no two spins share a ΔE, so the
+        // order is unique and rankshuffle! (:608-633) does nothing; equal values keep their order here.
+        double *dEs = P.dEs + r * N;
+        int32_t *rank = P.csj + r * (int64_t)(N + 1);
+        const double *ft = P.eo_ftau + r * P.eo_stride;
+        const double z = ft[N - 1];
+        uint64_t *cmin = P.eo_cmin + r * P.nchunks;
+        if (!h.built) { h.Emin = h.E; h.itmin = 0; for (int64_t w = 0; w < P.nchunks; w++) cmin[w] = X.s[w]; h.built = 1; }
+        bool at_min = false;
+        for (;;) {
+            if (!h.pending) {
+                if (h.it >= iters) { h.done = 1; break; }
+                h.it++;
+                if (h.it % step == 0) { EMIT_SAMPLE(); if (emitted >= P.quota) { h.pending = 1; break; } }
+            }
+            h.pending = 0;
+            const double rr = (1 - src.f64()) * z;
+            int lo = 0, hi = N;
+            while (lo < hi) { const int m = (lo + hi) >> 1; if (ft[m] < rr) lo = m + 1; else hi = m; }
+            const int i = lo + 1;
+            if (i > N || src.err) { if (!src.err) h.status = 3; h.done = 1; break; }
+            const int move = rank[i - 1];
+            const double dE = dEs[move];
+            if (at_min && !(h.E + dE < h.Emin)) { for (int64_t w = 0; w < P.nchunks; w++) cmin[w] = X.s[w]; at_min = false; }
+            gv_spinflip(X, move);
+            dEs[move] = gv_delta_energy(X, move);
+            gv_for_neighbors(X, move, false, [&](int j) { dEs[j] = gv_delta_energy(X, j); });
+            for (int p = 1; p < N; p++) {
+                const int key = rank[p]; const double kv = dEs[key];
+                int q = p - 1;
+                while (q >= 0 && dEs[rank[q]] > kv) { rank[q + 1] = rank[q]; q--; }
+                rank[q + 1] = key;
+            }
+            h.E += dE;
+            h.accepted++;
+            if (h.E < h.Emin) { h.Emin = h.E; h.itmin = h.it; at_min = true; }
+        }
+        if (at_min) for (int64_t w = 0; w < P.nchunks; w++) cmin[w] = X.s[w];
     } else if (P.sampler == CHAIN_EO) { // extremal_opt, RRRMC.jl:494-513 on EOCache (DeltaE.jl:413-543)
         // classes in ascending ΔE (findks, DeltaE.jl:413-422): K = 2L - has_zero, ΔE = 0 is one class
         dc.N = N; dc.L = P.nDE; dc.DE = P.DE; dc.t = h.t;

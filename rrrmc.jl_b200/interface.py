@@ -934,7 +934,7 @@ def eo_ftau(N, τ):
 def extremal_opt(X, τ, iters, *, seed=DEFAULT_SEED, step=1, hook=None, C0=None, quiet=False, ftau=None, return_Es=False):
     """extremal_opt(X, τ, iters; seed, step, hook, C0, quiet) (src/RRRMC.jl:468-521) -> (C, Emin, Cmin, itmin), batched
     over the replicas (Emin, itmin are arrays when the batch holds more than one chain; τ may be one value per chain).
-    hook(it, X, C, E, Emin)::Bool. DiscrGraph models only. `ftau` overrides the table built by `eo_ftau`;
+    hook(it, X, C, E, Emin)::Bool. DiscrGraph models (EOCache) and the Float64 SimpleGraphs (EOCacheCont). `ftau` overrides the table built by `eo_ftau`;
     `return_Es=True` appends the energies at the hook instants (a test aid, not in the reference)."""
     if step < 1:
         raise ValueError("step must be ≥ 1")

@@ -111,7 +111,34 @@ def test_extremal_opt_argument_errors():
         rb.extremal_opt(X, 1.3, 10, ftau=np.ones(X.N + 3), quiet=True)
     with pytest.raises((ValueError, rb.RRRMCError)):   # decreasing table
         rb.extremal_opt(X, 1.3, 10, ftau=np.linspace(2, 1, X.N), quiet=True)
-    A, J = ea_instance(4, 2, seed=5, gaussian=True)
-    Y = rb.GraphEANormal(4, 2, replicas=2, A=A, J=J)   # not a DiscrGraph: EOCacheCont is off this path
+    Y = rb.GraphQSKT(8, 4, 0.3, 1.0, replicas=2, rng=np.random.default_rng(1))   # a DoubleGraph: not on this path
     with pytest.raises(NotImplementedError):
         rb.extremal_opt(Y, 1.3, 10, quiet=True)
+
+
+@pytest.mark.parametrize("name", ["EANormal(4,3)", "EANormal(6,2)", "SKNormal(48)"])
+@pytest.mark.parametrize("tau,step", [(1.3, 10), (2.0, 1)])
+def test_extremal_opt_cont_bit_exact_vs_oracle(name, tau, step):
+    """EOCacheCont (DeltaE.jl:555-635): extremal_opt on the Float64 SimpleGraphs — ΔEs of every spin kept sorted, one
+    draw per move. Bit-exact against the oracle's restatement (energies at the sampling instants, final configuration,
+    Emin, itmin, Cmin)."""
+    R, iters, seed = 4, 600, 777
+    if name.startswith("EANormal"):
+        L, D = (4, 3) if "4,3" in name else (6, 2)
+        A, J = ea_instance(L, D, seed=L, gaussian=True)
+        X, mk = rb.GraphEANormal(L, D, replicas=R, A=A, J=J), (lambda: ffi.Graph.ea_f64(A, J))
+    else:
+        Jm = rb.gen_J_gauss(48, np.random.default_rng(5))
+        X, mk = rb.GraphSKNormal(48, replicas=R, J=Jm), (lambda: ffi.Graph.sk_f64(Jm))
+    C0 = rb.Config(X.N, R, rng=np.random.default_rng(3))
+    ftau = rb.eo_ftau(X.N, tau)
+    Cf, Emin, Cmin, itmin, Es = rb.extremal_opt(X, tau, iters, step=step, seed=seed, C0=C0, quiet=True, return_Es=True)
+    Es = np.asarray(Es, np.float64).reshape(-1, R)
+    for r in range(R):
+        g = mk()
+        s = C0.chunks[r].copy()
+        want, cmin, res = ffi.extremal_opt(g, ftau, iters, s, ffi.PhiloxDraws(seed, chain=r), step=step)
+        assert np.array_equal(Es[:, r], want), (name, r)
+        assert np.array_equal(Cf.chunks[r], s), (name, r)
+        assert float(np.atleast_1d(Emin)[r]) == res.Emin and int(np.atleast_1d(itmin)[r]) == res.itmin, (name, r)
+        assert np.array_equal(Cmin.chunks[r], cmin), (name, r)
