@@ -257,6 +257,7 @@ def run_ours(args, rank, world, local_rank):
     # copies and transposes proceed — every step still uploads its input and downloads its result inside the timed
     # region, but the copies of step k+1 hide behind the sweeps of step k (a sampling service keeps the GPU busy this way).
     NPIPE = 2
+    sweep_lock = threading.Lock()
     pipes = [{"ctx": ctx, "X": X, "st": st, "h_in": h_in, "h_out": h_out, "h_E": h_E, "info": info}]
     for _ in range(NPIPE - 1):
         c2 = rb.Context(local_rank)
@@ -275,8 +276,10 @@ def run_ours(args, rank, world, local_rank):
                 P["ctx"].sync()
                 t.append(time.perf_counter())
         check(lib().rrrmc_state_upload(P["st"], 0, R_PER_GPU, P["h_in"].data_ptr())); mark()
-        check(lib().rrrmc_standard_mc(P["st"], ptr(betas), iters, iters, SEED + 17 * k + 1000 * rank, C.cast(None, _ffi.HOOK), None,
-                                      C.byref(opts), P["h_E"].data_ptr(), 1, C.byref(P["info"]))); mark()
+        with sweep_lock:   # one sampler call at a time per GPU: the sweep kernel is a persistent grid that fills the device, so
+            # two of them gain nothing from being in flight together; the other pipeline's copies are what overlaps
+            check(lib().rrrmc_standard_mc(P["st"], ptr(betas), iters, iters, SEED + 17 * k + 1000 * rank, C.cast(None, _ffi.HOOK), None,
+                                          C.byref(opts), P["h_E"].data_ptr(), 1, C.byref(P["info"]))); mark()
         check(lib().rrrmc_state_download(P["st"], 0, R_PER_GPU, P["h_out"].data_ptr())); mark()
         if phases is not None:
             names = ["h2d_upload_transpose", "standard_mc_sweeps_energy_d2h", "download_transpose_d2h"]
