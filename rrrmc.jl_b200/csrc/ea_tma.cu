@@ -22,6 +22,7 @@
 // without swizzling. The producer/consumer handshake is the usual full/empty mbarrier pair per stage; consumers
 // generate the (spin-independent) hit masks of a brick's two tasks BEFORE waiting for its data.
 #include <cuda.h>
+#include <mutex>
 #include <vector>
 #include "kernels.cuh"
 #include "ea_poisson_core.cuh"
@@ -764,6 +765,15 @@ rrrmc_status_t launch_checkerboard_flow(rrrmc_state *s, cbt_params &P, uint64_t 
             for (int k = 0; k < ngroups; k++) memcpy(c->ladder_key.data() + (size_t)k * CBP_LEN, groups[k].tbl, sizeof(uint32_t) * CBP_LEN);
         }
     }
+    // A persistent grid whose blocks wait for each other must never share the device with a second one of its kind: two
+    // half-resident grids (launched from two streams / contexts of this process) would wait for blocks that cannot become
+    // resident. Launches are therefore chained device-wide: each waits for the previous one's completion event.
+    static std::mutex flow_mu;
+    static cudaEvent_t flow_done[64] = {};
+    std::lock_guard<std::mutex> flow_lock(flow_mu);
+    const int dev = ctx->device & 63;
+    if (!flow_done[dev]) RR_CUDA(cudaEventCreateWithFlags(&flow_done[dev], cudaEventDisableTiming));
+    else RR_CUDA(cudaStreamWaitEvent(ctx->stream, flow_done[dev], 0));
     cbf_params F;
     memset(&F, 0, sizeof F);
     F.T = P; F.m_y6z = c->m_y6z; F.bricks = c->d_bricks; F.done = c->d_done;
@@ -796,5 +806,6 @@ rrrmc_status_t launch_checkerboard_flow(rrrmc_state *s, cbt_params &P, uint64_t 
         c->epoch += F.nhalf;
         left -= n; sw += (uint64_t)n;
     }
+    RR_CUDA(cudaEventRecord(flow_done[dev], ctx->stream));
     return RRRMC_OK;
 }
