@@ -149,6 +149,13 @@ __device__ __forceinline__ void cbp_flip_parts(const uint32_t (&b)[6], uint32_t 
     tt = lop3p<0xE0>(ks, s3, g);                                              // ks & (s3 | g)
 }
 
+// the rare part of a task's flip: lanes with a level-3 hit flip unconditionally. Out of line on purpose (see the caller);
+// everything by value, so that the call moves registers and not a stack frame. Returns kc | tt | h.
+static __device__ __noinline__ uint4 cbp_merge_level3(uint4 kc, uint4 tt, uint4 h)
+{
+    return make_uint4(kc.x | tt.x | h.x, kc.y | tt.y | h.y, kc.z | tt.z | h.z, kc.w | tt.w | h.w);
+}
+
 // Spin-independent half of a task: the hit masks of (site c1, group c2). Returns true when the task left the fast
 // path (only then can h, the level-3 hits, be non-zero).
 // Three tiers. (1) The fast path above: branch free. (2) A lane with more hits than static slots would stall its whole

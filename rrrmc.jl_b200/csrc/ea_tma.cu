@@ -508,12 +508,15 @@ __global__ void __launch_bounds__(NFLOW, MINB) k_checkerboard_flow(const __grid_
                     cbp_flip_parts(bp[w], m[j][w], gg[j][w], kc[w], tt[w]);
                     ns[w] = lop3p<0x1E>(sc[w], kc[w], tt[w]);
                 }
-                if (wslow[j]) {                              // a uniform branch, taken by ~13 % of the warps at β = 1
-                    asm volatile("" ::: "memory");
-                    if (slow[j]) {
-#pragma unroll
-                        for (int w = 0; w < 4; w++) { tt[w] |= h[j][w]; ns[w] = lop3p<0x1E>(sc[w], kc[w], tt[w]); }   // a level-3 hit flips its lane whatever the bonds say
-                    }
+                // a level-3 hit flips its lane whatever the bonds say. A uniform branch, taken by ~13 % of the warps at
+                // β = 1, and kept a BRANCH (an out-of-line call): if-converted, its eight LOP3 would take issue slots in
+                // every task, and integer issue is what bounds the kernel
+                if (wslow[j]) {
+                    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+                    const uint4 f = cbp_merge_level3(make_uint4(kc[0], kc[1], kc[2], kc[3]), make_uint4(tt[0], tt[1], tt[2], tt[3]),
+                                                     slow[j] ? make_uint4(h[j][0], h[j][1], h[j][2], h[j][3]) : z4);
+                    ns[0] = sc[0] ^ f.x; ns[1] = sc[1] ^ f.y; ns[2] = sc[2] ^ f.z; ns[3] = sc[3] ^ f.w;
+                    kc[0] = f.x; kc[1] = f.y; kc[2] = f.z; kc[3] = f.w;      // (the flip mask, for FLIPS)
                 }
                 const uint32_t idx = (j ? i1 : i0) * W4 + grp;
                 spins4[idx] = make_uint4(ns[0], ns[1], ns[2], ns[3]);
