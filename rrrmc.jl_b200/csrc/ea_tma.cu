@@ -72,13 +72,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 // compete with the consumer warps of its scheduler for issue slots (measured: 58 polls per brick without it)
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity)
 {
+    // try_wait with a suspend-time hint: the lane is parked by the hardware until the phase completes (or the hint
+    // expires) instead of polling (a __nanosleep(128) loop still issued an instruction every ~10 cycles)
     for (;;) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
         if (ok) break;
-        __nanosleep(128);
     }
 }
 __device__ __forceinline__ void tma_load5(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3, int c4)
@@ -347,12 +348,12 @@ __global__ void __launch_bounds__(NFLOW, MINB) k_checkerboard_flow(const __grid_
                     const int s = (int)(q & 1u);
                     const uint32_t sb = sm0 + s * STAGE_BYTES, full = bars + 8 * s, empty = bars + 16 + 8 * s;
                     if (hs > 0u) {
-                        while ((int32_t)(lds_volatile(gate) - (q + 1u)) < 0) __nanosleep(64);
+                        while ((int32_t)(lds_volatile(gate) - (q + 1u)) < 0) __nanosleep(500);
                         asm volatile("fence.acq_rel.cta;" ::: "memory");          // the gatekeeper's acquire, handed on
                         asm volatile("fence.proxy.async.global;" ::: "memory");   // the neighbours' generic-proxy stores, then TMA reads
                     }
                     if (q >= 2u) mbar_wait_sleep(empty, ((q >> 1) - 1u) & 1u);
-                    if (q >= 3u) while ((int32_t)(lds_volatile(pub) - (q - 2u)) < 0) __nanosleep(64);   // the publisher is at most 3 bricks behind
+                    if (q >= 3u) while ((int32_t)(lds_volatile(pub) - (q - 2u)) < 0) __nanosleep(500);   // the publisher is at most 3 bricks behind
                     const int slab = (int)e0.y, b = (int)e0.z;
                     const int x0 = (int)(e0.w & 1023u), y0 = (int)((e0.w >> 10) & 1023u), z0 = (int)(e0.w >> 20);
                     {
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(NFLOW, MINB) k_checkerboard_flow(const __grid_
                     for (int i = 0; i < 7; i++) worst = min(worst, (int32_t)(v[j][i] - need[j]));
                     if (valid[j] && worst >= 0 && n == j) n = j + 1;
                 }
-                if (n == 0) { __nanosleep(400); continue; }     // at the frontier: do not compete with the consumers for issue slots
+                if (n == 0) { __nanosleep(1000); continue; }     // at the frontier: do not compete with the consumers for issue slots
                 asm volatile("fence.acq_rel.gpu;" ::: "memory");
                 gq += (uint32_t)n;
                 for (int j = 0; j < n; j++) if (++gk == nk) { gk = 0; ghs++; }
