@@ -557,8 +557,8 @@ rrrmc_status_t chain_run(rrrmc_state *s, int sampler, const double *beta, int64_
     sk_dense_invalidate(s);
     if (o->site_pick == RRRMC_PICK_RANK) {
         if (!chain_warp_eligible(s, sampler)) {
-            rrrmc_set_error("site_pick = RANK (the warp-cooperative kernel) takes rrrMC / bklMC on a ±J GraphEA lattice with L >= 3, D <= 3 "
-                            "whose chain state fits shared memory (N <= ~110000)");
+            rrrmc_set_error("site_pick = RANK (the warp-cooperative kernel) takes rrrMC / bklMC on ±J graphs — GraphEA lattices with L >= 3, "
+                            "GraphRRG with 2..6 distinct neighbours and no zero coupling — whose chain state fits shared memory (N <= ~110000)");
             return RRRMC_ERR_UNSUPPORTED;
         }
         P.fast = 2; P.jcode = g->d_jcode; P.latL = g->L;

@@ -17,7 +17,9 @@
 //  * the counter-based draw stream (philox.cuh:chain_rng, draw n = Philox(n, chain)) is generated 32 draws at a time,
 //    one per lane, and consumed by shuffle.
 // Sampling instants, hook protocol (the kernel pauses after `quota` samples and resumes from the header) and the draw
-// order are those of k_chain_ea / k_chain_run. Eligibility: chain_warp_eligible().
+// order are those of k_chain_ea / k_chain_run. Two instantiations: GraphEA lattices (neighbours and bond signs from the
+// site index and the byte: shared memory only) and any ±J graph given by its adjacency table (GraphRRG, the benchmark
+// family of the RRR paper: A and J8 through L1/L2). Eligibility: chain_warp_eligible().
 #include <algorithm>
 #include <cmath>
 #include "chain.cuh"
@@ -33,11 +35,13 @@ struct warp_smem {
     int *cnt;                    // [WK][NB] members per 1024-site block
 };
 
-__device__ __forceinline__ int wclass(int D, int u, int sb)
+// class of a site (DeltaE.jl:108-118) from its degree K, its number u of unsatisfied bonds and its spin: ΔE = 2(K - 2u),
+// allΔE = {0, 4, ..} (even K) or {2, 6, ..} (odd K), so the index of |ΔE| in allΔE is |K - 2u| >> 1
+__device__ __forceinline__ int wclass(int K, int u, int sb)
 {
-    const int a = D - u, aa = a < 0 ? -a : a;
+    const int a = K - 2 * u, aa = (a < 0 ? -a : a) >> 1;
     const int up = a > 0 || (a == 0 && sb == 1);
-    return aa + 1 + (D + 1) * up;
+    return aa + 1 + ((K >> 1) + 1) * up;
 }
 
 // 32 draws of the chain's stream at a time: lane l holds draw number base + l
@@ -124,10 +128,12 @@ __device__ __forceinline__ int rank_select(const uint32_t *bmk, const int *cntk,
 
 struct warp_hdr { double E, pdE; long long it, accepted, nextstep, skip; int pending, pmove; };
 
-template <int D>
+// LAT: a GraphEA lattice — neighbours and bond signs come from the site index and the byte's forward-bond bits (shared
+// memory only); else any ±J graph of degree TWOD given by its adjacency table (GraphRRG: A and J8 through L1/L2)
+template <int TWOD, bool LAT>
 __global__ void __launch_bounds__(32) k_chain_warp(chain_params P)
 {
-    constexpr int TWOD = 2 * D, LC = D + 1, NK = 2 * LC;
+    constexpr int D = TWOD / 2, LC = (TWOD >> 1) + 1, NK = 2 * LC;
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x;
     const int64_t r = P.chain0 + blockIdx.x;
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(32) k_chain_warp(chain_params P)
 
     // ---- build the chain state from the configuration (every launch: the configuration is all that is kept) ----
     for (int i = lane; i < N; i += 32) {
-        const uint8_t jc = P.jcode[i];
+        const uint8_t jc = LAT ? P.jcode[i] : (uint8_t)0;
         const int sb = (int)((chunks[i >> 6] >> (i & 63)) & 1ull);
         S.st[i] = (uint8_t)((jc & 1) | ((jc >> 1) & 2) | ((jc >> 2) & 4) | (sb << 6));
     }
@@ -158,23 +164,31 @@ __global__ void __launch_bounds__(32) k_chain_warp(chain_params P)
         for (int b = 0; b < 32; b++) {
             const int i = 32 * w + b;
             if (i >= N) break;
-            int co[3], rem = i;
-#pragma unroll
-            for (int d = 0; d < D; d++) { co[d] = rem % L; rem /= L; }
             const int bi = S.st[i], si = (bi >> 6) & 1;
-            int u = 0, stride = 1;
+            int u = 0;
+            if (LAT) {
+                int co[3], rem = i, stride = 1;
 #pragma unroll
-            for (int d = 0; d < D; d++) {
-                const int up = i + ((co[d] + 1 == L ? 0 : co[d] + 1) - co[d]) * stride;
-                const int dn = i + ((co[d] == 0 ? L - 1 : co[d] - 1) - co[d]) * stride;
-                const int bu = S.st[up], bd = S.st[dn];
-                u += (si ^ ((bu >> 6) & 1)) ^ ((bi >> d) & 1);
-                u += (si ^ ((bd >> 6) & 1)) ^ ((bd >> d) & 1);
-                stride *= L;
+                for (int d = 0; d < D; d++) { co[d] = rem % L; rem /= L; }
+#pragma unroll
+                for (int d = 0; d < D; d++) {
+                    const int up = i + ((co[d] + 1 == L ? 0 : co[d] + 1) - co[d]) * stride;
+                    const int dn = i + ((co[d] == 0 ? L - 1 : co[d] - 1) - co[d]) * stride;
+                    const int bu = S.st[up], bd = S.st[dn];
+                    u += (si ^ ((bu >> 6) & 1)) ^ ((bi >> d) & 1);
+                    u += (si ^ ((bd >> 6) & 1)) ^ ((bd >> d) & 1);
+                    stride *= L;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < TWOD; q++) {
+                    const int y = P.A[(int64_t)i * TWOD + q];
+                    u += (si ^ ((S.st[y] >> 6) & 1)) ^ (P.J8[(int64_t)i * TWOD + q] < 0 ? 1 : 0);
+                }
             }
             // (the other lanes only read bits 0-2 and 6 of this byte during the pass)
             S.st[i] = (uint8_t)(bi | (u << 3));
-            const int k = wclass(D, u, si);
+            const int k = wclass(TWOD, u, si);
 #pragma unroll
             for (int kk = 0; kk < NK; kk++) if (kk + 1 == k) wk[kk] |= 1u << b;
         }
@@ -218,7 +232,7 @@ __global__ void __launch_bounds__(32) k_chain_warp(chain_params P)
         int k;
         if (hit) k = __ffs(hit);
         else k = 32 - __clz(__ballot_sync(FULLMASK, lane < NK && myt > 0));   // rounding: the last non-empty class
-        dE = k <= LC ? -4.0 * (double)(k - 1) : 4.0 * (double)(k - LC - 1);
+        dE = k <= LC ? -P.DE[k - 1] : P.DE[k - LC - 1];
         const int tk = __shfl_sync(FULLMASK, myt, k - 1);
         const int p = (int)src.range(tk, lane);
         return rank_select(S.bm + (size_t)(k - 1) * NW32, S.cnt + (k - 1) * NB, NB, NW32, p, lane);
@@ -229,25 +243,31 @@ __global__ void __launch_bounds__(32) k_chain_warp(chain_params P)
         const int bm_ = S.st[move], sm = (bm_ >> 6) & 1;
         int kk = 0;                                   // k0 | k1 << 4 of this lane's entry (0: no entry)
         if (lane < TWOD) {
-            const int d = lane >> 1, dir = lane & 1;
-            int c, stride;
-            if (pow2) { stride = 1 << (d * lsh); c = (move >> (d * lsh)) & (L - 1); }
-            else {
-                int rem = move; stride = 1; c = 0;
-                for (int q = 0; q <= d; q++) { c = rem % L; rem /= L; if (q < d) stride *= L; }
+            int neg;
+            if (LAT) {
+                const int d = lane >> 1, dir = lane & 1;
+                int c, stride;
+                if (pow2) { stride = 1 << (d * lsh); c = (move >> (d * lsh)) & (L - 1); }
+                else {
+                    int rem = move; stride = 1; c = 0;
+                    for (int q = 0; q <= d; q++) { c = rem % L; rem /= L; if (q < d) stride *= L; }
+                }
+                const int cn = dir == 0 ? (c + 1 == L ? 0 : c + 1) : (c == 0 ? L - 1 : c - 1);
+                ej = move + (cn - c) * stride;
+                neg = dir == 0 ? (bm_ >> d) & 1 : (S.st[ej] >> d) & 1;
+            } else {
+                ej = P.A[(int64_t)move * TWOD + lane];
+                neg = P.J8[(int64_t)move * TWOD + lane] < 0 ? 1 : 0;
             }
-            const int cn = dir == 0 ? (c + 1 == L ? 0 : c + 1) : (c == 0 ? L - 1 : c - 1);
-            ej = move + (cn - c) * stride;
             const int by = S.st[ej], sy = (by >> 6) & 1, uy = (by >> 3) & 7;
-            const int neg = dir == 0 ? (bm_ >> d) & 1 : (by >> d) & 1;
             const int unsat = (sm ^ sy) ^ neg;
             const int u1 = uy + (unsat ? -1 : 1);
-            ek0 = wclass(D, uy, sy); ek1 = wclass(D, u1, sy);
+            ek0 = wclass(TWOD, uy, sy); ek1 = wclass(TWOD, u1, sy);
             ebyte = (by & ~(7 << 3)) | (u1 << 3);
             kk = ek0 | ek1 << 4;
         } else if (lane == TWOD) {
             const int um = (bm_ >> 3) & 7, u1 = TWOD - um;
-            ej = move; ek0 = wclass(D, um, sm); ek1 = wclass(D, u1, sm ^ 1);
+            ej = move; ek0 = wclass(TWOD, um, sm); ek1 = wclass(TWOD, u1, sm ^ 1);
             ebyte = ((bm_ & 7) | (u1 << 3) | ((sm ^ 1) << 6));
             kk = ek0 | ek1 << 4;
         }
@@ -351,12 +371,23 @@ size_t warp_smem_bytes(int N)
 
 } // namespace
 
+// lattice path: GraphEA ±J with L >= 3 (neighbours from the site index); graph path: any ±J GraphEA / GraphRRG whose rows
+// hold 2..6 pairwise distinct neighbours and no zero coupling
+static bool warp_is_lattice(const rrrmc_graph *g) { return g->d_jcode && g->L >= 3 && g->D >= 1 && g->D <= 3; }
 bool chain_warp_eligible(const rrrmc_state *s, int sampler)
 {
     const rrrmc_graph *g = s->g;
     if (!(sampler == CHAIN_RRR || sampler == CHAIN_BKL)) return false;
-    if (g->kind != RRRMC_EA_PM1 || !g->d_jcode || g->L < 3 || g->D < 1 || g->D > 3) return false;
-    return warp_smem_bytes((int)g->N) <= 227 * 1024 - 1024;
+    if (g->kind != RRRMC_EA_PM1 || g->N >= ((int64_t)1 << 24)) return false;
+    if (warp_smem_bytes((int)g->N) > 227 * 1024 - 1024) return false;
+    if (warp_is_lattice(g)) return true;
+    if (g->twoD < 2 || g->twoD > 6) return false;
+    for (int64_t i = 0; i < g->N; i++)
+        for (int k = 0; k < g->twoD; k++) {
+            if (g->Ji[i * g->twoD + k] != 1 && g->Ji[i * g->twoD + k] != -1) return false;
+            for (int q = 0; q < k; q++) if (g->A0[i * g->twoD + q] == g->A0[i * g->twoD + k]) return false;
+        }
+    return true;
 }
 
 rrrmc_status_t chain_warp_launch(rrrmc_state *s, const chain_params &P)
@@ -364,17 +395,26 @@ rrrmc_status_t chain_warp_launch(rrrmc_state *s, const chain_params &P)
     const rrrmc_graph *g = s->g;
     cudaStream_t st = g->ctx->stream;
     const size_t sm = warp_smem_bytes(P.N);
-    static size_t configured[4] = { 0, 0, 0, 0 };
+    const bool lat = warp_is_lattice(g);
+    static size_t configured[2][8] = {};
     auto go = [&](auto kern) -> cudaError_t {
-        if (configured[g->D] < sm) {
+        if (configured[lat][g->twoD] < sm) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
             if (e != cudaSuccess) return e;
-            configured[g->D] = sm;
+            configured[lat][g->twoD] = sm;
         }
         kern<<<(unsigned)P.R, 32, sm, st>>>(P);
         return cudaGetLastError();
     };
-    cudaError_t e = g->D == 3 ? go(k_chain_warp<3>) : (g->D == 2 ? go(k_chain_warp<2>) : go(k_chain_warp<1>));
+    cudaError_t e;
+    if (lat) e = g->D == 3 ? go(k_chain_warp<6, true>) : (g->D == 2 ? go(k_chain_warp<4, true>) : go(k_chain_warp<2, true>));
+    else switch (g->twoD) {
+        case 2: e = go(k_chain_warp<2, false>); break;
+        case 3: e = go(k_chain_warp<3, false>); break;
+        case 4: e = go(k_chain_warp<4, false>); break;
+        case 5: e = go(k_chain_warp<5, false>); break;
+        default: e = go(k_chain_warp<6, false>); break;
+    }
     RR_CUDA(e);
     return RRRMC_OK;
 }

@@ -107,8 +107,10 @@ if "rrg" in which:
     scale = 10 if quick else 1
     runs = (("standardMC", lambda it, **kw: rb.standardMC(X, beta, it, schedule="random", **kw), 20_000_000 // scale),
             ("rrrMC", lambda it, **kw: rb.rrrMC(X, beta, it, **kw), 2_000_000 // scale),
-            ("bklMC", lambda it, **kw: rb.bklMC(X, beta, it, **kw), 40_000_000 // scale))
-    for name, fn, iters in runs:
+            ("bklMC", lambda it, **kw: rb.bklMC(X, beta, it, **kw), 40_000_000 // scale),
+            ("rrrMC", lambda it, **kw: rb.rrrMC(X, beta, it, site_pick="rank", **kw), 2_000_000 // scale),
+            ("bklMC", lambda it, **kw: rb.bklMC(X, beta, it, site_pick="rank", **kw), 40_000_000 // scale))
+    for irun, (name, fn, iters) in enumerate(runs):
         fn(iters // 20, step=iters // 20, seed=2, C0=C, quiet=True)
         Es, _ = fn(iters, step=iters, seed=3, C0=C, quiet=True)
         info = X.last_run
@@ -117,7 +119,7 @@ if "rrg" in which:
         t0 = time.perf_counter()
         _, res = getattr(ffi, name)(g, beta, cpu_it, s0, ffi.PhiloxDraws(3, chain=0), step=cpu_it)
         cdt = time.perf_counter() - t0
-        emit(config="RRG", sampler=name, N=N, K=K, replicas=R, beta=beta, iters_per_replica=iters,
+        emit(config="RRG", sampler=name, site_pick="rank (k_chain_warp)" if irun >= 3 else "reference", N=N, K=K, replicas=R, beta=beta, iters_per_replica=iters,
              iterations_per_s=R * iters / (info.device_ms * 1e-3), executed_moves_per_s=info.accepted_total / (info.device_ms * 1e-3),
              device_ms=info.device_ms, cpu_oracle_1core_iterations_per_s=cpu_it / cdt, cpu_oracle_1core_moves_per_s=res.accepted / cdt)
     samples = 40 // (4 if quick else 1)

@@ -39,6 +39,27 @@ def test_rank_kernel_bit_exact_vs_cpu_model(L, D, sampler):
     assert X.last_run.accepted_total == sum(r.accepted for r in res)
 
 
+@pytest.mark.parametrize("N,K", [(40, 3), (30, 4), (50, 5), (24, 6), (64, 2)])
+@pytest.mark.parametrize("sampler", ["rrr", "bkl"])
+def test_rank_kernel_on_rrg_bit_exact_vs_cpu_model(N, K, sampler):
+    """The adjacency-table instantiation: ±J GraphRRG of degree 2..6 (odd degrees: allΔE = 2, 6, ..: no zero class)."""
+    R, beta, iters, step = 4, 1.5, 3000, 100
+    rng = np.random.default_rng(100 * N + K)
+    A = rb.gen_RRG(N, K, rng)
+    J = rb.gen_J_graph(lambda n: rng.choice([-1.0, 1.0], n), A).astype(np.int64)
+    X = rb.GraphRRG(N, K, replicas=R, A=A, J=J)
+    g = ffi.Graph.rrg_int(A, J)
+    C0 = rb.Config(X.N, R, rng=np.random.default_rng(5))
+    if sampler == "rrr":
+        Es, Cf = rb.rrrMC(X, beta, iters, step=step, seed=17, C0=C0, quiet=True, site_pick="rank")
+        wantE, wantC, _ = _oracle(ffi.rank_rrrMC, g, beta, iters, step, C0, 17, R)
+    else:
+        Es, Cf = rb.bklMC(X, beta, iters, step=step, seed=17, C0=C0, quiet=True, site_pick="rank")
+        wantE, wantC, _ = _oracle(ffi.rank_bklMC, g, beta, iters, step, C0, 17, R)
+    assert np.array_equal(np.asarray(Es, np.float64), wantE)
+    assert np.array_equal(Cf.chunks, wantC)
+
+
 def test_rank_kernel_per_replica_beta_and_hook():
     """Per-replica β, a hook after every sample (the kernel pauses and rebuilds its shared-memory state from the
     configuration at every launch) and an early stop."""
@@ -91,7 +112,7 @@ def test_rank_kernel_baseline_config3_size():
 
 
 def test_rank_kernel_rejects_what_it_cannot_take():
-    X = rb.GraphEA(2, 3, replicas=2, rng=np.random.default_rng(1))       # L = 2: double bonds
+    X = rb.GraphEA(2, 3, replicas=2, rng=np.random.default_rng(1))       # L = 2: double bonds (repeated neighbours)
     with pytest.raises(Exception, match="site_pick = RANK"):
         rb.rrrMC(X, 1.0, 10, site_pick="rank", quiet=True)
     Xn = rb.GraphEANormal(4, 2, replicas=2, rng=np.random.default_rng(1))
