@@ -523,3 +523,32 @@ def test_tempered_checkerboard_orders_the_ladder():
     assert np.all(np.diff(E) < 0)
     rate = acc / att
     assert np.all(rate > 0.05) and np.all(rate <= 1.0)
+
+
+def test_checkerboard_ladder_full_size_bit_exact():
+    """BASELINE configs[1] at size with a β ladder: L = 64, R = 1024, eight distinct β (0.8 … 1.6, NW = 4), one sweep of the
+    multi-sweep brick kernel with per-group tables against orc_checkerboard_sweeps_poisson_ladder, then a tempering
+    exchange whose decisions are checked against orc_tempering_decide on the device's own energies."""
+    L, D, R = 64, 3, 1024
+    A, J = ea_instance(L, D, seed=64)
+    X = rb.GraphEA(L, D, replicas=R, A=A, J=J)
+    C0 = rb.Config(X.N, R, rng=np.random.default_rng(2))
+    bg = np.geomspace(0.8, 1.6, 8)
+    tbls = _ladder_tbls(bg)
+    X._upload(C0)
+    check(lib().rrrmc_checkerboard_sweeps_poisson_ladder(X._state, ptr(tbls), 8, 4, 0xABCDEF, 5, 1))
+    got = X._download()
+    sp = _multispin(C0)
+    ffi.checkerboard_sweeps_poisson_ladder(L, D, R, sp, _fwd(A, J, L, D), tbls, 4, 0xABCDEF, 5, 1)
+    assert got == _from_multispin(sp, R)
+    E = rb.energy(X, got)
+    want = ffi.tempering_decide(bg, E, 3, 0).astype(np.int64)
+    acc = np.zeros(7, np.int64)
+    check(lib().rrrmc_tempering_exchange(X._state, ptr(bg), 8, 3, 0, ptr(acc)))
+    assert np.array_equal(acc, want.sum(axis=1))
+    after = X._download()
+    perm = np.arange(R)
+    for g in range(7):
+        for l in np.nonzero(want[g])[0]:
+            perm[128 * g + l], perm[128 * (g + 1) + l] = perm[128 * (g + 1) + l], perm[128 * g + l]
+    assert np.array_equal(np.asarray(after.chunks), np.asarray(got.chunks)[perm])
