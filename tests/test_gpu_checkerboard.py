@@ -552,3 +552,35 @@ def test_checkerboard_ladder_full_size_bit_exact():
         for l in np.nonzero(want[g])[0]:
             perm[128 * g + l], perm[128 * (g + 1) + l] = perm[128 * (g + 1) + l], perm[128 * g + l]
     assert np.array_equal(np.asarray(after.chunks), np.asarray(got.chunks)[perm])
+
+
+def test_two_contexts_run_the_multi_sweep_kernel_from_two_threads():
+    """Two batches on two contexts (two streams) driven by two host threads at once, as bench.py's end-to-end arm does:
+    the persistent multi-sweep kernels are chained device-wide (two half-resident cooperative grids would wait for each
+    other forever), and every batch still reproduces the oracle's trajectory."""
+    import threading
+    L, D, R, beta, NW, nsw = 16, 3, 1024, 1.0, 2, 6
+    A, J = ea_instance(L, D, seed=3)
+    tbl = _poisson_tbl(beta, D)
+    Xs = [rb.GraphEA(L, D, replicas=R, A=A, J=J, ctx=rb.Context(0)) for _ in range(2)]
+    C0s = [rb.Config(Xs[0].N, R, rng=np.random.default_rng(40 + k)) for k in range(2)]
+    out, errs = [None, None], []
+
+    def work(k):
+        try:
+            Xs[k]._upload(C0s[k])
+            for rep in range(5):
+                check(lib().rrrmc_checkerboard_sweeps_poisson(Xs[k]._state, ptr(tbl), len(tbl), NW, 100 + k, rep * nsw, nsw))
+            out[k] = Xs[k]._download()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert not errs and all(not t.is_alive() for t in th)
+    for k in range(2):
+        sp = _multispin(C0s[k])
+        ffi.checkerboard_sweeps_poisson(L, D, R, sp, _fwd(A, J, L, D), tbl, NW, 100 + k, 0, 5 * nsw)
+        assert out[k] == _from_multispin(sp, R)
