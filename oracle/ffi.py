@@ -126,6 +126,8 @@ def lib():
         "orc_dfloat_to_f64": (f64, [i64]),
         "orc_dfloat_div_int": (i64, [i64, i64]),
         "orc_dfloat_ea_energy": (f64, [i64, i32, p(np.int64), p(np.float64), p(np.uint64), vp]),
+        "orc_sk_lockstep_sweeps": (None, [i32, i64, p(np.float64), p(np.uint64), i64, p(np.float64), p(np.float64), p(np.int64),
+                                          p(np.float64), C.c_uint64, C.c_uint64, i64]),
         "orc_tempering_decide": (None, [i64, p(np.float64), p(np.float64), C.c_uint64, C.c_uint64, p(np.uint8)]),
         "orc_checkerboard_sweeps_f64": (None, [i32, i32, i64, p(np.uint32), p(np.int64), p(np.float64), p(np.float64),
                                                C.c_uint64, C.c_uint64, i64, vp]),
@@ -541,6 +543,15 @@ def dfloat_ea_energy(A, J, s, fields=False):
     lf2 = np.zeros(N, np.int64)
     E = lib().orc_dfloat_ea_energy(N, twoD, A, J, s, lf2.ctypes.data if fields else None)
     return (E, lf2 / 1e5) if fields else E
+
+
+def sk_lockstep_sweeps(J, chunks, lf, E, acc, beta, seed, sweep0, nsweeps):
+    """CPU model of the engine's lock-step Metropolis sweeps on GraphSKNormal; chunks [R, nchunks] uint64, lf [R, N], E and
+    acc [R] are updated in place."""
+    J = np.ascontiguousarray(J, np.float64); N = J.shape[0]; R = chunks.shape[0]
+    b = np.ascontiguousarray(np.broadcast_to(np.asarray(beta, np.float64), (R,)))
+    assert chunks.dtype == np.uint64 and lf.shape == (R, N) and E.dtype == np.float64 and acc.dtype == np.int64
+    lib().orc_sk_lockstep_sweeps(N, R, J, chunks, chunks.shape[1], lf, E, acc, b, seed, sweep0, nsweeps)
 
 
 def tempering_decide(beta_group, E, seed, round_):

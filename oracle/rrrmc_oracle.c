@@ -1889,6 +1889,49 @@ void orc_checkerboard_sweeps_f64(int L, int D, int64_t R, uint32_t *spins, const
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Lock-step Metropolis sweeps on GraphSKNormal, CPU model of rrrmc.jl_b200/csrc/sk_dense.cu:k_sk_lockstep*.
+ * Every sweep visits the sites in order 1..N (the same site for every replica of the batch); per (site, replica):
+ *   ΔE = lfields[i]                                   (delta_energy, SK.jl:278-284)
+ *   accept(-βΔE): ΔE <= 0 flips, else u < exp(-βΔE)   (RRRMC.jl:39), u = 53-bit uniform from
+ *     Philox4x32-10(counter = (site, replica, t_lo, t_hi ^ "SKLS"), key = seed): (y:x) >> 11 · 2^-53
+ *   on a flip: E += ΔE, s[i] ^= 1, then update_cache! (SK.jl:252-265): lfields[j] += 4·(1 - 2(s_i ⊻ s_j))·J[i][j] for
+ *   j != i with s_i the NEW spin, lfields[i] = -lfields[i].
+ * chunks: [R][nchunks] packed spins (bit j of a replica = site j), lf: [R][N] fields, E / acc / beta: per replica.
+ * ---------------------------------------------------------------------------------------- */
+void orc_sk_lockstep_sweeps(int N, int64_t R, const double *J, uint64_t *chunks, int64_t nchunks, double *lf, double *E,
+                            int64_t *acc, const double *beta, uint64_t seed, uint64_t sweep0, int64_t nsweeps)
+{
+    const uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    for (int64_t r = 0; r < R; r++) {
+        uint64_t *s = chunks + r * nchunks; double *f = lf + r * (int64_t)N;
+        for (int64_t sw = 0; sw < nsweeps; sw++) {
+            const uint64_t t = sweep0 + (uint64_t)sw;
+            for (int i = 0; i < N; i++) {
+                const double dE = f[i], x = -beta[r] * dE;
+                int flip = x >= 0;
+                if (!flip) {
+                    uint32_t ctr[4] = { (uint32_t)i, (uint32_t)r, (uint32_t)t, (uint32_t)(t >> 32) ^ 0x534b4c53u }, o[4];
+                    orc_philox4x32_10(ctr, key, o);
+                    const double u = (double)((((uint64_t)o[1] << 32) | o[0]) >> 11) * 0x1.0p-53;
+                    flip = u < exp(x);
+                }
+                if (!flip) continue;
+                E[r] += dE; acc[r]++;
+                s[i >> 6] ^= 1ull << (i & 63);
+                const int si = (int)((s[i >> 6] >> (i & 63)) & 1ull);
+                const double *Ji = J + (int64_t)i * N;
+                for (int j = 0; j < N; j++) {
+                    if (j == i) continue;
+                    const int sj = (int)((s[j >> 6] >> (j & 63)) & 1ull);
+                    f[j] = f[j] + 4 * ((double)(1 - 2 * (si ^ sj)) * Ji[j]);
+                }
+                f[i] = -f[i];
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * Parallel-tempering exchange decisions, CPU model of rrrmc.jl_b200/csrc/tempering.cu:k_pt_decide.
  * A β ladder lies over the 128-replica groups of a batch: lane l of every group is one ladder, group g its rung.
  * Pairs (g, g+1) with g ≡ round (mod 2): a = replica 128 g + l, b = replica 128 (g+1) + l,

@@ -17,7 +17,9 @@
 #define RRRMC_ORACLE_H
 #include <stdint.h>
 #ifdef __cplusplus
-extern "C" {
+extern "C" {void orc_sk_lockstep_sweeps(int N, int64_t R, const double *J, uint64_t *chunks, int64_t nchunks, double *lf, double *E,
+                            int64_t *acc, const double *beta, uint64_t seed, uint64_t sweep0, int64_t nsweeps);
+
 #endif
 
 enum {
@@ -194,7 +196,9 @@ void orc_checkerboard_sweeps_f64(int L, int D, int64_t R, uint32_t *spins, const
                                  const double *beta, uint64_t seed, uint64_t sweep0, int64_t nsweeps, int64_t *accepted);
 
 #ifdef __cplusplus
-}
+}void orc_sk_lockstep_sweeps(int N, int64_t R, const double *J, uint64_t *chunks, int64_t nchunks, double *lf, double *E,
+                            int64_t *acc, const double *beta, uint64_t seed, uint64_t sweep0, int64_t nsweeps);
+
 #endif
 /* parallel-tempering exchange decisions: CPU model of csrc/tempering.cu */
 void orc_tempering_decide(int64_t G, const double *beta_group, const double *E, uint64_t seed, uint64_t round, uint8_t *swap);
@@ -213,5 +217,7 @@ int64_t orc_dfloat_sub(int64_t a, int64_t b);
 int64_t orc_dfloat_mul_int(int64_t k, int64_t a);
 int64_t orc_dfloat_div_int(int64_t a, int64_t k);
 double orc_dfloat_ea_energy(int64_t N, int twoD, const int64_t *A, const double *J, const uint64_t *s, int64_t *lf2);
+void orc_sk_lockstep_sweeps(int N, int64_t R, const double *J, uint64_t *chunks, int64_t nchunks, double *lf, double *E,
+                            int64_t *acc, const double *beta, uint64_t seed, uint64_t sweep0, int64_t nsweeps);
 
 #endif

@@ -441,6 +441,379 @@ __global__ void __launch_bounds__(512, 1) k_sk_lockstep_tma(sk_ls_params P)
     if (tid < RPC && rbase + tid < P.R) { P.E[rbase + tid] = E; P.acc[rbase + tid] = nacc; }
 }
 
+// The same sweeps, software-pipelined across sites: ONE block barrier per site instead of two, and the Metropolis decision
+// of site i+1 (an exp and a Philox call on RPC lanes) runs while the other sixteen warps apply the row of site i.
+// The decision of site i+1 needs lf[r][i+1] with every accepted flip up to site i applied; the flips before i were applied
+// by earlier bulk updates (complete at the barrier), and the deciding lane applies row i to that ONE element itself before
+// it decides — the bulk update skips it. Per element the operations and their order are those of the kernels above:
+// bit-identical fields, energies and configurations (same draw stream).
+template <int RPC>
+__global__ void __launch_bounds__(544, 1) k_sk_lockstep_pipe(sk_ls_params P)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int N = P.N, tid = threadIdx.x, nt = blockDim.x;
+    constexpr int NBUF = 3;                                                // rows in flight: a row is requested two sites ahead
+    double *Jb = reinterpret_cast<double *>(smem_raw);                     // [NBUF][N] coupling rows
+    double *lf = Jb + NBUF * (size_t)N;                                    // [RPC][N]
+    uint32_t *sp = reinterpret_cast<uint32_t *>(lf + (size_t)RPC * N);     // [RPC][nw]
+    const int nw = (N + 31) / 32;
+    __shared__ int flag[2][RPC];
+    __shared__ int snew[2][RPC];
+    __shared__ __align__(8) uint64_t bar[3];
+    const uint32_t rowbytes = (uint32_t)N * 8u;
+    const int64_t rbase = (int64_t)blockIdx.x * RPC;
+    if (tid == 0) {
+        for (int b = 0; b < 3; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(sk_smem_u32(&bar[b])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (int rp = 0; rp < RPC; rp++) {
+        const int64_t r = rbase + rp;
+        for (int j = tid; j < N; j += nt) lf[(size_t)rp * N + j] = r < P.R ? P.lf[r * N + j] : 0.0;
+        for (int w = tid; w < nw; w += nt) {
+            const uint64_t c = r < P.R ? P.chunks[r * P.nchunks + (w >> 1)] : 0ull;
+            sp[rp * nw + w] = (uint32_t)(c >> ((w & 1) * 32));
+        }
+    }
+    double E = 0.0, beta = 0.0; long long nacc = 0;
+    if (tid < RPC && rbase + tid < P.R) { E = P.E[rbase + tid]; beta = P.beta[rbase + tid]; nacc = P.acc[rbase + tid]; }
+    __syncthreads();
+    auto fetch_row = [&](int row, int buf) {      // thread 0: row -> Jb[buf], completion on bar[buf]
+        const uint32_t b = sk_smem_u32(&bar[buf]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(rowbytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(sk_smem_u32(Jb + (size_t)buf * N)), "l"(P.J + (size_t)row * N), "r"(rowbytes), "r"(b) : "memory");
+    };
+    // accept() of RRRMC.jl:39 for replica `tid` at site i of sweep t, given its (current) field; -> flag / snew of step `buf`
+    auto decide = [&](int i, uint64_t t, double dE, int buf) {
+        const int64_t r = rbase + tid;
+        int ok = 0;
+        if (r < P.R) {
+            const double x = -beta * dE;                                           // ΔE_i = +lfields[i], SK.jl:278-284
+            if (x >= 0) ok = 1;
+            else {
+                const philox_out u = philox4x32_10((uint32_t)i, (uint32_t)r, (uint32_t)t, (uint32_t)(t >> 32) ^ 0x534b4c53u,
+                                                   (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+                const double U = (double)((((uint64_t)u.y << 32) | u.x) >> 11) * 0x1.0p-53;
+                ok = U < exp(x);
+            }
+            if (ok) { E += dE; nacc++; }
+        }
+        flag[buf][tid] = ok;
+        snew[buf][tid] = 1 ^ (int)((sp[tid * nw + (i >> 5)] >> (i & 31)) & 1u);
+    };
+    const long long nsteps = (long long)P.nsweeps * N;
+    if (tid == 0 && nsteps > 0) fetch_row(0, 0);
+    if (tid == 0 && nsteps > 1) fetch_row(1 < N ? 1 : 0, 1);
+    if (tid < RPC && nsteps > 0) decide(0, P.sweep0, lf[(size_t)tid * N], 0);
+    __syncthreads();
+    long long g = 0;
+    for (int sw = 0; sw < P.nsweeps; sw++) {
+        for (int i = 0; i < N; i++, g++) {
+            const int cur = (int)(g & 1), nxt = cur ^ 1;
+            const int in = i + 1 < N ? i + 1 : 0;                                   // the site of step g + 1
+            // buffer (g+2) % 3 was last read in step g-1, which ended with the barrier: request the row of step g+2 now
+            // (one site ahead is not enough: a step is shorter than the latency of a 32 KB row from HBM/L2)
+            if (tid == 0 && g + 2 < nsteps) fetch_row(i + 2 < N ? i + 2 : i + 2 - N, (int)((g + 2) % NBUF));
+            const int rb = (int)(g % NBUF);
+            {   // every thread observes the arrival of row i
+                const uint32_t b = sk_smem_u32(&bar[rb]), parity = (uint32_t)((g / NBUF) & 1);
+                asm volatile("{\n\t.reg .pred p;\nW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra W_%=;\n\t}" :: "r"(b), "r"(parity) : "memory");
+            }
+            const double *Ji = Jb + (size_t)rb * N;
+            if (tid < 32) {
+                if (tid < RPC) {
+                    // the deciding lane of replica tid: flip spin i if it was accepted, bring lf[in] up to date with row i,
+                    // decide site `in` for the next step
+                    const int ok = flag[cur][tid];
+                    if (ok) sp[tid * nw + (i >> 5)] ^= 1u << (i & 31);
+                    if (g + 1 < nsteps) {
+                        // the lane owns the whole 16-byte pair that holds `in` (the bulk update skips that pair, so its
+                        // double2 path stays vectorised): row i applied to both elements, site i itself taking -v
+                        double v = lf[(size_t)tid * N + in];
+                        if (ok) {
+                            const int mate = in ^ 1;
+                            const uint32_t w = sp[tid * nw + (in >> 5)];
+                            if (in != i) {
+                                const double a = 4 * Ji[in];
+                                v = __dadd_rn(v, (snew[cur][tid] ^ (int)((w >> (in & 31)) & 1u)) ? -a : a);
+                                lf[(size_t)tid * N + in] = v;
+                            } else { v = -v; lf[(size_t)tid * N + in] = v; }
+                            double vm = lf[(size_t)tid * N + mate];
+                            if (mate != i) {
+                                const double a = 4 * Ji[mate];
+                                vm = __dadd_rn(vm, (snew[cur][tid] ^ (int)((w >> (mate & 31)) & 1u)) ? -a : a);
+                            } else vm = -vm;
+                            lf[(size_t)tid * N + mate] = vm;
+                        }
+                        decide(in, P.sweep0 + (uint64_t)(i + 1 < N ? sw : sw + 1), v, nxt);
+                    }
+                }
+            } else {
+                bool any = false;
+#pragma unroll
+                for (int rp = 0; rp < RPC; rp++) any |= flag[cur][rp] != 0;
+                if (any) {                                     // update_cache!, SK.jl:252-265, for the accepted replicas
+                    const double2 *Ji2 = reinterpret_cast<const double2 *>(Ji);
+                    for (int j2 = tid - 32; j2 < N / 2; j2 += nt - 32) {
+                        const double2 Jv = Ji2[j2];
+                        const double a0 = 4 * Jv.x, a1 = 4 * Jv.y;
+                        const int j = 2 * j2;
+                        if (j2 == (in >> 1) && g + 1 < nsteps) continue;   // the deciders' pair (the last step has no decider)
+#pragma unroll
+                        for (int rp = 0; rp < RPC; rp++) {
+                            if (!flag[cur][rp]) continue;
+                            // (bit i of the word may already be flipped by the decider: it is not used, site i takes -v)
+                            const uint32_t w = sp[rp * nw + (j >> 5)] >> (j & 31);
+                            const int s0 = snew[cur][rp] ^ (int)(w & 1u), s1 = snew[cur][rp] ^ (int)((w >> 1) & 1u);
+                            double2 *p = reinterpret_cast<double2 *>(&lf[(size_t)rp * N + j]);
+                            double2 v = *p;
+                            v.x = j == i ? -v.x : __dadd_rn(v.x, s0 ? -a0 : a0);
+                            v.y = j + 1 == i ? -v.y : __dadd_rn(v.y, s1 ? -a1 : a1);
+                            *p = v;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int rp = 0; rp < RPC; rp++) {
+        const int64_t r = rbase + rp;
+        if (r >= P.R) continue;
+        for (int j = tid; j < N; j += nt) P.lf[r * N + j] = lf[(size_t)rp * N + j];
+        for (int c = tid; c < (int)P.nchunks; c += nt) {
+            const uint64_t lo = sp[rp * nw + 2 * c], hi = 2 * c + 1 < nw ? sp[rp * nw + 2 * c + 1] : 0u;
+            P.chunks[r * P.nchunks + c] = lo | (hi << 32);
+        }
+    }
+    if (tid < RPC && rbase + tid < P.R) { P.E[rbase + tid] = E; P.acc[rbase + tid] = nacc; }
+}
+
+// Register-resident variant (N even, N <= 4096): the local fields of the block's RPC replicas live in the REGISTERS of
+// sixteen update warps (thread b owns the site pairs b, b+512, ... of every replica), so a site step moves no field
+// through shared memory at all — only the 8N-byte coupling row is read from it.
+//
+// The registers hold u_j = σ_j·lf_j (σ = 2s - 1) instead of lf_j. update_cache! (SK.jl:252-265) adds 4·σ_i'·σ_j·J_ij to
+// lf_j (σ_i' the new spin of the flipped site); multiplied by σ_j that is u_j += 4·σ_i'·J_ij — ONE multiplier per replica
+// and step, the same for every j, so the update is a single DFMA per field with no per-element sign work:
+//   u_j <- fma(J_ij, c, u_j),  c = ±4 for a replica that flipped, 0 for one that did not.
+// It is bit-identical to the reference order: 4·J is exact, so the DFMA rounds once like lf + (±4J), and rounding to
+// nearest is symmetric under the common sign σ_j. Site i itself needs nothing: J_ii = 0 (validated when the graph is
+// created) leaves u_i alone, and lf_i -> -lf_i together with σ_i -> -σ_i is u_i -> u_i. ΔE_i = lf_i = σ_i·u_i.
+//
+// Three roles, one barrier per site:
+//   warp 0, lanes < RPC   decide site i+1 of their replica while row i is being applied: u of site i+1 arrives through a
+//                         2-slot mailbox (published by its owner one step earlier), the lane applies row i to that one
+//                         value itself (same DFMA, same operands as the owner: the two copies are bit-identical), then
+//                         accept() of RRRMC.jl:39 with the uniform that warp 17 prepared, and posts the multiplier c;
+//   warps 1..16           the DFMAs above on their registers for every replica (branch-free: a site step runs this code
+//                         once, so skipping a replica costs more in instruction fetch and issue than its 8 DFMAs), then
+//                         the owner of site i+2 publishes its u for the next step;
+//   warp 17               requests coupling row i+2 (cp.async.bulk, three row buffers), draws the Philox uniforms of
+//                         site i+2 and waits for row i+1 before the barrier (so nobody else polls an mbarrier) — all
+//                         off the deciders' dependency chain c(i) -> u(i+1) -> exp -> c(i+1), which bounds a site step
+//                         together with the FP64 pipe (8 N RPC / 64 cycles).
+// The acceptance test u < exp(x) is decided in single precision whenever that is certain: e = __expf(x) is within
+// 2 + 1.173|x| ulp (CUDA math API) of exp(x), so for -32 <= x < 0 a uniform outside e·(1 ± 2^-15) has the same answer as the
+// double-precision comparison (error budget < 7e-6, margin 3e-5); inside the margin (probability < 1e-4 per decision), or
+// below -32 unless u is clearly larger than exp(-32), the lane evaluates the double-precision exp as the other kernels do.
+// Fields, energies and configurations are bit-identical to the kernels above (same draw stream).
+struct sk_draw { double u; float lo, hi; };   // the uniform of a decision and its single-precision bracket u·(1 ∓ 2^-15)
+template <int RPC>
+__global__ void __launch_bounds__(576, 1) k_sk_lockstep_reg(sk_ls_params P)
+{
+    constexpr int NB = 512, SLOTS = 4, NBUF = 3;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int N = P.N, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, bt = tid - 32, half = N >> 1;
+    double *Jb = reinterpret_cast<double *>(smem_raw);                     // [NBUF][N] coupling rows
+    uint32_t *sp = reinterpret_cast<uint32_t *>(Jb + NBUF * (size_t)N);    // [RPC][nw] spins, kept by the deciders
+    const int nw = (N + 31) / 32;
+    __shared__ __align__(16) double cmul[2][RPC];  // multiplier of each replica for the step that reads the slot: ±4, or 0 (no flip)
+    __shared__ double mail[2][RPC];                // u of the site decided in the step that reads the slot (before that step's row)
+    __shared__ __align__(16) sk_draw ubuf[2][RPC]; // its uniform draw
+    __shared__ __align__(8) uint64_t bar[NBUF];
+    const uint32_t rowbytes = (uint32_t)N * 8u;
+    const int64_t rbase = (int64_t)blockIdx.x * RPC;
+    const bool bulk = warp >= 1 && warp <= 16, decider = warp == 0 && lane < RPC, aux = warp == 17;
+    if (tid == 0) {
+        for (int b = 0; b < NBUF; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(sk_smem_u32(&bar[b])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    double2 v[SLOTS][RPC];                         // u of the pairs k·512 + bt
+#pragma unroll
+    for (int k = 0; k < SLOTS; k++) {
+        const int j2 = k * NB + bt;
+#pragma unroll
+        for (int rp = 0; rp < RPC; rp++) {
+            const int64_t r = rbase + rp;
+            v[k][rp] = make_double2(0.0, 0.0);
+            if (bulk && j2 < half && r < P.R) {
+                const double2 f = *reinterpret_cast<const double2 *>(&P.lf[r * N + 2 * j2]);
+                const uint32_t s2 = (uint32_t)(P.chunks[r * P.nchunks + (j2 >> 5)] >> ((2 * j2) & 63));
+                v[k][rp] = make_double2((s2 & 1u) ? f.x : -f.x, (s2 & 2u) ? f.y : -f.y);
+            }
+        }
+    }
+    for (int rp = 0; rp < RPC; rp++) {
+        const int64_t r = rbase + rp;
+        for (int w = tid; w < nw; w += blockDim.x) {
+            const uint64_t c = r < P.R ? P.chunks[r * P.nchunks + (w >> 1)] : 0ull;
+            sp[rp * nw + w] = (uint32_t)(c >> ((w & 1) * 32));
+        }
+    }
+    double E = 0.0, beta = 0.0; long long nacc = 0;
+    const int64_t rmine = rbase + lane;                                    // deciders and warp 17: the lane's replica
+    if (decider && rmine < P.R) { E = P.E[rmine]; beta = P.beta[rmine]; nacc = P.acc[rmine]; }
+    __syncthreads();
+    auto fetch_row = [&](int row, int buf) {      // one lane: row -> Jb[buf], completion on bar[buf]
+        const uint32_t b = sk_smem_u32(&bar[buf]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(rowbytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(sk_smem_u32(Jb + (size_t)buf * N)), "l"(P.J + (size_t)row * N), "r"(rowbytes), "r"(b) : "memory");
+    };
+    auto wait_row = [&](int buf, uint32_t parity) {
+        const uint32_t b = sk_smem_u32(&bar[buf]);
+        asm volatile("{\n\t.reg .pred p;\nW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra W_%=;\n\t}" :: "r"(b), "r"(parity) : "memory");
+    };
+    auto draw = [&](int i, uint64_t t) {          // the draw of (site i, sweep t) for replica rmine, as in the kernels above
+        const philox_out u = philox4x32_10((uint32_t)i, (uint32_t)rmine, (uint32_t)t, (uint32_t)(t >> 32) ^ 0x534b4c53u,
+                                           (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+        sk_draw d;
+        d.u = (double)((((uint64_t)u.y << 32) | u.x) >> 11) * 0x1.0p-53;
+        const float uf = (float)d.u;
+        d.lo = uf * (1.0f - 0x1.0p-15f); d.hi = uf * (1.0f + 0x1.0p-15f);
+        return d;
+    };
+    // accept() of RRRMC.jl:39 on x = -βΔE with the prepared draw
+    auto accept = [&](double x, const sk_draw &d) -> int {
+        if (x >= 0) return 1;
+        const float xf = (float)x, e = __expf(fmaxf(xf, -32.0f));
+        if (xf >= -32.0f && d.hi < e) return 1;
+        if (d.lo > e) return 0;
+        return d.u < exp(x);
+    };
+    auto publish = [&](int site, int buf) {       // update warps: the owner of `site` posts its u for every replica
+        const int p = site >> 1;
+        if (bt == (p & (NB - 1))) {
+            const int k0 = p / NB;
+#pragma unroll
+            for (int k = 0; k < SLOTS; k++)
+                if (k == k0) {
+#pragma unroll
+                    for (int rp = 0; rp < RPC; rp++) mail[buf][rp] = (site & 1) ? v[k][rp].y : v[k][rp].x;
+                }
+        }
+    };
+    const long long nsteps = (long long)P.nsweeps * N;
+    const int s1 = 1 < N ? 1 : 0;
+    double cp = 0.0;                                                               // deciders: the multiplier of the current step
+    if (nsteps > 0) {
+        if (aux && lane == 0) { fetch_row(0, 0); if (nsteps > 1) fetch_row(s1, 1); }
+        if (aux && lane < RPC) ubuf[0][lane] = draw(s1, P.sweep0 + (uint64_t)(N == 1));
+        if (decider) {
+            const double f = rmine < P.R ? P.lf[rmine * N] : 0.0;
+            const int ok = rmine < P.R ? accept(-beta * f, draw(0, P.sweep0)) : 0;
+            if (ok) { E += f; nacc++; }
+            cp = ok ? ((sp[lane * nw] & 1u) ? -4.0 : 4.0) : 0.0;                   // 4·σ' of the new spin
+            cmul[0][lane] = cp;
+        }
+        if (bulk) publish(s1, 0);
+        if (aux && lane == 0) wait_row(0, 0);
+    }
+    __syncthreads();
+    // One loop per role (the roles share nothing but the barrier, so each keeps only its own state in registers). Step g
+    // works on site i = g mod N: row i sits in buffer g % 3 — complete, warp 17 saw it arrive before the last barrier.
+    if (bulk) {
+        int in2 = 2 < N ? 2 : 2 - N, rb = 0, cur = 0;                             // in2: the site of step g + 2
+        const bool full = half == NB * SLOTS;                                      // N = 4096: every slot of every thread is live
+        for (long long g = 0; g < nsteps; g++) {
+            double c[RPC];
+#pragma unroll
+            for (int rp = 0; rp < RPC; rp++) c[rp] = cmul[cur][rp];
+            const double2 *Ji2 = reinterpret_cast<const double2 *>(Jb + (size_t)rb * N) + bt;
+#pragma unroll
+            for (int k = 0; k < SLOTS; k++) {
+                const double2 Jv = full || k * NB + bt < half ? Ji2[k * NB] : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int rp = 0; rp < RPC; rp++) {
+                    v[k][rp].x = fma(Jv.x, c[rp], v[k][rp].x);
+                    v[k][rp].y = fma(Jv.y, c[rp], v[k][rp].y);
+                }
+            }
+            cur ^= 1;
+            publish(in2, cur);
+            if (++in2 == N) in2 = 0;
+            if (++rb == NBUF) rb = 0;
+            __syncthreads();
+        }
+    } else if (warp == 0) {
+        int i = 0, rb = 0, cur = 0;
+        for (long long g = 0; g < nsteps; g++) {
+            const int in = i + 1 < N ? i + 1 : 0;                                   // the site of step g + 1
+            if (decider) {
+                if (cp != 0.0) sp[lane * nw + (i >> 5)] ^= 1u << (i & 31);
+                if (g + 1 < nsteps) {
+                    const double a = Jb[(size_t)rb * N + in];
+                    const sk_draw d = ubuf[cur][lane];
+                    const int sj = (int)((sp[lane * nw + (in >> 5)] >> (in & 31)) & 1u);
+                    const double u = fma(a, cp, mail[cur][lane]);                   // row i on u of site i+1 (N >= 2: in != i)
+                    const double f = sj ? u : -u;                                   // ΔE = lfields[i+1] = σ·u, SK.jl:278-284
+                    const int ok = rmine < P.R ? accept(-beta * f, d) : 0;
+                    if (ok) { E += f; nacc++; }
+                    cp = ok ? (sj ? -4.0 : 4.0) : 0.0;
+                    cmul[cur ^ 1][lane] = cp;
+                }
+            }
+            i = in; cur ^= 1;
+            if (++rb == NBUF) rb = 0;
+            __syncthreads();
+        }
+    } else {
+        int in2 = 2 < N ? 2 : 2 - N, nxt = 1, rb1 = 1; uint32_t par1 = 0;         // buffer of row g+1 and its mbarrier phase
+        uint64_t t2 = P.sweep0 + (uint64_t)(2 >= N);                               // sweep of step g + 2
+        for (long long g = 0; g < nsteps; g++) {
+            if (g + 2 < nsteps) {
+                // buffer (g+2) % 3 was last read in step g-1, which ended with the barrier
+                if (lane == 0) fetch_row(in2, rb1 + 1 == NBUF ? 0 : rb1 + 1);
+                if (lane < RPC) ubuf[nxt][lane] = draw(in2, t2);
+            }
+            if (lane == 0 && g + 1 < nsteps) wait_row(rb1, par1);
+            if (++in2 == N) { in2 = 0; t2++; }                                     // step g + 3 starts the next sweep
+            nxt ^= 1;
+            if (++rb1 == NBUF) { rb1 = 0; par1 ^= 1u; }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    if (bulk) {                                                                    // lf = σ·u with the final spins
+#pragma unroll
+        for (int k = 0; k < SLOTS; k++) {
+            const int j2 = k * NB + bt;
+#pragma unroll
+            for (int rp = 0; rp < RPC; rp++) {
+                const int64_t r = rbase + rp;
+                if (j2 < half && r < P.R) {
+                    const uint32_t s2 = sp[rp * nw + (j2 >> 4)] >> ((2 * j2) & 31);
+                    *reinterpret_cast<double2 *>(&P.lf[r * N + 2 * j2]) =
+                        make_double2((s2 & 1u) ? v[k][rp].x : -v[k][rp].x, (s2 & 2u) ? v[k][rp].y : -v[k][rp].y);
+                }
+            }
+        }
+    }
+    for (int rp = 0; rp < RPC; rp++) {
+        const int64_t r = rbase + rp;
+        if (r >= P.R) continue;
+        for (int c = tid; c < (int)P.nchunks; c += blockDim.x) {
+            const uint64_t lo = sp[rp * nw + 2 * c], hi = 2 * c + 1 < nw ? sp[rp * nw + 2 * c + 1] : 0u;
+            P.chunks[r * P.nchunks + c] = lo | (hi << 32);
+        }
+    }
+    if (decider && rmine < P.R) { P.E[rmine] = E; P.acc[rmine] = nacc; }
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -570,12 +943,29 @@ rrrmc_status_t sk_dense_sweeps(rrrmc_state *s, const double *beta, uint64_t seed
     const size_t smem_tma = smem + 2 * (size_t)N * 8;
     const char *skv = getenv("RRRMC_SK_VARIANT");
     const bool tma = N % 2 == 0 && smem_tma <= (size_t)225 * 1024 && !(skv && atoi(skv) == 1);
+    const size_t smem_pipe = smem + 3 * (size_t)N * 8;
+    const int variant = skv ? atoi(skv) : 0;   // RRRMC_SK_VARIANT: 0 best available, 1 plain loads, 2 TMA rows, 3 TMA rows + site pipeline
+    const bool pipe = tma && smem_pipe <= (size_t)226 * 1024 && variant != 2;
+    // fields in registers (N even, <= 4096): the default; one block per RPC replicas, RPC no larger than the SM count asks for
+    const bool reg = N % 2 == 0 && N >= 2 && N <= 4096 && variant == 0;
 #define LST(RP) do { RR_CUDA(cudaFuncSetAttribute(k_sk_lockstep_tma<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma)); \
                      k_sk_lockstep_tma<RP><<<grid, 512, smem_tma, ctx->stream>>>(P); } while (0)
-    if (tma) { if (rpc == 4) LST(4); else if (rpc == 2) LST(2); else LST(1); }
+#define LSP(RP) do { RR_CUDA(cudaFuncSetAttribute(k_sk_lockstep_pipe<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe)); \
+                     k_sk_lockstep_pipe<RP><<<grid, 544, smem_pipe, ctx->stream>>>(P); } while (0)
+#define LSR(RP) do { const size_t sm = 3 * (size_t)N * 8 + (size_t)RP * nw * 4; \
+                     RR_CUDA(cudaFuncSetAttribute(k_sk_lockstep_reg<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+                     k_sk_lockstep_reg<RP><<<div_up(s->R, RP), 576, sm, ctx->stream>>>(P); } while (0)
+    if (reg) {
+        const int nsm = ctx->sm_count > 0 ? ctx->sm_count : 148;
+        if (s->R > 2 * (int64_t)nsm) LSR(4); else if (s->R > nsm) LSR(2); else LSR(1);
+    }
+    else if (pipe) { if (rpc == 4) LSP(4); else if (rpc == 2) LSP(2); else LSP(1); }
+    else if (tma) { if (rpc == 4) LST(4); else if (rpc == 2) LST(2); else LST(1); }
     else if (rpc == 4) LS(4); else if (rpc == 2) LS(2); else LS(1);
+#undef LSR
 #undef LS
 #undef LST
+#undef LSP
     ctx->launches++;
     RR_CUDA(cudaGetLastError());
     s->ms_valid = false; s->chain_valid = true; s->chain_fields_valid = false; s->energy_valid = false;
