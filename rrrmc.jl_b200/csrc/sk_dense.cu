@@ -619,6 +619,11 @@ __global__ void __launch_bounds__(544, 1) k_sk_lockstep_pipe(sk_ls_params P)
 // double-precision comparison (error budget < 7e-6, margin 3e-5); inside the margin (probability < 1e-4 per decision), or
 // below -32 unless u is clearly larger than exp(-32), the lane evaluates the double-precision exp as the other kernels do.
 // Fields, energies and configurations are bit-identical to the kernels above (same draw stream).
+__device__ __forceinline__ double2 sk_lds_f64x2(uint32_t a) { double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ double sk_lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t sk_lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sk_sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sk_sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 struct sk_draw { double u; float lo, hi; };   // the uniform of a decision and its single-precision bracket u·(1 ∓ 2^-15)
 template <int RPC>
 __global__ void __launch_bounds__(576, 1) k_sk_lockstep_reg(sk_ls_params P)
@@ -631,7 +636,7 @@ __global__ void __launch_bounds__(576, 1) k_sk_lockstep_reg(sk_ls_params P)
     const int nw = (N + 31) / 32;
     __shared__ __align__(16) double cmul[2][RPC];  // multiplier of each replica for the step that reads the slot: ±4, or 0 (no flip)
     __shared__ double mail[2][RPC];                // u of the site decided in the step that reads the slot (before that step's row)
-    __shared__ __align__(16) sk_draw ubuf[2][RPC]; // its uniform draw
+    __shared__ __align__(16) sk_draw ubuf[16][RPC]; // the uniform draws of a ring of 16 steps (slot = step mod 16)
     __shared__ __align__(8) uint64_t bar[NBUF];
     const uint32_t rowbytes = (uint32_t)N * 8u;
     const int64_t rbase = (int64_t)blockIdx.x * RPC;
@@ -677,8 +682,11 @@ __global__ void __launch_bounds__(576, 1) k_sk_lockstep_reg(sk_ls_params P)
         const uint32_t b = sk_smem_u32(&bar[buf]);
         asm volatile("{\n\t.reg .pred p;\nW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra W_%=;\n\t}" :: "r"(b), "r"(parity) : "memory");
     };
-    auto draw = [&](int i, uint64_t t) {          // the draw of (site i, sweep t) for replica rmine, as in the kernels above
-        const philox_out u = philox4x32_10((uint32_t)i, (uint32_t)rmine, (uint32_t)t, (uint32_t)(t >> 32) ^ 0x534b4c53u,
+    constexpr int Q = 8, RING = 2 * Q;            // draws are made Q steps at a time, by Q·RPC lanes of warp 17, into a ring of 2Q steps
+    // the draw of step st (site st mod N of sweep sweep0 + st div N) for replica rbase + rp, as in the kernels above
+    auto draw = [&](long long st, int rp) {
+        const int i = (int)(st % N); const uint64_t t = P.sweep0 + (uint64_t)(st / N);
+        const philox_out u = philox4x32_10((uint32_t)i, (uint32_t)(rbase + rp), (uint32_t)t, (uint32_t)(t >> 32) ^ 0x534b4c53u,
                                            (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
         sk_draw d;
         d.u = (double)((((uint64_t)u.y << 32) | u.x) >> 11) * 0x1.0p-53;
@@ -686,13 +694,16 @@ __global__ void __launch_bounds__(576, 1) k_sk_lockstep_reg(sk_ls_params P)
         d.lo = uf * (1.0f - 0x1.0p-15f); d.hi = uf * (1.0f + 0x1.0p-15f);
         return d;
     };
-    // accept() of RRRMC.jl:39 on x = -βΔE with the prepared draw
-    auto accept = [&](double x, const sk_draw &d) -> int {
+    // accept() of RRRMC.jl:39 on x = -βΔE with the prepared draw (ex2.approx: 2 ulp, and -32·log2(e) is far above the
+    // denormal range, so no range reduction is needed)
+    auto accept = [&](double x, double u, float lo, float hi) -> int {
         if (x >= 0) return 1;
-        const float xf = (float)x, e = __expf(fmaxf(xf, -32.0f));
-        if (xf >= -32.0f && d.hi < e) return 1;
-        if (d.lo > e) return 0;
-        return d.u < exp(x);
+        const float xf = (float)x;
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaxf(xf, -32.0f) * 1.4426950408889634f));
+        if (xf >= -32.0f && hi < e) return 1;
+        if (lo > e) return 0;
+        return u < exp(x);
     };
     auto publish = [&](int site, int buf) {       // update warps: the owner of `site` posts its u for every replica
         const int p = site >> 1;
@@ -709,12 +720,14 @@ __global__ void __launch_bounds__(576, 1) k_sk_lockstep_reg(sk_ls_params P)
     const long long nsteps = (long long)P.nsweeps * N;
     const int s1 = 1 < N ? 1 : 0;
     double cp = 0.0;                                                               // deciders: the multiplier of the current step
+    const int qs = lane / RPC, qr = lane % RPC;                                    // warp 17: lane -> (step of the batch, replica)
     if (nsteps > 0) {
         if (aux && lane == 0) { fetch_row(0, 0); if (nsteps > 1) fetch_row(s1, 1); }
-        if (aux && lane < RPC) ubuf[0][lane] = draw(s1, P.sweep0 + (uint64_t)(N == 1));
+        if (aux && qs < Q) ubuf[(1 + qs) % RING][qr] = draw(1 + qs, qr);          // steps 1..Q, decided during steps 0..Q-1
         if (decider) {
             const double f = rmine < P.R ? P.lf[rmine * N] : 0.0;
-            const int ok = rmine < P.R ? accept(-beta * f, draw(0, P.sweep0)) : 0;
+            const sk_draw d = draw(0, lane);
+            const int ok = rmine < P.R ? accept(-beta * f, d.u, d.lo, d.hi) : 0;
             if (ok) { E += f; nacc++; }
             cp = ok ? ((sp[lane * nw] & 1u) ? -4.0 : 4.0) : 0.0;                   // 4·σ' of the new spin
             cmul[0][lane] = cp;
@@ -723,23 +736,36 @@ __global__ void __launch_bounds__(576, 1) k_sk_lockstep_reg(sk_ls_params P)
         if (aux && lane == 0) wait_row(0, 0);
     }
     __syncthreads();
-    // One loop per role (the roles share nothing but the barrier, so each keeps only its own state in registers). Step g
-    // works on site i = g mod N: row i sits in buffer g % 3 — complete, warp 17 saw it arrive before the last barrier.
+    // One loop per role (the roles share nothing but the barrier, so each keeps only its own state in registers, and its
+    // shared-memory addresses as 32-bit values computed once). Step g works on site i = g mod N: row i sits in buffer
+    // g % 3 — complete, warp 17 saw it arrive before the last barrier.
+    const uint32_t a_J = sk_smem_u32(Jb), a_cmul = sk_smem_u32(&cmul[0][0]), a_mail = sk_smem_u32(&mail[0][0]);
     if (bulk) {
         int in2 = 2 < N ? 2 : 2 - N, rb = 0, cur = 0;                             // in2: the site of step g + 2
-        const bool full = half == NB * SLOTS;                                      // N = 4096: every slot of every thread is live
+        // a dead slot (pair index >= N/2, only when N < 4096) reads pair bt of the row instead: its registers are never
+        // published nor written back, so the loop needs no predicates
+        uint32_t off[SLOTS];
+#pragma unroll
+        for (int k = 0; k < SLOTS; k++) off[k] = (uint32_t)((k * NB + bt < half ? k * NB + bt : (bt < half ? bt : 0)) * 16);
         for (long long g = 0; g < nsteps; g++) {
             double c[RPC];
+            if (RPC == 4) {
+                const double2 c01 = sk_lds_f64x2(a_cmul + cur * 32), c23 = sk_lds_f64x2(a_cmul + cur * 32 + 16);
+                c[0] = c01.x; c[1 % RPC] = c01.y; c[2 % RPC] = c23.x; c[3 % RPC] = c23.y;
+            } else if (RPC == 2) {
+                const double2 c01 = sk_lds_f64x2(a_cmul + cur * 16);
+                c[0] = c01.x; c[1 % RPC] = c01.y;
+            } else c[0] = sk_lds_f64(a_cmul + cur * 8);
+            const uint32_t row = a_J + (uint32_t)rb * rowbytes;
+            double2 Jv[SLOTS];
 #pragma unroll
-            for (int rp = 0; rp < RPC; rp++) c[rp] = cmul[cur][rp];
-            const double2 *Ji2 = reinterpret_cast<const double2 *>(Jb + (size_t)rb * N) + bt;
+            for (int k = 0; k < SLOTS; k++) Jv[k] = sk_lds_f64x2(row + off[k]);
 #pragma unroll
             for (int k = 0; k < SLOTS; k++) {
-                const double2 Jv = full || k * NB + bt < half ? Ji2[k * NB] : make_double2(0.0, 0.0);
 #pragma unroll
                 for (int rp = 0; rp < RPC; rp++) {
-                    v[k][rp].x = fma(Jv.x, c[rp], v[k][rp].x);
-                    v[k][rp].y = fma(Jv.y, c[rp], v[k][rp].y);
+                    v[k][rp].x = fma(Jv[k].x, c[rp], v[k][rp].x);
+                    v[k][rp].y = fma(Jv[k].y, c[rp], v[k][rp].y);
                 }
             }
             cur ^= 1;
@@ -749,39 +775,50 @@ __global__ void __launch_bounds__(576, 1) k_sk_lockstep_reg(sk_ls_params P)
             __syncthreads();
         }
     } else if (warp == 0) {
+        // (all 32 lanes run the loop and meet at the same barrier instruction; lanes >= RPC only keep the barrier count)
+        const bool live = decider && rmine < P.R;
+        const uint32_t a_sp = sk_smem_u32(sp + (size_t)(decider ? lane : 0) * nw), a_c = a_cmul + lane * 8, a_m = a_mail + lane * 8;
+        const uint32_t a_u = sk_smem_u32(&ubuf[0][decider ? lane : 0]);
+        const double nbeta = -beta;
         int i = 0, rb = 0, cur = 0;
         for (long long g = 0; g < nsteps; g++) {
             const int in = i + 1 < N ? i + 1 : 0;                                   // the site of step g + 1
             if (decider) {
-                if (cp != 0.0) sp[lane * nw + (i >> 5)] ^= 1u << (i & 31);
                 if (g + 1 < nsteps) {
-                    const double a = Jb[(size_t)rb * N + in];
-                    const sk_draw d = ubuf[cur][lane];
-                    const int sj = (int)((sp[lane * nw + (in >> 5)] >> (in & 31)) & 1u);
-                    const double u = fma(a, cp, mail[cur][lane]);                   // row i on u of site i+1 (N >= 2: in != i)
-                    const double f = sj ? u : -u;                                   // ΔE = lfields[i+1] = σ·u, SK.jl:278-284
-                    const int ok = rmine < P.R ? accept(-beta * f, d) : 0;
-                    if (ok) { E += f; nacc++; }
+                    // the chain: mailbox and coupling -> u of site i+1 under row i -> x = -β·σ·u -> accept -> multiplier
+                    const double m = sk_lds_f64(a_m + cur * (RPC * 8));
+                    const double a = sk_lds_f64(a_J + (uint32_t)rb * rowbytes + (uint32_t)in * 8);
+                    const uint32_t wj = sk_lds_u32(a_sp + (uint32_t)(in >> 5) * 4);
+                    const uint32_t ua = a_u + (uint32_t)((g + 1) % RING) * (RPC * 16);
+                    const double du = sk_lds_f64(ua);
+                    const uint32_t dlo = sk_lds_u32(ua + 8), dhi = sk_lds_u32(ua + 12);
+                    const int sj = (int)((wj >> (in & 31)) & 1u);
+                    const double bs = sj ? nbeta : beta;                            // -β·σ of site i+1
+                    const double u = fma(a, cp, m);                                 // row i on u of site i+1 (N >= 2: in != i)
+                    const int ok = live ? accept(bs * u, du, __uint_as_float(dlo), __uint_as_float(dhi)) : 0;
+                    if (cp != 0.0) {                                                // the flip of site i, decided one step ago
+                        const uint32_t aw = a_sp + (uint32_t)(i >> 5) * 4;
+                        sk_sts_u32(aw, sk_lds_u32(aw) ^ (1u << (i & 31)));
+                    }
                     cp = ok ? (sj ? -4.0 : 4.0) : 0.0;
-                    cmul[cur ^ 1][lane] = cp;
-                }
+                    sk_sts_f64(a_c + (cur ^ 1) * (RPC * 8), cp);
+                    if (ok) { E += sj ? u : -u; nacc++; }                           // ΔE = lfields[i+1] = σ·u, SK.jl:278-284
+                } else if (cp != 0.0) sp[lane * nw + (i >> 5)] ^= 1u << (i & 31);
             }
             i = in; cur ^= 1;
             if (++rb == NBUF) rb = 0;
             __syncthreads();
         }
     } else {
-        int in2 = 2 < N ? 2 : 2 - N, nxt = 1, rb1 = 1; uint32_t par1 = 0;         // buffer of row g+1 and its mbarrier phase
-        uint64_t t2 = P.sweep0 + (uint64_t)(2 >= N);                               // sweep of step g + 2
+        int in2 = 2 < N ? 2 : 2 - N, rb1 = 1; uint32_t par1 = 0;                  // buffer of row g+1 and its mbarrier phase
         for (long long g = 0; g < nsteps; g++) {
-            if (g + 2 < nsteps) {
-                // buffer (g+2) % 3 was last read in step g-1, which ended with the barrier
-                if (lane == 0) fetch_row(in2, rb1 + 1 == NBUF ? 0 : rb1 + 1);
-                if (lane < RPC) ubuf[nxt][lane] = draw(in2, t2);
-            }
+            // buffer (g+2) % 3 was last read in step g-1, which ended with the barrier
+            if (lane == 0 && g + 2 < nsteps) fetch_row(in2, rb1 + 1 == NBUF ? 0 : rb1 + 1);
+            // every Q steps: the draws of steps g+Q+1 .. g+2Q (read during steps g+Q .. g+2Q-1; their ring slots were last
+            // read during steps g-Q .. g-1)
+            if ((g & (Q - 1)) == 0 && qs < Q && g + Q + 1 + qs < nsteps) ubuf[(g + Q + 1 + qs) % RING][qr] = draw(g + Q + 1 + qs, qr);
             if (lane == 0 && g + 1 < nsteps) wait_row(rb1, par1);
-            if (++in2 == N) { in2 = 0; t2++; }                                     // step g + 3 starts the next sweep
-            nxt ^= 1;
+            if (++in2 == N) in2 = 0;
             if (++rb1 == NBUF) { rb1 = 0; par1 ^= 1u; }
             __syncthreads();
         }
