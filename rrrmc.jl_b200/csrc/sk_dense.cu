@@ -634,8 +634,8 @@ __global__ void __launch_bounds__(576, 1) k_sk_lockstep_reg(sk_ls_params P)
     double *Jb = reinterpret_cast<double *>(smem_raw);                     // [NBUF][N] coupling rows
     uint32_t *sp = reinterpret_cast<uint32_t *>(Jb + NBUF * (size_t)N);    // [RPC][nw] spins, kept by the deciders
     const int nw = (N + 31) / 32;
-    __shared__ __align__(16) double cmul[2][RPC];  // multiplier of each replica for the step that reads the slot: ±4, or 0 (no flip)
-    __shared__ double mail[2][RPC];                // u of the site decided in the step that reads the slot (before that step's row)
+    __shared__ __align__(64) double cmul[2][RPC];  // multiplier of each replica for the step that reads the slot: ±4, or 0 (no flip)
+    __shared__ __align__(64) double mail[2][RPC];                // u of the site decided in the step that reads the slot (before that step's row)
     __shared__ __align__(16) sk_draw ubuf[16][RPC]; // the uniform draws of a ring of 16 steps (slot = step mod 16)
     __shared__ __align__(8) uint64_t bar[NBUF];
     const uint32_t rowbytes = (uint32_t)N * 8u;
@@ -646,21 +646,6 @@ __global__ void __launch_bounds__(576, 1) k_sk_lockstep_reg(sk_ls_params P)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    double2 v[SLOTS][RPC];                         // u of the pairs k·512 + bt
-#pragma unroll
-    for (int k = 0; k < SLOTS; k++) {
-        const int j2 = k * NB + bt;
-#pragma unroll
-        for (int rp = 0; rp < RPC; rp++) {
-            const int64_t r = rbase + rp;
-            v[k][rp] = make_double2(0.0, 0.0);
-            if (bulk && j2 < half && r < P.R) {
-                const double2 f = *reinterpret_cast<const double2 *>(&P.lf[r * N + 2 * j2]);
-                const uint32_t s2 = (uint32_t)(P.chunks[r * P.nchunks + (j2 >> 5)] >> ((2 * j2) & 63));
-                v[k][rp] = make_double2((s2 & 1u) ? f.x : -f.x, (s2 & 2u) ? f.y : -f.y);
-            }
-        }
-    }
     for (int rp = 0; rp < RPC; rp++) {
         const int64_t r = rbase + rp;
         for (int w = tid; w < nw; w += blockDim.x) {
@@ -668,9 +653,6 @@ __global__ void __launch_bounds__(576, 1) k_sk_lockstep_reg(sk_ls_params P)
             sp[rp * nw + w] = (uint32_t)(c >> ((w & 1) * 32));
         }
     }
-    double E = 0.0, beta = 0.0; long long nacc = 0;
-    const int64_t rmine = rbase + lane;                                    // deciders and warp 17: the lane's replica
-    if (decider && rmine < P.R) { E = P.E[rmine]; beta = P.beta[rmine]; nacc = P.acc[rmine]; }
     __syncthreads();
     auto fetch_row = [&](int row, int buf) {      // one lane: row -> Jb[buf], completion on bar[buf]
         const uint32_t b = sk_smem_u32(&bar[buf]);
@@ -694,69 +676,60 @@ __global__ void __launch_bounds__(576, 1) k_sk_lockstep_reg(sk_ls_params P)
         d.lo = uf * (1.0f - 0x1.0p-15f); d.hi = uf * (1.0f + 0x1.0p-15f);
         return d;
     };
-    // accept() of RRRMC.jl:39 on x = -βΔE with the prepared draw (ex2.approx: 2 ulp, and -32·log2(e) is far above the
-    // denormal range, so no range reduction is needed)
-    auto accept = [&](double x, double u, float lo, float hi) -> int {
-        if (x >= 0) return 1;
-        const float xf = (float)x;
-        float e;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaxf(xf, -32.0f) * 1.4426950408889634f));
-        if (xf >= -32.0f && hi < e) return 1;
-        if (lo > e) return 0;
-        return u < exp(x);
-    };
-    auto publish = [&](int site, int buf) {       // update warps: the owner of `site` posts its u for every replica
-        const int p = site >> 1;
-        if (bt == (p & (NB - 1))) {
-            const int k0 = p / NB;
-#pragma unroll
-            for (int k = 0; k < SLOTS; k++)
-                if (k == k0) {
-#pragma unroll
-                    for (int rp = 0; rp < RPC; rp++) mail[buf][rp] = (site & 1) ? v[k][rp].y : v[k][rp].x;
-                }
-        }
-    };
     const long long nsteps = (long long)P.nsweeps * N;
     const int s1 = 1 < N ? 1 : 0;
-    double cp = 0.0;                                                               // deciders: the multiplier of the current step
-    const int qs = lane / RPC, qr = lane % RPC;                                    // warp 17: lane -> (step of the batch, replica)
-    if (nsteps > 0) {
-        if (aux && lane == 0) { fetch_row(0, 0); if (nsteps > 1) fetch_row(s1, 1); }
-        if (aux && qs < Q) ubuf[(1 + qs) % RING][qr] = draw(1 + qs, qr);          // steps 1..Q, decided during steps 0..Q-1
-        if (decider) {
-            const double f = rmine < P.R ? P.lf[rmine * N] : 0.0;
-            const sk_draw d = draw(0, lane);
-            const int ok = rmine < P.R ? accept(-beta * f, d.u, d.lo, d.hi) : 0;
-            if (ok) { E += f; nacc++; }
-            cp = ok ? ((sp[lane * nw] & 1u) ? -4.0 : 4.0) : 0.0;                   // 4·σ' of the new spin
-            cmul[0][lane] = cp;
-        }
-        if (bulk) publish(s1, 0);
-        if (aux && lane == 0) wait_row(0, 0);
-    }
-    __syncthreads();
-    // One loop per role (the roles share nothing but the barrier, so each keeps only its own state in registers, and its
-    // shared-memory addresses as 32-bit values computed once). Step g works on site i = g mod N: row i sits in buffer
-    // g % 3 — complete, warp 17 saw it arrive before the last barrier.
     const uint32_t a_J = sk_smem_u32(Jb), a_cmul = sk_smem_u32(&cmul[0][0]), a_mail = sk_smem_u32(&mail[0][0]);
+    // One code path per role (the roles share nothing but the barrier — one before the first step, one per step, one after
+    // the last — so each keeps only its own state in registers, with its shared-memory addresses as 32-bit values advanced
+    // incrementally). Step g works on site i = g mod N: row i sits in buffer g % 3 — complete, warp 17 saw it arrive
+    // before the last barrier. Slot g & 1 of cmul / mail belongs to step g.
     if (bulk) {
-        int in2 = 2 < N ? 2 : 2 - N, rb = 0, cur = 0;                             // in2: the site of step g + 2
+        double2 v[SLOTS][RPC];                     // u of the pairs k·512 + bt
+#pragma unroll
+        for (int k = 0; k < SLOTS; k++) {
+            const int j2 = k * NB + bt;
+#pragma unroll
+            for (int rp = 0; rp < RPC; rp++) {
+                const int64_t r = rbase + rp;
+                v[k][rp] = make_double2(0.0, 0.0);
+                if (j2 < half && r < P.R) {
+                    const double2 f = *reinterpret_cast<const double2 *>(&P.lf[r * N + 2 * j2]);
+                    const uint32_t s2 = (uint32_t)(P.chunks[r * P.nchunks + (j2 >> 5)] >> ((2 * j2) & 63));
+                    v[k][rp] = make_double2((s2 & 1u) ? f.x : -f.x, (s2 & 2u) ? f.y : -f.y);
+                }
+            }
+        }
+        auto publish = [&](int site, uint32_t a) { // the owner of `site` posts its u for every replica at mailbox slot a
+            const int p = site >> 1;
+            if (bt == (p & (NB - 1))) {
+                const int k0 = p / NB;
+#pragma unroll
+                for (int k = 0; k < SLOTS; k++)
+                    if (k == k0) {
+#pragma unroll
+                        for (int rp = 0; rp < RPC; rp++) sk_sts_f64(a + rp * 8, (site & 1) ? v[k][rp].y : v[k][rp].x);
+                    }
+            }
+        };
+        if (nsteps > 0) publish(s1, a_mail);
+        __syncthreads();
         // a dead slot (pair index >= N/2, only when N < 4096) reads pair bt of the row instead: its registers are never
         // published nor written back, so the loop needs no predicates
         uint32_t off[SLOTS];
 #pragma unroll
         for (int k = 0; k < SLOTS; k++) off[k] = (uint32_t)((k * NB + bt < half ? k * NB + bt : (bt < half ? bt : 0)) * 16);
+        int in2 = 2 < N ? 2 : 2 - N;                                               // the site of step g + 2
+        uint32_t a_c = a_cmul, a_m = a_mail + RPC * 8, row = a_J;
+        const uint32_t row_end = a_J + NBUF * rowbytes;
         for (long long g = 0; g < nsteps; g++) {
             double c[RPC];
             if (RPC == 4) {
-                const double2 c01 = sk_lds_f64x2(a_cmul + cur * 32), c23 = sk_lds_f64x2(a_cmul + cur * 32 + 16);
+                const double2 c01 = sk_lds_f64x2(a_c), c23 = sk_lds_f64x2(a_c + 16);
                 c[0] = c01.x; c[1 % RPC] = c01.y; c[2 % RPC] = c23.x; c[3 % RPC] = c23.y;
             } else if (RPC == 2) {
-                const double2 c01 = sk_lds_f64x2(a_cmul + cur * 16);
+                const double2 c01 = sk_lds_f64x2(a_c);
                 c[0] = c01.x; c[1 % RPC] = c01.y;
-            } else c[0] = sk_lds_f64(a_cmul + cur * 8);
-            const uint32_t row = a_J + (uint32_t)rb * rowbytes;
+            } else c[0] = sk_lds_f64(a_c);
             double2 Jv[SLOTS];
 #pragma unroll
             for (int k = 0; k < SLOTS; k++) Jv[k] = sk_lds_f64x2(row + off[k]);
@@ -768,48 +741,97 @@ __global__ void __launch_bounds__(576, 1) k_sk_lockstep_reg(sk_ls_params P)
                     v[k][rp].y = fma(Jv[k].y, c[rp], v[k][rp].y);
                 }
             }
-            cur ^= 1;
-            publish(in2, cur);
+            publish(in2, a_m);
             if (++in2 == N) in2 = 0;
-            if (++rb == NBUF) rb = 0;
+            a_c ^= RPC * 8; a_m ^= RPC * 8;
+            row += rowbytes; if (row == row_end) row = a_J;
             __syncthreads();
+        }
+        __syncthreads();                                                           // the deciders have flushed the final spins
+#pragma unroll
+        for (int k = 0; k < SLOTS; k++) {                                          // lf = σ·u
+            const int j2 = k * NB + bt;
+#pragma unroll
+            for (int rp = 0; rp < RPC; rp++) {
+                const int64_t r = rbase + rp;
+                if (j2 < half && r < P.R) {
+                    const uint32_t s2 = sp[rp * nw + (j2 >> 4)] >> ((2 * j2) & 31);
+                    *reinterpret_cast<double2 *>(&P.lf[r * N + 2 * j2]) =
+                        make_double2((s2 & 1u) ? v[k][rp].x : -v[k][rp].x, (s2 & 2u) ? v[k][rp].y : -v[k][rp].y);
+                }
+            }
         }
     } else if (warp == 0) {
-        // (all 32 lanes run the loop and meet at the same barrier instruction; lanes >= RPC only keep the barrier count)
+        // (all 32 lanes run the loop and meet at the same barrier instructions; lanes >= RPC only keep the barrier count)
+        const int64_t rmine = rbase + lane;
         const bool live = decider && rmine < P.R;
-        const uint32_t a_sp = sk_smem_u32(sp + (size_t)(decider ? lane : 0) * nw), a_c = a_cmul + lane * 8, a_m = a_mail + lane * 8;
-        const uint32_t a_u = sk_smem_u32(&ubuf[0][decider ? lane : 0]);
+        double E = 0.0, beta = 0.0, cp = 0.0; long long nacc = 0;                  // cp: the multiplier of the current step
+        if (live) { E = P.E[rmine]; beta = P.beta[rmine]; nacc = P.acc[rmine]; }
         const double nbeta = -beta;
-        int i = 0, rb = 0, cur = 0;
-        for (long long g = 0; g < nsteps; g++) {
-            const int in = i + 1 < N ? i + 1 : 0;                                   // the site of step g + 1
+        // accept() of RRRMC.jl:39 on x = -βΔE with the prepared draw at shared address ad (ex2.approx: 2 ulp, and
+        // -32·log2(e) is far above the denormal range, so no range reduction is needed)
+        auto accept = [&](double x, uint32_t ad) -> int {
+            if (x >= 0) return 1;
+            float lo, hi, e;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(lo), "=f"(hi) : "r"(ad + 8) : "memory");
+            const float xf = (float)x;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaxf(xf, -32.0f) * 1.4426950408889634f));
+            if (xf >= -32.0f && hi < e) return 1;
+            if (lo > e) return 0;
+            return sk_lds_f64(ad) < exp(x);
+        };
+        // the replica's spins: the word that holds the site being decided stays in a register (nobody else reads the
+        // shared copy before the end) and is written back when the sweep moves on to the next word
+        const uint32_t a_sp = sk_smem_u32(sp + (size_t)(decider ? lane : 0) * nw);
+        uint32_t w = decider ? sk_lds_u32(a_sp) : 0u, a_w = a_sp;
+        if (decider && nsteps > 0) {
+            const double f = live ? P.lf[rmine * N] : 0.0;
+            const sk_draw d = draw(0, lane);
+            ubuf[0][lane] = d;
+            const int ok = live ? accept(-beta * f, sk_smem_u32(&ubuf[0][lane])) : 0;
+            if (ok) { E += f; nacc++; }
+            cp = ok ? ((w & 1u) ? -4.0 : 4.0) : 0.0;                               // 4·σ' of the new spin
+            cmul[0][lane] = cp;
+            w ^= (uint32_t)ok;
+        }
+        __syncthreads();
+        uint32_t a_m = a_mail + lane * 8, a_c = a_cmul + lane * 8 + RPC * 8, row = a_J;
+        const uint32_t a_u0 = sk_smem_u32(&ubuf[0][decider ? lane : 0]), a_uend = a_u0 + RING * RPC * 16, row_end = a_J + NBUF * rowbytes;
+        uint32_t a_u = a_u0 + RPC * 16;                                            // the draw of step g + 1
+        int in = s1;                                                               // the site of step g + 1
+        for (long long g = 0; g + 1 < nsteps; g++) {
             if (decider) {
-                if (g + 1 < nsteps) {
-                    // the chain: mailbox and coupling -> u of site i+1 under row i -> x = -β·σ·u -> accept -> multiplier
-                    const double m = sk_lds_f64(a_m + cur * (RPC * 8));
-                    const double a = sk_lds_f64(a_J + (uint32_t)rb * rowbytes + (uint32_t)in * 8);
-                    const uint32_t wj = sk_lds_u32(a_sp + (uint32_t)(in >> 5) * 4);
-                    const uint32_t ua = a_u + (uint32_t)((g + 1) % RING) * (RPC * 16);
-                    const double du = sk_lds_f64(ua);
-                    const uint32_t dlo = sk_lds_u32(ua + 8), dhi = sk_lds_u32(ua + 12);
-                    const int sj = (int)((wj >> (in & 31)) & 1u);
-                    const double bs = sj ? nbeta : beta;                            // -β·σ of site i+1
-                    const double u = fma(a, cp, m);                                 // row i on u of site i+1 (N >= 2: in != i)
-                    const int ok = live ? accept(bs * u, du, __uint_as_float(dlo), __uint_as_float(dhi)) : 0;
-                    if (cp != 0.0) {                                                // the flip of site i, decided one step ago
-                        const uint32_t aw = a_sp + (uint32_t)(i >> 5) * 4;
-                        sk_sts_u32(aw, sk_lds_u32(aw) ^ (1u << (i & 31)));
-                    }
-                    cp = ok ? (sj ? -4.0 : 4.0) : 0.0;
-                    sk_sts_f64(a_c + (cur ^ 1) * (RPC * 8), cp);
-                    if (ok) { E += sj ? u : -u; nacc++; }                           // ΔE = lfields[i+1] = σ·u, SK.jl:278-284
-                } else if (cp != 0.0) sp[lane * nw + (i >> 5)] ^= 1u << (i & 31);
+                if ((in & 31) == 0) { sk_sts_u32(a_w, w); a_w = a_sp + (uint32_t)(in >> 5) * 4; w = sk_lds_u32(a_w); }
+                // the chain: mailbox and coupling -> u of site i+1 under row i -> x = -β·σ·u -> accept -> multiplier
+                const double m = sk_lds_f64(a_m);
+                const double a = sk_lds_f64(row + (uint32_t)in * 8);
+                const uint32_t sj = (w >> (in & 31)) & 1u;
+                const double bs = sj ? nbeta : beta;                                // -β·σ of site i+1
+                const double c4 = sj ? -4.0 : 4.0, sd = sj ? 1.0 : -1.0;
+                const double u = fma(a, cp, m);                                     // row i on u of site i+1 (N >= 2: in != i)
+                const int ok = live ? accept(bs * u, a_u) : 0;
+                cp = ok ? c4 : 0.0;
+                sk_sts_f64(a_c, cp);
+                if (ok) { E = fma(u, sd, E); nacc++; w ^= 1u << (in & 31); }        // ΔE = lfields[i+1] = σ·u, SK.jl:278-284
             }
-            i = in; cur ^= 1;
-            if (++rb == NBUF) rb = 0;
+            if (++in == N) in = 0;
+            a_m ^= RPC * 8; a_c ^= RPC * 8;
+            a_u += RPC * 16; if (a_u == a_uend) a_u = a_u0;
+            row += rowbytes; if (row == row_end) row = a_J;
             __syncthreads();
         }
+        if (decider) sk_sts_u32(a_w, w);
+        if (nsteps > 0) __syncthreads();                                           // the last step: nothing left to decide
+        __syncthreads();
+        if (live) { P.E[rmine] = E; P.acc[rmine] = nacc; }
     } else {
+        const int qs = lane / RPC, qr = lane % RPC;                                // lane -> (step of the batch, replica)
+        if (nsteps > 0) {
+            if (lane == 0) { fetch_row(0, 0); if (nsteps > 1) fetch_row(s1, 1); }
+            if (qs < Q) ubuf[(1 + qs) % RING][qr] = draw(1 + qs, qr);              // steps 1..Q, decided during steps 0..Q-1
+            if (lane == 0) wait_row(0, 0);
+        }
+        __syncthreads();
         int in2 = 2 < N ? 2 : 2 - N, rb1 = 1; uint32_t par1 = 0;                  // buffer of row g+1 and its mbarrier phase
         for (long long g = 0; g < nsteps; g++) {
             // buffer (g+2) % 3 was last read in step g-1, which ended with the barrier
@@ -822,22 +844,7 @@ __global__ void __launch_bounds__(576, 1) k_sk_lockstep_reg(sk_ls_params P)
             if (++rb1 == NBUF) { rb1 = 0; par1 ^= 1u; }
             __syncthreads();
         }
-    }
-    __syncthreads();
-    if (bulk) {                                                                    // lf = σ·u with the final spins
-#pragma unroll
-        for (int k = 0; k < SLOTS; k++) {
-            const int j2 = k * NB + bt;
-#pragma unroll
-            for (int rp = 0; rp < RPC; rp++) {
-                const int64_t r = rbase + rp;
-                if (j2 < half && r < P.R) {
-                    const uint32_t s2 = sp[rp * nw + (j2 >> 4)] >> ((2 * j2) & 31);
-                    *reinterpret_cast<double2 *>(&P.lf[r * N + 2 * j2]) =
-                        make_double2((s2 & 1u) ? v[k][rp].x : -v[k][rp].x, (s2 & 2u) ? v[k][rp].y : -v[k][rp].y);
-                }
-            }
-        }
+        __syncthreads();
     }
     for (int rp = 0; rp < RPC; rp++) {
         const int64_t r = rbase + rp;
@@ -847,7 +854,6 @@ __global__ void __launch_bounds__(576, 1) k_sk_lockstep_reg(sk_ls_params P)
             P.chunks[r * P.nchunks + c] = lo | (hi << 32);
         }
     }
-    if (decider && rmine < P.R) { P.E[rmine] = E; P.acc[rmine] = nacc; }
 }
 
 
