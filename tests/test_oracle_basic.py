@@ -154,3 +154,48 @@ def test_discrete_cache_consistency():
         s = random_config(g.N, 2)
         sites = rng.integers(1, g.N + 1, 300).astype(np.int64)
         assert ffi.lib().orc_check_discrete_cache(g.h, s, 1.3, sites, len(sites)) == 0, name
+
+
+def test_sk_lockstep_sweeps_restatement():
+    """orc_sk_lockstep_sweeps against a line-by-line numpy version of the same schedule (accept of RRRMC.jl:39 on
+    ΔE = lfields[i], update_cache! of SK.jl:252-265), and the checkenergy invariant: tracked E and incrementally updated
+    fields equal a from-scratch energy() (SK.jl:212-237)."""
+    import math
+    N, R, nsw, seed, sweep0 = 12, 3, 4, 0x1234567890ab, (1 << 32) - 2
+    J = sk_gauss(N, 5)
+    g = ffi.Graph.sk_f64(J)
+    beta = np.array([0.4, 1.0, 2.5])
+    chunks = np.stack([random_config(N, 20 + r) for r in range(R)]).astype(np.uint64)
+    lf = np.zeros((R, N)); E = np.zeros(R)
+    for r in range(R):
+        E[r] = g.energy(chunks[r]); lf[r] = g.lfields()
+    want_s = np.stack([bits(chunks[r], N) for r in range(R)]).astype(np.int64)
+    want_lf, want_E, want_acc = lf.copy(), E.copy(), np.zeros(R, np.int64)
+    key = np.array([seed & 0xffffffff, seed >> 32], np.uint32)
+    for r in range(R):
+        for sw in range(nsw):
+            t = sweep0 + sw
+            for i in range(N):
+                dE = want_lf[r, i]; x = -beta[r] * dE
+                ok = x >= 0
+                if not ok:
+                    ctr = np.array([i, r, t & 0xffffffff, (t >> 32) ^ 0x534b4c53], np.uint32); o = np.zeros(4, np.uint32)
+                    ffi.lib().orc_philox4x32_10(ctr, key, o)
+                    u = float(((int(o[1]) << 32) | int(o[0])) >> 11) * 2.0 ** -53
+                    ok = u < math.exp(x)
+                if not ok:
+                    continue
+                want_E[r] += dE; want_acc[r] += 1
+                want_s[r, i] ^= 1
+                for j in range(N):
+                    if j != i:
+                        want_lf[r, j] = want_lf[r, j] + 4 * ((1 - 2 * (want_s[r, i] ^ want_s[r, j])) * J[i, j])
+                want_lf[r, i] = -want_lf[r, i]
+    acc = np.zeros(R, np.int64)
+    ffi.sk_lockstep_sweeps(J, chunks, lf, E, acc, beta, seed, sweep0, nsw)
+    got_s = np.stack([bits(chunks[r], N) for r in range(R)])
+    assert np.array_equal(got_s, want_s) and np.array_equal(lf, want_lf) and np.array_equal(E, want_E)
+    assert np.array_equal(acc, want_acc) and acc.sum() > 0
+    for r in range(R):
+        assert g.energy(chunks[r]) == pytest.approx(E[r], abs=1e-12)
+        assert np.allclose(g.lfields(), lf[r], atol=1e-12)
