@@ -66,7 +66,7 @@ def test_lockstep_invariants(N, R):
 
 
 @pytest.mark.parametrize("variant", ["0", "3", "2", "1"])   # registers / site pipeline / TMA rows / plain loads
-@pytest.mark.parametrize("N,R,nsw", [(2, 5, 9), (64, 300, 6), (96, 33, 5), (512, 64, 3), (1026, 149, 2), (4096, 8, 1)])
+@pytest.mark.parametrize("N,R,nsw", [(2, 5, 9), (64, 300, 6), (96, 33, 5), (512, 64, 3), (1026, 149, 2), (4096, 8, 1), (4098, 6, 1)])
 def test_lockstep_trajectory_vs_oracle(N, R, nsw, variant, monkeypatch):
     """Bit-exact trajectory parity of every lock-step kernel with the CPU restatement (orc_sk_lockstep_sweeps): same
     configurations, fields, tracked energies and acceptance counts, per-replica β; two calls continue one run."""
