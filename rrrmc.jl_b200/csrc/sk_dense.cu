@@ -21,7 +21,7 @@
 #include "philox.cuh"
 
 constexpr int SKQ_SLICES = 5;          // 8-bit digit planes of the fixed-point couplings
-constexpr int TC_M = 128, TC_N = 64, TC_KB = 128; // CTA tile: 128 sites x 64 replicas, 128 bytes of K per stage
+constexpr int TC_M = 128, TC_N = 64, TC_KB = 128; // CTA tile: 128 replicas x 64 sites (x 5 digit planes), 128 bytes of K per stage
 
 // ------------------------------------------------------------------------------------------------
 // spins as int8 ±1, [R][Npad] (B operand of the GEMM; K-major)
@@ -75,13 +75,17 @@ struct sk_tc_params {
     double scale;           // 2^-P
 };
 
-// Pipeline: a stage holds one 128-byte K chunk of all five digit planes of the A tile (5 x 16 KiB) and of the B tile
-// (8 KiB, loaded once per chunk instead of once per plane); two stages in dynamic shared memory. All threads fill
-// stage kc with cp.async (16-byte chunks straight into the 128-byte-swizzled layout, four full 128-byte lines per
-// warp instruction) while the tensor core consumes stage kc-1; a per-stage mbarrier armed by tcgen05.commit tells
-// the producers when the MMAs have drained a stage.
-constexpr int TC_STAGE_BYTES = (SKQ_SLICES * TC_M + TC_N) * TC_KB;   // 88 KiB
-constexpr int TC_STAGES = 2;
+// Tiling: the M side of the MMA (128 TMEM lanes) is the REPLICAS, the N side 64 sites of one digit plane, five
+// accumulators of 64 columns (TMEM's 512 columns allow no more). The kernel is bound by the operand bytes that cross
+// L2 -> SM per MAC, and this orientation needs 128 + 5·64 = 448 bytes per K byte for 5·128·64 MACs where the other one
+// (128 sites x 64 replicas) needs 704; each J tile is read by R/128 CTAs instead of R/64.
+// Pipeline: a stage holds one 128-byte K chunk of the spin tile (16 KiB) and of the five digit-plane tiles (5 x 8 KiB);
+// three stages in dynamic shared memory. All threads fill stage kc+2 with cp.async (16-byte chunks straight into the
+// 128-byte-swizzled layout, four full 128-byte lines per warp instruction) AFTER the MMAs of chunk kc have been queued,
+// so the tensor pipe always has the next chunk's instructions behind the running ones; a per-stage mbarrier armed by
+// tcgen05.commit tells the producers when the MMAs have drained a stage.
+constexpr int TC_STAGE_BYTES = (TC_M + SKQ_SLICES * TC_N) * TC_KB;   // 56 KiB
+constexpr int TC_STAGES = 3;
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(g) : "memory");
@@ -92,8 +96,8 @@ __global__ void __launch_bounds__(128, 1) k_sk_fields_tc(sk_tc_params P)
     __shared__ __align__(8) uint64_t mbar[TC_STAGES];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int i0 = blockIdx.x * TC_M;
-    const int64_t r0 = (int64_t)blockIdx.y * TC_N;
+    const int i0 = blockIdx.x * TC_N;                // first site of the tile
+    const int64_t r0 = (int64_t)blockIdx.y * TC_M;   // first replica
     constexpr uint32_t TMEM_COLS = 512;              // 5 accumulators x 64 columns, rounded up to a power of two
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     if (warp == 0) {
@@ -113,34 +117,34 @@ __global__ void __launch_bounds__(128, 1) k_sk_fields_tc(sk_tc_params P)
     const int nkc = P.Npad / TC_KB;
     const int c16 = lane & 7, rsub = lane >> 3;      // this lane's 16-byte chunk and row offset inside a 4-row group
 
-    auto fill = [&](int kc) {                        // all threads: stage kc % 2 <- K chunk kc
+    auto fill = [&](int kc) {                        // all threads: stage kc % 3 <- K chunk kc
         uint8_t *stg = base + (size_t)(kc % TC_STAGES) * TC_STAGE_BYTES;
+        const int8_t *A = P.S8 + (size_t)kc * TC_KB + c16 * 16;
+        const uint32_t sA = smem_u32(stg);
 #pragma unroll
-        for (int sl = 0; sl < SKQ_SLICES; sl++) {
-            const int8_t *A = P.Jq + (size_t)sl * P.Npad * P.Npad + (size_t)kc * TC_KB + c16 * 16;
-            const uint32_t sA = smem_u32(stg + (size_t)sl * TC_M * TC_KB);
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int row = warp * 32 + j * 4 + rsub;
-                cp_async16(sA + sw128_off(row, c16), A + (size_t)(i0 + row) * P.Npad);
-            }
+        for (int j = 0; j < 8; j++) {                // 128 replica rows
+            const int row = warp * 32 + j * 4 + rsub;
+            cp_async16(sA + sw128_off(row, c16), A + (size_t)(r0 + row) * P.Npad);
         }
-        const int8_t *B = P.S8 + (size_t)kc * TC_KB + c16 * 16;
-        const uint32_t sB = smem_u32(stg + (size_t)SKQ_SLICES * TC_M * TC_KB);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int row = warp * 16 + j * 4 + rsub;
-            cp_async16(sB + sw128_off(row, c16), B + (size_t)(r0 + row) * P.Npad);
+        for (int sl = 0; sl < SKQ_SLICES; sl++) {    // 64 site rows of each digit plane
+            const int8_t *B = P.Jq + (size_t)sl * P.Npad * P.Npad + (size_t)kc * TC_KB + c16 * 16;
+            const uint32_t sB = smem_u32(stg + (size_t)TC_M * TC_KB + (size_t)sl * TC_N * TC_KB);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int row = warp * 16 + j * 4 + rsub;
+                cp_async16(sB + sw128_off(row, c16), B + (size_t)(i0 + row) * P.Npad);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto mma = [&](int kc) {                         // thread 0: 5 planes x 4 K-steps on stage kc % 2, then arm its mbarrier
+    auto mma = [&](int kc) {                         // thread 0: 5 planes x 4 K-steps on stage kc % 3, then arm its mbarrier
         const uint32_t stg = smem_u32(base + (size_t)(kc % TC_STAGES) * TC_STAGE_BYTES);
-        const uint64_t descB = umma_desc_k_sw128(stg + SKQ_SLICES * TC_M * TC_KB);
+        const uint64_t descA = umma_desc_k_sw128(stg);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int sl = 0; sl < SKQ_SLICES; sl++) {
-            const uint64_t descA = umma_desc_k_sw128(stg + sl * TC_M * TC_KB);
+            const uint64_t descB = umma_desc_k_sw128(stg + TC_M * TC_KB + sl * TC_N * TC_KB);
 #pragma unroll
             for (int k = 0; k < TC_KB / 32; k++) {   // K = 32 bytes per instruction for 8-bit operands
                 const uint32_t accumulate = (kc | k) ? 1u : 0u;
@@ -155,22 +159,25 @@ __global__ void __launch_bounds__(128, 1) k_sk_fields_tc(sk_tc_params P)
     };
 
     fill(0);
+    if (nkc > 1) fill(1);
     for (int kc = 0; kc < nkc; kc++) {
-        if (kc + 1 < nkc) {
-            // stage (kc+1)%2 was last read by the MMAs of chunk kc-1: their commit is completion number (kc-1)/2 of that barrier
-            if (kc >= 1) mbar_wait(smem_u32(&mbar[(kc + 1) % TC_STAGES]), (uint32_t)(((kc - 1) / TC_STAGES) & 1));
-            fill(kc + 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");     // chunk kc has landed (this thread's part)
-        } else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (kc + 1 < nkc) asm volatile("cp.async.wait_group 1;" ::: "memory");   // chunk kc has landed (this thread's part)
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
         __syncthreads();
         if (tid == 0) mma(kc);
+        if (kc + 2 < nkc) {
+            // stage (kc+2)%3 was last read by the MMAs of chunk kc-1 (running or done; chunk kc is queued behind them):
+            // their commit is completion number (kc-1)/3 of that stage's barrier
+            if (kc >= 1) mbar_wait(smem_u32(&mbar[(kc + 2) % TC_STAGES]), (uint32_t)(((kc - 1) / TC_STAGES) & 1));
+            fill(kc + 2);
+        }
     }
-    // all MMAs done: the last commit of each stage's barrier
+    // all MMAs done: the last commit of the last stage's barrier (commits complete in order)
     mbar_wait(smem_u32(&mbar[(nkc - 1) % TC_STAGES]), (uint32_t)(((nkc - 1) / TC_STAGES) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // epilogue: thread = TMEM lane = site i0+tid; columns = replicas. Recombine the five digit accumulators exactly.
-    const int i = i0 + tid;
+    // epilogue: thread = TMEM lane = replica r0+tid; columns = sites. Recombine the five digit accumulators exactly.
+    const int64_t r = r0 + tid;
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
     for (int c0 = 0; c0 < TC_N; c0 += 16) {
         long long acc[16];
@@ -187,14 +194,15 @@ __global__ void __launch_bounds__(128, 1) k_sk_fields_tc(sk_tc_params P)
 #pragma unroll
             for (int n = 0; n < 16; n++) acc[n] = acc[n] * 256 + (long long)(int32_t)v[n];
         }
-        if (i < P.N) {
+        if (r < P.R) {
+            const int4 sv = *reinterpret_cast<const int4 *>(P.S8 + (size_t)r * P.Npad + i0 + c0);   // the replica's 16 spins (±1, 0 in the padding)
+            const int8_t *sb = reinterpret_cast<const int8_t *>(&sv);
 #pragma unroll
             for (int n = 0; n < 16; n++) {
-                const int64_t r = r0 + c0 + n;
-                if (r < P.R) {
+                const int i = i0 + c0 + n;
+                if (i < P.N) {
                     const double H = (double)acc[n] * P.scale;           // Σ_j J_ij σ_rj
-                    const double si = (double)P.S8[(size_t)r * P.Npad + i];
-                    P.lf[(size_t)r * P.N + i] = 2.0 * si * H;
+                    P.lf[(size_t)r * P.N + i] = 2.0 * (double)sb[n] * H;
                 }
             }
         }
@@ -897,8 +905,8 @@ static rrrmc_status_t sk_dense_quantise(rrrmc_state *s, const std::vector<double
     rrrmc_graph *g = s->g; sk_dense_store *d = s->skd;
     if (d->Jq) return RRRMC_OK;
     const int64_t N = g->N;
-    d->Npad = (int)(((N + TC_M - 1) / TC_M) * TC_M);
-    d->Rpad = ((s->R + TC_N - 1) / TC_N) * TC_N;
+    d->Npad = (int)(((N + TC_KB - 1) / TC_KB) * TC_KB);
+    d->Rpad = ((s->R + TC_M - 1) / TC_M) * TC_M;
     double mx = 0;
     for (double v : J) mx = std::max(mx, std::fabs(v));
     int e = 0; if (mx > 0) frexp(mx, &e);                 // mx < 2^e
@@ -935,7 +943,7 @@ rrrmc_status_t sk_dense_fields_init(rrrmc_state *s, int use_tensor_cores, double
         RR_CUDA(cudaEventRecord(e0, ctx->stream));
         k_spins_to_s8<<<div_up(s->R * d->Npad, 256), 256, 0, ctx->stream>>>(s->d_chunks, s->nchunks, s->R, N, d->Npad, d->S8);
         sk_tc_params P{ d->Jq, d->S8, d->lf, N, d->Npad, s->R, d->Rpad, d->scale };
-        dim3 grid(d->Npad / TC_M, (unsigned)(d->Rpad / TC_N));
+        dim3 grid(d->Npad / TC_N, (unsigned)(d->Rpad / TC_M));
         const int tc_smem = TC_STAGES * TC_STAGE_BYTES + 1024;
         RR_CUDA(cudaFuncSetAttribute(k_sk_fields_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem));
         k_sk_fields_tc<<<grid, 128, tc_smem, ctx->stream>>>(P);
