@@ -48,7 +48,7 @@ def needs_build():
 
 
 def _compile(nvcc, src, obj):
-    cmd = [nvcc] + NVCC_FLAGS + ["-c", "-o", obj, src]
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("RRRMC_NVCC_EXTRA", "").split() + ["-c", "-o", obj, src]   # (diagnostic builds: -DFLOW_DIAG)
     res = subprocess.run(cmd, capture_output=True, text=True)
     return res.returncode, " ".join(cmd) + "\n" + res.stdout + res.stderr
 

@@ -61,6 +61,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
+// The consumers' "stage is free" arrive. It must not be issued before the thread's ld.shared of the stage have actually
+// RETURNED: ptxas places SYNCS.ARRIVE right behind the (still outstanding) LDS, and once the last thread has arrived the
+// issuer refills the stage through the async proxy — measured on B200 (scripts/stress_flow.py): one warp of a block's first
+// brick now and then computed its second site from the NEXT brick's bytes. So the barrier address is made to depend on a
+// value computed from every word the thread loaded (dep·1 − dep = 0, `one` being a launch parameter opaque to ptxas): the
+// arrive waits on the loads' scoreboards like any consumer of their data.
+__device__ __forceinline__ void mbar_arrive_after(uint32_t bar, uint32_t dep, uint32_t one)
+{
+    const uint32_t z = dep * one - dep;
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar + z) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     asm volatile("{\n\t.reg .pred p;\n"
@@ -226,7 +237,6 @@ __global__ void __launch_bounds__(NCONS + 32, MINB) k_checkerboard_tma(const __g
                 v[2] = lds128<DZ2 + PLANE_BYTES + BX * ROWB>(a0); v[3] = lds128<DZ2 + PLANE_BYTES - BX * ROWB>(a0);
                 v[4] = lds128<DZ2 + 2 * PLANE_BYTES>(a0); v[5] = lds128<DZ2>(a0);
                 ja = lds128<32 * 32>(aj); jb = lds64<32 * 32 + 16>(aj);
-                mbar_arrive(empty);                      // this thread has read everything it needs from the stage
             }
             const uint32_t neg[6] = { ja.x, ja.y, ja.z, ja.w, jb.x, jb.y };
             uint32_t sc[4] = { c.x, c.y, c.z, c.w }, bp[4][2 * D], fl[4];
@@ -237,6 +247,7 @@ __global__ void __launch_bounds__(NCONS + 32, MINB) k_checkerboard_tma(const __g
             }
 #pragma unroll
             for (int w = 0; w < 4; w++) fl[w] = cbp_flip_planes<D>(bp[w], m[j][w], gg[j][w]);
+            if (j == 1) mbar_arrive_after(empty, fl[0], p.one);   // this thread has read everything it needs from the stage (fl[0] depends on all of it)
             if (wslow[j]) {                              // a uniform branch, taken by ~13 % of the warps at β = 1
                 asm volatile("" ::: "memory");           // (kept a branch: predicating it would cost every task 8 instructions)
                 if (slow[j]) {
@@ -494,7 +505,6 @@ __global__ void __launch_bounds__(NFLOW, MINB) k_checkerboard_flow(const __grid_
                     v[2] = lds128<DZ2 + PLANE_BYTES + BX * ROWB>(a0); v[3] = lds128<DZ2 + PLANE_BYTES - BX * ROWB>(a0);
                     v[4] = lds128<DZ2 + 2 * PLANE_BYTES>(a0); v[5] = lds128<DZ2>(a0);
                     ja = lds128<32 * 32>(aj); jb = lds64<32 * 32 + 16>(aj);
-                    mbar_arrive(empty);                      // this thread has read everything it needs from the stage
                 }
                 const uint32_t neg[6] = { ja.x, ja.y, ja.z, ja.w, jb.x, jb.y };
                 uint32_t sc[4] = { c.x, c.y, c.z, c.w }, bp[4][2 * D], kc[4], tt[4], ns[4];
@@ -509,6 +519,7 @@ __global__ void __launch_bounds__(NFLOW, MINB) k_checkerboard_flow(const __grid_
                     cbp_flip_parts(bp[w], m[j][w], gg[j][w], kc[w], tt[w]);
                     ns[w] = lop3p<0x1E>(sc[w], kc[w], tt[w]);
                 }
+                if (j == 1) mbar_arrive_after(empty, ns[0], p.one);   // this thread has read everything it needs from the stage (ns[0] depends on all of it)
                 // a level-3 hit flips its lane whatever the bonds say. A uniform branch, taken by ~13 % of the warps at
                 // β = 1, and kept a BRANCH (an out-of-line call): if-converted, its eight LOP3 would take issue slots in
                 // every task, and integer issue is what bounds the kernel

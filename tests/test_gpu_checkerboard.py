@@ -554,6 +554,27 @@ def test_checkerboard_ladder_full_size_bit_exact():
     assert np.array_equal(np.asarray(after.chunks), np.asarray(got.chunks)[perm])
 
 
+def test_checkerboard_ladder_full_size_repeated_runs_agree():
+    """Regression for a shared-memory stage race of the brick kernels (the consumers' "stage is free" arrive was issued
+    while their ld.shared were still outstanding, and the refill through the async proxy could overtake them: about one
+    run in ten of the ladder kernel at this size computed one warp's task from the next brick's bytes). Forty runs from
+    the same start must all reproduce the oracle's trajectory (scripts/stress_flow.py is the long version)."""
+    L, D, R = 64, 3, 1024
+    A, J = ea_instance(L, D, seed=64)
+    X = rb.GraphEA(L, D, replicas=R, A=A, J=J)
+    C0 = rb.Config(X.N, R, rng=np.random.default_rng(2))
+    tbls = _ladder_tbls(np.geomspace(1.0, 1.6, 8))
+    sp = _multispin(C0)
+    ffi.checkerboard_sweeps_poisson_ladder(L, D, R, sp, _fwd(A, J, L, D), tbls, 2, 0xABCDEF, 5, 1)
+    want = np.asarray(_from_multispin(sp, R).chunks)
+    bad = 0
+    for _ in range(40):
+        X._upload(C0)
+        check(lib().rrrmc_checkerboard_sweeps_poisson_ladder(X._state, ptr(tbls), 8, 2, 0xABCDEF, 5, 1))
+        bad += not np.array_equal(np.asarray(X._download().chunks), want)
+    assert bad == 0, "%d of 40 runs differ from the oracle" % bad
+
+
 def test_two_contexts_run_the_multi_sweep_kernel_from_two_threads():
     """Two batches on two contexts (two streams) driven by two host threads at once, as bench.py's end-to-end arm does:
     the persistent multi-sweep kernels are chained device-wide (two half-resident cooperative grids would wait for each
