@@ -416,8 +416,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (β-sweep runs)")
     args = ap.parse_args()
     globals()["BETA"] = args.beta
-    if "BENCH_METHOD" not in os.environ and args.beta < 0.6:
-        globals()["METHOD"] = "planes"   # what RRRMC_CB_AUTO selects for warm runs: the count procedures lose to bit planes below β ≈ 0.6
+    if "BENCH_METHOD" not in os.environ and args.beta < 0.54:
+        globals()["METHOD"] = "planes"   # what RRRMC_CB_AUTO selects for warm runs: the count procedures lose to bit planes below β ≈ 0.54
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":

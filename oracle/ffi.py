@@ -512,7 +512,7 @@ def cb_poisson_nw(tbl, tol=None):
     tol=None: the engine's per-NW defaults."""
     if tbl[CBP_KA - 2] != 0xffffffff:
         return 0
-    for nw, d in ((1, 0.03), (2, 0.2), (4, 0.06), (6, 0.05)):
+    for nw, d in ((1, 0.03), (2, 0.2), (4, 0.06), (6, 0.012)):
         if 1.0 - (float(tbl[4 * nw - 1]) + 1.0) / 2.0 ** 32 <= (d if tol is None else tol):
             return nw
     return 0

@@ -1027,7 +1027,9 @@ extern "C" int rrrmc_checkerboard_poisson_nw(const uint32_t *tbl, double tol)
     if (!tbl) return 0;
     if (tbl[CBP_KA - 2] != 0xffffffffu) return 0;   // the 64-entry table does not cover the count distribution
     const int nws[4] = { 1, 2, 4, 6 };
-    const double dflt[4] = { 0.03, 0.2, 0.06, 0.05 };
+    // (NW = 6: with 1.2 % of the tasks overflowing, a fifth of the warps take the second tier; beyond that — β < 0.54 in 3D —
+    // the bit-plane kernel is faster: measured 2.5 vs 3.0·10¹² at β = 0.5, 3.1 vs 2.9 at 0.55, profiles/r2x_beta_sweep.jsonl)
+    const double dflt[4] = { 0.03, 0.2, 0.06, 0.012 };
     for (int k = 0; k < 4; k++)
         if (1.0 - ((double)tbl[4 * nws[k] - 1] + 1.0) / 4294967296.0 <= (tol > 0 ? tol : dflt[k])) return nws[k];
     return 0;
