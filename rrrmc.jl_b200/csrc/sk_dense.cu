@@ -260,7 +260,7 @@ struct sk_ls_params {
 template <int RPC>
 __global__ void __launch_bounds__(512, 1) k_sk_lockstep(sk_ls_params P)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int N = P.N, tid = threadIdx.x, nt = blockDim.x;
     double *lf = reinterpret_cast<double *>(smem_raw);                    // [RPC][N]
     uint32_t *sp = reinterpret_cast<uint32_t *>(lf + (size_t)RPC * N);     // [RPC][nw]
@@ -449,155 +449,6 @@ __global__ void __launch_bounds__(512, 1) k_sk_lockstep_tma(sk_ls_params P)
     if (tid < RPC && rbase + tid < P.R) { P.E[rbase + tid] = E; P.acc[rbase + tid] = nacc; }
 }
 
-// The same sweeps, software-pipelined across sites: ONE block barrier per site instead of two, and the Metropolis decision
-// of site i+1 (an exp and a Philox call on RPC lanes) runs while the other sixteen warps apply the row of site i.
-// The decision of site i+1 needs lf[r][i+1] with every accepted flip up to site i applied; the flips before i were applied
-// by earlier bulk updates (complete at the barrier), and the deciding lane applies row i to that ONE element itself before
-// it decides — the bulk update skips it. Per element the operations and their order are those of the kernels above:
-// bit-identical fields, energies and configurations (same draw stream).
-template <int RPC>
-__global__ void __launch_bounds__(544, 1) k_sk_lockstep_pipe(sk_ls_params P)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int N = P.N, tid = threadIdx.x, nt = blockDim.x;
-    constexpr int NBUF = 3;                                                // rows in flight: a row is requested two sites ahead
-    double *Jb = reinterpret_cast<double *>(smem_raw);                     // [NBUF][N] coupling rows
-    double *lf = Jb + NBUF * (size_t)N;                                    // [RPC][N]
-    uint32_t *sp = reinterpret_cast<uint32_t *>(lf + (size_t)RPC * N);     // [RPC][nw]
-    const int nw = (N + 31) / 32;
-    __shared__ int flag[2][RPC];
-    __shared__ int snew[2][RPC];
-    __shared__ __align__(8) uint64_t bar[3];
-    const uint32_t rowbytes = (uint32_t)N * 8u;
-    const int64_t rbase = (int64_t)blockIdx.x * RPC;
-    if (tid == 0) {
-        for (int b = 0; b < 3; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(sk_smem_u32(&bar[b])) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    for (int rp = 0; rp < RPC; rp++) {
-        const int64_t r = rbase + rp;
-        for (int j = tid; j < N; j += nt) lf[(size_t)rp * N + j] = r < P.R ? P.lf[r * N + j] : 0.0;
-        for (int w = tid; w < nw; w += nt) {
-            const uint64_t c = r < P.R ? P.chunks[r * P.nchunks + (w >> 1)] : 0ull;
-            sp[rp * nw + w] = (uint32_t)(c >> ((w & 1) * 32));
-        }
-    }
-    double E = 0.0, beta = 0.0; long long nacc = 0;
-    if (tid < RPC && rbase + tid < P.R) { E = P.E[rbase + tid]; beta = P.beta[rbase + tid]; nacc = P.acc[rbase + tid]; }
-    __syncthreads();
-    auto fetch_row = [&](int row, int buf) {      // thread 0: row -> Jb[buf], completion on bar[buf]
-        const uint32_t b = sk_smem_u32(&bar[buf]);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(rowbytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     :: "r"(sk_smem_u32(Jb + (size_t)buf * N)), "l"(P.J + (size_t)row * N), "r"(rowbytes), "r"(b) : "memory");
-    };
-    // accept() of RRRMC.jl:39 for replica `tid` at site i of sweep t, given its (current) field; -> flag / snew of step `buf`
-    auto decide = [&](int i, uint64_t t, double dE, int buf) {
-        const int64_t r = rbase + tid;
-        int ok = 0;
-        if (r < P.R) {
-            const double x = -beta * dE;                                           // ΔE_i = +lfields[i], SK.jl:278-284
-            if (x >= 0) ok = 1;
-            else {
-                const philox_out u = philox4x32_10((uint32_t)i, (uint32_t)r, (uint32_t)t, (uint32_t)(t >> 32) ^ 0x534b4c53u,
-                                                   (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
-                const double U = (double)((((uint64_t)u.y << 32) | u.x) >> 11) * 0x1.0p-53;
-                ok = U < exp(x);
-            }
-            if (ok) { E += dE; nacc++; }
-        }
-        flag[buf][tid] = ok;
-        snew[buf][tid] = 1 ^ (int)((sp[tid * nw + (i >> 5)] >> (i & 31)) & 1u);
-    };
-    const long long nsteps = (long long)P.nsweeps * N;
-    if (tid == 0 && nsteps > 0) fetch_row(0, 0);
-    if (tid == 0 && nsteps > 1) fetch_row(1 < N ? 1 : 0, 1);
-    if (tid < RPC && nsteps > 0) decide(0, P.sweep0, lf[(size_t)tid * N], 0);
-    __syncthreads();
-    long long g = 0;
-    for (int sw = 0; sw < P.nsweeps; sw++) {
-        for (int i = 0; i < N; i++, g++) {
-            const int cur = (int)(g & 1), nxt = cur ^ 1;
-            const int in = i + 1 < N ? i + 1 : 0;                                   // the site of step g + 1
-            // buffer (g+2) % 3 was last read in step g-1, which ended with the barrier: request the row of step g+2 now
-            // (one site ahead is not enough: a step is shorter than the latency of a 32 KB row from HBM/L2)
-            if (tid == 0 && g + 2 < nsteps) fetch_row(i + 2 < N ? i + 2 : i + 2 - N, (int)((g + 2) % NBUF));
-            const int rb = (int)(g % NBUF);
-            {   // every thread observes the arrival of row i
-                const uint32_t b = sk_smem_u32(&bar[rb]), parity = (uint32_t)((g / NBUF) & 1);
-                asm volatile("{\n\t.reg .pred p;\nW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra W_%=;\n\t}" :: "r"(b), "r"(parity) : "memory");
-            }
-            const double *Ji = Jb + (size_t)rb * N;
-            if (tid < 32) {
-                if (tid < RPC) {
-                    // the deciding lane of replica tid: flip spin i if it was accepted, bring lf[in] up to date with row i,
-                    // decide site `in` for the next step
-                    const int ok = flag[cur][tid];
-                    if (ok) sp[tid * nw + (i >> 5)] ^= 1u << (i & 31);
-                    if (g + 1 < nsteps) {
-                        // the lane owns the whole 16-byte pair that holds `in` (the bulk update skips that pair, so its
-                        // double2 path stays vectorised): row i applied to both elements, site i itself taking -v
-                        double v = lf[(size_t)tid * N + in];
-                        if (ok) {
-                            const int mate = in ^ 1;
-                            const uint32_t w = sp[tid * nw + (in >> 5)];
-                            if (in != i) {
-                                const double a = 4 * Ji[in];
-                                v = __dadd_rn(v, (snew[cur][tid] ^ (int)((w >> (in & 31)) & 1u)) ? -a : a);
-                                lf[(size_t)tid * N + in] = v;
-                            } else { v = -v; lf[(size_t)tid * N + in] = v; }
-                            double vm = lf[(size_t)tid * N + mate];
-                            if (mate != i) {
-                                const double a = 4 * Ji[mate];
-                                vm = __dadd_rn(vm, (snew[cur][tid] ^ (int)((w >> (mate & 31)) & 1u)) ? -a : a);
-                            } else vm = -vm;
-                            lf[(size_t)tid * N + mate] = vm;
-                        }
-                        decide(in, P.sweep0 + (uint64_t)(i + 1 < N ? sw : sw + 1), v, nxt);
-                    }
-                }
-            } else {
-                bool any = false;
-#pragma unroll
-                for (int rp = 0; rp < RPC; rp++) any |= flag[cur][rp] != 0;
-                if (any) {                                     // update_cache!, SK.jl:252-265, for the accepted replicas
-                    const double2 *Ji2 = reinterpret_cast<const double2 *>(Ji);
-                    for (int j2 = tid - 32; j2 < N / 2; j2 += nt - 32) {
-                        const double2 Jv = Ji2[j2];
-                        const double a0 = 4 * Jv.x, a1 = 4 * Jv.y;
-                        const int j = 2 * j2;
-                        if (j2 == (in >> 1) && g + 1 < nsteps) continue;   // the deciders' pair (the last step has no decider)
-#pragma unroll
-                        for (int rp = 0; rp < RPC; rp++) {
-                            if (!flag[cur][rp]) continue;
-                            // (bit i of the word may already be flipped by the decider: it is not used, site i takes -v)
-                            const uint32_t w = sp[rp * nw + (j >> 5)] >> (j & 31);
-                            const int s0 = snew[cur][rp] ^ (int)(w & 1u), s1 = snew[cur][rp] ^ (int)((w >> 1) & 1u);
-                            double2 *p = reinterpret_cast<double2 *>(&lf[(size_t)rp * N + j]);
-                            double2 v = *p;
-                            v.x = j == i ? -v.x : __dadd_rn(v.x, s0 ? -a0 : a0);
-                            v.y = j + 1 == i ? -v.y : __dadd_rn(v.y, s1 ? -a1 : a1);
-                            *p = v;
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-    for (int rp = 0; rp < RPC; rp++) {
-        const int64_t r = rbase + rp;
-        if (r >= P.R) continue;
-        for (int j = tid; j < N; j += nt) P.lf[r * N + j] = lf[(size_t)rp * N + j];
-        for (int c = tid; c < (int)P.nchunks; c += nt) {
-            const uint64_t lo = sp[rp * nw + 2 * c], hi = 2 * c + 1 < nw ? sp[rp * nw + 2 * c + 1] : 0u;
-            P.chunks[r * P.nchunks + c] = lo | (hi << 32);
-        }
-    }
-    if (tid < RPC && rbase + tid < P.R) { P.E[rbase + tid] = E; P.acc[rbase + tid] = nacc; }
-}
-
 // Register-resident variant (N even, N <= 4096): the local fields of the block's RPC replicas live in the REGISTERS of
 // sixteen update warps (thread b owns the site pairs b, b+512, ... of every replica), so a site step moves no field
 // through shared memory at all — only the 8N-byte coupling row is read from it.
@@ -648,7 +499,7 @@ __global__ void __launch_bounds__(576, 1) k_sk_lockstep_reg(sk_ls_params P)
     __shared__ __align__(8) uint64_t bar[NBUF];
     const uint32_t rowbytes = (uint32_t)N * 8u;
     const int64_t rbase = (int64_t)blockIdx.x * RPC;
-    const bool bulk = warp >= 1 && warp <= 16, decider = warp == 0 && lane < RPC, aux = warp == 17;
+    const bool bulk = warp >= 1 && warp <= 16, decider = warp == 0 && lane < RPC;   // warp 17: rows and draws
     if (tid == 0) {
         for (int b = 0; b < NBUF; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(sk_smem_u32(&bar[b])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -994,15 +845,11 @@ rrrmc_status_t sk_dense_sweeps(rrrmc_state *s, const double *beta, uint64_t seed
     const size_t smem_tma = smem + 2 * (size_t)N * 8;
     const char *skv = getenv("RRRMC_SK_VARIANT");
     const bool tma = N % 2 == 0 && smem_tma <= (size_t)225 * 1024 && !(skv && atoi(skv) == 1);
-    const size_t smem_pipe = smem + 3 * (size_t)N * 8;
-    const int variant = skv ? atoi(skv) : 0;   // RRRMC_SK_VARIANT: 0 best available, 1 plain loads, 2 TMA rows, 3 TMA rows + site pipeline
-    const bool pipe = tma && smem_pipe <= (size_t)226 * 1024 && variant != 2;
+    const int variant = skv ? atoi(skv) : 0;   // RRRMC_SK_VARIANT: 0 best available, 1 plain loads, 2 TMA rows + fields in shared memory
     // fields in registers (N even, <= 4096): the default; one block per RPC replicas, RPC no larger than the SM count asks for
     const bool reg = N % 2 == 0 && N >= 2 && N <= 4096 && variant == 0;
 #define LST(RP) do { RR_CUDA(cudaFuncSetAttribute(k_sk_lockstep_tma<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma)); \
                      k_sk_lockstep_tma<RP><<<grid, 512, smem_tma, ctx->stream>>>(P); } while (0)
-#define LSP(RP) do { RR_CUDA(cudaFuncSetAttribute(k_sk_lockstep_pipe<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe)); \
-                     k_sk_lockstep_pipe<RP><<<grid, 544, smem_pipe, ctx->stream>>>(P); } while (0)
 #define LSR(RP) do { const size_t sm = 3 * (size_t)N * 8 + (size_t)RP * nw * 4; \
                      RR_CUDA(cudaFuncSetAttribute(k_sk_lockstep_reg<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
                      k_sk_lockstep_reg<RP><<<div_up(s->R, RP), 576, sm, ctx->stream>>>(P); } while (0)
@@ -1010,13 +857,11 @@ rrrmc_status_t sk_dense_sweeps(rrrmc_state *s, const double *beta, uint64_t seed
         const int nsm = ctx->sm_count > 0 ? ctx->sm_count : 148;
         if (s->R > 2 * (int64_t)nsm) LSR(4); else if (s->R > nsm) LSR(2); else LSR(1);
     }
-    else if (pipe) { if (rpc == 4) LSP(4); else if (rpc == 2) LSP(2); else LSP(1); }
     else if (tma) { if (rpc == 4) LST(4); else if (rpc == 2) LST(2); else LST(1); }
     else if (rpc == 4) LS(4); else if (rpc == 2) LS(2); else LS(1);
 #undef LSR
 #undef LS
 #undef LST
-#undef LSP
     ctx->launches++;
     RR_CUDA(cudaGetLastError());
     s->ms_valid = false; s->chain_valid = true; s->chain_fields_valid = false; s->energy_valid = false;

@@ -67,7 +67,7 @@ if "c4" in which:
         peak = float(_json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         pass
-    for variant, kname in (("0", "k_sk_lockstep_reg<4>"), ("3", "k_sk_lockstep_pipe<4>"), ("2", "k_sk_lockstep_tma<4>"), ("1", "k_sk_lockstep<4>")):
+    for variant, kname in (("0", "k_sk_lockstep_reg<4>"), ("2", "k_sk_lockstep_tma<4>"), ("1", "k_sk_lockstep<4>")):
         os.environ["RRRMC_SK_VARIANT"] = variant
         rb.sk_fields_init(X, C0, tensor_cores=True)
         rb.sk_metropolis_sweeps(X, beta, 2, seed=1)
