@@ -86,6 +86,39 @@ __device__ __forceinline__ void sk_update_part(const gview &c, int skind, int k,
     } else {
         const uint8_t *Ji = c.Jb + (int64_t)i * c.Nk;
         int32_t *lf = c.lfi + cur, *lfl = c.lfi + last;
+        if ((c.Nk & 3) == 0) {
+            // four sites per lane and step: one 4-byte coupling load, one 16-byte field load, four spin bits from one word
+            // (off + j is a multiple of 4: the bits never straddle a chunk), two 16-byte stores. Integer arithmetic: the
+            // same values as the scalar loop below in any order.
+            constexpr int UV = 2;
+            for (int j0 = 4 * lane; j0 < c.Nk; j0 += 4 * nl * UV) {
+                uchar4 Jv[UV]; int4 lv[UV]; uint32_t sb[UV];
+#pragma unroll
+                for (int u = 0; u < UV; u++) {
+                    const int j = j0 + u * 4 * nl;
+                    if (j < c.Nk) {
+                        Jv[u] = *reinterpret_cast<const uchar4 *>(Ji + j);
+                        lv[u] = *reinterpret_cast<const int4 *>(lf + j);
+                        const int64_t b = off + j;
+                        sb[u] = (uint32_t)(c.s[b >> 6] >> (b & 63));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UV; u++) {
+                    const int j = j0 + u * 4 * nl;
+                    if (j < c.Nk) {
+                        *reinterpret_cast<int4 *>(lfl + j) = lv[u];
+                        int4 nv;
+                        nv.x = lv[u].x + 8 * (si ^ (int)(sb[u] & 1u) ^ (int)Jv[u].x) - 4;
+                        nv.y = lv[u].y + 8 * (si ^ (int)((sb[u] >> 1) & 1u) ^ (int)Jv[u].y) - 4;
+                        nv.z = lv[u].z + 8 * (si ^ (int)((sb[u] >> 2) & 1u) ^ (int)Jv[u].z) - 4;
+                        nv.w = lv[u].w + 8 * (si ^ (int)((sb[u] >> 3) & 1u) ^ (int)Jv[u].w) - 4;
+                        *reinterpret_cast<int4 *>(lf + j) = nv;
+                    }
+                }
+            }
+            return;
+        }
         for (int j0 = lane; j0 < c.Nk; j0 += nl * UB) {
             int Jv[UB], lv[UB], sv[UB];
 #pragma unroll
