@@ -66,6 +66,36 @@ __device__ __forceinline__ void sk_update_part(const gview &c, int skind, int k,
     if (skind == RRRMC_SK_F64) {
         const double *Ji = c.Jd + (int64_t)i * c.Nk;
         double *lf = c.lfd + cur, *lfl = c.lfd + last;
+        if ((c.Nk & 1) == 0) {
+            // two sites per lane and step: 16-byte coupling and field loads, two spin bits from one chunk (off + j is even:
+            // the pair never straddles a chunk), 16-byte stores. Per element the same two roundings as the scalar loop.
+            constexpr int UV = 4;
+            for (int j0 = 2 * lane; j0 < c.Nk; j0 += 2 * nl * UV) {
+                double2 Jv[UV], lv[UV]; uint32_t sb[UV];
+#pragma unroll
+                for (int u = 0; u < UV; u++) {
+                    const int j = j0 + u * 2 * nl;
+                    if (j < c.Nk) {
+                        Jv[u] = *reinterpret_cast<const double2 *>(Ji + j);
+                        lv[u] = *reinterpret_cast<const double2 *>(lf + j);
+                        const int64_t b = off + j;
+                        sb[u] = (uint32_t)(c.s[b >> 6] >> (b & 63));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UV; u++) {
+                    const int j = j0 + u * 2 * nl;
+                    if (j < c.Nk) {
+                        *reinterpret_cast<double2 *>(lfl + j) = lv[u];
+                        double2 nv;
+                        nv.x = __dadd_rn(lv[u].x, 4 * __dmul_rn((double)(1 - 2 * (si ^ (int)(sb[u] & 1u))), Jv[u].x));
+                        nv.y = __dadd_rn(lv[u].y, 4 * __dmul_rn((double)(1 - 2 * (si ^ (int)((sb[u] >> 1) & 1u))), Jv[u].y));
+                        *reinterpret_cast<double2 *>(lf + j) = nv;
+                    }
+                }
+            }
+            return;
+        }
         for (int j0 = lane; j0 < c.Nk; j0 += nl * UB) {
             double Jv[UB], lv[UB]; int sv[UB];
 #pragma unroll
